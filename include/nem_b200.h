@@ -1,0 +1,168 @@
+/*
+ * nem_b200.h -- public C ABI of libnem_b200.so, the B200-native NEM partitioning engine.
+ *
+ * Plain C types only (no torch, no C++): this is the boundary a maintainer of
+ * labgem/pangenomeNEM binds instead of the reference's ppanggolin/NEM C sources.
+ * File:line citations refer to the reference tree (ppanggolin/...).
+ *
+ * Three layers:
+ *   1. nem()            drop-in for the reference's only exported symbol (NEM/nem_exe.h:23-35,
+ *                       NEM/nem_exe.c:239-704), what NEM/nem.pyx wraps and
+ *                       ppanggolin.py:1814-1826 calls.
+ *   2. nem_b200_ex()    same, plus the knobs nem() hard-codes (site update, tie rule, E-step
+ *                       sweeps, device) -- the reference only reaches them through its historic
+ *                       CLI (NEM/nem_hlp.c:109-289).
+ *   3. nemb_*           in-memory API: load a pangenome once (packed or dense host buffers),
+ *                       run fits, read posteriors -- replaces the text-file round trip of
+ *                       ppanggolin.py:821-930 + 1886-1972 for callers that can link it, and is
+ *                       what the parity tests and bench.py drive.  Stage entry points expose
+ *                       each kernel of the path for per-function parity tests.
+ *
+ * The library has NO CPU fallback: without a CUDA device every compute entry point fails
+ * with NEMB_E_CUDA and nem() returns EXIT_E_SYSTEM (5).
+ */
+#ifndef NEM_B200_H
+#define NEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------
+ * 1. drop-in entry point  -- replaces NEM/nem_exe.c:239-251 (prototype NEM/nem_exe.h:23-35)
+ * Return value: the reference's ExitET (NEM/lib_io.h:22-34, mapping nem_exe.c:637-703):
+ *   0 OK, 1 W_RESULT (empty class, no output files), 2 E_ARGS, 3 E_FILE, 4 E_MEMORY,
+ *   5 E_SYSTEM (no usable CUDA device), 6 E_BUG.
+ * Inputs  <Fname>.str .dat .nei(type S) .m(init_mode 2); outputs <Fname>.uf|.cf, .mf and with
+ * dolog .log and .stderr (nem_exe.c:272-282, 437-461, 1596-1781).
+ * ------------------------------------------------------------------------------------- */
+int nem(const char *Fname, const int nk, const char *algo, const float beta,
+        const char *convergence, const float convergence_th, const char *format,
+        const int it_max, const int dolog, const char *model_family, const char *proportion,
+        const char *dispersion, const int init_mode);
+
+/* knobs the reference fixes inside nem(): NemPara.SiteUpdate / TieRule / NbEIters / Seed
+ * (nem_exe.c:351-361, nem_typ.h:330-341).  Zero-initialise for the reference's behaviour. */
+typedef struct {
+    int32_t update;      /* 0 = seq (UPDATE_SEQ, reference default), 1 = para (UPDATE_PARA) */
+    int32_t sweep_impl;  /* seq+ncem only: 0 auto, 1 level-scheduled, 2 speculative fixed point */
+    int32_t device;      /* CUDA ordinal, -1 = env NEM_B200_DEVICE or current device */
+    int32_t n_random_inits; /* init_mode 1: number of random starts, 0 = 50 (nem_typ.h:94) */
+    int64_t seed;        /* init_mode 1 RNG seed, 0 = 42 (the reference uses time(NULL)) */
+    int32_t reserved[8];
+} nem_b200_extra;
+
+int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float beta,
+                const char *convergence, const float convergence_th, const char *format,
+                const int it_max, const int dolog, const char *model_family,
+                const char *proportion, const char *dispersion, const int init_mode,
+                const nem_b200_extra *extra);
+
+/* ---------------------------------------------------------------------------------------
+ * 3. in-memory API
+ * ------------------------------------------------------------------------------------- */
+enum { NEMB_OK = 0, NEMB_W_EMPTYCLASS = 1, NEMB_E_ARG = 2, NEMB_E_FILE = 3, NEMB_E_MEMORY = 4,
+       NEMB_E_CUDA = 5, NEMB_E_BUG = 6 };
+
+enum { NEMB_ALGO_NEM = 0, NEMB_ALGO_NCEM = 1 };                 /* nem_typ.h:120-126 */
+enum { NEMB_UPDATE_SEQ = 0, NEMB_UPDATE_PARA = 1 };             /* nem_typ.h:256-261 */
+enum { NEMB_CONV_NONE = 0, NEMB_CONV_CLAS = 1, NEMB_CONV_CRIT = 2 }; /* nem_typ.h:272-278 */
+enum { NEMB_PROP_EQUAL = 0, NEMB_PROP_K = 1 };                  /* nem_typ.h:200-205 */
+enum { NEMB_DISP___ = 0, NEMB_DISP_K_ = 1, NEMB_DISP__D = 2, NEMB_DISP_KD = 3 }; /* :191-198 */
+enum { NEMB_SWEEP_AUTO = 0, NEMB_SWEEP_LEVEL = 1, NEMB_SWEEP_SPEC = 2 };
+
+typedef struct nemb_handle nemb_handle;
+
+typedef struct {
+    int32_t k;            /* number of classes, 1..16 */
+    int32_t algo, update, conv, prop, disp;
+    int32_t it_max;
+    int32_t param_fixed;  /* .m flag 2: M-step skipped (nem_alg.c:1806) */
+    int32_t dolog;        /* evaluate the criteria before/after every sweep (nem_alg.c:2361,2398) */
+    int32_t sweep_impl;
+    int32_t profile;      /* 1: time every stage with CUDA events (adds event overhead) */
+    float   beta, conv_thr;
+    int32_t reserved[8];
+} nemb_options;
+
+typedef struct {
+    int32_t status;       /* NEMB_OK or NEMB_W_EMPTYCLASS */
+    int32_t iters;        /* EM iterations executed (nem_alg.c:1842) */
+    int32_t converged;
+    int32_t empty_class;  /* 1-based, 0 = none */
+    double  U, D, L, M, Z, G;      /* nem_alg.c:2702-2751 */
+    int64_t n_allnul;     /* families whose every class has zero density (last sweep) */
+    int64_t n_ties;       /* ncem: exact arg-max ties in the last sweep */
+    int64_t fixup_rounds; /* speculative sweep: fix-up rounds summed over all sweeps */
+    int64_t kernel_launches;   /* kernels this fit enqueued */
+    float   fit_ms;       /* device time of the whole fit, CUDA events on the engine's stream */
+    float   ms_density, ms_sweep, ms_mstep, ms_criteria;  /* profile=1 only */
+    int32_t n_density, n_sweep, n_mstep, n_criteria;      /* launches behind those sums */
+} nemb_result;
+
+/* Per-iteration trace for the .log writer (nem_alg.c:1995-2052, 2620-2646). */
+typedef void (*nemb_iter_cb)(void *user, int iter, const double crit_before[6],
+                             const double crit_after[6], const float *prop, const float *center,
+                             const float *disp, const float *nk);
+
+int  nemb_create(nemb_handle **out, int device);
+void nemb_destroy(nemb_handle *h);
+const char *nemb_last_error(const nemb_handle *h);
+int  nemb_set_stream(nemb_handle *h, void *cuda_stream);   /* default: an own non-blocking stream */
+
+/* Load one pangenome; all pointers are HOST buffers, copied to HBM inside the call.
+ * x_packed: uint32[n][words_per_row], genome d = bit d%32 of word d/32, padding bits zero.
+ * row_ptr/col/wgt: CSR of the neighbour graph (NULL row_ptr = non-spatial, beta forced to 0,
+ * nem_exe.c:570-574); order inside a row = order in the .nei file. */
+int nemb_load_packed(nemb_handle *h, int n, int d, int words_per_row, const uint32_t *x_packed,
+                     const int32_t *row_ptr, const int32_t *col, const float *wgt);
+int nemb_load_dense_u8(nemb_handle *h, int n, int d, const uint8_t *x, const int32_t *row_ptr,
+                       const int32_t *col, const float *wgt);
+/* X already resident in HBM (device pointer, packed layout as above); CSR still from host. */
+int nemb_load_packed_device(nemb_handle *h, int n, int d, int words_per_row,
+                            const uint32_t *x_packed_dev, const int32_t *row_ptr,
+                            const int32_t *col, const float *wgt);
+
+/* One fit = ClassifyByNemOneBeta's INIT_PARAM_FILE branch (nem_alg.c:1151-1169): blind sweep,
+ * beta sweep, EM loop, final criteria.  theta (prop[K], center[K*D], disp[K*D], float32, host)
+ * is the starting point on entry and the last M-step's estimate on return. */
+int nemb_fit(nemb_handle *h, const nemb_options *opt, float *prop, float *center, float *disp,
+             nemb_result *res);
+int nemb_fit_logged(nemb_handle *h, const nemb_options *opt, float *prop, float *center,
+                    float *disp, nemb_result *res, nemb_iter_cb cb, void *user);
+/* init_mode 1 (RandNemAlgo, nem_alg.c:1574-1742): n_starts random starts, best by criterion. */
+int nemb_fit_random(nemb_handle *h, const nemb_options *opt, int n_starts, int64_t seed,
+                    float *prop, float *center, float *disp, nemb_result *res);
+
+int nemb_get_posteriors(nemb_handle *h, float *t_out /*[n*k]*/);
+int nemb_get_labels(nemb_handle *h, int32_t *label_out /*[n]*/);   /* MAP, first maximum */
+
+/* loader products, for bit-exact packing / indexing tests */
+int nemb_get_dims(const nemb_handle *h, int *n, int *d, int *words_per_row, int *nwt,
+                  int *depth, int *nnz);
+int nemb_get_packed(nemb_handle *h, uint32_t *out /*[n*wpr]*/);
+int nemb_get_transposed(nemb_handle *h, uint32_t *out /*[d*nwt]*/);
+int nemb_get_levels(nemb_handle *h, int32_t *level_of_site /*[n]*/);
+
+/* stage entry points (each runs exactly the kernels nemb_fit uses for that step) */
+int nemb_stage_density(nemb_handle *h, int k, const float *prop, const float *center,
+                       const float *disp, int force_general, double *logpf_out /*[n*k]*/,
+                       int32_t *hamming_out /*[n*k] or NULL (popcount path only)*/,
+                       int *used_uniform);
+int nemb_stage_sweep(nemb_handle *h, const nemb_options *opt, const double *logpf /*[n*k]*/,
+                     float beta, float *t_inout /*[n*k]*/, int32_t *label_out /*[n] or NULL*/,
+                     int64_t *fixup_rounds);
+int nemb_stage_mstep(nemb_handle *h, const nemb_options *opt, const float *t /*[n*k]*/,
+                     float *prop, float *center, float *disp, double *nk_out /*[k]*/,
+                     double *skd_out /*[k*d]*/, int *empty_class);
+int nemb_stage_criteria(nemb_handle *h, const nemb_options *opt, const double *logpf,
+                        const float *t, float beta, double *crit6 /*U D L M Z G*/);
+
+const char *nemb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,263 @@
+"""ctypes binding of libnem_b200.so (include/nem_b200.h) -- the host-side mirror used by the
+tests, bench.py and the Python ``nem`` shim.  There is deliberately no fallback: if the CUDA
+library is missing or no GPU is visible, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libnem_b200.so")
+
+ALGO = {"nem": 0, "ncem": 1}
+UPDATE = {"seq": 0, "para": 1}
+CONV = {"none": 0, "clas": 1, "crit": 2}
+PROP = {"p_": 0, "pk": 1}
+DISP = {"s__": 0, "sk_": 1, "s_d": 2, "skd": 3}
+SWEEP = {"auto": 0, "level": 1, "spec": 2}
+STATUS = {0: "OK", 1: "W_EMPTYCLASS", 2: "E_ARG", 3: "E_FILE", 4: "E_MEMORY", 5: "E_CUDA", 6: "E_BUG"}
+
+
+class NemError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"nem_b200 error {code} ({STATUS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class Options(C.Structure):
+    _fields_ = [("k", C.c_int32), ("algo", C.c_int32), ("update", C.c_int32), ("conv", C.c_int32),
+                ("prop", C.c_int32), ("disp", C.c_int32), ("it_max", C.c_int32),
+                ("param_fixed", C.c_int32), ("dolog", C.c_int32), ("sweep_impl", C.c_int32),
+                ("profile", C.c_int32), ("beta", C.c_float), ("conv_thr", C.c_float),
+                ("reserved", C.c_int32 * 8)]
+
+
+class Result(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iters", C.c_int32), ("converged", C.c_int32),
+                ("empty_class", C.c_int32),
+                ("U", C.c_double), ("D", C.c_double), ("L", C.c_double), ("M", C.c_double),
+                ("Z", C.c_double), ("G", C.c_double),
+                ("n_allnul", C.c_int64), ("n_ties", C.c_int64), ("fixup_rounds", C.c_int64),
+                ("kernel_launches", C.c_int64), ("fit_ms", C.c_float),
+                ("ms_density", C.c_float), ("ms_sweep", C.c_float), ("ms_mstep", C.c_float),
+                ("ms_criteria", C.c_float),
+                ("n_density", C.c_int32), ("n_sweep", C.c_int32), ("n_mstep", C.c_int32),
+                ("n_criteria", C.c_int32)]
+
+
+class Extra(C.Structure):
+    _fields_ = [("update", C.c_int32), ("sweep_impl", C.c_int32), ("device", C.c_int32),
+                ("n_random_inits", C.c_int32), ("seed", C.c_int64), ("reserved", C.c_int32 * 8)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load the in-tree CUDA library; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m pangenomenem_b200.build` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.nemb_last_error.restype = C.c_char_p
+        lib.nemb_version.restype = C.c_char_p
+        sig = [C.c_char_p, C.c_int, C.c_char_p, C.c_float, C.c_char_p, C.c_float, C.c_char_p,
+               C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        if hasattr(lib, "nem"):
+            lib.nem.argtypes = sig
+            lib.nem_b200_ex.argtypes = sig + [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def make_options(k=3, algo="ncem", update="seq", conv="clas", conv_thr=1e-8, prop="pk",
+                 disp="sk_", it_max=100, beta=0.5, param_fixed=False, dolog=False,
+                 sweep_impl="auto", profile=False) -> Options:
+    return Options(k, ALGO[algo], UPDATE[update], CONV[conv], PROP[prop], DISP[disp], int(it_max),
+                   int(param_fixed), int(dolog), SWEEP[sweep_impl], int(profile), float(beta),
+                   float(conv_thr))
+
+
+@dataclass
+class Fit:
+    status: int
+    iters: int
+    converged: bool
+    prop: np.ndarray
+    center: np.ndarray
+    disp: np.ndarray
+    crit: dict
+    n_allnul: int
+    n_ties: int
+    fixup_rounds: int
+    kernel_launches: int
+    fit_ms: float
+    stage_ms: dict = field(default_factory=dict)
+    stage_launches: dict = field(default_factory=dict)
+    empty_class: int = 0
+
+
+class Engine:
+    """One CUDA context + one resident pangenome (nemb_handle)."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.nemb_create(C.byref(self.h), int(device))
+        if rc != 0:
+            raise NemError(rc, "nemb_create failed (no CUDA device?)")
+        self.n = self.d = 0
+
+    def close(self):
+        if self.h:
+            self.lib.nemb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, ok=(0,)):
+        if rc not in ok:
+            raise NemError(rc, self.lib.nemb_last_error(self.h).decode())
+        return rc
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.nemb_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    # ---- loaders
+    def _graph(self, row_ptr, col, wgt):
+        if row_ptr is None:
+            return None, None, None
+        return (np.ascontiguousarray(row_ptr, dtype=np.int32),
+                np.ascontiguousarray(col, dtype=np.int32),
+                np.ascontiguousarray(wgt, dtype=np.float32))
+
+    def load_dense(self, x, row_ptr=None, col=None, wgt=None):
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        rp, cl, wg = self._graph(row_ptr, col, wgt)
+        self.n, self.d = x.shape
+        self._check(self.lib.nemb_load_dense_u8(self.h, self.n, self.d, _p(x), _p(rp), _p(cl), _p(wg)))
+
+    def load_packed(self, xp, d, row_ptr=None, col=None, wgt=None):
+        xp = np.ascontiguousarray(xp, dtype=np.uint32)
+        rp, cl, wg = self._graph(row_ptr, col, wgt)
+        self.n, self.d = xp.shape[0], int(d)
+        self._check(self.lib.nemb_load_packed(self.h, self.n, self.d, xp.shape[1], _p(xp), _p(rp),
+                                              _p(cl), _p(wg)))
+
+    def load_packed_device(self, dev_ptr: int, n: int, d: int, wpr: int, row_ptr=None, col=None,
+                           wgt=None):
+        rp, cl, wg = self._graph(row_ptr, col, wgt)
+        self.n, self.d = int(n), int(d)
+        self._check(self.lib.nemb_load_packed_device(self.h, self.n, self.d, int(wpr),
+                                                     C.c_void_p(dev_ptr), _p(rp), _p(cl), _p(wg)))
+
+    def dims(self):
+        v = [C.c_int() for _ in range(6)]
+        self._check(self.lib.nemb_get_dims(self.h, *[C.byref(a) for a in v]))
+        return dict(zip(("n", "d", "wpr", "nwt", "depth", "nnz"), [a.value for a in v]))
+
+    def packed(self):
+        dm = self.dims()
+        out = np.zeros((dm["n"], dm["wpr"]), dtype=np.uint32)
+        self._check(self.lib.nemb_get_packed(self.h, _p(out)))
+        return out
+
+    def transposed(self):
+        dm = self.dims()
+        out = np.zeros((dm["d"], dm["nwt"]), dtype=np.uint32)
+        self._check(self.lib.nemb_get_transposed(self.h, _p(out)))
+        return out
+
+    def levels(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        self._check(self.lib.nemb_get_levels(self.h, _p(out)))
+        return out
+
+    # ---- fit
+    def fit(self, prop0, center0, disp0, n_random_starts=0, seed=42, **kw) -> Fit:
+        """theta0 = (prop0[K], center0[K,D], disp0[K,D]); kw = make_options() fields."""
+        o = make_options(**kw)
+        prop, center, disp = _f32(prop0).copy(), _f32(center0).copy(), _f32(disp0).copy()
+        r = Result()
+        if n_random_starts:
+            rc = self.lib.nemb_fit_random(self.h, C.byref(o), int(n_random_starts), C.c_int64(seed),
+                                          _p(prop), _p(center), _p(disp), C.byref(r))
+        else:
+            rc = self.lib.nemb_fit(self.h, C.byref(o), _p(prop), _p(center), _p(disp), C.byref(r))
+        self._check(rc, ok=(0, 1))
+        self.k = o.k
+        return Fit(r.status, r.iters, bool(r.converged), prop, center.reshape(o.k, self.d),
+                   disp.reshape(o.k, self.d), dict(U=r.U, D=r.D, L=r.L, M=r.M, Z=r.Z, G=r.G),
+                   r.n_allnul, r.n_ties, r.fixup_rounds, r.kernel_launches, r.fit_ms,
+                   dict(density=r.ms_density, sweep=r.ms_sweep, mstep=r.ms_mstep,
+                        criteria=r.ms_criteria),
+                   dict(density=r.n_density, sweep=r.n_sweep, mstep=r.n_mstep,
+                        criteria=r.n_criteria), r.empty_class)
+
+    def posteriors(self, k=None):
+        k = k or self.k
+        out = np.zeros((self.n, k), dtype=np.float32)
+        self._check(self.lib.nemb_get_posteriors(self.h, _p(out)))
+        return out
+
+    def labels(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        self._check(self.lib.nemb_get_labels(self.h, _p(out)))
+        return out
+
+    # ---- stages
+    def stage_density(self, prop, center, disp, k=3, force_general=False, want_hamming=False):
+        prop, center, disp = _f32(prop), _f32(center), _f32(disp)
+        out = np.zeros((self.n, k), dtype=np.float64)
+        ham = np.full((self.n, k), -1, dtype=np.int32) if want_hamming else None
+        used = C.c_int()
+        self._check(self.lib.nemb_stage_density(self.h, k, _p(prop), _p(center), _p(disp),
+                                                int(force_general), _p(out), _p(ham), C.byref(used)))
+        self.k = k
+        return out, ham, bool(used.value)
+
+    def stage_sweep(self, logpf, beta, t, **kw):
+        o = make_options(**kw)
+        t = _f32(t).copy()
+        lab = np.zeros(self.n, dtype=np.int32)
+        rounds = C.c_int64()
+        self._check(self.lib.nemb_stage_sweep(self.h, C.byref(o),
+                                              _p(np.ascontiguousarray(logpf, dtype=np.float64)),
+                                              C.c_float(beta), _p(t), _p(lab), C.byref(rounds)))
+        self.k = o.k
+        return t, lab, rounds.value
+
+    def stage_mstep(self, t, prop0, center0, disp0, **kw):
+        o = make_options(**kw)
+        prop, center, disp = _f32(prop0).copy(), _f32(center0).copy(), _f32(disp0).copy()
+        nk = np.zeros(o.k); skd = np.zeros((o.k, self.d)); empty = C.c_int()
+        self._check(self.lib.nemb_stage_mstep(self.h, C.byref(o), _p(_f32(t)), _p(prop), _p(center),
+                                              _p(disp), _p(nk), _p(skd), C.byref(empty)))
+        self.k = o.k
+        return empty.value, prop, center.reshape(o.k, self.d), disp.reshape(o.k, self.d), nk, skd
+
+    def stage_criteria(self, logpf, t, beta, **kw):
+        o = make_options(**kw)
+        out = np.zeros(6)
+        self._check(self.lib.nemb_stage_criteria(self.h, C.byref(o),
+                                                 _p(np.ascontiguousarray(logpf, dtype=np.float64)),
+                                                 _p(_f32(t)), C.c_float(beta), _p(out)))
+        return dict(zip("UDLMZG", out))

@@ -1,0 +1,113 @@
+/*
+ * nem_device.h -- internal thin C-ABI layer between the C host (nem_fit.c, nem_io.c,
+ * nem_api.c) and the CUDA kernels (nem_kernels.cu).  Every nemk_* function enqueues work on
+ * the given stream and returns; all pointers are DEVICE pointers.  Plain C types only.
+ */
+#ifndef NEM_DEVICE_H
+#define NEM_DEVICE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEMB_MAX_K 16
+
+/* Per-class coefficients derived from theta, read by the density kernels.
+ * uniform path: logpf = forb ? (H ? -inf : lp) : lp - (a*H + base)
+ * general path: logpf = nul ? -inf : lp - (base + sum_{d: x=1} delta[k][d]) */
+typedef struct {
+    double lp[NEMB_MAX_K];
+    double a[NEMB_MAX_K];
+    double base[NEMB_MAX_K];
+    int32_t forb[NEMB_MAX_K];   /* eps_k <= EPSILON: any mismatch => zero density */
+    int32_t uniform_ok;         /* 1 when every class is popcount-eligible */
+    int32_t empty_class;        /* 1-based index of an empty class (M-step) or 0 */
+    int32_t pad[2];
+} nemk_coef;
+
+/* Device scalars of one sweep / one iteration (host reads them back in one copy). */
+typedef struct {
+    int32_t changed;     /* ncem: number of labels != previous iteration's */
+    int32_t nfix;        /* speculative sweep: number of fix-up rounds the sweep needed */
+    int32_t allnul;      /* rows whose every class has zero density */
+    int32_t ties;        /* ncem rows whose arg max was an exact tie */
+    float   maxdiff;     /* nem: max |t - t_old| */
+    int32_t pad[3];
+} nemk_counters;
+
+typedef void *nemk_stream;
+
+/* ---- loader */
+void nemk_pack_u8(nemk_stream s, const uint8_t *x, int n, int d, int wpr, uint32_t *out);
+void nemk_transpose_bits(nemk_stream s, const uint32_t *x, int n, int wpr, int d, int nwt,
+                         uint32_t *xt);
+
+/* ---- theta -> tables */
+void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const float *prop,
+                       const float *center, const float *disp, nemk_coef *coef,
+                       uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
+                       uint32_t *mask_f1, double *delta);
+
+/* ---- E-step density */
+void nemk_density_uniform(nemk_stream s, int k, const uint32_t *x, int n, int wpr,
+                          const nemk_coef *coef, const uint32_t *mask_xor,
+                          const uint32_t *mask_valid, double *logpf, int32_t *hamming);
+void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d, int wpr,
+                          const nemk_coef *coef, const uint32_t *mask_f0, const uint32_t *mask_f1,
+                          const double *delta, double *logpf);
+
+/* ---- E-step sweeps.  label 255 = unlabelled (the reference's calloc'd ClassifM row).
+ * `skip` (nullable) points at a device flag; non-zero => the kernel returns at once (an empty
+ * class was found by the M-step, the reference does not run the E-step then). */
+void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int n, const double *logpf, const int32_t *row_ptr,
+                            const int32_t *col, const float *wgt, double beta,
+                            const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty, int32_t *wl,
+                            int32_t *wl_count, const int32_t *rrow_ptr, const int32_t *rcol,
+                            nemk_counters *cnt, const int32_t *skip);
+void nemk_sweep_ncem_fixup(nemk_stream s, int k, int n, const double *logpf, const int32_t *row_ptr,
+                           const int32_t *col, const float *wgt, double beta,
+                           const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a,
+                           int32_t *wl_b, int32_t *wl_counts, const int32_t *rrow_ptr,
+                           const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
+void nemk_sweep_ncem_level(nemk_stream s, int k, const double *logpf, const int32_t *row_ptr,
+                           const int32_t *col, const float *wgt, double beta, uint8_t *lab,
+                           const int32_t *sites, const int32_t *level_ptr, int lv_lo, int lv_hi,
+                           int grid_ctas, nemk_counters *cnt, const int32_t *skip);
+void nemk_sweep_nem_jacobi(nemk_stream s, int k, int n, const double *logpf, const int32_t *row_ptr,
+                           const int32_t *col, const float *wgt, double beta, const float *t_in,
+                           float *t_out, nemk_counters *cnt, const int32_t *skip);
+void nemk_sweep_nem_level(nemk_stream s, int k, const double *logpf, const int32_t *row_ptr,
+                          const int32_t *col, const float *wgt, double beta, float *t,
+                          const int32_t *sites, const int32_t *level_ptr, int lv_lo, int lv_hi,
+                          int grid_ctas, nemk_counters *cnt, const int32_t *skip);
+
+/* ---- M-step */
+void nemk_label_masks(nemk_stream s, int k, int n, int nwt, const uint8_t *lab, uint32_t *cm,
+                      int32_t *nk_int);
+void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint32_t *xt, const uint32_t *cm,
+                     int32_t *s_int);
+void nemk_mstep_nem(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x, const float *t,
+                    int rows_per_chunk, double *partial_s, double *partial_n, double *s_dbl,
+                    double *nk_dbl);
+void nemk_mstep_finalize(nemk_stream s, int k, int n, int d, int prop_model, int disp_model,
+                         const int32_t *s_int, const int32_t *nk_int, const double *s_dbl,
+                         const double *nk_dbl, float *prop, float *center, float *disp,
+                         float *iner_scratch, nemk_coef *coef);
+
+/* ---- criteria (U D L M Z G into crit6) */
+void nemk_criteria(nemk_stream s, int k, int n, const double *logpf, const int32_t *row_ptr,
+                   const int32_t *col, const float *wgt, double beta, const uint8_t *lab,
+                   const float *t, double *partials, int nblocks_cap, double *crit6);
+
+/* ---- helpers */
+void nemk_labels_to_t(nemk_stream s, int k, int n, const uint8_t *lab, float *t);
+void nemk_t_to_labels(nemk_stream s, int k, int n, const float *t, uint8_t *lab);
+void nemk_fill_u8(nemk_stream s, uint8_t *p, int v, size_t n);
+int  nemk_last_error(char *buf, int len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

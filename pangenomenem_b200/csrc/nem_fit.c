@@ -1,0 +1,971 @@
+/*
+ * nem_fit.c -- C host of the in-memory API (include/nem_b200.h, layer 3): device buffers, the
+ * loader (CSR, reader lists, sweep level schedule), the EM control flow and the stage entry
+ * points.  All numerics run in the CUDA kernels of nem_kernels.cu through nem_device.h; this
+ * file only sequences them.  No CPU fallback exists: every entry point needs a CUDA device.
+ *
+ * Control flow restated from the reference (root ppanggolin/NEM):
+ *   ClassifyByNemOneBeta, INIT_PARAM_FILE branch   nem_alg.c:1151-1169
+ *   ComputePartitionFromPara                       nem_alg.c:1951-1989
+ *   NemAlgo                                        nem_alg.c:1746-1879
+ *   HasConverged                                   nem_alg.c:2056-2112
+ *   RandNemAlgo / MakeRandomPara / InitPara        nem_alg.c:1574-1742, 1381-1473, 1200-1280
+ */
+#include "nem_b200.h"
+#include "nem_device.h"
+
+#include <cuda_runtime_api.h>
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NEMB_VERSION "nem-b200 0.1 (NEM 1.08-a compatible)"
+#define NARROW_LEVEL 2048   /* levels at most this wide are walked by one CTA */
+#define MAX_LEVEL_GRID 2368 /* 148 SMs x 16 CTAs of 256 threads */
+
+typedef struct { int lo, hi, grid; } sweep_step;
+
+typedef struct {
+    nemk_counters cnt;
+    double crit_before[6];
+    double crit_after[6];
+} iter_status;
+
+enum { ST_DENSITY = 0, ST_SWEEP = 1, ST_MSTEP = 2, ST_CRIT = 3, ST_NB = 4 };
+
+struct nemb_handle {
+    int device;
+    cudaStream_t stream;
+    int own_stream;
+    char err[512];
+    /* problem */
+    int n, d, wpr, nwt, nnz, spatial, symmetric, depth, loaded;
+    uint32_t *d_x, *d_xt;
+    int x_owned, have_xt;
+    int32_t *d_row_ptr, *d_col, *d_rrow_ptr, *d_rcol, *d_sites, *d_level_ptr;
+    float *d_wgt;
+    int32_t *h_level;      /* host: level of every site */
+    sweep_step *steps;
+    int n_steps;
+    /* per-K buffers */
+    int k_alloc;
+    float *d_prop, *d_center, *d_disp, *d_iner;
+    nemk_coef *d_coef;
+    uint32_t *d_mxor, *d_mval, *d_f0, *d_f1;
+    double *d_delta;
+    double *d_logpf;
+    uint8_t *d_lab[2];
+    float *d_t[2];
+    int cur, state_labels;
+    int32_t *d_dirty, *d_wl[2], *d_wl_counts;
+    uint32_t *d_cm;
+    int32_t *d_nk_int, *d_s_int;
+    double *d_partial_s, *d_partial_n, *d_s_dbl, *d_nk_dbl;
+    int rows_per_chunk, nchunks;
+    double *d_crit_partials;
+    int crit_blocks;
+    iter_status *d_status, *h_status;
+    int32_t *h_empty;
+    /* fit bookkeeping */
+    int64_t launches, fixup_rounds;
+    int profile;
+    cudaEvent_t *ev;
+    int *ev_kind;
+    int ev_cap, ev_n;
+};
+
+/* ------------------------------------------------------------------ errors */
+static int fail(nemb_handle *h, int code, const char *fmt, ...)
+{
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof h->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? NEMB_E_MEMORY : NEMB_E_CUDA,  \
+                        "%s: %s", #call, cudaGetErrorString(e_));                          \
+    } while (0)
+
+#define CKK()                                                                  \
+    do {                                                                       \
+        char b_[256];                                                          \
+        if (nemk_last_error(b_, sizeof b_))                                    \
+            return fail(h, NEMB_E_CUDA, "kernel launch failed: %s", b_);       \
+    } while (0)
+
+const char *nemb_version(void) { return NEMB_VERSION; }
+const char *nemb_last_error(const nemb_handle *h) { return h ? h->err : "null handle"; }
+
+/* ------------------------------------------------------------------ lifetime */
+int nemb_create(nemb_handle **out, int device)
+{
+    if (!out) return NEMB_E_ARG;
+    *out = NULL;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        fprintf(stderr, "nem_b200: no CUDA device available (%s); this engine has no CPU path\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        return NEMB_E_CUDA;
+    }
+    if (device < 0) {
+        const char *env = getenv("NEM_B200_DEVICE");
+        if (env && *env) device = atoi(env);
+        else if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) device = device % count;
+    nemb_handle *h = calloc(1, sizeof *h);
+    if (!h) return NEMB_E_MEMORY;
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        free(h);
+        return NEMB_E_CUDA;
+    }
+    h->own_stream = 1;
+    *out = h;
+    return NEMB_OK;
+}
+
+int nemb_set_stream(nemb_handle *h, void *cuda_stream)
+{
+    if (!h) return NEMB_E_ARG;
+    if (h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = 0;
+    return NEMB_OK;
+}
+
+static void free_k(nemb_handle *h)
+{
+    cudaFree(h->d_prop); cudaFree(h->d_center); cudaFree(h->d_disp); cudaFree(h->d_iner);
+    cudaFree(h->d_coef); cudaFree(h->d_mxor); cudaFree(h->d_mval); cudaFree(h->d_f0);
+    cudaFree(h->d_f1); cudaFree(h->d_delta); cudaFree(h->d_logpf);
+    cudaFree(h->d_lab[0]); cudaFree(h->d_lab[1]); cudaFree(h->d_t[0]); cudaFree(h->d_t[1]);
+    cudaFree(h->d_dirty); cudaFree(h->d_wl[0]); cudaFree(h->d_wl[1]); cudaFree(h->d_wl_counts);
+    cudaFree(h->d_cm); cudaFree(h->d_nk_int); cudaFree(h->d_s_int);
+    cudaFree(h->d_partial_s); cudaFree(h->d_partial_n); cudaFree(h->d_s_dbl);
+    cudaFree(h->d_nk_dbl); cudaFree(h->d_crit_partials); cudaFree(h->d_status);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_empty) cudaFreeHost(h->h_empty);
+    h->d_prop = h->d_center = h->d_disp = h->d_iner = NULL;
+    h->d_coef = NULL; h->d_mxor = h->d_mval = h->d_f0 = h->d_f1 = NULL;
+    h->d_delta = h->d_logpf = NULL;
+    h->d_lab[0] = h->d_lab[1] = NULL; h->d_t[0] = h->d_t[1] = NULL;
+    h->d_dirty = h->d_wl[0] = h->d_wl[1] = h->d_wl_counts = NULL;
+    h->d_cm = NULL; h->d_nk_int = h->d_s_int = NULL;
+    h->d_partial_s = h->d_partial_n = h->d_s_dbl = h->d_nk_dbl = h->d_crit_partials = NULL;
+    h->d_status = NULL; h->h_status = NULL; h->h_empty = NULL;
+    h->k_alloc = 0;
+}
+
+static void free_problem(nemb_handle *h)
+{
+    free_k(h);
+    if (h->x_owned) cudaFree(h->d_x);
+    cudaFree(h->d_xt);
+    cudaFree(h->d_row_ptr); cudaFree(h->d_col); cudaFree(h->d_wgt);
+    if (!h->symmetric) { cudaFree(h->d_rrow_ptr); cudaFree(h->d_rcol); }
+    cudaFree(h->d_sites); cudaFree(h->d_level_ptr);
+    free(h->h_level); free(h->steps);
+    h->d_x = h->d_xt = NULL; h->d_row_ptr = h->d_col = h->d_rrow_ptr = h->d_rcol = NULL;
+    h->d_sites = h->d_level_ptr = NULL; h->d_wgt = NULL; h->h_level = NULL; h->steps = NULL;
+    h->n_steps = 0; h->loaded = 0; h->have_xt = 0; h->x_owned = 0;
+}
+
+void nemb_destroy(nemb_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_problem(h);
+    for (int i = 0; i < h->ev_cap; i++) cudaEventDestroy(h->ev[i]);
+    free(h->ev); free(h->ev_kind);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    free(h);
+}
+
+/* ------------------------------------------------------------------ loader: graph */
+/* Reader lists (who reads site i = transpose of the CSR), symmetry test, Gauss-Seidel levels
+ * (i after every lower-index site it reads or is read by), sites sorted by (level, index) and
+ * the launch schedule of the level-scheduled sweep. */
+static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32_t *col,
+                      const float *wgt)
+{
+    h->spatial = row_ptr != NULL;
+    h->nnz = 0; h->depth = 0; h->symmetric = 1;
+    if (!h->spatial) return NEMB_OK;
+    int nnz = row_ptr[n];
+    h->nnz = nnz;
+    for (int i = 0; i < n; i++)
+        if (row_ptr[i + 1] < row_ptr[i]) return fail(h, NEMB_E_ARG, "row_ptr not monotone at %d", i);
+    for (int e = 0; e < nnz; e++)
+        if (col[e] < 0 || col[e] >= n) return fail(h, NEMB_E_ARG, "neighbour index out of range");
+
+    /* transpose */
+    int32_t *rrow = calloc((size_t)n + 1, sizeof(int32_t));
+    int32_t *rcol = malloc(sizeof(int32_t) * (size_t)(nnz ? nnz : 1));
+    int32_t *fill = malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
+    if (!rrow || !rcol || !fill) { free(rrow); free(rcol); free(fill); return fail(h, NEMB_E_MEMORY, "host alloc"); }
+    for (int e = 0; e < nnz; e++) rrow[col[e] + 1]++;
+    for (int i = 0; i < n; i++) rrow[i + 1] += rrow[i];
+    for (int i = 0; i < n; i++) fill[i] = rrow[i];
+    for (int i = 0; i < n; i++)
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) rcol[fill[col[e]]++] = i;
+    /* symmetric iff every row has the same neighbour SET as its reader list */
+    int sym = 1;
+    for (int i = 0; i < n && sym; i++) {
+        int a = row_ptr[i + 1] - row_ptr[i], b = rrow[i + 1] - rrow[i];
+        if (a != b) { sym = 0; break; }
+        /* reader lists are sorted by construction; rows may not be: compare as multisets */
+        long long s1 = 0, s2 = 0, q1 = 0, q2 = 0;
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) { s1 += col[e]; q1 += (long long)col[e] * col[e]; }
+        for (int e = rrow[i]; e < rrow[i + 1]; e++) { s2 += rcol[e]; q2 += (long long)rcol[e] * rcol[e]; }
+        if (s1 != s2 || q1 != q2) sym = 0;
+    }
+    h->symmetric = sym;
+
+    /* levels */
+    int32_t *level = calloc((size_t)(n ? n : 1), sizeof(int32_t));
+    int32_t *pend = calloc((size_t)(n ? n : 1), sizeof(int32_t));
+    int depth = 0;
+    for (int i = 0; i < n; i++) {
+        int lv = pend[i];
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+            int j = col[e];
+            if (j < i && level[j] > lv) lv = level[j];
+        }
+        level[i] = lv + 1;
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+            int j = col[e];
+            if (j > i && level[i] > pend[j]) pend[j] = level[i];
+        }
+        for (int e = rrow[i]; e < rrow[i + 1]; e++) { /* sites that read i and come later */
+            int j = rcol[e];
+            if (j > i && level[i] > pend[j]) pend[j] = level[i];
+        }
+        if (level[i] > depth) depth = level[i];
+    }
+    free(pend);
+    h->depth = depth;
+    h->h_level = level;
+    int32_t *lptr = calloc((size_t)depth + 2, sizeof(int32_t));
+    int32_t *sites = malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
+    for (int i = 0; i < n; i++) lptr[level[i]]++;          /* level l -> slot l (1-based) */
+    for (int l = 1; l <= depth; l++) lptr[l] += lptr[l - 1];
+    /* lptr[l] = number of sites with level <= l; start of level l (1-based) = lptr[l-1] */
+    for (int i = 0; i < n; i++) fill[i] = 0;
+    int32_t *pos = calloc((size_t)depth + 1, sizeof(int32_t));
+    for (int l = 1; l <= depth; l++) pos[l] = lptr[l - 1];
+    for (int i = 0; i < n; i++) sites[pos[level[i]]++] = i;
+    free(pos);
+    /* device level_ptr is 0-based over levels: level_ptr[q] = start of level q+1 */
+    /* schedule */
+    h->steps = malloc(sizeof(sweep_step) * (size_t)(depth ? depth : 1));
+    h->n_steps = 0;
+    for (int q = 0; q < depth;) {
+        int width = lptr[q + 1] - lptr[q];
+        if (width > NARROW_LEVEL) {
+            int grid = (width + 255) / 256;
+            if (grid > MAX_LEVEL_GRID) grid = MAX_LEVEL_GRID;
+            if (grid < 2) grid = 2;
+            h->steps[h->n_steps++] = (sweep_step){q, q + 1, grid};
+            q++;
+        } else {
+            int q2 = q;
+            while (q2 < depth && lptr[q2 + 1] - lptr[q2] <= NARROW_LEVEL) q2++;
+            h->steps[h->n_steps++] = (sweep_step){q, q2, 1};
+            q = q2;
+        }
+    }
+
+    int rc = NEMB_OK;
+    cudaError_t e1;
+#define UP(dst, src, bytes)                                                                  \
+    do {                                                                                     \
+        size_t b_ = (bytes);                                                                 \
+        if ((e1 = cudaMalloc((void **)&(dst), b_ ? b_ : 4)) != cudaSuccess ||                 \
+            (e1 = cudaMemcpyAsync((dst), (src), b_, cudaMemcpyHostToDevice, h->stream)) !=   \
+                cudaSuccess)                                                                 \
+            rc = fail(h, NEMB_E_CUDA, "graph upload: %s", cudaGetErrorString(e1));           \
+    } while (0)
+    UP(h->d_row_ptr, row_ptr, sizeof(int32_t) * ((size_t)n + 1));
+    UP(h->d_col, col, sizeof(int32_t) * (size_t)nnz);
+    UP(h->d_wgt, wgt, sizeof(float) * (size_t)nnz);
+    if (sym) { h->d_rrow_ptr = h->d_row_ptr; h->d_rcol = h->d_col; }
+    else {
+        UP(h->d_rrow_ptr, rrow, sizeof(int32_t) * ((size_t)n + 1));
+        UP(h->d_rcol, rcol, sizeof(int32_t) * (size_t)nnz);
+    }
+    UP(h->d_sites, sites, sizeof(int32_t) * (size_t)n);
+    UP(h->d_level_ptr, lptr, sizeof(int32_t) * ((size_t)depth + 1));
+#undef UP
+    cudaStreamSynchronize(h->stream);
+    free(rrow); free(rcol); free(fill); free(lptr); free(sites);
+    return rc;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static int load_common(nemb_handle *h, int n, int d, const int32_t *row_ptr, const int32_t *col,
+                       const float *wgt)
+{
+    if (n <= 0 || d <= 0) return fail(h, NEMB_E_ARG, "n and d must be > 0 (n=%d d=%d)", n, d);
+    h->n = n; h->d = d;
+    h->nwt = round_up((n + 31) / 32, 4);
+    int rc = load_graph(h, n, row_ptr, col, wgt);
+    if (rc == NEMB_OK) h->loaded = 1;
+    return rc;
+}
+
+int nemb_load_packed(nemb_handle *h, int n, int d, int wpr, const uint32_t *x,
+                     const int32_t *row_ptr, const int32_t *col, const float *wgt)
+{
+    if (!h || !x) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    free_problem(h);
+    if (wpr < (d + 31) / 32) return fail(h, NEMB_E_ARG, "words_per_row %d too small for d=%d", wpr, d);
+    int wpr_dev = round_up(wpr, 4);
+    size_t bytes = sizeof(uint32_t) * (size_t)n * wpr_dev;
+    CK(cudaMalloc((void **)&h->d_x, bytes));
+    h->x_owned = 1;
+    if (wpr_dev == wpr) {
+        CK(cudaMemcpyAsync(h->d_x, x, bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        CK(cudaMemsetAsync(h->d_x, 0, bytes, h->stream));
+        CK(cudaMemcpy2DAsync(h->d_x, sizeof(uint32_t) * (size_t)wpr_dev, x,
+                             sizeof(uint32_t) * (size_t)wpr, sizeof(uint32_t) * (size_t)wpr, n,
+                             cudaMemcpyHostToDevice, h->stream));
+    }
+    h->wpr = wpr_dev;
+    return load_common(h, n, d, row_ptr, col, wgt);
+}
+
+int nemb_load_packed_device(nemb_handle *h, int n, int d, int wpr, const uint32_t *x_dev,
+                            const int32_t *row_ptr, const int32_t *col, const float *wgt)
+{
+    if (!h || !x_dev) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    free_problem(h);
+    if (wpr % 4 || wpr < (d + 31) / 32)
+        return fail(h, NEMB_E_ARG, "device X needs words_per_row %% 4 == 0 and >= ceil(d/32)");
+    h->d_x = (uint32_t *)x_dev;
+    h->x_owned = 0;
+    h->wpr = wpr;
+    return load_common(h, n, d, row_ptr, col, wgt);
+}
+
+int nemb_load_dense_u8(nemb_handle *h, int n, int d, const uint8_t *x, const int32_t *row_ptr,
+                       const int32_t *col, const float *wgt)
+{
+    if (!h || !x) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    free_problem(h);
+    if (n <= 0 || d <= 0) return fail(h, NEMB_E_ARG, "n and d must be > 0");
+    int wpr = round_up((d + 31) / 32, 4);
+    uint8_t *d_dense = NULL;
+    CK(cudaMalloc((void **)&d_dense, (size_t)n * d));
+    CK(cudaMalloc((void **)&h->d_x, sizeof(uint32_t) * (size_t)n * wpr));
+    h->x_owned = 1;
+    CK(cudaMemcpyAsync(d_dense, x, (size_t)n * d, cudaMemcpyHostToDevice, h->stream));
+    nemk_pack_u8(h->stream, d_dense, n, d, wpr, h->d_x);
+    CKK();
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_dense);
+    h->wpr = wpr;
+    return load_common(h, n, d, row_ptr, col, wgt);
+}
+
+/* ------------------------------------------------------------------ per-K buffers */
+static int ensure_k(nemb_handle *h, int k)
+{
+    if (h->k_alloc == k) return NEMB_OK;
+    free_k(h);
+    size_t n = h->n, d = h->d, kd = (size_t)k * d, kw = (size_t)k * h->wpr;
+    CK(cudaMalloc((void **)&h->d_prop, sizeof(float) * k));
+    CK(cudaMalloc((void **)&h->d_center, sizeof(float) * kd));
+    CK(cudaMalloc((void **)&h->d_disp, sizeof(float) * kd));
+    CK(cudaMalloc((void **)&h->d_iner, sizeof(float) * kd));
+    CK(cudaMalloc((void **)&h->d_coef, sizeof(nemk_coef)));
+    CK(cudaMemset(h->d_coef, 0, sizeof(nemk_coef)));
+    CK(cudaMalloc((void **)&h->d_mxor, sizeof(uint32_t) * kw));
+    CK(cudaMalloc((void **)&h->d_mval, sizeof(uint32_t) * kw));
+    CK(cudaMalloc((void **)&h->d_f0, sizeof(uint32_t) * kw));
+    CK(cudaMalloc((void **)&h->d_f1, sizeof(uint32_t) * kw));
+    CK(cudaMalloc((void **)&h->d_delta, sizeof(double) * (kd + k)));
+    CK(cudaMalloc((void **)&h->d_logpf, sizeof(double) * n * k));
+    for (int b = 0; b < 2; b++) {
+        CK(cudaMalloc((void **)&h->d_lab[b], n));
+        CK(cudaMalloc((void **)&h->d_t[b], sizeof(float) * n * k));
+        CK(cudaMalloc((void **)&h->d_wl[b], sizeof(int32_t) * n));
+    }
+    CK(cudaMalloc((void **)&h->d_dirty, sizeof(int32_t) * n));
+    CK(cudaMemset(h->d_dirty, 0, sizeof(int32_t) * n));
+    CK(cudaMalloc((void **)&h->d_wl_counts, sizeof(int32_t) * 2));
+    CK(cudaMemset(h->d_wl_counts, 0, sizeof(int32_t) * 2));
+    CK(cudaMalloc((void **)&h->d_cm, sizeof(uint32_t) * (size_t)k * h->nwt));
+    CK(cudaMalloc((void **)&h->d_nk_int, sizeof(int32_t) * k));
+    CK(cudaMalloc((void **)&h->d_s_int, sizeof(int32_t) * kd));
+    h->rows_per_chunk = 4096;
+    h->nchunks = (h->n + h->rows_per_chunk - 1) / h->rows_per_chunk;
+    CK(cudaMalloc((void **)&h->d_partial_s, sizeof(double) * kd * h->nchunks));
+    CK(cudaMalloc((void **)&h->d_partial_n, sizeof(double) * (size_t)k * h->nchunks));
+    CK(cudaMalloc((void **)&h->d_s_dbl, sizeof(double) * kd));
+    CK(cudaMalloc((void **)&h->d_nk_dbl, sizeof(double) * k));
+    h->crit_blocks = 1184; /* 148 SMs x 8 */
+    CK(cudaMalloc((void **)&h->d_crit_partials, sizeof(double) * 4 * h->crit_blocks));
+    CK(cudaMalloc((void **)&h->d_status, sizeof(iter_status)));
+    CK(cudaMemset(h->d_status, 0, sizeof(iter_status)));
+    CK(cudaMallocHost((void **)&h->h_status, sizeof(iter_status)));
+    CK(cudaMallocHost((void **)&h->h_empty, sizeof(int32_t)));
+    h->k_alloc = k;
+    return NEMB_OK;
+}
+
+static int ensure_xt(nemb_handle *h)
+{
+    if (h->have_xt) return NEMB_OK;
+    CK(cudaMalloc((void **)&h->d_xt, sizeof(uint32_t) * (size_t)h->d * h->nwt));
+    nemk_transpose_bits(h->stream, h->d_x, h->n, h->wpr, h->d, h->nwt, h->d_xt);
+    CKK();
+    h->have_xt = 1;
+    return NEMB_OK;
+}
+
+/* ------------------------------------------------------------------ stage timing */
+static void stage_mark(nemb_handle *h, int kind_or_end)
+{
+    if (!h->profile) return;
+    if (h->ev_n >= h->ev_cap) {
+        int nc = h->ev_cap ? h->ev_cap * 2 : 256;
+        h->ev = realloc(h->ev, sizeof(cudaEvent_t) * nc);
+        h->ev_kind = realloc(h->ev_kind, sizeof(int) * nc);
+        for (int i = h->ev_cap; i < nc; i++) cudaEventCreate(&h->ev[i]);
+        h->ev_cap = nc;
+    }
+    h->ev_kind[h->ev_n] = kind_or_end;
+    cudaEventRecord(h->ev[h->ev_n++], h->stream);
+}
+#define STAGE_BEGIN(kind) stage_mark(h, (kind))
+#define STAGE_END() stage_mark(h, -1)
+
+/* popcount-path eligibility of theta, evaluated on the host copy (mirrors k_theta_tables) */
+static int theta_uniform(int k, int d, const float *center, const float *disp)
+{
+    for (int c = 0; c < k; c++) {
+        float e0 = disp[(size_t)c * d];
+        for (int j = 0; j < d; j++) {
+            float mu = center[(size_t)c * d + j], e = disp[(size_t)c * d + j];
+            int m0 = abs((int)(0.0f - mu)), m1 = abs((int)(1.0f - mu));
+            if (memcmp(&e, &e0, sizeof e) || m0 > 1 || m1 > 1) return 0;
+        }
+    }
+    return 1;
+}
+
+/* ------------------------------------------------------------------ steps of one fit */
+static int run_tables(nemb_handle *h, int k)
+{
+    nemk_theta_tables(h->stream, k, h->d, h->wpr, h->d_prop, h->d_center, h->d_disp, h->d_coef,
+                      h->d_mxor, h->d_mval, h->d_f0, h->d_f1, h->d_delta);
+    h->launches++;
+    CKK();
+    return NEMB_OK;
+}
+
+static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming)
+{
+    STAGE_BEGIN(ST_DENSITY);
+    if (uniform)
+        nemk_density_uniform(h->stream, k, h->d_x, h->n, h->wpr, h->d_coef, h->d_mxor, h->d_mval,
+                             h->d_logpf, d_hamming);
+    else
+        nemk_density_general(h->stream, k, h->d_x, h->n, h->d, h->wpr, h->d_coef, h->d_f0, h->d_f1,
+                             h->d_delta, h->d_logpf);
+    STAGE_END();
+    h->launches++;
+    CKK();
+    return NEMB_OK;
+}
+
+/* one E-step sweep; *flipped tells whether the state moved to the other buffer */
+static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *flipped)
+{
+    int k = o->k, n = h->n;
+    const int32_t *skip = &h->d_coef->empty_class;
+    const int32_t *rp = h->spatial ? h->d_row_ptr : NULL;
+    int seq = o->update == NEMB_UPDATE_SEQ && h->spatial && beta != 0.0;
+    *flipped = 0;
+    CK(cudaMemsetAsync(&h->d_status->cnt, 0, sizeof(nemk_counters), h->stream));
+    STAGE_BEGIN(ST_SWEEP);
+    if (o->algo == NEMB_ALGO_NCEM) {
+        uint8_t *in = h->d_lab[h->cur], *out = h->d_lab[h->cur ^ 1];
+        int impl = o->sweep_impl == NEMB_SWEEP_AUTO ? NEMB_SWEEP_SPEC : o->sweep_impl;
+        if (!seq) {
+            nemk_sweep_ncem_jacobi(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+                                   out, NULL, NULL, NULL, NULL, NULL, &h->d_status->cnt, skip);
+            h->launches++;
+            *flipped = 1;
+        } else if (impl == NEMB_SWEEP_SPEC) {
+            nemk_sweep_ncem_jacobi(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+                                   out, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
+                                   h->d_rcol, &h->d_status->cnt, skip);
+            nemk_sweep_ncem_fixup(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+                                  out, h->d_dirty, h->d_wl[0], h->d_wl[1], h->d_wl_counts,
+                                  h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip);
+            h->launches += 2;
+            *flipped = 1;
+        } else {
+            for (int s = 0; s < h->n_steps; s++) {
+                nemk_sweep_ncem_level(h->stream, k, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+                                      h->d_sites, h->d_level_ptr, h->steps[s].lo, h->steps[s].hi,
+                                      h->steps[s].grid, &h->d_status->cnt, skip);
+                h->launches++;
+            }
+        }
+    } else {
+        float *in = h->d_t[h->cur], *out = h->d_t[h->cur ^ 1];
+        if (!seq) {
+            nemk_sweep_nem_jacobi(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in, out,
+                                  &h->d_status->cnt, skip);
+            h->launches++;
+            *flipped = 1;
+        } else {
+            for (int s = 0; s < h->n_steps; s++) {
+                nemk_sweep_nem_level(h->stream, k, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+                                     h->d_sites, h->d_level_ptr, h->steps[s].lo, h->steps[s].hi,
+                                     h->steps[s].grid, &h->d_status->cnt, skip);
+                h->launches++;
+            }
+        }
+    }
+    STAGE_END();
+    CKK();
+    if (*flipped) h->cur ^= 1;
+    return NEMB_OK;
+}
+
+static int run_mstep(nemb_handle *h, const nemb_options *o)
+{
+    int k = o->k, rc;
+    STAGE_BEGIN(ST_MSTEP);
+    if (o->algo == NEMB_ALGO_NCEM) {
+        if ((rc = ensure_xt(h)) != NEMB_OK) return rc;
+        nemk_label_masks(h->stream, k, h->n, h->nwt, h->d_lab[h->cur], h->d_cm, h->d_nk_int);
+        nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_s_int);
+        nemk_mstep_finalize(h->stream, k, h->n, h->d, o->prop, o->disp, h->d_s_int, h->d_nk_int,
+                            NULL, NULL, h->d_prop, h->d_center, h->d_disp, h->d_iner, h->d_coef);
+        h->launches += 3;
+    } else {
+        nemk_mstep_nem(h->stream, k, h->n, h->d, h->wpr, h->d_x, h->d_t[h->cur], h->rows_per_chunk,
+                       h->d_partial_s, h->d_partial_n, h->d_s_dbl, h->d_nk_dbl);
+        nemk_mstep_finalize(h->stream, k, h->n, h->d, o->prop, o->disp, NULL, NULL, h->d_s_dbl,
+                            h->d_nk_dbl, h->d_prop, h->d_center, h->d_disp, h->d_iner, h->d_coef);
+        h->launches += 3;
+    }
+    STAGE_END();
+    CKK();
+    return run_tables(h, k);
+}
+
+static int run_criteria(nemb_handle *h, const nemb_options *o, double beta, double *d_out)
+{
+    STAGE_BEGIN(ST_CRIT);
+    nemk_criteria(h->stream, o->k, h->n, h->d_logpf, h->spatial ? h->d_row_ptr : NULL, h->d_col,
+                  h->d_wgt, beta, o->algo == NEMB_ALGO_NCEM ? h->d_lab[h->cur] : NULL,
+                  o->algo == NEMB_ALGO_NCEM ? NULL : h->d_t[h->cur], h->d_crit_partials,
+                  h->crit_blocks, d_out);
+    STAGE_END();
+    h->launches += 2;
+    CKK();
+    return NEMB_OK;
+}
+
+static int check_options(nemb_handle *h, const nemb_options *o)
+{
+    if (!h->loaded) return fail(h, NEMB_E_ARG, "no pangenome loaded");
+    if (o->k < 1 || o->k > NEMB_MAX_K) return fail(h, NEMB_E_ARG, "k must be in 1..%d (here %d)", NEMB_MAX_K, o->k);
+    if (o->algo != NEMB_ALGO_NEM && o->algo != NEMB_ALGO_NCEM) return fail(h, NEMB_E_ARG, "bad algo %d", o->algo);
+    if (o->update != NEMB_UPDATE_SEQ && o->update != NEMB_UPDATE_PARA) return fail(h, NEMB_E_ARG, "bad update %d", o->update);
+    if (o->conv < 0 || o->conv > 2) return fail(h, NEMB_E_ARG, "bad convergence test %d", o->conv);
+    if (o->conv != NEMB_CONV_NONE && !(o->conv_thr > 0)) return fail(h, NEMB_E_ARG, "conv threshold must be > 0");
+    if (o->prop < 0 || o->prop > 1 || o->disp < 0 || o->disp > 3) return fail(h, NEMB_E_ARG, "bad model");
+    if (o->it_max < 0) return fail(h, NEMB_E_ARG, "it_max must be >= 0");
+    return NEMB_OK;
+}
+
+static int read_status(nemb_handle *h)
+{
+    CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEMB_OK;
+}
+
+static int init_state(nemb_handle *h, const nemb_options *o)
+{
+    h->cur = 0;
+    h->state_labels = o->algo == NEMB_ALGO_NCEM;
+    if (h->state_labels) CK(cudaMemsetAsync(h->d_lab[0], 255, h->n, h->stream));
+    else CK(cudaMemsetAsync(h->d_t[0], 0, sizeof(float) * (size_t)h->n * o->k, h->stream));
+    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, sizeof(int32_t), h->stream));
+    return NEMB_OK;
+}
+
+/* EM from the theta already resident on the device (d_prop/d_center/d_disp). */
+static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_result *res,
+                   nemb_iter_cb cb, void *user, float *prop, float *center, float *disp)
+{
+    int k = o->k, rc, flipped;
+    double beta = h->spatial ? (double)o->beta : 0.0;   /* nem_exe.c:570-574 */
+    int uniform_m = o->param_fixed ? uniform0 : (o->disp == NEMB_DISP_K_ || o->disp == NEMB_DISP___);
+    int want_crit_each = o->dolog || o->conv == NEMB_CONV_CRIT;
+    size_t kd = (size_t)k * h->d;
+    float *nk_host = cb ? malloc(sizeof(float) * k) : NULL;
+
+    if ((rc = init_state(h, o)) != NEMB_OK) return rc;
+    if ((rc = run_tables(h, k)) != NEMB_OK) return rc;
+    if ((rc = run_density(h, k, uniform0, NULL)) != NEMB_OK) return rc;
+    /* ComputePartitionFromPara(Needinit=1): blind sweep then beta sweep (nem_alg.c:1970-1981) */
+    if ((rc = run_sweep(h, o, 0.0, &flipped)) != NEMB_OK) return rc;
+    if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
+    if ((rc = run_sweep(h, o, beta, &flipped)) != NEMB_OK) return rc;
+    if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
+    double oldcrit = 0.0;
+    if (o->dolog || cb || o->it_max == 0) {
+        if ((rc = read_status(h)) != NEMB_OK) return rc;
+        h->fixup_rounds += h->h_status->cnt.nfix;
+        res->n_allnul = h->h_status->cnt.allnul;
+        res->n_ties = h->h_status->cnt.ties;
+        oldcrit = h->h_status->crit_after[3];
+        if (cb) {
+            for (int c = 0; c < k; c++) nk_host[c] = NAN;
+            cb(user, 0, h->h_status->crit_before, h->h_status->crit_after, prop, center, disp, nk_host);
+        }
+    }
+
+    int iter, converged = 0, status = NEMB_OK, empty = 0;
+    for (iter = 1; iter <= o->it_max && !converged && status == NEMB_OK; iter++) {
+        if (!o->param_fixed && (rc = run_mstep(h, o)) != NEMB_OK) return rc;
+        if ((rc = run_density(h, k, uniform_m, NULL)) != NEMB_OK) return rc;
+        if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
+        if ((rc = run_sweep(h, o, beta, &flipped)) != NEMB_OK) return rc;
+        if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
+        if (cb) {
+            CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+        }
+        if ((rc = read_status(h)) != NEMB_OK) return rc;
+        empty = *h->h_empty;
+        if (empty) {              /* nem_alg.c:1831-1838: E-step not run, loop ends */
+            status = NEMB_W_EMPTYCLASS;
+            if (flipped) h->cur ^= 1;
+            continue;
+        }
+        h->fixup_rounds += h->h_status->cnt.nfix;
+        res->n_allnul = h->h_status->cnt.allnul;
+        res->n_ties = h->h_status->cnt.ties;
+        if (o->conv == NEMB_CONV_CLAS) {
+            float md = o->algo == NEMB_ALGO_NCEM ? (h->h_status->cnt.changed ? 1.0f : 0.0f)
+                                                 : h->h_status->cnt.maxdiff;
+            converged = md < o->conv_thr;
+        } else if (o->conv == NEMB_CONV_CRIT) {
+            double curc = h->h_status->crit_after[3];
+            float dif = curc != 0 ? (float)fabs((curc - oldcrit) / curc) : FLT_MAX;
+            converged = dif < o->conv_thr;
+        }
+        if (want_crit_each) oldcrit = h->h_status->crit_after[3];
+        if (cb) {
+            if (o->param_fixed) {
+                for (int c = 0; c < k; c++) nk_host[c] = NAN;
+            } else if (o->algo == NEMB_ALGO_NCEM) {
+                int32_t ni[NEMB_MAX_K];
+                CK(cudaMemcpy(ni, h->d_nk_int, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
+                for (int c = 0; c < k; c++) nk_host[c] = (float)ni[c];
+            } else {
+                double nd[NEMB_MAX_K];
+                CK(cudaMemcpy(nd, h->d_nk_dbl, sizeof(double) * k, cudaMemcpyDeviceToHost));
+                for (int c = 0; c < k; c++) nk_host[c] = (float)nd[c];
+            }
+            cb(user, iter, h->h_status->crit_before, h->h_status->crit_after, prop, center, disp, nk_host);
+        }
+    }
+    iter -= 1;
+    if (iter == 0) { /* nem_alg.c:1845-1851 */
+        if ((rc = run_mstep(h, o)) != NEMB_OK) return rc;
+        if ((rc = run_density(h, k, uniform_m, NULL)) != NEMB_OK) return rc;
+    }
+    if ((rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
+    CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = read_status(h)) != NEMB_OK) return rc;
+    if (iter == 0 && *h->h_empty) { status = NEMB_W_EMPTYCLASS; empty = *h->h_empty; }
+    res->status = status; res->iters = iter; res->converged = converged; res->empty_class = empty;
+    const double *c6 = h->h_status->crit_after;
+    res->U = c6[0]; res->D = c6[1]; res->L = c6[2]; res->M = c6[3]; res->Z = c6[4]; res->G = c6[5];
+    free(nk_host);
+    return NEMB_OK;
+}
+
+static void collect_profile(nemb_handle *h, nemb_result *res, cudaEvent_t e0, cudaEvent_t e1)
+{
+    cudaEventElapsedTime(&res->fit_ms, e0, e1);
+    res->kernel_launches = h->launches;
+    res->fixup_rounds = h->fixup_rounds;
+    if (!h->profile) return;
+    float *ms[ST_NB] = {&res->ms_density, &res->ms_sweep, &res->ms_mstep, &res->ms_criteria};
+    int32_t *cn[ST_NB] = {&res->n_density, &res->n_sweep, &res->n_mstep, &res->n_criteria};
+    for (int i = 0; i + 1 < h->ev_n; i++) {
+        int kind = h->ev_kind[i];
+        if (kind < 0 || h->ev_kind[i + 1] != -1) continue;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]);
+        *ms[kind] += t;
+        *cn[kind] += 1;
+    }
+}
+
+int nemb_fit_logged(nemb_handle *h, const nemb_options *o, float *prop, float *center, float *disp,
+                    nemb_result *res, nemb_iter_cb cb, void *user)
+{
+    if (!h || !o || !prop || !center || !disp || !res) return NEMB_E_ARG;
+    int rc;
+    CK(cudaSetDevice(h->device));
+    if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if ((rc = ensure_k(h, o->k)) != NEMB_OK) return rc;
+    memset(res, 0, sizeof *res);
+    h->launches = 0; h->fixup_rounds = 0; h->profile = o->profile; h->ev_n = 0;
+    size_t kd = (size_t)o->k * h->d;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->stream));
+    CK(cudaMemcpyAsync(h->d_prop, prop, sizeof(float) * o->k, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_center, center, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_disp, disp, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
+    int uniform0 = theta_uniform(o->k, h->d, center, disp);
+    rc = em_core(h, o, uniform0, res, cb, user, prop, center, disp);
+    cudaEventRecord(e1, h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (rc == NEMB_OK) collect_profile(h, res, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != NEMB_OK) return rc;
+    return res->status;
+}
+
+int nemb_fit(nemb_handle *h, const nemb_options *o, float *prop, float *center, float *disp,
+             nemb_result *res)
+{
+    return nemb_fit_logged(h, o, prop, center, disp, res, NULL, NULL);
+}
+
+/* ------------------------------------------------------------------ results */
+int nemb_get_posteriors(nemb_handle *h, float *t_out)
+{
+    if (!h || !t_out || !h->k_alloc) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    int k = h->k_alloc;
+    float *src = h->d_t[h->cur];
+    if (h->state_labels) {
+        src = h->d_t[0];
+        nemk_labels_to_t(h->stream, k, h->n, h->d_lab[h->cur], src);
+        CKK();
+    }
+    CK(cudaMemcpyAsync(t_out, src, sizeof(float) * (size_t)h->n * k, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEMB_OK;
+}
+
+int nemb_get_labels(nemb_handle *h, int32_t *label_out)
+{
+    if (!h || !label_out || !h->k_alloc) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    uint8_t *src = h->d_lab[h->cur];
+    if (!h->state_labels) {
+        src = h->d_lab[0];
+        nemk_t_to_labels(h->stream, h->k_alloc, h->n, h->d_t[h->cur], src);
+        CKK();
+    }
+    uint8_t *tmp = malloc(h->n);
+    if (!tmp) return fail(h, NEMB_E_MEMORY, "host alloc");
+    cudaError_t e = cudaMemcpyAsync(tmp, src, h->n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { free(tmp); return fail(h, NEMB_E_CUDA, "%s", cudaGetErrorString(e)); }
+    for (int i = 0; i < h->n; i++) label_out[i] = tmp[i] == 255 ? -1 : tmp[i];
+    free(tmp);
+    return NEMB_OK;
+}
+
+int nemb_get_dims(const nemb_handle *h, int *n, int *d, int *wpr, int *nwt, int *depth, int *nnz)
+{
+    if (!h || !h->loaded) return NEMB_E_ARG;
+    if (n) *n = h->n;
+    if (d) *d = h->d;
+    if (wpr) *wpr = h->wpr;
+    if (nwt) *nwt = h->nwt;
+    if (depth) *depth = h->depth;
+    if (nnz) *nnz = h->nnz;
+    return NEMB_OK;
+}
+
+int nemb_get_packed(nemb_handle *h, uint32_t *out)
+{
+    if (!h || !h->loaded || !out) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(out, h->d_x, sizeof(uint32_t) * (size_t)h->n * h->wpr, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEMB_OK;
+}
+
+int nemb_get_transposed(nemb_handle *h, uint32_t *out)
+{
+    if (!h || !h->loaded || !out) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_xt(h);
+    if (rc != NEMB_OK) return rc;
+    CK(cudaMemcpyAsync(out, h->d_xt, sizeof(uint32_t) * (size_t)h->d * h->nwt, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEMB_OK;
+}
+
+int nemb_get_levels(nemb_handle *h, int32_t *level)
+{
+    if (!h || !h->loaded || !level) return NEMB_E_ARG;
+    if (!h->spatial) { for (int i = 0; i < h->n; i++) level[i] = 1; return NEMB_OK; }
+    memcpy(level, h->h_level, sizeof(int32_t) * (size_t)h->n);
+    return NEMB_OK;
+}
+
+/* ------------------------------------------------------------------ stage entry points */
+static int upload_theta(nemb_handle *h, int k, const float *prop, const float *center, const float *disp)
+{
+    size_t kd = (size_t)k * h->d;
+    CK(cudaMemcpyAsync(h->d_prop, prop, sizeof(float) * k, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_center, center, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_disp, disp, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, sizeof(int32_t), h->stream));
+    return NEMB_OK;
+}
+
+int nemb_stage_density(nemb_handle *h, int k, const float *prop, const float *center,
+                       const float *disp, int force_general, double *logpf_out,
+                       int32_t *hamming_out, int *used_uniform)
+{
+    if (!h || !h->loaded || !prop || !center || !disp || !logpf_out) return NEMB_E_ARG;
+    if (k < 1 || k > NEMB_MAX_K) return fail(h, NEMB_E_ARG, "bad k");
+    int rc;
+    CK(cudaSetDevice(h->device));
+    if ((rc = ensure_k(h, k)) != NEMB_OK) return rc;
+    h->profile = 0;
+    if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
+    int uniform = !force_general && theta_uniform(k, h->d, center, disp);
+    int32_t *d_ham = NULL;
+    size_t nk = (size_t)h->n * k;
+    if (hamming_out && uniform) CK(cudaMalloc((void **)&d_ham, sizeof(int32_t) * nk));
+    if ((rc = run_tables(h, k)) != NEMB_OK) return rc;
+    if ((rc = run_density(h, k, uniform, d_ham)) != NEMB_OK) return rc;
+    CK(cudaMemcpyAsync(logpf_out, h->d_logpf, sizeof(double) * nk, cudaMemcpyDeviceToHost, h->stream));
+    if (d_ham) CK(cudaMemcpyAsync(hamming_out, d_ham, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_ham);
+    if (used_uniform) *used_uniform = uniform;
+    return NEMB_OK;
+}
+
+static int upload_state(nemb_handle *h, const nemb_options *o, const float *t)
+{
+    size_t nk = (size_t)h->n * o->k;
+    h->cur = 0;
+    h->state_labels = o->algo == NEMB_ALGO_NCEM;
+    CK(cudaMemcpyAsync(h->d_t[h->state_labels ? 1 : 0], t, sizeof(float) * nk, cudaMemcpyHostToDevice, h->stream));
+    if (h->state_labels) {
+        nemk_t_to_labels(h->stream, o->k, h->n, h->d_t[1], h->d_lab[0]);
+        CKK();
+    }
+    return NEMB_OK;
+}
+
+int nemb_stage_sweep(nemb_handle *h, const nemb_options *o, const double *logpf, float beta,
+                     float *t_inout, int32_t *label_out, int64_t *fixup_rounds)
+{
+    if (!h || !o || !logpf || !t_inout) return NEMB_E_ARG;
+    int rc, flipped;
+    CK(cudaSetDevice(h->device));
+    if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if ((rc = ensure_k(h, o->k)) != NEMB_OK) return rc;
+    h->profile = 0;
+    size_t nk = (size_t)h->n * o->k;
+    CK(cudaMemcpyAsync(h->d_logpf, logpf, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, sizeof(int32_t), h->stream));
+    if ((rc = upload_state(h, o, t_inout)) != NEMB_OK) return rc;
+    if ((rc = run_sweep(h, o, h->spatial ? (double)beta : 0.0, &flipped)) != NEMB_OK) return rc;
+    if ((rc = read_status(h)) != NEMB_OK) return rc;
+    if (fixup_rounds) *fixup_rounds = h->h_status->cnt.nfix;
+    if ((rc = nemb_get_posteriors(h, t_inout)) != NEMB_OK) return rc;
+    if (label_out && (rc = nemb_get_labels(h, label_out)) != NEMB_OK) return rc;
+    return NEMB_OK;
+}
+
+int nemb_stage_mstep(nemb_handle *h, const nemb_options *o, const float *t, float *prop,
+                     float *center, float *disp, double *nk_out, double *skd_out, int *empty_class)
+{
+    if (!h || !o || !t || !prop || !center || !disp) return NEMB_E_ARG;
+    int rc, k = o->k;
+    CK(cudaSetDevice(h->device));
+    if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if ((rc = ensure_k(h, k)) != NEMB_OK) return rc;
+    h->profile = 0;
+    size_t kd = (size_t)k * h->d;
+    if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
+    if ((rc = upload_state(h, o, t)) != NEMB_OK) return rc;
+    if ((rc = run_mstep(h, o)) != NEMB_OK) return rc;
+    CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = read_status(h)) != NEMB_OK) return rc;
+    if (empty_class) *empty_class = *h->h_empty;
+    if (nk_out || skd_out) {
+        if (o->algo == NEMB_ALGO_NCEM) {
+            int32_t *ti = malloc(sizeof(int32_t) * (kd + k));
+            CK(cudaMemcpy(ti, h->d_s_int, sizeof(int32_t) * kd, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ti + kd, h->d_nk_int, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
+            if (skd_out) for (size_t q = 0; q < kd; q++) skd_out[q] = ti[q];
+            if (nk_out) for (int c = 0; c < k; c++) nk_out[c] = ti[kd + c];
+            free(ti);
+        } else {
+            if (skd_out) CK(cudaMemcpy(skd_out, h->d_s_dbl, sizeof(double) * kd, cudaMemcpyDeviceToHost));
+            if (nk_out) CK(cudaMemcpy(nk_out, h->d_nk_dbl, sizeof(double) * k, cudaMemcpyDeviceToHost));
+        }
+    }
+    return NEMB_OK;
+}
+
+int nemb_stage_criteria(nemb_handle *h, const nemb_options *o, const double *logpf, const float *t,
+                        float beta, double *crit6)
+{
+    if (!h || !o || !logpf || !t || !crit6) return NEMB_E_ARG;
+    int rc;
+    CK(cudaSetDevice(h->device));
+    if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if ((rc = ensure_k(h, o->k)) != NEMB_OK) return rc;
+    h->profile = 0;
+    size_t nk = (size_t)h->n * o->k;
+    CK(cudaMemcpyAsync(h->d_logpf, logpf, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = upload_state(h, o, t)) != NEMB_OK) return rc;
+    if ((rc = run_criteria(h, o, h->spatial ? (double)beta : 0.0, h->d_status->crit_after)) != NEMB_OK) return rc;
+    if ((rc = read_status(h)) != NEMB_OK) return rc;
+    memcpy(crit6, h->h_status->crit_after, sizeof(double) * 6);
+    return NEMB_OK;
+}
