@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- NEM family-iterations/s on B200 (BASELINE.json metric) + roofline + CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1] [--impl reference]
+
+One "step" = one complete NEM fit (blind sweep, beta sweep, EM iterations until the `clas`
+convergence test, final criteria) of the synthetic pangenome, run exactly as PPanGGOLiN runs it
+(ncem, sequential sweep, bern pk sk_, K=3; reference ppanggolin.py:1814-1826).
+value = N x (EM iterations executed) / fit seconds, inputs resident in HBM.
+e2e   = same metric through the C ABI with HOST buffers (H2D of packed X + CSR, graph
+        preprocessing, fit, D2H of the labels and theta inside the timed region).
+N > 1 : one process per GPU (torchrun); every rank fits an independent replica of the workload
+        (BASELINE config 5 "independent runs spread across GPUs", no communication) => weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (families, genomes, beta, graph)
+    "c1": (20_000, 50, 0.5, "pangenome"),       # BASELINE config 1 (reference's CPU-runnable case)
+    "c2": (100_000, 500, 0.0, "none"),          # pure Bernoulli mixture
+    "c3": (250_000, 1000, 0.5, "pangenome"),    # full NEM, 1 GPU
+    "c4": (1_000_000, 5000, 0.5, "pangenome"),  # large pangenome, the metric's 1/2/4/8-GPU config
+}
+K = 3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                              ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def write_sample_files(base, x_rows, row_ptr, col, wgt):
+    from pangenomenem_b200 import synth
+    pg = synth.Pangenome(x=x_rows, row_ptr=row_ptr, col=col, wgt=wgt,
+                         latent=np.zeros(x_rows.shape[0], dtype=np.int8))
+    synth.write_nem_files(base, pg)
+
+
+def make_cpu_sample(n_s, d, beta, graph, seed):
+    """A bounded sample of the workload: n_s families of the same D, its own pangenome-like graph."""
+    from pangenomenem_b200 import synth
+    pg = synth.make_pangenome(n_s, d, seed=seed, graph=graph if beta != 0 else "none")
+    return pg
+
+
+def run_reference_pairs(bases, beta, n_s, spatial):
+    """All samples in parallel, it_max=1 then it_max=3 with convergence=none; returns
+    (family-iterations/s aggregate, seconds of the 2 extra iterations, T1, T3)."""
+    from oracle import nemo
+
+    def launch(itmax):
+        t0 = time.time()
+        procs = [subprocess.Popen([nemo.REF_CLI, b, str(K), "ncem", repr(float(beta)), "none", "0.01",
+                                   "fuzzy", str(itmax), "0", "bern", "pk", "sk_", "2"],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                 for b in bases]
+        for p in procs:
+            p.wait()
+        return time.time() - t0
+    t1 = launch(1)
+    t3 = launch(3)
+    dt = max(t3 - t1, 1e-9)
+    return len(bases) * n_s * 2 / dt, dt, t1, t3
+
+
+def run_port(pg, beta):
+    from oracle import nemo
+    pb = nemo.Problem(pg.x, pg.row_ptr if beta else None, pg.col if beta else None,
+                      pg.wgt if beta else None, k=K, algo="ncem", beta=beta, conv="none", it_max=3)
+    t0 = time.time(); pb.fit(*nemo.default_theta(K, pg.d)); t3 = time.time() - t0
+    pb = nemo.Problem(pg.x, pg.row_ptr if beta else None, pg.col if beta else None,
+                      pg.wgt if beta else None, k=K, algo="ncem", beta=beta, conv="none", it_max=1)
+    t0 = time.time(); pb.fit(*nemo.default_theta(K, pg.d)); t1 = time.time() - t0
+    return pg.n * 2 / max(t3 - t1, 1e-9)
+
+
+def cpu_baseline(workload, cores, budget_cells=6.0e7):
+    """Times the reference (oracle/_ref, kind "reference") or, if it is absent, the C port on a
+    bounded sample: `cores` independent samples in parallel, one process per core."""
+    from oracle import nemo
+    n, d, beta, graph = WORKLOADS[workload]
+    n_s = int(max(500, min(n, budget_cells / d / 3)))
+    tmp = tempfile.mkdtemp(prefix="nem_cpu_")
+    if nemo.have_ref():
+        bases = []
+        for c in range(cores):
+            pg = make_cpu_sample(n_s, d, beta, graph, seed=100 + c)
+            base = os.path.join(tmp, f"s{c}", "nem_file")
+            from pangenomenem_b200 import synth
+            synth.write_nem_files(base, pg, spatial=beta != 0)
+            bases.append(base)
+        rate, dt, t1, t3 = run_reference_pairs(bases, beta, n_s, beta != 0)
+        kind = "reference"
+        note = (f"{cores} x ({n_s} families x {d} genomes) samples of {workload}, unmodified reference "
+                f"nem() via oracle/_ref/nem_ref_cli, ncem beta={beta} sk_ pk, per-iteration time = "
+                f"(T[it_max=3]-T[it_max=1])/2 = {dt / 2:.3f}s (file parsing and the per-genome qsort "
+                f"excluded; T1={t1:.1f}s T3={t3:.1f}s)")
+        if d >= 2000:
+            note += "; at this D the reference's linear-domain densities underflow (results degenerate, timing still representative)"
+    else:
+        pg = make_cpu_sample(n_s, d, beta, graph, seed=100)
+        rate = run_port(pg, beta)
+        kind, cores = "port", 1
+        note = f"{n_s} families x {d} genomes sample of {workload}, oracle/nem_oracle.c (float64 C port), 1 thread"
+    return {"value": rate, "unit": "family-iterations/s", "cores": cores, "kind": kind, "sample": note}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals, last = [], None
+    for step in range(args.warmup + args.steps):
+        last = cpu_baseline(args.workload, cores, budget_cells=2.0e7)
+        if step >= args.warmup:
+            vals.append(last["value"])
+    n, d, beta, graph = WORKLOADS[args.workload]
+    v = float(np.mean(vals))
+    last["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": "NEM family-iterations/s", "value": v,
+        "unit": "family-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "families": n, "genomes": d, "K": K,
+                   "beta": beta, "algo": "ncem", "update": "seq"},
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": "family-iterations/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_name(w):
+    n, d, beta, graph = WORKLOADS[w]
+    return f"{w}: {n} families x {d} genomes, K={K}, beta={beta}, graph={graph}, ncem seq bern pk sk_"
+
+
+# ----------------------------------------------------------------------------- our arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import nemo  # theta0 helper only (cpu_baseline leg uses the rest)
+    from pangenomenem_b200 import capi, synth_gpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, d, beta, graph = WORKLOADS[args.workload]
+    if args.rows:
+        n = args.rows
+    wb = 4 * ((d + 31) // 32)            # unpadded packed row bytes
+    tk = 4 * K
+
+    # ---- synthetic pangenome: X drawn + packed on the device, graph on the host
+    t0 = time.time()
+    xdev, _ = synth_gpu.make_packed_on_device(n, d, seed=42 + rank, device=dev)
+    wpr = xdev.shape[1]
+    xhost = torch.empty(xdev.shape, dtype=torch.int32, pin_memory=True)
+    xhost.copy_(xdev)
+    torch.cuda.synchronize()
+    xh = xhost.numpy()
+    if beta != 0 and graph != "none":
+        row_ptr, col, wgt = synth_gpu.make_graph(n, xh, seed=42 + rank, kind=graph)
+    else:
+        row_ptr = col = wgt = None
+    gen_s = time.time() - t0
+    nnz = 0 if col is None else int(col.shape[0])
+    theta0 = nemo.default_theta(K, d)
+    opts = dict(k=K, algo="ncem", update="seq", beta=beta, conv="clas", conv_thr=1e-8,
+                it_max=100, prop="pk", disp="sk_", sweep_impl="auto")
+
+    eng = capi.Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.load_packed_device(xdev.data_ptr(), n, d, wpr, row_ptr, col, wgt)
+    depth = eng.dims()["depth"]
+    x_bytes = n * wpr * 4
+    flush = None
+    if x_bytes < 256 << 20:              # X fits the 126 MB L2: flush between timed steps
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_fit(profile):
+        return eng.fit(*theta0, profile=profile, **opts)
+
+    for _ in range(args.warmup):
+        one_fit(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    fits = []
+    barrier()
+    w0 = time.time()
+    for s in range(args.steps):
+        if flush is not None:
+            flush.fill_(s & 0xff)
+        ev[s][0].record(stream)
+        fits.append(one_fit(True))
+        ev[s][1].record(stream)
+    barrier()
+    wall = time.time() - w0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    iters = sum(f.iters for f in fits)
+    launches = sum(f.kernel_launches for f in fits)
+
+    # ---- e2e through the C ABI with host buffers (pinned X), H2D + preprocessing + fit + D2H
+    e2e_steps = max(1, min(args.steps, 3))
+    eng2 = capi.Engine(local)
+    eng2.set_stream(stream.cuda_stream)
+    lab_host = None
+    barrier()
+    e0 = time.time()
+    e_iters = 0
+    for _ in range(e2e_steps):
+        eng2.load_packed(xh.view(np.uint32), d, row_ptr, col, wgt)
+        f = eng2.fit(*theta0, **opts)
+        lab_host = eng2.labels()
+        e_iters += f.iters
+    barrier()
+    e_wall = time.time() - e0
+    eng2.close()
+    h2d = x_bytes + (0 if col is None else (n + 1) * 4 * 2 + nnz * 8 + n * 4 + depth * 4) + 2 * (K + 2 * K * d) * 4
+    d2h = n + (K + 2 * K * d) * 4 + 256
+
+    # ---- max over ranks
+    t_dev = torch.tensor([dev_ms, e_wall * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n * iters), float(n * e_iters), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e_ms_max, wall_ms_max = [float(v) for v in t_dev.tolist()]
+    fam_iters, e_fam_iters, launches_all = [float(v) for v in tot.tolist()]
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        f = fits[-1]
+        n_den = sum(x.stage_launches["density"] for x in fits)
+        n_ms = sum(x.stage_launches["mstep"] for x in fits)
+        ms_den = sum(x.stage_ms["density"] for x in fits) / max(n_den, 1)
+        ms_ms = sum(x.stage_ms["mstep"] for x in fits) / max(n_ms, 1)
+        ms_sw = sum(x.stage_ms["sweep"] for x in fits) / max(sum(x.stage_launches["sweep"] for x in fits), 1)
+        den_bytes = n * wb + n * tk                      # SURVEY 8d "E-step-only bytes (density)"
+        achieved = den_bytes / (ms_den * 1e-3) / 1e9 if ms_den > 0 else 0.0
+        ms_bytes = n * wb + n * tk                       # M-step: X once + t once
+        b_iter = 2 * n * wb + 5 * n * tk + 8 * nnz + 4 * (n + 1) + 2 * 4 * K * d
+        iter_ms = dev_ms / max(iters, 1)
+        value = fam_iters / (dev_ms_max * 1e-3)
+        cpu = cpu_baseline(args.workload, 1) if (world == 1 and not args.no_cpu) else None
+        line = {
+            "metric": "NEM family-iterations/s", "value": value, "unit": "family-iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 popcount + f64 log-domain posteriors",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "families": n, "genomes": d, "K": K,
+                       "beta": beta, "algo": "ncem", "update": "seq", "nnz": nnz,
+                       "sweep_dag_depth": depth,
+                       "em_iterations_per_fit": f.iters, "converged": f.converged,
+                       "fixup_rounds_per_fit": f.fixup_rounds,
+                       "multi_gpu": "independent replicas, one per GPU" if world > 1 else "single GPU",
+                       "l2": ("inputs larger than L2 (X = %d MB)" % (x_bytes >> 20)) if flush is None
+                       else "L2 flushed (512 MB write) between timed steps",
+                       "synth_seconds": round(gen_s, 1)},
+            "clocks": clocks,
+            "gpu_launches": int(launches_all),
+            "wall_ms_per_step": wall_ms_max / args.steps,
+            "e2e": {"value": e_fam_iters / (e_ms_max * 1e-3), "unit": "family-iterations/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "ms_per_step": e_ms_max / e2e_steps,
+                    "what": "nemb_load_packed(host pinned X + CSR) + nemb_fit + nemb_get_labels"},
+            "roofline": {"bound": "hbm", "kernel": "k_density_uniform (E-step Bernoulli log-likelihood)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": den_bytes, "avg_launch_ms": ms_den,
+                         "mstep": {"avg_ms": ms_ms, "achieved": ms_bytes / (ms_ms * 1e-3) / 1e9 if ms_ms > 0 else 0.0,
+                                   "what": "label masks + X^T popcount + finalize, X read once"},
+                         "sweep_avg_ms": ms_sw,
+                         "iteration": {"algorithmic_bytes": b_iter, "avg_ms": iter_ms,
+                                       "achieved": b_iter / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else 0.0,
+                                       "note": "whole fit time / EM iterations (includes init sweeps, host syncs)"}},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the number of families (debug)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,8 @@ typedef struct {
     float   fit_ms;       /* device time of the whole fit, CUDA events on the engine's stream */
     float   ms_density, ms_sweep, ms_mstep, ms_criteria;  /* profile=1 only */
     int32_t n_density, n_sweep, n_mstep, n_criteria;      /* launches behind those sums */
+    int32_t best_start;   /* nemb_fit_random: 1-based index of the retained start, else 0 */
+    int32_t n_success;    /* nemb_fit_random: starts that ended without an empty class */
 } nemb_result;
 
 /* Per-iteration trace for the .log writer (nem_alg.c:1995-2052, 2620-2646). */
@@ -159,6 +161,30 @@ int nemb_stage_mstep(nemb_handle *h, const nemb_options *opt, const float *t /*[
                      double *skd_out /*[k*d]*/, int *empty_class);
 int nemb_stage_criteria(nemb_handle *h, const nemb_options *opt, const double *logpf,
                         const float *t, float beta, double *crit6 /*U D L M Z G*/);
+
+/* ---------------------------------------------------------------------------------------
+ * host-side loader / writers (no GPU needed): the NEM file contract as in-memory buffers.
+ * Replaces ReadStrFile / ReadMatrixFile / ReadParamFile / ReadNeiFile (nem_exe.c:739-898,
+ * 973-1091, 1278-1478) and SaveResults (nem_exe.c:1596-1781).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t  n, d, words_per_row;
+    int32_t  spatial;        /* 1 = type S (.nei read), 0 = type N */
+    int32_t  nnz, max_neigh;
+    int32_t  m_flag;         /* .m first token: 1 = initial, 2 = fixed; 0 = .m not read */
+    uint32_t *x_packed;      /* [n][words_per_row] */
+    int32_t  *row_ptr, *col; /* CSR, NULL when not spatial */
+    float    *wgt;
+    float    *prop, *center, *disp;   /* [k], [k*d], [k*d] when k > 0 */
+} nemb_host_problem;
+
+/* k = 0 skips <base>.m.  Returns a NEMB_* code; messages go to stderr. */
+int  nemb_read_files(const char *base, int k, nemb_host_problem *out);
+void nemb_free_host_problem(nemb_host_problem *p);
+int  nemb_write_uf(const char *path, int n, int k, const float *t);
+int  nemb_write_cf(const char *path, int n, const int32_t *label);
+int  nemb_write_mf(const char *path, int k, int d, double U, double D, double L, double M,
+                   float beta, const float *prop, const float *center, const float *disp);
 
 const char *nemb_version(void);
 

@@ -45,12 +45,22 @@ class Result(C.Structure):
                 ("ms_density", C.c_float), ("ms_sweep", C.c_float), ("ms_mstep", C.c_float),
                 ("ms_criteria", C.c_float),
                 ("n_density", C.c_int32), ("n_sweep", C.c_int32), ("n_mstep", C.c_int32),
-                ("n_criteria", C.c_int32)]
+                ("n_criteria", C.c_int32), ("best_start", C.c_int32), ("n_success", C.c_int32)]
 
 
 class Extra(C.Structure):
     _fields_ = [("update", C.c_int32), ("sweep_impl", C.c_int32), ("device", C.c_int32),
                 ("n_random_inits", C.c_int32), ("seed", C.c_int64), ("reserved", C.c_int32 * 8)]
+
+
+class HostProblem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("d", C.c_int32), ("words_per_row", C.c_int32),
+                ("spatial", C.c_int32), ("nnz", C.c_int32), ("max_neigh", C.c_int32),
+                ("m_flag", C.c_int32),
+                ("x_packed", C.POINTER(C.c_uint32)), ("row_ptr", C.POINTER(C.c_int32)),
+                ("col", C.POINTER(C.c_int32)), ("wgt", C.POINTER(C.c_float)),
+                ("prop", C.POINTER(C.c_float)), ("center", C.POINTER(C.c_float)),
+                ("disp", C.POINTER(C.c_float))]
 
 
 _lib = None
@@ -67,11 +77,15 @@ def load_library():
         lib = C.CDLL(LIB_PATH)
         lib.nemb_last_error.restype = C.c_char_p
         lib.nemb_version.restype = C.c_char_p
+        lib.nemb_free_host_problem.restype = None
         sig = [C.c_char_p, C.c_int, C.c_char_p, C.c_float, C.c_char_p, C.c_float, C.c_char_p,
                C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         if hasattr(lib, "nem"):
             lib.nem.argtypes = sig
             lib.nem_b200_ex.argtypes = sig + [C.c_void_p]
+        lib.nemb_write_mf.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, C.c_float, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
         _lib = lib
     return _lib
 
@@ -261,3 +275,76 @@ class Engine:
                                                  _p(np.ascontiguousarray(logpf, dtype=np.float64)),
                                                  _p(_f32(t)), C.c_float(beta), _p(out)))
         return dict(zip("UDLMZG", out))
+
+
+# ------------------------------------------------------------------ host loader / writers (no GPU)
+def read_files(base: str, k: int = 0) -> dict:
+    """Parse <base>.str/.dat/.nei(/.m) with the engine's C loader; numpy copies of its buffers."""
+    lib = load_library()
+    hp = HostProblem()
+    rc = lib.nemb_read_files(base.encode(), int(k), C.byref(hp))
+    if rc != 0:
+        raise NemError(rc, f"nemb_read_files({base})")
+    try:
+        n, d, wpr = hp.n, hp.d, hp.words_per_row
+        out = dict(n=n, d=d, wpr=wpr, spatial=bool(hp.spatial), nnz=hp.nnz, max_neigh=hp.max_neigh,
+                   m_flag=hp.m_flag,
+                   x_packed=np.ctypeslib.as_array(hp.x_packed, shape=(n, wpr)).copy())
+        if hp.spatial:
+            out["row_ptr"] = np.ctypeslib.as_array(hp.row_ptr, shape=(n + 1,)).copy()
+            nnz = max(hp.nnz, 1)
+            out["col"] = np.ctypeslib.as_array(hp.col, shape=(nnz,)).copy()[:hp.nnz]
+            out["wgt"] = np.ctypeslib.as_array(hp.wgt, shape=(nnz,)).copy()[:hp.nnz]
+        if k > 0:
+            out["prop"] = np.ctypeslib.as_array(hp.prop, shape=(k,)).copy()
+            out["center"] = np.ctypeslib.as_array(hp.center, shape=(k, d)).copy()
+            out["disp"] = np.ctypeslib.as_array(hp.disp, shape=(k, d)).copy()
+        return out
+    finally:
+        lib.nemb_free_host_problem(C.byref(hp))
+
+
+def write_uf(path: str, t) -> None:
+    t = _f32(t)
+    rc = load_library().nemb_write_uf(path.encode(), t.shape[0], t.shape[1], _p(t))
+    if rc:
+        raise NemError(rc, path)
+
+
+def write_cf(path: str, label) -> None:
+    label = np.ascontiguousarray(label, dtype=np.int32)
+    rc = load_library().nemb_write_cf(path.encode(), label.shape[0], _p(label))
+    if rc:
+        raise NemError(rc, path)
+
+
+def write_mf(path: str, crit: dict, beta: float, prop, center, disp) -> None:
+    center = _f32(center); k, d = center.shape
+    rc = load_library().nemb_write_mf(path.encode(), k, d, C.c_double(crit["U"]), C.c_double(crit["D"]),
+                                      C.c_double(crit["L"]), C.c_double(crit["M"]), C.c_float(beta),
+                                      _p(_f32(prop)), _p(center), _p(_f32(disp)))
+    if rc:
+        raise NemError(rc, path)
+
+
+def nem(Fname, nk, algo, beta, convergence, convergence_th, format, it_max, dolog, model_family,
+        proportion, dispersion, init_mode) -> int:
+    """Keyword-callable mirror of the reference's Cython ``nem.nem`` (NEM/nem.pyx:1-14): bytes
+    strings, same argument names and meaning, returns the ExitET code."""
+    def b(v):
+        return v if isinstance(v, bytes) else str(v).encode()
+    return load_library().nem(b(Fname), int(nk), b(algo), float(beta), b(convergence),
+                              float(convergence_th), b(format), int(it_max), int(bool(dolog)),
+                              b(model_family), b(proportion), b(dispersion), int(init_mode))
+
+
+def nem_ex(Fname, nk, algo, beta, convergence, convergence_th, format, it_max, dolog, model_family,
+           proportion, dispersion, init_mode, update="seq", sweep_impl="auto", device=-1,
+           n_random_inits=0, seed=0) -> int:
+    def b(v):
+        return v if isinstance(v, bytes) else str(v).encode()
+    ex = Extra(UPDATE[update], SWEEP[sweep_impl], int(device), int(n_random_inits), int(seed))
+    return load_library().nem_b200_ex(b(Fname), int(nk), b(algo), float(beta), b(convergence),
+                                      float(convergence_th), b(format), int(it_max),
+                                      int(bool(dolog)), b(model_family), b(proportion),
+                                      b(dispersion), int(init_mode), C.byref(ex))

@@ -1,0 +1,388 @@
+/*
+ * nem_api.c -- the reference-facing boundary: int nem(...) with the reference's 13 arguments
+ * (NEM/nem_exe.h:23-35, NEM/nem_exe.c:239-704), reading <Fname>.str/.dat/.nei/.m and writing
+ * <Fname>.uf|.cf, .mf and, with dolog, .log and .stderr exactly where and how the reference
+ * does, so that ppanggolin.py:1814-1826 + 1886-1972 drives it unchanged.
+ *
+ * What differs on purpose (INTEGRATION.md "Behavioural notes"):
+ *   - arguments are validated BEFORE any file is read and a bad value returns EXIT_E_ARGS;
+ *     the reference overwrites its own error flag (nem_exe.c:371-431 vs 472) and carries on
+ *     with enum value -1;
+ *   - every error returns an ExitET code; the reference's early returns leak raw StatusET
+ *     values (nem_exe.c:301,309,476,520);
+ *   - stderr is never closed when dolog=0 (nem_exe.c:274,657 closes the process's stderr);
+ *   - MAP ties go to the first class (TIE_FIRST); the reference draws them with a wall-clock
+ *     seeded random() (nem_exe.c:353,361,621);
+ *   - norm/lapl families, gem, init modes 0/3/4 and image data are off the PPanGGOLiN path
+ *      and return EXIT_E_ARGS with a message.
+ */
+#include "nem_b200.h"
+#include "nem_io.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+enum { EXIT_OK_ = 0, EXIT_W_RESULT_ = 1, EXIT_E_ARGS_ = 2, EXIT_E_FILE_ = 3, EXIT_E_MEMORY_ = 4,
+       EXIT_E_SYSTEM_ = 5, EXIT_E_BUG_ = 6 };   /* ExitET, NEM/lib_io.h:22-34 */
+
+static const char *kVersion = "1.08-a";          /* NemVersionStrC, nem_exe.c:233 */
+static const char *kAlgoDes[] = {"NEM", "NCEM (C-step)", "GEM (Monte-Carlo at E-step)"};
+static const char *kPropDes[] = {"P_", "Pk"};
+static const char *kDispDes[] = {"S__", "SK_", "S_D", "S_KD"};
+
+static int find_str(const char *s, const char *const *tab, int n)
+{
+    if (!s) return -1;
+    for (int i = 0; i < n; i++)
+        if (!strcmp(s, tab[i])) return i;      /* GetEnum, nem_exe.c:1784-1809: exact match */
+    return -1;
+}
+
+typedef struct {
+    FILE *flog, *ferr;
+    int k, d, n;
+    double mult;
+    float beta;
+} log_ctx;
+
+/* WriteLogCrit (nem_alg.c:2620-2646) x2 + WriteLogClasses (nem_alg.c:1995-2052) */
+static void log_iteration(void *user, int iter, const double cb[6], const double ca[6],
+                          const float *prop, const float *center, const float *disp,
+                          const float *nk)
+{
+    log_ctx *L = user;
+    if (L->ferr) {
+        if (iter > 0) fprintf(L->ferr, "\b\b\b\b\b%4d ", iter);   /* nem_alg.c:1795-1796 */
+    }
+    if (!L->flog) return;
+    FILE *f = L->flog;
+    fprintf(f, "%4d ", iter);
+    fprintf(f, " %5.0f %5.0f %5.3f", (double)(float)cb[0] * L->mult, (double)(float)cb[3] * L->mult, (double)NAN);
+    fprintf(f, " %5.0f %5.0f %5.3f", (double)(float)ca[0] * L->mult, (double)(float)ca[3] * L->mult, (double)NAN);
+    fprintf(f, "  %5.3f ", (double)L->beta);
+    for (int c = 0; c < L->k; c++) fprintf(f, " %5.3f", (double)prop[c]);
+    fprintf(f, " ");
+    for (int q = 0; q < L->k * L->d; q++) fprintf(f, " %7.3f", (double)center[q]);
+    fprintf(f, " ");
+    for (int q = 0; q < L->k * L->d; q++) fprintf(f, " %7.3f", (double)disp[q]);
+    fprintf(f, " ");
+    for (int c = 0; c < L->k; c++)
+        for (int j = 0; j < L->d; j++) fprintf(f, " %7.1f", (double)nk[c]);
+    fprintf(f, "\n");
+    if (iter == 0) { /* Needinit blank line, then WriteLogHeader (nem_alg.c:1986-1987, 1883-1946) */
+        fprintf(f, "\n");
+        fprintf(f, "%4s  %5s %5s %5s", "It", "UM", "PM", "Er");
+        fprintf(f, " %3s%-2d %3s%-2d %3s%-2d", "UE", 1, "PE", 1, "Er", 1);
+        fprintf(f, "  %5s ", "Beta");
+        for (int c = 0; c < L->k; c++) fprintf(f, " %3s%02d", "P", c + 1);
+        fprintf(f, " ");
+        for (int c = 0; c < L->k; c++)
+            for (int j = 0; j < L->d; j++) fprintf(f, " %3s%02d_%1d", "M", c + 1, j + 1);
+        fprintf(f, " ");
+        for (int c = 0; c < L->k; c++)
+            for (int j = 0; j < L->d; j++) fprintf(f, " %3s%02d_%1d", "D", c + 1, j + 1);
+        fprintf(f, " ");
+        for (int c = 0; c < L->k; c++)
+            for (int j = 0; j < L->d; j++) fprintf(f, " %3s%02d_%1d", "n", c + 1, j + 1);
+        fprintf(f, "\n");
+    }
+}
+
+static int finish(FILE *ferr, int own_err, int code)
+{
+    switch (code) {                      /* messages of nem_exe.c:637-703 */
+    case EXIT_W_RESULT_: fprintf(ferr, "*** NEM warning status : empty class\n"); break;
+    case EXIT_E_ARGS_:   fprintf(ferr, "*** NEM error status : bad arguments\n"); break;
+    case EXIT_E_MEMORY_: fprintf(ferr, "*** NEM error status : not enough memory\n"); break;
+    case EXIT_E_FILE_:   fprintf(ferr, "*** NEM error status : wrong file format\n"); break;
+    case EXIT_E_SYSTEM_: fprintf(ferr, "*** NEM error status : no usable CUDA device (no CPU path)\n"); break;
+    case EXIT_E_BUG_:    fprintf(ferr, "*** NEM internal error\n"); break;
+    default: break;
+    }
+    if (own_err) fclose(ferr); else fflush(ferr);
+    return code;
+}
+
+static int map_status(int nemb)
+{
+    switch (nemb) {
+    case NEMB_OK: return EXIT_OK_;
+    case NEMB_W_EMPTYCLASS: return EXIT_W_RESULT_;
+    case NEMB_E_ARG: return EXIT_E_ARGS_;
+    case NEMB_E_FILE: return EXIT_E_FILE_;
+    case NEMB_E_MEMORY: return EXIT_E_MEMORY_;
+    case NEMB_E_CUDA: return EXIT_E_SYSTEM_;
+    default: return EXIT_E_BUG_;
+    }
+}
+
+int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float beta,
+                const char *convergence, const float convergence_th, const char *format,
+                const int it_max, const int dolog, const char *model_family,
+                const char *proportion, const char *dispersion, const int init_mode,
+                const nem_b200_extra *extra)
+{
+    static const char *algoS[] = {"nem", "ncem", "gem"};
+    static const char *convS[] = {"none", "clas", "crit"};
+    static const char *fmtS[] = {"hard", "fuzzy"};
+    static const char *famS[] = {"norm", "lapl", "bern"};
+    static const char *propS[] = {"p_", "pk"};
+    static const char *dispS[] = {"s__", "sk_", "s_d", "skd"};
+    nem_b200_extra ex;
+    memset(&ex, 0, sizeof ex);
+    ex.device = -1;
+    if (extra) ex = *extra;
+    else {
+        const char *u = getenv("NEM_B200_UPDATE");           /* "para" | "seq" */
+        if (u && !strcmp(u, "para")) ex.update = NEMB_UPDATE_PARA;
+        const char *si = getenv("NEM_B200_SWEEP");           /* "level" | "spec" */
+        if (si && !strcmp(si, "level")) ex.sweep_impl = NEMB_SWEEP_LEVEL;
+        if (si && !strcmp(si, "spec")) ex.sweep_impl = NEMB_SWEEP_SPEC;
+        const char *sd = getenv("NEM_B200_SEED");
+        if (sd && *sd) ex.seed = atoll(sd);
+    }
+
+    if (!Fname) return EXIT_E_ARGS_;
+    FILE *ferr = stderr;
+    int own_err = 0;
+    char path[4200];
+    if (dolog) {                                             /* nem_exe.c:272-282 */
+        snprintf(path, sizeof path, "%s.stderr", Fname);
+        FILE *f = fopen(path, "w");
+        if (f) { ferr = f; own_err = 1; }
+    }
+    fprintf(ferr, " * * * NEM (spatial data clustering) v%s * * *\n", kVersion);
+
+    /* ---- arguments (nem_exe.c:296-435) */
+    int bad = 0;
+    if (nk <= 0) { fprintf(ferr, "Nb of classes must be > 0 (here %d)\n", nk); bad = 1; }
+    else if (nk > 16) { fprintf(ferr, "Nb of classes must be <= 16 in this engine (here %d)\n", nk); bad = 1; }
+    int a = find_str(algo, algoS, 3), cv = find_str(convergence, convS, 3);
+    int fm = find_str(format, fmtS, 2), fa = find_str(model_family, famS, 3);
+    int pr = find_str(proportion, propS, 2), di = find_str(dispersion, dispS, 4);
+    if (a < 0) { fprintf(ferr, " Unknown type of algorithm %s\n", algo ? algo : "(null)"); bad = 1; }
+    if (cv < 0) { fprintf(ferr, " Unknown convergence test %s\n", convergence ? convergence : "(null)"); bad = 1; }
+    else if (cv != 0 && !(convergence_th > 0)) { fprintf(ferr, " Conv threshold must be > 0 (here %f)\n", convergence_th); bad = 1; }
+    if (fm < 0) { fprintf(ferr, " Unknown format %s\n", format ? format : "(null)"); bad = 1; }
+    if (it_max < 0) { fprintf(ferr, "Nb iterations must be >= 0 (here %d)\n", it_max); bad = 1; }
+    if (fa < 0) { fprintf(ferr, " Unknown family %s\n", model_family ? model_family : "(null)"); bad = 1; }
+    if (pr < 0) { fprintf(ferr, " Unknown proportion %s\n", proportion ? proportion : "(null)"); bad = 1; }
+    if (di < 0) { fprintf(ferr, " Unknown dispersion %s\n", dispersion ? dispersion : "(null)"); bad = 1; }
+    if (a == 2) { fprintf(ferr, " Algorithm gem is not available in the B200 engine\n"); bad = 1; }
+    if (fa == 0 || fa == 1) { fprintf(ferr, " Family %s is not available in the B200 engine (bern only)\n", model_family); bad = 1; }
+    if (init_mode != 1 && init_mode != 2) {
+        fprintf(ferr, "Initialization mode %d is not available in the B200 engine "
+                      "(1 = random starts, 2 = parameter file)\n", init_mode);
+        bad = 1;
+    }
+    if (bad) return finish(ferr, own_err, EXIT_E_ARGS_);
+
+    /* ---- files */
+    char type = 0, datadesc[2048] = "", neidesc[2048] = "";
+    int n = 0, d = 0, rc;
+    if ((rc = nemio_read_str(Fname, ferr, &type, &n, &d, datadesc, sizeof datadesc)) != NEMB_OK)
+        return finish(ferr, own_err, map_status(rc));
+    if (type == 'I') {
+        fprintf(ferr, "Image data (type I) is not available in the B200 engine\n");
+        return finish(ferr, own_err, EXIT_E_ARGS_);
+    }
+    int wpr = ((d + 31) / 32 + 3) / 4 * 4;
+    uint32_t *xp = NULL;
+    int32_t *row_ptr = NULL, *col = NULL;
+    float *wgt = NULL;
+    size_t kd = (size_t)nk * d;
+    float *prop = calloc(nk, sizeof(float)), *center = calloc(kd, sizeof(float)),
+          *disp = calloc(kd, sizeof(float));
+    float *t = NULL;
+    int32_t *label = NULL;
+    nemb_handle *h = NULL;
+    int code = EXIT_OK_, flag = 1, max_neigh = 0;
+    log_ctx L;
+    memset(&L, 0, sizeof L);
+    if (!prop || !center || !disp) { code = EXIT_E_MEMORY_; goto done; }
+
+    fprintf(ferr, "Reading points ...\n");
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    snprintf(path, sizeof path, "%s.dat", Fname);
+    if ((rc = nemio_read_dat(path, ferr, n, d, wpr, &xp, ncpu > 16 ? 16 : (int)ncpu)) != NEMB_OK) {
+        code = map_status(rc); goto done;
+    }
+    if (init_mode == 2) {
+        fprintf(ferr, "Reading parameter file ...\n");
+        snprintf(path, sizeof path, "%s.m", Fname);
+        if ((rc = nemio_read_m(path, ferr, nk, d, &flag, prop, center, disp)) != NEMB_OK) {
+            code = map_status(rc); goto done;
+        }
+    }
+    if (type == 'S') {
+        fprintf(ferr, "Reading neighborhood information ...\n");
+        if ((rc = nemio_read_nei(Fname, ferr, n, &row_ptr, &col, &wgt, &max_neigh, neidesc,
+                                 sizeof neidesc)) != NEMB_OK) {
+            code = map_status(rc); goto done;
+        }
+    }
+    float beta_eff = type == 'S' ? beta : 0.0f;                 /* nem_exe.c:570-574 */
+
+    /* ---- banner (nem_exe.c:576-614) */
+    fprintf(ferr, "\nData : ");
+    if (datadesc[0]) fprintf(ferr, "%s\n", datadesc); else fprintf(ferr, "\n");
+    fprintf(ferr, "  file names =  %10s   |   nb points   = %10d\n", Fname, n);
+    fprintf(ferr, "  type       =  %10s   |   dim         = %10d\n", type == 'S' ? "Spatial" : "NoSpatial", d);
+    if (type == 'S') {
+        fprintf(ferr, "Neighborhood system :\n  max neighb =  %10d\n", max_neigh);
+        fprintf(ferr, "%s\n", neidesc);
+    }
+    fprintf(ferr, "\nNEM parameters :\nType of algorithm : '%s'\n", kAlgoDes[a]);
+    fprintf(ferr, "  beta       =  %10.2f   |   nk                    = %3d\n", (double)beta_eff, nk);
+    fprintf(ferr, "                %10s   |   model                 = %s, %s %s\n", " ", "Bernoulli",
+            kPropDes[pr], kDispDes[di]);
+    fprintf(ferr, "\n");
+
+    /* ---- engine */
+    if ((rc = nemb_create(&h, ex.device)) != NEMB_OK) { code = map_status(rc); goto done; }
+    if ((rc = nemb_load_packed(h, n, d, wpr, xp, row_ptr, col, wgt)) != NEMB_OK) {
+        fprintf(ferr, "%s\n", nemb_last_error(h));
+        code = map_status(rc); goto done;
+    }
+    free(xp); xp = NULL;
+    nemb_options o;
+    memset(&o, 0, sizeof o);
+    o.k = nk; o.algo = a; o.update = ex.update; o.conv = cv; o.prop = pr; o.disp = di;
+    o.it_max = it_max; o.param_fixed = (init_mode == 2 && flag == 2); o.dolog = dolog != 0;
+    o.sweep_impl = ex.sweep_impl; o.beta = beta; o.conv_thr = convergence_th;
+    nemb_result res;
+    L.ferr = ferr; L.k = nk; L.d = d; L.n = n; L.beta = beta_eff;
+    if (dolog) {                                                /* StartLogFile, nem_alg.c:1478-1498 */
+        snprintf(path, sizeof path, "%s.log", Fname);
+        L.flog = fopen(path, "w");
+        if (!L.flog) fprintf(ferr, "Could not open file '%s' in write mode\n", path);
+        else {
+            time_t timer = time(NULL);
+            fprintf(L.flog, "NEM log file  -  %s\n", asctime(localtime(&timer)));
+            L.mult = exp(-((int)(log(n / 1000.) / log(10))) * log(10));
+            fprintf(L.flog, "  Criteria are multiplied by %f\n\n", L.mult);
+        }
+    }
+    if (init_mode == 2) {
+        fprintf(ferr, "Initializing parameters from given value\n");
+        if (L.flog) fprintf(L.flog, "Initializing parameters from given value :\n");
+        fprintf(ferr, "  Iterations : %4d ", 0);
+        rc = nemb_fit_logged(h, &o, prop, center, disp, &res, dolog ? log_iteration : NULL, &L);
+    } else {
+        fprintf(ferr, "Random initial partitions (%d starts)\n", ex.n_random_inits ? ex.n_random_inits : 50);
+        rc = nemb_fit_random(h, &o, ex.n_random_inits, ex.seed, prop, center, disp, &res);
+        if (rc == NEMB_OK)
+            fprintf(ferr, "Best start was %d (%s = %g)\n", res.best_start, "M", res.M);
+    }
+    if (L.flog) { fclose(L.flog); L.flog = NULL; }
+    if (rc != NEMB_OK && rc != NEMB_W_EMPTYCLASS) {
+        fprintf(ferr, "\n%s\n", nemb_last_error(h));
+        code = map_status(rc); goto done;
+    }
+    fprintf(ferr, "\n  criterion NEM = %6.3f / Ps-Like = %6.3f / Lmix = %6.3f\n", res.U, res.M, res.L);
+    if (rc == NEMB_W_EMPTYCLASS) {
+        fprintf(ferr, "Class %d empty at iteration %d\n", res.empty_class, res.iters);
+        code = EXIT_W_RESULT_; goto done;                       /* no result files, nem_exe.c:624-631 */
+    }
+    if (cv != 0 && init_mode == 2)
+        fprintf(ferr, res.converged ? "  NEM converged after %d iterations\n"
+                                    : "  NEM did not converge after %d iterations\n", res.iters);
+
+    /* ---- SaveResults (nem_exe.c:1596-1781) */
+    fprintf(ferr, "Saving results ...\n");
+    char outname[4200];
+    snprintf(outname, sizeof outname, "%s%s", Fname, fm == 0 ? ".cf" : ".uf");
+    if (fm == 0) {
+        label = malloc(sizeof(int32_t) * (size_t)n);
+        if (!label) { code = EXIT_E_MEMORY_; goto done; }
+        if ((rc = nemb_get_labels(h, label)) != NEMB_OK) { code = map_status(rc); goto done; }
+        rc = nemio_write_cf(outname, ferr, n, label);
+    } else {
+        t = malloc(sizeof(float) * (size_t)n * nk);
+        if (!t) { code = EXIT_E_MEMORY_; goto done; }
+        if ((rc = nemb_get_posteriors(h, t)) != NEMB_OK) { code = map_status(rc); goto done; }
+        rc = nemio_write_uf(outname, ferr, n, nk, t);
+    }
+    if (rc != NEMB_OK) { code = map_status(rc); goto done; }
+    snprintf(path, sizeof path, "%s.mf", Fname);
+    double crit4[4] = {res.U, res.D, res.L, res.M};
+    if ((rc = nemio_write_mf(path, ferr, nk, d, crit4, beta_eff, prop, center, disp)) != NEMB_OK) {
+        code = map_status(rc); goto done;
+    }
+    fprintf(ferr, "NEM completed, classification in %s\n", outname);
+    fprintf(ferr, " criteria and parameters in %s%s\n", Fname, ".mf");
+    if (dolog) fprintf(ferr, "Log of detailed running in %s.log\n", Fname);
+
+done:
+    if (L.flog) fclose(L.flog);
+    if (h) nemb_destroy(h);
+    free(xp); free(row_ptr); free(col); free(wgt); free(prop); free(center); free(disp);
+    free(t); free(label);
+    return finish(ferr, own_err, code);
+}
+
+int nem(const char *Fname, const int nk, const char *algo, const float beta,
+        const char *convergence, const float convergence_th, const char *format,
+        const int it_max, const int dolog, const char *model_family, const char *proportion,
+        const char *dispersion, const int init_mode)
+{
+    return nem_b200_ex(Fname, nk, algo, beta, convergence, convergence_th, format, it_max, dolog,
+                       model_family, proportion, dispersion, init_mode, NULL);
+}
+
+/* ------------------------------------------------------------------ host loader / writers */
+int nemb_read_files(const char *base, int k, nemb_host_problem *out)
+{
+    if (!base || !out || k < 0) return NEMB_E_ARG;
+    memset(out, 0, sizeof *out);
+    char type = 0, path[4200];
+    int n = 0, d = 0, rc;
+    if ((rc = nemio_read_str(base, stderr, &type, &n, &d, NULL, 0)) != NEMB_OK) return rc;
+    if (type == 'I') { fprintf(stderr, "Image data (type I) is not available in the B200 engine\n"); return NEMB_E_ARG; }
+    out->n = n; out->d = d; out->spatial = type == 'S';
+    out->words_per_row = ((d + 31) / 32 + 3) / 4 * 4;
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    snprintf(path, sizeof path, "%s.dat", base);
+    if ((rc = nemio_read_dat(path, stderr, n, d, out->words_per_row, &out->x_packed,
+                             ncpu > 16 ? 16 : (int)ncpu)) != NEMB_OK) goto fail;
+    if (k > 0) {
+        size_t kd = (size_t)k * d;
+        out->prop = calloc(k, sizeof(float)); out->center = calloc(kd, sizeof(float));
+        out->disp = calloc(kd, sizeof(float));
+        if (!out->prop || !out->center || !out->disp) { rc = NEMB_E_MEMORY; goto fail; }
+        snprintf(path, sizeof path, "%s.m", base);
+        int flag = 0;
+        if ((rc = nemio_read_m(path, stderr, k, d, &flag, out->prop, out->center, out->disp)) != NEMB_OK) goto fail;
+        out->m_flag = flag;
+    }
+    if (out->spatial) {
+        int mx = 0;
+        if ((rc = nemio_read_nei(base, stderr, n, &out->row_ptr, &out->col, &out->wgt, &mx, NULL, 0)) != NEMB_OK) goto fail;
+        out->max_neigh = mx; out->nnz = out->row_ptr[n];
+    }
+    return NEMB_OK;
+fail:
+    nemb_free_host_problem(out);
+    return rc;
+}
+
+void nemb_free_host_problem(nemb_host_problem *p)
+{
+    if (!p) return;
+    free(p->x_packed); free(p->row_ptr); free(p->col); free(p->wgt);
+    free(p->prop); free(p->center); free(p->disp);
+    memset(p, 0, sizeof *p);
+}
+
+int nemb_write_uf(const char *path, int n, int k, const float *t) { return nemio_write_uf(path, stderr, n, k, t); }
+int nemb_write_cf(const char *path, int n, const int32_t *label) { return nemio_write_cf(path, stderr, n, label); }
+int nemb_write_mf(const char *path, int k, int d, double U, double D, double L, double M, float beta,
+                  const float *prop, const float *center, const float *disp)
+{
+    double c4[4] = {U, D, L, M};
+    return nemio_write_mf(path, stderr, k, d, c4, beta, prop, center, disp);
+}

@@ -969,3 +969,121 @@ int nemb_stage_criteria(nemb_handle *h, const nemb_options *o, const double *log
     memcpy(crit6, h->h_status->crit_after, sizeof(double) * 6);
     return NEMB_OK;
 }
+
+/* ------------------------------------------------------------------ init_mode 1: random starts */
+/* RandNemAlgo (nem_alg.c:1574-1742): InitPara's whole-sample dispersion (1247-1265: an M-step
+ * with every family in class 1), then n_starts x { MakeRandomPara (1381-1473): eps = sample
+ * dispersion / K, p = 1/K, centres = distinct random families ; blind+beta sweeps ; NemAlgo },
+ * keep the start with the best criterion M (DEFAULT_CRIT, nem_typ.h:80), final M-step on the
+ * best partition (1715).  The reference draws with libc random() seeded by the wall clock
+ * (nem_exe.c:353,621); we use a documented splitmix64 stream, so parity is statistical. */
+static uint64_t splitmix64(uint64_t *s)
+{
+    uint64_t z = (*s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+int nemb_fit_random(nemb_handle *h, const nemb_options *o, int n_starts, int64_t seed, float *prop,
+                    float *center, float *disp, nemb_result *res)
+{
+    if (!h || !o || !prop || !center || !disp || !res) return NEMB_E_ARG;
+    int rc, k = o->k;
+    CK(cudaSetDevice(h->device));
+    if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if ((rc = ensure_k(h, k)) != NEMB_OK) return rc;
+    if (n_starts <= 0) n_starts = 50;                       /* DEFAULT_NBRANDINITS */
+    uint64_t rng = seed ? (uint64_t)seed : 42;
+    int n = h->n, d = h->d, wpr = h->wpr;
+    size_t kd = (size_t)k * d, nk = (size_t)n * k;
+    memset(res, 0, sizeof *res);
+    h->launches = 0; h->fixup_rounds = 0; h->profile = 0; h->ev_n = 0;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->stream));
+
+    /* whole-sample dispersion under the requested model */
+    float *sam = malloc(sizeof(float) * d), *best_theta = malloc(sizeof(float) * (2 * kd + k));
+    uint32_t *rows = malloc(sizeof(uint32_t) * (size_t)k * wpr);
+    int *picked = malloc(sizeof(int) * k);
+    void *best_state = NULL;
+    size_t state_bytes = o->algo == NEMB_ALGO_NCEM ? (size_t)n : sizeof(float) * nk;
+    CK(cudaMalloc(&best_state, state_bytes));
+    for (size_t q = 0; q < kd; q++) { center[q] = 0.5f; disp[q] = 0.5f; }
+    for (int c = 0; c < k; c++) prop[c] = (float)(1.0 / k);
+    if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
+    h->cur = 0; h->state_labels = o->algo == NEMB_ALGO_NCEM;
+    CK(cudaMemsetAsync(h->d_lab[0], 0, n, h->stream));
+    if (!h->state_labels) { nemk_labels_to_t(h->stream, k, n, h->d_lab[0], h->d_t[0]); CKK(); }
+    if ((rc = run_mstep(h, o)) != NEMB_OK) return rc;
+    CK(cudaMemcpyAsync(sam, h->d_disp, sizeof(float) * d, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+
+    int nsucc = 0, best_try = -1, last_status = NEMB_W_EMPTYCLASS;
+    nemb_result best_res, cur;
+    memset(&best_res, 0, sizeof best_res);
+    for (int s = 0; s < n_starts; s++) {
+        for (int c = 0; c < k; c++) {
+            prop[c] = (float)(1.0 / k);
+            for (int j = 0; j < d; j++) disp[(size_t)c * d + j] = sam[j] / (float)k;
+            int ipt = 0;
+            for (int draw = 0, again = 1; again && draw < 100; draw++) {
+                ipt = (int)(splitmix64(&rng) % (uint64_t)n);
+                CK(cudaMemcpy(rows + (size_t)c * wpr, h->d_x + (size_t)ipt * wpr,
+                              sizeof(uint32_t) * wpr, cudaMemcpyDeviceToHost));
+                again = 0;
+                for (int p = 0; p < c && !again; p++)
+                    if (!memcmp(rows + (size_t)p * wpr, rows + (size_t)c * wpr, sizeof(uint32_t) * wpr))
+                        again = 1;
+            }
+            picked[c] = ipt;
+            for (int j = 0; j < d; j++)
+                center[(size_t)c * d + j] = (float)((rows[(size_t)c * wpr + (j >> 5)] >> (j & 31)) & 1u);
+        }
+        if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
+        memset(&cur, 0, sizeof cur);
+        rc = em_core(h, o, theta_uniform(k, d, center, disp), &cur, NULL, NULL, prop, center, disp);
+        if (rc != NEMB_OK) return rc;
+        last_status = cur.status;
+        if (cur.status != NEMB_OK) continue;
+        nsucc++;
+        if (nsucc == 1 || cur.M > best_res.M) {
+            best_res = cur; best_try = s;
+            memcpy(best_theta, prop, sizeof(float) * k);
+            memcpy(best_theta + k, center, sizeof(float) * kd);
+            memcpy(best_theta + k + kd, disp, sizeof(float) * kd);
+            CK(cudaMemcpyAsync(best_state, o->algo == NEMB_ALGO_NCEM ? (void *)h->d_lab[h->cur]
+                                                                    : (void *)h->d_t[h->cur],
+                               state_bytes, cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
+    if (nsucc > 0) {
+        memcpy(prop, best_theta, sizeof(float) * k);
+        memcpy(center, best_theta + k, sizeof(float) * kd);
+        memcpy(disp, best_theta + k + kd, sizeof(float) * kd);
+        if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
+        h->cur = 0;
+        CK(cudaMemcpyAsync(o->algo == NEMB_ALGO_NCEM ? (void *)h->d_lab[0] : (void *)h->d_t[0],
+                           best_state, state_bytes, cudaMemcpyDeviceToDevice, h->stream));
+        if ((rc = run_mstep(h, o)) != NEMB_OK) return rc;   /* final EstimPara, nem_alg.c:1715 */
+        CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+        *res = best_res;
+        res->status = NEMB_OK;
+        res->best_start = best_try + 1;
+        res->n_success = nsucc;
+    } else {
+        res->status = last_status;
+    }
+    cudaEventRecord(e1, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaEventElapsedTime(&res->fit_ms, e0, e1);
+    res->kernel_launches = h->launches;
+    res->fixup_rounds = h->fixup_rounds;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(best_state);
+    free(sam); free(best_theta); free(rows); free(picked);
+    return res->status;
+}

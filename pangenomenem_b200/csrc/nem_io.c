@@ -1,0 +1,488 @@
+/*
+ * nem_io.c -- the NEM loader (host side) and result writers.
+ *
+ * Readers restate, with the same tolerance, the reference's
+ *   ReadOpeningComments  NEM/lib_io.c:32-87     leading '#' comment lines
+ *   ReadStrFile          NEM/nem_exe.c:739-830  "S|N|I  N  D"
+ *   ReadMatrixFile       NEM/nem_exe.c:834-898  whitespace-separated "%f" tokens, short file = error
+ *   ReadParamFile        NEM/nem_exe.c:973-1091 flag, K-1 proportions, K*D centres, K*D dispersions
+ *   ReadPtsNeighs        NEM/nem_exe.c:1342-1478 weighted flag, then "id nb n_1..n_nb [w_1..w_nb]"
+ * but produce the engine's HBM layout directly: X is bit-packed while it is parsed (never a
+ * float matrix), the neighbour lists become one CSR in file order.
+ * Writers restate SaveResults (NEM/nem_exe.c:1596-1781) format for format.
+ *
+ * Deliberate deviations (all outside what PPanGGOLiN can emit, ppanggolin.py:829-930):
+ *   - .dat cells must be 0 or 1 (Bernoulli data); NaN / other values are rejected with E_FILE
+ *     instead of being carried as floats;
+ *   - a .nei entry is dropped when its index is out of 1..N OR its weight is 0; the reference
+ *     compacts the two lists independently (nem_exe.c:1416-1446) which misaligns such files;
+ *   - a record for a point id outside 1..N is an error (the reference writes out of bounds).
+ */
+#include "nem_io.h"
+#include "nem_b200.h"
+
+#include <ctype.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------ mapped files + tokens */
+typedef struct {
+    const char *p, *end, *base;
+    size_t len;
+} cursor;
+
+static int map_file(const char *path, cursor *c)
+{
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return -1;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return -1; }
+    c->len = (size_t)st.st_size;
+    if (c->len == 0) {
+        c->base = c->p = c->end = "";
+        close(fd);
+        return 0;
+    }
+    void *m = mmap(NULL, c->len, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return -1;
+    madvise(m, c->len, MADV_SEQUENTIAL);
+    c->base = c->p = m;
+    c->end = c->p + c->len;
+    return 0;
+}
+
+static void unmap_file(cursor *c)
+{
+    if (c->len) munmap((void *)c->base, c->len);
+    c->len = 0;
+}
+
+static inline int is_ws(char ch) { return ch == ' ' || (ch >= '\t' && ch <= '\r'); }
+
+static inline int next_token(cursor *c, const char **tok, size_t *len)
+{
+    const char *p = c->p, *e = c->end;
+    while (p < e && is_ws(*p)) p++;
+    if (p >= e) { c->p = p; return 0; }
+    const char *q = p;
+    while (q < e && !is_ws(*q)) q++;
+    *tok = p; *len = (size_t)(q - p);
+    c->p = q;
+    return 1;
+}
+
+static int tok_int(const char *t, size_t len, long *out)
+{
+    char buf[64];
+    if (len == 0 || len >= sizeof buf) return 0;
+    memcpy(buf, t, len); buf[len] = 0;
+    char *endp;
+    errno = 0;
+    long v = strtol(buf, &endp, 10);
+    if (endp == buf || *endp) return 0;
+    *out = v;
+    return 1;
+}
+
+static int tok_float(const char *t, size_t len, float *out)
+{
+    char buf[128];
+    if (len == 0 || len >= sizeof buf) return 0;
+    memcpy(buf, t, len); buf[len] = 0;
+    char *endp;
+    float v = strtof(buf, &endp);
+    if (endp == buf || *endp) return 0;
+    *out = v;
+    return 1;
+}
+
+/* skip the opening lines that start with '#', keep their text (lib_io.c:32-87) */
+static void skip_comments(cursor *c, char *comment, int comment_len)
+{
+    if (comment && comment_len > 0) comment[0] = 0;
+    while (c->p < c->end && *c->p == '#') {
+        const char *q = c->p;
+        while (q < c->end && *q != '\n') q++;
+        if (q < c->end) q++;
+        if (comment) {
+            size_t have = strlen(comment), add = (size_t)(q - c->p - 1);
+            if (have + add + 1 < (size_t)comment_len) {
+                memcpy(comment + have, c->p + 1, add);
+                comment[have + add] = 0;
+            }
+        }
+        c->p = q;
+    }
+}
+
+/* ------------------------------------------------------------------ .str */
+int nemio_read_str(const char *base, FILE *err, char *type, int *n, int *d, char *comment,
+                   int comment_len)
+{
+    char path[4200];
+    snprintf(path, sizeof path, "%s.str", base);
+    cursor c;
+    if (map_file(path, &c) != 0) {
+        fprintf(err, "File str %s does not exist\n", path);
+        return NEMB_E_FILE;
+    }
+    skip_comments(&c, comment, comment_len);
+    const char *t; size_t len; long v[3]; int nf = 0;
+    char ty = 0;
+    if (next_token(&c, &t, &len)) { ty = (char)toupper((unsigned char)t[0]); if (len != 1) ty = 0; }
+    while (nf < 3 && next_token(&c, &t, &len) && tok_int(t, len, &v[nf])) nf++;
+    unmap_file(&c);
+    if (!ty || nf < 2) {
+        fprintf(err, "Structure file (%s) not enough fields\n", path);
+        return NEMB_E_FILE;
+    }
+    if (ty == 'I') {
+        if (nf < 3) { fprintf(err, "Structure file (%s) not enough fields\n", path); return NEMB_E_FILE; }
+        *type = 'I'; *n = (int)(v[0] * v[1]); *d = (int)v[2];
+        return NEMB_OK;
+    }
+    if (ty != 'S' && ty != 'N') {
+        fprintf(err, "Data type %c unknown in file %s\n", ty, path);
+        return NEMB_E_FILE;
+    }
+    *type = ty; *n = (int)v[0]; *d = (int)v[1];
+    if (*n <= 0 || *d <= 0) {
+        fprintf(err, "Structure file (%s): N and D must be > 0\n", path);
+        return NEMB_E_FILE;
+    }
+    return NEMB_OK;
+}
+
+/* ------------------------------------------------------------------ .dat -> packed bits */
+typedef struct {
+    const char *src; int d, wpr, r0, r1; uint32_t *out; int bad;
+} dat_job;
+
+/* fast path: PPanGGOLiN's exact layout, one char per cell + one separator (ppanggolin.py:850) */
+static void *dat_worker(void *arg)
+{
+    dat_job *j = arg;
+    int d = j->d, wpr = j->wpr;
+    size_t stride = (size_t)2 * d;
+    for (int r = j->r0; r < j->r1; r++) {
+        const unsigned char *p = (const unsigned char *)j->src + (size_t)r * stride;
+        uint32_t *o = j->out + (size_t)r * wpr;
+        unsigned bad = 0;
+        for (int w = 0; w * 32 < d; w++) {
+            int nb = d - w * 32 < 32 ? d - w * 32 : 32;
+            uint32_t word = 0;
+            const unsigned char *q = p + (size_t)w * 64;
+            for (int b = 0; b < nb; b++) {
+                unsigned ch = q[2 * b];
+                bad |= (ch | 1u) ^ '1';
+                bad |= !is_ws((char)q[2 * b + 1]);
+                word |= (uint32_t)(ch & 1u) << b;
+            }
+            o[w] = word;
+        }
+        if (bad) { j->bad = 1; return NULL; }
+    }
+    return NULL;
+}
+
+int nemio_read_dat(const char *path, FILE *err, int n, int d, int wpr, uint32_t **packed_out,
+                   int n_threads)
+{
+    cursor c;
+    *packed_out = NULL;
+    if (map_file(path, &c) != 0) {
+        fprintf(err, "File matrix %s does not exist\n", path);
+        return NEMB_E_FILE;
+    }
+    uint32_t *out = calloc((size_t)n * wpr, sizeof(uint32_t));
+    if (!out) { unmap_file(&c); return NEMB_E_MEMORY; }
+    size_t want = (size_t)n * 2 * d;
+    int done = 0;
+    if (c.len == want || c.len + 1 == want) {
+        /* the last separator may be missing: pad-check it separately */
+        int last_missing = (c.len + 1 == want);
+        if (n_threads < 1) n_threads = 1;
+        if (n_threads > 64) n_threads = 64;
+        if (n < 4096) n_threads = 1;
+        pthread_t th[64]; dat_job jobs[64];
+        int rows = last_missing ? n - 1 : n;
+        for (int t = 0; t < n_threads; t++) {
+            jobs[t] = (dat_job){c.base, d, wpr, (int)((long long)rows * t / n_threads),
+                                (int)((long long)rows * (t + 1) / n_threads), out, 0};
+            if (n_threads > 1) pthread_create(&th[t], NULL, dat_worker, &jobs[t]);
+            else dat_worker(&jobs[t]);
+        }
+        int bad = 0;
+        for (int t = 0; t < n_threads; t++) {
+            if (n_threads > 1) pthread_join(th[t], NULL);
+            bad |= jobs[t].bad;
+        }
+        done = !bad && !last_missing;
+    }
+    if (!done) { /* general tokenizer: any whitespace, any float spelling of 0 / 1 */
+        memset(out, 0, (size_t)n * wpr * sizeof(uint32_t));
+        c.p = c.base;
+        const char *t; size_t len;
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j < d; j++) {
+                float v;
+                if (!next_token(&c, &t, &len)) {
+                    fprintf(err, "%s : short file (%d/%d lines and %d/%d columns)\n", path, i, n, j, d);
+                    free(out); unmap_file(&c);
+                    return NEMB_E_FILE;
+                }
+                int bit;
+                if (len == 1 && (t[0] == '0' || t[0] == '1')) bit = t[0] - '0';
+                else if (tok_float(t, len, &v) && (v == 0.0f || v == 1.0f)) bit = (v == 1.0f);
+                else {
+                    fprintf(err, "%s : value '%.*s' at line %d column %d is not 0 or 1 "
+                                 "(Bernoulli engine: binary data without missing values only)\n",
+                            path, (int)(len > 32 ? 32 : len), t, i + 1, j + 1);
+                    free(out); unmap_file(&c);
+                    return NEMB_E_FILE;
+                }
+                if (bit) out[(size_t)i * wpr + (j >> 5)] |= 1u << (j & 31);
+            }
+        }
+    }
+    unmap_file(&c);
+    *packed_out = out;
+    return NEMB_OK;
+}
+
+/* ------------------------------------------------------------------ .m */
+int nemio_read_m(const char *path, FILE *err, int k, int d, int *flag, float *prop, float *center,
+                 float *disp)
+{
+    cursor c;
+    if (map_file(path, &c) != 0) {
+        fprintf(err, "File param %s does not exist\n", path);
+        return NEMB_E_FILE;
+    }
+    int nbvalues = 1 + (k - 1) + 2 * k * d, rc = NEMB_OK;
+    const char *t; size_t len; long fl; float v;
+#define NEED_TOKEN()                                                                          \
+    if (!next_token(&c, &t, &len)) {                                                          \
+        fprintf(err, "The file %s needs at least %d values (%d missing)\n", path,             \
+                1 + (k - 1) + 2 * k * d, nbvalues);                                           \
+        unmap_file(&c);                                                                       \
+        return NEMB_E_FILE;                                                                   \
+    }                                                                                         \
+    nbvalues--
+    NEED_TOKEN();
+    if (!tok_int(t, len, &fl) || (fl != 1 && fl != 2)) {
+        fprintf(err, "First line of file %s must be 1 (parameters at beginning) or 2 (fixed "
+                     "parameters throughout the clustering process) \n", path);
+        unmap_file(&c);
+        return NEMB_E_FILE;
+    }
+    *flag = (int)fl;
+    float pk = 1.0f;
+    for (int i = 0; i < k - 1; i++) {
+        NEED_TOKEN();
+        if (!tok_float(t, len, &v)) goto bad;
+        prop[i] = v;
+        pk = pk - prop[i];                      /* float, nem_exe.c:1032 */
+    }
+    prop[k - 1] = pk;
+    if (pk <= 0.0f) { fprintf(err, "Last class has pK = %5.2f <= 0\n", pk); rc = NEMB_E_FILE; }
+    for (int i = 0; i < k * d; i++) {
+        NEED_TOKEN();
+        if (!tok_float(t, len, &v)) goto bad;
+        center[i] = v;
+    }
+    for (int i = 0; i < k * d; i++) {
+        NEED_TOKEN();
+        if (!tok_float(t, len, &v)) goto bad;
+        disp[i] = v;
+        if (!(v > 0)) {
+            fprintf(err, "Dispersion(k=%d, d=%d) = %5.3f <= 0\n", i / d + 1, i % d + 1, v);
+            rc = NEMB_E_FILE;
+        }
+    }
+    if (next_token(&c, &t, &len)) {
+        fprintf(err, "The file %s needs do not need more than %d values\n", path, 1 + (k - 1) + 2 * k * d);
+        rc = NEMB_E_FILE;
+    }
+    unmap_file(&c);
+    return rc;
+bad:
+    fprintf(err, "The file %s holds a token that is not a number: '%.*s'\n", path,
+            (int)(len > 32 ? 32 : len), t);
+    unmap_file(&c);
+    return NEMB_E_FILE;
+#undef NEED_TOKEN
+}
+
+/* ------------------------------------------------------------------ .nei -> CSR */
+int nemio_read_nei(const char *base, FILE *err, int n, int32_t **row_ptr_out, int32_t **col_out,
+                   float **wgt_out, int *max_neigh, char *comment, int comment_len)
+{
+    char path[4200];
+    snprintf(path, sizeof path, "%s.nei", base);
+    cursor c;
+    *row_ptr_out = NULL; *col_out = NULL; *wgt_out = NULL; *max_neigh = 0;
+    if (map_file(path, &c) != 0) {
+        fprintf(err, "File Neigh %s File does not exist\n", path);
+        return NEMB_E_FILE;
+    }
+    skip_comments(&c, comment, comment_len);
+    const char *t; size_t len; long v;
+    int weighted = 0, rc = NEMB_OK;
+    if (next_token(&c, &t, &len) && tok_int(t, len, &v)) weighted = v != 0;
+
+    /* records land in a scratch pool; start[i]/cnt[i] point at the LAST record of point i */
+    size_t cap = 1 << 16, used = 0;
+    int32_t *pool_c = malloc(cap * sizeof(int32_t));
+    float *pool_w = malloc(cap * sizeof(float));
+    int64_t *start = malloc(sizeof(int64_t) * (size_t)n);
+    int32_t *cnt = calloc((size_t)n, sizeof(int32_t));
+    if (!pool_c || !pool_w || !start || !cnt) { rc = NEMB_E_MEMORY; goto out; }
+    for (int i = 0; i < n; i++) start[i] = 0;
+    int line = 0;
+    while (next_token(&c, &t, &len)) {
+        long id, nb;
+        if (!tok_int(t, len, &id)) break;                 /* reference: loop just ends */
+        if (!next_token(&c, &t, &len) || !tok_int(t, len, &nb)) break;
+        if (id < 1 || id > n || nb < 0) {
+            fprintf(err, "Error in neighb. file l.%d : point id %ld out of 1..%d\n", line, id, n);
+            rc = NEMB_E_FILE; goto out;
+        }
+        if (used + (size_t)nb > cap) {
+            while (used + (size_t)nb > cap) cap *= 2;
+            pool_c = realloc(pool_c, cap * sizeof(int32_t));
+            pool_w = realloc(pool_w, cap * sizeof(float));
+            if (!pool_c || !pool_w) { rc = NEMB_E_MEMORY; goto out; }
+        }
+        size_t s0 = used;
+        for (long q = 0; q < nb; q++) {
+            long nbr;
+            if (!next_token(&c, &t, &len) || !tok_int(t, len, &nbr)) {
+                fprintf(err, "Error in neighb. file l.%d : neighbor %ld\n", line, q);
+                rc = NEMB_E_FILE; goto out;
+            }
+            pool_c[s0 + q] = (int32_t)nbr;
+            pool_w[s0 + q] = 1.0f;
+        }
+        if (weighted) {
+            for (long q = 0; q < nb; q++) {
+                float w;
+                if (!next_token(&c, &t, &len) || !tok_float(t, len, &w)) {
+                    fprintf(err, "Error in neighb. file l.%d : weight %ld\n", line, q);
+                    rc = NEMB_E_FILE; goto out;
+                }
+                pool_w[s0 + q] = w;
+            }
+        }
+        /* compact: keep entries with a valid index and a non-zero weight */
+        size_t nv = 0;
+        for (long q = 0; q < nb; q++) {
+            int32_t nbr = pool_c[s0 + q]; float w = pool_w[s0 + q];
+            if (nbr >= 1 && nbr <= n && w != 0.0f) {
+                pool_c[s0 + nv] = nbr - 1; pool_w[s0 + nv] = w; nv++;
+            }
+        }
+        start[id - 1] = (int64_t)s0; cnt[id - 1] = (int32_t)nv;
+        used = s0 + nv;
+        line++;
+    }
+    {
+        int32_t *rp = malloc(sizeof(int32_t) * ((size_t)n + 1));
+        int64_t nnz = 0;
+        for (int i = 0; i < n; i++) nnz += cnt[i];
+        if (nnz > 2147483647LL) { fprintf(err, "neighbourhood too large\n"); rc = NEMB_E_FILE; free(rp); goto out; }
+        int32_t *cl = malloc(sizeof(int32_t) * (size_t)(nnz ? nnz : 1));
+        float *wg = malloc(sizeof(float) * (size_t)(nnz ? nnz : 1));
+        if (!rp || !cl || !wg) { rc = NEMB_E_MEMORY; free(rp); free(cl); free(wg); goto out; }
+        int32_t o = 0, mx = 0;
+        for (int i = 0; i < n; i++) {
+            rp[i] = o;
+            memcpy(cl + o, pool_c + start[i], sizeof(int32_t) * (size_t)cnt[i]);
+            memcpy(wg + o, pool_w + start[i], sizeof(float) * (size_t)cnt[i]);
+            o += cnt[i];
+            if (cnt[i] > mx) mx = cnt[i];
+        }
+        rp[n] = o;
+        *row_ptr_out = rp; *col_out = cl; *wgt_out = wg; *max_neigh = mx;
+    }
+out:
+    free(pool_c); free(pool_w); free(start); free(cnt);
+    unmap_file(&c);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ writers */
+/* " %5.3f " of a value in [0,1], rounded like printf (exact product, ties to even) */
+static inline char *put_uf(char *p, float v)
+{
+    if (!(v >= 0.0f && v <= 1.0f)) return p + sprintf(p, " %5.3f ", (double)v);
+    double y = (double)v * 1000.0;            /* exact: 24-bit x 10-bit mantissas */
+    double fl = floor(y), fr = y - fl;
+    long q = (long)fl;
+    if (fr > 0.5 || (fr == 0.5 && (q & 1))) q++;
+    p[0] = ' '; p[1] = (char)('0' + q / 1000); p[2] = '.';
+    p[3] = (char)('0' + (q / 100) % 10); p[4] = (char)('0' + (q / 10) % 10);
+    p[5] = (char)('0' + q % 10); p[6] = ' ';
+    return p + 7;
+}
+
+int nemio_write_uf(const char *path, FILE *err, int n, int k, const float *t)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) { fprintf(err, "Could not open file '%s' in write mode\n", path); return NEMB_E_FILE; }
+    size_t per = (size_t)k * 32 + 2, rows = 4096;
+    char *buf = malloc(per * rows);
+    if (!buf) { fclose(f); return NEMB_E_MEMORY; }
+    for (int i0 = 0; i0 < n; i0 += (int)rows) {
+        char *p = buf;
+        int i1 = i0 + (int)rows < n ? i0 + (int)rows : n;
+        for (int i = i0; i < i1; i++) {
+            for (int c = 0; c < k; c++) p = put_uf(p, t[(size_t)i * k + c]);
+            *p++ = '\n';
+        }
+        fwrite(buf, 1, (size_t)(p - buf), f);
+    }
+    free(buf);
+    fclose(f);
+    return NEMB_OK;
+}
+
+int nemio_write_cf(const char *path, FILE *err, int n, const int32_t *label)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) { fprintf(err, "Could not open file '%s' in write mode\n", path); return NEMB_E_FILE; }
+    for (int i = 0; i < n; i++) fprintf(f, "%d ", label[i] + 1);   /* nem_exe.c:1652 */
+    fprintf(f, "\n");
+    fclose(f);
+    return NEMB_OK;
+}
+
+int nemio_write_mf(const char *path, FILE *err, int k, int d, const double crit[4], float beta,
+                   const float *prop, const float *center, const float *disp)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) { fprintf(err, "Could not open file '%s' in write mode\n", path); return NEMB_E_FILE; }
+    /* nem_exe.c:1708-1773; criteria are float in the reference (CriterT), error rate is NaN */
+    fprintf(f, "Criteria U=NEM, D=Hathaway, L=mixture, M=markov ps-like, error\n\n");
+    fprintf(f, "  %g    %g    %g    %g   %g\n\n", (double)(float)crit[0], (double)(float)crit[1],
+            (double)(float)crit[2], (double)(float)crit[3], (double)NAN);
+    fprintf(f, "Beta (%s)\n", "fixed");
+    fprintf(f, "  %6.4f\n", (double)beta);
+    fprintf(f, "Mu (%d), Pk, and disp (%d) of the %d classes\n\n", d, d, k);
+    for (int c = 0; c < k; c++) {
+        for (int j = 0; j < d; j++) fprintf(f, " %10.3g ", (double)center[(size_t)c * d + j]);
+        fprintf(f, "  %5.3g  ", (double)prop[c]);
+        for (int j = 0; j < d; j++) fprintf(f, " %10g ", (double)disp[(size_t)c * d + j]);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return NEMB_OK;
+}
