@@ -71,6 +71,12 @@ void nemk_sweep_ncem_fixup(nemk_stream s, int k, int n, const double *logpf, con
                            const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a,
                            int32_t *wl_b, int32_t *wl_counts, const int32_t *rrow_ptr,
                            const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
+void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, const double *logpf, const int32_t *row_ptr,
+                                 const int32_t *col, const float *wgt, double beta,
+                                 const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty,
+                                 const int32_t *cur_list, int32_t *next_list,
+                                 const int32_t *cur_cnt, int32_t *next_cnt, const int32_t *rrow_ptr,
+                                 const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
 void nemk_sweep_ncem_level(nemk_stream s, int k, const double *logpf, const int32_t *row_ptr,
                            const int32_t *col, const float *wgt, double beta, uint8_t *lab,
                            const int32_t *sites, const int32_t *level_ptr, int lv_lo, int lv_hi,

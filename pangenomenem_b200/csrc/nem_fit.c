@@ -412,8 +412,8 @@ static int ensure_k(nemb_handle *h, int k)
     }
     CK(cudaMalloc((void **)&h->d_dirty, sizeof(int32_t) * n));
     CK(cudaMemset(h->d_dirty, 0, sizeof(int32_t) * n));
-    CK(cudaMalloc((void **)&h->d_wl_counts, sizeof(int32_t) * 2));
-    CK(cudaMemset(h->d_wl_counts, 0, sizeof(int32_t) * 2));
+    CK(cudaMalloc((void **)&h->d_wl_counts, sizeof(int32_t) * 8));
+    CK(cudaMemset(h->d_wl_counts, 0, sizeof(int32_t) * 8));
     CK(cudaMalloc((void **)&h->d_cm, sizeof(uint32_t) * (size_t)k * h->nwt));
     CK(cudaMalloc((void **)&h->d_nk_int, sizeof(int32_t) * k));
     CK(cudaMalloc((void **)&h->d_s_int, sizeof(int32_t) * kd));
@@ -518,13 +518,23 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
             h->launches++;
             *flipped = 1;
         } else if (impl == NEMB_SWEEP_SPEC) {
+            /* round 0 (Jacobi) fills list 0; GRID_ROUNDS grid-wide rounds ping-pong the two lists
+             * through per-round counters (all zeroed above); one CTA finishes the tail */
+            enum { GRID_ROUNDS = 3 };
+            CK(cudaMemsetAsync(h->d_wl_counts, 0, sizeof(int32_t) * 8, h->stream));
             nemk_sweep_ncem_jacobi(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
                                    out, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
                                    h->d_rcol, &h->d_status->cnt, skip);
+            for (int r = 0; r < GRID_ROUNDS; r++)
+                nemk_sweep_ncem_fixup_round(h->stream, k, h->d_logpf, rp, h->d_col, h->d_wgt, beta,
+                                            in, out, h->d_dirty, h->d_wl[r & 1], h->d_wl[(r + 1) & 1],
+                                            &h->d_wl_counts[r], &h->d_wl_counts[r + 1],
+                                            h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip);
             nemk_sweep_ncem_fixup(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
-                                  out, h->d_dirty, h->d_wl[0], h->d_wl[1], h->d_wl_counts,
+                                  out, h->d_dirty, h->d_wl[GRID_ROUNDS & 1],
+                                  h->d_wl[(GRID_ROUNDS + 1) & 1], &h->d_wl_counts[GRID_ROUNDS],
                                   h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip);
-            h->launches += 2;
+            h->launches += 2 + GRID_ROUNDS;
             *flipped = 1;
         } else {
             for (int s = 0; s < h->n_steps; s++) {

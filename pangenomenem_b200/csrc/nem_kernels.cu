@@ -19,6 +19,8 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #define NEM_EPSILON 1e-20  // nem_typ.h:65
 #define FULL 0xffffffffu
@@ -107,7 +109,7 @@ __global__ void k_transpose_bits(const uint32_t *__restrict__ x, int n, int wpr,
 // theta -> per-class tables.  DensBernoulli's per-variable term (nem_mod.c:656-670):
 //   absdif = abs((int)(x - mu));  disp > EPSILON: absdif*log((1-disp)/disp) - log(1-disp)
 //   else absdif != 0 -> zero density.   (1-disp)/disp and 1-disp are FLOAT expressions there.
-// one CTA; class after class, variables in parallel.
+// one CTA per class, variables in parallel.
 // =============================================================================================
 #define TT_THREADS 1024
 __global__ void __launch_bounds__(TT_THREADS)
@@ -118,8 +120,8 @@ k_theta_tables(int K, int D, int wpr, const float *__restrict__ prop,
     __shared__ double sh[32];
     __shared__ int sh_ok;
     int tid = threadIdx.x, lane = tid & 31;
-    int all_ok = 1;
-    for (int k = 0; k < K; k++) {
+    {
+        const int k = blockIdx.x;
         if (tid == 0) sh_ok = 1;
         __syncthreads();
         const float e0 = disp[(size_t)k * D];
@@ -172,11 +174,9 @@ k_theta_tables(int K, int D, int wpr, const float *__restrict__ prop,
                 coef->a[k] = 0.0; coef->base[k] = base_g; coef->forb[k] = 0;
             }
             delta[(size_t)K * D + k] = base_g;  // general-path base: sum_d cost0_kd
+            if (!sh_ok) atomicAnd(&coef->uniform_ok, 0);   // preset to non-zero by the launcher
         }
-        all_ok &= sh_ok;
-        __syncthreads();
     }
-    if (tid == 0) coef->uniform_ok = all_ok;
 }
 
 // =============================================================================================
@@ -229,6 +229,240 @@ k_density_uniform(int K, const uint4 *__restrict__ x, int n, int wpr4,
                     logpf[(size_t)row * K + k] = v;
                     if (hamming) hamming[(size_t)row * K + k] = h[k];
                 }
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// E-step density, popcount path, v2: TMA-staged row tiles + one thread per family.
+//
+// v1 above spends its time on shared-memory mask reads (6 LDS.128 per 16 B of X) and on the
+// quarter-rate POPC (XU) pipe (ncu: profiles/r1_c4_v1_ncu_summary.csv).  Here
+//   - a tile of ROWS families is copied to shared memory by cp.async.bulk (TMA, one bulk copy
+//     per family, 16-byte granules, completion on an mbarrier), double buffered, so the HBM
+//     stream never waits on the ALUs;
+//   - the shared row stride is an ODD number of uint4, which makes "lane r reads chunk c of
+//     row r" a conflict-free LDS.128;
+//   - every lane is at the same chunk at the same time, so the class masks are warp-uniform
+//     (broadcast LDS.128, one wavefront);
+//   - popcounts go through carry-save adders: per class  ones' = ones^a^b, carry = maj(ones,a,b)
+//     (2 LOP3 on the full-rate ALU pipe) and ONE popc(carry) per two words instead of two.
+// H_ik = 2*sum popc(carry) + popc(ones).  Same arithmetic result as v1 (integers).
+// =============================================================================================
+static __device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+static __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+static __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+static __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                                uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+static __device__ __forceinline__ uint32_t lop_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    return a ^ b ^ c;
+}
+static __device__ __forceinline__ uint32_t lop_maj3(uint32_t a, uint32_t b, uint32_t c) {
+    return (a & b) | (c & (a | b));
+}
+
+// ROWS families per tile, T column groups per family: thread (r, t) owns the chunks
+// [t*wpr4/T, (t+1)*wpr4/T) of family r, so that t (hence the mask address) is warp-uniform and
+// lane r reads chunk c of row r (odd stride => conflict-free).  Partial counts meet in shared
+// memory through integer atomics; ONE block barrier per tile; the epilogue of tile i (log-density
+// + store) runs after that barrier, overlapped with the other warps starting tile i+1.
+template <int KT, int ROWS, int T, bool EXACT>
+__global__ void __launch_bounds__(ROWS *T)
+k_density_tma(int K, const uint4 *__restrict__ x, int n, int wpr4, int stride4, int n_tiles,
+              int n_stages, const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
+              const uint4 *__restrict__ mval, double *__restrict__ logpf,
+              int32_t *__restrict__ hamming) {
+    if (coef->empty_class) return;
+    extern __shared__ __align__(128) uint4 dsm[];
+    __shared__ __align__(8) uint64_t bars[16];
+    __shared__ int hsum[2][ROWS * KT];
+    uint4 *smask = dsm;                                // [wpr4][KT][2] (xor, valid)
+    uint4 *tiles = dsm + (size_t)2 * KT * wpr4;        // n_stages x ROWS x stride4 ring
+    const int tid = threadIdx.x;
+    const int r = tid % ROWS, t = tid / ROWS;
+    const int kk = EXACT ? KT : K;
+    for (int i = tid; i < KT * wpr4; i += ROWS * T) {
+        int c = i / KT, k = i % KT;
+        bool live = k < K;
+        smask[2 * i] = live ? mxor[k * wpr4 + c] : make_uint4(0, 0, 0, 0);
+        smask[2 * i + 1] = live ? mval[k * wpr4 + c] : make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < 2 * ROWS * KT; i += ROWS * T) (&hsum[0][0])[i] = 0;
+    if (tid == 0) {
+        for (int q = 0; q < n_stages; q++) mbar_init(&bars[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t row_bytes = (uint32_t)wpr4 * 16u;
+    const int c_lo = (int)((long long)wpr4 * t / T), c_hi = (int)((long long)wpr4 * (t + 1) / T);
+    auto issue = [&](int tile, int stage) {
+        long long r0 = (long long)tile * ROWS;
+        int rows = (int)min((long long)ROWS, (long long)n - r0);
+        if (tid == 0) mbar_expect_tx(&bars[stage], (uint32_t)rows * row_bytes);
+        if (tid < rows)
+            bulk_g2s(tiles + ((size_t)stage * ROWS + tid) * stride4, x + (size_t)(r0 + tid) * wpr4,
+                     row_bytes, &bars[stage]);
+    };
+    auto epilogue = [&](int tile, int slot) {   // threads of column group 0 only
+        long long row = (long long)tile * ROWS + r;
+#pragma unroll
+        for (int k = 0; k < KT; k++) {
+            int h = hsum[slot][r * KT + k];
+            hsum[slot][r * KT + k] = 0;
+            if (k < kk && row < n) {
+                double lp = coef->lp[k], val;
+                if (coef->forb[k]) val = h ? neg_inf() : lp;
+                else val = lp - (coef->a[k] * (double)h + coef->base[k]);
+                logpf[(size_t)row * K + k] = val;
+                if (hamming) hamming[(size_t)row * K + k] = h;
+            }
+        }
+    };
+    // ring of n_stages tiles: n_stages-1 bulk loads stay in flight behind the tile being counted
+    int tile = blockIdx.x, it = 0, prev_tile = -1;
+    for (int q = 0; q < n_stages - 1; q++) {
+        long long tq = (long long)tile + (long long)q * gridDim.x;
+        if (tq < n_tiles) issue((int)tq, q);
+    }
+    for (; tile < n_tiles; tile += gridDim.x, it++) {
+        int stage = it % n_stages;
+        long long next = (long long)tile + (long long)(n_stages - 1) * gridDim.x;
+        if (next < n_tiles) issue((int)next, (it + n_stages - 1) % n_stages);
+        if (t == 0 && prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1);
+        mbar_wait(&bars[stage], (uint32_t)((it / n_stages) & 1));
+        long long row = (long long)tile * ROWS + r;
+        uint32_t ones[KT], cnt2[KT];
+#pragma unroll
+        for (int k = 0; k < KT; k++) { ones[k] = 0u; cnt2[k] = 0u; }
+        if (row < n) {
+            const uint4 *xr = tiles + ((size_t)stage * ROWS + r) * stride4;
+#pragma unroll 2
+            for (int c = c_lo; c < c_hi; c++) {
+                uint4 v = xr[c];
+                const uint4 *mk = smask + (size_t)2 * KT * c;
+#pragma unroll
+                for (int k = 0; k < KT; k++) {
+                    if (EXACT || k < kk) {
+                        uint4 a = mk[2 * k], b = mk[2 * k + 1];
+                        uint32_t m0 = (v.x ^ a.x) & b.x, m1 = (v.y ^ a.y) & b.y;
+                        uint32_t m2 = (v.z ^ a.z) & b.z, m3 = (v.w ^ a.w) & b.w;
+                        uint32_t c0 = lop_maj3(ones[k], m0, m1);
+                        uint32_t o1 = lop_xor3(ones[k], m0, m1);
+                        uint32_t c1 = lop_maj3(o1, m2, m3);
+                        ones[k] = lop_xor3(o1, m2, m3);
+                        cnt2[k] += __popc(c0) + __popc(c1);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KT; k++) {
+            int h = (int)(2u * cnt2[k]) + __popc(ones[k]);
+            if (T > 1) { if (h) atomicAdd(&hsum[it & 1][r * KT + k], h); }
+            else hsum[it & 1][r * KT + k] = h;
+        }
+        prev_tile = tile;
+        __syncthreads();  // the stage is free again and hsum[it&1] is complete
+    }
+    if (t == 0 && prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1);
+}
+
+// =============================================================================================
+// E-step density, popcount path, v3 "direct": one lane per family, no staging, no barriers.
+// Lane r walks its own row 16 bytes at a time with PF loads in flight; two consecutive chunks
+// share a 32-byte sector, so every sector is fetched from L2 once and hit in L1 once (X is read
+// from HBM exactly once).  Every lane of a warp is at the same chunk => warp-uniform class masks
+// (broadcast LDS.128) and carry-save popcounts as in v2.  Warps are fully independent: latency is
+// hidden by (warps x PF) outstanding 16-byte loads, not by a tile pipeline.
+// =============================================================================================
+template <int KT, bool EXACT, int PF>
+__global__ void __launch_bounds__(256)
+k_density_direct(int K, const uint4 *__restrict__ x, int n, int wpr4,
+                 const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
+                 const uint4 *__restrict__ mval, double *__restrict__ logpf,
+                 int32_t *__restrict__ hamming) {
+    if (coef->empty_class) return;
+    extern __shared__ __align__(16) uint4 dsm2[];
+    uint4 *smask = dsm2;  // [wpr4][KT][2] (xor, valid): the 2*KT masks of a chunk are contiguous
+    for (int i = threadIdx.x; i < KT * wpr4; i += blockDim.x) {
+        int c = i / KT, k = i % KT;
+        bool live = k < K;
+        smask[2 * i] = live ? mxor[k * wpr4 + c] : make_uint4(0, 0, 0, 0);
+        smask[2 * i + 1] = live ? mval[k * wpr4 + c] : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const int kk = EXACT ? KT : K;
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n;
+         row += (long long)gridDim.x * blockDim.x) {
+        const uint4 *xr = x + (size_t)row * wpr4;
+        uint32_t ones[KT], cnt2[KT];
+#pragma unroll
+        for (int k = 0; k < KT; k++) { ones[k] = 0u; cnt2[k] = 0u; }
+        uint4 buf[PF];
+#pragma unroll
+        for (int q = 0; q < PF; q++) buf[q] = (q < wpr4) ? __ldg(xr + q) : make_uint4(0, 0, 0, 0);
+        for (int c0 = 0; c0 < wpr4; c0 += PF) {
+#pragma unroll
+            for (int q = 0; q < PF; q++) {
+                int c = c0 + q;
+                uint4 v = buf[q];
+                if (c + PF < wpr4) buf[q] = __ldg(xr + c + PF);
+                if (c < wpr4) {
+                    const uint4 *mk = smask + (size_t)2 * KT * c;
+#pragma unroll
+                    for (int k = 0; k < KT; k++) {
+                        if (EXACT || k < kk) {
+                            uint4 a = mk[2 * k], b = mk[2 * k + 1];
+                            uint32_t m0 = (v.x ^ a.x) & b.x, m1 = (v.y ^ a.y) & b.y;
+                            uint32_t m2 = (v.z ^ a.z) & b.z, m3 = (v.w ^ a.w) & b.w;
+                            uint32_t c0_ = lop_maj3(ones[k], m0, m1);
+                            uint32_t o1 = lop_xor3(ones[k], m0, m1);
+                            uint32_t c1_ = lop_maj3(o1, m2, m3);
+                            ones[k] = lop_xor3(o1, m2, m3);
+                            cnt2[k] += __popc(c0_) + __popc(c1_);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KT; k++) {
+            if (k < kk) {
+                int h = (int)(2u * cnt2[k]) + __popc(ones[k]);
+                double lp = coef->lp[k], val;
+                if (coef->forb[k]) val = h ? neg_inf() : lp;
+                else val = lp - (coef->a[k] * (double)h + coef->base[k]);
+                logpf[(size_t)row * K + k] = val;
+                if (hamming) hamming[(size_t)row * K + k] = h;
             }
         }
     }
@@ -299,7 +533,10 @@ struct SiteCtx {
     double v[KT];
 };
 
-// context from hard labels: ctx_k = sum_j w_ij [lab_j == k]; `pick(j)` returns neighbour j's label
+// context from hard labels: ctx_k = sum_j w_ij [lab_j == k]; `pick(j)` returns neighbour j's label.
+// Neighbours are fetched four at a time (indices, weights, then the four label gathers together) so
+// a site costs ~3 dependent memory round trips instead of 2 per neighbour; the sum order stays the
+// file order (SumNeighsOfClass, nem_alg.c:2865-2875).
 template <int KT, typename Pick>
 static __device__ __forceinline__ void ctx_labels(int K, int i, const int32_t *__restrict__ row_ptr,
                                                   const int32_t *__restrict__ col,
@@ -309,13 +546,24 @@ static __device__ __forceinline__ void ctx_labels(int K, int i, const int32_t *_
     for (int k = 0; k < KT; k++) ctx[k] = 0.0;
     if (!row_ptr) return;
     int lo = row_ptr[i], hi = row_ptr[i + 1];
-    for (int e = lo; e < hi; e++) {
-        int j = col[e];
-        unsigned l = pick(j);
-        double w = (double)wgt[e];
+    for (int e = lo; e < hi; e += 4) {
+        int j[4];
+        float w[4];
+        unsigned l[4];
 #pragma unroll
-        for (int k = 0; k < KT; k++)
-            if (l == (unsigned)k) ctx[k] += w;
+        for (int q = 0; q < 4; q++) {
+            bool in = e + q < hi;
+            j[q] = in ? col[e + q] : -1;
+            w[q] = in ? wgt[e + q] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) l[q] = j[q] >= 0 ? pick(j[q]) : 255u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int k = 0; k < KT; k++)
+                if (l[q] == (unsigned)k) ctx[k] += (double)w[q];
+        }
     }
 }
 
@@ -383,7 +631,7 @@ k_sweep_ncem_jacobi(int K, int n, const double *__restrict__ logpf,
     }
 }
 
-// ---- ncem, speculative sequential sweep, fix-up rounds (ONE CTA, no host round trips).
+// ---- ncem, speculative sequential sweep, fix-up rounds (no host round trips).
 // The in-place index-order sweep (UPDATE_SEQ, nem_alg.c:2378-2383) defines
 //     cur_i = F_i( cur_j for j<i , old_j for j>=i )
 // a triangular system with a unique solution.  Round 0 (the Jacobi kernel) evaluates F with old
@@ -392,18 +640,65 @@ k_sweep_ncem_jacobi(int K, int n, const double *__restrict__ logpf,
 // the data term dominates).  A site clears its dirty flag BEFORE reading its inputs and every
 // change re-queues its later readers AFTER publishing the new label, so no update is lost and
 // the fixed point reached is the sequential sweep's result whatever the interleaving.
+// The first rounds (long work lists) run grid-wide, one launch per round; the tail runs in one
+// CTA that loops until the list is empty.
+template <int KT>
+static __device__ __forceinline__ int fixup_site(int K, int i, const double *__restrict__ logpf,
+                                                 const int32_t *__restrict__ row_ptr,
+                                                 const int32_t *__restrict__ col,
+                                                 const float *__restrict__ wgt, double beta,
+                                                 const uint8_t *__restrict__ lab_old,
+                                                 uint8_t *lab_cur, int32_t *dirty, int32_t *next_list,
+                                                 int32_t *next_cnt,
+                                                 const int32_t *__restrict__ rrow_ptr,
+                                                 const int32_t *__restrict__ rcol) {
+    atomicExch(&dirty[i], 0);
+    __threadfence();
+    double ctx[KT];
+    ctx_labels<KT>(K, i, row_ptr, col, wgt,
+                   [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
+    int flags;
+    int km = site_argmax<KT>(K, logpf + (size_t)i * K, ctx, beta, flags);
+    int was = __ldcg(lab_cur + i);
+    if (km == was) return 0;
+    lab_cur[i] = (uint8_t)km;
+    __threadfence();
+    mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt);
+    int old = lab_old[i];
+    return (km != old) - (was != old);
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+k_sweep_ncem_fixup_round(int K, const double *__restrict__ logpf,
+                         const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                         const float *__restrict__ wgt, double beta,
+                         const uint8_t *__restrict__ lab_old, uint8_t *lab_cur, int32_t *dirty,
+                         const int32_t *__restrict__ cur_list, int32_t *next_list,
+                         const int32_t *__restrict__ cur_cnt, int32_t *next_cnt,
+                         const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
+                         nemk_counters *cnt, const int32_t *__restrict__ skip) {
+    if (skip && *skip) return;
+    int count = *cur_cnt;
+    int dchanged = 0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x)
+        dchanged += fixup_site<KT>(K, cur_list[idx], logpf, row_ptr, col, wgt, beta, lab_old, lab_cur,
+                                   dirty, next_list, next_cnt, rrow_ptr, rcol);
+    if (dchanged) atomicAdd(&cnt->changed, dchanged);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(&cnt->nfix, 1);
+}
+
 template <int KT>
 __global__ void __launch_bounds__(1024)
 k_sweep_ncem_fixup(int K, int n, const double *__restrict__ logpf,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_old,
                    uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a, int32_t *wl_b,
-                   int32_t *wl_counts /*[2]*/, const int32_t *__restrict__ rrow_ptr,
+                   int32_t *wl_counts /*[2]: a, b*/, const int32_t *__restrict__ rrow_ptr,
                    const int32_t *__restrict__ rcol, nemk_counters *cnt,
                    const int32_t *__restrict__ skip) {
     if (skip && *skip) return;
     __shared__ int s_count;
-    const volatile uint8_t *vcur = lab_cur;
     int32_t *cur_list = wl_a, *next_list = wl_b;
     int32_t *cur_cnt = &wl_counts[0], *next_cnt = &wl_counts[1];
     int rounds = 0, dchanged = 0;
@@ -413,33 +708,15 @@ k_sweep_ncem_fixup(int K, int n, const double *__restrict__ logpf,
         int count = s_count;
         if (count == 0) break;
         rounds++;
-        for (int idx = threadIdx.x; idx < count; idx += blockDim.x) {
-            int i = cur_list[idx];
-            atomicExch(&dirty[i], 0);
-            __threadfence_block();
-            double ctx[KT];
-            ctx_labels<KT>(K, i, row_ptr, col, wgt,
-                           [&](int j) { return (unsigned)(j < i ? vcur[j] : lab_old[j]); }, ctx);
-            int flags;
-            int km = site_argmax<KT>(K, logpf + (size_t)i * K, ctx, beta, flags);
-            int was = vcur[i];
-            if (km != was) {
-                lab_cur[i] = (uint8_t)km;
-                __threadfence_block();
-                mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt);
-                int old = lab_old[i];
-                dchanged += (km != old) - (was != old);
-            }
-        }
+        for (int idx = threadIdx.x; idx < count; idx += blockDim.x)
+            dchanged += fixup_site<KT>(K, cur_list[idx], logpf, row_ptr, col, wgt, beta, lab_old,
+                                       lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
         __syncthreads();
         int32_t *tl = cur_list; cur_list = next_list; next_list = tl;
         int32_t *tc = cur_cnt; cur_cnt = next_cnt; next_cnt = tc;
     }
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
-    if (threadIdx.x == 0) {
-        cnt->nfix = rounds;
-        wl_counts[0] = 0; wl_counts[1] = 0;
-    }
+    if (threadIdx.x == 0 && rounds) atomicAdd(&cnt->nfix, rounds);
 }
 
 // ---- ncem, level-scheduled exact sequential sweep (reference order), in place.
@@ -605,46 +882,72 @@ template <int KT>
 __global__ void __launch_bounds__(256)
 k_label_masks(int K, int n, int nwt, const uint8_t *__restrict__ lab, uint32_t *__restrict__ cm,
               int32_t *nk) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int snk[KT];
+    if (threadIdx.x < KT) snk[threadIdx.x] = 0;
+    __syncthreads();
     int lane = threadIdx.x & 31;
-    unsigned l = (i < n) ? lab[i] : 255u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwt * 32; i += gridDim.x * blockDim.x) {
+        unsigned l = (i < n) ? lab[i] : 255u;
 #pragma unroll
-    for (int k = 0; k < KT; k++) {
-        if (k < K) {
-            unsigned m = __ballot_sync(FULL, l == (unsigned)k);
-            if (lane == 0 && (i >> 5) < nwt) {
-                cm[(size_t)k * nwt + (i >> 5)] = m;
-                if (m) atomicAdd(&nk[k], __popc(m));
+        for (int k = 0; k < KT; k++) {
+            if (k < K) {
+                unsigned m = __ballot_sync(FULL, l == (unsigned)k);
+                if (lane == 0) {
+                    cm[(size_t)k * nwt + (i >> 5)] = m;
+                    if (m) atomicAdd(&snk[k], __popc(m));
+                }
             }
         }
     }
+    __syncthreads();
+    if (threadIdx.x < K && snk[threadIdx.x]) atomicAdd(&nk[threadIdx.x], snk[threadIdx.x]);
 }
 
-// ncem: S_kd = sum_w popc(XT[d][w] & cm[k][w]).  A warp owns 32 uint4 (4096 families), keeps its
-// class masks in registers and walks a chunk of genomes; integer adds => exact and order-free.
-template <int KT>
+// ncem: S_kd = sum_w popc(XT[d][w] & cm[k][w]).  A warp owns 32 x MU uint4 of a column (4096 x MU
+// families), keeps its class masks in registers and walks a chunk of genomes.  Popcounts go through
+// carry-save adders (ones' = ones^a^b, carry = maj(ones,a,b): 2 LOP3 on the full-rate ALU pipe, one
+// quarter-rate POPC per TWO words); integer adds => exact and order-free (run-to-run reproducible).
+template <int KT, int MU>
 __global__ void __launch_bounds__(256)
 k_mstep_ncem(int K, int D, int nwt4, const uint4 *__restrict__ xt, const uint4 *__restrict__ cm,
              int dchunk, int32_t *S) {
     int lane = threadIdx.x & 31;
     int warp_in_block = threadIdx.x >> 5;
-    int wg = blockIdx.x * (blockDim.x >> 5) + warp_in_block;  // word group
-    int c = wg * 32 + lane;
-    bool in = c < nwt4;
-    uint4 m[KT];
+    int wg = blockIdx.x * (blockDim.x >> 5) + warp_in_block;  // word group: 32*MU uint4
+    int base = wg * 32 * MU;
+    if (base >= nwt4) return;
+    uint4 m[KT][MU];
 #pragma unroll
-    for (int k = 0; k < KT; k++)
-        m[k] = (in && k < K) ? cm[(size_t)k * nwt4 + c] : make_uint4(0, 0, 0, 0);
+    for (int u = 0; u < MU; u++) {
+        int c = base + u * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < KT; k++)
+            m[k][u] = (c < nwt4 && k < K) ? cm[(size_t)k * nwt4 + c] : make_uint4(0, 0, 0, 0);
+    }
     int d0 = blockIdx.y * dchunk, d1 = min(D, d0 + dchunk);
-    if (wg * 32 >= nwt4) return;
-#pragma unroll 4
+#pragma unroll 2
     for (int dd = d0; dd < d1; dd++) {
-        uint4 v = in ? __ldg(xt + (size_t)dd * nwt4 + c) : make_uint4(0, 0, 0, 0);
+        uint4 v[MU];
+#pragma unroll
+        for (int u = 0; u < MU; u++) {
+            int c = base + u * 32 + lane;
+            v[u] = (c < nwt4) ? __ldg(xt + (size_t)dd * nwt4 + c) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
         for (int k = 0; k < KT; k++) {
             if (k < K) {
-                int s = __popc(v.x & m[k].x) + __popc(v.y & m[k].y) + __popc(v.z & m[k].z) +
-                        __popc(v.w & m[k].w);
+                uint32_t ones = 0u, cnt2 = 0u;
+#pragma unroll
+                for (int u = 0; u < MU; u++) {
+                    uint32_t a0 = v[u].x & m[k][u].x, a1 = v[u].y & m[k][u].y;
+                    uint32_t a2 = v[u].z & m[k][u].z, a3 = v[u].w & m[k][u].w;
+                    uint32_t c0 = lop_maj3(ones, a0, a1);
+                    uint32_t o1 = lop_xor3(ones, a0, a1);
+                    uint32_t c1 = lop_maj3(o1, a2, a3);
+                    ones = lop_xor3(o1, a2, a3);
+                    cnt2 += __popc(c0) + __popc(c1);
+                }
+                int s = (int)(2u * cnt2) + __popc(ones);
                 s = __reduce_add_sync(FULL, s);
                 if (lane == k && s) atomicAdd(&S[(size_t)k * D + dd], s);
             }
@@ -877,18 +1180,22 @@ k_criteria_partial(int K, int n, const double *__restrict__ logpf,
     }
 }
 
-__global__ void k_criteria_final(int nblocks, const double *__restrict__ partials, double beta,
-                                 double *crit6) {
-    if (threadIdx.x || blockIdx.x) return;
-    double D = 0, G = 0, L = 0, Z = 0;
-    for (int b = 0; b < nblocks; b++) {
-        D += partials[b * 4 + 0]; G += partials[b * 4 + 1];
-        L += partials[b * 4 + 2]; Z += partials[b * 4 + 3];
+__global__ void __launch_bounds__(256)
+k_criteria_final(int nblocks, const double *__restrict__ partials, double beta, double *crit6) {
+    __shared__ double sh[32];
+    double v[4] = {0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblocks; b += 256)   // fixed assignment => deterministic
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] += partials[b * 4 + q];
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = block_sum<256>(v[q], sh);
+    if (threadIdx.x == 0) {
+        double D = v[0], G = v[1], L = v[2], Z = v[3];
+        crit6[0] = D + 0.5 * beta * G;
+        crit6[1] = D; crit6[2] = L;
+        crit6[3] = D + beta * G + Z;
+        crit6[4] = Z; crit6[5] = G;
     }
-    crit6[0] = D + 0.5 * beta * G;
-    crit6[1] = D; crit6[2] = L;
-    crit6[3] = D + beta * G + Z;
-    crit6[4] = Z; crit6[5] = G;
 }
 
 // =============================================================================================
@@ -952,7 +1259,8 @@ extern "C" void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const fl
                                   const float *center, const float *disp, nemk_coef *coef,
                                   uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
                                   uint32_t *mask_f1, double *delta) {
-    k_theta_tables<<<1, TT_THREADS, 0, S(s)>>>(k, d, wpr, prop, center, disp, coef, mask_xor,
+    cudaMemsetAsync(&coef->uniform_ok, 1, sizeof(int32_t), S(s));
+    k_theta_tables<<<k, TT_THREADS, 0, S(s)>>>(k, d, wpr, prop, center, disp, coef, mask_xor,
                                               mask_valid, mask_f0, mask_f1, delta);
     note_launch();
 }
@@ -989,10 +1297,119 @@ static void launch_density_uniform(cudaStream_t st, int K, const uint32_t *x, in
 #undef LAUNCH_DU
 }
 
+template <int KT, int T, int ROWS>
+static bool launch_density_tma_t(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
+                                 const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
+                                 double *logpf, int32_t *hamming) {
+    int wpr4 = wpr / 4;
+    int stride4 = wpr4 | 1;  // odd number of uint4 per shared row => conflict-free LDS.128
+    size_t mask_b = (size_t)2 * KT * wpr4 * sizeof(uint4);
+    size_t tile_b = (size_t)ROWS * stride4 * sizeof(uint4);
+    size_t stat = (size_t)2 * ROWS * KT * 4 + 192;
+    const size_t budget = 224 * 1024;
+    if (mask_b + 2 * tile_b + stat > budget) return false;
+    static int force_s = -1, force_c = -1;
+    if (force_s < 0) { const char *e = getenv("NEM_B200_DENSITY_STAGES"); force_s = e ? atoi(e) : 0; }
+    if (force_c < 0) { const char *e = getenv("NEM_B200_DENSITY_CTAS"); force_c = e ? atoi(e) : 0; }
+    // CTAs per SM: enough threads for the ALUs (>= 1024 threads/SM when they fit), and the rest of
+    // the shared memory goes to pipeline depth
+    int by_threads = 2048 / (ROWS * T);
+    int per_sm = force_c ? force_c : (1024 + ROWS * T - 1) / (ROWS * T);
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm < 1) per_sm = 1;
+    while (per_sm > 1 && (mask_b + 2 * tile_b + stat + 1024) * per_sm > budget) per_sm--;
+    int n_stages = (int)((budget / per_sm - mask_b - stat - 1024) / tile_b);
+    if (force_s) n_stages = force_s;
+    if (n_stages > 16) n_stages = 16;
+    if (n_stages < 2) n_stages = 2;
+    size_t smem = mask_b + (size_t)n_stages * tile_b;
+    if (smem + stat > budget) return false;
+    int n_tiles = cdiv(n, ROWS);
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        cudaFuncSetAttribute(k_density_tma<KT, ROWS, T, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget - stat));
+        cudaFuncSetAttribute(k_density_tma<KT, ROWS, T, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget - stat));
+        attr_set = budget;
+    }
+    int grid = num_sms() * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    if (K == KT)
+        k_density_tma<KT, ROWS, T, true><<<grid, ROWS * T, smem, st>>>(
+            K, (const uint4 *)x, n, wpr4, stride4, n_tiles, n_stages, coef, (const uint4 *)mx,
+            (const uint4 *)mv, logpf, hamming);
+    else
+        k_density_tma<KT, ROWS, T, false><<<grid, ROWS * T, smem, st>>>(
+            K, (const uint4 *)x, n, wpr4, stride4, n_tiles, n_stages, coef, (const uint4 *)mx,
+            (const uint4 *)mv, logpf, hamming);
+    return true;
+}
+
+template <int KT>
+static bool launch_density_tma(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
+                               const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
+                               double *logpf, int32_t *hamming) {
+    int wpr4 = wpr / 4;
+    static int force_t = -1;
+    if (force_t < 0) { const char *e = getenv("NEM_B200_DENSITY_T"); force_t = e ? atoi(e) : 0; }
+    int t = force_t ? force_t : (wpr4 >= 32 ? 4 : wpr4 >= 16 ? 2 : 1);   // measured on B200, DESIGN.md
+    static int force_r = -1;
+    if (force_r < 0) { const char *e = getenv("NEM_B200_DENSITY_ROWS"); force_r = e ? atoi(e) : 0; }
+    int rows = force_r ? force_r : 128;
+    if (KT > 4) t = t > 2 ? 2 : t;   // keep the static partial buffer small for large K
+#define DT(TT, RR) launch_density_tma_t<KT, TT, RR>(st, K, x, n, wpr, coef, mx, mv, logpf, hamming)
+    if constexpr (KT <= 4) {
+        if (t >= 8) return rows <= 32 ? DT(8, 32) : rows <= 64 ? DT(8, 64) : DT(8, 128);
+        if (t >= 4) return rows <= 32 ? DT(4, 32) : rows <= 64 ? DT(4, 64) : DT(4, 128);
+    }
+    if (t >= 2) return rows <= 64 ? DT(2, 64) : DT(2, 128);
+    return DT(1, 128);
+#undef DT
+}
+
+template <int KT>
+static bool launch_density_direct(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
+                                  const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
+                                  double *logpf, int32_t *hamming) {
+    int wpr4 = wpr / 4;
+    size_t smem = (size_t)2 * KT * wpr4 * sizeof(uint4);
+    if (smem > 96 * 1024) return false;
+    static int thr = -1, ctas = -1;
+    if (thr < 0) { const char *e = getenv("NEM_B200_DIRECT_THREADS"); thr = e ? atoi(e) : 128; }
+    if (ctas < 0) { const char *e = getenv("NEM_B200_DIRECT_CTAS"); ctas = e ? atoi(e) : 8; }
+    int grid = num_sms() * ctas;
+    int need = cdiv(n, thr);
+    if (grid > need) grid = need;
+#define DD(EX) do { \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_density_direct<KT, EX, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k_density_direct<KT, EX, 4><<<grid, thr, smem, st>>>(K, (const uint4 *)x, n, wpr4, coef, (const uint4 *)mx, (const uint4 *)mv, logpf, hamming); } while (0)
+    if (K == KT) DD(true); else DD(false);
+#undef DD
+    return true;
+}
+
+static int g_density_impl = -1;  // 0 = v1, 1 = v2 (TMA tiles), 2 = v3 (direct); env NEM_B200_DENSITY
 extern "C" void nemk_density_uniform(nemk_stream s, int k, const uint32_t *x, int n, int wpr,
                                      const nemk_coef *coef, const uint32_t *mask_xor,
                                      const uint32_t *mask_valid, double *logpf, int32_t *hamming) {
     if (n <= 0) return;
+    if (g_density_impl < 0) {
+        const char *e = getenv("NEM_B200_DENSITY");
+        g_density_impl = (e && !strcmp(e, "v1")) ? 0 : (e && !strcmp(e, "v3")) ? 2 : 1;
+    }
+    if (g_density_impl == 2) {
+        bool done = false;
+        DISPATCH_K(k, (done = launch_density_direct<KT>(S(s), k, x, n, wpr, coef, mask_xor,
+                                                        mask_valid, logpf, hamming)));
+        if (done) { note_launch(); return; }
+    }
+    if (g_density_impl == 1) {
+        bool done = false;
+        DISPATCH_K(k, (done = launch_density_tma<KT>(S(s), k, x, n, wpr, coef, mask_xor, mask_valid,
+                                                     logpf, hamming)));
+        if (done) { note_launch(); return; }
+    }
     DISPATCH_K(k, (launch_density_uniform<KT>(S(s), k, x, n, wpr, coef, mask_xor, mask_valid,
                                               logpf, hamming)));
     note_launch();
@@ -1039,6 +1456,21 @@ extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int n, const double 
     note_launch();
 }
 
+extern "C" void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, const double *logpf,
+                                            const int32_t *row_ptr, const int32_t *col,
+                                            const float *wgt, double beta, const uint8_t *lab_old,
+                                            uint8_t *lab_cur, int32_t *dirty, const int32_t *cur_list,
+                                            int32_t *next_list, const int32_t *cur_cnt,
+                                            int32_t *next_cnt, const int32_t *rrow_ptr,
+                                            const int32_t *rcol, nemk_counters *cnt,
+                                            const int32_t *skip) {
+    int grid = num_sms() * 2;
+    DISPATCH_K(k, (k_sweep_ncem_fixup_round<KT><<<grid, 256, 0, S(s)>>>(
+                      k, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty, cur_list, next_list,
+                      cur_cnt, next_cnt, rrow_ptr, rcol, cnt, skip)));
+    note_launch();
+}
+
 extern "C" void nemk_sweep_ncem_level(nemk_stream s, int k, const double *logpf,
                                       const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                       double beta, uint8_t *lab, const int32_t *sites,
@@ -1077,10 +1509,11 @@ extern "C" void nemk_sweep_nem_level(nemk_stream s, int k, const double *logpf,
 
 extern "C" void nemk_label_masks(nemk_stream s, int k, int n, int nwt, const uint8_t *lab,
                                  uint32_t *cm, int32_t *nk_int) {
-    cudaMemsetAsync(cm, 0, (size_t)k * nwt * sizeof(uint32_t), S(s));
     cudaMemsetAsync(nk_int, 0, (size_t)k * sizeof(int32_t), S(s));
     if (n <= 0) return;
-    DISPATCH_K(k, (k_label_masks<KT><<<cdiv(n, 256), 256, 0, S(s)>>>(k, n, nwt, lab, cm, nk_int)));
+    int grid = cdiv((long long)nwt * 32, 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    DISPATCH_K(k, (k_label_masks<KT><<<grid, 256, 0, S(s)>>>(k, n, nwt, lab, cm, nk_int)));
     note_launch();
 }
 
@@ -1089,18 +1522,25 @@ extern "C" void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint
     cudaMemsetAsync(s_int, 0, (size_t)k * d * sizeof(int32_t), S(s));
     int nwt4 = nwt / 4;
     if (nwt4 <= 0 || d <= 0) return;
-    int wgroups = cdiv(nwt4, 32);
+    static int mu_env = -1;
+    if (mu_env < 0) { const char *e = getenv("NEM_B200_MSTEP_MU"); mu_env = e ? atoi(e) : 0; }
+    int mu = mu_env ? mu_env : (k <= 4 && nwt4 >= 2048 ? 4 : nwt4 >= 512 ? 2 : 1);
+    if (k > 4 && mu > 2) mu = 2;   // registers: KT x MU uint4 of masks
+    if (k > 8) mu = 1;
+    int wgroups = cdiv(nwt4, 32 * mu);
     int gx = cdiv(wgroups, 8);
-    // enough CTAs to fill the machine: split the genomes into chunks
-    int want = num_sms() * 8;
+    int want = num_sms() * 16;   // CTAs: fill the machine, genomes split into chunks
     int ny = cdiv(want, gx);
     if (ny < 1) ny = 1;
     if (ny > d) ny = d;
     int dchunk = cdiv(d, ny);
     ny = cdiv(d, dchunk);
     dim3 grid(gx, ny);
-    DISPATCH_K(k, (k_mstep_ncem<KT><<<grid, 256, 0, S(s)>>>(k, d, nwt4, (const uint4 *)xt,
-                                                           (const uint4 *)cm, dchunk, s_int)));
+#define MS(KTT, MUU) k_mstep_ncem<KTT, MUU><<<grid, 256, 0, S(s)>>>(k, d, nwt4, (const uint4 *)xt, (const uint4 *)cm, dchunk, s_int)
+    if (mu >= 4) { if (k <= 2) MS(2, 4); else if (k == 3) MS(3, 4); else MS(4, 4); }
+    else if (mu == 2) { if (k <= 2) MS(2, 2); else if (k == 3) MS(3, 2); else if (k == 4) MS(4, 2); else MS(8, 2); }
+    else { DISPATCH_K(k, (MS(KT, 1))); }
+#undef MS
     note_launch();
 }
 
@@ -1138,7 +1578,7 @@ extern "C" void nemk_criteria(nemk_stream s, int k, int n, const double *logpf,
     DISPATCH_K(k, (k_criteria_partial<KT><<<nb, 256, 0, S(s)>>>(k, n, logpf, row_ptr, col, wgt, beta,
                                                                lab, t, partials)));
     note_launch();
-    k_criteria_final<<<1, 32, 0, S(s)>>>(nb, partials, beta, crit6);
+    k_criteria_final<<<1, 256, 0, S(s)>>>(nb, partials, beta, crit6);
     note_launch();
 }
 
