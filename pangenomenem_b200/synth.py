@@ -248,12 +248,17 @@ def read_cf(path: str) -> np.ndarray:
 def read_mf(path: str, k: int, d: int) -> dict:
     """Parse ``.mf`` (layout nem_exe.c:1708-1773; consumer ppanggolin.py:1898-1923)."""
     with open(path) as f:
-        lines = f.readlines()
+        return read_mf_text(f.read(), k, d)
+
+
+def read_mf_text(text: str, k: int, d: int) -> dict:
+    lines = text.splitlines()
     crit = [float(v) for v in lines[2].split()]
     out = {"U": crit[0], "D": crit[1], "L": crit[2], "M": crit[3], "err": crit[4],
            "beta": float(lines[5].split()[0])}
     mu = np.empty((k, d)); eps = np.empty((k, d)); p = np.empty(k)
-    for kk, ln in enumerate(lines[-k:]):
+    body = [ln for ln in lines if ln.strip()]
+    for kk, ln in enumerate(body[-k:]):
         v = ln.split()
         mu[kk] = [float(t) for t in v[:d]]
         p[kk] = float(v[d])

@@ -1,0 +1,77 @@
+"""GPU: the CUDA engine, through the C ABI, against the committed outputs of the unmodified
+reference (tests/golden/*.npz) -- both the in-memory API and the drop-in nem() file route that
+ppanggolin.py:1814-1826 + 1886-1972 drives."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, Golden, check_against_reference
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_engine_reproduces_reference(engine, oracle, name):
+    g = Golden(name)
+    engine.load_dense(g.x, g.row_ptr, g.col, g.wgt)
+    fit = engine.fit(*oracle.default_theta(3, g.d), **g.opt)
+    assert fit.status == 0 and fit.kernel_launches > 0
+    check_against_reference(g, engine.posteriors(), engine.labels(), fit.prop, fit.center, fit.disp,
+                            fit.crit, fit.iters, fit.converged)
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if Golden(n).text("uf")])
+@pytest.mark.parametrize("dolog", [False, True])
+def test_nem_dropin_on_the_reference_input_files(tmp_path, name, dolog):
+    """nem() with the reference's 13 arguments on the very files the reference consumed; outputs
+    parsed like run_partitioning (ppanggolin.py:1890-1972)."""
+    from pangenomenem_b200 import capi, synth
+    g = Golden(name)
+    base = str(tmp_path / "run" / "nem_file")
+    g.write_files(base)
+    rc = capi.nem(Fname=base.encode(), nk=3, algo=g.opt["algo"].encode(), beta=g.opt["beta"],
+                  convergence=b"clas", convergence_th=1e-8, format=b"fuzzy", it_max=g.opt["it_max"],
+                  dolog=dolog, model_family=b"bern", proportion=g.opt["prop"].encode(),
+                  dispersion=g.opt["disp"].encode(), init_mode=2)
+    assert rc == 0
+    uf = synth.read_uf(base + ".uf", 3)
+    mf = synth.read_mf(base + ".mf", 3, g.d)
+    uf_ref = np.array(g.text("uf").split(), dtype=np.float64).reshape(g.n, 3)
+    mf_ref = synth.read_mf_text(g.text("mf"), 3, g.d)
+    if g.opt["algo"] == "ncem":
+        # the reference's nem() breaks exact ties at random (wall-clock seed): allow those rows
+        assert (uf.argmax(axis=1) != uf_ref.argmax(axis=1)).sum() <= 2
+        assert np.array_equal(uf.argmax(axis=1), g.label)
+    else:
+        assert np.abs(uf - uf_ref).max() <= 2e-3
+    assert np.array_equal(mf["mu"], mf_ref["mu"])
+    assert np.allclose(mf["eps"], mf_ref["eps"], rtol=2e-4) and np.allclose(mf["p"], mf_ref["p"], rtol=2e-3, atol=1e-3)
+    for key in "UDL":
+        assert abs(mf[key] - mf_ref[key]) <= 2e-3 * abs(mf_ref[key])
+    assert synth.classify_psc(uf, mf) == synth.classify_psc(uf_ref, mf_ref) or g.opt["algo"] == "nem"
+    assert os.path.exists(base + ".log") == dolog and os.path.exists(base + ".stderr") == dolog
+    if dolog:
+        txt = open(base + ".stderr").read()
+        assert ("NEM converged after %d iterations" % g.iters in txt) == g.converged
+
+
+def test_nem_hard_format_and_empty_class(tmp_path):
+    from pangenomenem_b200 import capi, synth
+    g = Golden("ppanggolin_ncem_sk")
+    base = str(tmp_path / "run" / "nem_file")
+    g.write_files(base)
+    args = dict(nk=3, algo=b"ncem", beta=0.5, convergence=b"clas", convergence_th=1e-8,
+                it_max=100, dolog=False, model_family=b"bern", proportion=b"pk", dispersion=b"sk_",
+                init_mode=2)
+    assert capi.nem(Fname=base.encode(), format=b"hard", **args) == 0
+    cf = synth.read_cf(base + ".cf")
+    assert np.array_equal(cf - 1, g.label)                       # 1-based MAP, nem_exe.c:1683-1700
+    # a starting point that empties a class: EXIT_W_RESULT and no result files (nem_exe.c:624-631)
+    os.remove(base + ".cf"); os.remove(base + ".mf")
+    d = g.d
+    line = "1 0.98 0.01 " + " ".join(["1"] * d + ["1"] * d + ["1"] * d) + " " + \
+           " ".join(["0.4"] * d + ["1e-9"] * d + ["1e-9"] * d)
+    open(base + ".m", "w").write(line)
+    assert capi.nem(Fname=base.encode(), format=b"fuzzy", **args) == 1
+    assert not os.path.exists(base + ".uf") and not os.path.exists(base + ".mf")
