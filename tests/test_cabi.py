@@ -88,3 +88,28 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".c", ".cu", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "nem_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_cython_dropin_module_has_the_reference_interface(tmp_path):
+    """The top-level module `nem` PPanGGOLiN imports (ppanggolin.py:20, NEM/nem.pyx:1-14):
+    keyword-callable with bytes strings, returns the ExitET int."""
+    import importlib
+    import sys
+    from pangenomenem_b200 import build_pyx
+    so = build_pyx.build()
+    sys.path.insert(0, os.path.dirname(so))
+    try:
+        mod = importlib.import_module("nem")
+        assert os.path.dirname(mod.__file__) == os.path.dirname(so)
+        rc = mod.nem(Fname=str(tmp_path / "nothing").encode("ascii") + b"/nem_file", nk=3, algo=b"ncem",
+                     beta=0.5, convergence=b"clas", convergence_th=0.00000001, format=b"fuzzy",
+                     it_max=100, dolog=True, model_family=b"bern", proportion=b"pk",
+                     dispersion=b"sk_", init_mode=2)
+        assert rc == 3
+        with pytest.raises(TypeError):
+            mod.nem(Fname="a str is not bytes", nk=3, algo=b"ncem", beta=0.5, convergence=b"clas",
+                    convergence_th=1e-8, format=b"fuzzy", it_max=1, dolog=False,
+                    model_family=b"bern", proportion=b"pk", dispersion=b"sk_", init_mode=2)
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("nem", None)

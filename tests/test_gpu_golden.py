@@ -75,3 +75,26 @@ def test_nem_hard_format_and_empty_class(tmp_path):
     open(base + ".m", "w").write(line)
     assert capi.nem(Fname=base.encode(), format=b"fuzzy", **args) == 1
     assert not os.path.exists(base + ".uf") and not os.path.exists(base + ".mf")
+
+
+def test_cython_nem_module_drives_the_engine(tmp_path):
+    """`from nem import *` + the exact call of ppanggolin.py:1814-1826."""
+    import importlib
+    import sys
+    from pangenomenem_b200 import build_pyx, synth
+    so = build_pyx.module_path() or build_pyx.build()
+    sys.path.insert(0, os.path.dirname(so))
+    try:
+        nem = importlib.import_module("nem").nem
+        g = Golden("ppanggolin_ncem_sk")
+        nem_dir_path = str(tmp_path / "NEM_results")
+        g.write_files(nem_dir_path + "/nem_file")
+        rc = nem(Fname=nem_dir_path.encode("ascii") + b"/nem_file", nk=3, algo=b"ncem", beta=0.5,
+                 convergence=b"clas", convergence_th=0.00000001, format=b"fuzzy", it_max=100,
+                 dolog=True, model_family=b"bern", proportion=b"pk", dispersion=b"sk_", init_mode=2)
+        assert rc == 0
+        uf = synth.read_uf(nem_dir_path + "/nem_file.uf", 3)
+        assert np.array_equal(uf.argmax(axis=1), g.label)
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("nem", None)
