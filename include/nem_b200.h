@@ -24,6 +24,7 @@
 #ifndef NEM_B200_H
 #define NEM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -127,6 +128,55 @@ int nemb_load_packed_device(nemb_handle *h, int n, int d, int words_per_row,
                             const uint32_t *x_packed_dev, const int32_t *row_ptr,
                             const int32_t *col, const float *wgt);
 
+/* ---------------------------------------------------------------------------------------
+ * Row-sharded fits (one process per GPU).  The reference has no counterpart: its engine is one
+ * single-threaded process.  Families are split into `world` contiguous
+ * id ranges of shard_len = ceil(n_glob / world) rows; rank r owns rows [r*shard_len,
+ * min(n_glob, (r+1)*shard_len)).  X is sharded; the neighbour graph (5 % of the bytes), theta
+ * and the 1-byte labels are replicated.  Per EM iteration the ranks exchange
+ *   - the M-step sufficient statistics S[K*D] + n[K] (all-gather + rank-ordered sum = a
+ *     deterministic all-reduce), and
+ *   - after every sweep round, the label slices (halo exchange of the 1-byte hard labels, or of
+ *     the float posteriors for algo nem), so that the SEQUENTIAL sweep keeps its exact
+ *     single-process result (speculative fixed point across ranks, DESIGN.md "Multi-GPU").
+ * The only primitive the engine needs is an all-gather on device pointers, supplied through
+ * this vtable (NCCL binding below; an in-process test double for single-GPU tests).
+ * ------------------------------------------------------------------------------------- */
+typedef struct nemb_comm {
+    void   *ctx;
+    int32_t rank, world;
+    /* every rank contributes bytes_per_rank bytes from `send`; `recv` receives world blocks in
+     * rank order.  `send` may be recv + rank*bytes_per_rank (in place).  Device pointers; the
+     * work is enqueued on cuda_stream.  Returns 0 on success. */
+    int   (*allgather)(void *ctx, const void *send, void *recv, size_t bytes_per_rank,
+                       void *cuda_stream);
+    void  (*destroy)(void *ctx);
+} nemb_comm;
+
+/* NCCL binding (libnccl.so.2 is dlopen'ed; NEM_B200_NCCL_LIB overrides the path).  Rank 0 makes
+ * the 128-byte id and ships it to the other ranks by any means (torch.distributed broadcast in
+ * pangenomenem_b200/sharded.py). */
+int  nemb_nccl_unique_id(uint8_t id_out[128]);
+int  nemb_comm_create_nccl(nemb_comm **out, const uint8_t id[128], int rank, int world);
+/* In-process test double: `world` communicators for `world` host threads driving `world`
+ * handles on ONE device; collectives are staged device copies ordered by events. */
+int  nemb_comm_create_local(nemb_comm **out_array /*[world]*/, int world);
+void nemb_comm_destroy(nemb_comm *c);
+/* Attach before loading; NULL detaches (single GPU).  The handle does not own the comm. */
+int  nemb_set_comm(nemb_handle *h, nemb_comm *comm);
+
+/* Load this rank's shard: x_packed = rows [row0, row0+n_loc) (host buffer), graph = the GLOBAL
+ * CSR over n_glob families (every rank passes the same).  Needs a comm with world > 1 or
+ * row0 == 0 && n_loc == n_glob. */
+int nemb_load_shard(nemb_handle *h, int n_glob, int row0, int n_loc, int d, int words_per_row,
+                    const uint32_t *x_packed, const int32_t *row_ptr, const int32_t *col,
+                    const float *wgt);
+int nemb_load_shard_device(nemb_handle *h, int n_glob, int row0, int n_loc, int d,
+                           int words_per_row, const uint32_t *x_packed_dev, const int32_t *row_ptr,
+                           const int32_t *col, const float *wgt);
+/* shard geometry helper: shard_len and this rank's [row0, row0+n_loc) */
+void nemb_shard_range(int n_glob, int world, int rank, int *shard_len, int *row0, int *n_loc);
+
 /* One fit = ClassifyByNemOneBeta's INIT_PARAM_FILE branch (nem_alg.c:1151-1169): blind sweep,
  * beta sweep, EM loop, final criteria.  theta (prop[K], center[K*D], disp[K*D], float32, host)
  * is the starting point on entry and the last M-step's estimate on return. */
@@ -138,6 +188,7 @@ int nemb_fit_logged(nemb_handle *h, const nemb_options *opt, float *prop, float 
 int nemb_fit_random(nemb_handle *h, const nemb_options *opt, int n_starts, int64_t seed,
                     float *prop, float *center, float *disp, nemb_result *res);
 
+/* n = the GLOBAL number of families (every rank of a sharded fit holds all labels) */
 int nemb_get_posteriors(nemb_handle *h, float *t_out /*[n*k]*/);
 int nemb_get_labels(nemb_handle *h, int32_t *label_out /*[n]*/);   /* MAP, first maximum */
 

@@ -25,7 +25,7 @@ CC_FLAGS = ["-O2", "-std=gnu11", "-Wall", "-Wno-unused-function", "-fPIC", "-ffp
             "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", os.path.join(CUDA_HOME, "include")]
 
 CU_SOURCES = ["nem_kernels.cu"]
-C_SOURCES = ["nem_fit.c", "nem_io.c", "nem_api.c"]
+C_SOURCES = ["nem_fit.c", "nem_comm.c", "nem_io.c", "nem_api.c"]
 
 
 def _newer(src_list, target):

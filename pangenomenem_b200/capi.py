@@ -53,6 +53,12 @@ class Extra(C.Structure):
                 ("n_random_inits", C.c_int32), ("seed", C.c_int64), ("reserved", C.c_int32 * 8)]
 
 
+class Comm(C.Structure):
+    """nemb_comm: the all-gather vtable of a row-sharded fit (include/nem_b200.h)."""
+    _fields_ = [("ctx", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32),
+                ("allgather", C.c_void_p), ("destroy", C.c_void_p)]
+
+
 class HostProblem(C.Structure):
     _fields_ = [("n", C.c_int32), ("d", C.c_int32), ("words_per_row", C.c_int32),
                 ("spatial", C.c_int32), ("nnz", C.c_int32), ("max_neigh", C.c_int32),
@@ -78,6 +84,10 @@ def load_library():
         lib.nemb_last_error.restype = C.c_char_p
         lib.nemb_version.restype = C.c_char_p
         lib.nemb_free_host_problem.restype = None
+        lib.nemb_comm_destroy.restype = None
+        lib.nemb_comm_destroy.argtypes = [C.c_void_p]
+        lib.nemb_shard_range.restype = None
+        lib.nemb_set_comm.argtypes = [C.c_void_p, C.c_void_p]
         sig = [C.c_char_p, C.c_int, C.c_char_p, C.c_float, C.c_char_p, C.c_float, C.c_char_p,
                C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         if hasattr(lib, "nem"):
@@ -183,6 +193,25 @@ class Engine:
         self._check(self.lib.nemb_load_packed_device(self.h, self.n, self.d, int(wpr),
                                                      C.c_void_p(dev_ptr), _p(rp), _p(cl), _p(wg)))
 
+    # ---- row shards (one Engine per rank)
+    def set_comm(self, comm_ptr):
+        """comm_ptr: a nemb_comm* (int / c_void_p) from nccl_comm() or local_comms(); None detaches."""
+        self._check(self.lib.nemb_set_comm(self.h, C.c_void_p(comm_ptr) if comm_ptr else None))
+
+    def load_shard(self, xp_local, n_glob, row0, d, row_ptr=None, col=None, wgt=None):
+        xp = np.ascontiguousarray(xp_local, dtype=np.uint32)
+        rp, cl, wg = self._graph(row_ptr, col, wgt)
+        self.n, self.d = int(n_glob), int(d)
+        self._check(self.lib.nemb_load_shard(self.h, int(n_glob), int(row0), xp.shape[0], self.d,
+                                             xp.shape[1], _p(xp), _p(rp), _p(cl), _p(wg)))
+
+    def load_shard_device(self, dev_ptr, n_glob, row0, n_loc, d, wpr, row_ptr=None, col=None, wgt=None):
+        rp, cl, wg = self._graph(row_ptr, col, wgt)
+        self.n, self.d = int(n_glob), int(d)
+        self._check(self.lib.nemb_load_shard_device(self.h, int(n_glob), int(row0), int(n_loc),
+                                                    self.d, int(wpr), C.c_void_p(dev_ptr), _p(rp),
+                                                    _p(cl), _p(wg)))
+
     def dims(self):
         v = [C.c_int() for _ in range(6)]
         self._check(self.lib.nemb_get_dims(self.h, *[C.byref(a) for a in v]))
@@ -275,6 +304,47 @@ class Engine:
                                                  _p(np.ascontiguousarray(logpf, dtype=np.float64)),
                                                  _p(_f32(t)), C.c_float(beta), _p(out)))
         return dict(zip("UDLMZG", out))
+
+
+# ------------------------------------------------------------------ communicators
+def shard_range(n_glob: int, world: int, rank: int):
+    """(shard_len, row0, n_loc) exactly as the engine computes them (nemb_shard_range)."""
+    sl, r0, nl = C.c_int(), C.c_int(), C.c_int()
+    load_library().nemb_shard_range(int(n_glob), int(world), int(rank), C.byref(sl), C.byref(r0),
+                                    C.byref(nl))
+    return sl.value, r0.value, nl.value
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    rc = load_library().nemb_nccl_unique_id(buf)
+    if rc:
+        raise NemError(rc, "ncclGetUniqueId (is libnccl.so.2 loadable?)")
+    return bytes(buf)
+
+
+def nccl_comm(uid: bytes, rank: int, world: int) -> int:
+    """ncclCommInitRank on the CURRENT CUDA device; returns a nemb_comm* (int)."""
+    out = C.c_void_p()
+    buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+    rc = load_library().nemb_comm_create_nccl(C.byref(out), buf, int(rank), int(world))
+    if rc:
+        raise NemError(rc, f"nemb_comm_create_nccl(rank {rank} of {world})")
+    return out.value
+
+
+def local_comms(world: int) -> list:
+    """In-process test double: `world` nemb_comm* for `world` threads on one device."""
+    arr = (C.c_void_p * world)()
+    rc = load_library().nemb_comm_create_local(arr, int(world))
+    if rc:
+        raise NemError(rc, "nemb_comm_create_local")
+    return [arr[i] for i in range(world)]
+
+
+def comm_destroy(comm_ptr) -> None:
+    if comm_ptr:
+        load_library().nemb_comm_destroy(C.c_void_p(comm_ptr))
 
 
 # ------------------------------------------------------------------ host loader / writers (no GPU)

@@ -34,7 +34,8 @@ typedef struct {
     int32_t allnul;      /* rows whose every class has zero density */
     int32_t ties;        /* ncem rows whose arg max was an exact tie */
     float   maxdiff;     /* nem: max |t - t_old| */
-    int32_t pad[3];
+    int32_t pending;     /* row-sharded sweep: local sites queued by the last label exchange */
+    int32_t pad[2];
 } nemk_counters;
 
 typedef void *nemk_stream;
@@ -58,32 +59,43 @@ void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d,
                           const nemk_coef *coef, const uint32_t *mask_f0, const uint32_t *mask_f1,
                           const double *delta, double *logpf);
 
+/* ---- loader: graph validation.  flags2[0] bit0 row_ptr broken, bit1 neighbour out of range,
+ * bit2 some edge i->j has no j->i (reader lists differ from neighbour lists); flags2[1] = max degree */
+void nemk_graph_check(nemk_stream s, int n, int nnz, const int32_t *row_ptr, const int32_t *col,
+                      int32_t *flags2);
+
 /* ---- E-step sweeps.  label 255 = unlabelled (the reference's calloc'd ClassifM row).
  * `skip` (nullable) points at a device flag; non-zero => the kernel returns at once (an empty
- * class was found by the M-step, the reference does not run the E-step then). */
-void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int n, const double *logpf, const int32_t *row_ptr,
-                            const int32_t *col, const float *wgt, double beta,
-                            const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty, int32_t *wl,
-                            int32_t *wl_count, const int32_t *rrow_ptr, const int32_t *rcol,
-                            nemk_counters *cnt, const int32_t *skip);
-void nemk_sweep_ncem_fixup(nemk_stream s, int k, int n, const double *logpf, const int32_t *row_ptr,
-                           const int32_t *col, const float *wgt, double beta,
+ * class was found by the M-step, the reference does not run the E-step then).
+ * Row sharding: this rank owns the global rows [row0, row0+n_loc); labels, t, CSR, dirty flags and
+ * work lists are indexed by GLOBAL family id, logpf by local row.  One GPU: row0 = 0, n_loc = N.
+ * Work lists: wl_a/wl_b used alternately, wl_cnt[4] rotating counters (round r: list r&1). */
+void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+                            const int32_t *row_ptr, const int32_t *col, const float *wgt,
+                            double beta, const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
+                            int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
+                            const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
+void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+                           const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
                            const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a,
-                           int32_t *wl_b, int32_t *wl_counts, const int32_t *rrow_ptr,
+                           int32_t *wl_b, int32_t *wl_cnt, int round, const int32_t *rrow_ptr,
                            const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
-void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, const double *logpf, const int32_t *row_ptr,
-                                 const int32_t *col, const float *wgt, double beta,
-                                 const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty,
-                                 const int32_t *cur_list, int32_t *next_list,
-                                 const int32_t *cur_cnt, int32_t *next_cnt, const int32_t *rrow_ptr,
-                                 const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
+void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+                                 const int32_t *row_ptr, const int32_t *col, const float *wgt,
+                                 double beta, const uint8_t *lab_old, uint8_t *lab_cur,
+                                 int32_t *dirty, int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt,
+                                 int round, const int32_t *rrow_ptr, const int32_t *rcol,
+                                 nemk_counters *cnt, const int32_t *skip);
+void nemk_mark_remote(nemk_stream s, int n_glob, int row0, int n_loc, const uint8_t *lab_cur,
+                      uint8_t *lab_seen, int32_t *dirty, int32_t *wl, int32_t *wl_count,
+                      const int32_t *rrow_ptr, const int32_t *rcol, int32_t *pending);
 void nemk_sweep_ncem_level(nemk_stream s, int k, const double *logpf, const int32_t *row_ptr,
                            const int32_t *col, const float *wgt, double beta, uint8_t *lab,
                            const int32_t *sites, const int32_t *level_ptr, int lv_lo, int lv_hi,
                            int grid_ctas, nemk_counters *cnt, const int32_t *skip);
-void nemk_sweep_nem_jacobi(nemk_stream s, int k, int n, const double *logpf, const int32_t *row_ptr,
-                           const int32_t *col, const float *wgt, double beta, const float *t_in,
-                           float *t_out, nemk_counters *cnt, const int32_t *skip);
+void nemk_sweep_nem_jacobi(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+                           const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
+                           const float *t_in, float *t_out, nemk_counters *cnt, const int32_t *skip);
 void nemk_sweep_nem_level(nemk_stream s, int k, const double *logpf, const int32_t *row_ptr,
                           const int32_t *col, const float *wgt, double beta, float *t,
                           const int32_t *sites, const int32_t *level_ptr, int lv_lo, int lv_hi,
@@ -102,10 +114,17 @@ void nemk_mstep_finalize(nemk_stream s, int k, int n, int d, int prop_model, int
                          const double *nk_dbl, float *prop, float *center, float *disp,
                          float *iner_scratch, nemk_coef *coef);
 
-/* ---- criteria (U D L M Z G into crit6) */
-void nemk_criteria(nemk_stream s, int k, int n, const double *logpf, const int32_t *row_ptr,
-                   const int32_t *col, const float *wgt, double beta, const uint8_t *lab,
-                   const float *t, double *partials, int nblocks_cap, double *crit6);
+/* ---- criteria: per-rank partial sums (exactly nblocks rows of 4 doubles: D G L Z), then the
+ * final fixed-order sum over the partial rows of every rank -> U D L M Z G */
+int  nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+                           const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
+                           const uint8_t *lab, const float *t, double *partials, int nblocks);
+void nemk_criteria_final(nemk_stream s, int nblocks_total, const double *partials, double beta,
+                         double *crit6);
+
+/* ---- rank-ordered sums over an all-gathered stage [world][count] */
+void nemk_sum_ranks_i32(nemk_stream s, int world, size_t count, const int32_t *stage, int32_t *out);
+void nemk_sum_ranks_f64(nemk_stream s, int world, size_t count, const double *stage, double *out);
 
 /* ---- helpers */
 void nemk_labels_to_t(nemk_stream s, int k, int n, const uint8_t *lab, float *t);

@@ -1,8 +1,9 @@
 /*
  * nem_fit.c -- C host of the in-memory API (include/nem_b200.h, layer 3): device buffers, the
- * loader (CSR, reader lists, sweep level schedule), the EM control flow and the stage entry
- * points.  All numerics run in the CUDA kernels of nem_kernels.cu through nem_device.h; this
- * file only sequences them.  No CPU fallback exists: every entry point needs a CUDA device.
+ * loader (CSR upload, device-side validation, lazy sweep level schedule), the EM control flow
+ * for one GPU and for row shards, and the stage entry points.  All numerics run in the CUDA
+ * kernels of nem_kernels.cu through nem_device.h; this file only sequences them.  No CPU
+ * fallback exists: every entry point needs a CUDA device.
  *
  * Control flow restated from the reference (root ppanggolin/NEM):
  *   ClassifyByNemOneBeta, INIT_PARAM_FILE branch   nem_alg.c:1151-1169
@@ -22,9 +23,12 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define NEMB_VERSION "nem-b200 0.1 (NEM 1.08-a compatible)"
+#define NEMB_VERSION "nem-b200 0.2 (NEM 1.08-a compatible)"
 #define NARROW_LEVEL 2048   /* levels at most this wide are walked by one CTA */
 #define MAX_LEVEL_GRID 2368 /* 148 SMs x 16 CTAs of 256 threads */
+#define MAX_WORLD 64
+#define CRIT_BLOCKS_MAX 1184 /* 148 SMs x 8 */
+#define CRIT_BLOCKS_SHARD 296
 
 typedef struct { int lo, hi, grid; } sweep_step;
 
@@ -36,41 +40,52 @@ typedef struct {
 
 enum { ST_DENSITY = 0, ST_SWEEP = 1, ST_MSTEP = 2, ST_CRIT = 3, ST_NB = 4 };
 
+typedef struct { void *p; size_t cap; } dbuf;   /* grow-only device buffer */
+
 struct nemb_handle {
     int device;
     cudaStream_t stream;
     int own_stream;
     char err[512];
-    /* problem */
-    int n, d, wpr, nwt, nnz, spatial, symmetric, depth, loaded;
+    nemb_comm *comm;
+    int rank, world;
+    /* problem.  n = rows this rank owns, n_glob = families of the whole pangenome, row0 = global
+     * id of local row 0, shard_len = rows per rank slot (lab_len = world * shard_len >= n_glob) */
+    int n, n_glob, row0, shard_len, lab_len;
+    int d, wpr, nwt, nnz, spatial, symmetric, max_neigh, loaded;
     uint32_t *d_x, *d_xt;
     int x_owned, have_xt;
+    dbuf b_x, b_xt, b_row_ptr, b_col, b_wgt, b_rrow_ptr, b_rcol, b_sites, b_level_ptr, b_flags;
     int32_t *d_row_ptr, *d_col, *d_rrow_ptr, *d_rcol, *d_sites, *d_level_ptr;
     float *d_wgt;
-    int32_t *h_level;      /* host: level of every site */
+    int have_levels, depth;
+    int32_t *h_level;      /* host: level of every site (lazy) */
     sweep_step *steps;
     int n_steps;
-    /* per-K buffers */
+    /* per-K buffers: one slab */
     int k_alloc;
+    dbuf b_slab, b_t[2], b_nem;
     float *d_prop, *d_center, *d_disp, *d_iner;
     nemk_coef *d_coef;
     uint32_t *d_mxor, *d_mval, *d_f0, *d_f1;
     double *d_delta;
     double *d_logpf;
-    uint8_t *d_lab[2];
+    uint8_t *d_lab[3];     /* two sweep buffers + the labels last seen from remote ranks */
     float *d_t[2];
     int cur, state_labels;
     int32_t *d_dirty, *d_wl[2], *d_wl_counts;
     uint32_t *d_cm;
-    int32_t *d_nk_int, *d_s_int;
-    double *d_partial_s, *d_partial_n, *d_s_dbl, *d_nk_dbl;
+    int32_t *d_stat_int, *d_stat_int_stage;   /* S[K*D] then n[K]; stage = [world][K*D+K] */
+    double *d_stat_dbl, *d_stat_dbl_stage;
+    double *d_partial_s, *d_partial_n;
     int rows_per_chunk, nchunks;
     double *d_crit_partials;
     int crit_blocks;
     iter_status *d_status, *h_status;
+    nemk_counters *d_cnt_all, *h_cnt_all;     /* [world] gathered sweep counters */
     int32_t *h_empty;
     /* fit bookkeeping */
-    int64_t launches, fixup_rounds;
+    int64_t launches, fixup_rounds, exchanges;
     int profile;
     cudaEvent_t *ev;
     int *ev_kind;
@@ -107,6 +122,22 @@ static int fail(nemb_handle *h, int code, const char *fmt, ...)
 const char *nemb_version(void) { return NEMB_VERSION; }
 const char *nemb_last_error(const nemb_handle *h) { return h ? h->err : "null handle"; }
 
+static int reserve(nemb_handle *h, dbuf *b, size_t bytes)
+{
+    if (bytes < 256) bytes = 256;
+    if (b->cap >= bytes) return NEMB_OK;
+    if (b->p) { cudaFree(b->p); b->p = NULL; b->cap = 0; }
+    size_t want = bytes + bytes / 16;   /* a little slack: reloads of slightly larger problems */
+    cudaError_t e = cudaMalloc(&b->p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&b->p, want); }
+    if (e != cudaSuccess)
+        return fail(h, e == cudaErrorMemoryAllocation ? NEMB_E_MEMORY : NEMB_E_CUDA,
+                    "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    b->cap = want;
+    return NEMB_OK;
+}
+static void release(dbuf *b) { if (b->p) cudaFree(b->p); b->p = NULL; b->cap = 0; }
+
 /* ------------------------------------------------------------------ lifetime */
 int nemb_create(nemb_handle **out, int device)
 {
@@ -128,6 +159,7 @@ int nemb_create(nemb_handle **out, int device)
     nemb_handle *h = calloc(1, sizeof *h);
     if (!h) return NEMB_E_MEMORY;
     h->device = device;
+    h->world = 1;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
         free(h);
@@ -147,41 +179,39 @@ int nemb_set_stream(nemb_handle *h, void *cuda_stream)
     return NEMB_OK;
 }
 
-static void free_k(nemb_handle *h)
+int nemb_set_comm(nemb_handle *h, nemb_comm *comm)
 {
-    cudaFree(h->d_prop); cudaFree(h->d_center); cudaFree(h->d_disp); cudaFree(h->d_iner);
-    cudaFree(h->d_coef); cudaFree(h->d_mxor); cudaFree(h->d_mval); cudaFree(h->d_f0);
-    cudaFree(h->d_f1); cudaFree(h->d_delta); cudaFree(h->d_logpf);
-    cudaFree(h->d_lab[0]); cudaFree(h->d_lab[1]); cudaFree(h->d_t[0]); cudaFree(h->d_t[1]);
-    cudaFree(h->d_dirty); cudaFree(h->d_wl[0]); cudaFree(h->d_wl[1]); cudaFree(h->d_wl_counts);
-    cudaFree(h->d_cm); cudaFree(h->d_nk_int); cudaFree(h->d_s_int);
-    cudaFree(h->d_partial_s); cudaFree(h->d_partial_n); cudaFree(h->d_s_dbl);
-    cudaFree(h->d_nk_dbl); cudaFree(h->d_crit_partials); cudaFree(h->d_status);
-    if (h->h_status) cudaFreeHost(h->h_status);
-    if (h->h_empty) cudaFreeHost(h->h_empty);
-    h->d_prop = h->d_center = h->d_disp = h->d_iner = NULL;
-    h->d_coef = NULL; h->d_mxor = h->d_mval = h->d_f0 = h->d_f1 = NULL;
-    h->d_delta = h->d_logpf = NULL;
-    h->d_lab[0] = h->d_lab[1] = NULL; h->d_t[0] = h->d_t[1] = NULL;
-    h->d_dirty = h->d_wl[0] = h->d_wl[1] = h->d_wl_counts = NULL;
-    h->d_cm = NULL; h->d_nk_int = h->d_s_int = NULL;
-    h->d_partial_s = h->d_partial_n = h->d_s_dbl = h->d_nk_dbl = h->d_crit_partials = NULL;
-    h->d_status = NULL; h->h_status = NULL; h->h_empty = NULL;
+    if (!h) return NEMB_E_ARG;
+    if (comm && (comm->world < 1 || comm->world > MAX_WORLD || comm->rank < 0 ||
+                 comm->rank >= comm->world || !comm->allgather))
+        return fail(h, NEMB_E_ARG, "bad communicator (rank %d of %d)", comm->rank, comm->world);
+    h->comm = comm;
+    h->rank = comm ? comm->rank : 0;
+    h->world = comm ? comm->world : 1;
+    h->loaded = 0;
     h->k_alloc = 0;
+    return NEMB_OK;
 }
 
-static void free_problem(nemb_handle *h)
+void nemb_shard_range(int n_glob, int world, int rank, int *shard_len, int *row0, int *n_loc)
 {
-    free_k(h);
-    if (h->x_owned) cudaFree(h->d_x);
-    cudaFree(h->d_xt);
-    cudaFree(h->d_row_ptr); cudaFree(h->d_col); cudaFree(h->d_wgt);
-    if (!h->symmetric) { cudaFree(h->d_rrow_ptr); cudaFree(h->d_rcol); }
-    cudaFree(h->d_sites); cudaFree(h->d_level_ptr);
+    if (world < 1) world = 1;
+    int sl = (n_glob + world - 1) / world;
+    long long r0 = (long long)rank * sl;
+    int nl = r0 >= n_glob ? 0 : (int)((long long)n_glob - r0 < sl ? (long long)n_glob - r0 : sl);
+    if (shard_len) *shard_len = sl;
+    if (row0) *row0 = (int)(r0 > n_glob ? n_glob : r0);
+    if (n_loc) *n_loc = nl;
+}
+
+/* logical reset; device buffers are kept for the next load (grow-only) */
+static void reset_problem(nemb_handle *h)
+{
+    if (!h->x_owned) h->d_x = NULL;
     free(h->h_level); free(h->steps);
-    h->d_x = h->d_xt = NULL; h->d_row_ptr = h->d_col = h->d_rrow_ptr = h->d_rcol = NULL;
-    h->d_sites = h->d_level_ptr = NULL; h->d_wgt = NULL; h->h_level = NULL; h->steps = NULL;
-    h->n_steps = 0; h->loaded = 0; h->have_xt = 0; h->x_owned = 0;
+    h->h_level = NULL; h->steps = NULL;
+    h->n_steps = 0; h->loaded = 0; h->have_xt = 0; h->have_levels = 0; h->depth = 0;
+    h->k_alloc = 0;
 }
 
 void nemb_destroy(nemb_handle *h)
@@ -189,7 +219,14 @@ void nemb_destroy(nemb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    free_problem(h);
+    reset_problem(h);
+    dbuf *all[] = {&h->b_x, &h->b_xt, &h->b_row_ptr, &h->b_col, &h->b_wgt, &h->b_rrow_ptr,
+                   &h->b_rcol, &h->b_sites, &h->b_level_ptr, &h->b_flags, &h->b_slab, &h->b_t[0],
+                   &h->b_t[1], &h->b_nem};
+    for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) release(all[i]);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_cnt_all) cudaFreeHost(h->h_cnt_all);
+    if (h->h_empty) cudaFreeHost(h->h_empty);
     for (int i = 0; i < h->ev_cap; i++) cudaEventDestroy(h->ev[i]);
     free(h->ev); free(h->ev_kind);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -197,23 +234,48 @@ void nemb_destroy(nemb_handle *h)
 }
 
 /* ------------------------------------------------------------------ loader: graph */
-/* Reader lists (who reads site i = transpose of the CSR), symmetry test, Gauss-Seidel levels
- * (i after every lower-index site it reads or is read by), sites sorted by (level, index) and
- * the launch schedule of the level-scheduled sweep. */
+/* The CSR goes to the device as is; k_graph_check validates it there (row_ptr monotone,
+ * neighbours in range) and tells whether every edge has its reverse, in which case the reader
+ * lists of the speculative sweep ARE the neighbour lists.  Only a directed .nei file makes the
+ * host build the transpose. */
+static int upload(nemb_handle *h, dbuf *b, const void *src, size_t bytes)
+{
+    int rc = reserve(h, b, bytes);
+    if (rc != NEMB_OK) return rc;
+    if (bytes) CK(cudaMemcpyAsync(b->p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return NEMB_OK;
+}
+
 static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32_t *col,
                       const float *wgt)
 {
+    int rc;
     h->spatial = row_ptr != NULL;
-    h->nnz = 0; h->depth = 0; h->symmetric = 1;
+    h->nnz = 0; h->symmetric = 1; h->max_neigh = 0;
+    h->d_row_ptr = h->d_col = h->d_rrow_ptr = h->d_rcol = NULL; h->d_wgt = NULL;
     if (!h->spatial) return NEMB_OK;
+    if (row_ptr[0] != 0) return fail(h, NEMB_E_ARG, "row_ptr[0] must be 0");
     int nnz = row_ptr[n];
+    if (nnz < 0) return fail(h, NEMB_E_ARG, "row_ptr[n] < 0");
+    if (nnz > 0 && (!col || !wgt)) return fail(h, NEMB_E_ARG, "col/wgt missing");
     h->nnz = nnz;
-    for (int i = 0; i < n; i++)
-        if (row_ptr[i + 1] < row_ptr[i]) return fail(h, NEMB_E_ARG, "row_ptr not monotone at %d", i);
-    for (int e = 0; e < nnz; e++)
-        if (col[e] < 0 || col[e] >= n) return fail(h, NEMB_E_ARG, "neighbour index out of range");
+    if ((rc = upload(h, &h->b_row_ptr, row_ptr, sizeof(int32_t) * ((size_t)n + 1))) != NEMB_OK) return rc;
+    if ((rc = upload(h, &h->b_col, col, sizeof(int32_t) * (size_t)nnz)) != NEMB_OK) return rc;
+    if ((rc = upload(h, &h->b_wgt, wgt, sizeof(float) * (size_t)nnz)) != NEMB_OK) return rc;
+    if ((rc = reserve(h, &h->b_flags, 64)) != NEMB_OK) return rc;
+    h->d_row_ptr = h->b_row_ptr.p; h->d_col = h->b_col.p; h->d_wgt = h->b_wgt.p;
+    nemk_graph_check(h->stream, n, nnz, h->d_row_ptr, h->d_col, (int32_t *)h->b_flags.p);
+    CKK();
+    int32_t flags[2] = {0, 0};
+    CK(cudaMemcpyAsync(flags, h->b_flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flags[0] & 1) return fail(h, NEMB_E_ARG, "row_ptr is not monotone");
+    if (flags[0] & 2) return fail(h, NEMB_E_ARG, "neighbour index out of range");
+    h->max_neigh = flags[1];
+    h->symmetric = !(flags[0] & 4);
+    if (h->symmetric) { h->d_rrow_ptr = h->d_row_ptr; h->d_rcol = h->d_col; return NEMB_OK; }
 
-    /* transpose */
+    /* directed graph: reader lists = transpose of the CSR */
     int32_t *rrow = calloc((size_t)n + 1, sizeof(int32_t));
     int32_t *rcol = malloc(sizeof(int32_t) * (size_t)(nnz ? nnz : 1));
     int32_t *fill = malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
@@ -223,20 +285,38 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
     for (int i = 0; i < n; i++) fill[i] = rrow[i];
     for (int i = 0; i < n; i++)
         for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) rcol[fill[col[e]]++] = i;
-    /* symmetric iff every row has the same neighbour SET as its reader list */
-    int sym = 1;
-    for (int i = 0; i < n && sym; i++) {
-        int a = row_ptr[i + 1] - row_ptr[i], b = rrow[i + 1] - rrow[i];
-        if (a != b) { sym = 0; break; }
-        /* reader lists are sorted by construction; rows may not be: compare as multisets */
-        long long s1 = 0, s2 = 0, q1 = 0, q2 = 0;
-        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) { s1 += col[e]; q1 += (long long)col[e] * col[e]; }
-        for (int e = rrow[i]; e < rrow[i + 1]; e++) { s2 += rcol[e]; q2 += (long long)rcol[e] * rcol[e]; }
-        if (s1 != s2 || q1 != q2) sym = 0;
-    }
-    h->symmetric = sym;
+    rc = upload(h, &h->b_rrow_ptr, rrow, sizeof(int32_t) * ((size_t)n + 1));
+    if (rc == NEMB_OK) rc = upload(h, &h->b_rcol, rcol, sizeof(int32_t) * (size_t)nnz);
+    if (rc == NEMB_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, NEMB_E_CUDA, "graph upload");
+    free(rrow); free(rcol); free(fill);
+    h->d_rrow_ptr = h->b_rrow_ptr.p; h->d_rcol = h->b_rcol.p;
+    return rc;
+}
 
-    /* levels */
+/* Gauss-Seidel levels of the index-order sweep (i after every lower-index site it reads or is
+ * read by), sites sorted by (level, index) and the launch schedule of the level-scheduled sweep.
+ * Built on first use (level sweep, sequential fuzzy sweep, nemb_get_levels): the default
+ * speculative sweep does not need it. */
+static int ensure_levels(nemb_handle *h)
+{
+    if (h->have_levels || !h->spatial) return NEMB_OK;
+    if (h->world > 1) return fail(h, NEMB_E_ARG, "the level schedule is not available on row shards");
+    int n = h->n_glob, nnz = h->nnz;
+    int32_t *row_ptr = malloc(sizeof(int32_t) * ((size_t)n + 1));
+    int32_t *col = malloc(sizeof(int32_t) * (size_t)(nnz ? nnz : 1));
+    int32_t *rrow = NULL, *rcol = NULL;
+    if (!row_ptr || !col) { free(row_ptr); free(col); return fail(h, NEMB_E_MEMORY, "host alloc"); }
+    CK(cudaMemcpyAsync(row_ptr, h->d_row_ptr, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(col, h->d_col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->symmetric) {
+        rrow = malloc(sizeof(int32_t) * ((size_t)n + 1));
+        rcol = malloc(sizeof(int32_t) * (size_t)(nnz ? nnz : 1));
+        CK(cudaMemcpyAsync(rrow, h->d_rrow_ptr, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(rcol, h->d_rcol, sizeof(int32_t) * (size_t)nnz, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    const int32_t *rr = rrow ? rrow : row_ptr, *rc_ = rcol ? rcol : col;
+
     int32_t *level = calloc((size_t)(n ? n : 1), sizeof(int32_t));
     int32_t *pend = calloc((size_t)(n ? n : 1), sizeof(int32_t));
     int depth = 0;
@@ -251,8 +331,8 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
             int j = col[e];
             if (j > i && level[i] > pend[j]) pend[j] = level[i];
         }
-        for (int e = rrow[i]; e < rrow[i + 1]; e++) { /* sites that read i and come later */
-            int j = rcol[e];
+        for (int e = rr[i]; e < rr[i + 1]; e++) { /* sites that read i and come later */
+            int j = rc_[e];
             if (j > i && level[i] > pend[j]) pend[j] = level[i];
         }
         if (level[i] > depth) depth = level[i];
@@ -265,13 +345,11 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
     for (int i = 0; i < n; i++) lptr[level[i]]++;          /* level l -> slot l (1-based) */
     for (int l = 1; l <= depth; l++) lptr[l] += lptr[l - 1];
     /* lptr[l] = number of sites with level <= l; start of level l (1-based) = lptr[l-1] */
-    for (int i = 0; i < n; i++) fill[i] = 0;
     int32_t *pos = calloc((size_t)depth + 1, sizeof(int32_t));
     for (int l = 1; l <= depth; l++) pos[l] = lptr[l - 1];
     for (int i = 0; i < n; i++) sites[pos[level[i]]++] = i;
     free(pos);
     /* device level_ptr is 0-based over levels: level_ptr[q] = start of level q+1 */
-    /* schedule */
     h->steps = malloc(sizeof(sweep_step) * (size_t)(depth ? depth : 1));
     h->n_steps = 0;
     for (int q = 0; q < depth;) {
@@ -289,157 +367,243 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
             q = q2;
         }
     }
-
-    int rc = NEMB_OK;
-    cudaError_t e1;
-#define UP(dst, src, bytes)                                                                  \
-    do {                                                                                     \
-        size_t b_ = (bytes);                                                                 \
-        if ((e1 = cudaMalloc((void **)&(dst), b_ ? b_ : 4)) != cudaSuccess ||                 \
-            (e1 = cudaMemcpyAsync((dst), (src), b_, cudaMemcpyHostToDevice, h->stream)) !=   \
-                cudaSuccess)                                                                 \
-            rc = fail(h, NEMB_E_CUDA, "graph upload: %s", cudaGetErrorString(e1));           \
-    } while (0)
-    UP(h->d_row_ptr, row_ptr, sizeof(int32_t) * ((size_t)n + 1));
-    UP(h->d_col, col, sizeof(int32_t) * (size_t)nnz);
-    UP(h->d_wgt, wgt, sizeof(float) * (size_t)nnz);
-    if (sym) { h->d_rrow_ptr = h->d_row_ptr; h->d_rcol = h->d_col; }
-    else {
-        UP(h->d_rrow_ptr, rrow, sizeof(int32_t) * ((size_t)n + 1));
-        UP(h->d_rcol, rcol, sizeof(int32_t) * (size_t)nnz);
-    }
-    UP(h->d_sites, sites, sizeof(int32_t) * (size_t)n);
-    UP(h->d_level_ptr, lptr, sizeof(int32_t) * ((size_t)depth + 1));
-#undef UP
-    cudaStreamSynchronize(h->stream);
-    free(rrow); free(rcol); free(fill); free(lptr); free(sites);
+    int rc = upload(h, &h->b_sites, sites, sizeof(int32_t) * (size_t)n);
+    if (rc == NEMB_OK) rc = upload(h, &h->b_level_ptr, lptr, sizeof(int32_t) * ((size_t)depth + 1));
+    if (rc == NEMB_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, NEMB_E_CUDA, "level upload");
+    h->d_sites = h->b_sites.p; h->d_level_ptr = h->b_level_ptr.p;
+    free(row_ptr); free(col); free(rrow); free(rcol); free(lptr); free(sites);
+    if (rc == NEMB_OK) h->have_levels = 1;
     return rc;
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-static int load_common(nemb_handle *h, int n, int d, const int32_t *row_ptr, const int32_t *col,
-                       const float *wgt)
+/* shard geometry + graph; X is already on its way to the device */
+static int load_common(nemb_handle *h, int n_glob, int row0, int n_loc, int d,
+                       const int32_t *row_ptr, const int32_t *col, const float *wgt)
 {
-    if (n <= 0 || d <= 0) return fail(h, NEMB_E_ARG, "n and d must be > 0 (n=%d d=%d)", n, d);
-    h->n = n; h->d = d;
-    h->nwt = round_up((n + 31) / 32, 4);
-    int rc = load_graph(h, n, row_ptr, col, wgt);
+    if (n_glob <= 0 || d <= 0) return fail(h, NEMB_E_ARG, "n and d must be > 0 (n=%d d=%d)", n_glob, d);
+    int sl, r0, nl;
+    nemb_shard_range(n_glob, h->world, h->rank, &sl, &r0, &nl);
+    if (row0 != r0 || n_loc != nl)
+        return fail(h, NEMB_E_ARG, "rank %d of %d must own rows [%d,%d) of %d (got [%d,%d))", h->rank,
+                    h->world, r0, r0 + nl, n_glob, row0, row0 + n_loc);
+    h->n = n_loc; h->n_glob = n_glob; h->row0 = row0; h->shard_len = sl;
+    h->lab_len = sl * h->world;
+    h->d = d;
+    h->nwt = round_up((n_loc + 31) / 32, 4);
+    if (h->nwt < 4) h->nwt = 4;
+    int rc = load_graph(h, n_glob, row_ptr, col, wgt);
     if (rc == NEMB_OK) h->loaded = 1;
     return rc;
+}
+
+int nemb_load_shard(nemb_handle *h, int n_glob, int row0, int n_loc, int d, int wpr,
+                    const uint32_t *x, const int32_t *row_ptr, const int32_t *col, const float *wgt)
+{
+    if (!h || (!x && n_loc > 0)) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    reset_problem(h);
+    if (n_loc < 0 || d <= 0) return fail(h, NEMB_E_ARG, "bad shape");
+    if (wpr < (d + 31) / 32) return fail(h, NEMB_E_ARG, "words_per_row %d too small for d=%d", wpr, d);
+    int wpr_dev = round_up(wpr, 4), rc;
+    size_t bytes = sizeof(uint32_t) * (size_t)n_loc * wpr_dev;
+    if ((rc = reserve(h, &h->b_x, bytes)) != NEMB_OK) return rc;
+    h->d_x = h->b_x.p;
+    h->x_owned = 1;
+    if (n_loc > 0) {
+        if (wpr_dev == wpr) {
+            CK(cudaMemcpyAsync(h->d_x, x, bytes, cudaMemcpyHostToDevice, h->stream));
+        } else {
+            CK(cudaMemsetAsync(h->d_x, 0, bytes, h->stream));
+            CK(cudaMemcpy2DAsync(h->d_x, sizeof(uint32_t) * (size_t)wpr_dev, x,
+                                 sizeof(uint32_t) * (size_t)wpr, sizeof(uint32_t) * (size_t)wpr, n_loc,
+                                 cudaMemcpyHostToDevice, h->stream));
+        }
+    }
+    h->wpr = wpr_dev;
+    return load_common(h, n_glob, row0, n_loc, d, row_ptr, col, wgt);
+}
+
+int nemb_load_shard_device(nemb_handle *h, int n_glob, int row0, int n_loc, int d, int wpr,
+                           const uint32_t *x_dev, const int32_t *row_ptr, const int32_t *col,
+                           const float *wgt)
+{
+    if (!h || (!x_dev && n_loc > 0)) return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    reset_problem(h);
+    if (wpr % 4 || wpr < (d + 31) / 32)
+        return fail(h, NEMB_E_ARG, "device X needs words_per_row %% 4 == 0 and >= ceil(d/32)");
+    h->d_x = (uint32_t *)x_dev;
+    h->x_owned = 0;
+    h->wpr = wpr;
+    return load_common(h, n_glob, row0, n_loc, d, row_ptr, col, wgt);
+}
+
+static int need_single(nemb_handle *h, const char *what)
+{
+    if (h->world > 1) return fail(h, NEMB_E_ARG, "%s is a single-GPU entry point; use nemb_load_shard", what);
+    return NEMB_OK;
 }
 
 int nemb_load_packed(nemb_handle *h, int n, int d, int wpr, const uint32_t *x,
                      const int32_t *row_ptr, const int32_t *col, const float *wgt)
 {
     if (!h || !x) return NEMB_E_ARG;
-    CK(cudaSetDevice(h->device));
-    free_problem(h);
-    if (wpr < (d + 31) / 32) return fail(h, NEMB_E_ARG, "words_per_row %d too small for d=%d", wpr, d);
-    int wpr_dev = round_up(wpr, 4);
-    size_t bytes = sizeof(uint32_t) * (size_t)n * wpr_dev;
-    CK(cudaMalloc((void **)&h->d_x, bytes));
-    h->x_owned = 1;
-    if (wpr_dev == wpr) {
-        CK(cudaMemcpyAsync(h->d_x, x, bytes, cudaMemcpyHostToDevice, h->stream));
-    } else {
-        CK(cudaMemsetAsync(h->d_x, 0, bytes, h->stream));
-        CK(cudaMemcpy2DAsync(h->d_x, sizeof(uint32_t) * (size_t)wpr_dev, x,
-                             sizeof(uint32_t) * (size_t)wpr, sizeof(uint32_t) * (size_t)wpr, n,
-                             cudaMemcpyHostToDevice, h->stream));
-    }
-    h->wpr = wpr_dev;
-    return load_common(h, n, d, row_ptr, col, wgt);
+    int rc = need_single(h, "nemb_load_packed");
+    if (rc != NEMB_OK) return rc;
+    return nemb_load_shard(h, n, 0, n, d, wpr, x, row_ptr, col, wgt);
 }
 
 int nemb_load_packed_device(nemb_handle *h, int n, int d, int wpr, const uint32_t *x_dev,
                             const int32_t *row_ptr, const int32_t *col, const float *wgt)
 {
     if (!h || !x_dev) return NEMB_E_ARG;
-    CK(cudaSetDevice(h->device));
-    free_problem(h);
-    if (wpr % 4 || wpr < (d + 31) / 32)
-        return fail(h, NEMB_E_ARG, "device X needs words_per_row %% 4 == 0 and >= ceil(d/32)");
-    h->d_x = (uint32_t *)x_dev;
-    h->x_owned = 0;
-    h->wpr = wpr;
-    return load_common(h, n, d, row_ptr, col, wgt);
+    int rc = need_single(h, "nemb_load_packed_device");
+    if (rc != NEMB_OK) return rc;
+    return nemb_load_shard_device(h, n, 0, n, d, wpr, x_dev, row_ptr, col, wgt);
 }
 
 int nemb_load_dense_u8(nemb_handle *h, int n, int d, const uint8_t *x, const int32_t *row_ptr,
                        const int32_t *col, const float *wgt)
 {
     if (!h || !x) return NEMB_E_ARG;
+    int rc = need_single(h, "nemb_load_dense_u8");
+    if (rc != NEMB_OK) return rc;
     CK(cudaSetDevice(h->device));
-    free_problem(h);
+    reset_problem(h);
     if (n <= 0 || d <= 0) return fail(h, NEMB_E_ARG, "n and d must be > 0");
     int wpr = round_up((d + 31) / 32, 4);
-    uint8_t *d_dense = NULL;
-    CK(cudaMalloc((void **)&d_dense, (size_t)n * d));
-    CK(cudaMalloc((void **)&h->d_x, sizeof(uint32_t) * (size_t)n * wpr));
+    /* the dense bytes are staged in the (not yet needed) transposed-bits buffer */
+    if ((rc = reserve(h, &h->b_xt, (size_t)n * d)) != NEMB_OK) return rc;
+    if ((rc = reserve(h, &h->b_x, sizeof(uint32_t) * (size_t)n * wpr)) != NEMB_OK) return rc;
+    h->d_x = h->b_x.p;
     h->x_owned = 1;
-    CK(cudaMemcpyAsync(d_dense, x, (size_t)n * d, cudaMemcpyHostToDevice, h->stream));
-    nemk_pack_u8(h->stream, d_dense, n, d, wpr, h->d_x);
+    CK(cudaMemcpyAsync(h->b_xt.p, x, (size_t)n * d, cudaMemcpyHostToDevice, h->stream));
+    nemk_pack_u8(h->stream, h->b_xt.p, n, d, wpr, h->d_x);
     CKK();
-    CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_dense);
     h->wpr = wpr;
-    return load_common(h, n, d, row_ptr, col, wgt);
+    return load_common(h, n, 0, n, d, row_ptr, col, wgt);
 }
 
 /* ------------------------------------------------------------------ per-K buffers */
+static size_t carve(size_t *off, size_t bytes)
+{
+    size_t at = (*off + 255) & ~(size_t)255;
+    *off = at + bytes;
+    return at;
+}
+
 static int ensure_k(nemb_handle *h, int k)
 {
     if (h->k_alloc == k) return NEMB_OK;
-    free_k(h);
-    size_t n = h->n, d = h->d, kd = (size_t)k * d, kw = (size_t)k * h->wpr;
-    CK(cudaMalloc((void **)&h->d_prop, sizeof(float) * k));
-    CK(cudaMalloc((void **)&h->d_center, sizeof(float) * kd));
-    CK(cudaMalloc((void **)&h->d_disp, sizeof(float) * kd));
-    CK(cudaMalloc((void **)&h->d_iner, sizeof(float) * kd));
-    CK(cudaMalloc((void **)&h->d_coef, sizeof(nemk_coef)));
-    CK(cudaMemset(h->d_coef, 0, sizeof(nemk_coef)));
-    CK(cudaMalloc((void **)&h->d_mxor, sizeof(uint32_t) * kw));
-    CK(cudaMalloc((void **)&h->d_mval, sizeof(uint32_t) * kw));
-    CK(cudaMalloc((void **)&h->d_f0, sizeof(uint32_t) * kw));
-    CK(cudaMalloc((void **)&h->d_f1, sizeof(uint32_t) * kw));
-    CK(cudaMalloc((void **)&h->d_delta, sizeof(double) * (kd + k)));
-    CK(cudaMalloc((void **)&h->d_logpf, sizeof(double) * n * k));
-    for (int b = 0; b < 2; b++) {
-        CK(cudaMalloc((void **)&h->d_lab[b], n));
-        CK(cudaMalloc((void **)&h->d_t[b], sizeof(float) * n * k));
-        CK(cudaMalloc((void **)&h->d_wl[b], sizeof(int32_t) * n));
+    size_t n = h->n, d = h->d, kd = (size_t)k * d, kw = (size_t)k * h->wpr, L = h->lab_len;
+    size_t W = h->world, stat = kd + k;
+    h->crit_blocks = h->world > 1 ? CRIT_BLOCKS_SHARD : (int)((n + 255) / 256);
+    if (h->crit_blocks > CRIT_BLOCKS_MAX) h->crit_blocks = CRIT_BLOCKS_MAX;
+    if (h->crit_blocks < 1) h->crit_blocks = 1;
+    size_t off = 0;
+    size_t o_prop = carve(&off, sizeof(float) * k), o_center = carve(&off, sizeof(float) * kd);
+    size_t o_disp = carve(&off, sizeof(float) * kd), o_iner = carve(&off, sizeof(float) * kd);
+    size_t o_coef = carve(&off, sizeof(nemk_coef));
+    size_t o_mxor = carve(&off, 4 * kw), o_mval = carve(&off, 4 * kw);
+    size_t o_f0 = carve(&off, 4 * kw), o_f1 = carve(&off, 4 * kw);
+    size_t o_delta = carve(&off, sizeof(double) * (kd + k));
+    size_t o_logpf = carve(&off, sizeof(double) * n * k);
+    size_t o_lab0 = carve(&off, L), o_lab1 = carve(&off, L), o_lab2 = carve(&off, L);
+    size_t o_dirty = carve(&off, 4 * L);
+    size_t o_wl0 = carve(&off, 4 * (n + 1)), o_wl1 = carve(&off, 4 * (n + 1));
+    size_t o_wlc = carve(&off, 4 * 8);
+    size_t o_cm = carve(&off, 4 * (size_t)k * h->nwt);
+    size_t o_si = carve(&off, 4 * stat), o_sis = carve(&off, 4 * stat * W);
+    size_t o_sd = carve(&off, 8 * stat), o_sds = carve(&off, 8 * stat * W);
+    size_t o_crit = carve(&off, sizeof(double) * 4 * h->crit_blocks * W);
+    size_t o_status = carve(&off, sizeof(iter_status));
+    size_t o_cnt = carve(&off, sizeof(nemk_counters) * W);
+    int rc = reserve(h, &h->b_slab, off);
+    if (rc != NEMB_OK) return rc;
+    char *base = h->b_slab.p;
+    h->d_prop = (float *)(base + o_prop); h->d_center = (float *)(base + o_center);
+    h->d_disp = (float *)(base + o_disp); h->d_iner = (float *)(base + o_iner);
+    h->d_coef = (nemk_coef *)(base + o_coef);
+    h->d_mxor = (uint32_t *)(base + o_mxor); h->d_mval = (uint32_t *)(base + o_mval);
+    h->d_f0 = (uint32_t *)(base + o_f0); h->d_f1 = (uint32_t *)(base + o_f1);
+    h->d_delta = (double *)(base + o_delta); h->d_logpf = (double *)(base + o_logpf);
+    h->d_lab[0] = (uint8_t *)(base + o_lab0); h->d_lab[1] = (uint8_t *)(base + o_lab1);
+    h->d_lab[2] = (uint8_t *)(base + o_lab2);
+    h->d_dirty = (int32_t *)(base + o_dirty);
+    h->d_wl[0] = (int32_t *)(base + o_wl0); h->d_wl[1] = (int32_t *)(base + o_wl1);
+    h->d_wl_counts = (int32_t *)(base + o_wlc);
+    h->d_cm = (uint32_t *)(base + o_cm);
+    h->d_stat_int = (int32_t *)(base + o_si); h->d_stat_int_stage = (int32_t *)(base + o_sis);
+    h->d_stat_dbl = (double *)(base + o_sd); h->d_stat_dbl_stage = (double *)(base + o_sds);
+    h->d_crit_partials = (double *)(base + o_crit);
+    h->d_status = (iter_status *)(base + o_status);
+    h->d_cnt_all = (nemk_counters *)(base + o_cnt);
+    CK(cudaMemsetAsync(h->d_coef, 0, sizeof(nemk_coef), h->stream));
+    CK(cudaMemsetAsync(h->d_dirty, 0, 4 * L, h->stream));
+    CK(cudaMemsetAsync(h->d_wl_counts, 0, 4 * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_status, 0, sizeof(iter_status), h->stream));
+    h->d_t[0] = h->d_t[1] = NULL;
+    h->d_partial_s = h->d_partial_n = NULL;
+    if (!h->h_status) CK(cudaMallocHost((void **)&h->h_status, sizeof(iter_status)));
+    if (!h->h_cnt_all) CK(cudaMallocHost((void **)&h->h_cnt_all, sizeof(nemk_counters) * MAX_WORLD));
+    if (!h->h_empty) CK(cudaMallocHost((void **)&h->h_empty, sizeof(int32_t)));
+    h->k_alloc = k;
+    return NEMB_OK;
+}
+
+/* float posteriors [lab_len][K]: only algo nem (both buffers) and nemb_get_posteriors (one) */
+static int ensure_t(nemb_handle *h, int k, int both)
+{
+    size_t bytes = sizeof(float) * (size_t)h->lab_len * k;
+    for (int b = 0; b < (both ? 2 : 1); b++) {
+        int rc = reserve(h, &h->b_t[b], bytes);
+        if (rc != NEMB_OK) return rc;
+        h->d_t[b] = h->b_t[b].p;
     }
-    CK(cudaMalloc((void **)&h->d_dirty, sizeof(int32_t) * n));
-    CK(cudaMemset(h->d_dirty, 0, sizeof(int32_t) * n));
-    CK(cudaMalloc((void **)&h->d_wl_counts, sizeof(int32_t) * 8));
-    CK(cudaMemset(h->d_wl_counts, 0, sizeof(int32_t) * 8));
-    CK(cudaMalloc((void **)&h->d_cm, sizeof(uint32_t) * (size_t)k * h->nwt));
-    CK(cudaMalloc((void **)&h->d_nk_int, sizeof(int32_t) * k));
-    CK(cudaMalloc((void **)&h->d_s_int, sizeof(int32_t) * kd));
+    return NEMB_OK;
+}
+
+/* fuzzy M-step scratch: per-chunk partial sums */
+static int ensure_nem_scratch(nemb_handle *h, int k)
+{
+    size_t kd = (size_t)k * h->d;
     h->rows_per_chunk = 4096;
     h->nchunks = (h->n + h->rows_per_chunk - 1) / h->rows_per_chunk;
-    CK(cudaMalloc((void **)&h->d_partial_s, sizeof(double) * kd * h->nchunks));
-    CK(cudaMalloc((void **)&h->d_partial_n, sizeof(double) * (size_t)k * h->nchunks));
-    CK(cudaMalloc((void **)&h->d_s_dbl, sizeof(double) * kd));
-    CK(cudaMalloc((void **)&h->d_nk_dbl, sizeof(double) * k));
-    h->crit_blocks = 1184; /* 148 SMs x 8 */
-    CK(cudaMalloc((void **)&h->d_crit_partials, sizeof(double) * 4 * h->crit_blocks));
-    CK(cudaMalloc((void **)&h->d_status, sizeof(iter_status)));
-    CK(cudaMemset(h->d_status, 0, sizeof(iter_status)));
-    CK(cudaMallocHost((void **)&h->h_status, sizeof(iter_status)));
-    CK(cudaMallocHost((void **)&h->h_empty, sizeof(int32_t)));
-    h->k_alloc = k;
+    if (h->nchunks < 1) h->nchunks = 1;
+    size_t off = 0;
+    size_t o_s = carve(&off, sizeof(double) * kd * h->nchunks);
+    size_t o_n = carve(&off, sizeof(double) * (size_t)k * h->nchunks);
+    int rc = reserve(h, &h->b_nem, off);
+    if (rc != NEMB_OK) return rc;
+    h->d_partial_s = (double *)((char *)h->b_nem.p + o_s);
+    h->d_partial_n = (double *)((char *)h->b_nem.p + o_n);
     return NEMB_OK;
 }
 
 static int ensure_xt(nemb_handle *h)
 {
     if (h->have_xt) return NEMB_OK;
-    CK(cudaMalloc((void **)&h->d_xt, sizeof(uint32_t) * (size_t)h->d * h->nwt));
+    int rc = reserve(h, &h->b_xt, sizeof(uint32_t) * (size_t)h->d * h->nwt);
+    if (rc != NEMB_OK) return rc;
+    h->d_xt = h->b_xt.p;
     nemk_transpose_bits(h->stream, h->d_x, h->n, h->wpr, h->d, h->nwt, h->d_xt);
     CKK();
     h->have_xt = 1;
+    return NEMB_OK;
+}
+
+/* ------------------------------------------------------------------ collectives */
+static int gather(nemb_handle *h, const void *send, void *recv, size_t bytes_per_rank)
+{
+    if (h->world <= 1) {
+        if (send != recv) CK(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, h->stream));
+        return NEMB_OK;
+    }
+    int rc = h->comm->allgather(h->comm->ctx, send, recv, bytes_per_rank, (void *)h->stream);
+    h->exchanges++;
+    if (rc) return fail(h, NEMB_E_CUDA, "all-gather failed on rank %d (code %d)", h->rank, rc);
     return NEMB_OK;
 }
 
@@ -499,44 +663,100 @@ static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming)
     return NEMB_OK;
 }
 
+/* counters of the last sweep, summed over the ranks, on the host (one sync) */
+static int read_status(nemb_handle *h)
+{
+    int rc = gather(h, &h->d_status->cnt, h->d_cnt_all, sizeof(nemk_counters));
+    if (rc != NEMB_OK) return rc;
+    CK(cudaMemcpyAsync(h->h_cnt_all, h->d_cnt_all, sizeof(nemk_counters) * h->world, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    nemk_counters tot;
+    memset(&tot, 0, sizeof tot);
+    for (int r = 0; r < h->world; r++) {
+        const nemk_counters *c = &h->h_cnt_all[r];
+        tot.changed += c->changed; tot.allnul += c->allnul; tot.ties += c->ties;
+        tot.pending += c->pending;
+        if (c->nfix > tot.nfix) tot.nfix = c->nfix;
+        if (c->maxdiff > tot.maxdiff) tot.maxdiff = c->maxdiff;
+    }
+    h->h_status->cnt = tot;
+    return NEMB_OK;
+}
+
+/* jacobi round 0 left the first work list in list 0 / counter 0: three grid-wide rounds, then
+ * one CTA walks the tail to exhaustion (and leaves the four counters at 0) */
+enum { GRID_ROUNDS = 3 };
+static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, uint8_t *out,
+                         const int32_t *rp, const int32_t *skip)
+{
+    for (int r = 0; r < GRID_ROUNDS; r++)
+        nemk_sweep_ncem_fixup_round(h->stream, k, h->row0, h->n, h->d_logpf, rp, h->d_col, h->d_wgt,
+                                    beta, in, out, h->d_dirty, h->d_wl[0], h->d_wl[1],
+                                    h->d_wl_counts, r, h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt,
+                                    skip);
+    nemk_sweep_ncem_fixup(h->stream, k, h->row0, h->n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+                          out, h->d_dirty, h->d_wl[0], h->d_wl[1], h->d_wl_counts, GRID_ROUNDS,
+                          h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip);
+    h->launches += 1 + GRID_ROUNDS;
+}
+
 /* one E-step sweep; *flipped tells whether the state moved to the other buffer */
 static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *flipped)
 {
-    int k = o->k, n = h->n;
+    int k = o->k, n = h->n, row0 = h->row0, rc;
     const int32_t *skip = &h->d_coef->empty_class;
     const int32_t *rp = h->spatial ? h->d_row_ptr : NULL;
     int seq = o->update == NEMB_UPDATE_SEQ && h->spatial && beta != 0.0;
+    size_t L = h->lab_len, SL = h->shard_len;
     *flipped = 0;
     CK(cudaMemsetAsync(&h->d_status->cnt, 0, sizeof(nemk_counters), h->stream));
     STAGE_BEGIN(ST_SWEEP);
     if (o->algo == NEMB_ALGO_NCEM) {
-        uint8_t *in = h->d_lab[h->cur], *out = h->d_lab[h->cur ^ 1];
+        uint8_t *in = h->d_lab[h->cur], *out = h->d_lab[h->cur ^ 1], *seen = h->d_lab[2];
         int impl = o->sweep_impl == NEMB_SWEEP_AUTO ? NEMB_SWEEP_SPEC : o->sweep_impl;
         if (!seq) {
-            nemk_sweep_ncem_jacobi(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+            nemk_sweep_ncem_jacobi(h->stream, k, row0, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
                                    out, NULL, NULL, NULL, NULL, NULL, &h->d_status->cnt, skip);
             h->launches++;
+            /* halo exchange of the hard labels: every rank's slice, 1 byte per family */
+            if (h->world > 1 && (rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
             *flipped = 1;
         } else if (impl == NEMB_SWEEP_SPEC) {
-            /* round 0 (Jacobi) fills list 0; GRID_ROUNDS grid-wide rounds ping-pong the two lists
-             * through per-round counters (all zeroed above); one CTA finishes the tail */
-            enum { GRID_ROUNDS = 3 };
-            CK(cudaMemsetAsync(h->d_wl_counts, 0, sizeof(int32_t) * 8, h->stream));
-            nemk_sweep_ncem_jacobi(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+            if (h->world > 1) {   /* remote labels start at their old value, here and in `seen` */
+                CK(cudaMemcpyAsync(out, in, L, cudaMemcpyDeviceToDevice, h->stream));
+                CK(cudaMemcpyAsync(seen, in, L, cudaMemcpyDeviceToDevice, h->stream));
+            }
+            nemk_sweep_ncem_jacobi(h->stream, k, row0, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
                                    out, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
                                    h->d_rcol, &h->d_status->cnt, skip);
-            for (int r = 0; r < GRID_ROUNDS; r++)
-                nemk_sweep_ncem_fixup_round(h->stream, k, h->d_logpf, rp, h->d_col, h->d_wgt, beta,
-                                            in, out, h->d_dirty, h->d_wl[r & 1], h->d_wl[(r + 1) & 1],
-                                            &h->d_wl_counts[r], &h->d_wl_counts[r + 1],
-                                            h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip);
-            nemk_sweep_ncem_fixup(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
-                                  out, h->d_dirty, h->d_wl[GRID_ROUNDS & 1],
-                                  h->d_wl[(GRID_ROUNDS + 1) & 1], &h->d_wl_counts[GRID_ROUNDS],
-                                  h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip);
-            h->launches += 2 + GRID_ROUNDS;
+            h->launches++;
+            local_fixups(h, k, beta, in, out, rp, skip);
+            if (h->world > 1) {
+                /* speculative fixed point ACROSS ranks: exchange label slices, queue the local
+                 * readers of every remote label that moved, fix up, until no rank queues anything
+                 * (then every rank holds the sequential sweep's labels for all families) */
+                enum { ROUNDS_PER_CHECK = 2 };
+                for (int guard = 0;; guard++) {
+                    for (int r = 0; r < ROUNDS_PER_CHECK; r++) {
+                        if ((rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
+                        CK(cudaMemsetAsync(&h->d_status->cnt.pending, 0, sizeof(int32_t), h->stream));
+                        nemk_mark_remote(h->stream, h->n_glob, row0, n, out, seen, h->d_dirty,
+                                         h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr, h->d_rcol,
+                                         &h->d_status->cnt.pending);
+                        h->launches++;
+                        if (r + 1 < ROUNDS_PER_CHECK) local_fixups(h, k, beta, in, out, rp, skip);
+                    }
+                    if ((rc = read_status(h)) != NEMB_OK) return rc;
+                    if (h->h_status->cnt.pending == 0 || *h->h_empty) break;
+                    if (guard > h->n_glob) return fail(h, NEMB_E_BUG, "sharded sweep did not settle");
+                    local_fixups(h, k, beta, in, out, rp, skip);
+                }
+            }
             *flipped = 1;
         } else {
+            if ((rc = ensure_levels(h)) != NEMB_OK) return rc;
             for (int s = 0; s < h->n_steps; s++) {
                 nemk_sweep_ncem_level(h->stream, k, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
                                       h->d_sites, h->d_level_ptr, h->steps[s].lo, h->steps[s].hi,
@@ -547,11 +767,15 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
     } else {
         float *in = h->d_t[h->cur], *out = h->d_t[h->cur ^ 1];
         if (!seq) {
-            nemk_sweep_nem_jacobi(h->stream, k, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in, out,
-                                  &h->d_status->cnt, skip);
+            nemk_sweep_nem_jacobi(h->stream, k, row0, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+                                  out, &h->d_status->cnt, skip);
             h->launches++;
+            size_t slice = sizeof(float) * SL * k;   /* halo exchange of the posteriors */
+            if (h->world > 1 &&
+                (rc = gather(h, (char *)out + (size_t)h->rank * slice, out, slice)) != NEMB_OK) return rc;
             *flipped = 1;
         } else {
+            if ((rc = ensure_levels(h)) != NEMB_OK) return rc;
             for (int s = 0; s < h->n_steps; s++) {
                 nemk_sweep_nem_level(h->stream, k, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
                                      h->d_sites, h->d_level_ptr, h->steps[s].lo, h->steps[s].hi,
@@ -569,20 +793,38 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
 static int run_mstep(nemb_handle *h, const nemb_options *o)
 {
     int k = o->k, rc;
+    size_t kd = (size_t)k * h->d, stat = kd + k;
     STAGE_BEGIN(ST_MSTEP);
     if (o->algo == NEMB_ALGO_NCEM) {
+        /* exact integer counts: S_kd and n_k of this rank's rows, summed over the ranks */
         if ((rc = ensure_xt(h)) != NEMB_OK) return rc;
-        nemk_label_masks(h->stream, k, h->n, h->nwt, h->d_lab[h->cur], h->d_cm, h->d_nk_int);
-        nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_s_int);
-        nemk_mstep_finalize(h->stream, k, h->n, h->d, o->prop, o->disp, h->d_s_int, h->d_nk_int,
-                            NULL, NULL, h->d_prop, h->d_center, h->d_disp, h->d_iner, h->d_coef);
-        h->launches += 3;
+        nemk_label_masks(h->stream, k, h->n, h->nwt, h->d_lab[h->cur] + h->row0, h->d_cm,
+                         h->d_stat_int + kd);
+        nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_stat_int);
+        h->launches += 2;
+        if (h->world > 1) {
+            if ((rc = gather(h, h->d_stat_int, h->d_stat_int_stage, sizeof(int32_t) * stat)) != NEMB_OK) return rc;
+            nemk_sum_ranks_i32(h->stream, h->world, stat, h->d_stat_int_stage, h->d_stat_int);
+            h->launches++;
+        }
+        nemk_mstep_finalize(h->stream, k, h->n_glob, h->d, o->prop, o->disp, h->d_stat_int,
+                            h->d_stat_int + kd, NULL, NULL, h->d_prop, h->d_center, h->d_disp,
+                            h->d_iner, h->d_coef);
+        h->launches++;
     } else {
-        nemk_mstep_nem(h->stream, k, h->n, h->d, h->wpr, h->d_x, h->d_t[h->cur], h->rows_per_chunk,
-                       h->d_partial_s, h->d_partial_n, h->d_s_dbl, h->d_nk_dbl);
-        nemk_mstep_finalize(h->stream, k, h->n, h->d, o->prop, o->disp, NULL, NULL, h->d_s_dbl,
-                            h->d_nk_dbl, h->d_prop, h->d_center, h->d_disp, h->d_iner, h->d_coef);
-        h->launches += 3;
+        if ((rc = ensure_nem_scratch(h, k)) != NEMB_OK) return rc;
+        nemk_mstep_nem(h->stream, k, h->n, h->d, h->wpr, h->d_x,
+                       h->d_t[h->cur] + (size_t)h->row0 * k, h->rows_per_chunk, h->d_partial_s,
+                       h->d_partial_n, h->d_stat_dbl, h->d_stat_dbl + kd);
+        h->launches += 2;
+        if (h->world > 1) {   /* rank-ordered float64 sum: same bits on every rank, every run */
+            if ((rc = gather(h, h->d_stat_dbl, h->d_stat_dbl_stage, sizeof(double) * stat)) != NEMB_OK) return rc;
+            nemk_sum_ranks_f64(h->stream, h->world, stat, h->d_stat_dbl_stage, h->d_stat_dbl);
+            h->launches++;
+        }
+        nemk_mstep_finalize(h->stream, k, h->n_glob, h->d, o->prop, o->disp, NULL, NULL, h->d_stat_dbl,
+                            h->d_stat_dbl + kd, h->d_prop, h->d_center, h->d_disp, h->d_iner, h->d_coef);
+        h->launches++;
     }
     STAGE_END();
     CKK();
@@ -591,11 +833,16 @@ static int run_mstep(nemb_handle *h, const nemb_options *o)
 
 static int run_criteria(nemb_handle *h, const nemb_options *o, double beta, double *d_out)
 {
+    int rc;
     STAGE_BEGIN(ST_CRIT);
-    nemk_criteria(h->stream, o->k, h->n, h->d_logpf, h->spatial ? h->d_row_ptr : NULL, h->d_col,
-                  h->d_wgt, beta, o->algo == NEMB_ALGO_NCEM ? h->d_lab[h->cur] : NULL,
-                  o->algo == NEMB_ALGO_NCEM ? NULL : h->d_t[h->cur], h->d_crit_partials,
-                  h->crit_blocks, d_out);
+    size_t mine = (size_t)h->rank * h->crit_blocks * 4;
+    nemk_criteria_partial(h->stream, o->k, h->row0, h->n, h->d_logpf, h->spatial ? h->d_row_ptr : NULL,
+                          h->d_col, h->d_wgt, beta, o->algo == NEMB_ALGO_NCEM ? h->d_lab[h->cur] : NULL,
+                          o->algo == NEMB_ALGO_NCEM ? NULL : h->d_t[h->cur], h->d_crit_partials + mine,
+                          h->crit_blocks);
+    if (h->world > 1 && (rc = gather(h, h->d_crit_partials + mine, h->d_crit_partials,
+                                     sizeof(double) * 4 * h->crit_blocks)) != NEMB_OK) return rc;
+    nemk_criteria_final(h->stream, h->crit_blocks * h->world, h->d_crit_partials, beta, d_out);
     STAGE_END();
     h->launches += 2;
     CKK();
@@ -612,23 +859,26 @@ static int check_options(nemb_handle *h, const nemb_options *o)
     if (o->conv != NEMB_CONV_NONE && !(o->conv_thr > 0)) return fail(h, NEMB_E_ARG, "conv threshold must be > 0");
     if (o->prop < 0 || o->prop > 1 || o->disp < 0 || o->disp > 3) return fail(h, NEMB_E_ARG, "bad model");
     if (o->it_max < 0) return fail(h, NEMB_E_ARG, "it_max must be >= 0");
-    return NEMB_OK;
-}
-
-static int read_status(nemb_handle *h)
-{
-    CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (h->world > 1 && h->spatial && o->update == NEMB_UPDATE_SEQ) {
+        if (o->algo == NEMB_ALGO_NEM)
+            return fail(h, NEMB_E_ARG, "row shards: the sequential fuzzy sweep is single-GPU only (use update=para)");
+        if (o->sweep_impl == NEMB_SWEEP_LEVEL)
+            return fail(h, NEMB_E_ARG, "row shards: the level-scheduled sweep is single-GPU only");
+    }
     return NEMB_OK;
 }
 
 static int init_state(nemb_handle *h, const nemb_options *o)
 {
+    int rc;
     h->cur = 0;
     h->state_labels = o->algo == NEMB_ALGO_NCEM;
-    if (h->state_labels) CK(cudaMemsetAsync(h->d_lab[0], 255, h->n, h->stream));
-    else CK(cudaMemsetAsync(h->d_t[0], 0, sizeof(float) * (size_t)h->n * o->k, h->stream));
+    if (h->state_labels) CK(cudaMemsetAsync(h->d_lab[0], 255, h->lab_len, h->stream));
+    else {
+        if ((rc = ensure_t(h, o->k, 1)) != NEMB_OK) return rc;
+        CK(cudaMemsetAsync(h->d_t[0], 0, sizeof(float) * (size_t)h->lab_len * o->k, h->stream));
+        CK(cudaMemsetAsync(h->d_t[1], 0, sizeof(float) * (size_t)h->lab_len * o->k, h->stream));
+    }
     CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, sizeof(int32_t), h->stream));
     return NEMB_OK;
 }
@@ -702,11 +952,11 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
                 for (int c = 0; c < k; c++) nk_host[c] = NAN;
             } else if (o->algo == NEMB_ALGO_NCEM) {
                 int32_t ni[NEMB_MAX_K];
-                CK(cudaMemcpy(ni, h->d_nk_int, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ni, h->d_stat_int + kd, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
                 for (int c = 0; c < k; c++) nk_host[c] = (float)ni[c];
             } else {
                 double nd[NEMB_MAX_K];
-                CK(cudaMemcpy(nd, h->d_nk_dbl, sizeof(double) * k, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(nd, h->d_stat_dbl + kd, sizeof(double) * k, cudaMemcpyDeviceToHost));
                 for (int c = 0; c < k; c++) nk_host[c] = (float)nd[c];
             }
             cb(user, iter, h->h_status->crit_before, h->h_status->crit_after, prop, center, disp, nk_host);
@@ -721,7 +971,9 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
-    if ((rc = read_status(h)) != NEMB_OK) return rc;
+    CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     if (iter == 0 && *h->h_empty) { status = NEMB_W_EMPTYCLASS; empty = *h->h_empty; }
     res->status = status; res->iters = iter; res->converged = converged; res->empty_class = empty;
     const double *c6 = h->h_status->crit_after;
@@ -757,7 +1009,7 @@ int nemb_fit_logged(nemb_handle *h, const nemb_options *o, float *prop, float *c
     if ((rc = check_options(h, o)) != NEMB_OK) return rc;
     if ((rc = ensure_k(h, o->k)) != NEMB_OK) return rc;
     memset(res, 0, sizeof *res);
-    h->launches = 0; h->fixup_rounds = 0; h->profile = o->profile; h->ev_n = 0;
+    h->launches = 0; h->fixup_rounds = 0; h->exchanges = 0; h->profile = o->profile; h->ev_n = 0;
     size_t kd = (size_t)o->k * h->d;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -786,14 +1038,15 @@ int nemb_get_posteriors(nemb_handle *h, float *t_out)
 {
     if (!h || !t_out || !h->k_alloc) return NEMB_E_ARG;
     CK(cudaSetDevice(h->device));
-    int k = h->k_alloc;
+    int k = h->k_alloc, rc;
     float *src = h->d_t[h->cur];
     if (h->state_labels) {
+        if ((rc = ensure_t(h, k, 0)) != NEMB_OK) return rc;
         src = h->d_t[0];
-        nemk_labels_to_t(h->stream, k, h->n, h->d_lab[h->cur], src);
+        nemk_labels_to_t(h->stream, k, h->n_glob, h->d_lab[h->cur], src);
         CKK();
     }
-    CK(cudaMemcpyAsync(t_out, src, sizeof(float) * (size_t)h->n * k, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(t_out, src, sizeof(float) * (size_t)h->n_glob * k, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return NEMB_OK;
 }
@@ -803,24 +1056,33 @@ int nemb_get_labels(nemb_handle *h, int32_t *label_out)
     if (!h || !label_out || !h->k_alloc) return NEMB_E_ARG;
     CK(cudaSetDevice(h->device));
     uint8_t *src = h->d_lab[h->cur];
+    int n = h->n_glob;
     if (!h->state_labels) {
         src = h->d_lab[0];
-        nemk_t_to_labels(h->stream, h->k_alloc, h->n, h->d_t[h->cur], src);
+        nemk_t_to_labels(h->stream, h->k_alloc, n, h->d_t[h->cur], src);
         CKK();
     }
-    uint8_t *tmp = malloc(h->n);
+    uint8_t *tmp = malloc(n);
     if (!tmp) return fail(h, NEMB_E_MEMORY, "host alloc");
-    cudaError_t e = cudaMemcpyAsync(tmp, src, h->n, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaMemcpyAsync(tmp, src, n, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { free(tmp); return fail(h, NEMB_E_CUDA, "%s", cudaGetErrorString(e)); }
-    for (int i = 0; i < h->n; i++) label_out[i] = tmp[i] == 255 ? -1 : tmp[i];
+    for (int i = 0; i < n; i++) label_out[i] = tmp[i] == 255 ? -1 : tmp[i];
     free(tmp);
     return NEMB_OK;
 }
 
-int nemb_get_dims(const nemb_handle *h, int *n, int *d, int *wpr, int *nwt, int *depth, int *nnz)
+/* n = rows this rank holds; depth = Gauss-Seidel DAG depth (builds the level schedule on first
+ * request; 0 on row shards and for non-spatial data) */
+int nemb_get_dims(const nemb_handle *hc, int *n, int *d, int *wpr, int *nwt, int *depth, int *nnz)
 {
+    nemb_handle *h = (nemb_handle *)hc;
     if (!h || !h->loaded) return NEMB_E_ARG;
+    if (depth && h->spatial && h->world == 1 && !h->have_levels) {
+        if (cudaSetDevice(h->device) != cudaSuccess) return NEMB_E_CUDA;
+        int rc = ensure_levels(h);
+        if (rc != NEMB_OK) return rc;
+    }
     if (n) *n = h->n;
     if (d) *d = h->d;
     if (wpr) *wpr = h->wpr;
@@ -854,6 +1116,9 @@ int nemb_get_levels(nemb_handle *h, int32_t *level)
 {
     if (!h || !h->loaded || !level) return NEMB_E_ARG;
     if (!h->spatial) { for (int i = 0; i < h->n; i++) level[i] = 1; return NEMB_OK; }
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_levels(h);
+    if (rc != NEMB_OK) return rc;
     memcpy(level, h->h_level, sizeof(int32_t) * (size_t)h->n);
     return NEMB_OK;
 }
@@ -876,6 +1141,7 @@ int nemb_stage_density(nemb_handle *h, int k, const float *prop, const float *ce
     if (!h || !h->loaded || !prop || !center || !disp || !logpf_out) return NEMB_E_ARG;
     if (k < 1 || k > NEMB_MAX_K) return fail(h, NEMB_E_ARG, "bad k");
     int rc;
+    if ((rc = need_single(h, "nemb_stage_density")) != NEMB_OK) return rc;
     CK(cudaSetDevice(h->device));
     if ((rc = ensure_k(h, k)) != NEMB_OK) return rc;
     h->profile = 0;
@@ -897,6 +1163,9 @@ int nemb_stage_density(nemb_handle *h, int k, const float *prop, const float *ce
 static int upload_state(nemb_handle *h, const nemb_options *o, const float *t)
 {
     size_t nk = (size_t)h->n * o->k;
+    int rc;
+    if ((rc = need_single(h, "stage entry points")) != NEMB_OK) return rc;
+    if ((rc = ensure_t(h, o->k, 1)) != NEMB_OK) return rc;
     h->cur = 0;
     h->state_labels = o->algo == NEMB_ALGO_NCEM;
     CK(cudaMemcpyAsync(h->d_t[h->state_labels ? 1 : 0], t, sizeof(float) * nk, cudaMemcpyHostToDevice, h->stream));
@@ -949,14 +1218,13 @@ int nemb_stage_mstep(nemb_handle *h, const nemb_options *o, const float *t, floa
     if (nk_out || skd_out) {
         if (o->algo == NEMB_ALGO_NCEM) {
             int32_t *ti = malloc(sizeof(int32_t) * (kd + k));
-            CK(cudaMemcpy(ti, h->d_s_int, sizeof(int32_t) * kd, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(ti + kd, h->d_nk_int, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ti, h->d_stat_int, sizeof(int32_t) * (kd + k), cudaMemcpyDeviceToHost));
             if (skd_out) for (size_t q = 0; q < kd; q++) skd_out[q] = ti[q];
             if (nk_out) for (int c = 0; c < k; c++) nk_out[c] = ti[kd + c];
             free(ti);
         } else {
-            if (skd_out) CK(cudaMemcpy(skd_out, h->d_s_dbl, sizeof(double) * kd, cudaMemcpyDeviceToHost));
-            if (nk_out) CK(cudaMemcpy(nk_out, h->d_nk_dbl, sizeof(double) * k, cudaMemcpyDeviceToHost));
+            if (skd_out) CK(cudaMemcpy(skd_out, h->d_stat_dbl, sizeof(double) * kd, cudaMemcpyDeviceToHost));
+            if (nk_out) CK(cudaMemcpy(nk_out, h->d_stat_dbl + kd, sizeof(double) * k, cudaMemcpyDeviceToHost));
         }
     }
     return NEMB_OK;
@@ -1002,7 +1270,9 @@ int nemb_fit_random(nemb_handle *h, const nemb_options *o, int n_starts, int64_t
     int rc, k = o->k;
     CK(cudaSetDevice(h->device));
     if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if ((rc = need_single(h, "nemb_fit_random")) != NEMB_OK) return rc;
     if ((rc = ensure_k(h, k)) != NEMB_OK) return rc;
+    if (o->algo != NEMB_ALGO_NCEM && (rc = ensure_t(h, k, 1)) != NEMB_OK) return rc;
     if (n_starts <= 0) n_starts = 50;                       /* DEFAULT_NBRANDINITS */
     uint64_t rng = seed ? (uint64_t)seed : 42;
     int n = h->n, d = h->d, wpr = h->wpr;

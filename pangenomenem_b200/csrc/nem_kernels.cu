@@ -592,35 +592,42 @@ static __device__ __forceinline__ int site_argmax(int K, const double *__restric
 // the work list of the next round.
 static __device__ __forceinline__ void mark_readers(int i, const int32_t *__restrict__ rrow_ptr,
                                                     const int32_t *__restrict__ rcol,
-                                                    int32_t *dirty, int32_t *wl, int32_t *wl_count) {
+                                                    int32_t *dirty, int32_t *wl, int32_t *wl_count,
+                                                    int row0, int row1) {
     int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
     for (int e = lo; e < hi; e++) {
         int j = rcol[e];
-        if (j > i && atomicExch(&dirty[j], 1) == 0) wl[atomicAdd(wl_count, 1)] = j;
+        // only sites this rank owns ([row0,row1), the whole graph on one GPU) are queued here;
+        // the owner of a remote reader queues it when it sees i's new label (k_mark_remote)
+        if (j > i && j >= row0 && j < row1 && atomicExch(&dirty[j], 1) == 0)
+            wl[atomicAdd(wl_count, 1)] = j;
     }
 }
 
 // ---- ncem, parallel (Jacobi) update; also round 0 of the speculative sequential sweep
 // (dirty != nullptr): changed sites queue their later readers for the fix-up rounds.
+// Rows [row0, row0+n_loc) of the GLOBAL graph are this rank's (row0 = 0, n_loc = N on one GPU);
+// labels, CSR, dirty flags and work lists are indexed by global family id, logpf by local row.
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_sweep_ncem_jacobi(int K, int n, const double *__restrict__ logpf,
+k_sweep_ncem_jacobi(int K, int row0, int n_loc, const double *__restrict__ logpf,
                     const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                     const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_in,
                     uint8_t *__restrict__ lab_out, int32_t *dirty, int32_t *wl, int32_t *wl_count,
                     const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
                     nemk_counters *cnt, const int32_t *__restrict__ skip) {
     if (skip && *skip) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int il = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = row0 + il;
     int changed = 0, flags = 0;
-    if (i < n) {
+    if (il < n_loc) {
         double ctx[KT];
         ctx_labels<KT>(K, i, beta != 0.0 ? row_ptr : nullptr, col, wgt,
                        [&](int j) { return (unsigned)lab_in[j]; }, ctx);
-        int km = site_argmax<KT>(K, logpf + (size_t)i * K, ctx, beta, flags);
+        int km = site_argmax<KT>(K, logpf + (size_t)il * K, ctx, beta, flags);
         lab_out[i] = (uint8_t)km;
         changed = (km != (int)lab_in[i]);
-        if (changed && dirty) mark_readers(i, rrow_ptr, rcol, dirty, wl, wl_count);
+        if (changed && dirty) mark_readers(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc);
     }
     unsigned bc = __ballot_sync(FULL, changed), bn = __ballot_sync(FULL, flags & 1),
              bt = __ballot_sync(FULL, flags & 2);
@@ -643,7 +650,8 @@ k_sweep_ncem_jacobi(int K, int n, const double *__restrict__ logpf,
 // The first rounds (long work lists) run grid-wide, one launch per round; the tail runs in one
 // CTA that loops until the list is empty.
 template <int KT>
-static __device__ __forceinline__ int fixup_site(int K, int i, const double *__restrict__ logpf,
+static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row1,
+                                                 const double *__restrict__ logpf,
                                                  const int32_t *__restrict__ row_ptr,
                                                  const int32_t *__restrict__ col,
                                                  const float *__restrict__ wgt, double beta,
@@ -658,65 +666,98 @@ static __device__ __forceinline__ int fixup_site(int K, int i, const double *__r
     ctx_labels<KT>(K, i, row_ptr, col, wgt,
                    [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
     int flags;
-    int km = site_argmax<KT>(K, logpf + (size_t)i * K, ctx, beta, flags);
+    int km = site_argmax<KT>(K, logpf + (size_t)(i - row0) * K, ctx, beta, flags);
     int was = __ldcg(lab_cur + i);
     if (km == was) return 0;
     lab_cur[i] = (uint8_t)km;
     __threadfence();
-    mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt);
+    mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1);
     int old = lab_old[i];
     return (km != old) - (was != old);
 }
 
+// Work lists: two lists used alternately, FOUR rotating counters.  Round r consumes list r&1 with
+// count wl_cnt[r&3], appends to list (r+1)&1 through wl_cnt[(r+1)&3] and clears wl_cnt[(r+2)&3]
+// (idle during round r), so no memset sits between rounds.  The tail kernel leaves all four at 0.
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_sweep_ncem_fixup_round(int K, const double *__restrict__ logpf,
+k_sweep_ncem_fixup_round(int K, int row0, int row1, const double *__restrict__ logpf,
                          const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                          const float *__restrict__ wgt, double beta,
                          const uint8_t *__restrict__ lab_old, uint8_t *lab_cur, int32_t *dirty,
-                         const int32_t *__restrict__ cur_list, int32_t *next_list,
-                         const int32_t *__restrict__ cur_cnt, int32_t *next_cnt,
+                         int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt, int round,
                          const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
                          nemk_counters *cnt, const int32_t *__restrict__ skip) {
     if (skip && *skip) return;
-    int count = *cur_cnt;
+    const int32_t *cur_list = (round & 1) ? wl_b : wl_a;
+    int32_t *next_list = (round & 1) ? wl_a : wl_b;
+    int count = wl_cnt[round & 3];
+    int32_t *next_cnt = &wl_cnt[(round + 1) & 3];
+    if (blockIdx.x == 0 && threadIdx.x == 0) wl_cnt[(round + 2) & 3] = 0;
     int dchanged = 0;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x)
-        dchanged += fixup_site<KT>(K, cur_list[idx], logpf, row_ptr, col, wgt, beta, lab_old, lab_cur,
-                                   dirty, next_list, next_cnt, rrow_ptr, rcol);
+        dchanged += fixup_site<KT>(K, cur_list[idx], row0, row1, logpf, row_ptr, col, wgt, beta,
+                                   lab_old, lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
     if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(&cnt->nfix, 1);
 }
 
 template <int KT>
 __global__ void __launch_bounds__(1024)
-k_sweep_ncem_fixup(int K, int n, const double *__restrict__ logpf,
+k_sweep_ncem_fixup(int K, int row0, int row1, const double *__restrict__ logpf,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_old,
                    uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a, int32_t *wl_b,
-                   int32_t *wl_counts /*[2]: a, b*/, const int32_t *__restrict__ rrow_ptr,
+                   int32_t *wl_cnt, int round, const int32_t *__restrict__ rrow_ptr,
                    const int32_t *__restrict__ rcol, nemk_counters *cnt,
                    const int32_t *__restrict__ skip) {
     if (skip && *skip) return;
     __shared__ int s_count;
-    int32_t *cur_list = wl_a, *next_list = wl_b;
-    int32_t *cur_cnt = &wl_counts[0], *next_cnt = &wl_counts[1];
     int rounds = 0, dchanged = 0;
-    for (;;) {
-        if (threadIdx.x == 0) { s_count = *(volatile int32_t *)cur_cnt; *next_cnt = 0; }
+    for (;; round++) {
+        int32_t *cur_list = (round & 1) ? wl_b : wl_a, *next_list = (round & 1) ? wl_a : wl_b;
+        int32_t *next_cnt = &wl_cnt[(round + 1) & 3];
+        if (threadIdx.x == 0) {
+            s_count = *(volatile int32_t *)&wl_cnt[round & 3];
+            *next_cnt = 0;
+        }
         __syncthreads();
         int count = s_count;
         if (count == 0) break;
         rounds++;
         for (int idx = threadIdx.x; idx < count; idx += blockDim.x)
-            dchanged += fixup_site<KT>(K, cur_list[idx], logpf, row_ptr, col, wgt, beta, lab_old,
-                                       lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
+            dchanged += fixup_site<KT>(K, cur_list[idx], row0, row1, logpf, row_ptr, col, wgt, beta,
+                                       lab_old, lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
         __syncthreads();
-        int32_t *tl = cur_list; cur_list = next_list; next_list = tl;
-        int32_t *tc = cur_cnt; cur_cnt = next_cnt; next_cnt = tc;
     }
+    if (threadIdx.x < 4) wl_cnt[threadIdx.x] = 0;
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
     if (threadIdx.x == 0 && rounds) atomicAdd(&cnt->nfix, rounds);
+}
+
+// Row-sharded sweep, after a label exchange: every remote site whose label differs from the one
+// this rank last saw queues the local sites that read it and are visited later.  `pending`
+// accumulates the number of queued sites (the ranks stop exchanging when the global sum is 0).
+__global__ void __launch_bounds__(256)
+k_mark_remote(int n_glob, int row0, int row1, const uint8_t *__restrict__ lab_cur, uint8_t *lab_seen,
+              int32_t *dirty, int32_t *wl, int32_t *wl_count, const int32_t *__restrict__ rrow_ptr,
+              const int32_t *__restrict__ rcol, int32_t *pending) {
+    int queued = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_glob; j += gridDim.x * blockDim.x) {
+        if (j >= row0 && j < row1) continue;
+        uint8_t c = lab_cur[j];
+        if (c == lab_seen[j]) continue;
+        lab_seen[j] = c;
+        int lo = rrow_ptr[j], hi = rrow_ptr[j + 1];
+        for (int e = lo; e < hi; e++) {
+            int i = rcol[e];
+            if (i > j && i >= row0 && i < row1 && atomicExch(&dirty[i], 1) == 0) {
+                wl[atomicAdd(wl_count, 1)] = i;
+                queued++;
+            }
+        }
+    }
+    if (queued) atomicAdd(pending, queued);
 }
 
 // ---- ncem, level-scheduled exact sequential sweep (reference order), in place.
@@ -812,20 +853,21 @@ static __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
 
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_sweep_nem_jacobi(int K, int n, const double *__restrict__ logpf,
+k_sweep_nem_jacobi(int K, int row0, int n_loc, const double *__restrict__ logpf,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const float *__restrict__ wgt, double beta, const float *__restrict__ t_in,
                    float *__restrict__ t_out, nemk_counters *cnt,
                    const int32_t *__restrict__ skip) {
     if (skip && *skip) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int il = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = row0 + il;
     float md = 0.f;
     int allnul = 0;
-    if (i < n) {
+    if (il < n_loc) {
         double ctx[KT];
         ctx_fuzzy<KT>(K, i, beta != 0.0 ? row_ptr : nullptr, col, wgt, t_in, ctx);
         float tn[KT];
-        md = site_softmax<KT>(K, logpf + (size_t)i * K, ctx, beta, t_in + (size_t)i * K, tn, allnul);
+        md = site_softmax<KT>(K, logpf + (size_t)il * K, ctx, beta, t_in + (size_t)i * K, tn, allnul);
 #pragma unroll
         for (int k = 0; k < KT; k++)
             if (k < K) t_out[(size_t)i * K + k] = tn[k];
@@ -1127,13 +1169,14 @@ k_mstep_finalize(int K, int N, int D, int prop_model, int disp_model,
 // =============================================================================================
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_criteria_partial(int K, int n, const double *__restrict__ logpf,
+k_criteria_partial(int K, int row0, int n_loc, const double *__restrict__ logpf,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab,
                    const float *__restrict__ t, double *__restrict__ partials) {
     __shared__ double sh[32];
     double cD = 0, cG = 0, cL = 0, cZ = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int il = blockIdx.x * blockDim.x + threadIdx.x; il < n_loc; il += gridDim.x * blockDim.x) {
+        const int i = row0 + il;
         double ctx[KT];
         float ti[KT];
         if (lab) {
@@ -1146,7 +1189,7 @@ k_criteria_partial(int K, int n, const double *__restrict__ logpf,
 #pragma unroll
             for (int k = 0; k < KT; k++) ti[k] = (k < K) ? t[(size_t)i * K + k] : 0.f;
         }
-        const double *lp = logpf + (size_t)i * K;
+        const double *lp = logpf + (size_t)il * K;
         double lmx = neg_inf(), zmx = neg_inf();
 #pragma unroll
         for (int k = 0; k < KT; k++) {
@@ -1196,6 +1239,53 @@ k_criteria_final(int nblocks, const double *__restrict__ partials, double beta, 
         crit6[3] = D + beta * G + Z;
         crit6[4] = Z; crit6[5] = G;
     }
+}
+
+// out[q] = sum over ranks of stage[r][q], ranks added in order 0..W-1 (deterministic; used to build
+// all-reduces of the M-step statistics on top of a single all-gather)
+__global__ void k_sum_ranks_i32(int world, size_t count, const int32_t *__restrict__ stage,
+                                int32_t *__restrict__ out) {
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    int32_t s = 0;
+    for (int r = 0; r < world; r++) s += stage[(size_t)r * count + q];
+    out[q] = s;
+}
+__global__ void k_sum_ranks_f64(int world, size_t count, const double *__restrict__ stage,
+                                double *__restrict__ out) {
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    double s = 0.0;
+    for (int r = 0; r < world; r++) s += stage[(size_t)r * count + q];
+    out[q] = s;
+}
+
+// =============================================================================================
+// Loader: graph validation on the device (replaces the checks of ReadPtsNeighs,
+// nem_exe.c:1342-1478, and decides whether the reader lists equal the neighbour lists).
+// flags[0] |= 1 row_ptr not monotone, |= 2 neighbour out of range, |= 4 some edge i->j has no j->i;
+// flags[1] = max degree.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_graph_check(int n, int nnz, const int32_t *__restrict__ row_ptr,
+              const int32_t *__restrict__ col, int32_t *flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = row_ptr[i], hi = row_ptr[i + 1];
+    int bad = 0;
+    if (hi < lo || lo < 0 || hi > nnz) { atomicOr(&flags[0], 1); return; }
+    for (int e = lo; e < hi; e++) {
+        int j = col[e];
+        if (j < 0 || j >= n) { bad |= 2; continue; }
+        if (j == i) continue;
+        int jl = row_ptr[j], jh = row_ptr[j + 1];
+        if (jl < 0 || jh > nnz) continue;   // reported by row j itself
+        bool found = false;
+        for (int f = jl; f < jh && !found; f++) found = (col[f] == i);
+        if (!found) bad |= 4;
+    }
+    if (bad) atomicOr(&flags[0], bad);
+    atomicMax(&flags[1], hi - lo);
 }
 
 // =============================================================================================
@@ -1248,8 +1338,8 @@ extern "C" void nemk_pack_u8(nemk_stream s, const uint8_t *x, int n, int d, int 
 
 extern "C" void nemk_transpose_bits(nemk_stream s, const uint32_t *x, int n, int wpr, int d,
                                     int nwt, uint32_t *xt) {
-    if (n <= 0) return;
     cudaMemsetAsync(xt, 0, (size_t)d * nwt * sizeof(uint32_t), S(s));
+    if (n <= 0) return;
     dim3 grid(cdiv(n, 32), cdiv(wpr, 32));
     k_transpose_bits<<<grid, 1024, 0, S(s)>>>(x, n, wpr, d, nwt, xt);
     note_launch();
@@ -1430,44 +1520,77 @@ extern "C" void nemk_density_general(nemk_stream s, int k, const uint32_t *x, in
     note_launch();
 }
 
-extern "C" void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int n, const double *logpf,
-                                       const int32_t *row_ptr, const int32_t *col, const float *wgt,
-                                       double beta, const uint8_t *lab_in, uint8_t *lab_out,
-                                       int32_t *dirty, int32_t *wl, int32_t *wl_count,
-                                       const int32_t *rrow_ptr, const int32_t *rcol,
-                                       nemk_counters *cnt, const int32_t *skip) {
-    if (n <= 0) return;
-    DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<cdiv(n, 256), 256, 0, S(s)>>>(
-                      k, n, logpf, row_ptr, col, wgt, beta, lab_in, lab_out, dirty, wl, wl_count,
-                      rrow_ptr, rcol, cnt, skip)));
+extern "C" void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc,
+                                       const double *logpf, const int32_t *row_ptr,
+                                       const int32_t *col, const float *wgt, double beta,
+                                       const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
+                                       int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
+                                       const int32_t *rcol, nemk_counters *cnt, const int32_t *skip) {
+    if (n_loc <= 0) return;
+    DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<cdiv(n_loc, 256), 256, 0, S(s)>>>(
+                      k, row0, n_loc, logpf, row_ptr, col, wgt, beta, lab_in, lab_out, dirty, wl,
+                      wl_count, rrow_ptr, rcol, cnt, skip)));
     note_launch();
 }
 
-extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int n, const double *logpf,
+extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
                                       const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                       double beta, const uint8_t *lab_old, uint8_t *lab_cur,
-                                      int32_t *dirty, int32_t *wl_a, int32_t *wl_b,
-                                      int32_t *wl_counts, const int32_t *rrow_ptr,
-                                      const int32_t *rcol, nemk_counters *cnt, const int32_t *skip) {
-    if (n <= 0) return;
+                                      int32_t *dirty, int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt,
+                                      int round, const int32_t *rrow_ptr, const int32_t *rcol,
+                                      nemk_counters *cnt, const int32_t *skip) {
+    if (n_loc <= 0) return;
     DISPATCH_K(k, (k_sweep_ncem_fixup<KT><<<1, 1024, 0, S(s)>>>(
-                      k, n, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty, wl_a, wl_b,
-                      wl_counts, rrow_ptr, rcol, cnt, skip)));
+                      k, row0, row0 + n_loc, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
+                      wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip)));
     note_launch();
 }
 
-extern "C" void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, const double *logpf,
-                                            const int32_t *row_ptr, const int32_t *col,
-                                            const float *wgt, double beta, const uint8_t *lab_old,
-                                            uint8_t *lab_cur, int32_t *dirty, const int32_t *cur_list,
-                                            int32_t *next_list, const int32_t *cur_cnt,
-                                            int32_t *next_cnt, const int32_t *rrow_ptr,
-                                            const int32_t *rcol, nemk_counters *cnt,
-                                            const int32_t *skip) {
+extern "C" void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc,
+                                            const double *logpf, const int32_t *row_ptr,
+                                            const int32_t *col, const float *wgt, double beta,
+                                            const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty,
+                                            int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt, int round,
+                                            const int32_t *rrow_ptr, const int32_t *rcol,
+                                            nemk_counters *cnt, const int32_t *skip) {
+    if (n_loc <= 0) return;
     int grid = num_sms() * 2;
     DISPATCH_K(k, (k_sweep_ncem_fixup_round<KT><<<grid, 256, 0, S(s)>>>(
-                      k, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty, cur_list, next_list,
-                      cur_cnt, next_cnt, rrow_ptr, rcol, cnt, skip)));
+                      k, row0, row0 + n_loc, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
+                      wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip)));
+    note_launch();
+}
+
+extern "C" void nemk_mark_remote(nemk_stream s, int n_glob, int row0, int n_loc,
+                                 const uint8_t *lab_cur, uint8_t *lab_seen, int32_t *dirty,
+                                 int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
+                                 const int32_t *rcol, int32_t *pending) {
+    if (n_glob <= 0) return;
+    int grid = cdiv(n_glob, 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    k_mark_remote<<<grid, 256, 0, S(s)>>>(n_glob, row0, row0 + n_loc, lab_cur, lab_seen, dirty, wl,
+                                          wl_count, rrow_ptr, rcol, pending);
+    note_launch();
+}
+
+extern "C" void nemk_sum_ranks_i32(nemk_stream s, int world, size_t count, const int32_t *stage,
+                                   int32_t *out) {
+    if (!count) return;
+    k_sum_ranks_i32<<<cdiv((long long)count, 256), 256, 0, S(s)>>>(world, count, stage, out);
+    note_launch();
+}
+extern "C" void nemk_sum_ranks_f64(nemk_stream s, int world, size_t count, const double *stage,
+                                   double *out) {
+    if (!count) return;
+    k_sum_ranks_f64<<<cdiv((long long)count, 256), 256, 0, S(s)>>>(world, count, stage, out);
+    note_launch();
+}
+
+extern "C" void nemk_graph_check(nemk_stream s, int n, int nnz, const int32_t *row_ptr,
+                                 const int32_t *col, int32_t *flags2) {
+    cudaMemsetAsync(flags2, 0, 2 * sizeof(int32_t), S(s));
+    if (n <= 0) return;
+    k_graph_check<<<cdiv(n, 256), 256, 0, S(s)>>>(n, nnz, row_ptr, col, flags2);
     note_launch();
 }
 
@@ -1484,13 +1607,13 @@ extern "C" void nemk_sweep_ncem_level(nemk_stream s, int k, const double *logpf,
     note_launch();
 }
 
-extern "C" void nemk_sweep_nem_jacobi(nemk_stream s, int k, int n, const double *logpf,
+extern "C" void nemk_sweep_nem_jacobi(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
                                       const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                       double beta, const float *t_in, float *t_out,
                                       nemk_counters *cnt, const int32_t *skip) {
-    if (n <= 0) return;
-    DISPATCH_K(k, (k_sweep_nem_jacobi<KT><<<cdiv(n, 256), 256, 0, S(s)>>>(
-                      k, n, logpf, row_ptr, col, wgt, beta, t_in, t_out, cnt, skip)));
+    if (n_loc <= 0) return;
+    DISPATCH_K(k, (k_sweep_nem_jacobi<KT><<<cdiv(n_loc, 256), 256, 0, S(s)>>>(
+                      k, row0, n_loc, logpf, row_ptr, col, wgt, beta, t_in, t_out, cnt, skip)));
     note_launch();
 }
 
@@ -1568,17 +1691,20 @@ extern "C" void nemk_mstep_finalize(nemk_stream s, int k, int n, int d, int prop
     note_launch();
 }
 
-extern "C" void nemk_criteria(nemk_stream s, int k, int n, const double *logpf,
-                              const int32_t *row_ptr, const int32_t *col, const float *wgt,
-                              double beta, const uint8_t *lab, const float *t, double *partials,
-                              int nblocks_cap, double *crit6) {
-    int nb = cdiv(n, 256);
-    if (nb > nblocks_cap) nb = nblocks_cap;
-    if (nb < 1) nb = 1;
-    DISPATCH_K(k, (k_criteria_partial<KT><<<nb, 256, 0, S(s)>>>(k, n, logpf, row_ptr, col, wgt, beta,
-                                                               lab, t, partials)));
+extern "C" int nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+                                     const int32_t *row_ptr, const int32_t *col, const float *wgt,
+                                     double beta, const uint8_t *lab, const float *t,
+                                     double *partials, int nblocks) {
+    // always exactly `nblocks` partial rows (idle blocks write zeros) so that the ranks of a
+    // sharded fit can gather equal-sized buffers
+    DISPATCH_K(k, (k_criteria_partial<KT><<<nblocks, 256, 0, S(s)>>>(k, row0, n_loc, logpf, row_ptr,
+                                                                    col, wgt, beta, lab, t, partials)));
     note_launch();
-    k_criteria_final<<<1, 256, 0, S(s)>>>(nb, partials, beta, crit6);
+    return nblocks;
+}
+extern "C" void nemk_criteria_final(nemk_stream s, int nblocks_total, const double *partials,
+                                    double beta, double *crit6) {
+    k_criteria_final<<<1, 256, 0, S(s)>>>(nblocks_total, partials, beta, crit6);
     note_launch();
 }
 
