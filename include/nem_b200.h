@@ -103,6 +103,12 @@ typedef struct {
     int32_t n_density, n_sweep, n_mstep, n_criteria;      /* launches behind those sums */
     int32_t best_start;   /* nemb_fit_random: 1-based index of the retained start, else 0 */
     int32_t n_success;    /* nemb_fit_random: starts that ended without an empty class */
+    /* profile=1: ms_density/n_density count only the passes that READ X; the iterations whose
+     * class centres did not move rebuild logpf from the cached Hamming counts (ms_density_cached).
+     * ms_mstep/n_mstep count the full X^T recounts; ms_mstep_delta the incremental updates. */
+    float   ms_density_cached, ms_mstep_delta;
+    int32_t n_density_cached, n_mstep_delta;
+    int64_t exchanges;    /* row shards: all-gathers this fit issued */
 } nemb_result;
 
 /* Per-iteration trace for the .log writer (nem_alg.c:1995-2052, 2620-2646). */

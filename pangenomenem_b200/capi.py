@@ -45,7 +45,10 @@ class Result(C.Structure):
                 ("ms_density", C.c_float), ("ms_sweep", C.c_float), ("ms_mstep", C.c_float),
                 ("ms_criteria", C.c_float),
                 ("n_density", C.c_int32), ("n_sweep", C.c_int32), ("n_mstep", C.c_int32),
-                ("n_criteria", C.c_int32), ("best_start", C.c_int32), ("n_success", C.c_int32)]
+                ("n_criteria", C.c_int32), ("best_start", C.c_int32), ("n_success", C.c_int32),
+                ("ms_density_cached", C.c_float), ("ms_mstep_delta", C.c_float),
+                ("n_density_cached", C.c_int32), ("n_mstep_delta", C.c_int32),
+                ("exchanges", C.c_int64)]
 
 
 class Extra(C.Structure):
@@ -133,6 +136,7 @@ class Fit:
     stage_ms: dict = field(default_factory=dict)
     stage_launches: dict = field(default_factory=dict)
     empty_class: int = 0
+    exchanges: int = 0
 
 
 class Engine:
@@ -251,9 +255,11 @@ class Engine:
                    disp.reshape(o.k, self.d), dict(U=r.U, D=r.D, L=r.L, M=r.M, Z=r.Z, G=r.G),
                    r.n_allnul, r.n_ties, r.fixup_rounds, r.kernel_launches, r.fit_ms,
                    dict(density=r.ms_density, sweep=r.ms_sweep, mstep=r.ms_mstep,
-                        criteria=r.ms_criteria),
+                        criteria=r.ms_criteria, density_cached=r.ms_density_cached,
+                        mstep_delta=r.ms_mstep_delta),
                    dict(density=r.n_density, sweep=r.n_sweep, mstep=r.n_mstep,
-                        criteria=r.n_criteria), r.empty_class)
+                        criteria=r.n_criteria, density_cached=r.n_density_cached,
+                        mstep_delta=r.n_mstep_delta), r.empty_class, r.exchanges)
 
     def posteriors(self, k=None):
         k = k or self.k

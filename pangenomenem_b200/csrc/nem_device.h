@@ -24,7 +24,9 @@ typedef struct {
     int32_t forb[NEMB_MAX_K];   /* eps_k <= EPSILON: any mismatch => zero density */
     int32_t uniform_ok;         /* 1 when every class is popcount-eligible */
     int32_t empty_class;        /* 1-based index of an empty class (M-step) or 0 */
-    int32_t pad[2];
+    int32_t mu_changed;         /* the class bit masks differ from the previous tables (or forced):
+                                   the cached Hamming counts are stale, the density pass must run */
+    int32_t pad[1];
 } nemk_coef;
 
 /* Device scalars of one sweep / one iteration (host reads them back in one copy). */
@@ -49,12 +51,14 @@ void nemk_transpose_bits(nemk_stream s, const uint32_t *x, int n, int wpr, int d
 void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const float *prop,
                        const float *center, const float *disp, nemk_coef *coef,
                        uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
-                       uint32_t *mask_f1, double *delta);
+                       uint32_t *mask_f1, double *delta, int force_mu_changed);
 
 /* ---- E-step density */
+/* cached != 0: `hamming` is the engine's persistent H cache; the X pass only runs when
+ * coef->mu_changed, otherwise logpf is rebuilt from the cached counts (same formula, same bits) */
 void nemk_density_uniform(nemk_stream s, int k, const uint32_t *x, int n, int wpr,
                           const nemk_coef *coef, const uint32_t *mask_xor,
-                          const uint32_t *mask_valid, double *logpf, int32_t *hamming);
+                          const uint32_t *mask_valid, double *logpf, int32_t *hamming, int cached);
 void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d, int wpr,
                           const nemk_coef *coef, const uint32_t *mask_f0, const uint32_t *mask_f1,
                           const double *delta, double *logpf);
@@ -63,6 +67,11 @@ void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d,
  * bit2 some edge i->j has no j->i (reader lists differ from neighbour lists); flags2[1] = max degree */
 void nemk_graph_check(nemk_stream s, int n, int nnz, const int32_t *row_ptr, const int32_t *col,
                       int32_t *flags2);
+
+/* index-sorted list of this rank's hubs (degree > 16), evaluated one warp per site by the sweeps
+ * and the criteria; block_counts needs ceil(n_loc/1024) ints, list up to n_loc ints */
+void nemk_heavy_list(nemk_stream s, int row0, int n_loc, const int32_t *row_ptr,
+                     int32_t *block_counts, int32_t *list, int32_t *total);
 
 /* ---- E-step sweeps.  label 255 = unlabelled (the reference's calloc'd ClassifM row).
  * `skip` (nullable) points at a device flag; non-zero => the kernel returns at once (an empty
@@ -74,7 +83,8 @@ void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc, const dou
                             const int32_t *row_ptr, const int32_t *col, const float *wgt,
                             double beta, const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
                             int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
-                            const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
+                            const int32_t *rcol, const int32_t *heavy, int n_heavy,
+                            nemk_counters *cnt, const int32_t *skip);
 void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
                            const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
                            const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a,
@@ -102,23 +112,34 @@ void nemk_sweep_nem_level(nemk_stream s, int k, const double *logpf, const int32
                           int grid_ctas, nemk_counters *cnt, const int32_t *skip);
 
 /* ---- M-step */
+/* lab_m (nullable): receives a copy of the labels = the state the statistics now describe */
 void nemk_label_masks(nemk_stream s, int k, int n, int nwt, const uint8_t *lab, uint32_t *cm,
-                      int32_t *nk_int);
+                      int32_t *nk_int, uint8_t *lab_m);
+/* incremental ncem statistics: rows whose label differs from lab_m move their bits from
+ * S[old] to S[new] (exact integer updates), then lab_m = lab.  list needs n ints + 1 counter */
+void nemk_mstep_delta(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x,
+                      const uint8_t *lab, uint8_t *lab_m, int32_t *list, int32_t *count,
+                      int32_t *s_int, int32_t *nk_int);
 void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint32_t *xt, const uint32_t *cm,
                      int32_t *s_int);
 void nemk_mstep_nem(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x, const float *t,
                     int rows_per_chunk, double *partial_s, double *partial_n, double *s_dbl,
                     double *nk_dbl);
-void nemk_mstep_finalize(nemk_stream s, int k, int n, int d, int prop_model, int disp_model,
-                         const int32_t *s_int, const int32_t *nk_int, const double *s_dbl,
-                         const double *nk_dbl, float *prop, float *center, float *disp,
-                         float *iner_scratch, nemk_coef *coef);
+/* M-step closed forms (mu, eps, p from S and n) + the density tables of the new theta, one CTA
+ * per class */
+void nemk_mstep_finalize_tables(nemk_stream s, int k, int n, int d, int wpr, int prop_model,
+                                int disp_model, const int32_t *s_int, const int32_t *nk_int,
+                                const double *s_dbl, const double *nk_dbl, float *prop,
+                                float *center, float *disp, nemk_coef *coef, uint32_t *mask_xor,
+                                uint32_t *mask_valid, uint32_t *mask_f0, uint32_t *mask_f1,
+                                double *delta, int force_mu_changed);
 
 /* ---- criteria: per-rank partial sums (exactly nblocks rows of 4 doubles: D G L Z), then the
  * final fixed-order sum over the partial rows of every rank -> U D L M Z G */
 int  nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
                            const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
-                           const uint8_t *lab, const float *t, double *partials, int nblocks);
+                           const uint8_t *lab, const float *t, const int32_t *heavy, int n_heavy,
+                           double *partials, int nblocks);
 void nemk_criteria_final(nemk_stream s, int nblocks_total, const double *partials, double beta,
                          double *crit6);
 

@@ -38,7 +38,7 @@ typedef struct {
     double crit_after[6];
 } iter_status;
 
-enum { ST_DENSITY = 0, ST_SWEEP = 1, ST_MSTEP = 2, ST_CRIT = 3, ST_NB = 4 };
+enum { ST_DENSITY = 0, ST_SWEEP = 1, ST_MSTEP = 2, ST_CRIT = 3, ST_DENSITY_CACHED = 4, ST_MSTEP_DELTA = 5, ST_NB = 6 };
 
 typedef struct { void *p; size_t cap; } dbuf;   /* grow-only device buffer */
 
@@ -55,7 +55,9 @@ struct nemb_handle {
     int d, wpr, nwt, nnz, spatial, symmetric, max_neigh, loaded;
     uint32_t *d_x, *d_xt;
     int x_owned, have_xt;
-    dbuf b_x, b_xt, b_row_ptr, b_col, b_wgt, b_rrow_ptr, b_rcol, b_sites, b_level_ptr, b_flags;
+    dbuf b_x, b_xt, b_row_ptr, b_col, b_wgt, b_rrow_ptr, b_rcol, b_sites, b_level_ptr, b_flags, b_heavy;
+    int32_t *d_heavy;      /* index-sorted hubs among this rank's rows */
+    int n_heavy;
     int32_t *d_row_ptr, *d_col, *d_rrow_ptr, *d_rcol, *d_sites, *d_level_ptr;
     float *d_wgt;
     int have_levels, depth;
@@ -70,12 +72,17 @@ struct nemb_handle {
     uint32_t *d_mxor, *d_mval, *d_f0, *d_f1;
     double *d_delta;
     double *d_logpf;
-    uint8_t *d_lab[3];     /* two sweep buffers + the labels last seen from remote ranks */
+    uint8_t *d_lab[4];     /* two sweep buffers, the labels last seen from remote ranks, and the
+                              labels the M-step statistics currently describe (local rows) */
+    int32_t *d_ham;        /* cached Hamming counts H[n][K] of the popcount density path */
+    int ham_valid, stats_valid;
+    int64_t last_changed;  /* labels moved by the last sweep (all ranks), -1 = unknown */
     float *d_t[2];
     int cur, state_labels;
     int32_t *d_dirty, *d_wl[2], *d_wl_counts;
     uint32_t *d_cm;
-    int32_t *d_stat_int, *d_stat_int_stage;   /* S[K*D] then n[K]; stage = [world][K*D+K] */
+    int32_t *d_stat_loc;                      /* this rank's S[K*D] then n[K] (kept incrementally) */
+    int32_t *d_stat_int, *d_stat_int_stage;   /* all ranks' sum; stage = [world][K*D+K] */
     double *d_stat_dbl, *d_stat_dbl_stage;
     double *d_partial_s, *d_partial_n;
     int rows_per_chunk, nchunks;
@@ -89,7 +96,7 @@ struct nemb_handle {
     int profile;
     cudaEvent_t *ev;
     int *ev_kind;
-    int ev_cap, ev_n;
+    int ev_cap, ev_n, ev_last_density;
 };
 
 /* ------------------------------------------------------------------ errors */
@@ -221,7 +228,7 @@ void nemb_destroy(nemb_handle *h)
     cudaStreamSynchronize(h->stream);
     reset_problem(h);
     dbuf *all[] = {&h->b_x, &h->b_xt, &h->b_row_ptr, &h->b_col, &h->b_wgt, &h->b_rrow_ptr,
-                   &h->b_rcol, &h->b_sites, &h->b_level_ptr, &h->b_flags, &h->b_slab, &h->b_t[0],
+                   &h->b_rcol, &h->b_sites, &h->b_level_ptr, &h->b_flags, &h->b_heavy, &h->b_slab, &h->b_t[0],
                    &h->b_t[1], &h->b_nem};
     for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) release(all[i]);
     if (h->h_status) cudaFreeHost(h->h_status);
@@ -251,7 +258,7 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
 {
     int rc;
     h->spatial = row_ptr != NULL;
-    h->nnz = 0; h->symmetric = 1; h->max_neigh = 0;
+    h->nnz = 0; h->symmetric = 1; h->max_neigh = 0; h->n_heavy = 0; h->d_heavy = NULL;
     h->d_row_ptr = h->d_col = h->d_rrow_ptr = h->d_rcol = NULL; h->d_wgt = NULL;
     if (!h->spatial) return NEMB_OK;
     if (row_ptr[0] != 0) return fail(h, NEMB_E_ARG, "row_ptr[0] must be 0");
@@ -266,12 +273,20 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
     h->d_row_ptr = h->b_row_ptr.p; h->d_col = h->b_col.p; h->d_wgt = h->b_wgt.p;
     nemk_graph_check(h->stream, n, nnz, h->d_row_ptr, h->d_col, (int32_t *)h->b_flags.p);
     CKK();
-    int32_t flags[2] = {0, 0};
+    /* hubs of this rank's rows (only meaningful if row_ptr is sane; re-checked below) */
+    size_t hl_blocks = ((size_t)h->n + 1023) / 1024 + 1;
+    if ((rc = reserve(h, &h->b_heavy, sizeof(int32_t) * (hl_blocks + (size_t)h->n + 1))) != NEMB_OK) return rc;
+    h->d_heavy = (int32_t *)h->b_heavy.p + hl_blocks;
+    nemk_heavy_list(h->stream, h->row0, h->n, h->d_row_ptr, h->b_heavy.p, h->d_heavy,
+                    (int32_t *)h->b_flags.p + 2);
+    CKK();
+    int32_t flags[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(flags, h->b_flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (flags[0] & 1) return fail(h, NEMB_E_ARG, "row_ptr is not monotone");
     if (flags[0] & 2) return fail(h, NEMB_E_ARG, "neighbour index out of range");
     h->max_neigh = flags[1];
+    h->n_heavy = flags[2];
     h->symmetric = !(flags[0] & 4);
     if (h->symmetric) { h->d_rrow_ptr = h->d_row_ptr; h->d_rcol = h->d_col; return NEMB_OK; }
 
@@ -511,6 +526,7 @@ static int ensure_k(nemb_handle *h, int k)
     size_t o_delta = carve(&off, sizeof(double) * (kd + k));
     size_t o_logpf = carve(&off, sizeof(double) * n * k);
     size_t o_lab0 = carve(&off, L), o_lab1 = carve(&off, L), o_lab2 = carve(&off, L);
+    size_t o_lab3 = carve(&off, n + 1), o_ham = carve(&off, 4 * n * k + 4), o_sl = carve(&off, 4 * (kd + k));
     size_t o_dirty = carve(&off, 4 * L);
     size_t o_wl0 = carve(&off, 4 * (n + 1)), o_wl1 = carve(&off, 4 * (n + 1));
     size_t o_wlc = carve(&off, 4 * 8);
@@ -530,7 +546,9 @@ static int ensure_k(nemb_handle *h, int k)
     h->d_f0 = (uint32_t *)(base + o_f0); h->d_f1 = (uint32_t *)(base + o_f1);
     h->d_delta = (double *)(base + o_delta); h->d_logpf = (double *)(base + o_logpf);
     h->d_lab[0] = (uint8_t *)(base + o_lab0); h->d_lab[1] = (uint8_t *)(base + o_lab1);
-    h->d_lab[2] = (uint8_t *)(base + o_lab2);
+    h->d_lab[2] = (uint8_t *)(base + o_lab2); h->d_lab[3] = (uint8_t *)(base + o_lab3);
+    h->d_ham = (int32_t *)(base + o_ham); h->d_stat_loc = (int32_t *)(base + o_sl);
+    h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1;
     h->d_dirty = (int32_t *)(base + o_dirty);
     h->d_wl[0] = (int32_t *)(base + o_wl0); h->d_wl[1] = (int32_t *)(base + o_wl1);
     h->d_wl_counts = (int32_t *)(base + o_wlc);
@@ -548,7 +566,7 @@ static int ensure_k(nemb_handle *h, int k)
     h->d_partial_s = h->d_partial_n = NULL;
     if (!h->h_status) CK(cudaMallocHost((void **)&h->h_status, sizeof(iter_status)));
     if (!h->h_cnt_all) CK(cudaMallocHost((void **)&h->h_cnt_all, sizeof(nemk_counters) * MAX_WORLD));
-    if (!h->h_empty) CK(cudaMallocHost((void **)&h->h_empty, sizeof(int32_t)));
+    if (!h->h_empty) CK(cudaMallocHost((void **)&h->h_empty, 2 * sizeof(int32_t)));
     h->k_alloc = k;
     return NEMB_OK;
 }
@@ -619,6 +637,7 @@ static void stage_mark(nemb_handle *h, int kind_or_end)
         h->ev_cap = nc;
     }
     h->ev_kind[h->ev_n] = kind_or_end;
+    if (kind_or_end == ST_DENSITY) h->ev_last_density = h->ev_n;
     cudaEventRecord(h->ev[h->ev_n++], h->stream);
 }
 #define STAGE_BEGIN(kind) stage_mark(h, (kind))
@@ -639,10 +658,13 @@ static int theta_uniform(int k, int d, const float *center, const float *disp)
 }
 
 /* ------------------------------------------------------------------ steps of one fit */
-static int run_tables(nemb_handle *h, int k)
+/* next_uniform: the density pass that follows takes the popcount path; its cached Hamming
+ * counts stay valid while the class bit masks do not move (k_theta_tables detects that) */
+static int run_tables(nemb_handle *h, int k, int next_uniform)
 {
+    int force = !(h->ham_valid && next_uniform);
     nemk_theta_tables(h->stream, k, h->d, h->wpr, h->d_prop, h->d_center, h->d_disp, h->d_coef,
-                      h->d_mxor, h->d_mval, h->d_f0, h->d_f1, h->d_delta);
+                      h->d_mxor, h->d_mval, h->d_f0, h->d_f1, h->d_delta, force);
     h->launches++;
     CKK();
     return NEMB_OK;
@@ -651,12 +673,17 @@ static int run_tables(nemb_handle *h, int k)
 static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming)
 {
     STAGE_BEGIN(ST_DENSITY);
-    if (uniform)
+    if (uniform) {
+        /* d_hamming == NULL: the fit's own pass, through the persistent H cache */
         nemk_density_uniform(h->stream, k, h->d_x, h->n, h->wpr, h->d_coef, h->d_mxor, h->d_mval,
-                             h->d_logpf, d_hamming);
-    else
+                             h->d_logpf, d_hamming ? d_hamming : h->d_ham, d_hamming == NULL);
+        h->ham_valid = d_hamming == NULL;
+        h->launches += h->ham_valid;
+    } else {
         nemk_density_general(h->stream, k, h->d_x, h->n, h->d, h->wpr, h->d_coef, h->d_f0, h->d_f1,
                              h->d_delta, h->d_logpf);
+        h->ham_valid = 0;
+    }
     STAGE_END();
     h->launches++;
     CKK();
@@ -670,8 +697,14 @@ static int read_status(nemb_handle *h)
     if (rc != NEMB_OK) return rc;
     CK(cudaMemcpyAsync(h->h_cnt_all, h->d_cnt_all, sizeof(nemk_counters) * h->world, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    /* h_empty[1] = coef->mu_changed of the last tables: 0 => the last popcount density pass did
+     * not read X (cached Hamming counts) */
+    if (h->profile && h->ev_last_density >= 0 && h->ham_valid && !h->h_empty[1]) {
+        h->ev_kind[h->ev_last_density] = ST_DENSITY_CACHED;
+        h->ev_last_density = -1;
+    }
     nemk_counters tot;
     memset(&tot, 0, sizeof tot);
     for (int r = 0; r < h->world; r++) {
@@ -718,7 +751,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
         int impl = o->sweep_impl == NEMB_SWEEP_AUTO ? NEMB_SWEEP_SPEC : o->sweep_impl;
         if (!seq) {
             nemk_sweep_ncem_jacobi(h->stream, k, row0, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
-                                   out, NULL, NULL, NULL, NULL, NULL, &h->d_status->cnt, skip);
+                                   out, NULL, NULL, NULL, NULL, NULL, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip);
             h->launches++;
             /* halo exchange of the hard labels: every rank's slice, 1 byte per family */
             if (h->world > 1 && (rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
@@ -730,7 +763,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
             }
             nemk_sweep_ncem_jacobi(h->stream, k, row0, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
                                    out, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
-                                   h->d_rcol, &h->d_status->cnt, skip);
+                                   h->d_rcol, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip);
             h->launches++;
             local_fixups(h, k, beta, in, out, rp, skip);
             if (h->world > 1) {
@@ -790,26 +823,39 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
     return NEMB_OK;
 }
 
-static int run_mstep(nemb_handle *h, const nemb_options *o)
+static int run_mstep(nemb_handle *h, const nemb_options *o, int next_uniform)
 {
     int k = o->k, rc;
     size_t kd = (size_t)k * h->d, stat = kd + k;
-    STAGE_BEGIN(ST_MSTEP);
+    int incremental = o->algo == NEMB_ALGO_NCEM && h->stats_valid && h->last_changed >= 0 &&
+                      h->last_changed <= h->n / 8 && !getenv("NEM_B200_FULL_MSTEP");
+    STAGE_BEGIN(incremental ? ST_MSTEP_DELTA : ST_MSTEP);
     if (o->algo == NEMB_ALGO_NCEM) {
-        /* exact integer counts: S_kd and n_k of this rank's rows, summed over the ranks */
-        if ((rc = ensure_xt(h)) != NEMB_OK) return rc;
-        nemk_label_masks(h->stream, k, h->n, h->nwt, h->d_lab[h->cur] + h->row0, h->d_cm,
-                         h->d_stat_int + kd);
-        nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_stat_int);
+        /* exact integer counts S_kd, n_k of this rank's rows: a full recount through X^T, or --
+         * when the last sweep moved few labels -- an update from the rows that changed class */
+        const uint8_t *lab_loc = h->d_lab[h->cur] + h->row0;
+        if (incremental) {
+            nemk_mstep_delta(h->stream, k, h->n, h->d, h->wpr, h->d_x, lab_loc, h->d_lab[3],
+                             h->d_wl[1], &h->d_wl_counts[4], h->d_stat_loc, h->d_stat_loc + kd);
+        } else {
+            if ((rc = ensure_xt(h)) != NEMB_OK) return rc;
+            nemk_label_masks(h->stream, k, h->n, h->nwt, lab_loc, h->d_cm, h->d_stat_loc + kd,
+                             h->d_lab[3]);
+            nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_stat_loc);
+            h->stats_valid = 1;
+        }
         h->launches += 2;
+        const int32_t *stat_glob = h->d_stat_loc;
         if (h->world > 1) {
-            if ((rc = gather(h, h->d_stat_int, h->d_stat_int_stage, sizeof(int32_t) * stat)) != NEMB_OK) return rc;
+            if ((rc = gather(h, h->d_stat_loc, h->d_stat_int_stage, sizeof(int32_t) * stat)) != NEMB_OK) return rc;
             nemk_sum_ranks_i32(h->stream, h->world, stat, h->d_stat_int_stage, h->d_stat_int);
             h->launches++;
+            stat_glob = h->d_stat_int;
         }
-        nemk_mstep_finalize(h->stream, k, h->n_glob, h->d, o->prop, o->disp, h->d_stat_int,
-                            h->d_stat_int + kd, NULL, NULL, h->d_prop, h->d_center, h->d_disp,
-                            h->d_iner, h->d_coef);
+        nemk_mstep_finalize_tables(h->stream, k, h->n_glob, h->d, h->wpr, o->prop, o->disp, stat_glob,
+                                   stat_glob + kd, NULL, NULL, h->d_prop, h->d_center, h->d_disp,
+                                   h->d_coef, h->d_mxor, h->d_mval, h->d_f0, h->d_f1, h->d_delta,
+                                   !(h->ham_valid && next_uniform));
         h->launches++;
     } else {
         if ((rc = ensure_nem_scratch(h, k)) != NEMB_OK) return rc;
@@ -822,13 +868,15 @@ static int run_mstep(nemb_handle *h, const nemb_options *o)
             nemk_sum_ranks_f64(h->stream, h->world, stat, h->d_stat_dbl_stage, h->d_stat_dbl);
             h->launches++;
         }
-        nemk_mstep_finalize(h->stream, k, h->n_glob, h->d, o->prop, o->disp, NULL, NULL, h->d_stat_dbl,
-                            h->d_stat_dbl + kd, h->d_prop, h->d_center, h->d_disp, h->d_iner, h->d_coef);
+        nemk_mstep_finalize_tables(h->stream, k, h->n_glob, h->d, h->wpr, o->prop, o->disp, NULL, NULL,
+                                   h->d_stat_dbl, h->d_stat_dbl + kd, h->d_prop, h->d_center,
+                                   h->d_disp, h->d_coef, h->d_mxor, h->d_mval, h->d_f0, h->d_f1,
+                                   h->d_delta, !(h->ham_valid && next_uniform));
         h->launches++;
     }
     STAGE_END();
     CKK();
-    return run_tables(h, k);
+    return NEMB_OK;
 }
 
 static int run_criteria(nemb_handle *h, const nemb_options *o, double beta, double *d_out)
@@ -838,8 +886,8 @@ static int run_criteria(nemb_handle *h, const nemb_options *o, double beta, doub
     size_t mine = (size_t)h->rank * h->crit_blocks * 4;
     nemk_criteria_partial(h->stream, o->k, h->row0, h->n, h->d_logpf, h->spatial ? h->d_row_ptr : NULL,
                           h->d_col, h->d_wgt, beta, o->algo == NEMB_ALGO_NCEM ? h->d_lab[h->cur] : NULL,
-                          o->algo == NEMB_ALGO_NCEM ? NULL : h->d_t[h->cur], h->d_crit_partials + mine,
-                          h->crit_blocks);
+                          o->algo == NEMB_ALGO_NCEM ? NULL : h->d_t[h->cur], h->d_heavy, h->n_heavy,
+                          h->d_crit_partials + mine, h->crit_blocks);
     if (h->world > 1 && (rc = gather(h, h->d_crit_partials + mine, h->d_crit_partials,
                                      sizeof(double) * 4 * h->crit_blocks)) != NEMB_OK) return rc;
     nemk_criteria_final(h->stream, h->crit_blocks * h->world, h->d_crit_partials, beta, d_out);
@@ -873,6 +921,7 @@ static int init_state(nemb_handle *h, const nemb_options *o)
     int rc;
     h->cur = 0;
     h->state_labels = o->algo == NEMB_ALGO_NCEM;
+    h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1;
     if (h->state_labels) CK(cudaMemsetAsync(h->d_lab[0], 255, h->lab_len, h->stream));
     else {
         if ((rc = ensure_t(h, o->k, 1)) != NEMB_OK) return rc;
@@ -895,7 +944,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     float *nk_host = cb ? malloc(sizeof(float) * k) : NULL;
 
     if ((rc = init_state(h, o)) != NEMB_OK) return rc;
-    if ((rc = run_tables(h, k)) != NEMB_OK) return rc;
+    if ((rc = run_tables(h, k, 0)) != NEMB_OK) return rc;
     if ((rc = run_density(h, k, uniform0, NULL)) != NEMB_OK) return rc;
     /* ComputePartitionFromPara(Needinit=1): blind sweep then beta sweep (nem_alg.c:1970-1981) */
     if ((rc = run_sweep(h, o, 0.0, &flipped)) != NEMB_OK) return rc;
@@ -917,7 +966,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
 
     int iter, converged = 0, status = NEMB_OK, empty = 0;
     for (iter = 1; iter <= o->it_max && !converged && status == NEMB_OK; iter++) {
-        if (!o->param_fixed && (rc = run_mstep(h, o)) != NEMB_OK) return rc;
+        if (!o->param_fixed && (rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
         if ((rc = run_density(h, k, uniform_m, NULL)) != NEMB_OK) return rc;
         if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
         if ((rc = run_sweep(h, o, beta, &flipped)) != NEMB_OK) return rc;
@@ -928,6 +977,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
             CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
         }
         if ((rc = read_status(h)) != NEMB_OK) return rc;
+        h->last_changed = o->algo == NEMB_ALGO_NCEM ? h->h_status->cnt.changed : -1;
         empty = *h->h_empty;
         if (empty) {              /* nem_alg.c:1831-1838: E-step not run, loop ends */
             status = NEMB_W_EMPTYCLASS;
@@ -952,7 +1002,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
                 for (int c = 0; c < k; c++) nk_host[c] = NAN;
             } else if (o->algo == NEMB_ALGO_NCEM) {
                 int32_t ni[NEMB_MAX_K];
-                CK(cudaMemcpy(ni, h->d_stat_int + kd, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ni, (h->world > 1 ? h->d_stat_int : h->d_stat_loc) + kd, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
                 for (int c = 0; c < k; c++) nk_host[c] = (float)ni[c];
             } else {
                 double nd[NEMB_MAX_K];
@@ -964,7 +1014,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     }
     iter -= 1;
     if (iter == 0) { /* nem_alg.c:1845-1851 */
-        if ((rc = run_mstep(h, o)) != NEMB_OK) return rc;
+        if ((rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
         if ((rc = run_density(h, k, uniform_m, NULL)) != NEMB_OK) return rc;
     }
     if ((rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
@@ -987,9 +1037,12 @@ static void collect_profile(nemb_handle *h, nemb_result *res, cudaEvent_t e0, cu
     cudaEventElapsedTime(&res->fit_ms, e0, e1);
     res->kernel_launches = h->launches;
     res->fixup_rounds = h->fixup_rounds;
+    res->exchanges = h->exchanges;
     if (!h->profile) return;
-    float *ms[ST_NB] = {&res->ms_density, &res->ms_sweep, &res->ms_mstep, &res->ms_criteria};
-    int32_t *cn[ST_NB] = {&res->n_density, &res->n_sweep, &res->n_mstep, &res->n_criteria};
+    float *ms[ST_NB] = {&res->ms_density, &res->ms_sweep, &res->ms_mstep, &res->ms_criteria,
+                        &res->ms_density_cached, &res->ms_mstep_delta};
+    int32_t *cn[ST_NB] = {&res->n_density, &res->n_sweep, &res->n_mstep, &res->n_criteria,
+                          &res->n_density_cached, &res->n_mstep_delta};
     for (int i = 0; i + 1 < h->ev_n; i++) {
         int kind = h->ev_kind[i];
         if (kind < 0 || h->ev_kind[i + 1] != -1) continue;
@@ -1010,6 +1063,7 @@ int nemb_fit_logged(nemb_handle *h, const nemb_options *o, float *prop, float *c
     if ((rc = ensure_k(h, o->k)) != NEMB_OK) return rc;
     memset(res, 0, sizeof *res);
     h->launches = 0; h->fixup_rounds = 0; h->exchanges = 0; h->profile = o->profile; h->ev_n = 0;
+    h->ev_last_density = -1;
     size_t kd = (size_t)o->k * h->d;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -1150,7 +1204,8 @@ int nemb_stage_density(nemb_handle *h, int k, const float *prop, const float *ce
     int32_t *d_ham = NULL;
     size_t nk = (size_t)h->n * k;
     if (hamming_out && uniform) CK(cudaMalloc((void **)&d_ham, sizeof(int32_t) * nk));
-    if ((rc = run_tables(h, k)) != NEMB_OK) return rc;
+    h->ham_valid = 0;
+    if ((rc = run_tables(h, k, 0)) != NEMB_OK) return rc;
     if ((rc = run_density(h, k, uniform, d_ham)) != NEMB_OK) return rc;
     CK(cudaMemcpyAsync(logpf_out, h->d_logpf, sizeof(double) * nk, cudaMemcpyDeviceToHost, h->stream));
     if (d_ham) CK(cudaMemcpyAsync(hamming_out, d_ham, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, h->stream));
@@ -1168,6 +1223,7 @@ static int upload_state(nemb_handle *h, const nemb_options *o, const float *t)
     if ((rc = ensure_t(h, o->k, 1)) != NEMB_OK) return rc;
     h->cur = 0;
     h->state_labels = o->algo == NEMB_ALGO_NCEM;
+    h->stats_valid = 0; h->ham_valid = 0; h->last_changed = -1;
     CK(cudaMemcpyAsync(h->d_t[h->state_labels ? 1 : 0], t, sizeof(float) * nk, cudaMemcpyHostToDevice, h->stream));
     if (h->state_labels) {
         nemk_t_to_labels(h->stream, o->k, h->n, h->d_t[1], h->d_lab[0]);
@@ -1209,7 +1265,7 @@ int nemb_stage_mstep(nemb_handle *h, const nemb_options *o, const float *t, floa
     size_t kd = (size_t)k * h->d;
     if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
     if ((rc = upload_state(h, o, t)) != NEMB_OK) return rc;
-    if ((rc = run_mstep(h, o)) != NEMB_OK) return rc;
+    if ((rc = run_mstep(h, o, 0)) != NEMB_OK) return rc;
     CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
@@ -1218,7 +1274,7 @@ int nemb_stage_mstep(nemb_handle *h, const nemb_options *o, const float *t, floa
     if (nk_out || skd_out) {
         if (o->algo == NEMB_ALGO_NCEM) {
             int32_t *ti = malloc(sizeof(int32_t) * (kd + k));
-            CK(cudaMemcpy(ti, h->d_stat_int, sizeof(int32_t) * (kd + k), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ti, h->d_stat_loc, sizeof(int32_t) * (kd + k), cudaMemcpyDeviceToHost));
             if (skd_out) for (size_t q = 0; q < kd; q++) skd_out[q] = ti[q];
             if (nk_out) for (int c = 0; c < k; c++) nk_out[c] = ti[kd + c];
             free(ti);
@@ -1296,7 +1352,8 @@ int nemb_fit_random(nemb_handle *h, const nemb_options *o, int n_starts, int64_t
     h->cur = 0; h->state_labels = o->algo == NEMB_ALGO_NCEM;
     CK(cudaMemsetAsync(h->d_lab[0], 0, n, h->stream));
     if (!h->state_labels) { nemk_labels_to_t(h->stream, k, n, h->d_lab[0], h->d_t[0]); CKK(); }
-    if ((rc = run_mstep(h, o)) != NEMB_OK) return rc;
+    h->stats_valid = 0; h->ham_valid = 0;
+    if ((rc = run_mstep(h, o, 0)) != NEMB_OK) return rc;
     CK(cudaMemcpyAsync(sam, h->d_disp, sizeof(float) * d, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
 
@@ -1346,7 +1403,8 @@ int nemb_fit_random(nemb_handle *h, const nemb_options *o, int n_starts, int64_t
         h->cur = 0;
         CK(cudaMemcpyAsync(o->algo == NEMB_ALGO_NCEM ? (void *)h->d_lab[0] : (void *)h->d_t[0],
                            best_state, state_bytes, cudaMemcpyDeviceToDevice, h->stream));
-        if ((rc = run_mstep(h, o)) != NEMB_OK) return rc;   /* final EstimPara, nem_alg.c:1715 */
+        h->stats_valid = 0; h->ham_valid = 0;
+        if ((rc = run_mstep(h, o, 0)) != NEMB_OK) return rc;   /* final EstimPara, nem_alg.c:1715 */
         CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));

@@ -83,26 +83,63 @@ __global__ void k_pack_u8(const uint8_t *__restrict__ x, int n, int d, int wpr,
     }
 }
 
-// 32x32 bit-tile transpose with ballots: block = 32 families x 32 words
-__global__ void k_transpose_bits(const uint32_t *__restrict__ x, int n, int wpr, int d, int nwt,
-                                 uint32_t *__restrict__ xt) {
-    __shared__ uint32_t tile[32][33];
-    int r0 = blockIdx.x * 32, w0 = blockIdx.y * 32;
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 32 warps
-    int r = r0 + wid, w = w0 + lane;
-    tile[wid][lane] = (r < n && w < wpr) ? x[(size_t)r * wpr + w] : 0u;
-    __syncthreads();
-    // warp `wid` now transposes word column w0+wid: lane = family r0+lane
-    uint32_t word = tile[lane][wid];
-    int wcol = w0 + wid;
-    uint32_t mine = 0;
+// Bit-matrix transpose X -> XT.  A CTA owns 256 families x 32 words (1024 genomes), staged in
+// shared memory with coalesced 128-byte row reads.  Each thread then transposes 32x32 bit tiles IN
+// REGISTERS (5 butterfly stages of masked swaps, ~200 integer ops per tile instead of 32 warp
+// ballots) and every genome's 8 output words (256 families = one 32-byte sector) leave as two
+// 16-byte stores.
+static __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
+    // a[r] bit c  ->  a[c] bit r   (Hacker's Delight 7-3, LSB-first variant)
+    uint32_t m = 0x0000ffffu;
 #pragma unroll
-    for (int b = 0; b < 32; b++) {
-        uint32_t v = __ballot_sync(FULL, (word >> b) & 1u);
-        if (lane == b) mine = v;
+    for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+            a[k] ^= t << j;
+            a[k + j] ^= t;
+        }
     }
-    int dd = wcol * 32 + lane;
-    if (wcol < wpr && dd < d) xt[(size_t)dd * nwt + blockIdx.x] = mine;
+}
+
+#define TB_ROWS 256
+__global__ void __launch_bounds__(256)
+k_transpose_bits(const uint32_t *__restrict__ x, int n, int wpr, int d, int nwt,
+                 uint32_t *__restrict__ xt) {
+    __shared__ uint32_t smem_t[1024 * 9];   // >= TB_ROWS*33; reused as out[1024][9]
+    uint32_t (*tile)[33] = reinterpret_cast<uint32_t (*)[33]>(smem_t);
+    const int r0 = blockIdx.x * TB_ROWS, w0 = blockIdx.y * 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 8 warps
+    for (int rr = wid; rr < TB_ROWS; rr += 8) {
+        int r = r0 + rr, w = w0 + lane;
+        tile[rr][lane] = (r < n && w < wpr) ? x[(size_t)r * wpr + w] : 0u;
+    }
+    __syncthreads();
+    // thread (g = wid, c = lane): the 32x32 tile of row group g (families r0+32g..+31), word
+    // column c.  tile[32g + r][c]: the 32 lanes of a warp read 32 consecutive columns of one row
+    uint32_t a[32];
+#pragma unroll
+    for (int r = 0; r < 32; r++) a[r] = tile[wid * 32 + r][lane];
+    transpose32(a);
+    __syncthreads();
+    // a[b] = families 32g..32g+31 of genome (w0+lane)*32 + b.  Re-stage so that one thread owns
+    // one genome's 8 words: out[slot(genome)][g]
+    uint32_t (*outw)[9] = reinterpret_cast<uint32_t (*)[9]>(smem_t);
+#pragma unroll
+    for (int b = 0; b < 32; b++) outw[b * 32 + lane][wid] = a[b];   // slot b*32+c: conflict-free
+    __syncthreads();
+    const int g8 = blockIdx.x * 8;   // first output word of this CTA's 256 families
+    for (int q = threadIdx.x; q < 1024; q += 256) {
+        int dd = (w0 + (q & 31)) * 32 + (q >> 5);   // slot q = b*32 + c  ->  genome (w0+c)*32 + b
+        if (dd >= d) continue;
+        uint32_t *dst = xt + (size_t)dd * nwt + g8;
+        if (g8 + 8 <= nwt) {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(outw[q][0], outw[q][1], outw[q][2], outw[q][3]);
+            *reinterpret_cast<uint4 *>(dst + 4) = make_uint4(outw[q][4], outw[q][5], outw[q][6], outw[q][7]);
+        } else {
+            for (int g = 0; g < 8 && g8 + g < nwt; g++) dst[g] = outw[q][g];
+        }
+    }
 }
 
 // =============================================================================================
@@ -112,6 +149,79 @@ __global__ void k_transpose_bits(const uint32_t *__restrict__ x, int n, int wpr,
 // one CTA per class, variables in parallel.
 // =============================================================================================
 #define TT_THREADS 1024
+// tables of class k, by one CTA.  The two log() of a variable are only evaluated when its
+// dispersion differs from the class's first one (never, for the per-class-constant models).
+static __device__ void tables_class(int k, int K, int D, int wpr, const float *prop,
+                                    const float *center, const float *disp, nemk_coef *coef,
+                                    uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
+                                    uint32_t *mask_f1, double *delta, double *sh /*[32]*/,
+                                    int *sh_ok) {
+    int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) *sh_ok = 1;
+    __syncthreads();
+    const float e0 = disp[(size_t)k * D];
+    const bool live0 = (double)e0 > NEM_EPSILON;
+    double a0 = 0.0, c0 = 0.0;
+    if (live0) {
+        float ratio = __fdiv_rn(__fsub_rn(1.0f, e0), e0);
+        float om = __fsub_rn(1.0f, e0);
+        a0 = log((double)ratio);
+        c0 = -log((double)om);
+    }
+    double base_u = 0.0, base_g = 0.0;
+    int ok = 1, mu_moved = 0;
+    for (int j0 = 0; j0 < wpr * 32; j0 += TT_THREADS) {
+        int j = j0 + tid;  // wpr*32 is a multiple of 32, so whole warps stay together
+        bool in = j < D;
+        float mu = in ? center[(size_t)k * D + j] : 0.5f;
+        float e = in ? disp[(size_t)k * D + j] : e0;
+        int m0 = abs((int)(0.0f - mu)), m1 = abs((int)(1.0f - mu));
+        bool same = __float_as_uint(e) == __float_as_uint(e0);
+        bool live = same ? live0 : ((double)e > NEM_EPSILON);
+        double a = same ? a0 : 0.0, c = same ? c0 : 0.0;
+        if (in && live && !same) {
+            float ratio = __fdiv_rn(__fsub_rn(1.0f, e), e);
+            float om = __fsub_rn(1.0f, e);
+            a = log((double)ratio);
+            c = -log((double)om);
+        }
+        double cost0 = in ? (m0 * a + c) : 0.0, cost1 = in ? (m1 * a + c) : 0.0;
+        if (in) {
+            delta[(size_t)k * D + j] = cost1 - cost0;
+            base_g += cost0;
+            base_u += c;
+            if (!same || m0 > 1 || m1 > 1) ok = 0;
+        }
+        unsigned bx = __ballot_sync(FULL, in && m0 == 1 && m1 == 0);
+        unsigned bv = __ballot_sync(FULL, in && m0 != m1);
+        unsigned b0 = __ballot_sync(FULL, in && !live && m0 != 0);
+        unsigned b1 = __ballot_sync(FULL, in && !live && m1 != 0);
+        if (lane == 0 && (j >> 5) < wpr) {
+            size_t o = (size_t)k * wpr + (j >> 5);
+            if (mask_xor[o] != bx || mask_valid[o] != bv) mu_moved = 1;
+            mask_xor[o] = bx; mask_valid[o] = bv; mask_f0[o] = b0; mask_f1[o] = b1;
+        }
+    }
+    if (!ok) *sh_ok = 0;  // benign race: every writer stores 0
+    if (mu_moved) atomicOr(&coef->mu_changed, 1);   // preset by the launcher (0, or 1 = forced)
+    base_u = block_sum<TT_THREADS>(base_u, sh);
+    base_g = block_sum<TT_THREADS>(base_g, sh);
+    __syncthreads();
+    if (tid == 0) {
+        double pk = prop[k];
+        coef->lp[k] = (pk > NEM_EPSILON) ? log(pk) : neg_inf();  // nem_alg.c:2265-2271
+        if (*sh_ok) {
+            coef->a[k] = live0 ? a0 : 0.0;
+            coef->base[k] = live0 ? base_u : 0.0;
+            coef->forb[k] = live0 ? 0 : 1;
+        } else {
+            coef->a[k] = 0.0; coef->base[k] = base_g; coef->forb[k] = 0;
+        }
+        delta[(size_t)K * D + k] = base_g;  // general-path base: sum_d cost0_kd
+        if (!*sh_ok) atomicAnd(&coef->uniform_ok, 0);   // preset to non-zero by the launcher
+    }
+}
+
 __global__ void __launch_bounds__(TT_THREADS)
 k_theta_tables(int K, int D, int wpr, const float *__restrict__ prop,
                const float *__restrict__ center, const float *__restrict__ disp, nemk_coef *coef,
@@ -119,64 +229,8 @@ k_theta_tables(int K, int D, int wpr, const float *__restrict__ prop,
                double *delta) {
     __shared__ double sh[32];
     __shared__ int sh_ok;
-    int tid = threadIdx.x, lane = tid & 31;
-    {
-        const int k = blockIdx.x;
-        if (tid == 0) sh_ok = 1;
-        __syncthreads();
-        const float e0 = disp[(size_t)k * D];
-        double base_u = 0.0, base_g = 0.0;
-        int ok = 1;
-        for (int j0 = 0; j0 < wpr * 32; j0 += TT_THREADS) {
-            int j = j0 + tid;  // wpr*32 is a multiple of 32, so whole warps stay together
-            bool in = j < D;
-            float mu = in ? center[(size_t)k * D + j] : 0.5f;
-            float e = in ? disp[(size_t)k * D + j] : e0;
-            int m0 = abs((int)(0.0f - mu)), m1 = abs((int)(1.0f - mu));
-            bool live = (double)e > NEM_EPSILON;
-            double a = 0.0, c = 0.0;
-            if (in && live) {
-                float ratio = __fdiv_rn(__fsub_rn(1.0f, e), e);
-                float om = __fsub_rn(1.0f, e);
-                a = log((double)ratio);
-                c = -log((double)om);
-            }
-            double cost0 = in ? (m0 * a + c) : 0.0, cost1 = in ? (m1 * a + c) : 0.0;
-            if (in) {
-                delta[(size_t)k * D + j] = cost1 - cost0;
-                base_g += cost0;
-                base_u += c;
-                if (__float_as_uint(e) != __float_as_uint(e0) || m0 > 1 || m1 > 1) ok = 0;
-            }
-            unsigned bx = __ballot_sync(FULL, in && m0 == 1 && m1 == 0);
-            unsigned bv = __ballot_sync(FULL, in && m0 != m1);
-            unsigned b0 = __ballot_sync(FULL, in && !live && m0 != 0);
-            unsigned b1 = __ballot_sync(FULL, in && !live && m1 != 0);
-            if (lane == 0 && (j >> 5) < wpr) {
-                size_t o = (size_t)k * wpr + (j >> 5);
-                mask_xor[o] = bx; mask_valid[o] = bv; mask_f0[o] = b0; mask_f1[o] = b1;
-            }
-        }
-        if (!ok) sh_ok = 0;  // benign race: every writer stores 0
-        base_u = block_sum<TT_THREADS>(base_u, sh);
-        base_g = block_sum<TT_THREADS>(base_g, sh);
-        __syncthreads();
-        if (tid == 0) {
-            double pk = prop[k];
-            coef->lp[k] = (pk > NEM_EPSILON) ? log(pk) : neg_inf();  // nem_alg.c:2265-2271
-            bool live = (double)e0 > NEM_EPSILON;
-            if (sh_ok) {
-                float ratio = __fdiv_rn(__fsub_rn(1.0f, e0), e0);
-                coef->a[k] = live ? log((double)ratio) : 0.0;
-                coef->base[k] = live ? base_u : 0.0;
-                coef->forb[k] = live ? 0 : 1;
-            } else {
-                coef->a[k] = 0.0; coef->base[k] = base_g; coef->forb[k] = 0;
-            }
-            delta[(size_t)K * D + k] = base_g;  // general-path base: sum_d cost0_kd
-            if (!sh_ok) atomicAnd(&coef->uniform_ok, 0);   // preset to non-zero by the launcher
-        }
-    }
+    tables_class(blockIdx.x, K, D, wpr, prop, center, disp, coef, mask_xor, mask_valid, mask_f0,
+                 mask_f1, delta, sh, &sh_ok);
 }
 
 // =============================================================================================
@@ -190,8 +244,9 @@ __global__ void __launch_bounds__(256)
 k_density_uniform(int K, const uint4 *__restrict__ x, int n, int wpr4,
                   const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
                   const uint4 *__restrict__ mval, double *__restrict__ logpf,
-                  int32_t *__restrict__ hamming) {
+                  int32_t *__restrict__ hamming, int cached) {
     if (coef->empty_class) return;  // M-step found an empty class: E-step is not run
+    if (cached && !coef->mu_changed) return;
     extern __shared__ uint4 smem[];
     uint4 *sx = smem, *sv = smem + (size_t)KT * wpr4;
     for (int i = threadIdx.x; i < K * wpr4; i += blockDim.x) { sx[i] = mxor[i]; sv[i] = mval[i]; }
@@ -300,8 +355,9 @@ __global__ void __launch_bounds__(ROWS *T)
 k_density_tma(int K, const uint4 *__restrict__ x, int n, int wpr4, int stride4, int n_tiles,
               int n_stages, const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
               const uint4 *__restrict__ mval, double *__restrict__ logpf,
-              int32_t *__restrict__ hamming) {
+              int32_t *__restrict__ hamming, int cached) {
     if (coef->empty_class) return;
+    if (cached && !coef->mu_changed) return;   // H cache still valid: k_logpf_from_h does the work
     extern __shared__ __align__(128) uint4 dsm[];
     __shared__ __align__(8) uint64_t bars[16];
     __shared__ int hsum[2][ROWS * KT];
@@ -409,8 +465,9 @@ __global__ void __launch_bounds__(256)
 k_density_direct(int K, const uint4 *__restrict__ x, int n, int wpr4,
                  const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
                  const uint4 *__restrict__ mval, double *__restrict__ logpf,
-                 int32_t *__restrict__ hamming) {
+                 int32_t *__restrict__ hamming, int cached) {
     if (coef->empty_class) return;
+    if (cached && !coef->mu_changed) return;
     extern __shared__ __align__(16) uint4 dsm2[];
     uint4 *smask = dsm2;  // [wpr4][KT][2] (xor, valid): the 2*KT masks of a chunk are contiguous
     for (int i = threadIdx.x; i < KT * wpr4; i += blockDim.x) {
@@ -606,6 +663,52 @@ static __device__ __forceinline__ void mark_readers(int i, const int32_t *__rest
 
 // ---- ncem, parallel (Jacobi) update; also round 0 of the speculative sequential sweep
 // (dirty != nullptr): changed sites queue their later readers for the fix-up rounds.
+// ---- high-degree sites ("hubs": backbone families carry ~100 island anchors).  One thread walking
+// a hub's neighbour list serialises ~3 memory round trips per 4 neighbours and becomes the tail of
+// the whole sweep, so sites with more than HEAVY_DEG neighbours are evaluated by a full warp: the
+// 32 lanes fetch 32 neighbours (index, weight, label) at once, then the weights are ADDED IN FILE
+// ORDER through shuffles, so the float64 sum is bit-identical to the one-thread sum
+// (SumNeighsOfClass order, nem_alg.c:2865-2875).  Every lane ends with the same ctx.
+#define HEAVY_DEG 16
+template <int KT, typename Pick>
+static __device__ __forceinline__ void ctx_labels_warp(int K, int i, const int32_t *__restrict__ row_ptr,
+                                                       const int32_t *__restrict__ col,
+                                                       const float *__restrict__ wgt, Pick pick,
+                                                       double *ctx) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < KT; k++) ctx[k] = 0.0;
+    if (!row_ptr) return;
+    int lo = row_ptr[i], hi = row_ptr[i + 1];
+    for (int e0 = lo; e0 < hi; e0 += 32) {
+        int e = e0 + lane;
+        bool in = e < hi;
+        int j = in ? col[e] : -1;
+        float w = in ? wgt[e] : 0.f;
+        unsigned l = in ? pick(j) : 255u;
+        int cnt = min(32, hi - e0);
+        for (int q = 0; q < cnt; q++) {
+            unsigned lq = __shfl_sync(FULL, l, q);
+            float wq = __shfl_sync(FULL, w, q);
+#pragma unroll
+            for (int k = 0; k < KT; k++)
+                if (lq == (unsigned)k) ctx[k] += (double)wq;
+        }
+    }
+}
+
+static __device__ __forceinline__ void mark_readers_warp(int i, const int32_t *__restrict__ rrow_ptr,
+                                                         const int32_t *__restrict__ rcol,
+                                                         int32_t *dirty, int32_t *wl,
+                                                         int32_t *wl_count, int row0, int row1) {
+    int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
+    for (int e = lo + (threadIdx.x & 31); e < hi; e += 32) {
+        int j = rcol[e];
+        if (j > i && j >= row0 && j < row1 && atomicExch(&dirty[j], 1) == 0)
+            wl[atomicAdd(wl_count, 1)] = j;
+    }
+}
+
 // Rows [row0, row0+n_loc) of the GLOBAL graph are this rank's (row0 = 0, n_loc = N on one GPU);
 // labels, CSR, dirty flags and work lists are indexed by global family id, logpf by local row.
 template <int KT>
@@ -615,23 +718,47 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const double *__restrict__ logpf
                     const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_in,
                     uint8_t *__restrict__ lab_out, int32_t *dirty, int32_t *wl, int32_t *wl_count,
                     const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
+                    const int32_t *__restrict__ heavy, int n_heavy, int heavy_blocks,
                     nemk_counters *cnt, const int32_t *__restrict__ skip) {
     if (skip && *skip) return;
-    int il = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = row0 + il;
+    const int lane = threadIdx.x & 31;
     int changed = 0, flags = 0;
-    if (il < n_loc) {
+    if ((int)blockIdx.x < heavy_blocks) {
+        // hubs first (longest work): one warp per site
+        int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (wid >= n_heavy) return;
+        int i = heavy[wid], il = i - row0;
         double ctx[KT];
-        ctx_labels<KT>(K, i, beta != 0.0 ? row_ptr : nullptr, col, wgt,
-                       [&](int j) { return (unsigned)lab_in[j]; }, ctx);
+        ctx_labels_warp<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
         int km = site_argmax<KT>(K, logpf + (size_t)il * K, ctx, beta, flags);
-        lab_out[i] = (uint8_t)km;
-        changed = (km != (int)lab_in[i]);
-        if (changed && dirty) mark_readers(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc);
+        int ch = (km != (int)lab_in[i]);
+        if (lane == 0) lab_out[i] = (uint8_t)km;
+        if (ch && dirty) mark_readers_warp(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc);
+        if (lane == 0) {
+            if (ch) atomicAdd(&cnt->changed, 1);
+            if (flags & 1) atomicAdd(&cnt->allnul, 1);
+            if (flags & 2) atomicAdd(&cnt->ties, 1);
+        }
+        return;
+    }
+    int il = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x;
+    int i = row0 + il;
+    if (il < n_loc) {
+        const int32_t *rp = beta != 0.0 ? row_ptr : nullptr;
+        bool is_heavy = heavy_blocks && rp && (rp[i + 1] - rp[i] > HEAVY_DEG);
+        if (!is_heavy) {
+            double ctx[KT];
+            ctx_labels<KT>(K, i, rp, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
+            int km = site_argmax<KT>(K, logpf + (size_t)il * K, ctx, beta, flags);
+            lab_out[i] = (uint8_t)km;
+            changed = (km != (int)lab_in[i]);
+            if (changed && dirty)
+                mark_readers(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc);
+        }
     }
     unsigned bc = __ballot_sync(FULL, changed), bn = __ballot_sync(FULL, flags & 1),
              bt = __ballot_sync(FULL, flags & 2);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (bc) atomicAdd(&cnt->changed, __popc(bc));
         if (bn) atomicAdd(&cnt->allnul, __popc(bn));
         if (bt) atomicAdd(&cnt->ties, __popc(bt));
@@ -676,6 +803,68 @@ static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row
     return (km != old) - (was != old);
 }
 
+// the same for a hub, by a whole warp (every lane returns the same delta)
+template <int KT>
+static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, int row1,
+                                                      const double *__restrict__ logpf,
+                                                      const int32_t *__restrict__ row_ptr,
+                                                      const int32_t *__restrict__ col,
+                                                      const float *__restrict__ wgt, double beta,
+                                                      const uint8_t *__restrict__ lab_old,
+                                                      uint8_t *lab_cur, int32_t *dirty,
+                                                      int32_t *next_list, int32_t *next_cnt,
+                                                      const int32_t *__restrict__ rrow_ptr,
+                                                      const int32_t *__restrict__ rcol) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) { atomicExch(&dirty[i], 0); __threadfence(); }
+    __syncwarp();
+    double ctx[KT];
+    ctx_labels_warp<KT>(K, i, row_ptr, col, wgt,
+                        [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
+    int flags;
+    int km = site_argmax<KT>(K, logpf + (size_t)(i - row0) * K, ctx, beta, flags);
+    int was = __shfl_sync(FULL, (int)__ldcg(lab_cur + i), 0);
+    if (km == was) return 0;
+    if (lane == 0) { lab_cur[i] = (uint8_t)km; __threadfence(); }
+    __syncwarp();
+    mark_readers_warp(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1);
+    int old = lab_old[i];
+    return (km != old) - (was != old);
+}
+
+// one work-list slot per lane; light sites by their lane, hubs afterwards by the whole warp.
+// `idx` must be warp-uniform in validity order (idx = base + lane).  Returns this lane's delta.
+template <int KT>
+static __device__ __forceinline__ int fixup_items(int K, int idx, int count,
+                                                  const int32_t *__restrict__ cur_list, int row0,
+                                                  int row1, const double *__restrict__ logpf,
+                                                  const int32_t *__restrict__ row_ptr,
+                                                  const int32_t *__restrict__ col,
+                                                  const float *__restrict__ wgt, double beta,
+                                                  const uint8_t *__restrict__ lab_old,
+                                                  uint8_t *lab_cur, int32_t *dirty,
+                                                  int32_t *next_list, int32_t *next_cnt,
+                                                  const int32_t *__restrict__ rrow_ptr,
+                                                  const int32_t *__restrict__ rcol) {
+    const int lane = threadIdx.x & 31;
+    int i = idx < count ? cur_list[idx] : -1;
+    bool hub = i >= 0 && (row_ptr[i + 1] - row_ptr[i] > HEAVY_DEG);
+    int d = 0;
+    if (i >= 0 && !hub)
+        d = fixup_site<KT>(K, i, row0, row1, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
+                           next_list, next_cnt, rrow_ptr, rcol);
+    unsigned hm = __ballot_sync(FULL, hub);
+    while (hm) {
+        int src = __ffs(hm) - 1;
+        hm &= hm - 1;
+        int site = __shfl_sync(FULL, i, src);
+        int r = fixup_site_warp<KT>(K, site, row0, row1, logpf, row_ptr, col, wgt, beta, lab_old,
+                                    lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
+        if (lane == src) d = r;
+    }
+    return d;
+}
+
 // Work lists: two lists used alternately, FOUR rotating counters.  Round r consumes list r&1 with
 // count wl_cnt[r&3], appends to list (r+1)&1 through wl_cnt[(r+1)&3] and clears wl_cnt[(r+2)&3]
 // (idle during round r), so no memset sits between rounds.  The tail kernel leaves all four at 0.
@@ -695,9 +884,11 @@ k_sweep_ncem_fixup_round(int K, int row0, int row1, const double *__restrict__ l
     int32_t *next_cnt = &wl_cnt[(round + 1) & 3];
     if (blockIdx.x == 0 && threadIdx.x == 0) wl_cnt[(round + 2) & 3] = 0;
     int dchanged = 0;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x)
-        dchanged += fixup_site<KT>(K, cur_list[idx], row0, row1, logpf, row_ptr, col, wgt, beta,
-                                   lab_old, lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count;
+         base += gridDim.x * blockDim.x)
+        dchanged += fixup_items<KT>(K, base + (threadIdx.x & 31), count, cur_list, row0, row1, logpf,
+                                    row_ptr, col, wgt, beta, lab_old, lab_cur, dirty, next_list,
+                                    next_cnt, rrow_ptr, rcol);
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
     if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(&cnt->nfix, 1);
 }
@@ -725,9 +916,10 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const double *__restrict__ logpf,
         int count = s_count;
         if (count == 0) break;
         rounds++;
-        for (int idx = threadIdx.x; idx < count; idx += blockDim.x)
-            dchanged += fixup_site<KT>(K, cur_list[idx], row0, row1, logpf, row_ptr, col, wgt, beta,
-                                       lab_old, lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
+        for (int base = threadIdx.x & ~31; base < count; base += blockDim.x)
+            dchanged += fixup_items<KT>(K, base + (threadIdx.x & 31), count, cur_list, row0, row1,
+                                        logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
+                                        next_list, next_cnt, rrow_ptr, rcol);
         __syncthreads();
     }
     if (threadIdx.x < 4) wl_cnt[threadIdx.x] = 0;
@@ -923,13 +1115,14 @@ k_sweep_nem_level(int K, const double *__restrict__ logpf, const int32_t *__rest
 template <int KT>
 __global__ void __launch_bounds__(256)
 k_label_masks(int K, int n, int nwt, const uint8_t *__restrict__ lab, uint32_t *__restrict__ cm,
-              int32_t *nk) {
+              int32_t *nk, uint8_t *__restrict__ lab_m) {
     __shared__ int snk[KT];
     if (threadIdx.x < KT) snk[threadIdx.x] = 0;
     __syncthreads();
     int lane = threadIdx.x & 31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwt * 32; i += gridDim.x * blockDim.x) {
         unsigned l = (i < n) ? lab[i] : 255u;
+        if (lab_m && i < n) lab_m[i] = (uint8_t)l;
 #pragma unroll
         for (int k = 0; k < KT; k++) {
             if (k < K) {
@@ -994,6 +1187,102 @@ k_mstep_ncem(int K, int D, int nwt4, const uint4 *__restrict__ xt, const uint4 *
                 if (lane == k && s) atomicAdd(&S[(size_t)k * D + dd], s);
             }
         }
+    }
+}
+
+// ncem, incremental statistics.  After the first iterations only a few hundred families change
+// class per sweep (the centres stop moving), so instead of re-reading X^T
+// (N*D/8 bytes) the statistics are UPDATED: every row whose label differs from lab_m (the labels
+// S and n currently describe) moves its bits from S[old] to S[new].  Integer adds: exact, and the
+// result equals the full recount whatever the order.
+__global__ void __launch_bounds__(256)
+k_changed_rows(int n, const uint8_t *__restrict__ lab, const uint8_t *__restrict__ lab_m,
+               int32_t *list, int32_t *count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ch = i < n && lab[i] != lab_m[i];
+    unsigned m = __ballot_sync(FULL, ch);
+    int lane = threadIdx.x & 31, base = 0;
+    if (m && lane == 0) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (ch) list[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+// work item = (group of 32 changed rows, chunk of DELTA_CHUNK words): lane = row, its DELTA_CHUNK/4
+// uint4 loads are issued together; per 32-genome word a ballot transpose gives lane b the 32-row
+// column of genome 32w+b, which meets the rows' old/new class masks by popcount.  Items are spread
+// over the whole grid, so a few hundred changed rows cost microseconds.
+#define DELTA_CHUNK 16
+template <int KT>
+__global__ void __launch_bounds__(256)
+k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8_t *__restrict__ lab,
+              const uint8_t *__restrict__ lab_m, const int32_t *__restrict__ list,
+              const int32_t *__restrict__ count, int32_t *S, int32_t *nk) {
+    const int lane = threadIdx.x & 31;
+    const int total = *count;
+    const int groups = (total + 31) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
+    const int wreal = (D + 31) >> 5;
+    const int chunks = (wreal + DELTA_CHUNK - 1) / DELTA_CHUNK;
+    const long long items = (long long)groups * chunks;
+    for (long long it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += warps) {
+        int g = (int)(it / chunks), c = (int)(it % chunks);
+        int idx = g * 32 + lane;
+        int row = idx < total ? list[idx] : -1;
+        unsigned lo = row >= 0 ? lab_m[row] : 255u, ln = row >= 0 ? lab[row] : 255u;
+        unsigned plus[KT], minus[KT];
+#pragma unroll
+        for (int k = 0; k < KT; k++) {
+            plus[k] = __ballot_sync(FULL, ln == (unsigned)k);
+            minus[k] = __ballot_sync(FULL, lo == (unsigned)k);
+        }
+        if (c == 0 && lane < K) {
+            int dn = 0;
+#pragma unroll
+            for (int k = 0; k < KT; k++)
+                if (lane == k) dn = __popc(plus[k]) - __popc(minus[k]);
+            if (dn) atomicAdd(&nk[lane], dn);
+        }
+        const uint32_t *xr = x + (size_t)(row >= 0 ? row : 0) * wpr + (size_t)c * DELTA_CHUNK;
+        uint4 v4[DELTA_CHUNK / 4];
+#pragma unroll
+        for (int u = 0; u < DELTA_CHUNK / 4; u++)   // wpr is a multiple of 4: whole uint4 stay in the row
+            v4[u] = (row >= 0 && c * DELTA_CHUNK + u * 4 < wpr) ? __ldg((const uint4 *)xr + u)
+                                                              : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < DELTA_CHUNK / 4; u++) {
+            uint32_t vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int w = c * DELTA_CHUNK + u * 4 + q;
+                if (w >= wreal) break;
+                uint32_t word = vv[q], mine = 0;
+#pragma unroll
+                for (int b = 0; b < 32; b++) {
+                    uint32_t col = __ballot_sync(FULL, (word >> b) & 1u);
+                    if (lane == b) mine = col;
+                }
+                int d = w * 32 + lane;
+                if (d < D) {
+#pragma unroll
+                    for (int k = 0; k < KT; k++) {
+                        if (k < K) {
+                            int dv = __popc(mine & plus[k]) - __popc(mine & minus[k]);
+                            if (dv) atomicAdd(&S[(size_t)k * D + d], dv);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// lab_m <- lab for the rows of the list (after every item of k_mstep_delta has read lab_m)
+__global__ void __launch_bounds__(256)
+k_commit_labels(const uint8_t *__restrict__ lab, uint8_t *__restrict__ lab_m,
+                const int32_t *__restrict__ list, const int32_t *__restrict__ count) {
+    int total = *count;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int row = list[idx];
+        lab_m[row] = lab[row];
     }
 }
 
@@ -1084,83 +1373,99 @@ __global__ void k_mstep_nem_reduce(int K, int D, int nchunks, const double *__re
 // forced for Bernoulli, nem_mod.c:446-447);  proportions (nem_mod.c:455-465).
 // theta is float32 like the reference; divisions are float divisions.
 // =============================================================================================
-#define FIN_THREADS 1024
-__global__ void __launch_bounds__(FIN_THREADS)
-k_mstep_finalize(int K, int N, int D, int prop_model, int disp_model,
-                 const int32_t *__restrict__ s_int, const int32_t *__restrict__ nk_int,
-                 const double *__restrict__ s_dbl, const double *__restrict__ nk_dbl, float *prop,
-                 float *center, float *disp, float *iner, nemk_coef *coef) {
+// One CTA per class; a class's CTA derives mu, eps, p of ITS class (the models that pool classes,
+// s_d and s__, recompute the other classes' inertia from S and n: a few thousand flops) and goes
+// straight on to the class's density tables (tables_class) -- M-step closed forms and the E-step
+// tables in one launch.
+static __device__ __forceinline__ float iner_of(double s, double n, bool nonempty, float mu_keep) {
+    // EstimLaplaceCenters / ComputeMedian then EstimLaplaceIner; an empty class keeps its centre
+    // (nem_mod.c:1363) and has n = S = 0, hence zero inertia
+    double half = 0.5 * n;
+    float mu = nonempty ? (s > half ? 1.0f : (s < half ? 0.0f : 0.5f)) : mu_keep;
+    return (float)(s * fabs(1.0 - (double)mu) + (n - s) * fabs((double)mu));
+}
+
+__global__ void __launch_bounds__(TT_THREADS)
+k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_model,
+                        const int32_t *__restrict__ s_int, const int32_t *__restrict__ nk_int,
+                        const double *__restrict__ s_dbl, const double *__restrict__ nk_dbl,
+                        float *prop, float *center, float *disp, nemk_coef *coef,
+                        uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
+                        uint32_t *mask_f1, double *delta) {
     __shared__ double sh[32];
     __shared__ float nkf[NEMB_MAX_K];
     __shared__ double nkd[NEMB_MAX_K];
-    __shared__ int empty;
-    int tid = threadIdx.x;
-    if (tid == 0) empty = 0;
-    __syncthreads();
+    __shared__ int sh_ok;
+    const int tid = threadIdx.x, k = blockIdx.x;
     if (tid < K) {
         double v = s_int ? (double)nk_int[tid] : nk_dbl[tid];
         nkd[tid] = v;
         nkf[tid] = (float)v;
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int k = 0; k < K; k++)
-            if (!((double)nkf[k] > NEM_EPSILON)) empty = k + 1;  // nem_mod.c:1363,1404-1409
+    if (k == 0 && tid == 0) {
+        int empty = 0;
+        for (int c = 0; c < K; c++)
+            if (!((double)nkf[c] > NEM_EPSILON)) empty = c + 1;  // nem_mod.c:1363,1404-1409
         coef->empty_class = empty;  // like the reference: the LAST empty class, 1-based
     }
-    for (int q = tid; q < K * D; q += FIN_THREADS) {
-        int k = q / D;
-        double s = s_int ? (double)s_int[q] : s_dbl[q];
-        double n = nkd[k], half = 0.5 * n;
-        float mu = center[q];
-        if ((double)nkf[k] > NEM_EPSILON) {
-            mu = s > half ? 1.0f : (s < half ? 0.0f : 0.5f);
-            center[q] = mu;
+    auto S_of = [&](int c, int j) -> double {
+        size_t q = (size_t)c * D + j;
+        return s_int ? (double)s_int[q] : s_dbl[q];
+    };
+    const bool nonempty = (double)nkf[k] > NEM_EPSILON;
+    // centres of this class
+    for (int j = tid; j < D; j += TT_THREADS) {
+        if (nonempty) {
+            double s = S_of(k, j), half = 0.5 * nkd[k];
+            center[(size_t)k * D + j] = s > half ? 1.0f : (s < half ? 0.0f : 0.5f);
         }
-        double in = s * fabs(1.0 - (double)mu) + (n - s) * fabs((double)mu);
-        iner[q] = (float)in;
     }
-    __syncthreads();
+    // dispersions of this class
     if (disp_model == 3) {  // skd: nem_mod.c:1152-1170
-        for (int q = tid; q < K * D; q += FIN_THREADS) {
-            int k = q / D;
-            if ((double)nkf[k] > NEM_EPSILON) disp[q] = __fdiv_rn(iner[q], nkf[k]);
-        }
+        if (nonempty)
+            for (int j = tid; j < D; j += TT_THREADS)
+                disp[(size_t)k * D + j] =
+                    __fdiv_rn(iner_of(S_of(k, j), nkd[k], true, 0.f), nkf[k]);
     } else if (disp_model == 1) {  // sk_: nem_mod.c:1043-1073
-        for (int k = 0; k < K; k++) {
-            double si = 0.0;
-            for (int j = tid; j < D; j += FIN_THREADS) si += (double)iner[(size_t)k * D + j];
-            si = block_sum<FIN_THREADS>(si, sh);
-            if (nkf[k] > 0.f) {
-                double sn = (double)nkf[k] * (double)D;
-                float dk = __fdiv_rn((float)si, (float)sn);
-                for (int j = tid; j < D; j += FIN_THREADS) disp[(size_t)k * D + j] = dk;
-            }
+        double si = 0.0;
+        for (int j = tid; j < D; j += TT_THREADS)
+            si += (double)iner_of(S_of(k, j), nkd[k], nonempty, center[(size_t)k * D + j]);
+        si = block_sum<TT_THREADS>(si, sh);
+        if (nkf[k] > 0.f) {
+            double sn = (double)nkf[k] * (double)D;
+            float dk = __fdiv_rn((float)si, (float)sn);
+            for (int j = tid; j < D; j += TT_THREADS) disp[(size_t)k * D + j] = dk;
         }
-    } else if (disp_model == 2) {  // s_d: nem_mod.c:1104-1126, float sums over k in order
-        for (int j = tid; j < D; j += FIN_THREADS) {
+    } else if (disp_model == 2) {  // s_d: nem_mod.c:1104-1126, float sums over the classes in order
+        for (int j = tid; j < D; j += TT_THREADS) {
             float si = 0.f, sn = 0.f;
-            for (int k = 0; k < K; k++) {
-                sn = __fadd_rn(sn, nkf[k]);
-                si = __fadd_rn(si, iner[(size_t)k * D + j]);
+            for (int c = 0; c < K; c++) {
+                bool ne = (double)nkf[c] > NEM_EPSILON;
+                sn = __fadd_rn(sn, nkf[c]);
+                si = __fadd_rn(si, iner_of(S_of(c, j), nkd[c], ne, ne ? 0.f : center[(size_t)c * D + j]));
             }
-            float dd = __fdiv_rn(si, sn);
-            for (int k = 0; k < K; k++) disp[(size_t)k * D + j] = dd;
+            disp[(size_t)k * D + j] = __fdiv_rn(si, sn);
         }
     } else {  // s__: nem_mod.c:988-1015
         double si = 0.0, sn = 0.0;
-        for (int k = 0; k < K; k++) {
-            if (nkf[k] > 0.f) {
-                for (int j = tid; j < D; j += FIN_THREADS) si += (double)iner[(size_t)k * D + j];
-                sn += (double)nkf[k] * (double)D;
+        for (int c = 0; c < K; c++) {
+            if (nkf[c] > 0.f) {
+                bool ne = (double)nkf[c] > NEM_EPSILON;
+                for (int j = tid; j < D; j += TT_THREADS)
+                    si += (double)iner_of(S_of(c, j), nkd[c], ne, ne ? 0.f : center[(size_t)c * D + j]);
+                sn += (double)nkf[c] * (double)D;
             }
         }
-        si = block_sum<FIN_THREADS>(si, sh);
+        si = block_sum<TT_THREADS>(si, sh);
         float v = __fdiv_rn((float)si, (float)sn);
-        for (int q = tid; q < K * D; q += FIN_THREADS) disp[q] = v;
+        for (int j = tid; j < D; j += TT_THREADS) disp[(size_t)k * D + j] = v;
     }
-    if (tid < K)  // nem_mod.c:456-465
-        prop[tid] = prop_model == 1 ? __fdiv_rn(nkf[tid], (float)N) : (float)(1.0 / (double)K);
+    if (tid == 0)  // nem_mod.c:456-465
+        prop[k] = prop_model == 1 ? __fdiv_rn(nkf[k], (float)N) : (float)(1.0 / (double)K);
+    __syncthreads();   // this CTA's theta is written: build the class tables from it
+    tables_class(k, K, D, wpr, prop, center, disp, coef, mask_xor, mask_valid, mask_f0, mask_f1,
+                 delta, sh, &sh_ok);
 }
 
 // =============================================================================================
@@ -1168,50 +1473,77 @@ k_mstep_finalize(int K, int N, int D, int prop_model, int disp_model,
 // U = D + beta/2 G, M = D + beta G + Z; float64, log-domain L and Z, deterministic two-stage sum.
 // =============================================================================================
 template <int KT>
+static __device__ __forceinline__ void crit_site(int K, const double *__restrict__ lp,
+                                                 const double *ctx, const float *ti, double beta,
+                                                 double &cD, double &cG, double &cL, double &cZ) {
+    double lmx = neg_inf(), zmx = neg_inf();
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        if (k < K) { lmx = fmax(lmx, lp[k]); zmx = fmax(zmx, beta * ctx[k]); }
+    }
+    double fs = 0, zs = 0;
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        if (k < K) {
+            double l = lp[k];
+            float cik = ti[k];
+            if (cik > FLT_MIN) {  // MINFLOAT, nem_alg.c:2727
+                double lc = (l == neg_inf()) ? -(double)FLT_MAX : l;  // nem_mod.c:685
+                cD += (double)cik * (lc - log((double)cik));
+                cG += (double)cik * ctx[k];
+            }
+            if (lmx > neg_inf()) fs += exp(l - lmx);
+            zs += exp(beta * ctx[k] - zmx);
+        }
+    }
+    cL += (lmx > neg_inf()) ? lmx + log(fs) : neg_inf();
+    cZ -= zmx + log(zs);
+}
+
+// blocks [0, heavy_blocks): hubs of the (index-sorted) heavy list, one warp per site;
+// the other blocks: the remaining sites, one thread per site.  Fixed assignment => deterministic.
+template <int KT>
 __global__ void __launch_bounds__(256)
 k_criteria_partial(int K, int row0, int n_loc, const double *__restrict__ logpf,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab,
-                   const float *__restrict__ t, double *__restrict__ partials) {
+                   const float *__restrict__ t, const int32_t *__restrict__ heavy, int n_heavy,
+                   int heavy_blocks, double *__restrict__ partials) {
     __shared__ double sh[32];
     double cD = 0, cG = 0, cL = 0, cZ = 0;
-    for (int il = blockIdx.x * blockDim.x + threadIdx.x; il < n_loc; il += gridDim.x * blockDim.x) {
-        const int i = row0 + il;
-        double ctx[KT];
-        float ti[KT];
-        if (lab) {
-            ctx_labels<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab[j]; }, ctx);
+    if ((int)blockIdx.x < heavy_blocks) {
+        const int lane = threadIdx.x & 31;
+        int warps = heavy_blocks * (blockDim.x >> 5);
+        for (int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < n_heavy; wi += warps) {
+            int i = heavy[wi];
+            double ctx[KT];
+            float ti[KT];
+            ctx_labels_warp<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab[j]; }, ctx);
             unsigned l = lab[i];
 #pragma unroll
             for (int k = 0; k < KT; k++) ti[k] = (l == (unsigned)k) ? 1.f : 0.f;
-        } else {
-            ctx_fuzzy<KT>(K, i, row_ptr, col, wgt, t, ctx);
-#pragma unroll
-            for (int k = 0; k < KT; k++) ti[k] = (k < K) ? t[(size_t)i * K + k] : 0.f;
+            if (lane == 0) crit_site<KT>(K, logpf + (size_t)(i - row0) * K, ctx, ti, beta, cD, cG, cL, cZ);
         }
-        const double *lp = logpf + (size_t)il * K;
-        double lmx = neg_inf(), zmx = neg_inf();
+    } else {
+        int nb = gridDim.x - heavy_blocks;
+        for (int il = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x; il < n_loc;
+             il += nb * blockDim.x) {
+            const int i = row0 + il;
+            if (heavy_blocks && row_ptr && row_ptr[i + 1] - row_ptr[i] > HEAVY_DEG) continue;
+            double ctx[KT];
+            float ti[KT];
+            if (lab) {
+                ctx_labels<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab[j]; }, ctx);
+                unsigned l = lab[i];
 #pragma unroll
-        for (int k = 0; k < KT; k++) {
-            if (k < K) { lmx = fmax(lmx, lp[k]); zmx = fmax(zmx, beta * ctx[k]); }
-        }
-        double fs = 0, zs = 0;
+                for (int k = 0; k < KT; k++) ti[k] = (l == (unsigned)k) ? 1.f : 0.f;
+            } else {
+                ctx_fuzzy<KT>(K, i, row_ptr, col, wgt, t, ctx);
 #pragma unroll
-        for (int k = 0; k < KT; k++) {
-            if (k < K) {
-                double l = lp[k];
-                float cik = ti[k];
-                if (cik > FLT_MIN) {  // MINFLOAT, nem_alg.c:2727
-                    double lc = (l == neg_inf()) ? -(double)FLT_MAX : l;  // nem_mod.c:685
-                    cD += (double)cik * (lc - log((double)cik));
-                    cG += (double)cik * ctx[k];
-                }
-                if (lmx > neg_inf()) fs += exp(l - lmx);
-                zs += exp(beta * ctx[k] - zmx);
+                for (int k = 0; k < KT; k++) ti[k] = (k < K) ? t[(size_t)i * K + k] : 0.f;
             }
+            crit_site<KT>(K, logpf + (size_t)il * K, ctx, ti, beta, cD, cG, cL, cZ);
         }
-        cL += (lmx > neg_inf()) ? lmx + log(fs) : neg_inf();
-        cZ -= zmx + log(zs);
     }
     cD = block_sum<256>(cD, sh);
     cG = block_sum<256>(cG, sh);
@@ -1258,6 +1590,69 @@ __global__ void k_sum_ranks_f64(int world, size_t count, const double *__restric
     double s = 0.0;
     for (int r = 0; r < world; r++) s += stage[(size_t)r * count + q];
     out[q] = s;
+}
+
+// =============================================================================================
+// Loader: index-sorted list of the hubs (degree > HEAVY_DEG) among this rank's rows -- a
+// deterministic 3-kernel compaction (count per block, scan of the block counts, fill).
+// =============================================================================================
+#define HL_THREADS 1024
+__global__ void __launch_bounds__(HL_THREADS)
+k_heavy_count(int row0, int n_loc, const int32_t *__restrict__ row_ptr, int32_t *block_counts) {
+    int il = blockIdx.x * HL_THREADS + threadIdx.x;
+    int i = row0 + il;
+    int hv = (il < n_loc) && (row_ptr[i + 1] - row_ptr[i] > HEAVY_DEG);
+    int c = __syncthreads_count(hv);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(HL_THREADS)
+k_heavy_scan(int nblocks, int32_t *block_counts, int32_t *total) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nblocks; b0 += HL_THREADS) {
+        int b = b0 + threadIdx.x;
+        int v = b < nblocks ? block_counts[b] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int ws = wsum[lane], z = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL, z, o); if (lane >= o) z += y; }
+            wsum[lane] = z - ws;   // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        int excl = carry + wsum[w] + x - v;
+        if (b < nblocks) block_counts[b] = excl;
+        __syncthreads();
+        if (threadIdx.x == HL_THREADS - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(HL_THREADS)
+k_heavy_fill(int row0, int n_loc, const int32_t *__restrict__ row_ptr,
+             const int32_t *__restrict__ block_offsets, int32_t *list) {
+    __shared__ int wsum[32];
+    int il = blockIdx.x * HL_THREADS + threadIdx.x;
+    int i = row0 + il;
+    int hv = (il < n_loc) && (row_ptr[i + 1] - row_ptr[i] > HEAVY_DEG);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned m = __ballot_sync(FULL, hv);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    if (w == 0) {
+        int ws = wsum[lane], z = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL, z, o); if (lane >= o) z += y; }
+        wsum[lane] = z - ws;
+    }
+    __syncthreads();
+    if (hv) list[block_offsets[blockIdx.x] + wsum[w] + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 // =============================================================================================
@@ -1340,16 +1735,17 @@ extern "C" void nemk_transpose_bits(nemk_stream s, const uint32_t *x, int n, int
                                     int nwt, uint32_t *xt) {
     cudaMemsetAsync(xt, 0, (size_t)d * nwt * sizeof(uint32_t), S(s));
     if (n <= 0) return;
-    dim3 grid(cdiv(n, 32), cdiv(wpr, 32));
-    k_transpose_bits<<<grid, 1024, 0, S(s)>>>(x, n, wpr, d, nwt, xt);
+    dim3 grid(cdiv(n, TB_ROWS), cdiv(wpr, 32));
+    k_transpose_bits<<<grid, 256, 0, S(s)>>>(x, n, wpr, d, nwt, xt);
     note_launch();
 }
 
 extern "C" void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const float *prop,
                                   const float *center, const float *disp, nemk_coef *coef,
                                   uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
-                                  uint32_t *mask_f1, double *delta) {
+                                  uint32_t *mask_f1, double *delta, int force_mu_changed) {
     cudaMemsetAsync(&coef->uniform_ok, 1, sizeof(int32_t), S(s));
+    cudaMemsetAsync(&coef->mu_changed, force_mu_changed ? 1 : 0, sizeof(int32_t), S(s));
     k_theta_tables<<<k, TT_THREADS, 0, S(s)>>>(k, d, wpr, prop, center, disp, coef, mask_xor,
                                               mask_valid, mask_f0, mask_f1, delta);
     note_launch();
@@ -1358,7 +1754,7 @@ extern "C" void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const fl
 template <int KT>
 static void launch_density_uniform(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
                                    const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
-                                   double *logpf, int32_t *hamming) {
+                                   double *logpf, int32_t *hamming, int cached) {
     int wpr4 = wpr / 4;
     size_t smem = (size_t)2 * KT * wpr4 * sizeof(uint4);
     int lpr = 1;
@@ -1374,7 +1770,7 @@ static void launch_density_uniform(cudaStream_t st, int K, const uint32_t *x, in
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         k_density_uniform<KT, L><<<grid, 256, smem, st>>>(K, (const uint4 *)x, n, wpr4, coef,     \
                                                           (const uint4 *)mx, (const uint4 *)mv,   \
-                                                          logpf, hamming);                        \
+                                                          logpf, hamming, cached);                \
     } while (0)
     switch (lpr) {
     case 1: LAUNCH_DU(1); break;
@@ -1390,7 +1786,7 @@ static void launch_density_uniform(cudaStream_t st, int K, const uint32_t *x, in
 template <int KT, int T, int ROWS>
 static bool launch_density_tma_t(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
                                  const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
-                                 double *logpf, int32_t *hamming) {
+                                 double *logpf, int32_t *hamming, int cached) {
     int wpr4 = wpr / 4;
     int stride4 = wpr4 | 1;  // odd number of uint4 per shared row => conflict-free LDS.128
     size_t mask_b = (size_t)2 * KT * wpr4 * sizeof(uint4);
@@ -1428,18 +1824,18 @@ static bool launch_density_tma_t(cudaStream_t st, int K, const uint32_t *x, int 
     if (K == KT)
         k_density_tma<KT, ROWS, T, true><<<grid, ROWS * T, smem, st>>>(
             K, (const uint4 *)x, n, wpr4, stride4, n_tiles, n_stages, coef, (const uint4 *)mx,
-            (const uint4 *)mv, logpf, hamming);
+            (const uint4 *)mv, logpf, hamming, cached);
     else
         k_density_tma<KT, ROWS, T, false><<<grid, ROWS * T, smem, st>>>(
             K, (const uint4 *)x, n, wpr4, stride4, n_tiles, n_stages, coef, (const uint4 *)mx,
-            (const uint4 *)mv, logpf, hamming);
+            (const uint4 *)mv, logpf, hamming, cached);
     return true;
 }
 
 template <int KT>
 static bool launch_density_tma(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
                                const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
-                               double *logpf, int32_t *hamming) {
+                               double *logpf, int32_t *hamming, int cached) {
     int wpr4 = wpr / 4;
     static int force_t = -1;
     if (force_t < 0) { const char *e = getenv("NEM_B200_DENSITY_T"); force_t = e ? atoi(e) : 0; }
@@ -1448,7 +1844,7 @@ static bool launch_density_tma(cudaStream_t st, int K, const uint32_t *x, int n,
     if (force_r < 0) { const char *e = getenv("NEM_B200_DENSITY_ROWS"); force_r = e ? atoi(e) : 0; }
     int rows = force_r ? force_r : 128;
     if (KT > 4) t = t > 2 ? 2 : t;   // keep the static partial buffer small for large K
-#define DT(TT, RR) launch_density_tma_t<KT, TT, RR>(st, K, x, n, wpr, coef, mx, mv, logpf, hamming)
+#define DT(TT, RR) launch_density_tma_t<KT, TT, RR>(st, K, x, n, wpr, coef, mx, mv, logpf, hamming, cached)
     if constexpr (KT <= 4) {
         if (t >= 8) return rows <= 32 ? DT(8, 32) : rows <= 64 ? DT(8, 64) : DT(8, 128);
         if (t >= 4) return rows <= 32 ? DT(4, 32) : rows <= 64 ? DT(4, 64) : DT(4, 128);
@@ -1461,7 +1857,7 @@ static bool launch_density_tma(cudaStream_t st, int K, const uint32_t *x, int n,
 template <int KT>
 static bool launch_density_direct(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
                                   const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
-                                  double *logpf, int32_t *hamming) {
+                                  double *logpf, int32_t *hamming, int cached) {
     int wpr4 = wpr / 4;
     size_t smem = (size_t)2 * KT * wpr4 * sizeof(uint4);
     if (smem > 96 * 1024) return false;
@@ -1473,36 +1869,56 @@ static bool launch_density_direct(cudaStream_t st, int K, const uint32_t *x, int
     if (grid > need) grid = need;
 #define DD(EX) do { \
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_density_direct<KT, EX, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        k_density_direct<KT, EX, 4><<<grid, thr, smem, st>>>(K, (const uint4 *)x, n, wpr4, coef, (const uint4 *)mx, (const uint4 *)mv, logpf, hamming); } while (0)
+        k_density_direct<KT, EX, 4><<<grid, thr, smem, st>>>(K, (const uint4 *)x, n, wpr4, coef, (const uint4 *)mx, (const uint4 *)mv, logpf, hamming, cached); } while (0)
     if (K == KT) DD(true); else DD(false);
 #undef DD
     return true;
 }
 
 static int g_density_impl = -1;  // 0 = v1, 1 = v2 (TMA tiles), 2 = v3 (direct); env NEM_B200_DENSITY
+// logpf from the cached Hamming counts (the epilogue of the density kernels, same bits); runs
+// when the class bit masks did not move since the counts were taken
+template <int KT>
+__global__ void __launch_bounds__(256)
+k_logpf_from_h(int K, int n, const nemk_coef *__restrict__ coef, const int32_t *__restrict__ hamming,
+               double *__restrict__ logpf) {
+    if (coef->empty_class || coef->mu_changed) return;
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (size_t)n * K) return;
+    int k = (int)(q % K);
+    int h = hamming[q];
+    double lp = coef->lp[k], val;
+    if (coef->forb[k]) val = h ? neg_inf() : lp;
+    else val = lp - (coef->a[k] * (double)h + coef->base[k]);
+    logpf[q] = val;
+}
+
 extern "C" void nemk_density_uniform(nemk_stream s, int k, const uint32_t *x, int n, int wpr,
                                      const nemk_coef *coef, const uint32_t *mask_xor,
-                                     const uint32_t *mask_valid, double *logpf, int32_t *hamming) {
+                                     const uint32_t *mask_valid, double *logpf, int32_t *hamming,
+                                     int cached) {
     if (n <= 0) return;
+    if (!hamming) cached = 0;
     if (g_density_impl < 0) {
         const char *e = getenv("NEM_B200_DENSITY");
         g_density_impl = (e && !strcmp(e, "v1")) ? 0 : (e && !strcmp(e, "v3")) ? 2 : 1;
     }
-    if (g_density_impl == 2) {
-        bool done = false;
+    bool done = false;
+    if (g_density_impl == 2)
         DISPATCH_K(k, (done = launch_density_direct<KT>(S(s), k, x, n, wpr, coef, mask_xor,
-                                                        mask_valid, logpf, hamming)));
-        if (done) { note_launch(); return; }
-    }
-    if (g_density_impl == 1) {
-        bool done = false;
+                                                        mask_valid, logpf, hamming, cached)));
+    if (!done && g_density_impl >= 1)
         DISPATCH_K(k, (done = launch_density_tma<KT>(S(s), k, x, n, wpr, coef, mask_xor, mask_valid,
-                                                     logpf, hamming)));
-        if (done) { note_launch(); return; }
-    }
-    DISPATCH_K(k, (launch_density_uniform<KT>(S(s), k, x, n, wpr, coef, mask_xor, mask_valid,
-                                              logpf, hamming)));
+                                                     logpf, hamming, cached)));
+    if (!done)
+        DISPATCH_K(k, (launch_density_uniform<KT>(S(s), k, x, n, wpr, coef, mask_xor, mask_valid,
+                                                  logpf, hamming, cached)));
     note_launch();
+    if (cached) {
+        DISPATCH_K(k, (k_logpf_from_h<KT><<<cdiv((long long)n * k, 256), 256, 0, S(s)>>>(
+                          k, n, coef, hamming, logpf)));
+        note_launch();
+    }
 }
 
 extern "C" void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d, int wpr,
@@ -1525,11 +1941,24 @@ extern "C" void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc
                                        const int32_t *col, const float *wgt, double beta,
                                        const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
                                        int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
-                                       const int32_t *rcol, nemk_counters *cnt, const int32_t *skip) {
+                                       const int32_t *rcol, const int32_t *heavy, int n_heavy,
+                                       nemk_counters *cnt, const int32_t *skip) {
     if (n_loc <= 0) return;
-    DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<cdiv(n_loc, 256), 256, 0, S(s)>>>(
+    int hb = (row_ptr && beta != 0.0 && heavy) ? cdiv((long long)n_heavy * 32, 256) : 0;
+    DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<hb + cdiv(n_loc, 256), 256, 0, S(s)>>>(
                       k, row0, n_loc, logpf, row_ptr, col, wgt, beta, lab_in, lab_out, dirty, wl,
-                      wl_count, rrow_ptr, rcol, cnt, skip)));
+                      wl_count, rrow_ptr, rcol, heavy, n_heavy, hb, cnt, skip)));
+    note_launch();
+}
+
+extern "C" void nemk_heavy_list(nemk_stream s, int row0, int n_loc, const int32_t *row_ptr,
+                                int32_t *block_counts, int32_t *list, int32_t *total) {
+    cudaMemsetAsync(total, 0, sizeof(int32_t), S(s));
+    if (n_loc <= 0) return;
+    int nb = cdiv(n_loc, HL_THREADS);
+    k_heavy_count<<<nb, HL_THREADS, 0, S(s)>>>(row0, n_loc, row_ptr, block_counts);
+    k_heavy_scan<<<1, HL_THREADS, 0, S(s)>>>(nb, block_counts, total);
+    k_heavy_fill<<<nb, HL_THREADS, 0, S(s)>>>(row0, n_loc, row_ptr, block_counts, list);
     note_launch();
 }
 
@@ -1631,12 +2060,12 @@ extern "C" void nemk_sweep_nem_level(nemk_stream s, int k, const double *logpf,
 }
 
 extern "C" void nemk_label_masks(nemk_stream s, int k, int n, int nwt, const uint8_t *lab,
-                                 uint32_t *cm, int32_t *nk_int) {
+                                 uint32_t *cm, int32_t *nk_int, uint8_t *lab_m) {
     cudaMemsetAsync(nk_int, 0, (size_t)k * sizeof(int32_t), S(s));
     if (n <= 0) return;
     int grid = cdiv((long long)nwt * 32, 256);
     if (grid > num_sms() * 8) grid = num_sms() * 8;
-    DISPATCH_K(k, (k_label_masks<KT><<<grid, 256, 0, S(s)>>>(k, n, nwt, lab, cm, nk_int)));
+    DISPATCH_K(k, (k_label_masks<KT><<<grid, 256, 0, S(s)>>>(k, n, nwt, lab, cm, nk_int, lab_m)));
     note_launch();
 }
 
@@ -1667,6 +2096,21 @@ extern "C" void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint
     note_launch();
 }
 
+extern "C" void nemk_mstep_delta(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x,
+                                 const uint8_t *lab, uint8_t *lab_m, int32_t *list, int32_t *count,
+                                 int32_t *s_int, int32_t *nk_int) {
+    if (n <= 0) return;
+    cudaMemsetAsync(count, 0, sizeof(int32_t), S(s));
+    k_changed_rows<<<cdiv(n, 256), 256, 0, S(s)>>>(n, lab, lab_m, list, count);
+    note_launch();
+    int grid = num_sms() * 4;
+    DISPATCH_K(k, (k_mstep_delta<KT><<<grid, 256, 0, S(s)>>>(k, d, wpr, x, lab, lab_m, list, count,
+                                                            s_int, nk_int)));
+    note_launch();
+    k_commit_labels<<<num_sms(), 256, 0, S(s)>>>(lab, lab_m, list, count);
+    note_launch();
+}
+
 extern "C" void nemk_mstep_nem(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x,
                                const float *t, int rows_per_chunk, double *partial_s,
                                double *partial_n, double *s_dbl, double *nk_dbl) {
@@ -1680,25 +2124,35 @@ extern "C" void nemk_mstep_nem(nemk_stream s, int k, int n, int d, int wpr, cons
     note_launch();
 }
 
-extern "C" void nemk_mstep_finalize(nemk_stream s, int k, int n, int d, int prop_model,
-                                    int disp_model, const int32_t *s_int, const int32_t *nk_int,
-                                    const double *s_dbl, const double *nk_dbl, float *prop,
-                                    float *center, float *disp, float *iner_scratch,
-                                    nemk_coef *coef) {
-    k_mstep_finalize<<<1, FIN_THREADS, 0, S(s)>>>(k, n, d, prop_model, disp_model, s_int, nk_int,
-                                                 s_dbl, nk_dbl, prop, center, disp, iner_scratch,
-                                                 coef);
+extern "C" void nemk_mstep_finalize_tables(nemk_stream s, int k, int n, int d, int wpr,
+                                           int prop_model, int disp_model, const int32_t *s_int,
+                                           const int32_t *nk_int, const double *s_dbl,
+                                           const double *nk_dbl, float *prop, float *center,
+                                           float *disp, nemk_coef *coef, uint32_t *mask_xor,
+                                           uint32_t *mask_valid, uint32_t *mask_f0,
+                                           uint32_t *mask_f1, double *delta, int force_mu_changed) {
+    cudaMemsetAsync(&coef->uniform_ok, 1, sizeof(int32_t), S(s));
+    cudaMemsetAsync(&coef->mu_changed, force_mu_changed ? 1 : 0, sizeof(int32_t), S(s));
+    k_mstep_finalize_tables<<<k, TT_THREADS, 0, S(s)>>>(k, n, d, wpr, prop_model, disp_model, s_int,
+                                                       nk_int, s_dbl, nk_dbl, prop, center, disp,
+                                                       coef, mask_xor, mask_valid, mask_f0, mask_f1,
+                                                       delta);
     note_launch();
 }
 
 extern "C" int nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
                                      const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                      double beta, const uint8_t *lab, const float *t,
-                                     double *partials, int nblocks) {
+                                     const int32_t *heavy, int n_heavy, double *partials,
+                                     int nblocks) {
     // always exactly `nblocks` partial rows (idle blocks write zeros) so that the ranks of a
-    // sharded fit can gather equal-sized buffers
+    // sharded fit can gather equal-sized buffers; the first `hb` blocks take the hubs
+    int hb = (row_ptr && lab && heavy && n_heavy > 0) ? cdiv((long long)n_heavy * 32, 256) : 0;
+    if (hb > nblocks / 2) hb = nblocks / 2;
+    if (nblocks < 2) hb = 0;
     DISPATCH_K(k, (k_criteria_partial<KT><<<nblocks, 256, 0, S(s)>>>(k, row0, n_loc, logpf, row_ptr,
-                                                                    col, wgt, beta, lab, t, partials)));
+                                                                    col, wgt, beta, lab, t, heavy,
+                                                                    n_heavy, hb, partials)));
     note_launch();
     return nblocks;
 }
