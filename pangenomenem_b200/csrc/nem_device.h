@@ -22,6 +22,8 @@ typedef struct {
     double a[NEMB_MAX_K];
     double base[NEMB_MAX_K];
     int32_t forb[NEMB_MAX_K];   /* eps_k <= EPSILON: any mismatch => zero density */
+    int32_t kind[NEMB_MAX_K];   /* popcount path: 0 general, 1 centre 0 everywhere (H = popc x),
+                                   2 centre 1 everywhere (H = D - popc x), 3 all centres 1/2 (H = 0) */
     int32_t uniform_ok;         /* 1 when every class is popcount-eligible */
     int32_t empty_class;        /* 1-based index of an empty class (M-step) or 0 */
     int32_t mu_changed;         /* the class bit masks differ from the previous tables (or forced):
@@ -56,9 +58,12 @@ void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const float *prop,
 /* ---- E-step density */
 /* cached != 0: `hamming` is the engine's persistent H cache; the X pass only runs when
  * coef->mu_changed, otherwise logpf is rebuilt from the cached counts (same formula, same bits) */
-void nemk_density_uniform(nemk_stream s, int k, const uint32_t *x, int n, int wpr,
+void nemk_density_uniform(nemk_stream s, int k, int d, const uint32_t *x, int n, int wpr,
                           const nemk_coef *coef, const uint32_t *mask_xor,
                           const uint32_t *mask_valid, double *logpf, int32_t *hamming, int cached);
+/* runs only when !coef->mu_changed: logpf from the cached Hamming counts */
+void nemk_logpf_from_cache(nemk_stream s, int k, int n, const nemk_coef *coef,
+                           const int32_t *hamming, double *logpf);
 void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d, int wpr,
                           const nemk_coef *coef, const uint32_t *mask_f0, const uint32_t *mask_f1,
                           const double *delta, double *logpf);

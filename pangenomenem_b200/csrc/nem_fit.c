@@ -75,7 +75,7 @@ struct nemb_handle {
     uint8_t *d_lab[4];     /* two sweep buffers, the labels last seen from remote ranks, and the
                               labels the M-step statistics currently describe (local rows) */
     int32_t *d_ham;        /* cached Hamming counts H[n][K] of the popcount density path */
-    int ham_valid, stats_valid;
+    int ham_valid, stats_valid, tables_forced;
     int64_t last_changed;  /* labels moved by the last sweep (all ranks), -1 = unknown */
     float *d_t[2];
     int cur, state_labels;
@@ -96,7 +96,7 @@ struct nemb_handle {
     int profile;
     cudaEvent_t *ev;
     int *ev_kind;
-    int ev_cap, ev_n, ev_last_density;
+    int ev_cap, ev_n, ev_last_density, ev_last_cached;
 };
 
 /* ------------------------------------------------------------------ errors */
@@ -638,6 +638,7 @@ static void stage_mark(nemb_handle *h, int kind_or_end)
     }
     h->ev_kind[h->ev_n] = kind_or_end;
     if (kind_or_end == ST_DENSITY) h->ev_last_density = h->ev_n;
+    if (kind_or_end == ST_DENSITY_CACHED) h->ev_last_cached = h->ev_n;
     cudaEventRecord(h->ev[h->ev_n++], h->stream);
 }
 #define STAGE_BEGIN(kind) stage_mark(h, (kind))
@@ -663,6 +664,7 @@ static int theta_uniform(int k, int d, const float *center, const float *disp)
 static int run_tables(nemb_handle *h, int k, int next_uniform)
 {
     int force = !(h->ham_valid && next_uniform);
+    h->tables_forced = force;
     nemk_theta_tables(h->stream, k, h->d, h->wpr, h->d_prop, h->d_center, h->d_disp, h->d_coef,
                       h->d_mxor, h->d_mval, h->d_f0, h->d_f1, h->d_delta, force);
     h->launches++;
@@ -675,10 +677,19 @@ static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming)
     STAGE_BEGIN(ST_DENSITY);
     if (uniform) {
         /* d_hamming == NULL: the fit's own pass, through the persistent H cache */
-        nemk_density_uniform(h->stream, k, h->d_x, h->n, h->wpr, h->d_coef, h->d_mxor, h->d_mval,
+        nemk_density_uniform(h->stream, k, h->d, h->d_x, h->n, h->wpr, h->d_coef, h->d_mxor, h->d_mval,
                              h->d_logpf, d_hamming ? d_hamming : h->d_ham, d_hamming == NULL);
         h->ham_valid = d_hamming == NULL;
-        h->launches += h->ham_valid;
+        if (h->ham_valid) {   /* exactly one of the two kernels does work (coef->mu_changed) */
+            STAGE_END();
+            STAGE_BEGIN(ST_DENSITY_CACHED);
+            nemk_logpf_from_cache(h->stream, k, h->n, h->d_coef, h->d_ham, h->d_logpf);
+            h->launches++;
+            if (h->profile && h->tables_forced) {   /* the X pass certainly ran */
+                h->ev_kind[h->ev_last_cached] = -2;
+                h->ev_last_density = h->ev_last_cached = -1;
+            }
+        }
     } else {
         nemk_density_general(h->stream, k, h->d_x, h->n, h->d, h->wpr, h->d_coef, h->d_f0, h->d_f1,
                              h->d_delta, h->d_logpf);
@@ -701,9 +712,10 @@ static int read_status(nemb_handle *h)
     CK(cudaStreamSynchronize(h->stream));
     /* h_empty[1] = coef->mu_changed of the last tables: 0 => the last popcount density pass did
      * not read X (cached Hamming counts) */
-    if (h->profile && h->ev_last_density >= 0 && h->ham_valid && !h->h_empty[1]) {
-        h->ev_kind[h->ev_last_density] = ST_DENSITY_CACHED;
-        h->ev_last_density = -1;
+    if (h->profile && h->ham_valid && h->ev_last_density >= 0 && h->ev_last_cached >= 0) {
+        /* discard the stage whose kernel returned at once */
+        h->ev_kind[h->h_empty[1] ? h->ev_last_cached : h->ev_last_density] = -2;
+        h->ev_last_density = h->ev_last_cached = -1;
     }
     nemk_counters tot;
     memset(&tot, 0, sizeof tot);
@@ -856,6 +868,7 @@ static int run_mstep(nemb_handle *h, const nemb_options *o, int next_uniform)
                                    stat_glob + kd, NULL, NULL, h->d_prop, h->d_center, h->d_disp,
                                    h->d_coef, h->d_mxor, h->d_mval, h->d_f0, h->d_f1, h->d_delta,
                                    !(h->ham_valid && next_uniform));
+        h->tables_forced = !(h->ham_valid && next_uniform);
         h->launches++;
     } else {
         if ((rc = ensure_nem_scratch(h, k)) != NEMB_OK) return rc;
@@ -872,6 +885,7 @@ static int run_mstep(nemb_handle *h, const nemb_options *o, int next_uniform)
                                    h->d_stat_dbl, h->d_stat_dbl + kd, h->d_prop, h->d_center,
                                    h->d_disp, h->d_coef, h->d_mxor, h->d_mval, h->d_f0, h->d_f1,
                                    h->d_delta, !(h->ham_valid && next_uniform));
+        h->tables_forced = !(h->ham_valid && next_uniform);
         h->launches++;
     }
     STAGE_END();
@@ -1063,7 +1077,7 @@ int nemb_fit_logged(nemb_handle *h, const nemb_options *o, float *prop, float *c
     if ((rc = ensure_k(h, o->k)) != NEMB_OK) return rc;
     memset(res, 0, sizeof *res);
     h->launches = 0; h->fixup_rounds = 0; h->exchanges = 0; h->profile = o->profile; h->ev_n = 0;
-    h->ev_last_density = -1;
+    h->ev_last_density = h->ev_last_cached = -1;
     size_t kd = (size_t)o->k * h->d;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));

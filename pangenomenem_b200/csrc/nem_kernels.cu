@@ -14,6 +14,7 @@
 #include "nem_device.h"
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math_constants.h>
 #include <float.h>
 #include <math.h>
@@ -149,36 +150,42 @@ k_transpose_bits(const uint32_t *__restrict__ x, int n, int wpr, int d, int nwt,
 // one CTA per class, variables in parallel.
 // =============================================================================================
 #define TT_THREADS 1024
-// tables of class k, by one CTA.  The two log() of a variable are only evaluated when its
-// dispersion differs from the class's first one (never, for the per-class-constant models).
-static __device__ void tables_class(int k, int K, int D, int wpr, const float *prop,
-                                    const float *center, const float *disp, nemk_coef *coef,
-                                    uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
-                                    uint32_t *mask_f1, double *delta, double *sh /*[32]*/,
-                                    int *sh_ok) {
-    int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) *sh_ok = 1;
-    __syncthreads();
-    const float e0 = disp[(size_t)k * D];
-    const bool live0 = (double)e0 > NEM_EPSILON;
-    double a0 = 0.0, c0 = 0.0;
-    if (live0) {
+// Per-thread part of the tables of class k over the genomes [32*w_lo, 32*w_hi): writes the bit
+// masks and delta, returns the thread's partial sums.  The two log() of a variable are only
+// evaluated when its dispersion differs from the class's first one (never, for the
+// per-class-constant dispersion models).
+struct TablesPartial { double base_u, base_g; int notok, mu_moved, n_valid, n_x1; };
+struct ClassCoef { float e0; bool live0; double a0, c0; };
+
+static __device__ __forceinline__ ClassCoef class_coef(float e0) {
+    ClassCoef cc;
+    cc.e0 = e0;
+    cc.live0 = (double)e0 > NEM_EPSILON;
+    cc.a0 = 0.0; cc.c0 = 0.0;
+    if (cc.live0) {
         float ratio = __fdiv_rn(__fsub_rn(1.0f, e0), e0);
         float om = __fsub_rn(1.0f, e0);
-        a0 = log((double)ratio);
-        c0 = -log((double)om);
+        cc.a0 = log((double)ratio);
+        cc.c0 = -log((double)om);
     }
-    double base_u = 0.0, base_g = 0.0;
-    int ok = 1, mu_moved = 0;
-    for (int j0 = 0; j0 < wpr * 32; j0 += TT_THREADS) {
-        int j = j0 + tid;  // wpr*32 is a multiple of 32, so whole warps stay together
-        bool in = j < D;
+    return cc;
+}
+
+static __device__ __forceinline__ TablesPartial tables_words(
+    int k, int D, int wpr, int w_lo, int w_hi, const ClassCoef &cc, const float *center,
+    const float *disp, uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
+    uint32_t *mask_f1, double *delta) {
+    TablesPartial p = {0.0, 0.0, 0, 0, 0, 0};
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int j0 = w_lo * 32; j0 < w_hi * 32; j0 += blockDim.x) {
+        int j = j0 + tid;  // whole warps stay together: the range starts and ends on a word
+        bool in = j < D && j < w_hi * 32;
         float mu = in ? center[(size_t)k * D + j] : 0.5f;
-        float e = in ? disp[(size_t)k * D + j] : e0;
+        float e = in ? disp[(size_t)k * D + j] : cc.e0;
         int m0 = abs((int)(0.0f - mu)), m1 = abs((int)(1.0f - mu));
-        bool same = __float_as_uint(e) == __float_as_uint(e0);
-        bool live = same ? live0 : ((double)e > NEM_EPSILON);
-        double a = same ? a0 : 0.0, c = same ? c0 : 0.0;
+        bool same = __float_as_uint(e) == __float_as_uint(cc.e0);
+        bool live = same ? cc.live0 : ((double)e > NEM_EPSILON);
+        double a = same ? cc.a0 : 0.0, c = same ? cc.c0 : 0.0;
         if (in && live && !same) {
             float ratio = __fdiv_rn(__fsub_rn(1.0f, e), e);
             float om = __fsub_rn(1.0f, e);
@@ -188,49 +195,63 @@ static __device__ void tables_class(int k, int K, int D, int wpr, const float *p
         double cost0 = in ? (m0 * a + c) : 0.0, cost1 = in ? (m1 * a + c) : 0.0;
         if (in) {
             delta[(size_t)k * D + j] = cost1 - cost0;
-            base_g += cost0;
-            base_u += c;
-            if (!same || m0 > 1 || m1 > 1) ok = 0;
+            p.base_g += cost0;
+            p.base_u += c;
+            if (!same || m0 > 1 || m1 > 1) p.notok = 1;
         }
         unsigned bx = __ballot_sync(FULL, in && m0 == 1 && m1 == 0);
         unsigned bv = __ballot_sync(FULL, in && m0 != m1);
         unsigned b0 = __ballot_sync(FULL, in && !live && m0 != 0);
         unsigned b1 = __ballot_sync(FULL, in && !live && m1 != 0);
-        if (lane == 0 && (j >> 5) < wpr) {
+        if (lane == 0 && (j >> 5) < w_hi) {
             size_t o = (size_t)k * wpr + (j >> 5);
-            if (mask_xor[o] != bx || mask_valid[o] != bv) mu_moved = 1;
+            p.n_valid += __popc(bv); p.n_x1 += __popc(bx);
+            if (mask_xor[o] != bx || mask_valid[o] != bv) p.mu_moved = 1;
             mask_xor[o] = bx; mask_valid[o] = bv; mask_f0[o] = b0; mask_f1[o] = b1;
         }
     }
-    if (!ok) *sh_ok = 0;  // benign race: every writer stores 0
-    if (mu_moved) atomicOr(&coef->mu_changed, 1);   // preset by the launcher (0, or 1 = forced)
-    base_u = block_sum<TT_THREADS>(base_u, sh);
-    base_g = block_sum<TT_THREADS>(base_g, sh);
-    __syncthreads();
-    if (tid == 0) {
-        double pk = prop[k];
-        coef->lp[k] = (pk > NEM_EPSILON) ? log(pk) : neg_inf();  // nem_alg.c:2265-2271
-        if (*sh_ok) {
-            coef->a[k] = live0 ? a0 : 0.0;
-            coef->base[k] = live0 ? base_u : 0.0;
-            coef->forb[k] = live0 ? 0 : 1;
-        } else {
-            coef->a[k] = 0.0; coef->base[k] = base_g; coef->forb[k] = 0;
-        }
-        delta[(size_t)K * D + k] = base_g;  // general-path base: sum_d cost0_kd
-        if (!*sh_ok) atomicAnd(&coef->uniform_ok, 0);   // preset to non-zero by the launcher
-    }
+    return p;
 }
 
+static __device__ __forceinline__ void tables_commit(int k, int K, int D, const float *prop,
+                                                     nemk_coef *coef, double *delta,
+                                                     const ClassCoef &cc, double base_u,
+                                                     double base_g, bool ok, int n_valid, int n_x1) {
+    // popcount-path class kind: 3 = no genome counts (all centres 1/2), 1 = centre 0 everywhere
+    // (H = popc(x)), 2 = centre 1 everywhere (H = D - popc(x)), 0 = general
+    coef->kind[k] = n_valid == 0 ? 3 : (n_valid == D && n_x1 == 0) ? 1 : (n_valid == D && n_x1 == D) ? 2 : 0;
+    double pk = prop[k];
+    coef->lp[k] = (pk > NEM_EPSILON) ? log(pk) : neg_inf();  // nem_alg.c:2265-2271
+    if (ok) {
+        coef->a[k] = cc.live0 ? cc.a0 : 0.0;
+        coef->base[k] = cc.live0 ? base_u : 0.0;
+        coef->forb[k] = cc.live0 ? 0 : 1;
+    } else {
+        coef->a[k] = 0.0; coef->base[k] = base_g; coef->forb[k] = 0;
+    }
+    delta[(size_t)K * D + k] = base_g;  // general-path base: sum_d cost0_kd
+    if (!ok) atomicAnd(&coef->uniform_ok, 0);   // preset to non-zero by the launcher
+}
+
+// tables of the theta the caller supplied (start of a fit): one CTA per class
 __global__ void __launch_bounds__(TT_THREADS)
 k_theta_tables(int K, int D, int wpr, const float *__restrict__ prop,
                const float *__restrict__ center, const float *__restrict__ disp, nemk_coef *coef,
                uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0, uint32_t *mask_f1,
                double *delta) {
     __shared__ double sh[32];
-    __shared__ int sh_ok;
-    tables_class(blockIdx.x, K, D, wpr, prop, center, disp, coef, mask_xor, mask_valid, mask_f0,
-                 mask_f1, delta, sh, &sh_ok);
+    const int k = blockIdx.x;
+    ClassCoef cc = class_coef(disp[(size_t)k * D]);
+    TablesPartial p = tables_words(k, D, wpr, 0, wpr, cc, center, disp, mask_xor, mask_valid,
+                                   mask_f0, mask_f1, delta);
+    if (p.mu_moved) atomicOr(&coef->mu_changed, 1);   // preset by the launcher (0, or 1 = forced)
+    double base_u = block_sum<TT_THREADS>(p.base_u, sh);
+    double base_g = block_sum<TT_THREADS>(p.base_g, sh);
+    double notok = block_sum<TT_THREADS>((double)p.notok, sh);
+    double nv = block_sum<TT_THREADS>((double)p.n_valid, sh);
+    double nx = block_sum<TT_THREADS>((double)p.n_x1, sh);
+    if (threadIdx.x == 0)
+        tables_commit(k, K, D, prop, coef, delta, cc, base_u, base_g, notok == 0.0, (int)nv, (int)nx);
 }
 
 // =============================================================================================
@@ -349,10 +370,17 @@ static __device__ __forceinline__ uint32_t lop_maj3(uint32_t a, uint32_t b, uint
 // [t*wpr4/T, (t+1)*wpr4/T) of family r, so that t (hence the mask address) is warp-uniform and
 // lane r reads chunk c of row r (odd stride => conflict-free).  Partial counts meet in shared
 // memory through integer atomics; ONE block barrier per tile; the epilogue of tile i (log-density
-// + store) runs after that barrier, overlapped with the other warps starting tile i+1.
-template <int KT, int ROWS, int T, bool EXACT>
+// + store, one OUTPUT per thread: contiguous 8-byte stores) runs after that barrier, overlapped
+// with the next tile's counting.
+//
+// Class kinds (coef->kind, set with the tables): a class whose centre is 0 for every genome has
+// H = P = popc(x), one whose centre is 1 everywhere has H = D - P, one whose centres are all 1/2
+// has H = 0; only "general" classes (kind 0) pay the per-word mask work.  P is one mask-free
+// carry-save stream shared by all constant classes.  In a pangenome the persistent class is all
+// ones and the cloud class all zeros, so typically ONE class of three is general.
+template <int KT, int ROWS, int T>
 __global__ void __launch_bounds__(ROWS *T)
-k_density_tma(int K, const uint4 *__restrict__ x, int n, int wpr4, int stride4, int n_tiles,
+k_density_tma(int K, int D, const uint4 *__restrict__ x, int n, int wpr4, int stride4, int n_tiles,
               int n_stages, const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
               const uint4 *__restrict__ mval, double *__restrict__ logpf,
               int32_t *__restrict__ hamming, int cached) {
@@ -360,22 +388,35 @@ k_density_tma(int K, const uint4 *__restrict__ x, int n, int wpr4, int stride4, 
     if (cached && !coef->mu_changed) return;   // H cache still valid: k_logpf_from_h does the work
     extern __shared__ __align__(128) uint4 dsm[];
     __shared__ __align__(8) uint64_t bars[16];
-    __shared__ int hsum[2][ROWS * KT];
-    uint4 *smask = dsm;                                // [wpr4][KT][2] (xor, valid)
-    uint4 *tiles = dsm + (size_t)2 * KT * wpr4;        // n_stages x ROWS x stride4 ring
+    __shared__ int hsum[3][ROWS * (KT + 1)];   // per row: KG general counts then P; 3 rotating slots
+    __shared__ int s_gidx[KT], s_kind[KT], s_slot[KT];
+    __shared__ int s_kg, s_needp;
     const int tid = threadIdx.x;
     const int r = tid % ROWS, t = tid / ROWS;
-    const int kk = EXACT ? KT : K;
-    for (int i = tid; i < KT * wpr4; i += ROWS * T) {
-        int c = i / KT, k = i % KT;
-        bool live = k < K;
-        smask[2 * i] = live ? mxor[k * wpr4 + c] : make_uint4(0, 0, 0, 0);
-        smask[2 * i + 1] = live ? mval[k * wpr4 + c] : make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        int kg = 0, needp = 0;
+        for (int k = 0; k < K; k++) {
+            int kind = coef->kind[k];
+            s_kind[k] = kind; s_slot[k] = -1;
+            if (kind == 0) { s_gidx[kg] = k; s_slot[k] = kg; kg++; }
+            else if (kind != 3) needp = 1;
+        }
+        s_kg = kg; s_needp = needp;
     }
-    for (int i = tid; i < 2 * ROWS * KT; i += ROWS * T) (&hsum[0][0])[i] = 0;
+    for (int i = tid; i < 3 * ROWS * (KT + 1); i += ROWS * T) (&hsum[0][0])[i] = 0;
     if (tid == 0) {
         for (int q = 0; q < n_stages; q++) mbar_init(&bars[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int KG = s_kg;
+    const bool needp = s_needp != 0;
+    uint4 *smask = dsm;                                // [wpr4][KG][2] (xor, valid), general classes
+    uint4 *tiles = dsm + (size_t)2 * KT * wpr4;        // n_stages x ROWS x stride4 ring
+    for (int i = tid; i < KG * wpr4; i += ROWS * T) {
+        int c = i / KG, g = i % KG, k = s_gidx[g];
+        smask[2 * i] = mxor[k * wpr4 + c];
+        smask[2 * i + 1] = mval[k * wpr4 + c];
     }
     __syncthreads();
     const uint32_t row_bytes = (uint32_t)wpr4 * 16u;
@@ -388,19 +429,19 @@ k_density_tma(int K, const uint4 *__restrict__ x, int n, int wpr4, int stride4, 
             bulk_g2s(tiles + ((size_t)stage * ROWS + tid) * stride4, x + (size_t)(r0 + tid) * wpr4,
                      row_bytes, &bars[stage]);
     };
-    auto epilogue = [&](int tile, int slot) {   // threads of column group 0 only
-        long long row = (long long)tile * ROWS + r;
-#pragma unroll
-        for (int k = 0; k < KT; k++) {
-            int h = hsum[slot][r * KT + k];
-            hsum[slot][r * KT + k] = 0;
-            if (k < kk && row < n) {
-                double lp = coef->lp[k], val;
-                if (coef->forb[k]) val = h ? neg_inf() : lp;
-                else val = lp - (coef->a[k] * (double)h + coef->base[k]);
-                logpf[(size_t)row * K + k] = val;
-                if (hamming) hamming[(size_t)row * K + k] = h;
-            }
+    auto epilogue = [&](int tile, int slot) {   // one output (row, class) per thread
+        for (int o = tid; o < ROWS * K; o += ROWS * T) {
+            int rr = o / K, k = o - rr * K;
+            long long row = (long long)tile * ROWS + rr;
+            if (row >= n) break;
+            const int *hs = &hsum[slot][rr * (KT + 1)];
+            int kind = s_kind[k], P = hs[KT];
+            int h = kind == 0 ? hs[s_slot[k]] : kind == 1 ? P : kind == 2 ? D - P : 0;
+            double lp = coef->lp[k], val;
+            if (coef->forb[k]) val = h ? neg_inf() : lp;
+            else val = lp - (coef->a[k] * (double)h + coef->base[k]);
+            logpf[(size_t)row * K + k] = val;
+            if (hamming) hamming[(size_t)row * K + k] = h;
         }
     };
     // ring of n_stages tiles: n_stages-1 bulk loads stay in flight behind the tile being counted
@@ -413,10 +454,14 @@ k_density_tma(int K, const uint4 *__restrict__ x, int n, int wpr4, int stride4, 
         int stage = it % n_stages;
         long long next = (long long)tile + (long long)(n_stages - 1) * gridDim.x;
         if (next < n_tiles) issue((int)next, (it + n_stages - 1) % n_stages);
-        if (t == 0 && prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1);
+        // slots rotate over 3: tile `it` accumulates into it%3, the epilogue of tile it-1 reads
+        // (it-1)%3, and (it+1)%3 -- last read one barrier ago -- is cleared for the next tile
+        if (T > 1)
+            for (int i = tid; i < ROWS * (KT + 1); i += ROWS * T) hsum[(it + 1) % 3][i] = 0;
+        if (prev_tile >= 0) epilogue(prev_tile, (it + 2) % 3);
         mbar_wait(&bars[stage], (uint32_t)((it / n_stages) & 1));
         long long row = (long long)tile * ROWS + r;
-        uint32_t ones[KT], cnt2[KT];
+        uint32_t ones[KT], cnt2[KT], onesP = 0u, cntP = 0u;
 #pragma unroll
         for (int k = 0; k < KT; k++) { ones[k] = 0u; cnt2[k] = 0u; }
         if (row < n) {
@@ -424,105 +469,47 @@ k_density_tma(int K, const uint4 *__restrict__ x, int n, int wpr4, int stride4, 
 #pragma unroll 2
             for (int c = c_lo; c < c_hi; c++) {
                 uint4 v = xr[c];
-                const uint4 *mk = smask + (size_t)2 * KT * c;
+                if (needp) {
+                    uint32_t c0 = lop_maj3(onesP, v.x, v.y);
+                    uint32_t o1 = lop_xor3(onesP, v.x, v.y);
+                    uint32_t c1 = lop_maj3(o1, v.z, v.w);
+                    onesP = lop_xor3(o1, v.z, v.w);
+                    cntP += __popc(c0) + __popc(c1);
+                }
+                const uint4 *mk = smask + (size_t)2 * KG * c;
 #pragma unroll
-                for (int k = 0; k < KT; k++) {
-                    if (EXACT || k < kk) {
-                        uint4 a = mk[2 * k], b = mk[2 * k + 1];
+                for (int g = 0; g < KT; g++) {
+                    if (g < KG) {
+                        uint4 a = mk[2 * g], b = mk[2 * g + 1];
                         uint32_t m0 = (v.x ^ a.x) & b.x, m1 = (v.y ^ a.y) & b.y;
                         uint32_t m2 = (v.z ^ a.z) & b.z, m3 = (v.w ^ a.w) & b.w;
-                        uint32_t c0 = lop_maj3(ones[k], m0, m1);
-                        uint32_t o1 = lop_xor3(ones[k], m0, m1);
+                        uint32_t c0 = lop_maj3(ones[g], m0, m1);
+                        uint32_t o1 = lop_xor3(ones[g], m0, m1);
                         uint32_t c1 = lop_maj3(o1, m2, m3);
-                        ones[k] = lop_xor3(o1, m2, m3);
-                        cnt2[k] += __popc(c0) + __popc(c1);
+                        ones[g] = lop_xor3(o1, m2, m3);
+                        cnt2[g] += __popc(c0) + __popc(c1);
                     }
                 }
             }
         }
+        int *hs = &hsum[it % 3][r * (KT + 1)];
 #pragma unroll
-        for (int k = 0; k < KT; k++) {
-            int h = (int)(2u * cnt2[k]) + __popc(ones[k]);
-            if (T > 1) { if (h) atomicAdd(&hsum[it & 1][r * KT + k], h); }
-            else hsum[it & 1][r * KT + k] = h;
+        for (int g = 0; g < KT; g++) {
+            if (g < KG) {
+                int h = (int)(2u * cnt2[g]) + __popc(ones[g]);
+                if (T > 1) { if (h) atomicAdd(&hs[g], h); }
+                else hs[g] = h;
+            }
+        }
+        if (needp) {
+            int h = (int)(2u * cntP) + __popc(onesP);
+            if (T > 1) { if (h) atomicAdd(&hs[KT], h); }
+            else hs[KT] = h;
         }
         prev_tile = tile;
-        __syncthreads();  // the stage is free again and hsum[it&1] is complete
+        __syncthreads();  // the stage is free again and hsum[it%3] is complete
     }
-    if (t == 0 && prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1);
-}
-
-// =============================================================================================
-// E-step density, popcount path, v3 "direct": one lane per family, no staging, no barriers.
-// Lane r walks its own row 16 bytes at a time with PF loads in flight; two consecutive chunks
-// share a 32-byte sector, so every sector is fetched from L2 once and hit in L1 once (X is read
-// from HBM exactly once).  Every lane of a warp is at the same chunk => warp-uniform class masks
-// (broadcast LDS.128) and carry-save popcounts as in v2.  Warps are fully independent: latency is
-// hidden by (warps x PF) outstanding 16-byte loads, not by a tile pipeline.
-// =============================================================================================
-template <int KT, bool EXACT, int PF>
-__global__ void __launch_bounds__(256)
-k_density_direct(int K, const uint4 *__restrict__ x, int n, int wpr4,
-                 const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
-                 const uint4 *__restrict__ mval, double *__restrict__ logpf,
-                 int32_t *__restrict__ hamming, int cached) {
-    if (coef->empty_class) return;
-    if (cached && !coef->mu_changed) return;
-    extern __shared__ __align__(16) uint4 dsm2[];
-    uint4 *smask = dsm2;  // [wpr4][KT][2] (xor, valid): the 2*KT masks of a chunk are contiguous
-    for (int i = threadIdx.x; i < KT * wpr4; i += blockDim.x) {
-        int c = i / KT, k = i % KT;
-        bool live = k < K;
-        smask[2 * i] = live ? mxor[k * wpr4 + c] : make_uint4(0, 0, 0, 0);
-        smask[2 * i + 1] = live ? mval[k * wpr4 + c] : make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    const int kk = EXACT ? KT : K;
-    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n;
-         row += (long long)gridDim.x * blockDim.x) {
-        const uint4 *xr = x + (size_t)row * wpr4;
-        uint32_t ones[KT], cnt2[KT];
-#pragma unroll
-        for (int k = 0; k < KT; k++) { ones[k] = 0u; cnt2[k] = 0u; }
-        uint4 buf[PF];
-#pragma unroll
-        for (int q = 0; q < PF; q++) buf[q] = (q < wpr4) ? __ldg(xr + q) : make_uint4(0, 0, 0, 0);
-        for (int c0 = 0; c0 < wpr4; c0 += PF) {
-#pragma unroll
-            for (int q = 0; q < PF; q++) {
-                int c = c0 + q;
-                uint4 v = buf[q];
-                if (c + PF < wpr4) buf[q] = __ldg(xr + c + PF);
-                if (c < wpr4) {
-                    const uint4 *mk = smask + (size_t)2 * KT * c;
-#pragma unroll
-                    for (int k = 0; k < KT; k++) {
-                        if (EXACT || k < kk) {
-                            uint4 a = mk[2 * k], b = mk[2 * k + 1];
-                            uint32_t m0 = (v.x ^ a.x) & b.x, m1 = (v.y ^ a.y) & b.y;
-                            uint32_t m2 = (v.z ^ a.z) & b.z, m3 = (v.w ^ a.w) & b.w;
-                            uint32_t c0_ = lop_maj3(ones[k], m0, m1);
-                            uint32_t o1 = lop_xor3(ones[k], m0, m1);
-                            uint32_t c1_ = lop_maj3(o1, m2, m3);
-                            ones[k] = lop_xor3(o1, m2, m3);
-                            cnt2[k] += __popc(c0_) + __popc(c1_);
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < KT; k++) {
-            if (k < kk) {
-                int h = (int)(2u * cnt2[k]) + __popc(ones[k]);
-                double lp = coef->lp[k], val;
-                if (coef->forb[k]) val = h ? neg_inf() : lp;
-                else val = lp - (coef->a[k] * (double)h + coef->base[k]);
-                logpf[(size_t)row * K + k] = val;
-                if (hamming) hamming[(size_t)row * K + k] = h;
-            }
-        }
-    }
+    if (prev_tile >= 0) epilogue(prev_tile, (it + 2) % 3);
 }
 
 // =============================================================================================
@@ -1373,10 +1360,16 @@ __global__ void k_mstep_nem_reduce(int K, int D, int nchunks, const double *__re
 // forced for Bernoulli, nem_mod.c:446-447);  proportions (nem_mod.c:455-465).
 // theta is float32 like the reference; divisions are float divisions.
 // =============================================================================================
-// One CTA per class; a class's CTA derives mu, eps, p of ITS class (the models that pool classes,
-// s_d and s__, recompute the other classes' inertia from S and n: a few thousand flops) and goes
-// straight on to the class's density tables (tables_class) -- M-step closed forms and the E-step
-// tables in one launch.
+// M-step closed forms + E-step tables of the new theta in ONE launch: a thread-block CLUSTER of
+// FT_CLUSTER CTAs per class, each CTA owning a slice of the genomes (whole 32-genome words).  The
+// sums over genomes (sk_/s__ inertia, the classes' base terms) are block-reduced, left in each
+// CTA's shared memory and combined through distributed shared memory in CTA-rank order (fixed
+// order => reproducible), with two cluster barriers instead of a second kernel launch.
+// The models that pool classes (s_d, s__) recompute the other classes' inertia from S and n.
+namespace cg = cooperative_groups;
+#define FT_CLUSTER 8
+#define FT_THREADS 512
+
 static __device__ __forceinline__ float iner_of(double s, double n, bool nonempty, float mu_keep) {
     // EstimLaplaceCenters / ComputeMedian then EstimLaplaceIner; an empty class keeps its centre
     // (nem_mod.c:1363) and has n = S = 0, hence zero inertia
@@ -1385,7 +1378,26 @@ static __device__ __forceinline__ float iner_of(double s, double n, bool nonempt
     return (float)(s * fabs(1.0 - (double)mu) + (n - s) * fabs((double)mu));
 }
 
-__global__ void __launch_bounds__(TT_THREADS)
+// sum of v[0..NV) over the cluster; every thread of every CTA gets the totals (rank order)
+template <int NV>
+static __device__ __forceinline__ void cluster_sum(cg::cluster_group &cluster, double (&v)[NV],
+                                                   double *sh /*[32]*/, double *slot /*[NV] smem*/) {
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        double r = block_sum<FT_THREADS>(v[q], sh);
+        if (threadIdx.x == 0) slot[q] = r;
+    }
+    cluster.sync();
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        double t = 0.0;
+        for (unsigned r = 0; r < cluster.num_blocks(); r++) t += cluster.map_shared_rank(slot, r)[q];
+        v[q] = t;
+    }
+    cluster.sync();   // slots may be rewritten
+}
+
+__global__ void __cluster_dims__(FT_CLUSTER, 1, 1) __launch_bounds__(FT_THREADS)
 k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_model,
                         const int32_t *__restrict__ s_int, const int32_t *__restrict__ nk_int,
                         const double *__restrict__ s_dbl, const double *__restrict__ nk_dbl,
@@ -1393,17 +1405,21 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
                         uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
                         uint32_t *mask_f1, double *delta) {
     __shared__ double sh[32];
+    __shared__ double slot[8];
     __shared__ float nkf[NEMB_MAX_K];
     __shared__ double nkd[NEMB_MAX_K];
-    __shared__ int sh_ok;
-    const int tid = threadIdx.x, k = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, k = blockIdx.x / FT_CLUSTER, part = blockIdx.x % FT_CLUSTER;
+    const int wreal = (D + 31) >> 5, wper = (wreal + FT_CLUSTER - 1) / FT_CLUSTER;
+    const int w_lo = min(wreal, part * wper), w_hi = min(wreal, w_lo + wper);
+    const int j_lo = w_lo * 32, j_hi = min(D, w_hi * 32);
     if (tid < K) {
         double v = s_int ? (double)nk_int[tid] : nk_dbl[tid];
         nkd[tid] = v;
         nkf[tid] = (float)v;
     }
     __syncthreads();
-    if (k == 0 && tid == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
         int empty = 0;
         for (int c = 0; c < K; c++)
             if (!((double)nkf[c] > NEM_EPSILON)) empty = c + 1;  // nem_mod.c:1363,1404-1409
@@ -1414,31 +1430,19 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
         return s_int ? (double)s_int[q] : s_dbl[q];
     };
     const bool nonempty = (double)nkf[k] > NEM_EPSILON;
-    // centres of this class
-    for (int j = tid; j < D; j += TT_THREADS) {
-        if (nonempty) {
+    // centres of this class (this CTA's genomes)
+    if (nonempty)
+        for (int j = j_lo + tid; j < j_hi; j += FT_THREADS) {
             double s = S_of(k, j), half = 0.5 * nkd[k];
             center[(size_t)k * D + j] = s > half ? 1.0f : (s < half ? 0.0f : 0.5f);
         }
-    }
     // dispersions of this class
     if (disp_model == 3) {  // skd: nem_mod.c:1152-1170
         if (nonempty)
-            for (int j = tid; j < D; j += TT_THREADS)
-                disp[(size_t)k * D + j] =
-                    __fdiv_rn(iner_of(S_of(k, j), nkd[k], true, 0.f), nkf[k]);
-    } else if (disp_model == 1) {  // sk_: nem_mod.c:1043-1073
-        double si = 0.0;
-        for (int j = tid; j < D; j += TT_THREADS)
-            si += (double)iner_of(S_of(k, j), nkd[k], nonempty, center[(size_t)k * D + j]);
-        si = block_sum<TT_THREADS>(si, sh);
-        if (nkf[k] > 0.f) {
-            double sn = (double)nkf[k] * (double)D;
-            float dk = __fdiv_rn((float)si, (float)sn);
-            for (int j = tid; j < D; j += TT_THREADS) disp[(size_t)k * D + j] = dk;
-        }
+            for (int j = j_lo + tid; j < j_hi; j += FT_THREADS)
+                disp[(size_t)k * D + j] = __fdiv_rn(iner_of(S_of(k, j), nkd[k], true, 0.f), nkf[k]);
     } else if (disp_model == 2) {  // s_d: nem_mod.c:1104-1126, float sums over the classes in order
-        for (int j = tid; j < D; j += TT_THREADS) {
+        for (int j = j_lo + tid; j < j_hi; j += FT_THREADS) {
             float si = 0.f, sn = 0.f;
             for (int c = 0; c < K; c++) {
                 bool ne = (double)nkf[c] > NEM_EPSILON;
@@ -1447,25 +1451,48 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
             }
             disp[(size_t)k * D + j] = __fdiv_rn(si, sn);
         }
-    } else {  // s__: nem_mod.c:988-1015
-        double si = 0.0, sn = 0.0;
-        for (int c = 0; c < K; c++) {
-            if (nkf[c] > 0.f) {
-                bool ne = (double)nkf[c] > NEM_EPSILON;
-                for (int j = tid; j < D; j += TT_THREADS)
-                    si += (double)iner_of(S_of(c, j), nkd[c], ne, ne ? 0.f : center[(size_t)c * D + j]);
-                sn += (double)nkf[c] * (double)D;
+    } else {  // sk_ (nem_mod.c:1043-1073) and s__ (nem_mod.c:988-1015): inertia summed over genomes
+        double v[1] = {0.0};
+        double sn = 0.0;
+        if (disp_model == 1) {
+            for (int j = j_lo + tid; j < j_hi; j += FT_THREADS)
+                v[0] += (double)iner_of(S_of(k, j), nkd[k], nonempty, nonempty ? 0.f : center[(size_t)k * D + j]);
+            sn = (double)nkf[k] * (double)D;
+        } else {
+            for (int c = 0; c < K; c++) {
+                if (nkf[c] > 0.f) {
+                    bool ne = (double)nkf[c] > NEM_EPSILON;
+                    for (int j = j_lo + tid; j < j_hi; j += FT_THREADS)
+                        v[0] += (double)iner_of(S_of(c, j), nkd[c], ne, ne ? 0.f : center[(size_t)c * D + j]);
+                    sn += (double)nkf[c] * (double)D;
+                }
             }
         }
-        si = block_sum<TT_THREADS>(si, sh);
-        float v = __fdiv_rn((float)si, (float)sn);
-        for (int j = tid; j < D; j += TT_THREADS) disp[(size_t)k * D + j] = v;
+        cluster_sum<1>(cluster, v, sh, slot);
+        if (disp_model == 0 || nkf[k] > 0.f) {
+            float dk = __fdiv_rn((float)v[0], (float)sn);
+            for (int j = j_lo + tid; j < j_hi; j += FT_THREADS) disp[(size_t)k * D + j] = dk;
+        }
     }
-    if (tid == 0)  // nem_mod.c:456-465
+    if (part == 0 && tid == 0)  // nem_mod.c:456-465
         prop[k] = prop_model == 1 ? __fdiv_rn(nkf[k], (float)N) : (float)(1.0 / (double)K);
-    __syncthreads();   // this CTA's theta is written: build the class tables from it
-    tables_class(k, K, D, wpr, prop, center, disp, coef, mask_xor, mask_valid, mask_f0, mask_f1,
-                 delta, sh, &sh_ok);
+    // the class's first dispersion (the popcount path's reference value) is written by part 0
+    __threadfence();
+    cluster.sync();
+    ClassCoef cc = class_coef(__ldcg(&disp[(size_t)k * D]));
+    TablesPartial p = tables_words(k, D, wpr, w_lo, w_hi, cc, center, disp, mask_xor, mask_valid,
+                                   mask_f0, mask_f1, delta);
+    // padding words [wreal, wpr) of the masks carry no genome: part 0 keeps them clean
+    if (part == 0)
+        for (int w = wreal + tid; w < wpr; w += FT_THREADS) {
+            size_t o = (size_t)k * wpr + w;
+            mask_xor[o] = 0u; mask_valid[o] = 0u; mask_f0[o] = 0u; mask_f1[o] = 0u;
+        }
+    if (p.mu_moved) atomicOr(&coef->mu_changed, 1);   // preset by the launcher (0, or 1 = forced)
+    double v[5] = {p.base_u, p.base_g, (double)p.notok, (double)p.n_valid, (double)p.n_x1};
+    cluster_sum<5>(cluster, v, sh, slot);
+    if (part == 0 && tid == 0)
+        tables_commit(k, K, D, prop, coef, delta, cc, v[0], v[1], v[2] == 0.0, (int)v[3], (int)v[4]);
 }
 
 // =============================================================================================
@@ -1784,14 +1811,14 @@ static void launch_density_uniform(cudaStream_t st, int K, const uint32_t *x, in
 }
 
 template <int KT, int T, int ROWS>
-static bool launch_density_tma_t(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
+static bool launch_density_tma_t(cudaStream_t st, int K, int D, const uint32_t *x, int n, int wpr,
                                  const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
                                  double *logpf, int32_t *hamming, int cached) {
     int wpr4 = wpr / 4;
     int stride4 = wpr4 | 1;  // odd number of uint4 per shared row => conflict-free LDS.128
     size_t mask_b = (size_t)2 * KT * wpr4 * sizeof(uint4);
     size_t tile_b = (size_t)ROWS * stride4 * sizeof(uint4);
-    size_t stat = (size_t)2 * ROWS * KT * 4 + 192;
+    size_t stat = (size_t)3 * ROWS * (KT + 1) * 4 + 512;
     const size_t budget = 224 * 1024;
     if (mask_b + 2 * tile_b + stat > budget) return false;
     static int force_s = -1, force_c = -1;
@@ -1813,27 +1840,20 @@ static bool launch_density_tma_t(cudaStream_t st, int K, const uint32_t *x, int 
     int n_tiles = cdiv(n, ROWS);
     static size_t attr_set = 0;
     if (smem > attr_set) {
-        cudaFuncSetAttribute(k_density_tma<KT, ROWS, T, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget - stat));
-        cudaFuncSetAttribute(k_density_tma<KT, ROWS, T, false>,
+        cudaFuncSetAttribute(k_density_tma<KT, ROWS, T>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget - stat));
         attr_set = budget;
     }
     int grid = num_sms() * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (K == KT)
-        k_density_tma<KT, ROWS, T, true><<<grid, ROWS * T, smem, st>>>(
-            K, (const uint4 *)x, n, wpr4, stride4, n_tiles, n_stages, coef, (const uint4 *)mx,
-            (const uint4 *)mv, logpf, hamming, cached);
-    else
-        k_density_tma<KT, ROWS, T, false><<<grid, ROWS * T, smem, st>>>(
-            K, (const uint4 *)x, n, wpr4, stride4, n_tiles, n_stages, coef, (const uint4 *)mx,
-            (const uint4 *)mv, logpf, hamming, cached);
+    k_density_tma<KT, ROWS, T><<<grid, ROWS * T, smem, st>>>(
+        K, D, (const uint4 *)x, n, wpr4, stride4, n_tiles, n_stages, coef, (const uint4 *)mx,
+        (const uint4 *)mv, logpf, hamming, cached);
     return true;
 }
 
 template <int KT>
-static bool launch_density_tma(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
+static bool launch_density_tma(cudaStream_t st, int K, int D, const uint32_t *x, int n, int wpr,
                                const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
                                double *logpf, int32_t *hamming, int cached) {
     int wpr4 = wpr / 4;
@@ -1844,7 +1864,7 @@ static bool launch_density_tma(cudaStream_t st, int K, const uint32_t *x, int n,
     if (force_r < 0) { const char *e = getenv("NEM_B200_DENSITY_ROWS"); force_r = e ? atoi(e) : 0; }
     int rows = force_r ? force_r : 128;
     if (KT > 4) t = t > 2 ? 2 : t;   // keep the static partial buffer small for large K
-#define DT(TT, RR) launch_density_tma_t<KT, TT, RR>(st, K, x, n, wpr, coef, mx, mv, logpf, hamming, cached)
+#define DT(TT, RR) launch_density_tma_t<KT, TT, RR>(st, K, D, x, n, wpr, coef, mx, mv, logpf, hamming, cached)
     if constexpr (KT <= 4) {
         if (t >= 8) return rows <= 32 ? DT(8, 32) : rows <= 64 ? DT(8, 64) : DT(8, 128);
         if (t >= 4) return rows <= 32 ? DT(4, 32) : rows <= 64 ? DT(4, 64) : DT(4, 128);
@@ -1854,28 +1874,7 @@ static bool launch_density_tma(cudaStream_t st, int K, const uint32_t *x, int n,
 #undef DT
 }
 
-template <int KT>
-static bool launch_density_direct(cudaStream_t st, int K, const uint32_t *x, int n, int wpr,
-                                  const nemk_coef *coef, const uint32_t *mx, const uint32_t *mv,
-                                  double *logpf, int32_t *hamming, int cached) {
-    int wpr4 = wpr / 4;
-    size_t smem = (size_t)2 * KT * wpr4 * sizeof(uint4);
-    if (smem > 96 * 1024) return false;
-    static int thr = -1, ctas = -1;
-    if (thr < 0) { const char *e = getenv("NEM_B200_DIRECT_THREADS"); thr = e ? atoi(e) : 128; }
-    if (ctas < 0) { const char *e = getenv("NEM_B200_DIRECT_CTAS"); ctas = e ? atoi(e) : 8; }
-    int grid = num_sms() * ctas;
-    int need = cdiv(n, thr);
-    if (grid > need) grid = need;
-#define DD(EX) do { \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_density_direct<KT, EX, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        k_density_direct<KT, EX, 4><<<grid, thr, smem, st>>>(K, (const uint4 *)x, n, wpr4, coef, (const uint4 *)mx, (const uint4 *)mv, logpf, hamming, cached); } while (0)
-    if (K == KT) DD(true); else DD(false);
-#undef DD
-    return true;
-}
-
-static int g_density_impl = -1;  // 0 = v1, 1 = v2 (TMA tiles), 2 = v3 (direct); env NEM_B200_DENSITY
+static int g_density_impl = -1;  // 0 = v1 (plain loads), 1 = v2 (TMA tiles); env NEM_B200_DENSITY=v1
 // logpf from the cached Hamming counts (the epilogue of the density kernels, same bits); runs
 // when the class bit masks did not move since the counts were taken
 template <int KT>
@@ -1893,7 +1892,7 @@ k_logpf_from_h(int K, int n, const nemk_coef *__restrict__ coef, const int32_t *
     logpf[q] = val;
 }
 
-extern "C" void nemk_density_uniform(nemk_stream s, int k, const uint32_t *x, int n, int wpr,
+extern "C" void nemk_density_uniform(nemk_stream s, int k, int d, const uint32_t *x, int n, int wpr,
                                      const nemk_coef *coef, const uint32_t *mask_xor,
                                      const uint32_t *mask_valid, double *logpf, int32_t *hamming,
                                      int cached) {
@@ -1901,24 +1900,24 @@ extern "C" void nemk_density_uniform(nemk_stream s, int k, const uint32_t *x, in
     if (!hamming) cached = 0;
     if (g_density_impl < 0) {
         const char *e = getenv("NEM_B200_DENSITY");
-        g_density_impl = (e && !strcmp(e, "v1")) ? 0 : (e && !strcmp(e, "v3")) ? 2 : 1;
+        g_density_impl = (e && !strcmp(e, "v1")) ? 0 : 1;
     }
     bool done = false;
-    if (g_density_impl == 2)
-        DISPATCH_K(k, (done = launch_density_direct<KT>(S(s), k, x, n, wpr, coef, mask_xor,
-                                                        mask_valid, logpf, hamming, cached)));
-    if (!done && g_density_impl >= 1)
-        DISPATCH_K(k, (done = launch_density_tma<KT>(S(s), k, x, n, wpr, coef, mask_xor, mask_valid,
+    if (g_density_impl >= 1)
+        DISPATCH_K(k, (done = launch_density_tma<KT>(S(s), k, d, x, n, wpr, coef, mask_xor, mask_valid,
                                                      logpf, hamming, cached)));
     if (!done)
         DISPATCH_K(k, (launch_density_uniform<KT>(S(s), k, x, n, wpr, coef, mask_xor, mask_valid,
                                                   logpf, hamming, cached)));
     note_launch();
-    if (cached) {
-        DISPATCH_K(k, (k_logpf_from_h<KT><<<cdiv((long long)n * k, 256), 256, 0, S(s)>>>(
-                          k, n, coef, hamming, logpf)));
-        note_launch();
-    }
+}
+
+extern "C" void nemk_logpf_from_cache(nemk_stream s, int k, int n, const nemk_coef *coef,
+                                      const int32_t *hamming, double *logpf) {
+    if (n <= 0) return;
+    DISPATCH_K(k, (k_logpf_from_h<KT><<<cdiv((long long)n * k, 256), 256, 0, S(s)>>>(
+                      k, n, coef, hamming, logpf)));
+    note_launch();
 }
 
 extern "C" void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d, int wpr,
@@ -2133,7 +2132,7 @@ extern "C" void nemk_mstep_finalize_tables(nemk_stream s, int k, int n, int d, i
                                            uint32_t *mask_f1, double *delta, int force_mu_changed) {
     cudaMemsetAsync(&coef->uniform_ok, 1, sizeof(int32_t), S(s));
     cudaMemsetAsync(&coef->mu_changed, force_mu_changed ? 1 : 0, sizeof(int32_t), S(s));
-    k_mstep_finalize_tables<<<k, TT_THREADS, 0, S(s)>>>(k, n, d, wpr, prop_model, disp_model, s_int,
+    k_mstep_finalize_tables<<<k * FT_CLUSTER, FT_THREADS, 0, S(s)>>>(k, n, d, wpr, prop_model, disp_model, s_int,
                                                        nk_int, s_dbl, nk_dbl, prop, center, disp,
                                                        coef, mask_xor, mask_valid, mask_f0, mask_f1,
                                                        delta);
