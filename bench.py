@@ -255,8 +255,7 @@ def build_global_graph(torch, dist, dev, rank, world, n_loc, xh, seed, kind):
 def main_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import nemo  # theta0 helper only (cpu_baseline leg uses the rest)
-    from pangenomenem_b200 import capi, sharded, synth_gpu
+    from pangenomenem_b200 import capi, sharded, synth, synth_gpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -293,7 +292,7 @@ def main_ours(args):
         row_ptr = col = wgt = None
     gen_s = time.time() - t0
     nnz = 0 if col is None else int(col.shape[0])
-    theta0 = nemo.default_theta(K, d)
+    theta0 = synth.default_theta(K, d)
     opts = dict(k=K, algo="ncem", update="seq", beta=beta, conv="clas", conv_thr=1e-8,
                 it_max=100, prop="pk", disp="sk_", sweep_impl="auto")
 

@@ -180,6 +180,17 @@ def sweep_dag_depth(row_ptr: np.ndarray, col: np.ndarray) -> int:
 
 # --------------------------------------------------------------------------- file contract
 
+def default_theta(k: int, d: int, low_disp: float = 0.1):
+    """PPanGGOLiN's default .m (ppanggolin.py:893-901) as the reference reads it
+    (nem_exe.c:1022-1034: last proportion = 1 - sum of the others, in float)."""
+    assert k == 3
+    prop = np.array([0.33333, 0.33333, 0.0], dtype=np.float32)
+    prop[2] = np.float32(np.float32(1.0) - prop[0]) - prop[1]
+    center = np.repeat(np.array([1.0, 0.5, 0.0], dtype=np.float32)[:, None], d, axis=1)
+    disp = np.repeat(np.array([low_disp, 0.5, low_disp], dtype=np.float32)[:, None], d, axis=1)
+    return prop, center, disp
+
+
 def default_m_line(d: int, low_disp: float = 0.1) -> str:
     """PPanGGOLiN's default ``.m`` (reference ppanggolin.py:893-901)."""
     return ("1 " + "0.33333 0.33333 " + " ".join(["1"] * d) + " " + " ".join(["0.5"] * d) + " "
