@@ -44,6 +44,16 @@ typedef struct {
 
 typedef void *nemk_stream;
 
+/* Where the consumers of log p_k f_k(x_i) (ncem sweeps, criteria) get it from: the materialised
+ * array logpf[n_loc][K], or -- popcount density path -- the cached Hamming counts ham[n_loc][K]
+ * plus the class coefficients: logpf = lp - (a*H + base), evaluated in registers with the density
+ * kernels' own expression (same bits), so no N*K*8-byte array is written or read. */
+typedef struct {
+    const double *logpf;
+    const int32_t *ham;      /* non-NULL selects the Hamming source */
+    const nemk_coef *coef;
+} nemk_lpsrc;
+
 /* ---- loader */
 void nemk_pack_u8(nemk_stream s, const uint8_t *x, int n, int d, int wpr, uint32_t *out);
 void nemk_transpose_bits(nemk_stream s, const uint32_t *x, int n, int wpr, int d, int nwt,
@@ -58,6 +68,7 @@ void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const float *prop,
 /* ---- E-step density */
 /* cached != 0: `hamming` is the engine's persistent H cache; the X pass only runs when
  * coef->mu_changed, otherwise logpf is rebuilt from the cached counts (same formula, same bits) */
+/* logpf may be NULL (only the Hamming counts are produced) */
 void nemk_density_uniform(nemk_stream s, int k, int d, const uint32_t *x, int n, int wpr,
                           const nemk_coef *coef, const uint32_t *mask_xor,
                           const uint32_t *mask_valid, double *logpf, int32_t *hamming, int cached);
@@ -84,18 +95,18 @@ void nemk_heavy_list(nemk_stream s, int row0, int n_loc, const int32_t *row_ptr,
  * Row sharding: this rank owns the global rows [row0, row0+n_loc); labels, t, CSR, dirty flags and
  * work lists are indexed by GLOBAL family id, logpf by local row.  One GPU: row0 = 0, n_loc = N.
  * Work lists: wl_a/wl_b used alternately, wl_cnt[4] rotating counters (round r: list r&1). */
-void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                             const int32_t *row_ptr, const int32_t *col, const float *wgt,
                             double beta, const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
                             int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
                             const int32_t *rcol, const int32_t *heavy, int n_heavy,
                             nemk_counters *cnt, const int32_t *skip);
-void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                            const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
                            const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a,
                            int32_t *wl_b, int32_t *wl_cnt, int round, const int32_t *rrow_ptr,
                            const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
-void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                                  const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                  double beta, const uint8_t *lab_old, uint8_t *lab_cur,
                                  int32_t *dirty, int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt,
@@ -104,7 +115,7 @@ void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc, cons
 void nemk_mark_remote(nemk_stream s, int n_glob, int row0, int n_loc, const uint8_t *lab_cur,
                       uint8_t *lab_seen, int32_t *dirty, int32_t *wl, int32_t *wl_count,
                       const int32_t *rrow_ptr, const int32_t *rcol, int32_t *pending);
-void nemk_sweep_ncem_level(nemk_stream s, int k, const double *logpf, const int32_t *row_ptr,
+void nemk_sweep_ncem_level(nemk_stream s, int k, nemk_lpsrc lps, const int32_t *row_ptr,
                            const int32_t *col, const float *wgt, double beta, uint8_t *lab,
                            const int32_t *sites, const int32_t *level_ptr, int lv_lo, int lv_hi,
                            int grid_ctas, nemk_counters *cnt, const int32_t *skip);
@@ -141,7 +152,7 @@ void nemk_mstep_finalize_tables(nemk_stream s, int k, int n, int d, int wpr, int
 
 /* ---- criteria: per-rank partial sums (exactly nblocks rows of 4 doubles: D G L Z), then the
  * final fixed-order sum over the partial rows of every rank -> U D L M Z G */
-int  nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+int  nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                            const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
                            const uint8_t *lab, const float *t, const int32_t *heavy, int n_heavy,
                            double *partials, int nblocks);

@@ -76,6 +76,7 @@ struct nemb_handle {
                               labels the M-step statistics currently describe (local rows) */
     int32_t *d_ham;        /* cached Hamming counts H[n][K] of the popcount density path */
     int ham_valid, stats_valid, tables_forced;
+    int lp_from_ham;       /* the consumers rebuild logpf from d_ham in registers (no logpf array) */
     int64_t last_changed;  /* labels moved by the last sweep (all ranks), -1 = unknown */
     float *d_t[2];
     int cur, state_labels;
@@ -659,6 +660,12 @@ static int theta_uniform(int k, int d, const float *center, const float *disp)
 }
 
 /* ------------------------------------------------------------------ steps of one fit */
+static nemk_lpsrc lpsrc(const nemb_handle *h)
+{
+    nemk_lpsrc s = {h->d_logpf, h->lp_from_ham ? h->d_ham : NULL, h->d_coef};
+    return s;
+}
+
 /* next_uniform: the density pass that follows takes the popcount path; its cached Hamming
  * counts stay valid while the class bit masks do not move (k_theta_tables detects that) */
 static int run_tables(nemb_handle *h, int k, int next_uniform)
@@ -672,15 +679,26 @@ static int run_tables(nemb_handle *h, int k, int next_uniform)
     return NEMB_OK;
 }
 
-static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming)
+/* lean: ncem fits on the popcount path keep only the Hamming counts; the sweeps and the criteria
+ * rebuild logpf from them in registers (nemk_lpsrc), so neither the N*K*8-byte array nor the
+ * separate cached-rebuild launch exists */
+static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming, int lean)
 {
     STAGE_BEGIN(ST_DENSITY);
+    h->lp_from_ham = 0;
     if (uniform) {
         /* d_hamming == NULL: the fit's own pass, through the persistent H cache */
+        lean = lean && d_hamming == NULL;
         nemk_density_uniform(h->stream, k, h->d, h->d_x, h->n, h->wpr, h->d_coef, h->d_mxor, h->d_mval,
-                             h->d_logpf, d_hamming ? d_hamming : h->d_ham, d_hamming == NULL);
+                             lean ? NULL : h->d_logpf, d_hamming ? d_hamming : h->d_ham, d_hamming == NULL);
         h->ham_valid = d_hamming == NULL;
-        if (h->ham_valid) {   /* exactly one of the two kernels does work (coef->mu_changed) */
+        h->lp_from_ham = lean;
+        if (lean) {
+            /* the kernel returns at once when the masks did not move (coef->mu_changed == 0):
+             * read_status relabels this stage as "cached" then */
+            h->ev_last_cached = -1;
+            if (h->profile && h->tables_forced) h->ev_last_density = -1;   /* the X pass certainly ran */
+        } else if (h->ham_valid) {   /* exactly one of the two kernels does work (coef->mu_changed) */
             STAGE_END();
             STAGE_BEGIN(ST_DENSITY_CACHED);
             nemk_logpf_from_cache(h->stream, k, h->n, h->d_coef, h->d_ham, h->d_logpf);
@@ -716,6 +734,9 @@ static int read_status(nemb_handle *h)
         /* discard the stage whose kernel returned at once */
         h->ev_kind[h->h_empty[1] ? h->ev_last_cached : h->ev_last_density] = -2;
         h->ev_last_density = h->ev_last_cached = -1;
+    } else if (h->profile && h->lp_from_ham && h->ev_last_density >= 0) {
+        if (!h->h_empty[1]) h->ev_kind[h->ev_last_density] = ST_DENSITY_CACHED;   /* X not read */
+        h->ev_last_density = -1;
     }
     nemk_counters tot;
     memset(&tot, 0, sizeof tot);
@@ -732,19 +753,21 @@ static int read_status(nemb_handle *h)
 
 /* jacobi round 0 left the first work list in list 0 / counter 0: three grid-wide rounds, then
  * one CTA walks the tail to exhaustion (and leaves the four counters at 0) */
-enum { GRID_ROUNDS = 3 };
+enum { GRID_ROUNDS = 3, SHORT_LIST = 4096 };
 static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, uint8_t *out,
                          const int32_t *rp, const int32_t *skip)
 {
-    for (int r = 0; r < GRID_ROUNDS; r++)
-        nemk_sweep_ncem_fixup_round(h->stream, k, h->row0, h->n, h->d_logpf, rp, h->d_col, h->d_wgt,
+    /* few labels moved last iteration => the work lists are short: one CTA walks them all */
+    int grid_rounds = (h->last_changed >= 0 && h->last_changed < SHORT_LIST) ? 0 : GRID_ROUNDS;
+    for (int r = 0; r < grid_rounds; r++)
+        nemk_sweep_ncem_fixup_round(h->stream, k, h->row0, h->n, lpsrc(h), rp, h->d_col, h->d_wgt,
                                     beta, in, out, h->d_dirty, h->d_wl[0], h->d_wl[1],
                                     h->d_wl_counts, r, h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt,
                                     skip);
-    nemk_sweep_ncem_fixup(h->stream, k, h->row0, h->n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
-                          out, h->d_dirty, h->d_wl[0], h->d_wl[1], h->d_wl_counts, GRID_ROUNDS,
+    nemk_sweep_ncem_fixup(h->stream, k, h->row0, h->n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
+                          out, h->d_dirty, h->d_wl[0], h->d_wl[1], h->d_wl_counts, grid_rounds,
                           h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip);
-    h->launches += 1 + GRID_ROUNDS;
+    h->launches += 1 + grid_rounds;
 }
 
 /* one E-step sweep; *flipped tells whether the state moved to the other buffer */
@@ -762,7 +785,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
         uint8_t *in = h->d_lab[h->cur], *out = h->d_lab[h->cur ^ 1], *seen = h->d_lab[2];
         int impl = o->sweep_impl == NEMB_SWEEP_AUTO ? NEMB_SWEEP_SPEC : o->sweep_impl;
         if (!seq) {
-            nemk_sweep_ncem_jacobi(h->stream, k, row0, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+            nemk_sweep_ncem_jacobi(h->stream, k, row0, n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
                                    out, NULL, NULL, NULL, NULL, NULL, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip);
             h->launches++;
             /* halo exchange of the hard labels: every rank's slice, 1 byte per family */
@@ -773,7 +796,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
                 CK(cudaMemcpyAsync(out, in, L, cudaMemcpyDeviceToDevice, h->stream));
                 CK(cudaMemcpyAsync(seen, in, L, cudaMemcpyDeviceToDevice, h->stream));
             }
-            nemk_sweep_ncem_jacobi(h->stream, k, row0, n, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+            nemk_sweep_ncem_jacobi(h->stream, k, row0, n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
                                    out, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
                                    h->d_rcol, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip);
             h->launches++;
@@ -803,7 +826,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
         } else {
             if ((rc = ensure_levels(h)) != NEMB_OK) return rc;
             for (int s = 0; s < h->n_steps; s++) {
-                nemk_sweep_ncem_level(h->stream, k, h->d_logpf, rp, h->d_col, h->d_wgt, beta, in,
+                nemk_sweep_ncem_level(h->stream, k, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
                                       h->d_sites, h->d_level_ptr, h->steps[s].lo, h->steps[s].hi,
                                       h->steps[s].grid, &h->d_status->cnt, skip);
                 h->launches++;
@@ -898,7 +921,7 @@ static int run_criteria(nemb_handle *h, const nemb_options *o, double beta, doub
     int rc;
     STAGE_BEGIN(ST_CRIT);
     size_t mine = (size_t)h->rank * h->crit_blocks * 4;
-    nemk_criteria_partial(h->stream, o->k, h->row0, h->n, h->d_logpf, h->spatial ? h->d_row_ptr : NULL,
+    nemk_criteria_partial(h->stream, o->k, h->row0, h->n, lpsrc(h), h->spatial ? h->d_row_ptr : NULL,
                           h->d_col, h->d_wgt, beta, o->algo == NEMB_ALGO_NCEM ? h->d_lab[h->cur] : NULL,
                           o->algo == NEMB_ALGO_NCEM ? NULL : h->d_t[h->cur], h->d_heavy, h->n_heavy,
                           h->d_crit_partials + mine, h->crit_blocks);
@@ -954,12 +977,13 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     double beta = h->spatial ? (double)o->beta : 0.0;   /* nem_exe.c:570-574 */
     int uniform_m = o->param_fixed ? uniform0 : (o->disp == NEMB_DISP_K_ || o->disp == NEMB_DISP___);
     int want_crit_each = o->dolog || o->conv == NEMB_CONV_CRIT;
+    int lean = o->algo == NEMB_ALGO_NCEM && !getenv("NEM_B200_KEEP_LOGPF");
     size_t kd = (size_t)k * h->d;
     float *nk_host = cb ? malloc(sizeof(float) * k) : NULL;
 
     if ((rc = init_state(h, o)) != NEMB_OK) return rc;
     if ((rc = run_tables(h, k, 0)) != NEMB_OK) return rc;
-    if ((rc = run_density(h, k, uniform0, NULL)) != NEMB_OK) return rc;
+    if ((rc = run_density(h, k, uniform0, NULL, lean)) != NEMB_OK) return rc;
     /* ComputePartitionFromPara(Needinit=1): blind sweep then beta sweep (nem_alg.c:1970-1981) */
     if ((rc = run_sweep(h, o, 0.0, &flipped)) != NEMB_OK) return rc;
     if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
@@ -981,7 +1005,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     int iter, converged = 0, status = NEMB_OK, empty = 0;
     for (iter = 1; iter <= o->it_max && !converged && status == NEMB_OK; iter++) {
         if (!o->param_fixed && (rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
-        if ((rc = run_density(h, k, uniform_m, NULL)) != NEMB_OK) return rc;
+        if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
         if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
         if ((rc = run_sweep(h, o, beta, &flipped)) != NEMB_OK) return rc;
         if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
@@ -1029,7 +1053,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     iter -= 1;
     if (iter == 0) { /* nem_alg.c:1845-1851 */
         if ((rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
-        if ((rc = run_density(h, k, uniform_m, NULL)) != NEMB_OK) return rc;
+        if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
     }
     if ((rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
     CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
@@ -1220,7 +1244,7 @@ int nemb_stage_density(nemb_handle *h, int k, const float *prop, const float *ce
     if (hamming_out && uniform) CK(cudaMalloc((void **)&d_ham, sizeof(int32_t) * nk));
     h->ham_valid = 0;
     if ((rc = run_tables(h, k, 0)) != NEMB_OK) return rc;
-    if ((rc = run_density(h, k, uniform, d_ham)) != NEMB_OK) return rc;
+    if ((rc = run_density(h, k, uniform, d_ham, 0)) != NEMB_OK) return rc;
     CK(cudaMemcpyAsync(logpf_out, h->d_logpf, sizeof(double) * nk, cudaMemcpyDeviceToHost, h->stream));
     if (d_ham) CK(cudaMemcpyAsync(hamming_out, d_ham, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1257,6 +1281,7 @@ int nemb_stage_sweep(nemb_handle *h, const nemb_options *o, const double *logpf,
     h->profile = 0;
     size_t nk = (size_t)h->n * o->k;
     CK(cudaMemcpyAsync(h->d_logpf, logpf, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
+    h->lp_from_ham = 0;
     CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, sizeof(int32_t), h->stream));
     if ((rc = upload_state(h, o, t_inout)) != NEMB_OK) return rc;
     if ((rc = run_sweep(h, o, h->spatial ? (double)beta : 0.0, &flipped)) != NEMB_OK) return rc;
@@ -1311,6 +1336,7 @@ int nemb_stage_criteria(nemb_handle *h, const nemb_options *o, const double *log
     h->profile = 0;
     size_t nk = (size_t)h->n * o->k;
     CK(cudaMemcpyAsync(h->d_logpf, logpf, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
+    h->lp_from_ham = 0;
     if ((rc = upload_state(h, o, t)) != NEMB_OK) return rc;
     if ((rc = run_criteria(h, o, h->spatial ? (double)beta : 0.0, h->d_status->crit_after)) != NEMB_OK) return rc;
     if ((rc = read_status(h)) != NEMB_OK) return rc;

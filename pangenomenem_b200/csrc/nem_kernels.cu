@@ -28,6 +28,24 @@
 
 static __device__ __forceinline__ double neg_inf() { return -CUDART_INF; }
 
+// log p_k f_k(x_i) of the popcount path from the Hamming count (ComputePkFkiM nem_alg.c:2260-2285 +
+// DensBernoulli nem_mod.c:649-674).  ONE expression shared by the density epilogues, the cached
+// rebuild and the consumers that evaluate it in registers (nemk_lpsrc), so the bits are the same
+// wherever it is computed.
+static __device__ __forceinline__ double logpf_of_h(const nemk_coef *__restrict__ coef, int k, int h) {
+    double lp = coef->lp[k];
+    if (coef->forb[k]) return h ? neg_inf() : lp;
+    return lp - (coef->a[k] * (double)h + coef->base[k]);
+}
+template <int KT>
+static __device__ __forceinline__ void load_lp(const nemk_lpsrc &src, int K, size_t il, double (&lp)[KT]) {
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        if (k < K) lp[k] = src.ham ? logpf_of_h(src.coef, k, src.ham[il * K + k]) : src.logpf[il * K + k];
+        else lp[k] = neg_inf();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // error bookkeeping for the launch layer
 static cudaError_t g_last_err = cudaSuccess;
@@ -299,10 +317,7 @@ k_density_uniform(int K, const uint4 *__restrict__ x, int n, int wpr4,
 #pragma unroll
             for (int k = 0; k < KT; k++) {
                 if (k < K) {
-                    double lp = coef->lp[k], v;
-                    if (coef->forb[k]) v = h[k] ? neg_inf() : lp;
-                    else v = lp - (coef->a[k] * (double)h[k] + coef->base[k]);
-                    logpf[(size_t)row * K + k] = v;
+                    if (logpf) logpf[(size_t)row * K + k] = logpf_of_h(coef, k, h[k]);
                     if (hamming) hamming[(size_t)row * K + k] = h[k];
                 }
             }
@@ -425,8 +440,14 @@ k_density_tma(int K, int D, const uint4 *__restrict__ x, int n, int wpr4, int st
         long long r0 = (long long)tile * ROWS;
         int rows = (int)min((long long)ROWS, (long long)n - r0);
         if (tid == 0) mbar_expect_tx(&bars[stage], (uint32_t)rows * row_bytes);
-        if (tid < rows)
-            bulk_g2s(tiles + ((size_t)stage * ROWS + tid) * stride4, x + (size_t)(r0 + tid) * wpr4,
+        // every warp issues its share of the tile's bulk copies (32/T rows per warp): one warp
+        // issuing them all arrives late at the tile barrier (profiles/r1_c4_density_stalls.txt).
+        // A copy may complete before thread 0's expect_tx: the transaction count goes negative,
+        // the phase still cannot complete before the arrival.
+        constexpr int RPW = 32 / T;
+        const int lane = tid & 31, rr = (tid >> 5) * RPW + lane;
+        if (lane < RPW && rr < rows)
+            bulk_g2s(tiles + ((size_t)stage * ROWS + rr) * stride4, x + (size_t)(r0 + rr) * wpr4,
                      row_bytes, &bars[stage]);
     };
     auto epilogue = [&](int tile, int slot) {   // one output (row, class) per thread
@@ -437,10 +458,7 @@ k_density_tma(int K, int D, const uint4 *__restrict__ x, int n, int wpr4, int st
             const int *hs = &hsum[slot][rr * (KT + 1)];
             int kind = s_kind[k], P = hs[KT];
             int h = kind == 0 ? hs[s_slot[k]] : kind == 1 ? P : kind == 2 ? D - P : 0;
-            double lp = coef->lp[k], val;
-            if (coef->forb[k]) val = h ? neg_inf() : lp;
-            else val = lp - (coef->a[k] * (double)h + coef->base[k]);
-            logpf[(size_t)row * K + k] = val;
+            if (logpf) logpf[(size_t)row * K + k] = logpf_of_h(coef, k, h);
             if (hamming) hamming[(size_t)row * K + k] = h;
         }
     };
@@ -700,7 +718,7 @@ static __device__ __forceinline__ void mark_readers_warp(int i, const int32_t *_
 // labels, CSR, dirty flags and work lists are indexed by global family id, logpf by local row.
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_sweep_ncem_jacobi(int K, int row0, int n_loc, const double *__restrict__ logpf,
+k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
                     const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                     const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_in,
                     uint8_t *__restrict__ lab_out, int32_t *dirty, int32_t *wl, int32_t *wl_count,
@@ -717,7 +735,9 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const double *__restrict__ logpf
         int i = heavy[wid], il = i - row0;
         double ctx[KT];
         ctx_labels_warp<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
-        int km = site_argmax<KT>(K, logpf + (size_t)il * K, ctx, beta, flags);
+        double lpv[KT];
+        load_lp<KT>(lps, K, (size_t)il, lpv);
+        int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
         int ch = (km != (int)lab_in[i]);
         if (lane == 0) lab_out[i] = (uint8_t)km;
         if (ch && dirty) mark_readers_warp(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc);
@@ -736,7 +756,9 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const double *__restrict__ logpf
         if (!is_heavy) {
             double ctx[KT];
             ctx_labels<KT>(K, i, rp, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
-            int km = site_argmax<KT>(K, logpf + (size_t)il * K, ctx, beta, flags);
+            double lpv[KT];
+            load_lp<KT>(lps, K, (size_t)il, lpv);
+            int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
             lab_out[i] = (uint8_t)km;
             changed = (km != (int)lab_in[i]);
             if (changed && dirty)
@@ -765,7 +787,7 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const double *__restrict__ logpf
 // CTA that loops until the list is empty.
 template <int KT>
 static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row1,
-                                                 const double *__restrict__ logpf,
+                                                 const nemk_lpsrc &lps,
                                                  const int32_t *__restrict__ row_ptr,
                                                  const int32_t *__restrict__ col,
                                                  const float *__restrict__ wgt, double beta,
@@ -780,7 +802,9 @@ static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row
     ctx_labels<KT>(K, i, row_ptr, col, wgt,
                    [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
     int flags;
-    int km = site_argmax<KT>(K, logpf + (size_t)(i - row0) * K, ctx, beta, flags);
+    double lpv[KT];
+    load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+    int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
     int was = __ldcg(lab_cur + i);
     if (km == was) return 0;
     lab_cur[i] = (uint8_t)km;
@@ -793,7 +817,7 @@ static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row
 // the same for a hub, by a whole warp (every lane returns the same delta)
 template <int KT>
 static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, int row1,
-                                                      const double *__restrict__ logpf,
+                                                      const nemk_lpsrc &lps,
                                                       const int32_t *__restrict__ row_ptr,
                                                       const int32_t *__restrict__ col,
                                                       const float *__restrict__ wgt, double beta,
@@ -809,7 +833,9 @@ static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, in
     ctx_labels_warp<KT>(K, i, row_ptr, col, wgt,
                         [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
     int flags;
-    int km = site_argmax<KT>(K, logpf + (size_t)(i - row0) * K, ctx, beta, flags);
+    double lpv[KT];
+    load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+    int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
     int was = __shfl_sync(FULL, (int)__ldcg(lab_cur + i), 0);
     if (km == was) return 0;
     if (lane == 0) { lab_cur[i] = (uint8_t)km; __threadfence(); }
@@ -824,7 +850,7 @@ static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, in
 template <int KT>
 static __device__ __forceinline__ int fixup_items(int K, int idx, int count,
                                                   const int32_t *__restrict__ cur_list, int row0,
-                                                  int row1, const double *__restrict__ logpf,
+                                                  int row1, const nemk_lpsrc &lps,
                                                   const int32_t *__restrict__ row_ptr,
                                                   const int32_t *__restrict__ col,
                                                   const float *__restrict__ wgt, double beta,
@@ -838,14 +864,14 @@ static __device__ __forceinline__ int fixup_items(int K, int idx, int count,
     bool hub = i >= 0 && (row_ptr[i + 1] - row_ptr[i] > HEAVY_DEG);
     int d = 0;
     if (i >= 0 && !hub)
-        d = fixup_site<KT>(K, i, row0, row1, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
+        d = fixup_site<KT>(K, i, row0, row1, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
                            next_list, next_cnt, rrow_ptr, rcol);
     unsigned hm = __ballot_sync(FULL, hub);
     while (hm) {
         int src = __ffs(hm) - 1;
         hm &= hm - 1;
         int site = __shfl_sync(FULL, i, src);
-        int r = fixup_site_warp<KT>(K, site, row0, row1, logpf, row_ptr, col, wgt, beta, lab_old,
+        int r = fixup_site_warp<KT>(K, site, row0, row1, lps, row_ptr, col, wgt, beta, lab_old,
                                     lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
         if (lane == src) d = r;
     }
@@ -857,7 +883,7 @@ static __device__ __forceinline__ int fixup_items(int K, int idx, int count,
 // (idle during round r), so no memset sits between rounds.  The tail kernel leaves all four at 0.
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_sweep_ncem_fixup_round(int K, int row0, int row1, const double *__restrict__ logpf,
+k_sweep_ncem_fixup_round(int K, int row0, int row1, const nemk_lpsrc lps,
                          const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                          const float *__restrict__ wgt, double beta,
                          const uint8_t *__restrict__ lab_old, uint8_t *lab_cur, int32_t *dirty,
@@ -873,7 +899,7 @@ k_sweep_ncem_fixup_round(int K, int row0, int row1, const double *__restrict__ l
     int dchanged = 0;
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count;
          base += gridDim.x * blockDim.x)
-        dchanged += fixup_items<KT>(K, base + (threadIdx.x & 31), count, cur_list, row0, row1, logpf,
+        dchanged += fixup_items<KT>(K, base + (threadIdx.x & 31), count, cur_list, row0, row1, lps,
                                     row_ptr, col, wgt, beta, lab_old, lab_cur, dirty, next_list,
                                     next_cnt, rrow_ptr, rcol);
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
@@ -882,7 +908,7 @@ k_sweep_ncem_fixup_round(int K, int row0, int row1, const double *__restrict__ l
 
 template <int KT>
 __global__ void __launch_bounds__(1024)
-k_sweep_ncem_fixup(int K, int row0, int row1, const double *__restrict__ logpf,
+k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_old,
                    uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a, int32_t *wl_b,
@@ -905,7 +931,7 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const double *__restrict__ logpf,
         rounds++;
         for (int base = threadIdx.x & ~31; base < count; base += blockDim.x)
             dchanged += fixup_items<KT>(K, base + (threadIdx.x & 31), count, cur_list, row0, row1,
-                                        logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
+                                        lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
                                         next_list, next_cnt, rrow_ptr, rcol);
         __syncthreads();
     }
@@ -945,7 +971,7 @@ k_mark_remote(int n_glob, int row0, int row1, const uint8_t *__restrict__ lab_cu
 // of narrow levels with __syncthreads between them).
 template <int KT>
 __global__ void __launch_bounds__(1024)
-k_sweep_ncem_level(int K, const double *__restrict__ logpf, const int32_t *__restrict__ row_ptr,
+k_sweep_ncem_level(int K, const nemk_lpsrc lps, const int32_t *__restrict__ row_ptr,
                    const int32_t *__restrict__ col, const float *__restrict__ wgt, double beta,
                    uint8_t *lab, const int32_t *__restrict__ sites,
                    const int32_t *__restrict__ level_ptr, int lv_lo, int lv_hi, int single_cta,
@@ -962,7 +988,9 @@ k_sweep_ncem_level(int K, const double *__restrict__ logpf, const int32_t *__res
             double ctx[KT];
             ctx_labels<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)vlab[j]; }, ctx);
             int flags;
-            int km = site_argmax<KT>(K, logpf + (size_t)i * K, ctx, beta, flags);
+            double lpv[KT];
+            load_lp<KT>(lps, K, (size_t)i, lpv);
+            int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
             changed += (km != (int)vlab[i]);
             nul += flags & 1;
             ties += (flags >> 1) & 1;
@@ -1198,7 +1226,7 @@ k_changed_rows(int n, const uint8_t *__restrict__ lab, const uint8_t *__restrict
 // uint4 loads are issued together; per 32-genome word a ballot transpose gives lane b the 32-row
 // column of genome 32w+b, which meets the rows' old/new class masks by popcount.  Items are spread
 // over the whole grid, so a few hundred changed rows cost microseconds.
-#define DELTA_CHUNK 16
+#define DELTA_CHUNK 4
 template <int KT>
 __global__ void __launch_bounds__(256)
 k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8_t *__restrict__ lab,
@@ -1531,7 +1559,7 @@ static __device__ __forceinline__ void crit_site(int K, const double *__restrict
 // the other blocks: the remaining sites, one thread per site.  Fixed assignment => deterministic.
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_criteria_partial(int K, int row0, int n_loc, const double *__restrict__ logpf,
+k_criteria_partial(int K, int row0, int n_loc, const nemk_lpsrc lps,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab,
                    const float *__restrict__ t, const int32_t *__restrict__ heavy, int n_heavy,
@@ -1549,7 +1577,11 @@ k_criteria_partial(int K, int row0, int n_loc, const double *__restrict__ logpf,
             unsigned l = lab[i];
 #pragma unroll
             for (int k = 0; k < KT; k++) ti[k] = (l == (unsigned)k) ? 1.f : 0.f;
-            if (lane == 0) crit_site<KT>(K, logpf + (size_t)(i - row0) * K, ctx, ti, beta, cD, cG, cL, cZ);
+            if (lane == 0) {
+                double lpv[KT];
+                load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+                crit_site<KT>(K, lpv, ctx, ti, beta, cD, cG, cL, cZ);
+            }
         }
     } else {
         int nb = gridDim.x - heavy_blocks;
@@ -1569,7 +1601,9 @@ k_criteria_partial(int K, int row0, int n_loc, const double *__restrict__ logpf,
 #pragma unroll
                 for (int k = 0; k < KT; k++) ti[k] = (k < K) ? t[(size_t)i * K + k] : 0.f;
             }
-            crit_site<KT>(K, logpf + (size_t)il * K, ctx, ti, beta, cD, cG, cL, cZ);
+            double lpv[KT];
+            load_lp<KT>(lps, K, (size_t)il, lpv);
+            crit_site<KT>(K, lpv, ctx, ti, beta, cD, cG, cL, cZ);
         }
     }
     cD = block_sum<256>(cD, sh);
@@ -1862,7 +1896,9 @@ static bool launch_density_tma(cudaStream_t st, int K, int D, const uint32_t *x,
     int t = force_t ? force_t : (wpr4 >= 32 ? 4 : wpr4 >= 16 ? 2 : 1);   // measured on B200, DESIGN.md
     static int force_r = -1;
     if (force_r < 0) { const char *e = getenv("NEM_B200_DENSITY_ROWS"); force_r = e ? atoi(e) : 0; }
-    int rows = force_r ? force_r : 128;
+    // two CTAs of 64 families x T column groups per SM: their tile barriers interleave (C4: 121 us
+    // against 128 us for one CTA of 128 families)
+    int rows = force_r ? force_r : (t >= 4 ? 64 : 128);
     if (KT > 4) t = t > 2 ? 2 : t;   // keep the static partial buffer small for large K
 #define DT(TT, RR) launch_density_tma_t<KT, TT, RR>(st, K, D, x, n, wpr, coef, mx, mv, logpf, hamming, cached)
     if constexpr (KT <= 4) {
@@ -1885,11 +1921,7 @@ k_logpf_from_h(int K, int n, const nemk_coef *__restrict__ coef, const int32_t *
     size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= (size_t)n * K) return;
     int k = (int)(q % K);
-    int h = hamming[q];
-    double lp = coef->lp[k], val;
-    if (coef->forb[k]) val = h ? neg_inf() : lp;
-    else val = lp - (coef->a[k] * (double)h + coef->base[k]);
-    logpf[q] = val;
+    logpf[q] = logpf_of_h(coef, k, hamming[q]);
 }
 
 extern "C" void nemk_density_uniform(nemk_stream s, int k, int d, const uint32_t *x, int n, int wpr,
@@ -1936,7 +1968,7 @@ extern "C" void nemk_density_general(nemk_stream s, int k, const uint32_t *x, in
 }
 
 extern "C" void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc,
-                                       const double *logpf, const int32_t *row_ptr,
+                                       nemk_lpsrc lps, const int32_t *row_ptr,
                                        const int32_t *col, const float *wgt, double beta,
                                        const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
                                        int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
@@ -1945,7 +1977,7 @@ extern "C" void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc
     if (n_loc <= 0) return;
     int hb = (row_ptr && beta != 0.0 && heavy) ? cdiv((long long)n_heavy * 32, 256) : 0;
     DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<hb + cdiv(n_loc, 256), 256, 0, S(s)>>>(
-                      k, row0, n_loc, logpf, row_ptr, col, wgt, beta, lab_in, lab_out, dirty, wl,
+                      k, row0, n_loc, lps, row_ptr, col, wgt, beta, lab_in, lab_out, dirty, wl,
                       wl_count, rrow_ptr, rcol, heavy, n_heavy, hb, cnt, skip)));
     note_launch();
 }
@@ -1961,7 +1993,7 @@ extern "C" void nemk_heavy_list(nemk_stream s, int row0, int n_loc, const int32_
     note_launch();
 }
 
-extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                                       const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                       double beta, const uint8_t *lab_old, uint8_t *lab_cur,
                                       int32_t *dirty, int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt,
@@ -1969,13 +2001,13 @@ extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc,
                                       nemk_counters *cnt, const int32_t *skip) {
     if (n_loc <= 0) return;
     DISPATCH_K(k, (k_sweep_ncem_fixup<KT><<<1, 1024, 0, S(s)>>>(
-                      k, row0, row0 + n_loc, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
+                      k, row0, row0 + n_loc, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
                       wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip)));
     note_launch();
 }
 
 extern "C" void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc,
-                                            const double *logpf, const int32_t *row_ptr,
+                                            nemk_lpsrc lps, const int32_t *row_ptr,
                                             const int32_t *col, const float *wgt, double beta,
                                             const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty,
                                             int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt, int round,
@@ -1984,7 +2016,7 @@ extern "C" void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int 
     if (n_loc <= 0) return;
     int grid = num_sms() * 2;
     DISPATCH_K(k, (k_sweep_ncem_fixup_round<KT><<<grid, 256, 0, S(s)>>>(
-                      k, row0, row0 + n_loc, logpf, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
+                      k, row0, row0 + n_loc, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
                       wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip)));
     note_launch();
 }
@@ -2022,7 +2054,7 @@ extern "C" void nemk_graph_check(nemk_stream s, int n, int nnz, const int32_t *r
     note_launch();
 }
 
-extern "C" void nemk_sweep_ncem_level(nemk_stream s, int k, const double *logpf,
+extern "C" void nemk_sweep_ncem_level(nemk_stream s, int k, nemk_lpsrc lps,
                                       const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                       double beta, uint8_t *lab, const int32_t *sites,
                                       const int32_t *level_ptr, int lv_lo, int lv_hi, int grid_ctas,
@@ -2030,7 +2062,7 @@ extern "C" void nemk_sweep_ncem_level(nemk_stream s, int k, const double *logpf,
     int single_cta = grid_ctas <= 1;
     int grid = single_cta ? 1 : grid_ctas, threads = single_cta ? 1024 : 256;
     DISPATCH_K(k, (k_sweep_ncem_level<KT><<<grid, threads, 0, S(s)>>>(
-                      k, logpf, row_ptr, col, wgt, beta, lab, sites, level_ptr, lv_lo, lv_hi,
+                      k, lps, row_ptr, col, wgt, beta, lab, sites, level_ptr, lv_lo, lv_hi,
                       single_cta, cnt, skip)));
     note_launch();
 }
@@ -2139,7 +2171,7 @@ extern "C" void nemk_mstep_finalize_tables(nemk_stream s, int k, int n, int d, i
     note_launch();
 }
 
-extern "C" int nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, const double *logpf,
+extern "C" int nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                                      const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                      double beta, const uint8_t *lab, const float *t,
                                      const int32_t *heavy, int n_heavy, double *partials,
@@ -2149,7 +2181,7 @@ extern "C" int nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, 
     int hb = (row_ptr && lab && heavy && n_heavy > 0) ? cdiv((long long)n_heavy * 32, 256) : 0;
     if (hb > nblocks / 2) hb = nblocks / 2;
     if (nblocks < 2) hb = 0;
-    DISPATCH_K(k, (k_criteria_partial<KT><<<nblocks, 256, 0, S(s)>>>(k, row0, n_loc, logpf, row_ptr,
+    DISPATCH_K(k, (k_criteria_partial<KT><<<nblocks, 256, 0, S(s)>>>(k, row0, n_loc, lps, row_ptr,
                                                                     col, wgt, beta, lab, t, heavy,
                                                                     n_heavy, hb, partials)));
     note_launch();
