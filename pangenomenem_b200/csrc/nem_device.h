@@ -26,9 +26,11 @@ typedef struct {
                                    2 centre 1 everywhere (H = D - popc x), 3 all centres 1/2 (H = 0) */
     int32_t uniform_ok;         /* 1 when every class is popcount-eligible */
     int32_t empty_class;        /* 1-based index of an empty class (M-step) or 0 */
+    int32_t halt;               /* set by nemk_iter_end when the fit is over (converged, or an empty
+                                   class): every kernel of a later, speculatively enqueued iteration
+                                   returns at once.  Must follow empty_class (the `skip` pair). */
     int32_t mu_changed;         /* the class bit masks differ from the previous tables (or forced):
                                    the cached Hamming counts are stale, the density pass must run */
-    int32_t pad[1];
 } nemk_coef;
 
 /* Device scalars of one sweep / one iteration (host reads them back in one copy). */
@@ -41,6 +43,22 @@ typedef struct {
     int32_t pending;     /* row-sharded sweep: local sites queued by the last label exchange */
     int32_t pad[2];
 } nemk_counters;
+
+/* Device status block of one sweep / iteration, and the copy nemk_iter_end publishes into
+ * mapped pinned host memory (no memcpy, no stream synchronisation: the host polls `seq`). */
+typedef struct {
+    nemk_counters cnt;
+    double crit_before[6];
+    double crit_after[6];
+} nemk_iter_status;
+
+typedef struct {
+    nemk_counters cnt;             /* summed over the ranks (nfix, maxdiff: maximum) */
+    double crit_before[6];
+    double crit_after[6];
+    int32_t empty_class, mu_changed, halt, pad;
+    unsigned long long seq;        /* written last, after a system-wide fence */
+} nemk_host_status;
 
 typedef void *nemk_stream;
 
@@ -89,9 +107,18 @@ void nemk_graph_check(nemk_stream s, int n, int nnz, const int32_t *row_ptr, con
 void nemk_heavy_list(nemk_stream s, int row0, int n_loc, const int32_t *row_ptr,
                      int32_t *block_counts, int32_t *list, int32_t *total);
 
+/* ---- end of a sweep / an EM iteration: sum the ranks' counters, and when `decide` apply the
+ * convergence test on the device (HasConverged `clas`, nem_alg.c:2075-2089: ncem = no label
+ * changed, nem = max |t - t_old| < thr; conv: 0 none, 1 clas) and raise coef->halt when the fit is
+ * over (converged or empty class), then publish everything to the mapped host slot. */
+void nemk_iter_end(nemk_stream s, int world, const nemk_counters *cnt_all,
+                   const nemk_iter_status *st, nemk_coef *coef, int decide, int ncem, int conv,
+                   float thr, nemk_host_status *host_slot, unsigned long long seq);
+
 /* ---- E-step sweeps.  label 255 = unlabelled (the reference's calloc'd ClassifM row).
- * `skip` (nullable) points at a device flag; non-zero => the kernel returns at once (an empty
- * class was found by the M-step, the reference does not run the E-step then).
+ * `skip` (nullable) points at coef->empty_class: skip[0] = an empty class was found by the M-step
+ * (the reference does not run the E-step then), skip[1] = coef->halt; either non-zero => the
+ * kernel returns at once.
  * Row sharding: this rank owns the global rows [row0, row0+n_loc); labels, t, CSR, dirty flags and
  * work lists are indexed by GLOBAL family id, logpf by local row.  One GPU: row0 = 0, n_loc = N.
  * Work lists: wl_a/wl_b used alternately, wl_cnt[4] rotating counters (round r: list r&1). */
@@ -130,14 +157,14 @@ void nemk_sweep_nem_level(nemk_stream s, int k, const double *logpf, const int32
 /* ---- M-step */
 /* lab_m (nullable): receives a copy of the labels = the state the statistics now describe */
 void nemk_label_masks(nemk_stream s, int k, int n, int nwt, const uint8_t *lab, uint32_t *cm,
-                      int32_t *nk_int, uint8_t *lab_m);
+                      int32_t *nk_int, uint8_t *lab_m, const int32_t *halt);
 /* incremental ncem statistics: rows whose label differs from lab_m move their bits from
  * S[old] to S[new] (exact integer updates), then lab_m = lab.  list needs n ints + 1 counter */
 void nemk_mstep_delta(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x,
                       const uint8_t *lab, uint8_t *lab_m, int32_t *list, int32_t *count,
-                      int32_t *s_int, int32_t *nk_int);
+                      int32_t *s_int, int32_t *nk_int, const int32_t *halt);
 void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint32_t *xt, const uint32_t *cm,
-                     int32_t *s_int);
+                     int32_t *s_int, const int32_t *halt);
 void nemk_mstep_nem(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x, const float *t,
                     int rows_per_chunk, double *partial_s, double *partial_n, double *s_dbl,
                     double *nk_dbl);

@@ -29,14 +29,11 @@
 #define MAX_WORLD 64
 #define CRIT_BLOCKS_MAX 1184 /* 148 SMs x 8 */
 #define CRIT_BLOCKS_SHARD 296
+#define RING 4              /* status slots in mapped host memory */
 
 typedef struct { int lo, hi, grid; } sweep_step;
 
-typedef struct {
-    nemk_counters cnt;
-    double crit_before[6];
-    double crit_after[6];
-} iter_status;
+typedef nemk_iter_status iter_status;
 
 enum { ST_DENSITY = 0, ST_SWEEP = 1, ST_MSTEP = 2, ST_CRIT = 3, ST_DENSITY_CACHED = 4, ST_MSTEP_DELTA = 5, ST_NB = 6 };
 
@@ -92,6 +89,8 @@ struct nemb_handle {
     iter_status *d_status, *h_status;
     nemk_counters *d_cnt_all, *h_cnt_all;     /* [world] gathered sweep counters */
     int32_t *h_empty;
+    nemk_host_status *ring, *d_ring;          /* mapped pinned status slots, host / device view */
+    unsigned long long seq;                   /* last sequence number handed to nemk_iter_end */
     /* fit bookkeeping */
     int64_t launches, fixup_rounds, exchanges;
     int profile;
@@ -235,6 +234,7 @@ void nemb_destroy(nemb_handle *h)
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_cnt_all) cudaFreeHost(h->h_cnt_all);
     if (h->h_empty) cudaFreeHost(h->h_empty);
+    if (h->ring) cudaFreeHost(h->ring);
     for (int i = 0; i < h->ev_cap; i++) cudaEventDestroy(h->ev[i]);
     free(h->ev); free(h->ev_kind);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -568,6 +568,11 @@ static int ensure_k(nemb_handle *h, int k)
     if (!h->h_status) CK(cudaMallocHost((void **)&h->h_status, sizeof(iter_status)));
     if (!h->h_cnt_all) CK(cudaMallocHost((void **)&h->h_cnt_all, sizeof(nemk_counters) * MAX_WORLD));
     if (!h->h_empty) CK(cudaMallocHost((void **)&h->h_empty, 2 * sizeof(int32_t)));
+    if (!h->ring) {
+        CK(cudaHostAlloc((void **)&h->ring, sizeof(nemk_host_status) * RING, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h->ring, 0, sizeof(nemk_host_status) * RING);
+        CK(cudaHostGetDevicePointer((void **)&h->d_ring, h->ring, 0));
+    }
     h->k_alloc = k;
     return NEMB_OK;
 }
@@ -719,15 +724,51 @@ static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming, i
     return NEMB_OK;
 }
 
-/* counters of the last sweep, summed over the ranks, on the host (one sync) */
-static int read_status(nemb_handle *h)
+/* End of a sweep / iteration: (all-gather of the ranks' counters,) one tiny kernel that sums them,
+ * decides convergence when `o` is given (EM iteration; it raises the device halt flag) and writes
+ * the status block into a mapped pinned slot.  Returns the sequence number to wait for. */
+static int publish_status(nemb_handle *h, const nemb_options *o, unsigned long long *seq_out)
 {
-    int rc = gather(h, &h->d_status->cnt, h->d_cnt_all, sizeof(nemk_counters));
-    if (rc != NEMB_OK) return rc;
-    CK(cudaMemcpyAsync(h->h_cnt_all, h->d_cnt_all, sizeof(nemk_counters) * h->world, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    const nemk_counters *cnt_all = &h->d_status->cnt;
+    if (h->world > 1) {
+        int rc = gather(h, &h->d_status->cnt, h->d_cnt_all, sizeof(nemk_counters));
+        if (rc != NEMB_OK) return rc;
+        cnt_all = h->d_cnt_all;
+    }
+    unsigned long long seq = ++h->seq;
+    int decide = o && o->conv != NEMB_CONV_CRIT;
+    nemk_iter_end(h->stream, h->world, cnt_all, h->d_status, h->d_coef, decide,
+                  o ? o->algo == NEMB_ALGO_NCEM : 0, o ? o->conv : 0, o ? o->conv_thr : 0.f,
+                  h->d_ring + (seq % RING), seq);
+    h->launches++;
+    CKK();
+    *seq_out = seq;
+    return NEMB_OK;
+}
+
+/* spin on the slot's sequence number (the kernel wrote it after a system-wide fence) */
+static int wait_status(nemb_handle *h, unsigned long long seq)
+{
+    volatile nemk_host_status *s = &h->ring[seq % RING];
+    for (unsigned spins = 1; s->seq != seq; spins++) {
+        if ((spins & 0xfff) == 0) {
+            cudaError_t e = cudaStreamQuery(h->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return fail(h, NEMB_E_CUDA, "device error while waiting for the status: %s", cudaGetErrorString(e));
+            if (e == cudaSuccess && s->seq != seq)
+                return fail(h, NEMB_E_BUG, "stream drained without status %llu (slot holds %llu)", seq, (unsigned long long)s->seq);
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    const nemk_host_status *r = &h->ring[seq % RING];
+    h->h_status->cnt = r->cnt;
+    memcpy(h->h_status->crit_before, r->crit_before, sizeof r->crit_before);
+    memcpy(h->h_status->crit_after, r->crit_after, sizeof r->crit_after);
+    h->h_empty[0] = r->empty_class;
+    h->h_empty[1] = r->mu_changed;
     /* h_empty[1] = coef->mu_changed of the last tables: 0 => the last popcount density pass did
      * not read X (cached Hamming counts) */
     if (h->profile && h->ham_valid && h->ev_last_density >= 0 && h->ev_last_cached >= 0) {
@@ -738,26 +779,25 @@ static int read_status(nemb_handle *h)
         if (!h->h_empty[1]) h->ev_kind[h->ev_last_density] = ST_DENSITY_CACHED;   /* X not read */
         h->ev_last_density = -1;
     }
-    nemk_counters tot;
-    memset(&tot, 0, sizeof tot);
-    for (int r = 0; r < h->world; r++) {
-        const nemk_counters *c = &h->h_cnt_all[r];
-        tot.changed += c->changed; tot.allnul += c->allnul; tot.ties += c->ties;
-        tot.pending += c->pending;
-        if (c->nfix > tot.nfix) tot.nfix = c->nfix;
-        if (c->maxdiff > tot.maxdiff) tot.maxdiff = c->maxdiff;
-    }
-    h->h_status->cnt = tot;
     return NEMB_OK;
+}
+
+/* counters of the last sweep, summed over the ranks, on the host */
+static int read_status(nemb_handle *h)
+{
+    unsigned long long seq;
+    int rc = publish_status(h, NULL, &seq);
+    if (rc != NEMB_OK) return rc;
+    return wait_status(h, seq);
 }
 
 /* jacobi round 0 left the first work list in list 0 / counter 0: three grid-wide rounds, then
  * one CTA walks the tail to exhaustion (and leaves the four counters at 0) */
-enum { GRID_ROUNDS = 3, SHORT_LIST = 4096 };
+enum { GRID_ROUNDS = 3, SHORT_LIST = 32768 };
 static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, uint8_t *out,
                          const int32_t *rp, const int32_t *skip)
 {
-    /* few labels moved last iteration => the work lists are short: one CTA walks them all */
+    /* few labels moved last iteration => the work lists are short: the tail cluster walks them all */
     int grid_rounds = (h->last_changed >= 0 && h->last_changed < SHORT_LIST) ? 0 : GRID_ROUNDS;
     for (int r = 0; r < grid_rounds; r++)
         nemk_sweep_ncem_fixup_round(h->stream, k, h->row0, h->n, lpsrc(h), rp, h->d_col, h->d_wgt,
@@ -871,12 +911,14 @@ static int run_mstep(nemb_handle *h, const nemb_options *o, int next_uniform)
         const uint8_t *lab_loc = h->d_lab[h->cur] + h->row0;
         if (incremental) {
             nemk_mstep_delta(h->stream, k, h->n, h->d, h->wpr, h->d_x, lab_loc, h->d_lab[3],
-                             h->d_wl[1], &h->d_wl_counts[4], h->d_stat_loc, h->d_stat_loc + kd);
+                             h->d_wl[1], &h->d_wl_counts[4], h->d_stat_loc, h->d_stat_loc + kd,
+                             &h->d_coef->halt);
         } else {
             if ((rc = ensure_xt(h)) != NEMB_OK) return rc;
             nemk_label_masks(h->stream, k, h->n, h->nwt, lab_loc, h->d_cm, h->d_stat_loc + kd,
-                             h->d_lab[3]);
-            nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_stat_loc);
+                             h->d_lab[3], &h->d_coef->halt);
+            nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_stat_loc,
+                            &h->d_coef->halt);
             h->stats_valid = 1;
         }
         h->launches += 2;
@@ -965,7 +1007,7 @@ static int init_state(nemb_handle *h, const nemb_options *o)
         CK(cudaMemsetAsync(h->d_t[0], 0, sizeof(float) * (size_t)h->lab_len * o->k, h->stream));
         CK(cudaMemsetAsync(h->d_t[1], 0, sizeof(float) * (size_t)h->lab_len * o->k, h->stream));
     }
-    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
     return NEMB_OK;
 }
 
@@ -1002,19 +1044,40 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
         }
     }
 
-    int iter, converged = 0, status = NEMB_OK, empty = 0;
-    for (iter = 1; iter <= o->it_max && !converged && status == NEMB_OK; iter++) {
-        if (!o->param_fixed && (rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
-        if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
-        if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
-        if ((rc = run_sweep(h, o, beta, &flipped)) != NEMB_OK) return rc;
-        if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
-        if (cb) {
-            CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+    /* EM loop.  One iteration = M-step, densities, sweep, then nemk_iter_end: the convergence
+     * test runs on the device and the status lands in mapped host memory, so the host neither
+     * copies nor synchronises -- and once the fit is in its steady state (incremental M-step) the
+     * NEXT iteration is enqueued before this one's status is known.  If this one ends the fit, the
+     * device halt flag turns every kernel of the speculative iteration into a no-op and its
+     * host-side effects (buffer flip) are undone below. */
+    int iter = 0, enq = 0, converged = 0, status = NEMB_OK, empty = 0;
+    int flips[2] = {0, 0};
+    unsigned long long seqs[2] = {0, 0};
+    int can_spec = !o->dolog && !cb && !want_crit_each && !h->profile && h->world == 1 &&
+                   o->algo == NEMB_ALGO_NCEM && !o->param_fixed && !getenv("NEM_B200_NO_SPEC");
+    while (iter < o->it_max && !converged && status == NEMB_OK) {
+        int want = iter + 1;
+        if (can_spec && want < o->it_max && h->stats_valid && h->last_changed >= 0 &&
+            h->last_changed <= h->n / 8)
+            want++;
+        for (; enq < want; enq++) {
+            if (!o->param_fixed && (rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
+            if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
+            if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
+            if ((rc = run_sweep(h, o, beta, &flipped)) != NEMB_OK) return rc;
+            if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
+            if (cb) {
+                CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+            }
+            flips[enq & 1] = flipped;
+            if ((rc = publish_status(h, o, &seqs[enq & 1])) != NEMB_OK) return rc;
         }
-        if ((rc = read_status(h)) != NEMB_OK) return rc;
+        if ((rc = wait_status(h, seqs[iter & 1])) != NEMB_OK) return rc;
+        if (cb) CK(cudaStreamSynchronize(h->stream));   /* theta copies of this iteration */
+        flipped = flips[iter & 1];
+        iter++;
         h->last_changed = o->algo == NEMB_ALGO_NCEM ? h->h_status->cnt.changed : -1;
         empty = *h->h_empty;
         if (empty) {              /* nem_alg.c:1831-1838: E-step not run, loop ends */
@@ -1050,7 +1113,12 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
             cb(user, iter, h->h_status->crit_before, h->h_status->crit_after, prop, center, disp, nk_host);
         }
     }
-    iter -= 1;
+    if (enq > iter) {
+        /* the speculative iteration behind the last one: a no-op on the device if the fit ended
+         * (halt), otherwise (it_max cannot be hit here: want < it_max) it must not exist */
+        if (!(converged || status != NEMB_OK)) return fail(h, NEMB_E_BUG, "speculative iteration left over");
+        if (flips[(enq - 1) & 1]) h->cur ^= 1;
+    }
     if (iter == 0) { /* nem_alg.c:1845-1851 */
         if ((rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
         if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
@@ -1222,7 +1290,7 @@ static int upload_theta(nemb_handle *h, int k, const float *prop, const float *c
     CK(cudaMemcpyAsync(h->d_prop, prop, sizeof(float) * k, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_center, center, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_disp, disp, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
     return NEMB_OK;
 }
 
@@ -1282,7 +1350,7 @@ int nemb_stage_sweep(nemb_handle *h, const nemb_options *o, const double *logpf,
     size_t nk = (size_t)h->n * o->k;
     CK(cudaMemcpyAsync(h->d_logpf, logpf, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
     h->lp_from_ham = 0;
-    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
     if ((rc = upload_state(h, o, t_inout)) != NEMB_OK) return rc;
     if ((rc = run_sweep(h, o, h->spatial ? (double)beta : 0.0, &flipped)) != NEMB_OK) return rc;
     if ((rc = read_status(h)) != NEMB_OK) return rc;
@@ -1393,6 +1461,7 @@ int nemb_fit_random(nemb_handle *h, const nemb_options *o, int n_starts, int64_t
     CK(cudaMemsetAsync(h->d_lab[0], 0, n, h->stream));
     if (!h->state_labels) { nemk_labels_to_t(h->stream, k, n, h->d_lab[0], h->d_t[0]); CKK(); }
     h->stats_valid = 0; h->ham_valid = 0;
+    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
     if ((rc = run_mstep(h, o, 0)) != NEMB_OK) return rc;
     CK(cudaMemcpyAsync(sam, h->d_disp, sizeof(float) * d, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1444,6 +1513,7 @@ int nemb_fit_random(nemb_handle *h, const nemb_options *o, int n_starts, int64_t
         CK(cudaMemcpyAsync(o->algo == NEMB_ALGO_NCEM ? (void *)h->d_lab[0] : (void *)h->d_t[0],
                            best_state, state_bytes, cudaMemcpyDeviceToDevice, h->stream));
         h->stats_valid = 0; h->ham_valid = 0;
+        CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
         if ((rc = run_mstep(h, o, 0)) != NEMB_OK) return rc;   /* final EstimPara, nem_alg.c:1715 */
         CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));

@@ -284,7 +284,7 @@ k_density_uniform(int K, const uint4 *__restrict__ x, int n, int wpr4,
                   const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
                   const uint4 *__restrict__ mval, double *__restrict__ logpf,
                   int32_t *__restrict__ hamming, int cached) {
-    if (coef->empty_class) return;  // M-step found an empty class: E-step is not run
+    if (coef->empty_class | coef->halt) return;  // M-step found an empty class (E-step not run) / fit over
     if (cached && !coef->mu_changed) return;
     extern __shared__ uint4 smem[];
     uint4 *sx = smem, *sv = smem + (size_t)KT * wpr4;
@@ -399,7 +399,7 @@ k_density_tma(int K, int D, const uint4 *__restrict__ x, int n, int wpr4, int st
               int n_stages, const nemk_coef *__restrict__ coef, const uint4 *__restrict__ mxor,
               const uint4 *__restrict__ mval, double *__restrict__ logpf,
               int32_t *__restrict__ hamming, int cached) {
-    if (coef->empty_class) return;
+    if (coef->empty_class | coef->halt) return;
     if (cached && !coef->mu_changed) return;   // H cache still valid: k_logpf_from_h does the work
     extern __shared__ __align__(128) uint4 dsm[];
     __shared__ __align__(8) uint64_t bars[16];
@@ -542,7 +542,7 @@ k_density_general(int K, const uint32_t *__restrict__ x, int n, int D, int wpr,
                   const uint32_t *__restrict__ f0, const uint32_t *__restrict__ f1,
                   const double *__restrict__ delta, const double *__restrict__ base_g,
                   double *__restrict__ logpf) {
-    if (coef->empty_class) return;
+    if (coef->empty_class | coef->halt) return;
     int lane = threadIdx.x & 31;
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -725,7 +725,7 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
                     const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
                     const int32_t *__restrict__ heavy, int n_heavy, int heavy_blocks,
                     nemk_counters *cnt, const int32_t *__restrict__ skip) {
-    if (skip && *skip) return;
+    if (skip && (skip[0] | skip[1])) return;
     const int lane = threadIdx.x & 31;
     int changed = 0, flags = 0;
     if ((int)blockIdx.x < heavy_blocks) {
@@ -890,7 +890,7 @@ k_sweep_ncem_fixup_round(int K, int row0, int row1, const nemk_lpsrc lps,
                          int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt, int round,
                          const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
                          nemk_counters *cnt, const int32_t *__restrict__ skip) {
-    if (skip && *skip) return;
+    if (skip && (skip[0] | skip[1])) return;
     const int32_t *cur_list = (round & 1) ? wl_b : wl_a;
     int32_t *next_list = (round & 1) ? wl_a : wl_b;
     int count = wl_cnt[round & 3];
@@ -906,8 +906,12 @@ k_sweep_ncem_fixup_round(int K, int row0, int row1, const nemk_lpsrc lps,
     if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(&cnt->nfix, 1);
 }
 
+// Tail of the fix-up rounds in ONE launch: a thread-block cluster of FX_CLUSTER CTAs loops over the
+// rounds with a hardware cluster barrier between them (release/acquire at cluster scope, after a
+// device fence for the label/work-list stores) until the work list is empty.
+#define FX_CLUSTER 8
 template <int KT>
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(FX_CLUSTER, 1, 1) __launch_bounds__(1024)
 k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_old,
@@ -915,29 +919,30 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
                    int32_t *wl_cnt, int round, const int32_t *__restrict__ rrow_ptr,
                    const int32_t *__restrict__ rcol, nemk_counters *cnt,
                    const int32_t *__restrict__ skip) {
-    if (skip && *skip) return;
-    __shared__ int s_count;
+    if (skip && (skip[0] | skip[1])) return;
+    namespace cgx = cooperative_groups;
+    cgx::cluster_group cluster = cgx::this_cluster();
+    const int crank = (int)cluster.block_rank();
     int rounds = 0, dchanged = 0;
     for (;; round++) {
         int32_t *cur_list = (round & 1) ? wl_b : wl_a, *next_list = (round & 1) ? wl_a : wl_b;
         int32_t *next_cnt = &wl_cnt[(round + 1) & 3];
-        if (threadIdx.x == 0) {
-            s_count = *(volatile int32_t *)&wl_cnt[round & 3];
-            *next_cnt = 0;
-        }
-        __syncthreads();
-        int count = s_count;
+        // nobody appends to list round&1 during this round: every thread reads the same count
+        int count = *(volatile int32_t *)&wl_cnt[round & 3];
+        if (crank == 0 && threadIdx.x == 0) wl_cnt[(round + 2) & 3] = 0;   // idle counter
         if (count == 0) break;
         rounds++;
-        for (int base = threadIdx.x & ~31; base < count; base += blockDim.x)
+        for (int base = crank * 1024 + (threadIdx.x & ~31); base < count; base += FX_CLUSTER * 1024)
             dchanged += fixup_items<KT>(K, base + (threadIdx.x & 31), count, cur_list, row0, row1,
                                         lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
                                         next_list, next_cnt, rrow_ptr, rcol);
-        __syncthreads();
+        __threadfence();
+        cluster.sync();
     }
-    if (threadIdx.x < 4) wl_cnt[threadIdx.x] = 0;
+    cluster.sync();   // every CTA has read the last (zero) count
+    if (crank == 0 && threadIdx.x < 4) wl_cnt[threadIdx.x] = 0;
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
-    if (threadIdx.x == 0 && rounds) atomicAdd(&cnt->nfix, rounds);
+    if (crank == 0 && threadIdx.x == 0 && rounds) atomicAdd(&cnt->nfix, rounds);
 }
 
 // Row-sharded sweep, after a label exchange: every remote site whose label differs from the one
@@ -976,7 +981,7 @@ k_sweep_ncem_level(int K, const nemk_lpsrc lps, const int32_t *__restrict__ row_
                    uint8_t *lab, const int32_t *__restrict__ sites,
                    const int32_t *__restrict__ level_ptr, int lv_lo, int lv_hi, int single_cta,
                    nemk_counters *cnt, const int32_t *__restrict__ skip) {
-    if (skip && *skip) return;
+    if (skip && (skip[0] | skip[1])) return;
     const volatile uint8_t *vlab = lab;
     int changed = 0, nul = 0, ties = 0;
     for (int lv = lv_lo; lv < lv_hi; lv++) {
@@ -1065,7 +1070,7 @@ k_sweep_nem_jacobi(int K, int row0, int n_loc, const double *__restrict__ logpf,
                    const float *__restrict__ wgt, double beta, const float *__restrict__ t_in,
                    float *__restrict__ t_out, nemk_counters *cnt,
                    const int32_t *__restrict__ skip) {
-    if (skip && *skip) return;
+    if (skip && (skip[0] | skip[1])) return;
     int il = blockIdx.x * blockDim.x + threadIdx.x;
     int i = row0 + il;
     float md = 0.f;
@@ -1095,7 +1100,7 @@ k_sweep_nem_level(int K, const double *__restrict__ logpf, const int32_t *__rest
                   float *t, const int32_t *__restrict__ sites, const int32_t *__restrict__ level_ptr,
                   int lv_lo, int lv_hi, int single_cta, nemk_counters *cnt,
                   const int32_t *__restrict__ skip) {
-    if (skip && *skip) return;
+    if (skip && (skip[0] | skip[1])) return;
     float md = 0.f;
     int nul = 0;
     for (int lv = lv_lo; lv < lv_hi; lv++) {
@@ -1130,8 +1135,9 @@ k_sweep_nem_level(int K, const double *__restrict__ logpf, const int32_t *__rest
 template <int KT>
 __global__ void __launch_bounds__(256)
 k_label_masks(int K, int n, int nwt, const uint8_t *__restrict__ lab, uint32_t *__restrict__ cm,
-              int32_t *nk, uint8_t *__restrict__ lab_m) {
+              int32_t *nk, uint8_t *__restrict__ lab_m, const int32_t *__restrict__ halt) {
     __shared__ int snk[KT];
+    if (halt && *halt) return;
     if (threadIdx.x < KT) snk[threadIdx.x] = 0;
     __syncthreads();
     int lane = threadIdx.x & 31;
@@ -1160,7 +1166,8 @@ k_label_masks(int K, int n, int nwt, const uint8_t *__restrict__ lab, uint32_t *
 template <int KT, int MU>
 __global__ void __launch_bounds__(256)
 k_mstep_ncem(int K, int D, int nwt4, const uint4 *__restrict__ xt, const uint4 *__restrict__ cm,
-             int dchunk, int32_t *S) {
+             int dchunk, int32_t *S, const int32_t *__restrict__ halt) {
+    if (halt && *halt) return;
     int lane = threadIdx.x & 31;
     int warp_in_block = threadIdx.x >> 5;
     int wg = blockIdx.x * (blockDim.x >> 5) + warp_in_block;  // word group: 32*MU uint4
@@ -1212,7 +1219,8 @@ k_mstep_ncem(int K, int D, int nwt4, const uint4 *__restrict__ xt, const uint4 *
 // result equals the full recount whatever the order.
 __global__ void __launch_bounds__(256)
 k_changed_rows(int n, const uint8_t *__restrict__ lab, const uint8_t *__restrict__ lab_m,
-               int32_t *list, int32_t *count) {
+               int32_t *list, int32_t *count, const int32_t *__restrict__ halt) {
+    if (halt && *halt) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool ch = i < n && lab[i] != lab_m[i];
     unsigned m = __ballot_sync(FULL, ch);
@@ -1231,7 +1239,9 @@ template <int KT>
 __global__ void __launch_bounds__(256)
 k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8_t *__restrict__ lab,
               const uint8_t *__restrict__ lab_m, const int32_t *__restrict__ list,
-              const int32_t *__restrict__ count, int32_t *S, int32_t *nk) {
+              const int32_t *__restrict__ count, int32_t *S, int32_t *nk,
+              const int32_t *__restrict__ halt) {
+    if (halt && *halt) return;
     const int lane = threadIdx.x & 31;
     const int total = *count;
     const int groups = (total + 31) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
@@ -1293,7 +1303,9 @@ k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8
 // lab_m <- lab for the rows of the list (after every item of k_mstep_delta has read lab_m)
 __global__ void __launch_bounds__(256)
 k_commit_labels(const uint8_t *__restrict__ lab, uint8_t *__restrict__ lab_m,
-                const int32_t *__restrict__ list, const int32_t *__restrict__ count) {
+                const int32_t *__restrict__ list, const int32_t *__restrict__ count,
+                const int32_t *__restrict__ halt) {
+    if (halt && *halt) return;
     int total = *count;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         int row = list[idx];
@@ -1395,8 +1407,6 @@ __global__ void k_mstep_nem_reduce(int K, int D, int nchunks, const double *__re
 // order => reproducible), with two cluster barriers instead of a second kernel launch.
 // The models that pool classes (s_d, s__) recompute the other classes' inertia from S and n.
 namespace cg = cooperative_groups;
-#define FT_CLUSTER 8
-#define FT_THREADS 512
 
 static __device__ __forceinline__ float iner_of(double s, double n, bool nonempty, float mu_keep) {
     // EstimLaplaceCenters / ComputeMedian then EstimLaplaceIner; an empty class keeps its centre
@@ -1407,12 +1417,12 @@ static __device__ __forceinline__ float iner_of(double s, double n, bool nonempt
 }
 
 // sum of v[0..NV) over the cluster; every thread of every CTA gets the totals (rank order)
-template <int NV>
+template <int NV, int TH>
 static __device__ __forceinline__ void cluster_sum(cg::cluster_group &cluster, double (&v)[NV],
                                                    double *sh /*[32]*/, double *slot /*[NV] smem*/) {
 #pragma unroll
     for (int q = 0; q < NV; q++) {
-        double r = block_sum<FT_THREADS>(v[q], sh);
+        double r = block_sum<TH>(v[q], sh);
         if (threadIdx.x == 0) slot[q] = r;
     }
     cluster.sync();
@@ -1425,7 +1435,9 @@ static __device__ __forceinline__ void cluster_sum(cg::cluster_group &cluster, d
     cluster.sync();   // slots may be rewritten
 }
 
-__global__ void __cluster_dims__(FT_CLUSTER, 1, 1) __launch_bounds__(FT_THREADS)
+// CL CTAs per class (launched as a cluster of CL through cudaLaunchKernelEx), TH threads per CTA
+template <int CL, int TH>
+__global__ void __launch_bounds__(TH)
 k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_model,
                         const int32_t *__restrict__ s_int, const int32_t *__restrict__ nk_int,
                         const double *__restrict__ s_dbl, const double *__restrict__ nk_dbl,
@@ -1436,9 +1448,10 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
     __shared__ double slot[8];
     __shared__ float nkf[NEMB_MAX_K];
     __shared__ double nkd[NEMB_MAX_K];
+    if (coef->halt) return;   // uniform over the launch: only k_iter_end (another launch) writes it
     cg::cluster_group cluster = cg::this_cluster();
-    const int tid = threadIdx.x, k = blockIdx.x / FT_CLUSTER, part = blockIdx.x % FT_CLUSTER;
-    const int wreal = (D + 31) >> 5, wper = (wreal + FT_CLUSTER - 1) / FT_CLUSTER;
+    const int tid = threadIdx.x, k = blockIdx.x / CL, part = blockIdx.x % CL;
+    const int wreal = (D + 31) >> 5, wper = (wreal + CL - 1) / CL;
     const int w_lo = min(wreal, part * wper), w_hi = min(wreal, w_lo + wper);
     const int j_lo = w_lo * 32, j_hi = min(D, w_hi * 32);
     if (tid < K) {
@@ -1460,17 +1473,17 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
     const bool nonempty = (double)nkf[k] > NEM_EPSILON;
     // centres of this class (this CTA's genomes)
     if (nonempty)
-        for (int j = j_lo + tid; j < j_hi; j += FT_THREADS) {
+        for (int j = j_lo + tid; j < j_hi; j += TH) {
             double s = S_of(k, j), half = 0.5 * nkd[k];
             center[(size_t)k * D + j] = s > half ? 1.0f : (s < half ? 0.0f : 0.5f);
         }
     // dispersions of this class
     if (disp_model == 3) {  // skd: nem_mod.c:1152-1170
         if (nonempty)
-            for (int j = j_lo + tid; j < j_hi; j += FT_THREADS)
+            for (int j = j_lo + tid; j < j_hi; j += TH)
                 disp[(size_t)k * D + j] = __fdiv_rn(iner_of(S_of(k, j), nkd[k], true, 0.f), nkf[k]);
     } else if (disp_model == 2) {  // s_d: nem_mod.c:1104-1126, float sums over the classes in order
-        for (int j = j_lo + tid; j < j_hi; j += FT_THREADS) {
+        for (int j = j_lo + tid; j < j_hi; j += TH) {
             float si = 0.f, sn = 0.f;
             for (int c = 0; c < K; c++) {
                 bool ne = (double)nkf[c] > NEM_EPSILON;
@@ -1483,23 +1496,23 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
         double v[1] = {0.0};
         double sn = 0.0;
         if (disp_model == 1) {
-            for (int j = j_lo + tid; j < j_hi; j += FT_THREADS)
+            for (int j = j_lo + tid; j < j_hi; j += TH)
                 v[0] += (double)iner_of(S_of(k, j), nkd[k], nonempty, nonempty ? 0.f : center[(size_t)k * D + j]);
             sn = (double)nkf[k] * (double)D;
         } else {
             for (int c = 0; c < K; c++) {
                 if (nkf[c] > 0.f) {
                     bool ne = (double)nkf[c] > NEM_EPSILON;
-                    for (int j = j_lo + tid; j < j_hi; j += FT_THREADS)
+                    for (int j = j_lo + tid; j < j_hi; j += TH)
                         v[0] += (double)iner_of(S_of(c, j), nkd[c], ne, ne ? 0.f : center[(size_t)c * D + j]);
                     sn += (double)nkf[c] * (double)D;
                 }
             }
         }
-        cluster_sum<1>(cluster, v, sh, slot);
+        cluster_sum<1, TH>(cluster, v, sh, slot);
         if (disp_model == 0 || nkf[k] > 0.f) {
             float dk = __fdiv_rn((float)v[0], (float)sn);
-            for (int j = j_lo + tid; j < j_hi; j += FT_THREADS) disp[(size_t)k * D + j] = dk;
+            for (int j = j_lo + tid; j < j_hi; j += TH) disp[(size_t)k * D + j] = dk;
         }
     }
     if (part == 0 && tid == 0)  // nem_mod.c:456-465
@@ -1512,13 +1525,13 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
                                    mask_f0, mask_f1, delta);
     // padding words [wreal, wpr) of the masks carry no genome: part 0 keeps them clean
     if (part == 0)
-        for (int w = wreal + tid; w < wpr; w += FT_THREADS) {
+        for (int w = wreal + tid; w < wpr; w += TH) {
             size_t o = (size_t)k * wpr + w;
             mask_xor[o] = 0u; mask_valid[o] = 0u; mask_f0[o] = 0u; mask_f1[o] = 0u;
         }
     if (p.mu_moved) atomicOr(&coef->mu_changed, 1);   // preset by the launcher (0, or 1 = forced)
     double v[5] = {p.base_u, p.base_g, (double)p.notok, (double)p.n_valid, (double)p.n_x1};
-    cluster_sum<5>(cluster, v, sh, slot);
+    cluster_sum<5, TH>(cluster, v, sh, slot);
     if (part == 0 && tid == 0)
         tables_commit(k, K, D, prop, coef, delta, cc, v[0], v[1], v[2] == 0.0, (int)v[3], (int)v[4]);
 }
@@ -1745,6 +1758,44 @@ k_graph_check(int n, int nnz, const int32_t *__restrict__ row_ptr,
 }
 
 // =============================================================================================
+// End of a sweep / an EM iteration: counters summed over the ranks, the `clas` convergence test
+// (HasConverged, nem_alg.c:2075-2089) decided on the device, coef->halt raised when the fit is over,
+// and the whole status block published into mapped pinned host memory.  The host polls `seq`: no
+// memcpy, no stream synchronisation, and it may already have enqueued the next iteration (whose
+// kernels all return at once when halt is set).
+// =============================================================================================
+__global__ void k_iter_end(int world, const nemk_counters *__restrict__ cnt_all,
+                           const nemk_iter_status *__restrict__ st, nemk_coef *coef, int decide,
+                           int ncem, int conv, float thr, nemk_host_status *host,
+                           unsigned long long seq) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    nemk_counters tot;
+    tot.changed = 0; tot.nfix = 0; tot.allnul = 0; tot.ties = 0; tot.maxdiff = 0.f; tot.pending = 0;
+    tot.pad[0] = 0; tot.pad[1] = 0;
+    for (int r = 0; r < world; r++) {
+        nemk_counters c = cnt_all[r];
+        tot.changed += c.changed; tot.allnul += c.allnul; tot.ties += c.ties; tot.pending += c.pending;
+        tot.nfix = max(tot.nfix, c.nfix);
+        tot.maxdiff = fmaxf(tot.maxdiff, c.maxdiff);
+    }
+    int halt = coef->halt, empty = coef->empty_class;
+    if (decide && !halt) {
+        bool converged = false;
+        if (conv == 1) {
+            float md = ncem ? (tot.changed ? 1.0f : 0.0f) : tot.maxdiff;
+            converged = md < thr;
+        }
+        if (converged || empty) { halt = 1; coef->halt = 1; }
+    }
+    host->cnt = tot;
+#pragma unroll
+    for (int q = 0; q < 6; q++) { host->crit_before[q] = st->crit_before[q]; host->crit_after[q] = st->crit_after[q]; }
+    host->empty_class = empty; host->mu_changed = coef->mu_changed; host->halt = halt; host->pad = 0;
+    __threadfence_system();
+    *(volatile unsigned long long *)&host->seq = seq;
+}
+
+// =============================================================================================
 // small helpers
 // =============================================================================================
 __global__ void k_labels_to_t(int K, int n, const uint8_t *__restrict__ lab, float *__restrict__ t) {
@@ -1917,7 +1968,7 @@ template <int KT>
 __global__ void __launch_bounds__(256)
 k_logpf_from_h(int K, int n, const nemk_coef *__restrict__ coef, const int32_t *__restrict__ hamming,
                double *__restrict__ logpf) {
-    if (coef->empty_class || coef->mu_changed) return;
+    if (coef->empty_class | coef->halt | coef->mu_changed) return;
     size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= (size_t)n * K) return;
     int k = (int)(q % K);
@@ -2000,7 +2051,7 @@ extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc,
                                       int round, const int32_t *rrow_ptr, const int32_t *rcol,
                                       nemk_counters *cnt, const int32_t *skip) {
     if (n_loc <= 0) return;
-    DISPATCH_K(k, (k_sweep_ncem_fixup<KT><<<1, 1024, 0, S(s)>>>(
+    DISPATCH_K(k, (k_sweep_ncem_fixup<KT><<<FX_CLUSTER, 1024, 0, S(s)>>>(
                       k, row0, row0 + n_loc, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
                       wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip)));
     note_launch();
@@ -2014,7 +2065,7 @@ extern "C" void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int 
                                             const int32_t *rrow_ptr, const int32_t *rcol,
                                             nemk_counters *cnt, const int32_t *skip) {
     if (n_loc <= 0) return;
-    int grid = num_sms() * 2;
+    int grid = num_sms() * 8;   // CTAs beyond the list return at once; long lists need the threads
     DISPATCH_K(k, (k_sweep_ncem_fixup_round<KT><<<grid, 256, 0, S(s)>>>(
                       k, row0, row0 + n_loc, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
                       wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip)));
@@ -2090,18 +2141,26 @@ extern "C" void nemk_sweep_nem_level(nemk_stream s, int k, const double *logpf,
     note_launch();
 }
 
+extern "C" void nemk_iter_end(nemk_stream s, int world, const nemk_counters *cnt_all,
+                              const nemk_iter_status *st, nemk_coef *coef, int decide, int ncem,
+                              int conv, float thr, nemk_host_status *host_slot,
+                              unsigned long long seq) {
+    k_iter_end<<<1, 32, 0, S(s)>>>(world, cnt_all, st, coef, decide, ncem, conv, thr, host_slot, seq);
+    note_launch();
+}
+
 extern "C" void nemk_label_masks(nemk_stream s, int k, int n, int nwt, const uint8_t *lab,
-                                 uint32_t *cm, int32_t *nk_int, uint8_t *lab_m) {
+                                 uint32_t *cm, int32_t *nk_int, uint8_t *lab_m, const int32_t *halt) {
     cudaMemsetAsync(nk_int, 0, (size_t)k * sizeof(int32_t), S(s));
     if (n <= 0) return;
     int grid = cdiv((long long)nwt * 32, 256);
     if (grid > num_sms() * 8) grid = num_sms() * 8;
-    DISPATCH_K(k, (k_label_masks<KT><<<grid, 256, 0, S(s)>>>(k, n, nwt, lab, cm, nk_int, lab_m)));
+    DISPATCH_K(k, (k_label_masks<KT><<<grid, 256, 0, S(s)>>>(k, n, nwt, lab, cm, nk_int, lab_m, halt)));
     note_launch();
 }
 
 extern "C" void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint32_t *xt,
-                                const uint32_t *cm, int32_t *s_int) {
+                                const uint32_t *cm, int32_t *s_int, const int32_t *halt) {
     cudaMemsetAsync(s_int, 0, (size_t)k * d * sizeof(int32_t), S(s));
     int nwt4 = nwt / 4;
     if (nwt4 <= 0 || d <= 0) return;
@@ -2119,7 +2178,7 @@ extern "C" void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint
     int dchunk = cdiv(d, ny);
     ny = cdiv(d, dchunk);
     dim3 grid(gx, ny);
-#define MS(KTT, MUU) k_mstep_ncem<KTT, MUU><<<grid, 256, 0, S(s)>>>(k, d, nwt4, (const uint4 *)xt, (const uint4 *)cm, dchunk, s_int)
+#define MS(KTT, MUU) k_mstep_ncem<KTT, MUU><<<grid, 256, 0, S(s)>>>(k, d, nwt4, (const uint4 *)xt, (const uint4 *)cm, dchunk, s_int, halt)
     if (mu >= 4) { if (k <= 2) MS(2, 4); else if (k == 3) MS(3, 4); else MS(4, 4); }
     else if (mu == 2) { if (k <= 2) MS(2, 2); else if (k == 3) MS(3, 2); else if (k == 4) MS(4, 2); else MS(8, 2); }
     else { DISPATCH_K(k, (MS(KT, 1))); }
@@ -2129,16 +2188,16 @@ extern "C" void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint
 
 extern "C" void nemk_mstep_delta(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x,
                                  const uint8_t *lab, uint8_t *lab_m, int32_t *list, int32_t *count,
-                                 int32_t *s_int, int32_t *nk_int) {
+                                 int32_t *s_int, int32_t *nk_int, const int32_t *halt) {
     if (n <= 0) return;
     cudaMemsetAsync(count, 0, sizeof(int32_t), S(s));
-    k_changed_rows<<<cdiv(n, 256), 256, 0, S(s)>>>(n, lab, lab_m, list, count);
+    k_changed_rows<<<cdiv(n, 256), 256, 0, S(s)>>>(n, lab, lab_m, list, count, halt);
     note_launch();
     int grid = num_sms() * 4;
     DISPATCH_K(k, (k_mstep_delta<KT><<<grid, 256, 0, S(s)>>>(k, d, wpr, x, lab, lab_m, list, count,
-                                                            s_int, nk_int)));
+                                                            s_int, nk_int, halt)));
     note_launch();
-    k_commit_labels<<<num_sms(), 256, 0, S(s)>>>(lab, lab_m, list, count);
+    k_commit_labels<<<num_sms(), 256, 0, S(s)>>>(lab, lab_m, list, count, halt);
     note_launch();
 }
 
@@ -2164,10 +2223,27 @@ extern "C" void nemk_mstep_finalize_tables(nemk_stream s, int k, int n, int d, i
                                            uint32_t *mask_f1, double *delta, int force_mu_changed) {
     cudaMemsetAsync(&coef->uniform_ok, 1, sizeof(int32_t), S(s));
     cudaMemsetAsync(&coef->mu_changed, force_mu_changed ? 1 : 0, sizeof(int32_t), S(s));
-    k_mstep_finalize_tables<<<k * FT_CLUSTER, FT_THREADS, 0, S(s)>>>(k, n, d, wpr, prop_model, disp_model, s_int,
-                                                       nk_int, s_dbl, nk_dbl, prop, center, disp,
-                                                       coef, mask_xor, mask_valid, mask_f0, mask_f1,
-                                                       delta);
+    // the work is K*D elements: what costs is the chain of barriers.  Up to 8192 genomes one CTA of
+    // 1024 threads per class (block barriers only); beyond, a cluster of 8 CTAs per class (DSMEM sums)
+    static int force_cl = -1;
+    if (force_cl < 0) { const char *e = getenv("NEM_B200_FT_CLUSTER"); force_cl = e ? atoi(e) : 0; }
+    int cl = force_cl ? force_cl : 8;   // measured on C4 (D = 5000): 8-CTA clusters beat one CTA per class
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(k * cl); cfg.stream = S(s); cfg.attrs = at; cfg.numAttrs = 1;
+#define FT_LAUNCH(CL, TH)                                                                        \
+    do {                                                                                         \
+        cfg.blockDim = dim3(TH);                                                                 \
+        cudaLaunchKernelEx(&cfg, k_mstep_finalize_tables<CL, TH>, k, n, d, wpr, prop_model,      \
+                           disp_model, s_int, nk_int, s_dbl, nk_dbl, prop, center, disp, coef,   \
+                           mask_xor, mask_valid, mask_f0, mask_f1, delta);                       \
+    } while (0)
+    if (cl == 1) FT_LAUNCH(1, 1024);
+    else if (cl == 2) { cfg.gridDim = dim3(k * 2); FT_LAUNCH(2, 1024); }
+    else { cfg.gridDim = dim3(k * 8); FT_LAUNCH(8, 512); }
+#undef FT_LAUNCH
     note_launch();
 }
 
