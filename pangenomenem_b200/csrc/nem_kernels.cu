@@ -702,6 +702,56 @@ static __device__ __forceinline__ void ctx_labels_warp(int K, int i, const int32
     }
 }
 
+// ---- context of 32 CONSECUTIVE sites by one warp (the dense sweeps and the criteria): the CSR
+// segments of consecutive rows are contiguous, so the warp streams [row_ptr[i0], row_ptr[i0+32])
+// with coalesced loads (index, weight, then the label gather: 32 entries per instruction) into a
+// shared-memory stage, and every lane then adds ITS entries in file order (fp64, same sum as
+// SumNeighsOfClass, nem_alg.c:2865-2875).  Replaces 8 scattered 4-byte loads per site by ~1/4 of
+// the L1 sectors and a third of the instructions.  Lanes with an empty range (lo == hi: out of
+// range, or a hub handled elsewhere) only help loading; chunks no live lane intersects are skipped.
+// Must be called by all 32 lanes.
+#define COOP_C 4                    // entries per lane per chunk
+#define COOP_CHUNK (32 * COOP_C)
+template <int KT>
+static __device__ __forceinline__ void ctx_labels_coop(int lo, int hi, int seg_lo, int seg_hi,
+                                                       const int32_t *__restrict__ col,
+                                                       const float *__restrict__ wgt,
+                                                       const uint8_t *__restrict__ lab,
+                                                       float *s_w /*[COOP_CHUNK]*/,
+                                                       uint8_t *s_l /*[COOP_CHUNK]*/, double *ctx) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < KT; k++) ctx[k] = 0.0;
+    for (int chunk = seg_lo; chunk < seg_hi; chunk += COOP_CHUNK) {
+        const int chunk_end = min(chunk + COOP_CHUNK, seg_hi);
+        if (!__any_sync(FULL, lo < chunk_end && hi > chunk)) continue;
+        int j[COOP_C];
+        float w[COOP_C];
+#pragma unroll
+        for (int c = 0; c < COOP_C; c++) {
+            int e = chunk + c * 32 + lane;
+            bool in = e < chunk_end;
+            j[c] = in ? col[e] : -1;
+            w[c] = in ? wgt[e] : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < COOP_C; c++) {
+            s_w[c * 32 + lane] = w[c];
+            s_l[c * 32 + lane] = j[c] >= 0 ? lab[j[c]] : (uint8_t)255;
+        }
+        __syncwarp();
+        const int a = max(lo, chunk) - chunk, b = min(hi, chunk_end) - chunk;
+        for (int q = a; q < b; q++) {
+            unsigned l = s_l[q];
+            double wq = (double)s_w[q];
+#pragma unroll
+            for (int k = 0; k < KT; k++)
+                if (l == (unsigned)k) ctx[k] += wq;
+        }
+        __syncwarp();
+    }
+}
+
 static __device__ __forceinline__ void mark_readers_warp(int i, const int32_t *__restrict__ rrow_ptr,
                                                          const int32_t *__restrict__ rcol,
                                                          int32_t *dirty, int32_t *wl,
@@ -748,14 +798,28 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
         }
         return;
     }
+    __shared__ float s_w[8][COOP_CHUNK];
+    __shared__ uint8_t s_l[8][COOP_CHUNK];
     int il = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x;
     int i = row0 + il;
-    if (il < n_loc) {
+    if (il - lane >= n_loc) return;   // whole warp out of range
+    {
         const int32_t *rp = beta != 0.0 ? row_ptr : nullptr;
-        bool is_heavy = heavy_blocks && rp && (rp[i + 1] - rp[i] > HEAVY_DEG);
-        if (!is_heavy) {
-            double ctx[KT];
-            ctx_labels<KT>(K, i, rp, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
+        const bool valid = il < n_loc;
+        int lo = 0, hi = 0;
+        if (rp && valid) { lo = rp[i]; hi = rp[i + 1]; }
+        const bool is_heavy = heavy_blocks && (hi - lo > HEAVY_DEG);
+        double ctx[KT];
+        if (rp) {
+            int seg_lo = __shfl_sync(FULL, lo, 0), seg_hi = __reduce_max_sync(FULL, hi);
+            if (is_heavy) lo = hi = 0;   // evaluated by the hub blocks
+            ctx_labels_coop<KT>(lo, hi, seg_lo, seg_hi, col, wgt, lab_in, s_w[threadIdx.x >> 5],
+                                s_l[threadIdx.x >> 5], ctx);
+        } else {
+#pragma unroll
+            for (int k = 0; k < KT; k++) ctx[k] = 0.0;
+        }
+        if (valid && !is_heavy) {
             double lpv[KT];
             load_lp<KT>(lps, K, (size_t)il, lpv);
             int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
@@ -1597,19 +1661,34 @@ k_criteria_partial(int K, int row0, int n_loc, const nemk_lpsrc lps,
             }
         }
     } else {
-        int nb = gridDim.x - heavy_blocks;
-        for (int il = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x; il < n_loc;
-             il += nb * blockDim.x) {
-            const int i = row0 + il;
-            if (heavy_blocks && row_ptr && row_ptr[i + 1] - row_ptr[i] > HEAVY_DEG) continue;
+        __shared__ float s_w[8][COOP_CHUNK];
+        __shared__ uint8_t s_l[8][COOP_CHUNK];
+        const int nb = gridDim.x - heavy_blocks, lane = threadIdx.x & 31;
+        for (int base = (blockIdx.x - heavy_blocks) * blockDim.x + (threadIdx.x & ~31); base < n_loc;
+             base += nb * blockDim.x) {
+            const int il = base + lane, i = row0 + il;
+            const bool valid = il < n_loc;
+            int lo = 0, hi = 0;
+            if (row_ptr && valid) { lo = row_ptr[i]; hi = row_ptr[i + 1]; }
+            const bool is_heavy = heavy_blocks && (hi - lo > HEAVY_DEG);
             double ctx[KT];
             float ti[KT];
             if (lab) {
-                ctx_labels<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab[j]; }, ctx);
+                if (row_ptr) {
+                    int seg_lo = __shfl_sync(FULL, lo, 0), seg_hi = __reduce_max_sync(FULL, hi);
+                    if (is_heavy) lo = hi = 0;
+                    ctx_labels_coop<KT>(lo, hi, seg_lo, seg_hi, col, wgt, lab, s_w[threadIdx.x >> 5],
+                                        s_l[threadIdx.x >> 5], ctx);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KT; k++) ctx[k] = 0.0;
+                }
+                if (!valid || is_heavy) continue;
                 unsigned l = lab[i];
 #pragma unroll
                 for (int k = 0; k < KT; k++) ti[k] = (l == (unsigned)k) ? 1.f : 0.f;
             } else {
+                if (!valid || is_heavy) continue;
                 ctx_fuzzy<KT>(K, i, row_ptr, col, wgt, t, ctx);
 #pragma unroll
                 for (int k = 0; k < KT; k++) ti[k] = (k < K) ? t[(size_t)i * K + k] : 0.f;
