@@ -811,7 +811,10 @@ static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, 
 }
 
 /* one E-step sweep; *flipped tells whether the state moved to the other buffer */
-static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *flipped)
+/* decide (nullable): the options of the EM iteration this sweep ends -- the sharded sweep then
+ * publishes the iteration's status itself; *status_read tells the caller it did */
+static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *flipped,
+                     const nemb_options *decide, int *status_read)
 {
     int k = o->k, n = h->n, row0 = h->row0, rc;
     const int32_t *skip = &h->d_coef->empty_class;
@@ -819,6 +822,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
     int seq = o->update == NEMB_UPDATE_SEQ && h->spatial && beta != 0.0;
     size_t L = h->lab_len, SL = h->shard_len;
     *flipped = 0;
+    if (status_read) *status_read = 0;
     CK(cudaMemsetAsync(&h->d_status->cnt, 0, sizeof(nemk_counters), h->stream));
     STAGE_BEGIN(ST_SWEEP);
     if (o->algo == NEMB_ALGO_NCEM) {
@@ -844,23 +848,25 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
             if (h->world > 1) {
                 /* speculative fixed point ACROSS ranks: exchange label slices, queue the local
                  * readers of every remote label that moved, fix up, until no rank queues anything
-                 * (then every rank holds the sequential sweep's labels for all families) */
-                enum { ROUNDS_PER_CHECK = 2 };
+                 * (then every rank holds the sequential sweep's labels for all families).  One
+                 * label all-gather + one counter all-gather + one host poll per round; the last
+                 * round's status (counters summed over the ranks, convergence decided on the
+                 * device when `decide` is given) doubles as the iteration's status. */
                 for (int guard = 0;; guard++) {
-                    for (int r = 0; r < ROUNDS_PER_CHECK; r++) {
-                        if ((rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
-                        CK(cudaMemsetAsync(&h->d_status->cnt.pending, 0, sizeof(int32_t), h->stream));
-                        nemk_mark_remote(h->stream, h->n_glob, row0, n, out, seen, h->d_dirty,
-                                         h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr, h->d_rcol,
-                                         &h->d_status->cnt.pending);
-                        h->launches++;
-                        if (r + 1 < ROUNDS_PER_CHECK) local_fixups(h, k, beta, in, out, rp, skip);
-                    }
-                    if ((rc = read_status(h)) != NEMB_OK) return rc;
+                    if ((rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
+                    CK(cudaMemsetAsync(&h->d_status->cnt.pending, 0, sizeof(int32_t), h->stream));
+                    nemk_mark_remote(h->stream, h->n_glob, row0, n, out, seen, h->d_dirty,
+                                     h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr, h->d_rcol,
+                                     &h->d_status->cnt.pending);
+                    h->launches++;
+                    unsigned long long seq;
+                    if ((rc = publish_status(h, decide, &seq)) != NEMB_OK) return rc;
+                    if ((rc = wait_status(h, seq)) != NEMB_OK) return rc;
                     if (h->h_status->cnt.pending == 0 || *h->h_empty) break;
                     if (guard > h->n_glob) return fail(h, NEMB_E_BUG, "sharded sweep did not settle");
                     local_fixups(h, k, beta, in, out, rp, skip);
                 }
+                if (status_read) *status_read = 1;
             }
             *flipped = 1;
         } else {
@@ -1027,9 +1033,9 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     if ((rc = run_tables(h, k, 0)) != NEMB_OK) return rc;
     if ((rc = run_density(h, k, uniform0, NULL, lean)) != NEMB_OK) return rc;
     /* ComputePartitionFromPara(Needinit=1): blind sweep then beta sweep (nem_alg.c:1970-1981) */
-    if ((rc = run_sweep(h, o, 0.0, &flipped)) != NEMB_OK) return rc;
+    if ((rc = run_sweep(h, o, 0.0, &flipped, NULL, NULL)) != NEMB_OK) return rc;
     if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
-    if ((rc = run_sweep(h, o, beta, &flipped)) != NEMB_OK) return rc;
+    if ((rc = run_sweep(h, o, beta, &flipped, NULL, NULL)) != NEMB_OK) return rc;
     if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
     double oldcrit = 0.0;
     if (o->dolog || cb || o->it_max == 0) {
@@ -1064,7 +1070,8 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
             if (!o->param_fixed && (rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
             if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
             if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
-            if ((rc = run_sweep(h, o, beta, &flipped)) != NEMB_OK) return rc;
+            int status_read = 0;
+            if ((rc = run_sweep(h, o, beta, &flipped, (want_crit_each || cb) ? NULL : o, &status_read)) != NEMB_OK) return rc;
             if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
             if (cb) {
                 CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
@@ -1072,7 +1079,8 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
                 CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
             }
             flips[enq & 1] = flipped;
-            if ((rc = publish_status(h, o, &seqs[enq & 1])) != NEMB_OK) return rc;
+            if (status_read && !want_crit_each && !cb) seqs[enq & 1] = h->seq;   /* the sweep's last status */
+            else if ((rc = publish_status(h, o, &seqs[enq & 1])) != NEMB_OK) return rc;
         }
         if ((rc = wait_status(h, seqs[iter & 1])) != NEMB_OK) return rc;
         if (cb) CK(cudaStreamSynchronize(h->stream));   /* theta copies of this iteration */
@@ -1352,7 +1360,7 @@ int nemb_stage_sweep(nemb_handle *h, const nemb_options *o, const double *logpf,
     h->lp_from_ham = 0;
     CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
     if ((rc = upload_state(h, o, t_inout)) != NEMB_OK) return rc;
-    if ((rc = run_sweep(h, o, h->spatial ? (double)beta : 0.0, &flipped)) != NEMB_OK) return rc;
+    if ((rc = run_sweep(h, o, h->spatial ? (double)beta : 0.0, &flipped, NULL, NULL)) != NEMB_OK) return rc;
     if ((rc = read_status(h)) != NEMB_OK) return rc;
     if (fixup_rounds) *fixup_rounds = h->h_status->cnt.nfix;
     if ((rc = nemb_get_posteriors(h, t_inout)) != NEMB_OK) return rc;

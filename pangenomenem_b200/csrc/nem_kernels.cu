@@ -1858,7 +1858,7 @@ __global__ void k_iter_end(int world, const nemk_counters *__restrict__ cnt_all,
         tot.maxdiff = fmaxf(tot.maxdiff, c.maxdiff);
     }
     int halt = coef->halt, empty = coef->empty_class;
-    if (decide && !halt) {
+    if (decide && !halt && tot.pending == 0) {   // pending != 0: a row-sharded sweep is not settled yet
         bool converged = false;
         if (conv == 1) {
             float md = ncem ? (tot.changed ? 1.0f : 0.0f) : tot.maxdiff;
