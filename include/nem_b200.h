@@ -5,7 +5,7 @@
  * labgem/pangenomeNEM binds instead of the reference's ppanggolin/NEM C sources.
  * File:line citations refer to the reference tree (ppanggolin/...).
  *
- * Three layers:
+ * Layers:
  *   1. nem()            drop-in for the reference's only exported symbol (NEM/nem_exe.h:23-35,
  *                       NEM/nem_exe.c:239-704), what NEM/nem.pyx wraps and
  *                       ppanggolin.py:1814-1826 calls.
@@ -203,6 +203,8 @@ int nemb_get_dims(const nemb_handle *h, int *n, int *d, int *words_per_row, int 
                   int *depth, int *nnz);
 int nemb_get_packed(nemb_handle *h, uint32_t *out /*[n*wpr]*/);
 int nemb_get_transposed(nemb_handle *h, uint32_t *out /*[d*nwt]*/);
+/* the CSR as resident in HBM (any pointer may be NULL): row_ptr[n+1], col[nnz], wgt[nnz] */
+int nemb_get_graph(nemb_handle *h, int32_t *row_ptr, int32_t *col, float *wgt);
 int nemb_get_levels(nemb_handle *h, int32_t *level_of_site /*[n]*/);
 
 /* stage entry points (each runs exactly the kernels nemb_fit uses for that step) */
@@ -218,6 +220,49 @@ int nemb_stage_mstep(nemb_handle *h, const nemb_options *opt, const float *t /*[
                      double *skd_out /*[k*d]*/, int *empty_class);
 int nemb_stage_criteria(nemb_handle *h, const nemb_options *opt, const double *logpf,
                         const float *t, float beta, double *crit6 /*U D L M Z G*/);
+
+/* ---------------------------------------------------------------------------------------
+ * 4. resample driver -- NEM on organism subsets without the text round trip.
+ * Replaces, for callers that can link it, the per-sample work of the chunk loop of partition()
+ * (ppanggolin.py:995-1105: sample `chunck_size` organisms, __write_nem_input_files
+ * ppanggolin.py:821-930, nem(), vote) and of the evolution-curve workers
+ * (command_line.py:262-281, 599-619).  The subsample is built ON THE DEVICE from the resident
+ * pangenome exactly as the reference writes it: families without a selected organism are dropped
+ * and the others renumbered in order (ppanggolin.py:847-852); an edge is kept when it exists in
+ * at least one selected organism and its weight is that count (ppanggolin.py:862-880).
+ * ------------------------------------------------------------------------------------- */
+/* genome_mask: host, ceil(D/32) words, bit d = genome d selected.  edge_presence_dev: DEVICE
+ * uint32[nnz][words_per_row] -- bit d of row e = CSR entry e exists in genome d -- or NULL for
+ * the co-presence model (the edge exists wherever both families are present).  `dst` (same
+ * device, single GPU) becomes a loaded pangenome of n_eff families x d_eff genomes whose genomes
+ * are the selected ones in ascending order; fit it with nemb_fit().  The source graph must be
+ * symmetric.  Buffers of dst are sized by the source, so repeated calls do not allocate. */
+int nemb_subsample(nemb_handle *src, nemb_handle *dst, const uint32_t *genome_mask,
+                   const uint32_t *edge_presence_dev, int *n_eff, int *d_eff);
+/* original family id of every row of a device-built subsample (nem_file.index of the reference) */
+int nemb_get_family_index(nemb_handle *dst, int32_t *index_out /*[n_eff]*/);
+
+typedef struct {
+    int32_t n_runs;          /* samples fitted */
+    int32_t n_ok;            /* fits whose classes map to (persistent, shell, cloud) */
+    int32_t n_inconsistent;  /* class/parameter consistency check failed (ppanggolin.py:1956-1957):
+                                every family of the sample voted "undefined" */
+    int32_t n_failed;        /* empty class: the reference writes no .uf, all families undefined */
+    int64_t family_iterations;   /* sum over samples of n_eff x EM iterations */
+    int64_t kernel_launches;
+    double  fit_ms_sum;      /* device time of the fits (they overlap across workers) */
+} nemb_batch_stats;
+
+/* n_runs independent fits (K = 3, ncem, PPanGGOLiN's default initial parameters) on the genome
+ * subsets genome_masks[n_runs][ceil(D/32)], run r with beta betas[r] (NULL: opt->beta).
+ * n_workers host threads, each with its own stream and scratch handle, pull runs from a shared
+ * counter so the latency-bound small fits overlap on the device.  votes_out (host, nullable):
+ * int32[N][4] = how many samples put each family in persistent / shell / cloud / undefined
+ * (cpt_partition of ppanggolin.py:997-1037).  iters_out (nullable): EM iterations of every run. */
+int nemb_resample_batch(nemb_handle *src, int n_runs, const uint32_t *genome_masks,
+                        const float *betas, const nemb_options *opt, int n_workers,
+                        const uint32_t *edge_presence_dev, int32_t *votes_out, int32_t *iters_out,
+                        nemb_batch_stats *stats);
 
 /* ---------------------------------------------------------------------------------------
  * host-side loader / writers (no GPU needed): the NEM file contract as in-memory buffers.

@@ -24,8 +24,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 CC_FLAGS = ["-O2", "-std=gnu11", "-Wall", "-Wno-unused-function", "-fPIC", "-ffp-contract=off",
             "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", os.path.join(CUDA_HOME, "include")]
 
-CU_SOURCES = ["nem_kernels.cu"]
-C_SOURCES = ["nem_fit.c", "nem_comm.c", "nem_io.c", "nem_api.c"]
+CU_SOURCES = ["nem_kernels.cu", "nem_sub_kernels.cu"]
+C_SOURCES = ["nem_fit.c", "nem_resample.c", "nem_comm.c", "nem_io.c", "nem_api.c"]
 
 
 def _newer(src_list, target):

@@ -51,6 +51,23 @@ class Result(C.Structure):
                 ("exchanges", C.c_int64)]
 
 
+class BatchStats(C.Structure):
+    _fields_ = [("n_runs", C.c_int32), ("n_ok", C.c_int32), ("n_inconsistent", C.c_int32),
+                ("n_failed", C.c_int32), ("family_iterations", C.c_int64),
+                ("kernel_launches", C.c_int64), ("fit_ms_sum", C.c_double)]
+
+
+def pack_mask(mask, d: int) -> np.ndarray:
+    """bool[D] -> uint32[ceil(D/32)], genome j = bit j%32 of word j/32 (the layout of X's rows)."""
+    m = np.asarray(mask)
+    wm = (d + 31) // 32
+    if m.dtype == np.uint32 and m.shape == (wm,):
+        return np.ascontiguousarray(m)
+    b = np.zeros(wm * 32, dtype=np.uint8)
+    b[:d] = m.astype(bool)[:d]
+    return np.packbits(b.reshape(wm, 32), axis=1, bitorder="little").view(np.uint32).reshape(wm).copy()
+
+
 class Extra(C.Structure):
     _fields_ = [("update", C.c_int32), ("sweep_impl", C.c_int32), ("device", C.c_int32),
                 ("n_random_inits", C.c_int32), ("seed", C.c_int64), ("reserved", C.c_int32 * 8)]
@@ -227,6 +244,14 @@ class Engine:
         self._check(self.lib.nemb_get_packed(self.h, _p(out)))
         return out
 
+    def graph(self):
+        dm = self.dims()
+        rp = np.zeros(dm["n"] + 1, dtype=np.int32)
+        cl = np.zeros(dm["nnz"], dtype=np.int32)
+        wg = np.zeros(dm["nnz"], dtype=np.float32)
+        self._check(self.lib.nemb_get_graph(self.h, _p(rp), _p(cl), _p(wg)))
+        return rp, cl, wg
+
     def transposed(self):
         dm = self.dims()
         out = np.zeros((dm["d"], dm["nwt"]), dtype=np.uint32)
@@ -271,6 +296,43 @@ class Engine:
         out = np.zeros(self.n, dtype=np.int32)
         self._check(self.lib.nemb_get_labels(self.h, _p(out)))
         return out
+
+    # ---- resample driver (include/nem_b200.h layer 4)
+    def subsample_into(self, dst: "Engine", genome_mask, edge_presence_dev: int = 0):
+        """Build the genome subsample `genome_mask` (bool[D] or packed uint32 words) of this
+        pangenome into `dst` on the device; returns (n_eff, d_eff)."""
+        words = pack_mask(genome_mask, self.d)
+        n_eff, d_eff = C.c_int(), C.c_int()
+        rc = self.lib.nemb_subsample(self.h, dst.h, _p(words), C.c_void_p(edge_presence_dev or None),
+                                     C.byref(n_eff), C.byref(d_eff))
+        if rc:
+            raise NemError(rc, self.lib.nemb_last_error(dst.h).decode())
+        dst.n, dst.d = n_eff.value, d_eff.value
+        return n_eff.value, d_eff.value
+
+    def family_index(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        self._check(self.lib.nemb_get_family_index(self.h, _p(out)))
+        return out
+
+    def resample_batch(self, genome_masks, betas=None, n_workers=4, edge_presence_dev: int = 0, **kw):
+        """Fit every genome subset of `genome_masks` (bool[R][D] or uint32[R][ceil(D/32)]);
+        returns (votes int32[N][4] = P,S,C,U counts per family, iters int32[R], BatchStats)."""
+        gm = np.asarray(genome_masks)
+        if gm.dtype != np.uint32:
+            gm = np.stack([pack_mask(m, self.d) for m in gm])
+        gm = np.ascontiguousarray(gm, dtype=np.uint32)
+        assert gm.shape[1] == (self.d + 31) // 32, gm.shape
+        runs = gm.shape[0]
+        o = make_options(**kw)
+        bt = None if betas is None else _f32(betas)
+        votes = np.zeros((self.n, 4), dtype=np.int32)
+        iters = np.zeros(runs, dtype=np.int32)
+        st = BatchStats()
+        self._check(self.lib.nemb_resample_batch(self.h, runs, _p(gm), _p(bt), C.byref(o), int(n_workers),
+                                                 C.c_void_p(edge_presence_dev or None), _p(votes),
+                                                 _p(iters), C.byref(st)))
+        return votes, iters, st
 
     # ---- stages
     def stage_density(self, prop, center, disp, k=3, force_general=False, want_hamming=False):

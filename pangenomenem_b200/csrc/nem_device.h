@@ -190,6 +190,28 @@ void nemk_criteria_final(nemk_stream s, int nblocks_total, const double *partial
 void nemk_sum_ranks_i32(nemk_stream s, int world, size_t count, const int32_t *stage, int32_t *out);
 void nemk_sum_ranks_f64(nemk_stream s, int world, size_t count, const double *stage, double *out);
 
+/* ---- resample driver (nem_sub_kernels.cu): genome subsample of the resident pangenome */
+/* flag[n] = family has a selected genome; new_id[n+1] = exclusive scan; *n_eff = total */
+void nemk_sub_active(nemk_stream s, int n, int wpr, const uint32_t *x, const uint32_t *mask,
+                     int32_t *flag, int32_t *new_id, int32_t *block_tmp, int32_t *n_eff);
+/* x_new[new_id[i]] = the d_eff selected columns (cols[], ascending) of row i, re-packed; index */
+void nemk_sub_gather(nemk_stream s, int n, int wpr, int d_eff, int wpr_new, const uint32_t *x,
+                     const int32_t *cols, const int32_t *flag, const int32_t *new_id,
+                     uint32_t *x_new, int32_t *index);
+/* w_tmp[e] = popc(E_e & mask) (E = edge_bits, or x_i & x_j when NULL); cnt[n_cnt] kept entries per
+ * NEW row; new_row_ptr[n_cnt+1] = their exclusive scan; *nnz_new, *maxdeg */
+void nemk_sub_edges(nemk_stream s, int n, int wpr, const uint32_t *x, const uint32_t *mask,
+                    const uint32_t *edge_bits, const int32_t *row_ptr, const int32_t *col,
+                    const int32_t *flag, const int32_t *new_id, float *w_tmp, int32_t *cnt,
+                    int32_t *new_row_ptr, int32_t *block_tmp, int32_t *nnz_new, int32_t *maxdeg,
+                    int n_cnt);
+void nemk_sub_fill(nemk_stream s, int n, const int32_t *row_ptr, const int32_t *col,
+                   const float *w_tmp, const int32_t *flag, const int32_t *new_id,
+                   const int32_t *new_row_ptr, int32_t *col_new, float *wgt_new);
+/* votes[index[i]*4 + cls] += 1, cls = c_label (0 P, 1 S, 2 C) or 3 (U) */
+void nemk_sub_vote(nemk_stream s, int n_eff, const int32_t *index, const uint8_t *lab, int c0,
+                   int c1, int c2, int all_u, int32_t *votes);
+
 /* ---- helpers */
 void nemk_labels_to_t(nemk_stream s, int k, int n, const uint8_t *lab, float *t);
 void nemk_t_to_labels(nemk_stream s, int k, int n, const float *t, uint8_t *lab);
