@@ -17,6 +17,7 @@
 #include <cuda_runtime_api.h>
 #include <float.h>
 #include <math.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -674,6 +675,7 @@ static int wait_status(nemb_handle *h, unsigned long long seq)
 #if defined(__x86_64__) || defined(__i386__)
         __builtin_ia32_pause();
 #endif
+        if ((spins & 0xff) == 0) sched_yield();   /* several engines may poll on few cores */
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
     const nemk_host_status *r = &h->ring[seq % RING];

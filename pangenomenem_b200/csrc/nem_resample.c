@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 static int round_up4(int v) { return (v + 3) / 4 * 4; }
 static size_t carve(size_t *off, size_t bytes)
@@ -252,8 +253,10 @@ int nemb_resample_batch(nemb_handle *src, int n_runs, const uint32_t *genome_mas
     if (!src->loaded) return fail(h, NEMB_E_ARG, "nemb_resample_batch: no pangenome loaded");
     if (opt->k != 3) return fail(h, NEMB_E_ARG, "nemb_resample_batch: K must be 3 (persistent/shell/cloud)");
     if (opt->algo != NEMB_ALGO_NCEM) return fail(h, NEMB_E_ARG, "nemb_resample_batch: algo must be ncem");
-    if (n_workers < 1) n_workers = 4;
+    if (n_workers < 1) n_workers = 8;
     if (n_workers > 32) n_workers = 32;
+    long cores = sysconf(_SC_NPROCESSORS_ONLN);   /* every worker polls its status slot: leave cores free */
+    if (cores > 0 && n_workers > cores / 2) n_workers = cores / 2 > 0 ? (int)(cores / 2) : 1;
     if (n_workers > n_runs && n_runs > 0) n_workers = n_runs;
     CK(cudaSetDevice(src->device));
     CK(cudaStreamSynchronize(src->stream));   /* the source is read-only from here on */

@@ -112,71 +112,88 @@ static void exclusive_scan(cudaStream_t st, int n, const int32_t *in, int32_t *o
 }
 
 // bit gather: output word q of the new row = bits cols[32q .. 32q+31] of the old row.
-// One thread per output word; the 32 source positions of a word are shared by every row, so they
-// are staged in shared memory once per CTA (a CTA owns SG_ROWS rows x all words).
-#define SG_ROWS 8
+// A CTA owns SG_ROWS consecutive old rows: they are staged in shared memory with coalesced loads
+// (inactive rows too -- they are cheap and keep the loads regular), the column list is staged
+// once, and the (row, output word) items are spread over all threads.
+#define SG_ROWS 64
 __global__ void __launch_bounds__(256)
 k_sub_gather(int n, int wpr, int d_eff, int wpr_new, const uint32_t *__restrict__ x,
              const int32_t *__restrict__ cols, const int32_t *__restrict__ flag,
              const int32_t *__restrict__ new_id, uint32_t *__restrict__ x_new,
              int32_t *__restrict__ index) {
-    extern __shared__ int32_t s_cols[];   // d_eff entries
-    for (int q = threadIdx.x; q < d_eff; q += blockDim.x) s_cols[q] = cols[q];
+    extern __shared__ int32_t s_dyn[];
+    int32_t *s_cols = s_dyn;                                   // wpr_new * 32 entries (-1 = padding)
+    uint32_t *s_rows = (uint32_t *)(s_dyn + wpr_new * 32);     // SG_ROWS x (wpr + 1)
+    __shared__ int s_nid[SG_ROWS];
+    const int r0 = blockIdx.x * SG_ROWS, rows = min(SG_ROWS, n - r0), stride = wpr + 1;
+    for (int q = threadIdx.x; q < wpr_new * 32; q += blockDim.x) s_cols[q] = q < d_eff ? cols[q] : -1;
+    for (int q = threadIdx.x; q < rows * wpr; q += blockDim.x) {
+        int rr = q / wpr, w = q - rr * wpr;
+        s_rows[rr * stride + w] = x[(size_t)(r0 + rr) * wpr + w];
+    }
+    if (threadIdx.x < rows) {
+        int row = r0 + threadIdx.x;
+        int nid = flag[row] ? new_id[row] : -1;
+        s_nid[threadIdx.x] = nid;
+        if (nid >= 0) index[nid] = row;
+    }
     __syncthreads();
-    for (int rr = 0; rr < SG_ROWS; rr++) {
-        int row = blockIdx.x * SG_ROWS + rr;
-        if (row >= n) return;
-        if (!flag[row]) continue;
-        int nr = new_id[row];
-        const uint32_t *xr = x + (size_t)row * wpr;
-        if (threadIdx.x == 0) index[nr] = row;
-        for (int q = threadIdx.x; q < wpr_new; q += blockDim.x) {
-            uint32_t out = 0u;
-            int base = q * 32;
+    for (int it = threadIdx.x; it < rows * wpr_new; it += blockDim.x) {
+        int rr = it / wpr_new, q = it - rr * wpr_new;
+        int nid = s_nid[rr];
+        if (nid < 0) continue;
+        const uint32_t *xr = s_rows + rr * stride;
+        const int32_t *cq = s_cols + q * 32;
+        uint32_t out = 0u;
 #pragma unroll 8
-            for (int b = 0; b < 32; b++) {
-                int p = base + b;
-                if (p < d_eff) {
-                    int c = s_cols[p];
-                    out |= ((__ldg(xr + (c >> 5)) >> (c & 31)) & 1u) << b;
-                }
-            }
-            x_new[(size_t)nr * wpr_new + q] = out;
+        for (int b = 0; b < 32; b++) {
+            int c = cq[b];
+            if (c >= 0) out |= ((xr[c >> 5] >> (c & 31)) & 1u) << b;
         }
+        x_new[(size_t)nid * wpr_new + q] = out;
     }
 }
 
-// edge weights under the mask: one warp per (old) row walks its entries; lanes split the words.
-// w_tmp[e] = coverage (0 = dropped); cnt[new_id[i]] = kept entries of the row; maxdeg via atomicMax.
+// edge weights under the mask: one warp per (old) row; the warp is split into groups of LPE lanes
+// (LPE = the uint4 chunks of a row, rounded up to a power of two, at most 32) and every group takes
+// one CSR entry at a time.  w_tmp[e] = coverage (0 = dropped); cnt[new_id[i]] = kept entries of the
+// row; maxdeg via atomicMax.
+template <int LPE>
 __global__ void __launch_bounds__(256)
 k_sub_edges(int n, int wpr4, const uint4 *__restrict__ x, const uint4 *__restrict__ mask,
             const uint4 *__restrict__ edge_bits /* [nnz][wpr4] or null */,
             const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
             const int32_t *__restrict__ flag, const int32_t *__restrict__ new_id,
             float *__restrict__ w_tmp, int32_t *__restrict__ cnt, int32_t *maxdeg) {
+    constexpr int G = 32 / LPE;
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= n) return;
+    const int g = lane / LPE, sub = lane % LPE;
     int lo = row_ptr[row], hi = row_ptr[row + 1];
     bool act = flag[row] != 0;
     int kept = 0;
-    for (int e = lo; e < hi; e++) {
-        int j = col[e];
+    for (int e0 = lo; e0 < hi; e0 += G) {      // warp-uniform trip count
+        int e = e0 + g;
         int c = 0;
-        if (act && flag[j]) {
-            for (int q = lane; q < wpr4; q += 32) {
-                uint4 m = __ldg(mask + q), a;
-                if (edge_bits) a = __ldg(edge_bits + (size_t)e * wpr4 + q);
-                else {
-                    uint4 u = __ldg(x + (size_t)row * wpr4 + q), v = __ldg(x + (size_t)j * wpr4 + q);
-                    a = make_uint4(u.x & v.x, u.y & v.y, u.z & v.z, u.w & v.w);
+        if (e < hi && act) {
+            int j = col[e];
+            if (flag[j]) {
+                for (int q = sub; q < wpr4; q += LPE) {
+                    uint4 m = __ldg(mask + q), a;
+                    if (edge_bits) a = __ldg(edge_bits + (size_t)e * wpr4 + q);
+                    else {
+                        uint4 u = __ldg(x + (size_t)row * wpr4 + q), v = __ldg(x + (size_t)j * wpr4 + q);
+                        a = make_uint4(u.x & v.x, u.y & v.y, u.z & v.z, u.w & v.w);
+                    }
+                    c += __popc(a.x & m.x) + __popc(a.y & m.y) + __popc(a.z & m.z) + __popc(a.w & m.w);
                 }
-                c += __popc(a.x & m.x) + __popc(a.y & m.y) + __popc(a.z & m.z) + __popc(a.w & m.w);
             }
-            c = __reduce_add_sync(FULL, c);
         }
-        if (lane == 0) w_tmp[e] = (float)c;
-        kept += c > 0;
+#pragma unroll
+        for (int o = LPE / 2; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        if (sub == 0 && e < hi) { w_tmp[e] = (float)c; kept += c > 0; }
     }
+    kept = __reduce_add_sync(FULL, kept);
     if (lane == 0 && act) {
         cnt[new_id[row]] = kept;
         if (kept) atomicMax(maxdeg, kept);
@@ -221,7 +238,7 @@ extern "C" void nemk_sub_gather(nemk_stream s, int n, int wpr, int d_eff, int wp
                                 const int32_t *cols, const int32_t *flag, const int32_t *new_id,
                                 uint32_t *x_new, int32_t *index) {
     if (n <= 0) return;
-    size_t smem = sizeof(int32_t) * (size_t)(d_eff > 0 ? d_eff : 1);
+    size_t smem = sizeof(int32_t) * ((size_t)wpr_new * 32 + (size_t)SG_ROWS * (wpr + 1));
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_sub_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_sub_gather<<<cdiv(n, SG_ROWS), 256, smem, S(s)>>>(n, wpr, d_eff, wpr_new, x, cols, flag, new_id,
@@ -236,9 +253,12 @@ extern "C" void nemk_sub_edges(nemk_stream s, int n, int wpr, const uint32_t *x,
     if (n <= 0) return;
     cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)n_cnt, S(s));
     cudaMemsetAsync(maxdeg, 0, sizeof(int32_t), S(s));
-    k_sub_edges<<<cdiv((long long)n * 32, 256), 256, 0, S(s)>>>(
-        n, wpr / 4, (const uint4 *)x, (const uint4 *)mask, (const uint4 *)edge_bits, row_ptr, col, flag,
-        new_id, w_tmp, cnt, maxdeg);
+    const int wpr4 = wpr / 4, grid = cdiv((long long)n * 32, 256);
+#define SE(L) k_sub_edges<L><<<grid, 256, 0, S(s)>>>(n, wpr4, (const uint4 *)x, (const uint4 *)mask, \
+        (const uint4 *)edge_bits, row_ptr, col, flag, new_id, w_tmp, cnt, maxdeg)
+    if (wpr4 <= 2) SE(2); else if (wpr4 <= 4) SE(4); else if (wpr4 <= 8) SE(8);
+    else if (wpr4 <= 16) SE(16); else SE(32);
+#undef SE
     // the scan runs over the OLD row count (an upper bound of n_eff; the tail counts are zero)
     exclusive_scan(S(s), n_cnt, cnt, new_row_ptr, block_tmp, nnz_new);
 }
