@@ -40,8 +40,11 @@ typedef struct {
     int32_t allnul;      /* rows whose every class has zero density */
     int32_t ties;        /* ncem rows whose arg max was an exact tie */
     float   maxdiff;     /* nem: max |t - t_old| */
-    int32_t pending;     /* row-sharded sweep: local sites queued by the last label exchange */
-    int32_t pad[2];
+    int32_t pending;     /* row-sharded sweep: (reader, moved label) pairs across ranks found by the
+                            last label exchange -- the same number on every rank; 0 = settled */
+    int32_t changed_glob; /* row-sharded sweep: labels of ALL families != previous iteration's,
+                            counted by every rank from the exchanged labels (same on every rank) */
+    int32_t pad[1];
 } nemk_counters;
 
 /* Device status block of one sweep / iteration, and the copy nemk_iter_end publishes into
@@ -111,6 +114,8 @@ void nemk_heavy_list(nemk_stream s, int row0, int n_loc, const int32_t *row_ptr,
  * convergence test on the device (HasConverged `clas`, nem_alg.c:2075-2089: ncem = no label
  * changed, nem = max |t - t_old| < thr; conv: 0 none, 1 clas) and raise coef->halt when the fit is
  * over (converged or empty class), then publish everything to the mapped host slot. */
+/* world == 0: cnt_all is this rank's counter block of a row-sharded speculative sweep; its
+ * changed_glob / pending are already global (nemk_mark_remote), the other fields stay local */
 void nemk_iter_end(nemk_stream s, int world, const nemk_counters *cnt_all,
                    const nemk_iter_status *st, nemk_coef *coef, int decide, int ncem, int conv,
                    float thr, nemk_host_status *host_slot, unsigned long long seq);
@@ -121,13 +126,16 @@ void nemk_iter_end(nemk_stream s, int world, const nemk_counters *cnt_all,
  * kernel returns at once.
  * Row sharding: this rank owns the global rows [row0, row0+n_loc); labels, t, CSR, dirty flags and
  * work lists are indexed by GLOBAL family id, logpf by local row.  One GPU: row0 = 0, n_loc = N.
+ * nemk_sweep_ncem_jacobi with copy_ranks > 1 also copies the other ranks' label slices
+ * lab_in -> lab_out (slices of shard_len labels), so the fix-up rounds read the previous labels of
+ * remote families until the first exchange.
  * Work lists: wl_a/wl_b used alternately, wl_cnt[4] rotating counters (round r: list r&1). */
 void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                             const int32_t *row_ptr, const int32_t *col, const float *wgt,
                             double beta, const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
                             int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
                             const int32_t *rcol, const int32_t *heavy, int n_heavy,
-                            nemk_counters *cnt, const int32_t *skip);
+                            nemk_counters *cnt, const int32_t *skip, int copy_ranks, int shard_len);
 void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                            const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
                            const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a,
@@ -139,9 +147,15 @@ void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc, nemk
                                  int32_t *dirty, int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt,
                                  int round, const int32_t *rrow_ptr, const int32_t *rcol,
                                  nemk_counters *cnt, const int32_t *skip);
-void nemk_mark_remote(nemk_stream s, int n_glob, int row0, int n_loc, const uint8_t *lab_cur,
-                      uint8_t *lab_seen, int32_t *dirty, int32_t *wl, int32_t *wl_count,
-                      const int32_t *rrow_ptr, const int32_t *rcol, int32_t *pending);
+/* after a label exchange: every rank scans ALL families.  A label that differs from the one seen
+ * at the previous exchange (seen_in; the first exchange of a sweep passes the sweep's input labels)
+ * queues this rank's later readers and counts, for every rank alike, the cross-rank (reader,
+ * label) pairs -> cnt->pending; cnt->changed_glob = labels != lab_in.  seen_out receives lab_cur. */
+void nemk_mark_remote(nemk_stream s, int n_glob, int row0, int n_loc, int shard_len,
+                      const uint8_t *lab_cur, const uint8_t *lab_in, const uint8_t *seen_in,
+                      uint8_t *seen_out, int32_t *dirty, int32_t *wl, int32_t *wl_count,
+                      const int32_t *rrow_ptr, const int32_t *rcol, nemk_counters *cnt,
+                      const int32_t *skip);
 void nemk_sweep_ncem_level(nemk_stream s, int k, nemk_lpsrc lps, const int32_t *row_ptr,
                            const int32_t *col, const float *wgt, double beta, uint8_t *lab,
                            const int32_t *sites, const int32_t *level_ptr, int lv_lo, int lv_hi,

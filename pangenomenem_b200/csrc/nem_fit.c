@@ -745,37 +745,42 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
         int impl = o->sweep_impl == NEMB_SWEEP_AUTO ? NEMB_SWEEP_SPEC : o->sweep_impl;
         if (!seq) {
             nemk_sweep_ncem_jacobi(h->stream, k, row0, n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
-                                   out, NULL, NULL, NULL, NULL, NULL, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip);
+                                   out, NULL, NULL, NULL, NULL, NULL, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip,
+                                   0, 0);
             h->launches++;
             /* halo exchange of the hard labels: every rank's slice, 1 byte per family */
             if (h->world > 1 && (rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
             *flipped = 1;
         } else if (impl == NEMB_SWEEP_SPEC) {
-            if (h->world > 1) {   /* remote labels start at their old value, here and in `seen` */
-                CK(cudaMemcpyAsync(out, in, L, cudaMemcpyDeviceToDevice, h->stream));
-                CK(cudaMemcpyAsync(seen, in, L, cudaMemcpyDeviceToDevice, h->stream));
-            }
+            /* row shards: the jacobi kernel also copies the other ranks' slices in -> out (remote
+             * labels start the sweep at their previous value) */
             nemk_sweep_ncem_jacobi(h->stream, k, row0, n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
                                    out, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
-                                   h->d_rcol, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip);
+                                   h->d_rcol, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip,
+                                   h->world, (int)SL);
             h->launches++;
             local_fixups(h, k, beta, in, out, rp, skip);
             if (h->world > 1) {
                 /* speculative fixed point ACROSS ranks: exchange label slices, queue the local
                  * readers of every remote label that moved, fix up, until no rank queues anything
-                 * (then every rank holds the sequential sweep's labels for all families).  One
-                 * label all-gather + one counter all-gather + one host poll per round; the last
-                 * round's status (counters summed over the ranks, convergence decided on the
-                 * device when `decide` is given) doubles as the iteration's status. */
+                 * (then every rank holds the sequential sweep's labels for all families).  ONE
+                 * all-gather (the labels) and one host poll per round: every rank derives the
+                 * global pending / changed counts from the exchanged labels themselves
+                 * (k_mark_remote), and the last round's status -- convergence decided on the
+                 * device when `decide` is given -- doubles as the iteration's status. */
                 for (int guard = 0;; guard++) {
                     if ((rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
-                    CK(cudaMemsetAsync(&h->d_status->cnt.pending, 0, sizeof(int32_t), h->stream));
-                    nemk_mark_remote(h->stream, h->n_glob, row0, n, out, seen, h->d_dirty,
-                                     h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr, h->d_rcol,
-                                     &h->d_status->cnt.pending);
+                    CK(cudaMemsetAsync(&h->d_status->cnt.pending, 0, 2 * sizeof(int32_t), h->stream));   /* + changed_glob */
+                    nemk_mark_remote(h->stream, h->n_glob, row0, n, (int)SL, out, in, guard ? seen : in,
+                                     seen, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
+                                     h->d_rcol, &h->d_status->cnt, skip);
                     h->launches++;
-                    unsigned long long seq;
-                    if ((rc = publish_status(h, decide, &seq)) != NEMB_OK) return rc;
+                    unsigned long long seq = ++h->seq;
+                    nemk_iter_end(h->stream, 0, &h->d_status->cnt, h->d_status, h->d_coef,
+                                  decide && decide->conv != NEMB_CONV_CRIT, 1, decide ? decide->conv : 0,
+                                  decide ? decide->conv_thr : 0.f, h->d_ring + (seq % RING), seq);
+                    h->launches++;
+                    CKK();
                     if ((rc = wait_status(h, seq)) != NEMB_OK) return rc;
                     if (h->h_status->cnt.pending == 0 || *h->h_empty) break;
                     if (guard > h->n_glob) return fail(h, NEMB_E_BUG, "sharded sweep did not settle");
@@ -1041,6 +1046,13 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
          * (halt), otherwise (it_max cannot be hit here: want < it_max) it must not exist */
         if (!(converged || status != NEMB_OK)) return fail(h, NEMB_E_BUG, "speculative iteration left over");
         if (flips[(enq - 1) & 1]) h->cur ^= 1;
+    }
+    if (h->world > 1 && status == NEMB_OK && iter > 0) {
+        /* row shards: the per-iteration statuses of the speculative sweep carry this rank's
+         * all-null / tie counters only; one counter all-gather gives the totals of the last sweep */
+        if ((rc = read_status(h)) != NEMB_OK) return rc;
+        res->n_allnul = h->h_status->cnt.allnul;
+        res->n_ties = h->h_status->cnt.ties;
     }
     if (iter == 0) { /* nem_alg.c:1845-1851 */
         if ((rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;

@@ -774,10 +774,20 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
                     uint8_t *__restrict__ lab_out, int32_t *dirty, int32_t *wl, int32_t *wl_count,
                     const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
                     const int32_t *__restrict__ heavy, int n_heavy, int heavy_blocks,
-                    nemk_counters *cnt, const int32_t *__restrict__ skip) {
+                    nemk_counters *cnt, const int32_t *__restrict__ skip, int copy_ranks,
+                    int shard_len) {
     if (skip && (skip[0] | skip[1])) return;
     const int lane = threadIdx.x & 31;
     int changed = 0, flags = 0;
+    if ((int)blockIdx.x >= heavy_blocks && copy_ranks > 1) {
+        // row shards: the other ranks' labels start the sweep at their previous value
+        int q = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x;
+        if (q < shard_len) {
+            int mine = row0 / shard_len;
+            for (int r = 0; r < copy_ranks; r++)
+                if (r != mine) lab_out[(size_t)r * shard_len + q] = lab_in[(size_t)r * shard_len + q];
+        }
+    }
     if ((int)blockIdx.x < heavy_blocks) {
         // hubs first (longest work): one warp per site
         int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1009,29 +1019,44 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
     if (crank == 0 && threadIdx.x == 0 && rounds) atomicAdd(&cnt->nfix, rounds);
 }
 
-// Row-sharded sweep, after a label exchange: every remote site whose label differs from the one
-// this rank last saw queues the local sites that read it and are visited later.  `pending`
-// accumulates the number of queued sites (the ranks stop exchanging when the global sum is 0).
+// Row-sharded sweep, after a label exchange.  EVERY rank scans ALL families (1 byte each):
+//  - a label that differs from the one seen at the previous exchange has "moved": its later
+//    readers on OTHER ranks must be re-evaluated by their owners.  This rank queues the ones it
+//    owns; every (reader, moved label) pair across ranks is counted, so all ranks -- which hold the
+//    same labels and the same `seen` -- compute the SAME pending total without exchanging counters;
+//  - changed = labels that differ from the sweep's input labels, over all families (the
+//    convergence test of the iteration, again identical on every rank).
 __global__ void __launch_bounds__(256)
-k_mark_remote(int n_glob, int row0, int row1, const uint8_t *__restrict__ lab_cur, uint8_t *lab_seen,
+k_mark_remote(int n_glob, int row0, int row1, int shard_len, const uint8_t *__restrict__ lab_cur,
+              const uint8_t *__restrict__ lab_in, const uint8_t *seen_in, uint8_t *seen_out,
               int32_t *dirty, int32_t *wl, int32_t *wl_count, const int32_t *__restrict__ rrow_ptr,
-              const int32_t *__restrict__ rcol, int32_t *pending) {
-    int queued = 0;
+              const int32_t *__restrict__ rcol, nemk_counters *cnt,
+              const int32_t *__restrict__ skip) {
+    if (skip && (skip[0] | skip[1])) return;   // the sweep did not run: lab_cur holds nothing new
+    int pend = 0, changed = 0;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_glob; j += gridDim.x * blockDim.x) {
-        if (j >= row0 && j < row1) continue;
         uint8_t c = lab_cur[j];
-        if (c == lab_seen[j]) continue;
-        lab_seen[j] = c;
+        changed += c != lab_in[j];
+        bool moved = c != seen_in[j];
+        if (moved || seen_in != seen_out) seen_out[j] = c;
+        if (!moved) continue;
+        const int own_lo = (j / shard_len) * shard_len, own_hi = own_lo + shard_len;   // j's rank
+        const bool j_mine = j >= row0 && j < row1;
         int lo = rrow_ptr[j], hi = rrow_ptr[j + 1];
         for (int e = lo; e < hi; e++) {
             int i = rcol[e];
-            if (i > j && i >= row0 && i < row1 && atomicExch(&dirty[i], 1) == 0) {
+            if (i <= j || (i >= own_lo && i < own_hi)) continue;   // earlier, or same rank as j
+            pend++;
+            if (!j_mine && i >= row0 && i < row1 && atomicExch(&dirty[i], 1) == 0)
                 wl[atomicAdd(wl_count, 1)] = i;
-                queued++;
-            }
         }
     }
-    if (queued) atomicAdd(pending, queued);
+    pend = __reduce_add_sync(FULL, pend);
+    changed = __reduce_add_sync(FULL, changed);
+    if ((threadIdx.x & 31) == 0) {
+        if (pend) atomicAdd(&cnt->pending, pend);
+        if (changed) atomicAdd(&cnt->changed_glob, changed);
+    }
 }
 
 // ---- ncem, level-scheduled exact sequential sweep (reference order), in place.
@@ -1850,7 +1875,11 @@ __global__ void k_iter_end(int world, const nemk_counters *__restrict__ cnt_all,
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     nemk_counters tot;
     tot.changed = 0; tot.nfix = 0; tot.allnul = 0; tot.ties = 0; tot.maxdiff = 0.f; tot.pending = 0;
-    tot.pad[0] = 0; tot.pad[1] = 0;
+    tot.changed_glob = 0; tot.pad[0] = 0;
+    if (world == 0) {   // row-sharded speculative sweep: changed / pending are already global
+        tot = cnt_all[0];
+        tot.changed = tot.changed_glob;
+    }
     for (int r = 0; r < world; r++) {
         nemk_counters c = cnt_all[r];
         tot.changed += c.changed; tot.allnul += c.allnul; tot.ties += c.ties; tot.pending += c.pending;
@@ -2103,12 +2132,15 @@ extern "C" void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc
                                        const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
                                        int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
                                        const int32_t *rcol, const int32_t *heavy, int n_heavy,
-                                       nemk_counters *cnt, const int32_t *skip) {
-    if (n_loc <= 0) return;
-    int hb = (row_ptr && beta != 0.0 && heavy) ? cdiv((long long)n_heavy * 32, 256) : 0;
-    DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<hb + cdiv(n_loc, 256), 256, 0, S(s)>>>(
+                                       nemk_counters *cnt, const int32_t *skip, int copy_ranks,
+                                       int shard_len) {
+    if (n_loc <= 0 && copy_ranks <= 1) return;
+    int hb = (row_ptr && beta != 0.0 && heavy && n_loc > 0) ? cdiv((long long)n_heavy * 32, 256) : 0;
+    int cover = copy_ranks > 1 && shard_len > n_loc ? shard_len : n_loc;   // the copy spans a full slice
+    DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<hb + cdiv(cover, 256), 256, 0, S(s)>>>(
                       k, row0, n_loc, lps, row_ptr, col, wgt, beta, lab_in, lab_out, dirty, wl,
-                      wl_count, rrow_ptr, rcol, heavy, n_heavy, hb, cnt, skip)));
+                      wl_count, rrow_ptr, rcol, heavy, n_heavy, hb, cnt, skip, copy_ranks,
+                      shard_len)));
     note_launch();
 }
 
@@ -2151,15 +2183,16 @@ extern "C" void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int 
     note_launch();
 }
 
-extern "C" void nemk_mark_remote(nemk_stream s, int n_glob, int row0, int n_loc,
-                                 const uint8_t *lab_cur, uint8_t *lab_seen, int32_t *dirty,
+extern "C" void nemk_mark_remote(nemk_stream s, int n_glob, int row0, int n_loc, int shard_len,
+                                 const uint8_t *lab_cur, const uint8_t *lab_in,
+                                 const uint8_t *seen_in, uint8_t *seen_out, int32_t *dirty,
                                  int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
-                                 const int32_t *rcol, int32_t *pending) {
+                                 const int32_t *rcol, nemk_counters *cnt, const int32_t *skip) {
     if (n_glob <= 0) return;
     int grid = cdiv(n_glob, 256);
     if (grid > num_sms() * 8) grid = num_sms() * 8;
-    k_mark_remote<<<grid, 256, 0, S(s)>>>(n_glob, row0, row0 + n_loc, lab_cur, lab_seen, dirty, wl,
-                                          wl_count, rrow_ptr, rcol, pending);
+    k_mark_remote<<<grid, 256, 0, S(s)>>>(n_glob, row0, row0 + n_loc, shard_len, lab_cur, lab_in,
+                                          seen_in, seen_out, dirty, wl, wl_count, rrow_ptr, rcol, cnt, skip);
     note_launch();
 }
 
