@@ -44,6 +44,20 @@ C5_RUNS = 1024
 K = 3
 
 
+def measured_traffic(kernel_prefix):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture
+    (profiles/roofline_traffic.json, written from profiles/*_full.csv); None when absent."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        t = json.load(f)
+    for name, rec in t.items():
+        if name.startswith(kernel_prefix):
+            return rec.get("dram_bytes_per_launch"), rec.get("source")
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -66,7 +80,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                 "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -177,19 +191,21 @@ def main_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    vals, last = [], None
+    vals, last, t_steps = [], None, 0.0
     for step in range(args.warmup + args.steps):
+        t0 = time.time()
         last = cpu_baseline(args.workload, cores, budget_cells=2.0e7)
         if step >= args.warmup:
             vals.append(last["value"])
+            t_steps += time.time() - t0
     n, d, beta, graph = WORKLOADS[args.workload]
     v = float(np.mean(vals))
     last["value"] = v
     print(json.dumps({
         "impl": "reference", "metric": "NEM family-iterations/s", "value": v,
         "unit": "family-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": t_steps * 1e3 / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "families": n, "genomes": d, "K": K,
                    "beta": beta, "algo": "ncem", "update": "seq"},
         "cpu_baseline": last,
@@ -248,6 +264,9 @@ def main_c5(args):
     xh = xdev.cpu().numpy()
     row_ptr, col, wgt = synth_gpu.make_graph(n, xh, seed=42, kind=graph)
     masks, betas, sizes = c5_plan(d, runs)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if local_world * args.workers * 2 > (os.cpu_count() or 1):
+        os.environ.setdefault("NEM_B200_POLL", "relaxed")   # ranks x workers pollers share the host cores
     mine = np.arange(rank, runs, world)
     eng = capi.Engine(local)
     eng.load_packed(xh.view(np.uint32), d, row_ptr, col, wgt)
@@ -526,6 +545,7 @@ def main_ours(args):
         ms_dc = sum(x.stage_ms["density_cached"] for x in fits) / max(n_dc, 1)
         n_md = sum(x.stage_launches["mstep_delta"] for x in fits)
         ms_md = sum(x.stage_ms["mstep_delta"] for x in fits) / max(n_md, 1)
+        traffic, traffic_src = measured_traffic("k_density_tma") if args.workload == "c4" and not args.rows else (None, None)
         den_bytes = n * wb + n * tk                      # SURVEY 8d "E-step-only bytes (density)"
         achieved = den_bytes / (ms_den * 1e-3) / 1e9 if ms_den > 0 else 0.0
         ms_bytes = n * wb + n * tk                       # M-step: X once + t once
@@ -565,7 +585,8 @@ def main_ours(args):
                     "what": "nemb_load_shard(host pinned X + CSR: H2D, device-side graph validation) + nemb_fit + nemb_get_labels"},
             "roofline": {"bound": "hbm", "kernel": "k_density_tma (E-step Bernoulli log-likelihood, popcount path)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "bytes_per_launch": den_bytes, "avg_launch_ms": ms_den,
                          "launches_timed": n_den,
                          "note": ("achieved = algorithmic bytes of one X pass (N*Wb + N*K*4) / mean CUDA-event "

@@ -114,6 +114,19 @@ void nemk_heavy_list(nemk_stream s, int row0, int n_loc, const int32_t *row_ptr,
  * convergence test on the device (HasConverged `clas`, nem_alg.c:2075-2089: ncem = no label
  * changed, nem = max |t - t_old| < thr; conv: 0 none, 1 clas) and raise coef->halt when the fit is
  * over (converged or empty class), then publish everything to the mapped host slot. */
+/* The same work fused into the last kernel of a sweep (nemk_sweep_ncem_fixup): host == NULL = not
+ * fused. */
+typedef struct {
+    int32_t world;
+    const nemk_counters *cnt_all;
+    const nemk_iter_status *st;
+    nemk_coef *coef;
+    int32_t decide, ncem, conv;
+    float thr;
+    nemk_host_status *host;
+    unsigned long long seq;
+} nemk_iter_end_args;
+
 /* world == 0: cnt_all is this rank's counter block of a row-sharded speculative sweep; its
  * changed_glob / pending are already global (nemk_mark_remote), the other fields stay local */
 void nemk_iter_end(nemk_stream s, int world, const nemk_counters *cnt_all,
@@ -140,7 +153,8 @@ void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc
                            const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
                            const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a,
                            int32_t *wl_b, int32_t *wl_cnt, int round, const int32_t *rrow_ptr,
-                           const int32_t *rcol, nemk_counters *cnt, const int32_t *skip);
+                           const int32_t *rcol, nemk_counters *cnt, const int32_t *skip,
+                           const nemk_iter_end_args *fused /* nullable: publish the status too */);
 void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                                  const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                  double beta, const uint8_t *lab_old, uint8_t *lab_cur,
@@ -172,10 +186,10 @@ void nemk_sweep_nem_level(nemk_stream s, int k, const double *logpf, const int32
 /* lab_m (nullable): receives a copy of the labels = the state the statistics now describe */
 void nemk_label_masks(nemk_stream s, int k, int n, int nwt, const uint8_t *lab, uint32_t *cm,
                       int32_t *nk_int, uint8_t *lab_m, const int32_t *halt);
-/* incremental ncem statistics: rows whose label differs from lab_m move their bits from
- * S[old] to S[new] (exact integer updates), then lab_m = lab.  list needs n ints + 1 counter */
+/* incremental ncem statistics: rows whose label differs from lab_m (the labels S and n describe)
+ * move their bits from S[old] to S[new] (exact integer updates).  list: n ints + 1 counter */
 void nemk_mstep_delta(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x,
-                      const uint8_t *lab, uint8_t *lab_m, int32_t *list, int32_t *count,
+                      const uint8_t *lab, const uint8_t *lab_m, int32_t *list, int32_t *count,
                       int32_t *s_int, int32_t *nk_int, const int32_t *halt);
 void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint32_t *xt, const uint32_t *cm,
                      int32_t *s_int, const int32_t *halt);

@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 /* ------------------------------------------------------------------ errors */
 int nemb_i_fail(nemb_handle *h, int code, const char *fmt, ...)
@@ -675,7 +676,10 @@ static int wait_status(nemb_handle *h, unsigned long long seq)
 #if defined(__x86_64__) || defined(__i386__)
         __builtin_ia32_pause();
 #endif
-        if ((spins & 0xff) == 0) sched_yield();   /* several engines may poll on few cores */
+        if (h->poll_relaxed && spins > 64) {      /* resample workers: other streams keep the GPU busy */
+            struct timespec ts = {0, 2000};
+            nanosleep(&ts, NULL);
+        } else if ((spins & 0xff) == 0) sched_yield();   /* several engines may poll on few cores */
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
     const nemk_host_status *r = &h->ring[seq % RING];
@@ -710,7 +714,7 @@ static int read_status(nemb_handle *h)
  * one CTA walks the tail to exhaustion (and leaves the four counters at 0) */
 enum { GRID_ROUNDS = 3, SHORT_LIST = 32768 };
 static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, uint8_t *out,
-                         const int32_t *rp, const int32_t *skip)
+                         const int32_t *rp, const int32_t *skip, const nemk_iter_end_args *fused)
 {
     /* few labels moved last iteration => the work lists are short: the tail cluster walks them all */
     int grid_rounds = (h->last_changed >= 0 && h->last_changed < SHORT_LIST) ? 0 : GRID_ROUNDS;
@@ -721,7 +725,7 @@ static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, 
                                     skip);
     nemk_sweep_ncem_fixup(h->stream, k, h->row0, h->n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
                           out, h->d_dirty, h->d_wl[0], h->d_wl[1], h->d_wl_counts, grid_rounds,
-                          h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip);
+                          h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip, fused);
     h->launches += 1 + grid_rounds;
 }
 
@@ -759,7 +763,18 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
                                    h->d_rcol, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip,
                                    h->world, (int)SL);
             h->launches++;
-            local_fixups(h, k, beta, in, out, rp, skip);
+            if (h->world == 1 && decide) {
+                /* one GPU: the tail of the fix-up rounds ends the iteration -- it also decides
+                 * convergence and publishes the status (no separate nemk_iter_end launch) */
+                nemk_iter_end_args fa = {1, &h->d_status->cnt, h->d_status, h->d_coef,
+                                         decide->conv != NEMB_CONV_CRIT, 1, decide->conv, decide->conv_thr,
+                                         NULL, 0};
+                fa.seq = ++h->seq;
+                fa.host = h->d_ring + (fa.seq % RING);
+                local_fixups(h, k, beta, in, out, rp, skip, &fa);
+                if (status_read) *status_read = 1;
+            } else
+                local_fixups(h, k, beta, in, out, rp, skip, NULL);
             if (h->world > 1) {
                 /* speculative fixed point ACROSS ranks: exchange label slices, queue the local
                  * readers of every remote label that moved, fix up, until no rank queues anything
@@ -784,7 +799,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
                     if ((rc = wait_status(h, seq)) != NEMB_OK) return rc;
                     if (h->h_status->cnt.pending == 0 || *h->h_empty) break;
                     if (guard > h->n_glob) return fail(h, NEMB_E_BUG, "sharded sweep did not settle");
-                    local_fixups(h, k, beta, in, out, rp, skip);
+                    local_fixups(h, k, beta, in, out, rp, skip, NULL);
                 }
                 if (status_read) *status_read = 1;
             }
@@ -821,6 +836,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
     STAGE_END();
     CKK();
     if (*flipped) h->cur ^= 1;
+    h->prev_valid = *flipped;
     return NEMB_OK;
 }
 
@@ -828,7 +844,7 @@ static int run_mstep(nemb_handle *h, const nemb_options *o, int next_uniform)
 {
     int k = o->k, rc;
     size_t kd = (size_t)k * h->d, stat = kd + k;
-    int incremental = o->algo == NEMB_ALGO_NCEM && h->stats_valid && h->last_changed >= 0 &&
+    int incremental = o->algo == NEMB_ALGO_NCEM && h->stats_valid && h->prev_valid && h->last_changed >= 0 &&
                       h->last_changed <= h->n / 8 && !getenv("NEM_B200_FULL_MSTEP");
     STAGE_BEGIN(incremental ? ST_MSTEP_DELTA : ST_MSTEP);
     if (o->algo == NEMB_ALGO_NCEM) {
@@ -836,13 +852,15 @@ static int run_mstep(nemb_handle *h, const nemb_options *o, int next_uniform)
          * when the last sweep moved few labels -- an update from the rows that changed class */
         const uint8_t *lab_loc = h->d_lab[h->cur] + h->row0;
         if (incremental) {
-            nemk_mstep_delta(h->stream, k, h->n, h->d, h->wpr, h->d_x, lab_loc, h->d_lab[3],
+            /* the statistics describe the labels the last sweep started from: its other buffer */
+            nemk_mstep_delta(h->stream, k, h->n, h->d, h->wpr, h->d_x, lab_loc,
+                             h->d_lab[h->cur ^ 1] + h->row0,
                              h->d_wl[1], &h->d_wl_counts[4], h->d_stat_loc, h->d_stat_loc + kd,
                              &h->d_coef->halt);
         } else {
             if ((rc = ensure_xt(h)) != NEMB_OK) return rc;
             nemk_label_masks(h->stream, k, h->n, h->nwt, lab_loc, h->d_cm, h->d_stat_loc + kd,
-                             h->d_lab[3], &h->d_coef->halt);
+                             NULL, &h->d_coef->halt);
             nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_stat_loc,
                             &h->d_coef->halt);
             h->stats_valid = 1;
@@ -926,7 +944,7 @@ static int init_state(nemb_handle *h, const nemb_options *o)
     int rc;
     h->cur = 0;
     h->state_labels = o->algo == NEMB_ALGO_NCEM;
-    h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1;
+    h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1; h->prev_valid = 0;
     if (h->state_labels) CK(cudaMemsetAsync(h->d_lab[0], 255, h->lab_len, h->stream));
     else {
         if ((rc = ensure_t(h, o->k, 1)) != NEMB_OK) return rc;

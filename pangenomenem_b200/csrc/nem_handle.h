@@ -43,6 +43,7 @@ struct nemb_handle {
     dbuf b_x, b_xt, b_row_ptr, b_col, b_wgt, b_rrow_ptr, b_rcol, b_sites, b_level_ptr, b_flags, b_heavy;
     dbuf b_sub, b_index;   /* resample driver: builder scratch; original family id of every row */
     int32_t *d_index;      /* non-NULL when this problem is a device-built subsample */
+    int poll_relaxed;      /* status polling sleeps between probes (resample workers share the cores) */
     int32_t *d_heavy;      /* index-sorted hubs among this rank's rows */
     int n_heavy;
     int32_t *d_row_ptr, *d_col, *d_rrow_ptr, *d_rcol, *d_sites, *d_level_ptr;
@@ -63,6 +64,7 @@ struct nemb_handle {
                               labels the M-step statistics currently describe (local rows) */
     int32_t *d_ham;        /* cached Hamming counts H[n][K] of the popcount density path */
     int ham_valid, stats_valid, tables_forced;
+    int prev_valid;        /* d_lab[cur ^ 1] holds the input labels of the last sweep (it flipped) */
     int lp_from_ham;       /* the consumers rebuild logpf from d_ham in registers (no logpf array) */
     int64_t last_changed;  /* labels moved by the last sweep (all ranks), -1 = unknown */
     float *d_t[2];

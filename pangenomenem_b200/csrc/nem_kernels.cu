@@ -980,6 +980,11 @@ k_sweep_ncem_fixup_round(int K, int row0, int row1, const nemk_lpsrc lps,
     if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(&cnt->nfix, 1);
 }
 
+static __device__ void iter_end_body(int world, const nemk_counters *cnt_all,
+                                     const nemk_iter_status *st, nemk_coef *coef, int decide,
+                                     int ncem, int conv, float thr, nemk_host_status *host,
+                                     unsigned long long seq);
+
 // Tail of the fix-up rounds in ONE launch: a thread-block cluster of FX_CLUSTER CTAs loops over the
 // rounds with a hardware cluster barrier between them (release/acquire at cluster scope, after a
 // device fence for the label/work-list stores) until the work list is empty.
@@ -992,11 +997,16 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
                    uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a, int32_t *wl_b,
                    int32_t *wl_cnt, int round, const int32_t *__restrict__ rrow_ptr,
                    const int32_t *__restrict__ rcol, nemk_counters *cnt,
-                   const int32_t *__restrict__ skip) {
-    if (skip && (skip[0] | skip[1])) return;
+                   const int32_t *__restrict__ skip, const nemk_iter_end_args fused) {
     namespace cgx = cooperative_groups;
     cgx::cluster_group cluster = cgx::this_cluster();
     const int crank = (int)cluster.block_rank();
+    if (skip && (skip[0] | skip[1])) {   // nothing ran: the status is still due
+        if (fused.host && crank == 0 && threadIdx.x == 0)
+            iter_end_body(fused.world, fused.cnt_all, fused.st, fused.coef, fused.decide, fused.ncem,
+                          fused.conv, fused.thr, fused.host, fused.seq);
+        return;
+    }
     int rounds = 0, dchanged = 0;
     for (;; round++) {
         int32_t *cur_list = (round & 1) ? wl_b : wl_a, *next_list = (round & 1) ? wl_a : wl_b;
@@ -1017,6 +1027,13 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
     if (crank == 0 && threadIdx.x < 4) wl_cnt[threadIdx.x] = 0;
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
     if (crank == 0 && threadIdx.x == 0 && rounds) atomicAdd(&cnt->nfix, rounds);
+    if (fused.host) {   // end of the sweep = end of the iteration: decide + publish here (k_iter_end)
+        __threadfence();
+        cluster.sync();
+        if (crank == 0 && threadIdx.x == 0)
+            iter_end_body(fused.world, fused.cnt_all, fused.st, fused.coef, fused.decide, fused.ncem,
+                          fused.conv, fused.thr, fused.host, fused.seq);
+    }
 }
 
 // Row-sharded sweep, after a label exchange.  EVERY rank scans ALL families (1 byte each):
@@ -1304,8 +1321,9 @@ k_mstep_ncem(int K, int D, int nwt4, const uint4 *__restrict__ xt, const uint4 *
 // ncem, incremental statistics.  After the first iterations only a few hundred families change
 // class per sweep (the centres stop moving), so instead of re-reading X^T
 // (N*D/8 bytes) the statistics are UPDATED: every row whose label differs from lab_m (the labels
-// S and n currently describe) moves its bits from S[old] to S[new].  Integer adds: exact, and the
-// result equals the full recount whatever the order.
+// S and n currently describe = the input labels of the last sweep, which the sweep leaves intact in
+// its other buffer) moves its bits from S[old] to S[new].  Integer adds: exact, and the result
+// equals the full recount whatever the order.
 __global__ void __launch_bounds__(256)
 k_changed_rows(int n, const uint8_t *__restrict__ lab, const uint8_t *__restrict__ lab_m,
                int32_t *list, int32_t *count, const int32_t *__restrict__ halt) {
@@ -1386,19 +1404,6 @@ k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8
                 }
             }
         }
-    }
-}
-
-// lab_m <- lab for the rows of the list (after every item of k_mstep_delta has read lab_m)
-__global__ void __launch_bounds__(256)
-k_commit_labels(const uint8_t *__restrict__ lab, uint8_t *__restrict__ lab_m,
-                const int32_t *__restrict__ list, const int32_t *__restrict__ count,
-                const int32_t *__restrict__ halt) {
-    if (halt && *halt) return;
-    int total = *count;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        int row = list[idx];
-        lab_m[row] = lab[row];
     }
 }
 
@@ -1868,23 +1873,24 @@ k_graph_check(int n, int nnz, const int32_t *__restrict__ row_ptr,
 // memcpy, no stream synchronisation, and it may already have enqueued the next iteration (whose
 // kernels all return at once when halt is set).
 // =============================================================================================
-__global__ void k_iter_end(int world, const nemk_counters *__restrict__ cnt_all,
-                           const nemk_iter_status *__restrict__ st, nemk_coef *coef, int decide,
-                           int ncem, int conv, float thr, nemk_host_status *host,
-                           unsigned long long seq) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+static __device__ void iter_end_body(int world, const nemk_counters *cnt_all,
+                                     const nemk_iter_status *st, nemk_coef *coef, int decide,
+                                     int ncem, int conv, float thr, nemk_host_status *host,
+                                     unsigned long long seq) {
     nemk_counters tot;
     tot.changed = 0; tot.nfix = 0; tot.allnul = 0; tot.ties = 0; tot.maxdiff = 0.f; tot.pending = 0;
     tot.changed_glob = 0; tot.pad[0] = 0;
+    const volatile nemk_counters *vc = cnt_all;   // written by atomics of this very launch when fused
     if (world == 0) {   // row-sharded speculative sweep: changed / pending are already global
-        tot = cnt_all[0];
-        tot.changed = tot.changed_glob;
+        tot.changed = vc[0].changed_glob; tot.nfix = vc[0].nfix; tot.allnul = vc[0].allnul;
+        tot.ties = vc[0].ties; tot.maxdiff = vc[0].maxdiff; tot.pending = vc[0].pending;
+        tot.changed_glob = vc[0].changed_glob;
     }
     for (int r = 0; r < world; r++) {
-        nemk_counters c = cnt_all[r];
-        tot.changed += c.changed; tot.allnul += c.allnul; tot.ties += c.ties; tot.pending += c.pending;
-        tot.nfix = max(tot.nfix, c.nfix);
-        tot.maxdiff = fmaxf(tot.maxdiff, c.maxdiff);
+        tot.changed += vc[r].changed; tot.allnul += vc[r].allnul; tot.ties += vc[r].ties;
+        tot.pending += vc[r].pending;
+        tot.nfix = max(tot.nfix, vc[r].nfix);
+        tot.maxdiff = fmaxf(tot.maxdiff, vc[r].maxdiff);
     }
     int halt = coef->halt, empty = coef->empty_class;
     if (decide && !halt && tot.pending == 0) {   // pending != 0: a row-sharded sweep is not settled yet
@@ -1901,6 +1907,14 @@ __global__ void k_iter_end(int world, const nemk_counters *__restrict__ cnt_all,
     host->empty_class = empty; host->mu_changed = coef->mu_changed; host->halt = halt; host->pad = 0;
     __threadfence_system();
     *(volatile unsigned long long *)&host->seq = seq;
+}
+
+__global__ void k_iter_end(int world, const nemk_counters *__restrict__ cnt_all,
+                           const nemk_iter_status *__restrict__ st, nemk_coef *coef, int decide,
+                           int ncem, int conv, float thr, nemk_host_status *host,
+                           unsigned long long seq) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    iter_end_body(world, cnt_all, st, coef, decide, ncem, conv, thr, host, seq);
 }
 
 // =============================================================================================
@@ -2160,11 +2174,21 @@ extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc,
                                       double beta, const uint8_t *lab_old, uint8_t *lab_cur,
                                       int32_t *dirty, int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt,
                                       int round, const int32_t *rrow_ptr, const int32_t *rcol,
-                                      nemk_counters *cnt, const int32_t *skip) {
-    if (n_loc <= 0) return;
+                                      nemk_counters *cnt, const int32_t *skip,
+                                      const nemk_iter_end_args *fused) {
+    nemk_iter_end_args fa;
+    memset(&fa, 0, sizeof fa);
+    if (fused) fa = *fused;
+    if (n_loc <= 0) {
+        if (fa.host)
+            k_iter_end<<<1, 32, 0, S(s)>>>(fa.world, fa.cnt_all, fa.st, fa.coef, fa.decide, fa.ncem,
+                                           fa.conv, fa.thr, fa.host, fa.seq);
+        note_launch();
+        return;
+    }
     DISPATCH_K(k, (k_sweep_ncem_fixup<KT><<<FX_CLUSTER, 1024, 0, S(s)>>>(
                       k, row0, row0 + n_loc, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
-                      wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip)));
+                      wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip, fa)));
     note_launch();
 }
 
@@ -2299,7 +2323,7 @@ extern "C" void nemk_mstep_ncem(nemk_stream s, int k, int d, int nwt, const uint
 }
 
 extern "C" void nemk_mstep_delta(nemk_stream s, int k, int n, int d, int wpr, const uint32_t *x,
-                                 const uint8_t *lab, uint8_t *lab_m, int32_t *list, int32_t *count,
+                                 const uint8_t *lab, const uint8_t *lab_m, int32_t *list, int32_t *count,
                                  int32_t *s_int, int32_t *nk_int, const int32_t *halt) {
     if (n <= 0) return;
     cudaMemsetAsync(count, 0, sizeof(int32_t), S(s));
@@ -2308,8 +2332,6 @@ extern "C" void nemk_mstep_delta(nemk_stream s, int k, int n, int d, int wpr, co
     int grid = num_sms() * 4;
     DISPATCH_K(k, (k_mstep_delta<KT><<<grid, 256, 0, S(s)>>>(k, d, wpr, x, lab, lab_m, list, count,
                                                             s_int, nk_int, halt)));
-    note_launch();
-    k_commit_labels<<<num_sms(), 256, 0, S(s)>>>(lab, lab_m, list, count, halt);
     note_launch();
 }
 

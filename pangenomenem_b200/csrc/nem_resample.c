@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <sys/prctl.h>
 
 static int round_up4(int v) { return (v + 3) / 4 * 4; }
 static size_t carve(size_t *off, size_t bytes)
@@ -176,7 +177,7 @@ static int psc_consistent(int d, const float *center, const float *disp)
 
 typedef struct {
     nemb_handle *src;
-    int n_runs, wm, failed_rc;
+    int n_runs, wm, failed_rc, relaxed;
     const uint32_t *masks;
     const float *betas;
     const nemb_options *opt;
@@ -194,6 +195,7 @@ static void *batch_worker(void *arg)
     batch_ctx *c = arg;
     nemb_handle *h = NULL;
     int rc = nemb_create(&h, c->src->device);
+    if (rc == NEMB_OK && c->relaxed) { h->poll_relaxed = 1; prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0); }
     float *theta = NULL;
     int cap_d = 0;
     nemb_batch_stats loc;
@@ -256,14 +258,18 @@ int nemb_resample_batch(nemb_handle *src, int n_runs, const uint32_t *genome_mas
     if (n_workers < 1) n_workers = 8;
     if (n_workers > 32) n_workers = 32;
     long cores = sysconf(_SC_NPROCESSORS_ONLN);   /* every worker polls its status slot: leave cores free */
-    if (cores > 0 && n_workers > cores / 2) n_workers = cores / 2 > 0 ? (int)(cores / 2) : 1;
+    if (cores > 0 && n_workers > cores) n_workers = (int)cores;
+    /* more pollers than spare cores (several ranks per node count too: NEM_B200_POLL=relaxed) =>
+     * the workers sleep ~2 us between status probes instead of spinning */
+    const char *pe = getenv("NEM_B200_POLL");
+    int relaxed = pe ? !strcmp(pe, "relaxed") : (cores > 0 && n_workers > cores / 2);
     if (n_workers > n_runs && n_runs > 0) n_workers = n_runs;
     CK(cudaSetDevice(src->device));
     CK(cudaStreamSynchronize(src->stream));   /* the source is read-only from here on */
     batch_ctx c;
     memset(&c, 0, sizeof c);
     c.src = src; c.n_runs = n_runs; c.wm = (src->d + 31) / 32; c.masks = genome_masks; c.betas = betas;
-    c.opt = opt; c.edge_bits = edge_presence_dev; c.iters_out = iters_out; c.failed_rc = NEMB_OK;
+    c.opt = opt; c.edge_bits = edge_presence_dev; c.relaxed = relaxed; c.iters_out = iters_out; c.failed_rc = NEMB_OK;
     pthread_mutex_init(&c.mu, NULL);
     size_t vbytes = sizeof(int32_t) * 4 * (size_t)src->n;
     CK(cudaMalloc((void **)&c.d_votes, vbytes));
