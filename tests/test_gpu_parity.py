@@ -303,3 +303,53 @@ def test_fit_it_max_zero_and_k_other_than_3(engine, oracle):
         assert got.status == ref.status and got.iters == ref.iters
         if ref.status == 0:
             assert np.array_equal(engine.labels(), ref.label)
+
+
+@pytest.mark.parametrize("it_max", [1, 2, 3, 5, 8, 9, 10, 30])
+def test_speculative_iterations_change_nothing(engine, oracle, it_max, monkeypatch):
+    """The EM loop enqueues iteration i+1 before the status of iteration i is known (device halt
+    flag, nem_fit.c em_core); whatever it_max cuts, the fit must equal the synchronous loop and
+    the oracle: same iteration count, labels, theta, criteria."""
+    pg = make_case(20000, 50, seed=42)
+    theta = oracle.default_theta(3, pg.d)
+    kw = dict(k=3, algo="ncem", update="seq", disp="sk_", prop="pk", beta=0.5, it_max=it_max)
+    ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(*theta)
+    engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
+    out = []
+    for no_spec in ("", "1"):
+        if no_spec:
+            monkeypatch.setenv("NEM_B200_NO_SPEC", "1")
+        else:
+            monkeypatch.delenv("NEM_B200_NO_SPEC", raising=False)
+        for _ in range(2):                      # twice: a halted fit must leave the handle clean
+            got = engine.fit(*theta, **kw)
+            out.append((got, engine.labels()))
+    for got, lab in out:
+        assert got.iters == ref.iters and got.converged == ref.converged
+        assert np.array_equal(lab, ref.label)
+        assert np.array_equal(got.center, ref.center) and np.array_equal(got.disp, ref.disp)
+        assert np.array_equal(got.prop, ref.prop)
+        for c in "UDL":
+            assert abs(got.crit[c] - ref.crit[c]) <= 1e-6 * abs(ref.crit[c])
+
+
+def test_empty_class_then_the_handle_recovers(engine, oracle):
+    """An M-step that empties a class aborts the loop (nem_alg.c:1831-1838: E-step not run, no
+    further iteration); the device halt flag it raises must not leak into the next fit."""
+    pg = make_case(4000, 40, seed=3, graph="random")
+    prop = np.array([0.4, 0.4, 0.2], dtype=np.float32)
+    center = np.repeat(np.array([1.0, 0.0, 1.0], dtype=np.float32)[:, None], pg.d, axis=1)
+    center[2, ::2] = 0.0                                   # a pattern no family matches exactly
+    disp = np.repeat(np.array([0.1, 0.1, 1e-30], dtype=np.float32)[:, None], pg.d, axis=1)
+    kw = dict(k=3, algo="ncem", update="seq", disp="sk_", prop="pk", beta=0.5, it_max=50)
+    ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(prop, center, disp)
+    assert ref.status == 1                                 # W_EMPTYCLASS
+    engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
+    got = engine.fit(prop, center, disp, **kw)
+    assert got.status == ref.status and got.iters == ref.iters and got.empty_class == 3
+    assert np.array_equal(engine.labels(), ref.label)
+    theta = oracle.default_theta(3, pg.d)
+    ok = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(*theta)
+    again = engine.fit(*theta, **kw)
+    assert again.status == 0 and again.iters == ok.iters
+    assert np.array_equal(engine.labels(), ok.label)
