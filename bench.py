@@ -428,6 +428,13 @@ def main_ours(args):
     xhost.copy_(xdev)
     torch.cuda.synchronize()
     xh = xhost.numpy()
+
+    def pinned(a):      # e2e inputs live in pinned host memory (bench contract)
+        if a is None:
+            return None
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
     if beta != 0 and graph != "none":
         if mode == "sharded":
             row_ptr, col, wgt = build_global_graph(torch, dist, dev, rank, world, n, xh, 42, graph)
@@ -435,6 +442,7 @@ def main_ours(args):
             row_ptr, col, wgt = synth_gpu.make_graph(n, xh, seed=42 + rank, kind=graph)
     else:
         row_ptr = col = wgt = None
+    row_ptr, col, wgt = pinned(row_ptr), pinned(col), pinned(wgt)
     gen_s = time.time() - t0
     nnz = 0 if col is None else int(col.shape[0])
     theta0 = synth.default_theta(K, d)

@@ -79,6 +79,10 @@ typedef struct {
 void nemk_pack_u8(nemk_stream s, const uint8_t *x, int n, int d, int wpr, uint32_t *out);
 void nemk_transpose_bits(nemk_stream s, const uint32_t *x, int n, int wpr, int d, int nwt,
                          uint32_t *xt);
+/* the rows [row_base, row_base+rows) of x only (row_base % 256 == 0) into an already zeroed xt:
+ * lets the loader transpose chunk by chunk behind the host->device copy */
+void nemk_transpose_bits_rows(nemk_stream s, const uint32_t *x, int row_base, int rows, int wpr,
+                              int d, int nwt, uint32_t *xt);
 
 /* ---- theta -> tables */
 void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const float *prop,

@@ -150,6 +150,9 @@ void nemb_destroy(nemb_handle *h)
     if (h->h_cnt_all) cudaFreeHost(h->h_cnt_all);
     if (h->h_empty) cudaFreeHost(h->h_empty);
     if (h->ring) cudaFreeHost(h->ring);
+    if (h->h_lab_stage) cudaFreeHost(h->h_lab_stage);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 16; i++) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
     for (int i = 0; i < h->ev_cap; i++) cudaEventDestroy(h->ev[i]);
     free(h->ev); free(h->ev_kind);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -342,8 +345,28 @@ int nemb_load_shard(nemb_handle *h, int n_glob, int row0, int n_loc, int d, int 
     if ((rc = reserve(h, &h->b_x, bytes)) != NEMB_OK) return rc;
     h->d_x = h->b_x.p;
     h->x_owned = 1;
+    int pre_xt = 0;
     if (n_loc > 0) {
-        if (wpr_dev == wpr) {
+        if (wpr_dev == wpr && bytes >= ((size_t)64 << 20) && !getenv("NEM_B200_PLAIN_UPLOAD")) {
+            /* large X: upload in chunks on a copy stream and transpose every chunk (X^T feeds the
+             * first M-step) on the engine's stream as soon as it has landed, so the transpose and
+             * the graph upload/validation below hide behind the PCIe transfer */
+            int nwt = round_up((n_loc + 31) / 32, 4);
+            if (nwt < 4) nwt = 4;
+            if ((rc = reserve(h, &h->b_xt, sizeof(uint32_t) * (size_t)d * nwt)) != NEMB_OK) return rc;
+            if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            CK(cudaMemsetAsync(h->b_xt.p, 0, sizeof(uint32_t) * (size_t)d * nwt, h->stream));
+            int chunks = 8;
+            int rows_per = round_up((n_loc + chunks - 1) / chunks, 256);
+            for (int c = 0, r0 = 0; r0 < n_loc; c++, r0 += rows_per) {
+                int rows = n_loc - r0 < rows_per ? n_loc - r0 : rows_per;
+                if (!h->copy_ev[c]) CK(cudaEventCreateWithFlags(&h->copy_ev[c], cudaEventDisableTiming));
+                CK(cudaMemcpyAsync(h->d_x + (size_t)r0 * wpr, x + (size_t)r0 * wpr,
+                                   sizeof(uint32_t) * (size_t)rows * wpr, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaEventRecord(h->copy_ev[c], h->copy_stream));
+            }
+            pre_xt = rows_per;
+        } else if (wpr_dev == wpr) {
             CK(cudaMemcpyAsync(h->d_x, x, bytes, cudaMemcpyHostToDevice, h->stream));
         } else {
             CK(cudaMemsetAsync(h->d_x, 0, bytes, h->stream));
@@ -353,7 +376,20 @@ int nemb_load_shard(nemb_handle *h, int n_glob, int row0, int n_loc, int d, int 
         }
     }
     h->wpr = wpr_dev;
-    return load_common(h, n_glob, row0, n_loc, d, row_ptr, col, wgt);
+    /* the graph goes up and is validated on the engine's stream while X is still in flight */
+    rc = load_common(h, n_glob, row0, n_loc, d, row_ptr, col, wgt);
+    if (pre_xt) {
+        for (int c = 0, r0 = 0; r0 < n_loc; c++, r0 += pre_xt) {
+            int rows = n_loc - r0 < pre_xt ? n_loc - r0 : pre_xt;
+            cudaStreamWaitEvent(h->stream, h->copy_ev[c], 0);
+            nemk_transpose_bits_rows(h->stream, h->d_x, r0, rows, wpr_dev, d, h->nwt, h->b_xt.p);
+        }
+        /* the caller may reuse its buffer when we return */
+        cudaError_t e = cudaStreamSynchronize(h->copy_stream);
+        if (e != cudaSuccess && rc == NEMB_OK) rc = fail(h, NEMB_E_CUDA, "X upload: %s", cudaGetErrorString(e));
+        if (rc == NEMB_OK) { h->d_xt = h->b_xt.p; h->have_xt = 1; }
+    }
+    return rc;
 }
 
 int nemb_load_shard_device(nemb_handle *h, int n_glob, int row0, int n_loc, int d, int wpr,
@@ -1175,13 +1211,16 @@ int nemb_get_labels(nemb_handle *h, int32_t *label_out)
         nemk_t_to_labels(h->stream, h->k_alloc, n, h->d_t[h->cur], src);
         CKK();
     }
-    uint8_t *tmp = malloc(n);
-    if (!tmp) return fail(h, NEMB_E_MEMORY, "host alloc");
-    cudaError_t e = cudaMemcpyAsync(tmp, src, n, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) { free(tmp); return fail(h, NEMB_E_CUDA, "%s", cudaGetErrorString(e)); }
-    for (int i = 0; i < n; i++) label_out[i] = tmp[i] == 255 ? -1 : tmp[i];
-    free(tmp);
+    if (h->h_lab_cap < (size_t)n) {      /* pinned staging, grow-only */
+        if (h->h_lab_stage) cudaFreeHost(h->h_lab_stage);
+        h->h_lab_stage = NULL; h->h_lab_cap = 0;
+        CK(cudaMallocHost((void **)&h->h_lab_stage, (size_t)n + 64));
+        h->h_lab_cap = (size_t)n + 64;
+    }
+    const uint8_t *tmp = h->h_lab_stage;
+    CK(cudaMemcpyAsync(h->h_lab_stage, src, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; i++) label_out[i] = tmp[i] == 255 ? -1 : (int32_t)tmp[i];
     return NEMB_OK;
 }
 

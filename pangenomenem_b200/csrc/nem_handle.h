@@ -43,6 +43,10 @@ struct nemb_handle {
     dbuf b_x, b_xt, b_row_ptr, b_col, b_wgt, b_rrow_ptr, b_rcol, b_sites, b_level_ptr, b_flags, b_heavy;
     dbuf b_sub, b_index;   /* resample driver: builder scratch; original family id of every row */
     int32_t *d_index;      /* non-NULL when this problem is a device-built subsample */
+    cudaStream_t copy_stream;   /* loader: chunked upload of X, overlapped with the transposes */
+    cudaEvent_t copy_ev[16];
+    uint8_t *h_lab_stage;       /* pinned staging of the labels read-back */
+    size_t h_lab_cap;
     int poll_relaxed;      /* status polling sleeps between probes (resample workers share the cores) */
     int32_t *d_heavy;      /* index-sorted hubs among this rank's rows */
     int n_heavy;

@@ -123,11 +123,11 @@ static __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
 
 #define TB_ROWS 256
 __global__ void __launch_bounds__(256)
-k_transpose_bits(const uint32_t *__restrict__ x, int n, int wpr, int d, int nwt,
+k_transpose_bits(const uint32_t *__restrict__ x, int row_base, int n, int wpr, int d, int nwt,
                  uint32_t *__restrict__ xt) {
     __shared__ uint32_t smem_t[1024 * 9];   // >= TB_ROWS*33; reused as out[1024][9]
     uint32_t (*tile)[33] = reinterpret_cast<uint32_t (*)[33]>(smem_t);
-    const int r0 = blockIdx.x * TB_ROWS, w0 = blockIdx.y * 32;
+    const int r0 = row_base + blockIdx.x * TB_ROWS, w0 = blockIdx.y * 32;   // row_base: multiple of TB_ROWS
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 8 warps
     for (int rr = wid; rr < TB_ROWS; rr += 8) {
         int r = r0 + rr, w = w0 + lane;
@@ -147,7 +147,7 @@ k_transpose_bits(const uint32_t *__restrict__ x, int n, int wpr, int d, int nwt,
 #pragma unroll
     for (int b = 0; b < 32; b++) outw[b * 32 + lane][wid] = a[b];   // slot b*32+c: conflict-free
     __syncthreads();
-    const int g8 = blockIdx.x * 8;   // first output word of this CTA's 256 families
+    const int g8 = (r0 >> 5);        // first output word of this CTA's 256 families
     for (int q = threadIdx.x; q < 1024; q += 256) {
         int dd = (w0 + (q & 31)) * 32 + (q >> 5);   // slot q = b*32 + c  ->  genome (w0+c)*32 + b
         if (dd >= d) continue;
@@ -1970,7 +1970,16 @@ extern "C" void nemk_transpose_bits(nemk_stream s, const uint32_t *x, int n, int
     cudaMemsetAsync(xt, 0, (size_t)d * nwt * sizeof(uint32_t), S(s));
     if (n <= 0) return;
     dim3 grid(cdiv(n, TB_ROWS), cdiv(wpr, 32));
-    k_transpose_bits<<<grid, 256, 0, S(s)>>>(x, n, wpr, d, nwt, xt);
+    k_transpose_bits<<<grid, 256, 0, S(s)>>>(x, 0, n, wpr, d, nwt, xt);
+    note_launch();
+}
+
+// rows [row_base, row_base + rows) only (row_base a multiple of 256); xt must have been zeroed
+extern "C" void nemk_transpose_bits_rows(nemk_stream s, const uint32_t *x, int row_base, int rows,
+                                         int wpr, int d, int nwt, uint32_t *xt) {
+    if (rows <= 0) return;
+    dim3 grid(cdiv(rows, TB_ROWS), cdiv(wpr, 32));
+    k_transpose_bits<<<grid, 256, 0, S(s)>>>(x, row_base, row_base + rows, wpr, d, nwt, xt);
     note_launch();
 }
 
