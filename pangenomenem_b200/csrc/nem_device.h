@@ -97,6 +97,11 @@ void nemk_theta_tables(nemk_stream s, int k, int d, int wpr, const float *prop,
 void nemk_density_uniform(nemk_stream s, int k, int d, const uint32_t *x, int n, int wpr,
                           const nemk_coef *coef, const uint32_t *mask_xor,
                           const uint32_t *mask_valid, double *logpf, int32_t *hamming, int cached);
+/* pop[i] = popc(x_i) (theta-independent; rows [0,n) of the x pointer given) */
+void nemk_row_popcount(nemk_stream s, const uint32_t *x, int n, int wpr, int32_t *pop);
+/* every class has a constant centre (coef->kind 1/2/3): H = P, D - P or 0 without reading X */
+void nemk_ham_from_pop(nemk_stream s, int k, int n, int d, const nemk_coef *coef,
+                       const int32_t *pop, int32_t *ham);
 /* runs only when !coef->mu_changed: logpf from the cached Hamming counts */
 void nemk_logpf_from_cache(nemk_stream s, int k, int n, const nemk_coef *coef,
                            const int32_t *hamming, double *logpf);

@@ -129,7 +129,7 @@ static void reset_problem(nemb_handle *h)
     free(h->h_level); free(h->steps);
     h->h_level = NULL; h->steps = NULL;
     h->n_steps = 0; h->loaded = 0; h->have_xt = 0; h->have_levels = 0; h->depth = 0;
-    h->d_index = NULL;
+    h->d_index = NULL; h->have_pop = 0;
     h->k_alloc = 0;
 }
 
@@ -142,7 +142,7 @@ void nemb_destroy(nemb_handle *h)
     cudaStreamSynchronize(h->stream);
     reset_problem(h);
     dbuf *all[] = {&h->b_x, &h->b_xt, &h->b_row_ptr, &h->b_col, &h->b_wgt, &h->b_rrow_ptr,
-                   &h->b_rcol, &h->b_sites, &h->b_level_ptr, &h->b_flags, &h->b_heavy, &h->b_sub, &h->b_index,
+                   &h->b_rcol, &h->b_sites, &h->b_level_ptr, &h->b_flags, &h->b_heavy, &h->b_sub, &h->b_index, &h->b_pop,
                    &h->b_slab, &h->b_t[0],
                    &h->b_t[1], &h->b_nem};
     for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) release(all[i]);
@@ -354,6 +354,7 @@ int nemb_load_shard(nemb_handle *h, int n_glob, int row0, int n_loc, int d, int 
             int nwt = round_up((n_loc + 31) / 32, 4);
             if (nwt < 4) nwt = 4;
             if ((rc = reserve(h, &h->b_xt, sizeof(uint32_t) * (size_t)d * nwt)) != NEMB_OK) return rc;
+            if ((rc = reserve(h, &h->b_pop, sizeof(int32_t) * (size_t)n_loc)) != NEMB_OK) return rc;
             if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
             CK(cudaMemsetAsync(h->b_xt.p, 0, sizeof(uint32_t) * (size_t)d * nwt, h->stream));
             int chunks = 8;
@@ -383,11 +384,13 @@ int nemb_load_shard(nemb_handle *h, int n_glob, int row0, int n_loc, int d, int 
             int rows = n_loc - r0 < pre_xt ? n_loc - r0 : pre_xt;
             cudaStreamWaitEvent(h->stream, h->copy_ev[c], 0);
             nemk_transpose_bits_rows(h->stream, h->d_x, r0, rows, wpr_dev, d, h->nwt, h->b_xt.p);
+            if (h->b_pop.p) nemk_row_popcount(h->stream, h->d_x + (size_t)r0 * wpr_dev, rows, wpr_dev, (int32_t *)h->b_pop.p + r0);
         }
         /* the caller may reuse its buffer when we return */
         cudaError_t e = cudaStreamSynchronize(h->copy_stream);
         if (e != cudaSuccess && rc == NEMB_OK) rc = fail(h, NEMB_E_CUDA, "X upload: %s", cudaGetErrorString(e));
         if (rc == NEMB_OK) { h->d_xt = h->b_xt.p; h->have_xt = 1; }
+        if (rc == NEMB_OK && h->b_pop.p) { h->d_pop = h->b_pop.p; h->have_pop = 1; }
     }
     return rc;
 }
@@ -601,18 +604,37 @@ static void stage_mark(nemb_handle *h, int kind_or_end)
 #define STAGE_BEGIN(kind) stage_mark(h, (kind))
 #define STAGE_END() stage_mark(h, -1)
 
-/* popcount-path eligibility of theta, evaluated on the host copy (mirrors k_theta_tables) */
+/* popcount-path eligibility of theta, evaluated on the host copy (mirrors k_theta_tables):
+ * 0 = general path, 1 = popcount path, 2 = popcount path and every class has a constant centre
+ * (all 0, all 1 or all 1/2: the Hamming counts follow from the row popcounts alone) */
 static int theta_uniform(int k, int d, const float *center, const float *disp)
 {
+    int all_const = 1;
     for (int c = 0; c < k; c++) {
         float e0 = disp[(size_t)c * d];
+        int n_valid = 0, n_x1 = 0;
         for (int j = 0; j < d; j++) {
             float mu = center[(size_t)c * d + j], e = disp[(size_t)c * d + j];
             int m0 = abs((int)(0.0f - mu)), m1 = abs((int)(1.0f - mu));
             if (memcmp(&e, &e0, sizeof e) || m0 > 1 || m1 > 1) return 0;
+            n_valid += m0 != m1; n_x1 += m0 == 1 && m1 == 0;
         }
+        if (!(n_valid == 0 || (n_valid == d && (n_x1 == 0 || n_x1 == d)))) all_const = 0;
     }
-    return 1;
+    return all_const ? 2 : 1;
+}
+
+static int ensure_pop(nemb_handle *h)
+{
+    if (h->have_pop) return NEMB_OK;
+    int rc = reserve(h, &h->b_pop, sizeof(int32_t) * (size_t)(h->n ? h->n : 1));
+    if (rc != NEMB_OK) return rc;
+    h->d_pop = h->b_pop.p;
+    nemk_row_popcount(h->stream, h->d_x, h->n, h->wpr, h->d_pop);
+    h->launches++;
+    CKK();
+    h->have_pop = 1;
+    return NEMB_OK;
 }
 
 /* ------------------------------------------------------------------ steps of one fit */
@@ -640,6 +662,19 @@ static int run_tables(nemb_handle *h, int k, int next_uniform)
  * separate cached-rebuild launch exists */
 static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming, int lean)
 {
+    if (uniform == 2 && lean && d_hamming == NULL && !getenv("NEM_B200_NO_POPCACHE")) {
+        /* every class has a constant centre: H from the cached row popcounts, X is not read */
+        int rc = ensure_pop(h);
+        if (rc != NEMB_OK) return rc;
+        STAGE_BEGIN(ST_DENSITY_CACHED);
+        nemk_ham_from_pop(h->stream, k, h->n, h->d, h->d_coef, h->d_pop, h->d_ham);
+        STAGE_END();
+        h->launches++;
+        CKK();
+        h->ham_valid = 1; h->lp_from_ham = 1;
+        h->ev_last_density = h->ev_last_cached = -1;
+        return NEMB_OK;
+    }
     STAGE_BEGIN(ST_DENSITY);
     h->lp_from_ham = 0;
     if (uniform) {
@@ -997,7 +1032,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
 {
     int k = o->k, rc, flipped;
     double beta = h->spatial ? (double)o->beta : 0.0;   /* nem_exe.c:570-574 */
-    int uniform_m = o->param_fixed ? uniform0 : (o->disp == NEMB_DISP_K_ || o->disp == NEMB_DISP___);
+    int uniform_m = o->param_fixed ? uniform0 : (o->disp == NEMB_DISP_K_ || o->disp == NEMB_DISP___);   /* 1: theta lives on the device */
     int want_crit_each = o->dolog || o->conv == NEMB_CONV_CRIT;
     int lean = o->algo == NEMB_ALGO_NCEM && !getenv("NEM_B200_KEEP_LOGPF");
     size_t kd = (size_t)k * h->d;

@@ -41,6 +41,9 @@ struct nemb_handle {
     uint32_t *d_x, *d_xt;
     int x_owned, have_xt;
     dbuf b_x, b_xt, b_row_ptr, b_col, b_wgt, b_rrow_ptr, b_rcol, b_sites, b_level_ptr, b_flags, b_heavy;
+    dbuf b_pop;            /* row popcounts of X (lazy, or taken behind the chunked upload) */
+    int32_t *d_pop;
+    int have_pop;
     dbuf b_sub, b_index;   /* resample driver: builder scratch; original family id of every row */
     int32_t *d_index;      /* non-NULL when this problem is a device-built subsample */
     cudaStream_t copy_stream;   /* loader: chunked upload of X, overlapped with the transposes */

@@ -531,6 +531,41 @@ k_density_tma(int K, int D, const uint4 *__restrict__ x, int n, int wpr4, int st
 }
 
 // =============================================================================================
+// Row popcounts P_i = popc(x_i): theta-independent, taken once per load (behind the upload).  When
+// EVERY class has a constant centre -- PPanGGOLiN's initial parameters: 1 / 1/2 / 0 -- the Hamming
+// counts are H = P, D - P or 0 and the density pass does not read X at all.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_row_popcount(const uint4 *__restrict__ x, int n, int wpr4, int32_t *__restrict__ pop) {
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int c = 0;
+    for (int q = lane; q < wpr4; q += 32) {
+        uint4 v = __ldg(x + (size_t)row * wpr4 + q);
+        c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    c = __reduce_add_sync(FULL, c);
+    if (lane == 0) pop[row] = c;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+k_ham_from_pop(int K, int n, int D, const nemk_coef *__restrict__ coef,
+               const int32_t *__restrict__ pop, int32_t *__restrict__ ham) {
+    if (coef->empty_class | coef->halt) return;
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    int P = pop[row];
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        if (k < K) {
+            int kind = coef->kind[k];   // 1: centre 0 everywhere, 2: centre 1 everywhere, 3: all 1/2
+            ham[(size_t)row * K + k] = kind == 1 ? P : kind == 2 ? D - P : 0;
+        }
+    }
+}
+
+// =============================================================================================
 // E-step density, general path (skd / s_d / arbitrary .m): per-genome weights.
 //   logf = -(base_k + sum_{d: x_id=1} delta_kd), zero density if a forbidden cell mismatches.
 // One warp per family, lanes over words, set bits walked with ffs; fp64, fixed order.
@@ -2123,6 +2158,19 @@ extern "C" void nemk_density_uniform(nemk_stream s, int k, int d, const uint32_t
     if (!done)
         DISPATCH_K(k, (launch_density_uniform<KT>(S(s), k, x, n, wpr, coef, mask_xor, mask_valid,
                                                   logpf, hamming, cached)));
+    note_launch();
+}
+
+extern "C" void nemk_row_popcount(nemk_stream s, const uint32_t *x, int n, int wpr, int32_t *pop) {
+    if (n <= 0) return;
+    k_row_popcount<<<cdiv((long long)n * 32, 256), 256, 0, S(s)>>>((const uint4 *)x, n, wpr / 4, pop);
+    note_launch();
+}
+
+extern "C" void nemk_ham_from_pop(nemk_stream s, int k, int n, int d, const nemk_coef *coef,
+                                  const int32_t *pop, int32_t *ham) {
+    if (n <= 0) return;
+    DISPATCH_K(k, (k_ham_from_pop<KT><<<cdiv(n, 256), 256, 0, S(s)>>>(k, n, d, coef, pop, ham)));
     note_launch();
 }
 
