@@ -579,6 +579,7 @@ def main_ours(args):
                        "sweep_dag_depth": depth,
                        "em_iterations_per_fit": f.iters, "converged": f.converged,
                        "fixup_rounds_per_fit": f.fixup_rounds,
+                       "site_evaluations_saved_per_fit": f.n_kept,
                        "multi_gpu": multi,
                        "l2": ("inputs larger than L2 (X = %d MB)" % (x_bytes >> 20)) if flush is None
                        else "L2 flushed (512 MB write) between timed steps",

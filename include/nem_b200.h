@@ -109,6 +109,7 @@ typedef struct {
     float   ms_density_cached, ms_mstep_delta;
     int32_t n_density_cached, n_mstep_delta;
     int64_t exchanges;    /* row shards: all-gathers this fit issued */
+    int64_t n_kept;       /* site evaluations the margin cache of the dense sweep saved (all sweeps) */
 } nemb_result;
 
 /* Per-iteration trace for the .log writer (nem_alg.c:1995-2052, 2620-2646). */

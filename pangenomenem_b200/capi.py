@@ -48,7 +48,7 @@ class Result(C.Structure):
                 ("n_criteria", C.c_int32), ("best_start", C.c_int32), ("n_success", C.c_int32),
                 ("ms_density_cached", C.c_float), ("ms_mstep_delta", C.c_float),
                 ("n_density_cached", C.c_int32), ("n_mstep_delta", C.c_int32),
-                ("exchanges", C.c_int64)]
+                ("exchanges", C.c_int64), ("n_kept", C.c_int64)]
 
 
 class BatchStats(C.Structure):
@@ -154,6 +154,7 @@ class Fit:
     stage_launches: dict = field(default_factory=dict)
     empty_class: int = 0
     exchanges: int = 0
+    n_kept: int = 0
 
 
 class Engine:
@@ -284,7 +285,7 @@ class Engine:
                         mstep_delta=r.ms_mstep_delta),
                    dict(density=r.n_density, sweep=r.n_sweep, mstep=r.n_mstep,
                         criteria=r.n_criteria, density_cached=r.n_density_cached,
-                        mstep_delta=r.n_mstep_delta), r.empty_class, r.exchanges)
+                        mstep_delta=r.n_mstep_delta), r.empty_class, r.exchanges, r.n_kept)
 
     def posteriors(self, k=None):
         k = k or self.k

@@ -31,7 +31,26 @@ typedef struct {
                                    returns at once.  Must follow empty_class (the `skip` pair). */
     int32_t mu_changed;         /* the class bit masks differ from the previous tables (or forced):
                                    the cached Hamming counts are stale, the density pass must run */
+    /* margin cache of the dense sweep (nemk_margins): dstep[k] bounds how far class k's score
+     * lp - (a*H + base) can have moved, for any H in [0, D], between the previous tables and
+     * these (+inf: unknown); drift accumulates 2*max_k dstep over the sweeps since the margins
+     * were stored */
+    double  dstep[NEMB_MAX_K];
+    double  drift;
 } nemk_coef;
+
+/* Margin cache of the ncem speculative sweep (exact shortcut).  m[i] = (best - second best score
+ * of site i at its last evaluation) + the drift at that time.  While the class bit masks do not
+ * move, theta only changes the per-class coefficients: no score can move by more than dstep, so a
+ * site whose margin exceeds the drift accumulated since and none of whose later-or-equal
+ * neighbours changed label in the previous sweep (stale flags) keeps its label: the dense round
+ * copies it without touching the CSR.  m == NULL: feature off. */
+typedef struct {
+    float   *m;            /* [n_loc] */
+    uint8_t *stale_cur;    /* [lab_len] set during the previous sweep, consumed (cleared) by this one */
+    uint8_t *stale_next;   /* [lab_len] set by this sweep's label changes */
+    int32_t  on;           /* host: this sweep may skip (same beta as the previous sweep) */
+} nemk_margins;
 
 /* Device scalars of one sweep / one iteration (host reads them back in one copy). */
 typedef struct {
@@ -44,7 +63,7 @@ typedef struct {
                             last label exchange -- the same number on every rank; 0 = settled */
     int32_t changed_glob; /* row-sharded sweep: labels of ALL families != previous iteration's,
                             counted by every rank from the exchanged labels (same on every rank) */
-    int32_t pad[1];
+    int32_t kept;        /* dense round: sites whose label was copied thanks to the margin cache */
 } nemk_counters;
 
 /* Device status block of one sweep / iteration, and the copy nemk_iter_end publishes into
@@ -157,19 +176,21 @@ void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc, nemk_lpsr
                             double beta, const uint8_t *lab_in, uint8_t *lab_out, int32_t *dirty,
                             int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
                             const int32_t *rcol, const int32_t *heavy, int n_heavy,
-                            nemk_counters *cnt, const int32_t *skip, int copy_ranks, int shard_len);
+                            nemk_counters *cnt, const int32_t *skip, int copy_ranks, int shard_len,
+                            nemk_margins mg);
 void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                            const int32_t *row_ptr, const int32_t *col, const float *wgt, double beta,
                            const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a,
                            int32_t *wl_b, int32_t *wl_cnt, int round, const int32_t *rrow_ptr,
                            const int32_t *rcol, nemk_counters *cnt, const int32_t *skip,
-                           const nemk_iter_end_args *fused /* nullable: publish the status too */);
+                           const nemk_iter_end_args *fused /* nullable: publish the status too */,
+                           nemk_margins mg);
 void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc lps,
                                  const int32_t *row_ptr, const int32_t *col, const float *wgt,
                                  double beta, const uint8_t *lab_old, uint8_t *lab_cur,
                                  int32_t *dirty, int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt,
                                  int round, const int32_t *rrow_ptr, const int32_t *rcol,
-                                 nemk_counters *cnt, const int32_t *skip);
+                                 nemk_counters *cnt, const int32_t *skip, nemk_margins mg);
 /* after a label exchange: every rank scans ALL families.  A label that differs from the one seen
  * at the previous exchange (seen_in; the first exchange of a sweep passes the sweep's input labels)
  * queues this rank's later readers and counts, for every rank alike, the cross-rank (reader,

@@ -482,6 +482,7 @@ static int ensure_k(nemb_handle *h, int k)
     size_t o_logpf = carve(&off, sizeof(double) * n * k);
     size_t o_lab0 = carve(&off, L), o_lab1 = carve(&off, L), o_lab2 = carve(&off, L);
     size_t o_lab3 = carve(&off, n + 1), o_ham = carve(&off, 4 * n * k + 4), o_sl = carve(&off, 4 * (kd + k));
+    size_t o_margin = carve(&off, 4 * n + 4), o_stale0 = carve(&off, L), o_stale1 = carve(&off, L);
     size_t o_dirty = carve(&off, 4 * L);
     size_t o_wl0 = carve(&off, 4 * (n + 1)), o_wl1 = carve(&off, 4 * (n + 1));
     size_t o_wlc = carve(&off, 4 * 8);
@@ -503,6 +504,8 @@ static int ensure_k(nemb_handle *h, int k)
     h->d_lab[0] = (uint8_t *)(base + o_lab0); h->d_lab[1] = (uint8_t *)(base + o_lab1);
     h->d_lab[2] = (uint8_t *)(base + o_lab2); h->d_lab[3] = (uint8_t *)(base + o_lab3);
     h->d_ham = (int32_t *)(base + o_ham); h->d_stat_loc = (int32_t *)(base + o_sl);
+    h->d_margin = (float *)(base + o_margin);
+    h->d_stale[0] = (uint8_t *)(base + o_stale0); h->d_stale[1] = (uint8_t *)(base + o_stale1);
     h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1;
     h->d_dirty = (int32_t *)(base + o_dirty);
     h->d_wl[0] = (int32_t *)(base + o_wl0); h->d_wl[1] = (int32_t *)(base + o_wl1);
@@ -793,10 +796,10 @@ static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, 
         nemk_sweep_ncem_fixup_round(h->stream, k, h->row0, h->n, lpsrc(h), rp, h->d_col, h->d_wgt,
                                     beta, in, out, h->d_dirty, h->d_wl[0], h->d_wl[1],
                                     h->d_wl_counts, r, h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt,
-                                    skip);
+                                    skip, h->mg);
     nemk_sweep_ncem_fixup(h->stream, k, h->row0, h->n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
                           out, h->d_dirty, h->d_wl[0], h->d_wl[1], h->d_wl_counts, grid_rounds,
-                          h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip, fused);
+                          h->d_rrow_ptr, h->d_rcol, &h->d_status->cnt, skip, fused, h->mg);
     h->launches += 1 + grid_rounds;
 }
 
@@ -810,9 +813,10 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
     const int32_t *skip = &h->d_coef->empty_class;
     const int32_t *rp = h->spatial ? h->d_row_ptr : NULL;
     int seq = o->update == NEMB_UPDATE_SEQ && h->spatial && beta != 0.0;
-    size_t L = h->lab_len, SL = h->shard_len;
+    size_t SL = h->shard_len;
     *flipped = 0;
     if (status_read) *status_read = 0;
+    memset(&h->mg, 0, sizeof h->mg);
     CK(cudaMemsetAsync(&h->d_status->cnt, 0, sizeof(nemk_counters), h->stream));
     STAGE_BEGIN(ST_SWEEP);
     if (o->algo == NEMB_ALGO_NCEM) {
@@ -821,18 +825,27 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
         if (!seq) {
             nemk_sweep_ncem_jacobi(h->stream, k, row0, n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
                                    out, NULL, NULL, NULL, NULL, NULL, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip,
-                                   0, 0);
+                                   0, 0, h->mg);
             h->launches++;
             /* halo exchange of the hard labels: every rank's slice, 1 byte per family */
             if (h->world > 1 && (rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
             *flipped = 1;
         } else if (impl == NEMB_SWEEP_SPEC) {
+            /* margin cache (one GPU, Hamming-count scores): sites whose margin exceeds what theta
+             * can have moved and whose later neighbours kept their label are copied, not evaluated */
+            if (h->world == 1 && h->lp_from_ham && !getenv("NEM_B200_NO_MARGINS")) {
+                h->mg.m = h->d_margin;
+                h->mg.stale_cur = h->d_stale[h->stale_par];
+                h->mg.stale_next = h->d_stale[h->stale_par ^ 1];
+                h->mg.on = h->sweep_same_beta;
+                h->stale_par ^= 1;
+            }
             /* row shards: the jacobi kernel also copies the other ranks' slices in -> out (remote
              * labels start the sweep at their previous value) */
             nemk_sweep_ncem_jacobi(h->stream, k, row0, n, lpsrc(h), rp, h->d_col, h->d_wgt, beta, in,
                                    out, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
                                    h->d_rcol, h->d_heavy, h->n_heavy, &h->d_status->cnt, skip,
-                                   h->world, (int)SL);
+                                   h->world, (int)SL, h->mg);
             h->launches++;
             if (h->world == 1 && decide) {
                 /* one GPU: the tail of the fix-up rounds ends the iteration -- it also decides
@@ -1016,6 +1029,10 @@ static int init_state(nemb_handle *h, const nemb_options *o)
     h->cur = 0;
     h->state_labels = o->algo == NEMB_ALGO_NCEM;
     h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1; h->prev_valid = 0;
+    h->stale_par = 0; h->sweep_same_beta = 0;
+    memset(&h->mg, 0, sizeof h->mg);
+    CK(cudaMemsetAsync(h->d_stale[0], 0, h->lab_len, h->stream));
+    CK(cudaMemsetAsync(h->d_stale[1], 0, h->lab_len, h->stream));
     if (h->state_labels) CK(cudaMemsetAsync(h->d_lab[0], 255, h->lab_len, h->stream));
     else {
         if ((rc = ensure_t(h, o->k, 1)) != NEMB_OK) return rc;
@@ -1080,6 +1097,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
             if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
             if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
             int status_read = 0;
+            h->sweep_same_beta = 1;   /* the previous sweep used this beta: cached margins may apply */
             if ((rc = run_sweep(h, o, beta, &flipped, (want_crit_each || cb) ? NULL : o, &status_read)) != NEMB_OK) return rc;
             if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
             if (cb) {
@@ -1105,6 +1123,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
         h->fixup_rounds += h->h_status->cnt.nfix;
         res->n_allnul = h->h_status->cnt.allnul;
         res->n_ties = h->h_status->cnt.ties;
+        res->n_kept += h->h_status->cnt.kept;
         if (o->conv == NEMB_CONV_CLAS) {
             float md = o->algo == NEMB_ALGO_NCEM ? (h->h_status->cnt.changed ? 1.0f : 0.0f)
                                                  : h->h_status->cnt.maxdiff;

@@ -71,6 +71,10 @@ struct nemb_handle {
                               labels the M-step statistics currently describe (local rows) */
     int32_t *d_ham;        /* cached Hamming counts H[n][K] of the popcount density path */
     int ham_valid, stats_valid, tables_forced;
+    float *d_margin;       /* margin cache of the dense sweep (nemk_margins), local rows */
+    uint8_t *d_stale[2];   /* stale flags, swapped every speculative sweep */
+    int stale_par, sweep_same_beta;
+    nemk_margins mg;       /* the margins of the sweep being enqueued (m == NULL: off) */
     int prev_valid;        /* d_lab[cur ^ 1] holds the input labels of the last sweep (it flipped) */
     int lp_from_ham;       /* the consumers rebuild logpf from d_ham in registers (no logpf array) */
     int64_t last_changed;  /* labels moved by the last sweep (all ranks), -1 = unknown */

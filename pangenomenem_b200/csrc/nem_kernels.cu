@@ -234,7 +234,11 @@ static __device__ __forceinline__ TablesPartial tables_words(
 static __device__ __forceinline__ void tables_commit(int k, int K, int D, const float *prop,
                                                      nemk_coef *coef, double *delta,
                                                      const ClassCoef &cc, double base_u,
-                                                     double base_g, bool ok, int n_valid, int n_x1) {
+                                                     double base_g, bool ok, int n_valid, int n_x1,
+                                                     bool have_prev) {
+    // previous coefficients of the class (margin cache: how far can its score have moved?)
+    const double lp_o = coef->lp[k], a_o = coef->a[k], base_o = coef->base[k];
+    const int forb_o = coef->forb[k];
     // popcount-path class kind: 3 = no genome counts (all centres 1/2), 1 = centre 0 everywhere
     // (H = popc(x)), 2 = centre 1 everywhere (H = D - popc(x)), 0 = general
     coef->kind[k] = n_valid == 0 ? 3 : (n_valid == D && n_x1 == 0) ? 1 : (n_valid == D && n_x1 == D) ? 2 : 0;
@@ -249,6 +253,17 @@ static __device__ __forceinline__ void tables_commit(int k, int K, int D, const 
     }
     delta[(size_t)K * D + k] = base_g;  // general-path base: sum_d cost0_kd
     if (!ok) atomicAnd(&coef->uniform_ok, 0);   // preset to non-zero by the launcher
+    // |score_new - score_old| <= |d(lp - base)| + |d a| * D for every H in [0, D]; a forbidding
+    // class scores lp or -inf.  Anything else (first tables, general path, flag flips, infinities)
+    // = unknown.
+    double step = CUDART_INF;
+    if (have_prev && ok && forb_o == coef->forb[k]) {
+        double d0 = (coef->lp[k] - coef->base[k]) - (lp_o - base_o), da = coef->a[k] - a_o;
+        if (coef->forb[k]) { d0 = coef->lp[k] - lp_o; da = 0.0; }
+        double b = fabs(d0) + fabs(da) * (double)D;
+        if (b == b && b < CUDART_INF) step = b;   // finite, not NaN
+    }
+    coef->dstep[k] = step;
 }
 
 // tables of the theta the caller supplied (start of a fit): one CTA per class
@@ -269,7 +284,7 @@ k_theta_tables(int K, int D, int wpr, const float *__restrict__ prop,
     double nv = block_sum<TT_THREADS>((double)p.n_valid, sh);
     double nx = block_sum<TT_THREADS>((double)p.n_x1, sh);
     if (threadIdx.x == 0)
-        tables_commit(k, K, D, prop, coef, delta, cc, base_u, base_g, notok == 0.0, (int)nv, (int)nx);
+        tables_commit(k, K, D, prop, coef, delta, cc, base_u, base_g, notok == 0.0, (int)nv, (int)nx, false);
 }
 
 // =============================================================================================
@@ -667,7 +682,8 @@ static __device__ __forceinline__ void ctx_labels(int K, int i, const int32_t *_
 // returns arg max (first max); flags: bit0 = all classes have zero density, bit1 = exact tie
 template <int KT>
 static __device__ __forceinline__ int site_argmax(int K, const double *__restrict__ lp,
-                                                  const double *ctx, double beta, int &flags) {
+                                                  const double *ctx, double beta, int &flags,
+                                                  double &margin) {
     double mx = neg_inf();
     int km = 0;
     double sc[KT];
@@ -677,11 +693,43 @@ static __device__ __forceinline__ int site_argmax(int K, const double *__restric
         if (sc[k] > mx) { mx = sc[k]; km = k; }
     }
     flags = 0;
+    margin = neg_inf();   // never skipped
     if (mx == neg_inf()) { flags = 1; return 0; }
+    double second = neg_inf();
 #pragma unroll
-    for (int k = 0; k < KT; k++)
+    for (int k = 0; k < KT; k++) {
+        if (k != km && k < K) second = fmax(second, sc[k]);
         if (k > km && k < K && sc[k] == mx) flags |= 2;
+    }
+    margin = mx - second;   // 0 on an exact tie, +inf when every other class has zero density
     return km;
+}
+template <int KT>
+static __device__ __forceinline__ int site_argmax(int K, const double *__restrict__ lp,
+                                                  const double *ctx, double beta, int &flags) {
+    double margin;
+    return site_argmax<KT>(K, lp, ctx, beta, flags, margin);
+}
+
+// ---- margin cache (nemk_margins).  All kernels of one sweep derive the same two numbers from the
+// coefficients: `test` (a stored margin must exceed it for the site to be skipped) and `store`
+// (added to the margins stored by this sweep; it becomes coef->drift when the sweep ends).
+struct SweepThr { double test, store; };
+static __device__ __forceinline__ SweepThr sweep_thr(int K, const nemk_coef *__restrict__ coef,
+                                                     const nemk_margins &mg) {
+    SweepThr t;
+    t.test = CUDART_INF; t.store = 0.0;
+    if (!mg.m || !mg.on || coef->mu_changed) return t;
+    double step = 0.0;
+    for (int k = 0; k < K; k++) step = fmax(step, coef->dstep[k]);
+    if (!(step < CUDART_INF)) return t;   // +inf or NaN: unknown move, evaluate everything
+    t.store = coef->drift + 2.0 * step;
+    t.test = t.store + 1e-6;              // slack for the rounding of the scores themselves
+    return t;
+}
+static __device__ __forceinline__ void store_margin(const nemk_margins &mg, int il, double margin,
+                                                    double store) {
+    if (mg.m) mg.m[il] = __double2float_rd(margin + store);   // rounded down: conservative
 }
 
 // Speculative sequential sweep bookkeeping: every site that READS i and is visited later
@@ -690,10 +738,13 @@ static __device__ __forceinline__ int site_argmax(int K, const double *__restric
 static __device__ __forceinline__ void mark_readers(int i, const int32_t *__restrict__ rrow_ptr,
                                                     const int32_t *__restrict__ rcol,
                                                     int32_t *dirty, int32_t *wl, int32_t *wl_count,
-                                                    int row0, int row1) {
+                                                    int row0, int row1, uint8_t *stale_next = nullptr) {
     int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
     for (int e = lo; e < hi; e++) {
         int j = rcol[e];
+        // readers visited before i (or i itself) keep this sweep's evaluation, which saw i's OLD
+        // label: their cached margin is void for the next sweep
+        if (stale_next && j <= i && j >= row0 && j < row1) stale_next[j] = 1;
         // only sites this rank owns ([row0,row1), the whole graph on one GPU) are queued here;
         // the owner of a remote reader queues it when it sees i's new label (k_mark_remote)
         if (j > i && j >= row0 && j < row1 && atomicExch(&dirty[j], 1) == 0)
@@ -790,10 +841,12 @@ static __device__ __forceinline__ void ctx_labels_coop(int lo, int hi, int seg_l
 static __device__ __forceinline__ void mark_readers_warp(int i, const int32_t *__restrict__ rrow_ptr,
                                                          const int32_t *__restrict__ rcol,
                                                          int32_t *dirty, int32_t *wl,
-                                                         int32_t *wl_count, int row0, int row1) {
+                                                         int32_t *wl_count, int row0, int row1,
+                                                         uint8_t *stale_next = nullptr) {
     int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
     for (int e = lo + (threadIdx.x & 31); e < hi; e += 32) {
         int j = rcol[e];
+        if (stale_next && j <= i && j >= row0 && j < row1) stale_next[j] = 1;
         if (j > i && j >= row0 && j < row1 && atomicExch(&dirty[j], 1) == 0)
             wl[atomicAdd(wl_count, 1)] = j;
     }
@@ -810,10 +863,10 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
                     const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
                     const int32_t *__restrict__ heavy, int n_heavy, int heavy_blocks,
                     nemk_counters *cnt, const int32_t *__restrict__ skip, int copy_ranks,
-                    int shard_len) {
+                    int shard_len, const nemk_margins mg) {
     if (skip && (skip[0] | skip[1])) return;
     const int lane = threadIdx.x & 31;
-    int changed = 0, flags = 0;
+    int changed = 0, flags = 0, kept_site = 0;
     if ((int)blockIdx.x >= heavy_blocks && copy_ranks > 1) {
         // row shards: the other ranks' labels start the sweep at their previous value
         int q = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x;
@@ -823,19 +876,30 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
                 if (r != mine) lab_out[(size_t)r * shard_len + q] = lab_in[(size_t)r * shard_len + q];
         }
     }
+    const SweepThr thr = sweep_thr(K, lps.coef, mg);
+    const bool may_skip = mg.m && thr.test < CUDART_INF;
     if ((int)blockIdx.x < heavy_blocks) {
         // hubs first (longest work): one warp per site
         int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if (wid >= n_heavy) return;
         int i = heavy[wid], il = i - row0;
+        if (may_skip && !mg.stale_cur[i] && (double)mg.m[il] > thr.test && lab_in[i] != 255) {
+            if (lane == 0) lab_out[i] = lab_in[i];   // margin > possible move, context unchanged
+            return;
+        }
         double ctx[KT];
         ctx_labels_warp<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
-        double lpv[KT];
+        double lpv[KT], margin;
         load_lp<KT>(lps, K, (size_t)il, lpv);
-        int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
+        int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
         int ch = (km != (int)lab_in[i]);
-        if (lane == 0) lab_out[i] = (uint8_t)km;
-        if (ch && dirty) mark_readers_warp(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc);
+        if (lane == 0) {
+            lab_out[i] = (uint8_t)km;
+            store_margin(mg, il, margin, thr.store);
+            if (mg.m && mg.stale_cur[i]) mg.stale_cur[i] = 0;
+        }
+        if (ch && dirty)
+            mark_readers_warp(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc, mg.stale_next);
         if (lane == 0) {
             if (ch) atomicAdd(&cnt->changed, 1);
             if (flags & 1) atomicAdd(&cnt->allnul, 1);
@@ -845,41 +909,94 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
     }
     __shared__ float s_w[8][COOP_CHUNK];
     __shared__ uint8_t s_l[8][COOP_CHUNK];
+    __shared__ int s_act[256];
+    __shared__ int s_nact;
     int il = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x;
     int i = row0 + il;
-    if (il - lane >= n_loc) return;   // whole warp out of range
-    {
-        const int32_t *rp = beta != 0.0 ? row_ptr : nullptr;
-        const bool valid = il < n_loc;
+    const int32_t *rp = beta != 0.0 ? row_ptr : nullptr;
+    const bool valid = il < n_loc;
+    // margin cache: the site keeps its label when its stored margin exceeds everything theta
+    // can have moved since and no later-or-equal neighbour changed in the previous sweep
+    const bool keep = valid && may_skip && !mg.stale_cur[i] && (double)mg.m[il] > thr.test &&
+                      lab_in[i] != 255;
+    const bool act = valid && !keep;
+    kept_site = keep;
+    if (keep) lab_out[i] = lab_in[i];
+    // How many sites of this CTA are left?  Few (steady state: a few per cent): compact them so
+    // that one or two warps walk the dependent loads and the others retire at once.  Many: the
+    // warp-cooperative segment path below.
+    int sparse = 0;
+    if (may_skip) {
+        if (threadIdx.x == 0) s_nact = 0;
+        __syncthreads();
+        unsigned ba = __ballot_sync(FULL, act);
+        int base = 0;
+        if (lane == 0 && ba) base = atomicAdd(&s_nact, __popc(ba));
+        base = __shfl_sync(FULL, base, 0);
+        if (act) s_act[base + __popc(ba & ((1u << lane) - 1u))] = il;
+        __syncthreads();
+        sparse = s_nact <= 64;
+    }
+    if (sparse) {
+        const int nact = s_nact;
+        for (int q = threadIdx.x; q < nact; q += blockDim.x) {
+            const int sl = s_act[q], si = row0 + sl;
+            const bool hv = heavy_blocks && rp && (rp[si + 1] - rp[si] > HEAVY_DEG);
+            if (hv) continue;   // evaluated by the hub blocks
+            double ctx[KT], lpv[KT], margin;
+            ctx_labels<KT>(K, si, rp, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
+            load_lp<KT>(lps, K, (size_t)sl, lpv);
+            int fl;
+            int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
+            lab_out[si] = (uint8_t)km;
+            store_margin(mg, sl, margin, thr.store);
+            if (mg.stale_cur[si]) mg.stale_cur[si] = 0;
+            int ch = (km != (int)lab_in[si]);
+            if (ch && dirty)
+                mark_readers(si, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc, mg.stale_next);
+            changed += ch;          // a thread may take several sites here: counted directly
+            if (fl & 1) atomicAdd(&cnt->allnul, 1);
+            if (fl & 2) atomicAdd(&cnt->ties, 1);
+        }
+        if (changed) atomicAdd(&cnt->changed, changed);
+        unsigned bk2 = __ballot_sync(FULL, kept_site);
+        if (lane == 0 && bk2) atomicAdd(&cnt->kept, __popc(bk2));
+        return;
+    }
+    if (il - lane < n_loc) {   // warps entirely out of range have nothing to do
         int lo = 0, hi = 0;
-        if (rp && valid) { lo = rp[i]; hi = rp[i + 1]; }
+        if (rp && act) { lo = rp[i]; hi = rp[i + 1]; }
         const bool is_heavy = heavy_blocks && (hi - lo > HEAVY_DEG);
         double ctx[KT];
-        if (rp) {
-            int seg_lo = __shfl_sync(FULL, lo, 0), seg_hi = __reduce_max_sync(FULL, hi);
-            if (is_heavy) lo = hi = 0;   // evaluated by the hub blocks
-            ctx_labels_coop<KT>(lo, hi, seg_lo, seg_hi, col, wgt, lab_in, s_w[threadIdx.x >> 5],
-                                s_l[threadIdx.x >> 5], ctx);
-        } else {
 #pragma unroll
-            for (int k = 0; k < KT; k++) ctx[k] = 0.0;
+        for (int k = 0; k < KT; k++) ctx[k] = 0.0;
+        if (rp) {
+            int seg_lo = __reduce_min_sync(FULL, act ? lo : 0x7fffffff);
+            int seg_hi = __reduce_max_sync(FULL, act ? hi : 0);
+            if (is_heavy) lo = hi = 0;   // evaluated by the hub blocks
+            if (seg_lo < seg_hi)
+                ctx_labels_coop<KT>(lo, hi, seg_lo, seg_hi, col, wgt, lab_in, s_w[threadIdx.x >> 5],
+                                    s_l[threadIdx.x >> 5], ctx);
         }
-        if (valid && !is_heavy) {
-            double lpv[KT];
+        if (act && !is_heavy) {
+            double lpv[KT], margin;
             load_lp<KT>(lps, K, (size_t)il, lpv);
-            int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
+            int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
             lab_out[i] = (uint8_t)km;
+            store_margin(mg, il, margin, thr.store);
+            if (mg.m && mg.stale_cur[i]) mg.stale_cur[i] = 0;
             changed = (km != (int)lab_in[i]);
             if (changed && dirty)
-                mark_readers(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc);
+                mark_readers(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc, mg.stale_next);
         }
     }
     unsigned bc = __ballot_sync(FULL, changed), bn = __ballot_sync(FULL, flags & 1),
-             bt = __ballot_sync(FULL, flags & 2);
+             bt = __ballot_sync(FULL, flags & 2), bk = __ballot_sync(FULL, kept_site);
     if (lane == 0) {
         if (bc) atomicAdd(&cnt->changed, __popc(bc));
         if (bn) atomicAdd(&cnt->allnul, __popc(bn));
         if (bt) atomicAdd(&cnt->ties, __popc(bt));
+        if (bk) atomicAdd(&cnt->kept, __popc(bk));
     }
 }
 
@@ -904,21 +1021,23 @@ static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row
                                                  uint8_t *lab_cur, int32_t *dirty, int32_t *next_list,
                                                  int32_t *next_cnt,
                                                  const int32_t *__restrict__ rrow_ptr,
-                                                 const int32_t *__restrict__ rcol) {
+                                                 const int32_t *__restrict__ rcol,
+                                                 const nemk_margins &mg, double thr_store) {
     atomicExch(&dirty[i], 0);
     __threadfence();
     double ctx[KT];
     ctx_labels<KT>(K, i, row_ptr, col, wgt,
                    [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
     int flags;
-    double lpv[KT];
+    double lpv[KT], margin;
     load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
-    int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
+    int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
+    store_margin(mg, i - row0, margin, thr_store);   // the LAST evaluation of a site is its final one
     int was = __ldcg(lab_cur + i);
     if (km == was) return 0;
     lab_cur[i] = (uint8_t)km;
     __threadfence();
-    mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1);
+    mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1, mg.stale_next);
     int old = lab_old[i];
     return (km != old) - (was != old);
 }
@@ -934,7 +1053,8 @@ static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, in
                                                       uint8_t *lab_cur, int32_t *dirty,
                                                       int32_t *next_list, int32_t *next_cnt,
                                                       const int32_t *__restrict__ rrow_ptr,
-                                                      const int32_t *__restrict__ rcol) {
+                                                      const int32_t *__restrict__ rcol,
+                                                      const nemk_margins &mg, double thr_store) {
     const int lane = threadIdx.x & 31;
     if (lane == 0) { atomicExch(&dirty[i], 0); __threadfence(); }
     __syncwarp();
@@ -942,14 +1062,15 @@ static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, in
     ctx_labels_warp<KT>(K, i, row_ptr, col, wgt,
                         [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
     int flags;
-    double lpv[KT];
+    double lpv[KT], margin;
     load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
-    int km = site_argmax<KT>(K, lpv, ctx, beta, flags);
+    int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
+    if (lane == 0) store_margin(mg, i - row0, margin, thr_store);
     int was = __shfl_sync(FULL, (int)__ldcg(lab_cur + i), 0);
     if (km == was) return 0;
     if (lane == 0) { lab_cur[i] = (uint8_t)km; __threadfence(); }
     __syncwarp();
-    mark_readers_warp(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1);
+    mark_readers_warp(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1, mg.stale_next);
     int old = lab_old[i];
     return (km != old) - (was != old);
 }
@@ -967,21 +1088,22 @@ static __device__ __forceinline__ int fixup_items(int K, int idx, int count,
                                                   uint8_t *lab_cur, int32_t *dirty,
                                                   int32_t *next_list, int32_t *next_cnt,
                                                   const int32_t *__restrict__ rrow_ptr,
-                                                  const int32_t *__restrict__ rcol) {
+                                                  const int32_t *__restrict__ rcol,
+                                                  const nemk_margins &mg, double thr_store) {
     const int lane = threadIdx.x & 31;
     int i = idx < count ? cur_list[idx] : -1;
     bool hub = i >= 0 && (row_ptr[i + 1] - row_ptr[i] > HEAVY_DEG);
     int d = 0;
     if (i >= 0 && !hub)
         d = fixup_site<KT>(K, i, row0, row1, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
-                           next_list, next_cnt, rrow_ptr, rcol);
+                           next_list, next_cnt, rrow_ptr, rcol, mg, thr_store);
     unsigned hm = __ballot_sync(FULL, hub);
     while (hm) {
         int src = __ffs(hm) - 1;
         hm &= hm - 1;
         int site = __shfl_sync(FULL, i, src);
         int r = fixup_site_warp<KT>(K, site, row0, row1, lps, row_ptr, col, wgt, beta, lab_old,
-                                    lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol);
+                                    lab_cur, dirty, next_list, next_cnt, rrow_ptr, rcol, mg, thr_store);
         if (lane == src) d = r;
     }
     return d;
@@ -998,8 +1120,9 @@ k_sweep_ncem_fixup_round(int K, int row0, int row1, const nemk_lpsrc lps,
                          const uint8_t *__restrict__ lab_old, uint8_t *lab_cur, int32_t *dirty,
                          int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt, int round,
                          const int32_t *__restrict__ rrow_ptr, const int32_t *__restrict__ rcol,
-                         nemk_counters *cnt, const int32_t *__restrict__ skip) {
+                         nemk_counters *cnt, const int32_t *__restrict__ skip, const nemk_margins mg) {
     if (skip && (skip[0] | skip[1])) return;
+    const double thr_store = sweep_thr(K, lps.coef, mg).store;
     const int32_t *cur_list = (round & 1) ? wl_b : wl_a;
     int32_t *next_list = (round & 1) ? wl_a : wl_b;
     int count = wl_cnt[round & 3];
@@ -1010,7 +1133,7 @@ k_sweep_ncem_fixup_round(int K, int row0, int row1, const nemk_lpsrc lps,
          base += gridDim.x * blockDim.x)
         dchanged += fixup_items<KT>(K, base + (threadIdx.x & 31), count, cur_list, row0, row1, lps,
                                     row_ptr, col, wgt, beta, lab_old, lab_cur, dirty, next_list,
-                                    next_cnt, rrow_ptr, rcol);
+                                    next_cnt, rrow_ptr, rcol, mg, thr_store);
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
     if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(&cnt->nfix, 1);
 }
@@ -1032,7 +1155,8 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
                    uint8_t *lab_cur, int32_t *dirty, int32_t *wl_a, int32_t *wl_b,
                    int32_t *wl_cnt, int round, const int32_t *__restrict__ rrow_ptr,
                    const int32_t *__restrict__ rcol, nemk_counters *cnt,
-                   const int32_t *__restrict__ skip, const nemk_iter_end_args fused) {
+                   const int32_t *__restrict__ skip, const nemk_iter_end_args fused,
+                   const nemk_margins mg) {
     namespace cgx = cooperative_groups;
     cgx::cluster_group cluster = cgx::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -1043,6 +1167,7 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
         return;
     }
     int rounds = 0, dchanged = 0;
+    const double thr_store = sweep_thr(K, lps.coef, mg).store;
     for (;; round++) {
         int32_t *cur_list = (round & 1) ? wl_b : wl_a, *next_list = (round & 1) ? wl_a : wl_b;
         int32_t *next_cnt = &wl_cnt[(round + 1) & 3];
@@ -1054,12 +1179,14 @@ k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
         for (int base = crank * 1024 + (threadIdx.x & ~31); base < count; base += FX_CLUSTER * 1024)
             dchanged += fixup_items<KT>(K, base + (threadIdx.x & 31), count, cur_list, row0, row1,
                                         lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
-                                        next_list, next_cnt, rrow_ptr, rcol);
+                                        next_list, next_cnt, rrow_ptr, rcol, mg, thr_store);
         __threadfence();
         cluster.sync();
     }
     cluster.sync();   // every CTA has read the last (zero) count
     if (crank == 0 && threadIdx.x < 4) wl_cnt[threadIdx.x] = 0;
+    // the sweep is over: its margins carry thr_store, the drift the next sweep starts from
+    if (mg.m && crank == 0 && threadIdx.x == 0) const_cast<nemk_coef *>(lps.coef)->drift = thr_store;
     if (dchanged) atomicAdd(&cnt->changed, dchanged);
     if (crank == 0 && threadIdx.x == 0 && rounds) atomicAdd(&cnt->nfix, rounds);
     if (fused.host) {   // end of the sweep = end of the iteration: decide + publish here (k_iter_end)
@@ -1662,7 +1789,7 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
     double v[5] = {p.base_u, p.base_g, (double)p.notok, (double)p.n_valid, (double)p.n_x1};
     cluster_sum<5, TH>(cluster, v, sh, slot);
     if (part == 0 && tid == 0)
-        tables_commit(k, K, D, prop, coef, delta, cc, v[0], v[1], v[2] == 0.0, (int)v[3], (int)v[4]);
+        tables_commit(k, K, D, prop, coef, delta, cc, v[0], v[1], v[2] == 0.0, (int)v[3], (int)v[4], true);
 }
 
 // =============================================================================================
@@ -1914,16 +2041,16 @@ static __device__ void iter_end_body(int world, const nemk_counters *cnt_all,
                                      unsigned long long seq) {
     nemk_counters tot;
     tot.changed = 0; tot.nfix = 0; tot.allnul = 0; tot.ties = 0; tot.maxdiff = 0.f; tot.pending = 0;
-    tot.changed_glob = 0; tot.pad[0] = 0;
+    tot.changed_glob = 0; tot.kept = 0;
     const volatile nemk_counters *vc = cnt_all;   // written by atomics of this very launch when fused
     if (world == 0) {   // row-sharded speculative sweep: changed / pending are already global
         tot.changed = vc[0].changed_glob; tot.nfix = vc[0].nfix; tot.allnul = vc[0].allnul;
         tot.ties = vc[0].ties; tot.maxdiff = vc[0].maxdiff; tot.pending = vc[0].pending;
-        tot.changed_glob = vc[0].changed_glob;
+        tot.changed_glob = vc[0].changed_glob; tot.kept = vc[0].kept;
     }
     for (int r = 0; r < world; r++) {
         tot.changed += vc[r].changed; tot.allnul += vc[r].allnul; tot.ties += vc[r].ties;
-        tot.pending += vc[r].pending;
+        tot.pending += vc[r].pending; tot.kept += vc[r].kept;
         tot.nfix = max(tot.nfix, vc[r].nfix);
         tot.maxdiff = fmaxf(tot.maxdiff, vc[r].maxdiff);
     }
@@ -2204,14 +2331,14 @@ extern "C" void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc
                                        int32_t *wl, int32_t *wl_count, const int32_t *rrow_ptr,
                                        const int32_t *rcol, const int32_t *heavy, int n_heavy,
                                        nemk_counters *cnt, const int32_t *skip, int copy_ranks,
-                                       int shard_len) {
+                                       int shard_len, nemk_margins mg) {
     if (n_loc <= 0 && copy_ranks <= 1) return;
     int hb = (row_ptr && beta != 0.0 && heavy && n_loc > 0) ? cdiv((long long)n_heavy * 32, 256) : 0;
     int cover = copy_ranks > 1 && shard_len > n_loc ? shard_len : n_loc;   // the copy spans a full slice
     DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<hb + cdiv(cover, 256), 256, 0, S(s)>>>(
                       k, row0, n_loc, lps, row_ptr, col, wgt, beta, lab_in, lab_out, dirty, wl,
                       wl_count, rrow_ptr, rcol, heavy, n_heavy, hb, cnt, skip, copy_ranks,
-                      shard_len)));
+                      shard_len, mg)));
     note_launch();
 }
 
@@ -2232,7 +2359,7 @@ extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc,
                                       int32_t *dirty, int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt,
                                       int round, const int32_t *rrow_ptr, const int32_t *rcol,
                                       nemk_counters *cnt, const int32_t *skip,
-                                      const nemk_iter_end_args *fused) {
+                                      const nemk_iter_end_args *fused, nemk_margins mg) {
     nemk_iter_end_args fa;
     memset(&fa, 0, sizeof fa);
     if (fused) fa = *fused;
@@ -2245,7 +2372,7 @@ extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc,
     }
     DISPATCH_K(k, (k_sweep_ncem_fixup<KT><<<FX_CLUSTER, 1024, 0, S(s)>>>(
                       k, row0, row0 + n_loc, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
-                      wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip, fa)));
+                      wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip, fa, mg)));
     note_launch();
 }
 
@@ -2255,12 +2382,12 @@ extern "C" void nemk_sweep_ncem_fixup_round(nemk_stream s, int k, int row0, int 
                                             const uint8_t *lab_old, uint8_t *lab_cur, int32_t *dirty,
                                             int32_t *wl_a, int32_t *wl_b, int32_t *wl_cnt, int round,
                                             const int32_t *rrow_ptr, const int32_t *rcol,
-                                            nemk_counters *cnt, const int32_t *skip) {
+                                            nemk_counters *cnt, const int32_t *skip, nemk_margins mg) {
     if (n_loc <= 0) return;
     int grid = num_sms() * 8;   // CTAs beyond the list return at once; long lists need the threads
     DISPATCH_K(k, (k_sweep_ncem_fixup_round<KT><<<grid, 256, 0, S(s)>>>(
                       k, row0, row0 + n_loc, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
-                      wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip)));
+                      wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip, mg)));
     note_launch();
 }
 

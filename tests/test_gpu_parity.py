@@ -308,19 +308,22 @@ def test_fit_it_max_zero_and_k_other_than_3(engine, oracle):
 @pytest.mark.parametrize("it_max", [1, 2, 3, 5, 8, 9, 10, 30])
 def test_speculative_iterations_change_nothing(engine, oracle, it_max, monkeypatch):
     """The EM loop enqueues iteration i+1 before the status of iteration i is known (device halt
-    flag, nem_fit.c em_core); whatever it_max cuts, the fit must equal the synchronous loop and
-    the oracle: same iteration count, labels, theta, criteria."""
+    flag, nem_fit.c em_core), and the dense sweep copies the label of sites whose cached margin
+    exceeds what theta can have moved (nemk_margins).  Both are exact shortcuts: whatever it_max
+    cuts, with either switched off, the fit must equal the oracle: same iteration count, labels,
+    theta, criteria."""
     pg = make_case(20000, 50, seed=42)
     theta = oracle.default_theta(3, pg.d)
     kw = dict(k=3, algo="ncem", update="seq", disp="sk_", prop="pk", beta=0.5, it_max=it_max)
     ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(*theta)
     engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
     out = []
-    for no_spec in ("", "1"):
-        if no_spec:
-            monkeypatch.setenv("NEM_B200_NO_SPEC", "1")
-        else:
-            monkeypatch.delenv("NEM_B200_NO_SPEC", raising=False)
+    for no_spec, no_margins in (("", ""), ("1", ""), ("", "1"), ("1", "1")):
+        for name, val in (("NEM_B200_NO_SPEC", no_spec), ("NEM_B200_NO_MARGINS", no_margins)):
+            if val:
+                monkeypatch.setenv(name, val)
+            else:
+                monkeypatch.delenv(name, raising=False)
         for _ in range(2):                      # twice: a halted fit must leave the handle clean
             got = engine.fit(*theta, **kw)
             out.append((got, engine.labels()))
@@ -353,3 +356,26 @@ def test_empty_class_then_the_handle_recovers(engine, oracle):
     again = engine.fit(*theta, **kw)
     assert again.status == 0 and again.iters == ok.iters
     assert np.array_equal(engine.labels(), ok.label)
+
+
+@pytest.mark.parametrize("graph,beta,disp", [("pangenome", 0.5, "sk_"), ("random", 1.0, "sk_"),
+                                             ("pangenome", 2.5, "s__"), ("random", 0.3, "sk_")])
+def test_margin_cache_is_exact_on_long_fits(engine, oracle, graph, beta, disp, monkeypatch):
+    """Many iterations with slowly moving theta and labels that keep flipping near the class
+    borders (strong beta, noisy shell): the margin cache must never keep a label the full
+    evaluation would change."""
+    pg = make_case(30000, 64, seed=17, graph=graph)
+    theta = oracle.default_theta(3, pg.d, low_disp=0.3)
+    kw = dict(k=3, algo="ncem", update="seq", disp=disp, prop="pk", beta=beta, it_max=60)
+    ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(*theta)
+    engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
+    for off in ("", "1"):
+        if off:
+            monkeypatch.setenv("NEM_B200_NO_MARGINS", "1")
+        else:
+            monkeypatch.delenv("NEM_B200_NO_MARGINS", raising=False)
+        got = engine.fit(*theta, **kw)
+        assert got.iters == ref.iters and got.converged == ref.converged, (got.iters, ref.iters)
+        assert np.array_equal(engine.labels(), ref.label), int((engine.labels() != ref.label).sum())
+        assert np.array_equal(got.center, ref.center) and np.array_equal(got.disp, ref.disp)
+        assert got.n_ties == ref.n_ties and got.n_allnul == ref.n_allnul
