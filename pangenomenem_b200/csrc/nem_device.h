@@ -92,6 +92,9 @@ typedef struct {
     const double *logpf;
     const int32_t *ham;      /* non-NULL selects the Hamming source */
     const nemk_coef *coef;
+    int32_t wsum_any_order;  /* every edge weight is a small integer (checked at load): the fp64
+                                context sums are exact in ANY order, so hubs may add them in
+                                parallel; 0 = keep the file order of SumNeighsOfClass */
 } nemk_lpsrc;
 
 /* ---- loader */
@@ -129,9 +132,10 @@ void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d,
                           const double *delta, double *logpf);
 
 /* ---- loader: graph validation.  flags2[0] bit0 row_ptr broken, bit1 neighbour out of range,
- * bit2 some edge i->j has no j->i (reader lists differ from neighbour lists); flags2[1] = max degree */
+ * bit2 some edge i->j has no j->i (reader lists differ from neighbour lists), bit3 some weight is
+ * not an integer of magnitude <= 2^20 (context sums are then order dependent); flags2[1] = max degree */
 void nemk_graph_check(nemk_stream s, int n, int nnz, const int32_t *row_ptr, const int32_t *col,
-                      int32_t *flags2);
+                      const float *wgt, int32_t *flags2);
 
 /* index-sorted list of this rank's hubs (degree > 16), evaluated one warp per site by the sweeps
  * and the criteria; block_counts needs ceil(n_loc/1024) ints, list up to n_loc ints */

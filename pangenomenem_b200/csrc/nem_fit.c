@@ -178,6 +178,7 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
     int rc;
     h->spatial = row_ptr != NULL;
     h->nnz = 0; h->symmetric = 1; h->max_neigh = 0; h->n_heavy = 0; h->d_heavy = NULL;
+    h->wgt_integral = 0;
     h->d_row_ptr = h->d_col = h->d_rrow_ptr = h->d_rcol = NULL; h->d_wgt = NULL;
     if (!h->spatial) return NEMB_OK;
     if (row_ptr[0] != 0) return fail(h, NEMB_E_ARG, "row_ptr[0] must be 0");
@@ -190,7 +191,7 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
     if ((rc = upload(h, &h->b_wgt, wgt, sizeof(float) * (size_t)nnz)) != NEMB_OK) return rc;
     if ((rc = reserve(h, &h->b_flags, 64)) != NEMB_OK) return rc;
     h->d_row_ptr = h->b_row_ptr.p; h->d_col = h->b_col.p; h->d_wgt = h->b_wgt.p;
-    nemk_graph_check(h->stream, n, nnz, h->d_row_ptr, h->d_col, (int32_t *)h->b_flags.p);
+    nemk_graph_check(h->stream, n, nnz, h->d_row_ptr, h->d_col, h->d_wgt, (int32_t *)h->b_flags.p);
     CKK();
     /* hubs of this rank's rows (only meaningful if row_ptr is sane; re-checked below) */
     size_t hl_blocks = ((size_t)h->n + 1023) / 1024 + 1;
@@ -207,6 +208,7 @@ static int load_graph(nemb_handle *h, int n, const int32_t *row_ptr, const int32
     h->max_neigh = flags[1];
     h->n_heavy = flags[2];
     h->symmetric = !(flags[0] & 4);
+    h->wgt_integral = !(flags[0] & 8) && !getenv("NEM_B200_ORDERED_SUMS");
     if (h->symmetric) { h->d_rrow_ptr = h->d_row_ptr; h->d_rcol = h->d_col; return NEMB_OK; }
 
     /* directed graph: reader lists = transpose of the CSR */
@@ -643,7 +645,7 @@ static int ensure_pop(nemb_handle *h)
 /* ------------------------------------------------------------------ steps of one fit */
 static nemk_lpsrc lpsrc(const nemb_handle *h)
 {
-    nemk_lpsrc s = {h->d_logpf, h->lp_from_ham ? h->d_ham : NULL, h->d_coef};
+    nemk_lpsrc s = {h->d_logpf, h->lp_from_ham ? h->d_ham : NULL, h->d_coef, h->wgt_integral};
     return s;
 }
 

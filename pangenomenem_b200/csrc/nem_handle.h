@@ -38,6 +38,7 @@ struct nemb_handle {
      * id of local row 0, shard_len = rows per rank slot (lab_len = world * shard_len >= n_glob) */
     int n, n_glob, row0, shard_len, lab_len;
     int d, wpr, nwt, nnz, spatial, symmetric, max_neigh, loaded;
+    int wgt_integral;      /* every edge weight is an integer of magnitude <= 2^20 (exact sums) */
     uint32_t *d_x, *d_xt;
     int x_owned, have_xt;
     dbuf b_x, b_xt, b_row_ptr, b_col, b_wgt, b_rrow_ptr, b_rcol, b_sites, b_level_ptr, b_flags, b_heavy;

@@ -765,12 +765,41 @@ template <int KT, typename Pick>
 static __device__ __forceinline__ void ctx_labels_warp(int K, int i, const int32_t *__restrict__ row_ptr,
                                                        const int32_t *__restrict__ col,
                                                        const float *__restrict__ wgt, Pick pick,
-                                                       double *ctx) {
+                                                       double *ctx, bool any_order = false) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < KT; k++) ctx[k] = 0.0;
     if (!row_ptr) return;
     int lo = row_ptr[i], hi = row_ptr[i + 1];
+    if (any_order) {
+        // integer weights: every partial sum is exact, so the lanes add their strided share (four
+        // independent loads in flight per lane) and a butterfly adds the lanes -- same bits as the
+        // file-order sum, without its serial chain of dependent loads
+        for (int e0 = lo + lane; e0 < hi; e0 += 128) {
+            int j[4];
+            float w[4];
+            unsigned l[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int e = e0 + 32 * q;
+                bool in = e < hi;
+                j[q] = in ? col[e] : -1;
+                w[q] = in ? wgt[e] : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) l[q] = j[q] >= 0 ? pick(j[q]) : 255u;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int k = 0; k < KT; k++)
+                    if (l[q] == (unsigned)k) ctx[k] += (double)w[q];
+        }
+#pragma unroll
+        for (int k = 0; k < KT; k++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ctx[k] += __shfl_xor_sync(FULL, ctx[k], o);
+        return;
+    }
     for (int e0 = lo; e0 < hi; e0 += 32) {
         int e = e0 + lane;
         bool in = e < hi;
@@ -888,7 +917,8 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
             return;
         }
         double ctx[KT];
-        ctx_labels_warp<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
+        ctx_labels_warp<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx,
+                            lps.wsum_any_order != 0);
         double lpv[KT], margin;
         load_lp<KT>(lps, K, (size_t)il, lpv);
         int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
@@ -1060,7 +1090,8 @@ static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, in
     __syncwarp();
     double ctx[KT];
     ctx_labels_warp<KT>(K, i, row_ptr, col, wgt,
-                        [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
+                        [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx,
+                        lps.wsum_any_order != 0);
     int flags;
     double lpv[KT], margin;
     load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
@@ -1842,7 +1873,8 @@ k_criteria_partial(int K, int row0, int n_loc, const nemk_lpsrc lps,
             int i = heavy[wi];
             double ctx[KT];
             float ti[KT];
-            ctx_labels_warp<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab[j]; }, ctx);
+            ctx_labels_warp<KT>(K, i, row_ptr, col, wgt, [&](int j) { return (unsigned)lab[j]; }, ctx,
+                                lps.wsum_any_order != 0);
             unsigned l = lab[i];
 #pragma unroll
             for (int k = 0; k < KT; k++) ti[k] = (l == (unsigned)k) ? 1.f : 0.f;
@@ -2008,7 +2040,7 @@ k_heavy_fill(int row0, int n_loc, const int32_t *__restrict__ row_ptr,
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 k_graph_check(int n, int nnz, const int32_t *__restrict__ row_ptr,
-              const int32_t *__restrict__ col, int32_t *flags) {
+              const int32_t *__restrict__ col, const float *__restrict__ wgt, int32_t *flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int lo = row_ptr[i], hi = row_ptr[i + 1];
@@ -2016,6 +2048,8 @@ k_graph_check(int n, int nnz, const int32_t *__restrict__ row_ptr,
     if (hi < lo || lo < 0 || hi > nnz) { atomicOr(&flags[0], 1); return; }
     for (int e = lo; e < hi; e++) {
         int j = col[e];
+        float w = wgt[e];
+        if (!(w == rintf(w) && fabsf(w) <= 1048576.0f)) bad |= 8;   // sums of < 2^31 such terms are exact
         if (j < 0 || j >= n) { bad |= 2; continue; }
         if (j == i) continue;
         int jl = row_ptr[j], jh = row_ptr[j + 1];
@@ -2418,10 +2452,10 @@ extern "C" void nemk_sum_ranks_f64(nemk_stream s, int world, size_t count, const
 }
 
 extern "C" void nemk_graph_check(nemk_stream s, int n, int nnz, const int32_t *row_ptr,
-                                 const int32_t *col, int32_t *flags2) {
+                                 const int32_t *col, const float *wgt, int32_t *flags2) {
     cudaMemsetAsync(flags2, 0, 2 * sizeof(int32_t), S(s));
     if (n <= 0) return;
-    k_graph_check<<<cdiv(n, 256), 256, 0, S(s)>>>(n, nnz, row_ptr, col, flags2);
+    k_graph_check<<<cdiv(n, 256), 256, 0, S(s)>>>(n, nnz, row_ptr, col, wgt, flags2);
     note_launch();
 }
 

@@ -120,6 +120,7 @@ int nemb_subsample(nemb_handle *src, nemb_handle *h, const uint32_t *genome_mask
     h->d_row_ptr = h->d_col = h->d_rrow_ptr = h->d_rcol = NULL; h->d_wgt = NULL;
     if (h->spatial) {
         h->nnz = tot[1]; h->max_neigh = tot[2];
+        h->wgt_integral = !getenv("NEM_B200_ORDERED_SUMS");   /* coverages are popcounts */
         h->d_row_ptr = h->b_row_ptr.p; h->d_col = h->b_col.p; h->d_wgt = h->b_wgt.p;
         h->d_rrow_ptr = h->d_row_ptr; h->d_rcol = h->d_col;
         size_t hl_blocks = ((size_t)n + 1023) / 1024 + 1;

@@ -368,14 +368,40 @@ def test_margin_cache_is_exact_on_long_fits(engine, oracle, graph, beta, disp, m
     theta = oracle.default_theta(3, pg.d, low_disp=0.3)
     kw = dict(k=3, algo="ncem", update="seq", disp=disp, prop="pk", beta=beta, it_max=60)
     ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(*theta)
-    engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
-    for off in ("", "1"):
-        if off:
-            monkeypatch.setenv("NEM_B200_NO_MARGINS", "1")
-        else:
-            monkeypatch.delenv("NEM_B200_NO_MARGINS", raising=False)
+    for off, ordered in (("", ""), ("1", ""), ("", "1")):
+        # ordered: hubs add their neighbours' weights in file order even though the weights are
+        # integers (the default then is an order-free parallel sum, exact for integers)
+        for name, val in (("NEM_B200_NO_MARGINS", off), ("NEM_B200_ORDERED_SUMS", ordered)):
+            if val:
+                monkeypatch.setenv(name, val)
+            else:
+                monkeypatch.delenv(name, raising=False)
+        engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
         got = engine.fit(*theta, **kw)
         assert got.iters == ref.iters and got.converged == ref.converged, (got.iters, ref.iters)
         assert np.array_equal(engine.labels(), ref.label), int((engine.labels() != ref.label).sum())
         assert np.array_equal(got.center, ref.center) and np.array_equal(got.disp, ref.disp)
         assert got.n_ties == ref.n_ties and got.n_allnul == ref.n_allnul
+
+
+def test_fractional_weights_keep_the_file_order(engine, oracle):
+    """Non-integer edge weights: the fp64 context sums depend on the order, so the engine must add
+    them in file order like SumNeighsOfClass (nem_alg.c:2865-2875), hubs included."""
+    pg = make_case(12000, 48, seed=23, graph="pangenome")
+    rng = np.random.default_rng(5)
+    wgt = (pg.wgt * rng.uniform(0.05, 1.0, size=pg.wgt.shape)).astype(np.float32)
+    src = np.repeat(np.arange(pg.n), np.diff(pg.row_ptr))          # keep the graph symmetric in value
+    lo, hi = np.minimum(src, pg.col), np.maximum(src, pg.col)
+    key = lo.astype(np.int64) * pg.n + hi
+    order = np.argsort(key, kind="stable")
+    first = np.ones(key.size, dtype=bool); first[1:] = key[order][1:] != key[order][:-1]
+    canon = np.empty(key.size, dtype=np.float32)
+    canon[order] = np.repeat(wgt[order][first], np.diff(np.append(np.flatnonzero(first), key.size)))
+    theta = oracle.default_theta(3, pg.d)
+    kw = dict(k=3, algo="ncem", update="seq", disp="sk_", prop="pk", beta=0.7, it_max=60)
+    ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, canon, **kw).fit(*theta)
+    engine.load_dense(pg.x, pg.row_ptr, pg.col, canon)
+    got = engine.fit(*theta, **kw)
+    assert got.iters == ref.iters
+    assert np.array_equal(engine.labels(), ref.label)
+    assert np.array_equal(got.disp, ref.disp)
