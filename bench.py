@@ -497,6 +497,7 @@ def main_ours(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     iters = sum(f.iters for f in timed)
     launches = sum(f.kernel_launches for f in timed)
+    lab_resident = eng.labels()          # untimed: the e2e path below must reproduce these labels
     # per-stage CUDA-event timings (roofline): separate, untimed-for-`value` fits with profile=1
     for s in range(min(args.steps, 3)):
         if flush is not None:
@@ -527,6 +528,7 @@ def main_ours(args):
         e_iters += f.iters
     barrier()
     e_wall = time.time() - e0
+    e2e_same = bool(np.array_equal(lab_host, lab_resident))
     depth = eng.dims()["depth"] if mode != "sharded" else 0      # builds the level schedule: untimed
     h2d = x_bytes + (0 if col is None else (n_glob + 1) * 4 + nnz * 8) + (K + 2 * K * d) * 4
     d2h = n_glob + (K + 2 * K * d) * 4 + 256
@@ -591,6 +593,7 @@ def main_ours(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e_ms_max / e2e_steps,
                     "load_ms": t_load * 1e3 / e2e_steps, "fit_ms": t_fit * 1e3 / e2e_steps,
+                    "labels_equal_resident_fit": e2e_same,
                     "what": "nemb_load_shard(host pinned X + CSR: H2D, device-side graph validation) + nemb_fit + nemb_get_labels"},
             "roofline": {"bound": "hbm", "kernel": "k_density_tma (E-step Bernoulli log-likelihood, popcount path)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -195,6 +195,21 @@ int nemb_fit_logged(nemb_handle *h, const nemb_options *opt, float *prop, float 
 int nemb_fit_random(nemb_handle *h, const nemb_options *opt, int n_starts, int64_t seed,
                     float *prop, float *center, float *disp, nemb_result *res);
 
+/* The pieces of nemb_fit_random, exposed so that every start can be checked on its own:
+ * InitPara's whole-sample dispersion (nem_alg.c:1253-1265: the M-step with every family in the
+ * first class), and MakeRandomPara for start number `start` (nem_alg.c:1381-1473: centres =
+ * distinct random data rows, dispersion = sample dispersion / K, equal proportions).  Start s
+ * draws from its own splitmix64 stream derived from (seed, s): reproducible and independent of
+ * the order the starts run in. */
+int nemb_sample_dispersion(nemb_handle *h, const nemb_options *opt, float *disp_sample /*[d]*/);
+int nemb_random_start(nemb_handle *h, int k, int64_t seed, int start, const float *disp_sample,
+                      float *prop, float *center, float *disp);
+/* nemb_fit_random over n_workers host threads / streams sharing the resident pangenome (the
+ * result does not depend on n_workers; nemb_fit_random uses 4, env NEM_B200_RANDOM_WORKERS) */
+int nemb_fit_random_workers(nemb_handle *h, const nemb_options *opt, int n_starts, int64_t seed,
+                            int n_workers, float *prop, float *center, float *disp,
+                            nemb_result *res);
+
 /* n = the GLOBAL number of families (every rank of a sharded fit holds all labels) */
 int nemb_get_posteriors(nemb_handle *h, float *t_out /*[n*k]*/);
 int nemb_get_labels(nemb_handle *h, int32_t *label_out /*[n]*/);   /* MAP, first maximum */

@@ -155,6 +155,8 @@ class Fit:
     empty_class: int = 0
     exchanges: int = 0
     n_kept: int = 0
+    best_start: int = 0
+    n_success: int = 0
 
 
 class Engine:
@@ -265,12 +267,31 @@ class Engine:
         return out
 
     # ---- fit
-    def fit(self, prop0, center0, disp0, n_random_starts=0, seed=42, **kw) -> Fit:
+    def sample_dispersion(self, **kw):
+        o = make_options(**kw)
+        out = np.zeros(self.d, dtype=np.float32)
+        self._check(self.lib.nemb_sample_dispersion(self.h, C.byref(o), _p(out)))
+        self.k = o.k
+        return out
+
+    def random_start(self, k, seed, start, disp_sample):
+        prop = np.zeros(k, dtype=np.float32)
+        center = np.zeros((k, self.d), dtype=np.float32)
+        disp = np.zeros((k, self.d), dtype=np.float32)
+        self._check(self.lib.nemb_random_start(self.h, int(k), C.c_int64(seed), int(start),
+                                               _p(_f32(disp_sample)), _p(prop), _p(center), _p(disp)))
+        return prop, center, disp
+
+    def fit(self, prop0, center0, disp0, n_random_starts=0, seed=42, random_workers=0, **kw) -> Fit:
         """theta0 = (prop0[K], center0[K,D], disp0[K,D]); kw = make_options() fields."""
         o = make_options(**kw)
         prop, center, disp = _f32(prop0).copy(), _f32(center0).copy(), _f32(disp0).copy()
         r = Result()
-        if n_random_starts:
+        if n_random_starts and random_workers:
+            rc = self.lib.nemb_fit_random_workers(self.h, C.byref(o), int(n_random_starts), C.c_int64(seed),
+                                                  int(random_workers), _p(prop), _p(center), _p(disp),
+                                                  C.byref(r))
+        elif n_random_starts:
             rc = self.lib.nemb_fit_random(self.h, C.byref(o), int(n_random_starts), C.c_int64(seed),
                                           _p(prop), _p(center), _p(disp), C.byref(r))
         else:
@@ -285,7 +306,8 @@ class Engine:
                         mstep_delta=r.ms_mstep_delta),
                    dict(density=r.n_density, sweep=r.n_sweep, mstep=r.n_mstep,
                         criteria=r.n_criteria, density_cached=r.n_density_cached,
-                        mstep_delta=r.n_mstep_delta), r.empty_class, r.exchanges, r.n_kept)
+                        mstep_delta=r.n_mstep_delta), r.empty_class, r.exchanges, r.n_kept, r.best_start,
+                   r.n_success)
 
     def posteriors(self, k=None):
         k = k or self.k

@@ -17,6 +17,7 @@
 #include <cuda_runtime_api.h>
 #include <float.h>
 #include <math.h>
+#include <pthread.h>
 #include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -1487,111 +1488,269 @@ static uint64_t splitmix64(uint64_t *s)
     return z ^ (z >> 31);
 }
 
-int nemb_fit_random(nemb_handle *h, const nemb_options *o, int n_starts, int64_t seed, float *prop,
-                    float *center, float *disp, nemb_result *res)
+/* ------------------------------------------------------------------ random starts (init_mode 1)
+ * RandNemAlgo (nem_alg.c:1574-1742) = InitPara (1200-1280: dispersion of the whole sample from an
+ * all-in-class-1 M-step) + n_starts x { MakeRandomPara (1381-1473: centres = distinct random data
+ * rows, dispersion = sample dispersion / K, equal proportions); fit } + keep the best start by
+ * criterion M (first maximum) + a final EstimPara on the best partition.  The reference draws from
+ * libc random() seeded with time(NULL); here start s has its own splitmix64 stream derived from
+ * (seed, s), so the starts are reproducible and independent of the order they run in -- which lets
+ * several worker streams fit them concurrently. */
+int nemb_sample_dispersion(nemb_handle *h, const nemb_options *o, float *disp_sample)
+{
+    if (!h || !o || !disp_sample) return NEMB_E_ARG;
+    int rc, k = o->k;
+    CK(cudaSetDevice(h->device));
+    if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if ((rc = need_single(h, "nemb_sample_dispersion")) != NEMB_OK) return rc;
+    if ((rc = ensure_k(h, k)) != NEMB_OK) return rc;
+    if (o->algo != NEMB_ALGO_NCEM && (rc = ensure_t(h, k, 1)) != NEMB_OK) return rc;
+    size_t kd = (size_t)k * h->d;
+    float *theta = malloc(sizeof(float) * (k + 2 * kd));
+    if (!theta) return fail(h, NEMB_E_MEMORY, "host alloc");
+    for (int c = 0; c < k; c++) theta[c] = (float)(1.0 / k);
+    for (size_t q = 0; q < 2 * kd; q++) theta[k + q] = 0.5f;
+    rc = upload_theta(h, k, theta, theta + k, theta + k + kd);
+    free(theta);
+    if (rc != NEMB_OK) return rc;
+    h->cur = 0; h->state_labels = o->algo == NEMB_ALGO_NCEM;
+    CK(cudaMemsetAsync(h->d_lab[0], 0, h->n, h->stream));          /* every family in class 1 */
+    if (!h->state_labels) { nemk_labels_to_t(h->stream, k, h->n, h->d_lab[0], h->d_t[0]); CKK(); }
+    h->stats_valid = 0; h->ham_valid = 0; h->prev_valid = 0; h->last_changed = -1;
+    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
+    if ((rc = run_mstep(h, o, 0)) != NEMB_OK) return rc;
+    CK(cudaMemcpyAsync(disp_sample, h->d_disp, sizeof(float) * h->d, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEMB_OK;
+}
+
+int nemb_random_start(nemb_handle *h, int k, int64_t seed, int start, const float *disp_sample,
+                      float *prop, float *center, float *disp)
+{
+    if (!h || !h->loaded || !disp_sample || !prop || !center || !disp || k < 1 || k > NEMB_MAX_K || start < 0)
+        return NEMB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    int n = h->n, d = h->d, wpr = h->wpr;
+    uint64_t rng = (uint64_t)(seed ? seed : 42) + 0x632be59bd9b4e019ULL * (uint64_t)(start + 1);
+    uint32_t *rows = malloc(sizeof(uint32_t) * (size_t)k * wpr);
+    if (!rows) return fail(h, NEMB_E_MEMORY, "host alloc");
+    for (int c = 0; c < k; c++) {
+        prop[c] = (float)(1.0 / k);
+        for (int j = 0; j < d; j++) disp[(size_t)c * d + j] = disp_sample[j] / (float)k;
+        for (int draw = 0, again = 1; again && draw < 100; draw++) {
+            int ipt = (int)(splitmix64(&rng) % (uint64_t)n);
+            cudaError_t e = cudaMemcpyAsync(rows + (size_t)c * wpr, h->d_x + (size_t)ipt * wpr,
+                                            sizeof(uint32_t) * wpr, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { free(rows); return fail(h, NEMB_E_CUDA, "%s", cudaGetErrorString(e)); }
+            again = 0;   /* drawn again while identical to a previous centre (nem_alg.c:1421-1449) */
+            for (int p = 0; p < c && !again; p++)
+                if (!memcmp(rows + (size_t)p * wpr, rows + (size_t)c * wpr, sizeof(uint32_t) * wpr))
+                    again = 1;
+        }
+        for (int j = 0; j < d; j++)
+            center[(size_t)c * d + j] = (float)((rows[(size_t)c * wpr + (j >> 5)] >> (j & 31)) & 1u);
+    }
+    free(rows);
+    return NEMB_OK;
+}
+
+/* a second handle on the SAME resident pangenome (X, X^T, graph, hub list are borrowed, never
+ * freed or written through `w`); its per-fit state is its own */
+static void attach_problem(nemb_handle *w, const nemb_handle *src)
+{
+    reset_problem(w);
+    w->n = src->n; w->n_glob = src->n_glob; w->row0 = src->row0; w->shard_len = src->shard_len;
+    w->lab_len = src->lab_len; w->d = src->d; w->wpr = src->wpr; w->nwt = src->nwt;
+    w->nnz = src->nnz; w->spatial = src->spatial; w->symmetric = src->symmetric;
+    w->max_neigh = src->max_neigh; w->wgt_integral = src->wgt_integral;
+    w->d_x = src->d_x; w->x_owned = 0;
+    w->d_xt = src->d_xt; w->have_xt = src->have_xt;
+    w->d_pop = src->d_pop; w->have_pop = src->have_pop;
+    w->d_row_ptr = src->d_row_ptr; w->d_col = src->d_col; w->d_wgt = src->d_wgt;
+    w->d_rrow_ptr = src->d_rrow_ptr; w->d_rcol = src->d_rcol;
+    w->d_heavy = src->d_heavy; w->n_heavy = src->n_heavy;
+    w->loaded = 1;
+}
+
+typedef struct {
+    nemb_handle *src;
+    const nemb_options *opt;
+    const float *sam;
+    int64_t seed;
+    int n_starts, next, failed_rc;
+    size_t state_bytes;
+    pthread_mutex_t mu;
+    /* per worker results */
+    struct rs_best { int start, nsucc, last_status; nemb_result res; float *theta; void *state; nemb_handle *w; } *best;
+    int64_t launches;
+    char err[256];
+} rs_ctx;
+
+/* fits the starts it pulls from ctx->next on handle w; keeps its best (first maximum of M) */
+static int rs_run(rs_ctx *c, nemb_handle *w, struct rs_best *b)
+{
+    const nemb_options *o = c->opt;
+    int k = o->k, d = w->d, rc = NEMB_OK;
+    size_t kd = (size_t)k * d;
+    float *theta = malloc(sizeof(float) * (k + 2 * kd));
+    if (!theta) return NEMB_E_MEMORY;
+    b->start = -1; b->nsucc = 0; b->last_status = NEMB_W_EMPTYCLASS;
+    for (;;) {
+        int s = __atomic_fetch_add(&c->next, 1, __ATOMIC_RELAXED);
+        if (s >= c->n_starts) break;
+        float *prop = theta, *center = theta + k, *disp = theta + k + kd;
+        if ((rc = nemb_random_start(w, k, c->seed, s, c->sam, prop, center, disp)) != NEMB_OK) break;
+        nemb_options oo = *o;
+        oo.profile = 0;
+        nemb_result cur;
+        int frc = nemb_fit(w, &oo, prop, center, disp, &cur);
+        if (frc != NEMB_OK && frc != NEMB_W_EMPTYCLASS) { rc = frc; break; }
+        __atomic_fetch_add(&c->launches, cur.kernel_launches, __ATOMIC_RELAXED);
+        b->last_status = cur.status;
+        if (cur.status != NEMB_OK) continue;
+        b->nsucc++;
+        /* workers pull starts in increasing order: a strict > keeps the first maximum */
+        if (b->start < 0 || cur.M > b->res.M) {
+            b->res = cur; b->start = s;
+            memcpy(b->theta, theta, sizeof(float) * (k + 2 * kd));
+            cudaError_t e = cudaMemcpyAsync(b->state, o->algo == NEMB_ALGO_NCEM ? (void *)w->d_lab[w->cur]
+                                                                                : (void *)w->d_t[w->cur],
+                                            c->state_bytes, cudaMemcpyDeviceToDevice, w->stream);
+            if (e != cudaSuccess) { rc = NEMB_E_CUDA; break; }
+        }
+    }
+    cudaStreamSynchronize(w->stream);
+    free(theta);
+    return rc;
+}
+
+static void *rs_worker(void *arg)
+{
+    rs_ctx *c = ((void **)arg)[0];
+    struct rs_best *b = ((void **)arg)[1];
+    int rc = rs_run(c, b->w, b);
+    if (rc != NEMB_OK) {
+        pthread_mutex_lock(&c->mu);
+        if (c->failed_rc == NEMB_OK) { c->failed_rc = rc; snprintf(c->err, sizeof c->err, "%s", nemb_last_error(b->w)); }
+        pthread_mutex_unlock(&c->mu);
+    }
+    return NULL;
+}
+
+int nemb_fit_random_workers(nemb_handle *h, const nemb_options *o, int n_starts, int64_t seed,
+                            int n_workers, float *prop, float *center, float *disp, nemb_result *res)
 {
     if (!h || !o || !prop || !center || !disp || !res) return NEMB_E_ARG;
     int rc, k = o->k;
     CK(cudaSetDevice(h->device));
     if ((rc = check_options(h, o)) != NEMB_OK) return rc;
     if ((rc = need_single(h, "nemb_fit_random")) != NEMB_OK) return rc;
-    if ((rc = ensure_k(h, k)) != NEMB_OK) return rc;
-    if (o->algo != NEMB_ALGO_NCEM && (rc = ensure_t(h, k, 1)) != NEMB_OK) return rc;
-    if (n_starts <= 0) n_starts = 50;                       /* DEFAULT_NBRANDINITS */
-    uint64_t rng = seed ? (uint64_t)seed : 42;
-    int n = h->n, d = h->d, wpr = h->wpr;
-    size_t kd = (size_t)k * d, nk = (size_t)n * k;
+    if (n_starts <= 0) n_starts = 50;                       /* DEFAULT_NBRANDINITS, nem_typ.h:94 */
+    if (n_workers < 1) n_workers = 1;
+    if (n_workers > 16) n_workers = 16;
+    if (n_workers > n_starts) n_workers = n_starts;
+    int n = h->n, d = h->d;
+    size_t kd = (size_t)k * d;
     memset(res, 0, sizeof *res);
-    h->launches = 0; h->fixup_rounds = 0; h->profile = 0; h->ev_n = 0;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, h->stream));
-
-    /* whole-sample dispersion under the requested model */
-    float *sam = malloc(sizeof(float) * d), *best_theta = malloc(sizeof(float) * (2 * kd + k));
-    uint32_t *rows = malloc(sizeof(uint32_t) * (size_t)k * wpr);
-    int *picked = malloc(sizeof(int) * k);
-    void *best_state = NULL;
-    size_t state_bytes = o->algo == NEMB_ALGO_NCEM ? (size_t)n : sizeof(float) * nk;
-    CK(cudaMalloc(&best_state, state_bytes));
-    for (size_t q = 0; q < kd; q++) { center[q] = 0.5f; disp[q] = 0.5f; }
-    for (int c = 0; c < k; c++) prop[c] = (float)(1.0 / k);
-    if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
-    h->cur = 0; h->state_labels = o->algo == NEMB_ALGO_NCEM;
-    CK(cudaMemsetAsync(h->d_lab[0], 0, n, h->stream));
-    if (!h->state_labels) { nemk_labels_to_t(h->stream, k, n, h->d_lab[0], h->d_t[0]); CKK(); }
-    h->stats_valid = 0; h->ham_valid = 0;
-    CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
-    if ((rc = run_mstep(h, o, 0)) != NEMB_OK) return rc;
-    CK(cudaMemcpyAsync(sam, h->d_disp, sizeof(float) * d, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-
-    int nsucc = 0, best_try = -1, last_status = NEMB_W_EMPTYCLASS;
-    nemb_result best_res, cur;
-    memset(&best_res, 0, sizeof best_res);
-    for (int s = 0; s < n_starts; s++) {
-        for (int c = 0; c < k; c++) {
-            prop[c] = (float)(1.0 / k);
-            for (int j = 0; j < d; j++) disp[(size_t)c * d + j] = sam[j] / (float)k;
-            int ipt = 0;
-            for (int draw = 0, again = 1; again && draw < 100; draw++) {
-                ipt = (int)(splitmix64(&rng) % (uint64_t)n);
-                CK(cudaMemcpy(rows + (size_t)c * wpr, h->d_x + (size_t)ipt * wpr,
-                              sizeof(uint32_t) * wpr, cudaMemcpyDeviceToHost));
-                again = 0;
-                for (int p = 0; p < c && !again; p++)
-                    if (!memcmp(rows + (size_t)p * wpr, rows + (size_t)c * wpr, sizeof(uint32_t) * wpr))
-                        again = 1;
-            }
-            picked[c] = ipt;
-            for (int j = 0; j < d; j++)
-                center[(size_t)c * d + j] = (float)((rows[(size_t)c * wpr + (j >> 5)] >> (j & 31)) & 1u);
-        }
-        if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
-        memset(&cur, 0, sizeof cur);
-        rc = em_core(h, o, theta_uniform(k, d, center, disp), &cur, NULL, NULL, prop, center, disp);
-        if (rc != NEMB_OK) return rc;
-        last_status = cur.status;
-        if (cur.status != NEMB_OK) continue;
-        nsucc++;
-        if (nsucc == 1 || cur.M > best_res.M) {
-            best_res = cur; best_try = s;
-            memcpy(best_theta, prop, sizeof(float) * k);
-            memcpy(best_theta + k, center, sizeof(float) * kd);
-            memcpy(best_theta + k + kd, disp, sizeof(float) * kd);
-            CK(cudaMemcpyAsync(best_state, o->algo == NEMB_ALGO_NCEM ? (void *)h->d_lab[h->cur]
-                                                                    : (void *)h->d_t[h->cur],
-                               state_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    float *sam = malloc(sizeof(float) * d);
+    if (!sam) return fail(h, NEMB_E_MEMORY, "host alloc");
+    if ((rc = nemb_sample_dispersion(h, o, sam)) != NEMB_OK) { free(sam); return rc; }
+    /* the first full M-step built X^T; the workers borrow it with the rest of the problem */
+    rs_ctx c;
+    memset(&c, 0, sizeof c);
+    c.src = h; c.opt = o; c.sam = sam; c.seed = seed; c.n_starts = n_starts; c.failed_rc = NEMB_OK;
+    c.state_bytes = o->algo == NEMB_ALGO_NCEM ? (size_t)n : sizeof(float) * (size_t)n * k;
+    pthread_mutex_init(&c.mu, NULL);
+    c.best = calloc((size_t)n_workers, sizeof *c.best);
+    void *args[16][2];
+    pthread_t th[16];
+    int made = 0;
+    for (int w = 0; w < n_workers && rc == NEMB_OK; w++, made++) {
+        struct rs_best *b = &c.best[w];
+        b->theta = malloc(sizeof(float) * (k + 2 * kd));
+        if (cudaMalloc(&b->state, c.state_bytes) != cudaSuccess || !b->theta) { rc = fail(h, NEMB_E_MEMORY, "alloc"); made++; break; }
+        if (w == 0) b->w = h;                  /* the caller's handle fits starts too */
+        else {
+            if ((rc = nemb_create(&b->w, h->device)) != NEMB_OK) { made++; break; }
+            attach_problem(b->w, h);
         }
     }
-    if (nsucc > 0) {
-        memcpy(prop, best_theta, sizeof(float) * k);
-        memcpy(center, best_theta + k, sizeof(float) * kd);
-        memcpy(disp, best_theta + k + kd, sizeof(float) * kd);
-        if ((rc = upload_theta(h, k, prop, center, disp)) != NEMB_OK) return rc;
-        h->cur = 0;
-        CK(cudaMemcpyAsync(o->algo == NEMB_ALGO_NCEM ? (void *)h->d_lab[0] : (void *)h->d_t[0],
-                           best_state, state_bytes, cudaMemcpyDeviceToDevice, h->stream));
-        h->stats_valid = 0; h->ham_valid = 0;
-        CK(cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream));   /* + halt */
-        if ((rc = run_mstep(h, o, 0)) != NEMB_OK) return rc;   /* final EstimPara, nem_alg.c:1715 */
-        CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
-        *res = best_res;
-        res->status = NEMB_OK;
-        res->best_start = best_try + 1;
-        res->n_success = nsucc;
-    } else {
-        res->status = last_status;
+    if (rc == NEMB_OK) {
+        CK(cudaStreamSynchronize(h->stream));
+        int started = 0;
+        for (int w = 1; w < n_workers; w++) {
+            args[w][0] = &c; args[w][1] = &c.best[w];
+            if (pthread_create(&th[w], NULL, rs_worker, args[w]) == 0) started |= 1 << w;
+        }
+        int r0 = rs_run(&c, h, &c.best[0]);
+        for (int w = 1; w < n_workers; w++) if (started & (1 << w)) pthread_join(th[w], NULL);
+        rc = r0 != NEMB_OK ? r0 : c.failed_rc;
+        if (rc != NEMB_OK && r0 == NEMB_OK) fail(h, rc, "random-start worker: %s", c.err);
+    }
+    int best_w = -1, nsucc = 0, last_status = NEMB_W_EMPTYCLASS;
+    if (rc == NEMB_OK) {
+        for (int w = 0; w < n_workers; w++) {
+            struct rs_best *b = &c.best[w];
+            nsucc += b->nsucc;
+            if (b->nsucc == 0) { if (b->last_status != NEMB_W_EMPTYCLASS) last_status = b->last_status; continue; }
+            /* global first maximum: larger M, or the same M from an earlier start */
+            if (best_w < 0 || b->res.M > c.best[best_w].res.M ||
+                (b->res.M == c.best[best_w].res.M && b->start < c.best[best_w].start))
+                best_w = w;
+        }
+        if (best_w >= 0) {
+            struct rs_best *b = &c.best[best_w];
+            memcpy(prop, b->theta, sizeof(float) * k);
+            memcpy(center, b->theta + k, sizeof(float) * kd);
+            memcpy(disp, b->theta + k + kd, sizeof(float) * kd);
+            rc = ensure_k(h, k);
+            if (rc == NEMB_OK && o->algo != NEMB_ALGO_NCEM) rc = ensure_t(h, k, 1);
+            if (rc == NEMB_OK) rc = upload_theta(h, k, prop, center, disp);
+            if (rc == NEMB_OK) {
+                h->cur = 0; h->state_labels = o->algo == NEMB_ALGO_NCEM;
+                cudaMemcpyAsync(o->algo == NEMB_ALGO_NCEM ? (void *)h->d_lab[0] : (void *)h->d_t[0], b->state,
+                                c.state_bytes, cudaMemcpyDeviceToDevice, h->stream);
+                h->stats_valid = 0; h->ham_valid = 0; h->prev_valid = 0; h->last_changed = -1;
+                cudaMemsetAsync(&h->d_coef->empty_class, 0, 2 * sizeof(int32_t), h->stream);   /* + halt */
+                rc = run_mstep(h, o, 0);   /* final EstimPara on the best partition, nem_alg.c:1715 */
+            }
+            if (rc == NEMB_OK) {
+                cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream);
+                cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream);
+                cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream);
+                *res = b->res;
+                res->status = NEMB_OK;
+                res->best_start = b->start + 1;
+                res->n_success = nsucc;
+            }
+        } else {
+            res->status = last_status;
+        }
     }
     cudaEventRecord(e1, h->stream);
     cudaStreamSynchronize(h->stream);
     cudaEventElapsedTime(&res->fit_ms, e0, e1);
-    res->kernel_launches = h->launches;
-    res->fixup_rounds = h->fixup_rounds;
+    res->kernel_launches = c.launches;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(best_state);
-    free(sam); free(best_theta); free(rows); free(picked);
+    for (int w = 0; w < made && w < n_workers; w++) {
+        struct rs_best *b = &c.best[w];
+        if (b->state) cudaFree(b->state);
+        free(b->theta);
+        if (w > 0 && b->w) nemb_destroy(b->w);
+    }
+    free(c.best); free(sam);
+    pthread_mutex_destroy(&c.mu);
+    if (rc != NEMB_OK) return rc;
     return res->status;
+}
+
+int nemb_fit_random(nemb_handle *h, const nemb_options *o, int n_starts, int64_t seed, float *prop,
+                    float *center, float *disp, nemb_result *res)
+{
+    const char *e = getenv("NEM_B200_RANDOM_WORKERS");
+    return nemb_fit_random_workers(h, o, n_starts, seed, e ? atoi(e) : 4, prop, center, disp, res);
 }
