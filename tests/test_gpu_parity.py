@@ -405,3 +405,66 @@ def test_fractional_weights_keep_the_file_order(engine, oracle):
     assert got.iters == ref.iters
     assert np.array_equal(engine.labels(), ref.label)
     assert np.array_equal(got.disp, ref.disp)
+
+
+@pytest.mark.parametrize("algo,conv,thr,it_max", [("ncem", "crit", 1e-4, 40), ("ncem", "none", 0.01, 6),
+                                                 ("nem", "crit", 1e-3, 25), ("nem", "clas", 0.05, 40)])
+def test_convergence_tests(engine, oracle, algo, conv, thr, it_max):
+    """HasConverged (nem_alg.c:2056-2112): `crit` = relative change of criterion M, `none` = run
+    it_max iterations, `clas` on fuzzy posteriors = max |t - t_old| < thr."""
+    pg = make_case(5000, 40, seed=12)
+    engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
+    theta = oracle.default_theta(3, pg.d)
+    kw = dict(k=3, algo=algo, update="seq" if algo == "ncem" else "para", conv=conv, conv_thr=thr,
+              disp="sk_", prop="pk", beta=0.5, it_max=it_max)
+    ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(*theta)
+    got = engine.fit(*theta, **kw)
+    assert got.iters == ref.iters and got.converged == ref.converged
+    if conv == "none":
+        assert got.iters == it_max and not got.converged
+    if algo == "ncem":
+        assert np.array_equal(engine.labels(), ref.label)
+    else:
+        assert rel_close(engine.posteriors(), ref.t, RTOL, atol=1e-30)
+    for key in "UDLM":
+        assert rel_close(got.crit[key], ref.crit[key], RTOL), key
+
+
+@pytest.mark.parametrize("n,d", [(1, 1), (2, 33), (31, 1), (33, 32), (257, 65)])
+def test_tiny_and_ragged_shapes(oracle, n, d):
+    """Shapes around the packing granules: one family, one genome, N and D just past 32/64-bit
+    word and 256-row tile boundaries, families without neighbours."""
+    from pangenomenem_b200 import capi
+    rng = np.random.default_rng(n * 100 + d)
+    q = np.array([0.95, 0.5, 0.05])[np.arange(n) % 3]                     # persistent / shell / cloud rows
+    x = (rng.random((n, d)) < q[:, None]).astype(np.uint8)
+    x[x.sum(axis=1) == 0, 0] = 1
+    # a chain graph with integer weights; the last family stays isolated when n > 2
+    src, dst = [], []
+    for i in range(max(0, n - 2)):
+        src += [i, i + 1]; dst += [i + 1, i]
+    order = np.lexsort((dst, src)) if src else np.zeros(0, dtype=np.int64)
+    src, dst = np.asarray(src, dtype=np.int64)[order], np.asarray(dst, dtype=np.int32)[order]
+    row_ptr = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(row_ptr, src + 1, 1)
+    row_ptr = np.cumsum(row_ptr).astype(np.int32)
+    wgt = (1 + (np.arange(dst.size) % 3)).astype(np.float32)
+    wgt = np.where(src < dst, wgt, 0).astype(np.float32)                 # symmetric values
+    key = {(int(a), int(b)): float(w) for a, b, w in zip(src, dst, wgt) if a < b}
+    wgt = np.asarray([key[(min(a, b), max(a, b))] for a, b in zip(src, dst)], dtype=np.float32)
+    prop = np.array([0.5, 0.3, 0.2], dtype=np.float32)
+    center = np.repeat(np.array([1.0, 0.5, 0.0], dtype=np.float32)[:, None], d, axis=1)
+    disp = np.repeat(np.array([0.1, 0.45, 0.2], dtype=np.float32)[:, None], d, axis=1)
+    kw = dict(k=3, algo="ncem", update="seq", disp="sk_", prop="pk", beta=0.5, it_max=20)
+    ref = oracle.Problem(x, row_ptr, dst, wgt, **kw).fit(prop, center, disp)
+    eng = capi.Engine(0)
+    eng.load_dense(x, row_ptr, dst, wgt)
+    assert np.array_equal(eng.packed()[:, :(d + 31) // 32],
+                          np.packbits(np.pad(x, ((0, 0), (0, (-d) % 32))).reshape(n, -1, 32), axis=2,
+                                      bitorder="little").view(np.uint32).reshape(n, -1))
+    got = eng.fit(prop, center, disp, **kw)
+    assert got.status == ref.status and got.iters == ref.iters
+    if ref.status == 0:
+        assert np.array_equal(eng.labels(), ref.label)
+        assert np.array_equal(got.center, ref.center) and np.array_equal(got.disp, ref.disp)
+    eng.close()
