@@ -248,6 +248,18 @@ int  nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc
 void nemk_criteria_final(nemk_stream s, int nblocks_total, const double *partials, double beta,
                          double *crit6);
 
+/* ---- row-sharded sweep, sparse label exchange (nem_kernels.cu "SPARSE label exchange"): a block is
+ * 2 + 2*cap int32 words; blocks = the all-gathered [world] blocks.  After nemk_delta_apply
+ * cnt->pending is the global number of cross-rank (reader, moved label) pairs, or -1 when some
+ * rank moved more than cap labels (nothing was applied: do a full exchange instead);
+ * cnt->changed_glob = labels changed over all ranks. */
+void nemk_delta_pack(nemk_stream s, int row0, int n_loc, int cap, const uint8_t *lab_cur,
+                     const uint8_t *seen, const nemk_counters *cnt, int32_t *block, const int32_t *skip);
+void nemk_delta_apply(nemk_stream s, int world, int cap, const int32_t *blocks, int row0, int n_loc,
+                      int shard_len, uint8_t *lab_cur, uint8_t *seen, int32_t *dirty, int32_t *wl,
+                      int32_t *wl_count, const int32_t *rrow_ptr, const int32_t *rcol,
+                      nemk_counters *cnt, const int32_t *skip);
+
 /* ---- rank-ordered sums over an all-gathered stage [world][count] */
 void nemk_sum_ranks_i32(nemk_stream s, int world, size_t count, const int32_t *stage, int32_t *out);
 void nemk_sum_ranks_f64(nemk_stream s, int world, size_t count, const double *stage, double *out);

@@ -486,6 +486,8 @@ static int ensure_k(nemb_handle *h, int k)
     size_t o_lab0 = carve(&off, L), o_lab1 = carve(&off, L), o_lab2 = carve(&off, L);
     size_t o_lab3 = carve(&off, n + 1), o_ham = carve(&off, 4 * n * k + 4), o_sl = carve(&off, 4 * (kd + k));
     size_t o_margin = carve(&off, 4 * n + 4), o_stale0 = carve(&off, L), o_stale1 = carve(&off, L);
+    size_t delta_b = sizeof(int32_t) * (2 + 2 * DELTA_CAP);
+    size_t o_xchg = carve(&off, delta_b), o_xchg_all = carve(&off, delta_b * W);
     size_t o_dirty = carve(&off, 4 * L);
     size_t o_wl0 = carve(&off, 4 * (n + 1)), o_wl1 = carve(&off, 4 * (n + 1));
     size_t o_wlc = carve(&off, 4 * 8);
@@ -508,6 +510,7 @@ static int ensure_k(nemb_handle *h, int k)
     h->d_lab[2] = (uint8_t *)(base + o_lab2); h->d_lab[3] = (uint8_t *)(base + o_lab3);
     h->d_ham = (int32_t *)(base + o_ham); h->d_stat_loc = (int32_t *)(base + o_sl);
     h->d_margin = (float *)(base + o_margin);
+    h->d_xchg = (int32_t *)(base + o_xchg); h->d_xchg_all = (int32_t *)(base + o_xchg_all);
     h->d_stale[0] = (uint8_t *)(base + o_stale0); h->d_stale[1] = (uint8_t *)(base + o_stale1);
     h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1;
     h->d_dirty = (int32_t *)(base + o_dirty);
@@ -831,7 +834,10 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
                                    0, 0, h->mg);
             h->launches++;
             /* halo exchange of the hard labels: every rank's slice, 1 byte per family */
-            if (h->world > 1 && (rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
+            if (h->world > 1) {
+                if ((rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
+                CK(cudaMemcpyAsync(seen, out, h->lab_len, cudaMemcpyDeviceToDevice, h->stream));   /* invariant: seen == labels */
+            }
             *flipped = 1;
         } else if (impl == NEMB_SWEEP_SPEC) {
             /* margin cache (one GPU, Hamming-count scores): sites whose margin exceeds what theta
@@ -870,20 +876,48 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
                  * global pending / changed counts from the exchanged labels themselves
                  * (k_mark_remote), and the last round's status -- convergence decided on the
                  * device when `decide` is given -- doubles as the iteration's status. */
+                const int dec = decide && decide->conv != NEMB_CONV_CRIT;
+                const size_t delta_b = sizeof(int32_t) * (2 + 2 * DELTA_CAP);
                 for (int guard = 0;; guard++) {
-                    if ((rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
-                    CK(cudaMemsetAsync(&h->d_status->cnt.pending, 0, 2 * sizeof(int32_t), h->stream));   /* + changed_glob */
-                    nemk_mark_remote(h->stream, h->n_glob, row0, n, (int)SL, out, in, guard ? seen : in,
-                                     seen, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
-                                     h->d_rcol, &h->d_status->cnt, skip);
-                    h->launches++;
-                    unsigned long long seq = ++h->seq;
-                    nemk_iter_end(h->stream, 0, &h->d_status->cnt, h->d_status, h->d_coef,
-                                  decide && decide->conv != NEMB_CONV_CRIT, 1, decide ? decide->conv : 0,
-                                  decide ? decide->conv_thr : 0.f, h->d_ring + (seq % RING), seq);
-                    h->launches++;
-                    CKK();
-                    if ((rc = wait_status(h, seq)) != NEMB_OK) return rc;
+                    unsigned long long seq;
+                    /* sparse round first when few labels are expected to have moved: blocks of
+                     * (family, label) pairs instead of whole slices.  `seen` holds, on every
+                     * rank, the labels as of the previous exchange (== the input labels at the
+                     * start of a sweep). */
+                    int sparse = !getenv("NEM_B200_FULL_EXCHANGE") &&
+                                 (guard > 0 || (h->last_changed >= 0 && h->last_changed <= DELTA_CAP));
+                    int settled = -1;
+                    if (sparse) {
+                        nemk_delta_pack(h->stream, row0, n, DELTA_CAP, out, seen, &h->d_status->cnt,
+                                        h->d_xchg, skip);
+                        if ((rc = gather(h, h->d_xchg, h->d_xchg_all, delta_b)) != NEMB_OK) return rc;
+                        CK(cudaMemsetAsync(&h->d_status->cnt.pending, 0, 2 * sizeof(int32_t), h->stream));   /* + changed_glob */
+                        nemk_delta_apply(h->stream, h->world, DELTA_CAP, h->d_xchg_all, row0, n, (int)SL, out,
+                                         seen, h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
+                                         h->d_rcol, &h->d_status->cnt, skip);
+                        seq = ++h->seq;
+                        nemk_iter_end(h->stream, 0, &h->d_status->cnt, h->d_status, h->d_coef, dec, 1,
+                                      decide ? decide->conv : 0, decide ? decide->conv_thr : 0.f,
+                                      h->d_ring + (seq % RING), seq);
+                        h->launches += 3;
+                        CKK();
+                        if ((rc = wait_status(h, seq)) != NEMB_OK) return rc;
+                        settled = h->h_status->cnt.pending;   /* < 0: some rank moved too many labels */
+                    }
+                    if (settled < 0) {
+                        if ((rc = gather(h, out + (size_t)h->rank * SL, out, SL)) != NEMB_OK) return rc;
+                        CK(cudaMemsetAsync(&h->d_status->cnt.pending, 0, 2 * sizeof(int32_t), h->stream));   /* + changed_glob */
+                        nemk_mark_remote(h->stream, h->n_glob, row0, n, (int)SL, out, in, seen, seen,
+                                         h->d_dirty, h->d_wl[0], &h->d_wl_counts[0], h->d_rrow_ptr,
+                                         h->d_rcol, &h->d_status->cnt, skip);
+                        seq = ++h->seq;
+                        nemk_iter_end(h->stream, 0, &h->d_status->cnt, h->d_status, h->d_coef, dec, 1,
+                                      decide ? decide->conv : 0, decide ? decide->conv_thr : 0.f,
+                                      h->d_ring + (seq % RING), seq);
+                        h->launches += 2;
+                        CKK();
+                        if ((rc = wait_status(h, seq)) != NEMB_OK) return rc;
+                    }
                     if (h->h_status->cnt.pending == 0 || *h->h_empty) break;
                     if (guard > h->n_glob) return fail(h, NEMB_E_BUG, "sharded sweep did not settle");
                     local_fixups(h, k, beta, in, out, rp, skip, NULL);
@@ -1037,6 +1071,7 @@ static int init_state(nemb_handle *h, const nemb_options *o)
     CK(cudaMemsetAsync(h->d_stale[0], 0, h->lab_len, h->stream));
     CK(cudaMemsetAsync(h->d_stale[1], 0, h->lab_len, h->stream));
     if (h->state_labels) CK(cudaMemsetAsync(h->d_lab[0], 255, h->lab_len, h->stream));
+    if (h->state_labels && h->world > 1) CK(cudaMemsetAsync(h->d_lab[2], 255, h->lab_len, h->stream));   /* labels all ranks last saw */
     else {
         if ((rc = ensure_t(h, o->k, 1)) != NEMB_OK) return rc;
         CK(cudaMemsetAsync(h->d_t[0], 0, sizeof(float) * (size_t)h->lab_len * o->k, h->stream));

@@ -17,6 +17,7 @@
 #define MAX_WORLD 64
 #define CRIT_BLOCKS_MAX 1184 /* 148 SMs x 8 */
 #define CRIT_BLOCKS_SHARD 296
+#define DELTA_CAP 2048       /* labels a rank may publish per sparse exchange */
 #define RING 4              /* status slots in mapped host memory */
 
 typedef struct { int lo, hi, grid; } sweep_step;
@@ -76,6 +77,7 @@ struct nemb_handle {
     uint8_t *d_stale[2];   /* stale flags, swapped every speculative sweep */
     int stale_par, sweep_same_beta;
     nemk_margins mg;       /* the margins of the sweep being enqueued (m == NULL: off) */
+    int32_t *d_xchg, *d_xchg_all;     /* row shards: sparse label-exchange blocks (own, all ranks) */
     int prev_valid;        /* d_lab[cur ^ 1] holds the input labels of the last sweep (it flipped) */
     int lp_from_ham;       /* the consumers rebuild logpf from d_ham in registers (no logpf array) */
     int64_t last_changed;  /* labels moved by the last sweep (all ranks), -1 = unknown */

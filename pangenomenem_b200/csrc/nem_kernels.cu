@@ -1269,6 +1269,80 @@ k_mark_remote(int n_glob, int row0, int row1, int shard_len, const uint8_t *__re
     }
 }
 
+// ---- row-sharded sweep, SPARSE label exchange.  In the steady state a rank moves a few hundred
+// labels per sweep: instead of all-gathering whole 1-byte-per-family slices (and scanning them),
+// every rank packs (family, label) pairs for its own rows whose label differs from the one all
+// ranks last saw, the fixed-size blocks are all-gathered, and every rank applies ALL blocks:
+// remote labels are written into its copy, `seen` is refreshed, the later readers it owns are
+// queued, and the cross-rank (reader, label) pairs are counted -- the same number on every rank.
+// Block layout (int32 words): [0] entries wanted (> cap = overflow: nothing is applied and the
+// host falls back to a full exchange), [1] this rank's net changed-label count, then cap x
+// (family, label).
+__global__ void __launch_bounds__(256)
+k_delta_pack(int row0, int n_loc, int cap, const uint8_t *__restrict__ lab_cur,
+             const uint8_t *__restrict__ seen, const nemk_counters *__restrict__ cnt, int32_t *block,
+             const int32_t *__restrict__ skip) {
+    if (skip && (skip[0] | skip[1])) return;
+    int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il == 0) block[1] = cnt->changed;
+    bool mv = false;
+    int i = row0 + il;
+    uint8_t c = 0;
+    if (il < n_loc) { c = lab_cur[i]; mv = c != seen[i]; }
+    unsigned m = __ballot_sync(FULL, mv);
+    int lane = threadIdx.x & 31, base = 0;
+    if (m && lane == 0) base = atomicAdd(&block[0], __popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (mv) {
+        int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < cap) { block[2 + 2 * pos] = i; block[3 + 2 * pos] = (int)c; }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_delta_apply(int world, int cap, int block_words, const int32_t *__restrict__ blocks, int row0,
+              int row1, int shard_len, uint8_t *lab_cur, uint8_t *seen, int32_t *dirty, int32_t *wl,
+              int32_t *wl_count, const int32_t *__restrict__ rrow_ptr,
+              const int32_t *__restrict__ rcol, nemk_counters *cnt,
+              const int32_t *__restrict__ skip) {
+    if (skip && (skip[0] | skip[1])) return;
+    bool overflow = false;
+    int changed = 0;
+    for (int r = 0; r < world; r++) {
+        int c = blocks[(size_t)r * block_words];
+        overflow |= c > cap;
+        changed += blocks[(size_t)r * block_words + 1];
+    }
+    if (overflow) {   // uniform over the grid and over the ranks: the host sees pending < 0
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt->pending = -1;
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt->changed_glob = changed;
+    int pend = 0;
+    for (int r = blockIdx.y; r < world; r += gridDim.y) {
+        const int32_t *b = blocks + (size_t)r * block_words;
+        const int count = b[0];
+        const int own_lo = r * shard_len, own_hi = own_lo + shard_len;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+            const int j = b[2 + 2 * e];
+            const uint8_t l = (uint8_t)b[3 + 2 * e];
+            const bool j_mine = j >= row0 && j < row1;
+            if (!j_mine) lab_cur[j] = l;
+            seen[j] = l;
+            int lo = rrow_ptr[j], hi = rrow_ptr[j + 1];
+            for (int q = lo; q < hi; q++) {
+                int i = rcol[q];
+                if (i <= j || (i >= own_lo && i < own_hi)) continue;   // earlier, or same rank as j
+                pend++;
+                if (!j_mine && i >= row0 && i < row1 && atomicExch(&dirty[i], 1) == 0)
+                    wl[atomicAdd(wl_count, 1)] = i;
+            }
+        }
+    }
+    pend = __reduce_add_sync(FULL, pend);
+    if ((threadIdx.x & 31) == 0 && pend) atomicAdd(&cnt->pending, pend);
+}
+
 // ---- ncem, level-scheduled exact sequential sweep (reference order), in place.
 // sites[] is sorted by (level, index); no two sites of a level are neighbours, so a level is
 // updated in parallel; levels run in order (one launch per wide level, or one CTA walking a run
@@ -2435,6 +2509,26 @@ extern "C" void nemk_mark_remote(nemk_stream s, int n_glob, int row0, int n_loc,
     if (grid > num_sms() * 8) grid = num_sms() * 8;
     k_mark_remote<<<grid, 256, 0, S(s)>>>(n_glob, row0, row0 + n_loc, shard_len, lab_cur, lab_in,
                                           seen_in, seen_out, dirty, wl, wl_count, rrow_ptr, rcol, cnt, skip);
+    note_launch();
+}
+
+extern "C" void nemk_delta_pack(nemk_stream s, int row0, int n_loc, int cap, const uint8_t *lab_cur,
+                                const uint8_t *seen, const nemk_counters *cnt, int32_t *block,
+                                const int32_t *skip) {
+    cudaMemsetAsync(block, 0, 2 * sizeof(int32_t), S(s));
+    if (n_loc <= 0) return;
+    k_delta_pack<<<cdiv(n_loc, 256), 256, 0, S(s)>>>(row0, n_loc, cap, lab_cur, seen, cnt, block, skip);
+    note_launch();
+}
+
+extern "C" void nemk_delta_apply(nemk_stream s, int world, int cap, const int32_t *blocks, int row0,
+                                 int n_loc, int shard_len, uint8_t *lab_cur, uint8_t *seen,
+                                 int32_t *dirty, int32_t *wl, int32_t *wl_count,
+                                 const int32_t *rrow_ptr, const int32_t *rcol, nemk_counters *cnt,
+                                 const int32_t *skip) {
+    dim3 grid(8, world < 32 ? world : 32);
+    k_delta_apply<<<grid, 256, 0, S(s)>>>(world, cap, 2 + 2 * cap, blocks, row0, row0 + n_loc, shard_len,
+                                          lab_cur, seen, dirty, wl, wl_count, rrow_ptr, rcol, cnt, skip);
     note_launch();
 }
 
