@@ -55,13 +55,19 @@ def _worker(rank, world, port, q):
         t1, lab1 = full.sweep(logpf_full, 0.0, t_full0)
         res["blind_equal"] = bool(np.array_equal(lab, lab1))
         total_x = 0
+        pend_log = []
         for it in range(3):
-            lab, nx = proto.sharded_seq_sweep(dist, p, logpf, lab, pg.row_ptr, pg.col, pg.wgt, beta, k)
+            # cap 64 then 4: the second value forces the whole-slice fallback
+            lab, nx = proto.sharded_seq_sweep(dist, p, logpf, lab, pg.row_ptr, pg.col, pg.wgt, beta, k,
+                                              cap=64 if it != 1 else 4, check=pend_log)
             total_x += nx
             t1, lab1 = full.sweep(logpf_full, beta, t1)
             res[f"sweep{it}_equal"] = bool(np.array_equal(lab, lab1))
             res[f"sweep{it}_moved"] = int((lab1 != np.argmax(logpf_full, axis=1)).sum())
         res["exchanges"] = total_x
+        logs = [None] * world
+        dist.all_gather_object(logs, pend_log)              # test only: the engine exchanges no counters
+        res["pending_agree"] = all(l == logs[0] for l in logs) and any(v > 0 for v in logs[0])
 
         # (3) M-step statistics: rank-ordered sum of the per-rank integer counts == full counts
         t_loc = np.eye(k, dtype=np.float32)[lab[p.rows]]
@@ -92,7 +98,7 @@ def test_world2_protocol_matches_oracle():
     assert all(p.exitcode == 0 for p in procs)
     for rank in (0, 1):
         r = out[rank]
-        assert r["uid_same"] and r["blind_equal"] and r["stats_equal"], r
+        assert r["uid_same"] and r["blind_equal"] and r["stats_equal"] and r["pending_agree"], r
         assert all(r[f"sweep{i}_equal"] for i in range(3)), r
         assert r["sweep0_moved"] > 0, "the coupled sweep should move labels in this test"
         assert r["exchanges"] >= 3 and r["cut_edges"] > 0
