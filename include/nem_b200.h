@@ -52,7 +52,16 @@ typedef struct {
     int32_t device;      /* CUDA ordinal, -1 = env NEM_B200_DEVICE or current device */
     int32_t n_random_inits; /* init_mode 1: number of random starts, 0 = 50 (nem_typ.h:94) */
     int64_t seed;        /* init_mode 1 RNG seed, 0 = 42 (the reference uses time(NULL)) */
-    int32_t reserved[8];
+    /* beta estimation, the CLI's -B / -G / -H (nem_hlp.c:220-245, defaults nem_typ.h:70-79):
+     * beta_mode 0 fix, 1 psgrad, 2 heu_d, 3 heu_l (BetaET, nem_typ.h:128-135).  A zero
+     * parameter means the reference's default. */
+    int32_t beta_mode;
+    int32_t grad_n_iter;                 /* -G nit  [1]  */
+    float   grad_conv, grad_step;        /* -G conv [0.001] step [0 = Newton-like step] */
+    float   heu_step, heu_max;           /* -H bstep [0.1] bmax [2.0] */
+    float   heu_ddrop, heu_dloss;        /* -H ddrop [0.8] dloss [0.5] */
+    float   heu_lloss;                   /* -H lloss [0.02] */
+    int32_t reserved[7];
 } nem_b200_extra;
 
 int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float beta,
@@ -73,6 +82,7 @@ enum { NEMB_CONV_NONE = 0, NEMB_CONV_CLAS = 1, NEMB_CONV_CRIT = 2 }; /* nem_typ.
 enum { NEMB_PROP_EQUAL = 0, NEMB_PROP_K = 1 };                  /* nem_typ.h:200-205 */
 enum { NEMB_DISP___ = 0, NEMB_DISP_K_ = 1, NEMB_DISP__D = 2, NEMB_DISP_KD = 3 }; /* :191-198 */
 enum { NEMB_SWEEP_AUTO = 0, NEMB_SWEEP_LEVEL = 1, NEMB_SWEEP_SPEC = 2 };
+enum { NEMB_BETA_FIX = 0, NEMB_BETA_PSGRAD = 1, NEMB_BETA_HEUD = 2, NEMB_BETA_HEUL = 3 }; /* nem_typ.h:128-135 */
 
 typedef struct nemb_handle nemb_handle;
 
@@ -85,7 +95,14 @@ typedef struct {
     int32_t sweep_impl;
     int32_t profile;      /* 1: time every stage with CUDA events (adds event overhead) */
     float   beta, conv_thr;
-    int32_t reserved[8];
+    /* BETA_PSGRAD (EstimBeta, nem_alg.c:2120-2230): beta is re-estimated after every M-step by
+     * gradient ascent on the pseudo-likelihood of the current classification.  beta_mode is
+     * NEMB_BETA_FIX or NEMB_BETA_PSGRAD here; the two heuristics are nemb_fit_beta_heuristic(). */
+    int32_t beta_mode;
+    int32_t grad_n_iter;  /* gradient iterations per EM iteration; 0 = 1 (nem_typ.h:76) */
+    float   grad_conv;    /* stop when |gradient| < grad_conv * N; 0 = 0.001 (nem_typ.h:77) */
+    float   grad_step;    /* > 0: beta += grad*step/N; 0: beta += grad / max(4 dsec, N/10) (nem_typ.h:78) */
+    int32_t reserved[4];
 } nemb_options;
 
 typedef struct {
@@ -110,6 +127,9 @@ typedef struct {
     int32_t n_density_cached, n_mstep_delta;
     int64_t exchanges;    /* row shards: all-gathers this fit issued */
     int64_t n_kept;       /* site evaluations the margin cache of the dense sweep saved (all sweeps) */
+    float   beta;         /* beta of the last sweep and of the criteria (ModelParaT.Beta on return):
+                             the option's, or the estimate of psgrad / of a heuristic */
+    int32_t n_beta_tested;   /* nemb_fit_beta_heuristic: fits that ended without an empty class */
 } nemb_result;
 
 /* Per-iteration trace for the .log writer (nem_alg.c:1995-2052, 2620-2646). */
@@ -194,6 +214,36 @@ int nemb_fit_logged(nemb_handle *h, const nemb_options *opt, float *prop, float 
 /* init_mode 1 (RandNemAlgo, nem_alg.c:1574-1742): n_starts random starts, best by criterion. */
 int nemb_fit_random(nemb_handle *h, const nemb_options *opt, int n_starts, int64_t seed,
                     float *prop, float *center, float *disp, nemb_result *res);
+
+/* INIT_FILE (ClassifyByNemOneBeta, nem_alg.c:1091-1113): start NemAlgo from a given
+ * classification t_init[n*k] (host; under ncem every row must be one-hot) instead of the two
+ * initial sweeps.  The first M-step estimates theta from it (InitPara + MakeParaFromLabeled +
+ * the first EstimPara of NemAlgo); a class without any family ends the call with
+ * NEMB_W_EMPTYCLASS ("Class %d has no labeled observation", nem_alg.c:1338-1345).
+ * prop/center/disp are outputs only.  Single GPU. */
+int nemb_fit_from_partition(nemb_handle *h, const nemb_options *opt, const float *t_init,
+                            float *prop, float *center, float *disp, nemb_result *res);
+
+/* One evaluation of EstimBeta (nem_alg.c:2120-2230) on a classification t[n*k] (host): returns
+ * the new beta in *beta_io and, when sums3 != NULL, the log pseudo-likelihood, its gradient and
+ * minus its second derivative of the last gradient iteration.  Stage entry point of psgrad. */
+int nemb_stage_estim_beta(nemb_handle *h, const nemb_options *opt, const float *t, float *beta_io,
+                          double *sums3);
+
+/* ClassifyByNemHeuBeta (nem_alg.c:731-992): estimate beta by a sweep of complete fits at
+ * beta = 0, step, 2 step, ... <= max.  mode NEMB_BETA_HEUD: Hathaway criterion D, stop at the
+ * first drop of its slope below -ddrop * N, else threshold its total loss at dloss;
+ * NEMB_BETA_HEUL: mixture likelihood L, stop when it falls lloss * N under its maximum.  Like
+ * the reference every fit starts from the all-zero classification and from the PARAMETERS THE
+ * PREVIOUS FIT LEFT; the final fit at the estimate starts from the classification saved before
+ * the drop (INIT_FILE) or, for heu_d without a detected drop, from scratch.  A zero field of
+ * `hp` means the reference's default (nem_typ.h:71-75).  beta_trace/crit_trace (nullable, cap
+ * entries): the tested betas and their criterion.  res->beta = the estimate.  Single GPU. */
+typedef struct { float step, max, ddrop, dloss, lloss; } nemb_beta_heuristic;
+int nemb_fit_beta_heuristic(nemb_handle *h, const nemb_options *opt, int mode,
+                            const nemb_beta_heuristic *hp, float *prop, float *center,
+                            float *disp, nemb_result *res, float *beta_trace, float *crit_trace,
+                            int cap);
 
 /* The pieces of nemb_fit_random, exposed so that every start can be checked on its own:
  * InitPara's whole-sample dispersion (nem_alg.c:1253-1265: the M-step with every family in the

@@ -353,43 +353,117 @@ static float max_abs_diff(const float *a, const float *b, size_t m)
     return mx;
 }
 
-/* ClassifyByNemOneBeta INIT_PARAM_FILE branch (nem_alg.c:1151-1169):
- * ComputePartitionFromPara(Needinit=1) (nem_alg.c:1951-1989) then NemAlgo (1746-1879). */
-int nemo_fit(const nemo_problem *pb0, float *prop, float *center, float *disp,
-             float *t, int32_t *label, nemo_result *res)
+/* ------------------------------------------------------------------ beta estimation */
+/* EstimBeta, BETA_PSGRAD (nem_alg.c:2120-2230): gradient ascent on the log pseudo-likelihood of
+ * the classification t under the Potts prior,
+ *     crit = sum_i [ beta sum_k t_ik c_ik - log sum_k exp(beta c_ik) ],  c_ik = sum_j w_ij t_jk,
+ *     grad = sum_i [ sum_k t_ik c_ik - E_i(c) ],   dsec = sum_i Var_i(c)   (softmax(beta c_i.) law),
+ * step <= 0: beta += grad / max(4 dsec, N/10) (integer N/10, nem_alg.c:2194-2200), else
+ * beta += grad * step / N; stop after n_iter iterations or when |grad| < conv_thr * N; clamp to
+ * [-5, 5] (MAX_BETA/MIN_BETA, nem_alg.c:84-85), NaN -> 0.
+ * float64 site sums in index order (the reference: float32 running sums), softmax moments taken
+ * relative to max_k(beta c_ik) -- the same numbers as nem_alg.c:2172-2191 wherever the
+ * reference's float exp() does not overflow (there it yields NaN and beta = 0).  beta itself and
+ * its update stay float like *BetaP.  out3 (nullable) = crit, grad, dsec of the LAST iteration. */
+float nemo_estim_beta(const nemo_problem *pb, const nemo_psgrad *g, const float *t, float beta,
+                      double *out3)
+{
+    int n = pb->n, K = pb->k;
+    if (!pb->row_ptr) return beta;                      /* TYPE_NONSPATIAL: nem_alg.c:2150-2151 */
+    double *ctx = malloc(sizeof(double) * K);
+    double crit = 0, grad = 0, dsec = 0;
+    int conv = 0;
+    for (int it = 0; it < g->n_iter && !conv; it++) {
+        crit = grad = dsec = 0;
+        for (int i = 0; i < n; i++) {
+            context(pb, i, t, ctx);
+            const float *ti = t + (size_t)i * K;
+            double b = (double)beta, mx = -INFINITY;
+            for (int k = 0; k < K; k++) if (b * ctx[k] > mx) mx = b * ctx[k];
+            double se = 0, sce = 0, sc2e = 0, stc = 0;
+            for (int k = 0; k < K; k++) {
+                double e = exp(b * ctx[k] - mx);
+                se += e; sce += ctx[k] * e; sc2e += ctx[k] * ctx[k] * e;
+                stc += (double)ti[k] * ctx[k];
+            }
+            crit += b * stc - (mx + log(se));
+            grad += stc - sce / se;
+            dsec += (sc2e * se - sce * sce) / (se * se);
+        }
+        float gradf = (float)grad, dsecf = (float)dsec;
+        if (g->step <= 0.0f) {
+            dsecf = dsecf * 4;
+            if (dsecf < (float)(n / 10)) dsecf = (float)(n / 10);
+            beta += gradf / dsecf;
+        } else {
+            beta += gradf * (g->step / n);
+        }
+        conv = fabs(gradf) < (g->conv_thr * n);
+    }
+    free(ctx);
+    if (out3) { out3[0] = crit; out3[1] = grad; out3[2] = dsec; }
+    if (beta > 5.0f) return 5.0f;
+    if (beta < -5.0f) return -5.0f;
+    if (isnan(beta)) return 0.0f;
+    return beta;
+}
+
+/* ------------------------------------------------------------------ EM driver (general) */
+/* ClassifyByNemOneBeta (nem_alg.c:997-1192) for
+ *   from_partition = 0: INIT_PARAM_FILE (1151-1169): ComputePartitionFromPara(Needinit=1) from the
+ *                       all-zero classification, then NemAlgo;
+ *   from_partition = 1: INIT_FILE (1091-1113): t holds the starting classification; InitPara +
+ *                       MakeParaFromLabeled = one EstimPara of it (an empty class ends the call,
+ *                       1338-1345), whose result NemAlgo's first M-step recomputes; then NemAlgo.
+ * g != NULL: BETA_PSGRAD, beta re-estimated after every M-step (nem_alg.c:1810-1812) from the
+ * classification the M-step used, and carried on (ParaP->Beta). */
+int nemo_fit_ex(const nemo_problem *pb0, int from_partition, const nemo_psgrad *g, float *prop,
+                float *center, float *disp, float *t, int32_t *label, nemo_result *res,
+                float *beta_out)
 {
     nemo_problem pbv = *pb0; const nemo_problem *pb = &pbv;
     int n = pb->n, K = pb->k;
     size_t nk = (size_t)n * K;
-    double beta = pb->row_ptr ? (double)pb->beta : 0.0; /* nem_exe.c:570-574 */
+    float betaf = pb->row_ptr ? pb->beta : 0.0f; /* nem_exe.c:570-574 */
     double *logpf = malloc(sizeof(double) * nk);
     float *told = malloc(sizeof(float) * nk);
     double crit[6] = {0, 0, 0, 0, 0, 0};
     memset(res, 0, sizeof *res);
-    memset(t, 0, sizeof(float) * nk);              /* calloc'd ClassifM, nem_exe.c:524-526 */
-
-    nemo_logpf(pb, prop, center, disp, logpf);
-    sweep_impl(pb, logpf, 0.0, t, label, NULL, NULL);          /* blind, nem_alg.c:1970-1977 */
-    sweep_impl(pb, logpf, beta, t, label, &res->n_allnul, &res->n_ties);
-    if (pb->dolog) nemo_criteria(pb, logpf, t, beta, crit);    /* WriteLogCrit, nem_alg.c:2398 */
-
     int iter, converged = 0, status = NEMO_OK;
+
+    if (from_partition) {
+        status = nemo_mstep(pb, t, prop, center, disp, NULL, NULL);
+        if (status != NEMO_OK) {                    /* "Class %d has no labeled observation" */
+            res->status = status;
+            if (beta_out) *beta_out = betaf;
+            free(logpf); free(told);
+            return status;
+        }
+    } else {
+        memset(t, 0, sizeof(float) * nk);              /* calloc'd ClassifM, nem_exe.c:524-526 */
+        nemo_logpf(pb, prop, center, disp, logpf);
+        sweep_impl(pb, logpf, 0.0, t, label, NULL, NULL);          /* blind, nem_alg.c:1970-1977 */
+        sweep_impl(pb, logpf, (double)betaf, t, label, &res->n_allnul, &res->n_ties);
+        if (pb->dolog) nemo_criteria(pb, logpf, t, (double)betaf, crit);    /* WriteLogCrit, nem_alg.c:2398 */
+    }
+
     for (iter = 1; iter <= pb->it_max && !converged && status == NEMO_OK; iter++) {
         double oldcrit = crit[3]; /* ChosenCrit(CRIT_M), nem_alg.c:1802, nem_exe.c:346 */
         memcpy(told, t, sizeof(float) * nk);
         if (!pb->param_fixed) status = nemo_mstep(pb, t, prop, center, disp, NULL, NULL);
+        if (g) betaf = nemo_estim_beta(pb, g, t, betaf, NULL);
         if (status != NEMO_OK) continue; /* empty class: loop condition ends the run */
         nemo_logpf(pb, prop, center, disp, logpf);
-        sweep_impl(pb, logpf, beta, t, label, &res->n_allnul, &res->n_ties);
+        sweep_impl(pb, logpf, (double)betaf, t, label, &res->n_allnul, &res->n_ties);
         if (pb->conv == NEMO_CONV_CLAS) {
             converged = max_abs_diff(t, told, nk) < pb->conv_thr;
         } else if (pb->conv == NEMO_CONV_CRIT) {
-            nemo_criteria(pb, logpf, t, beta, crit);
+            nemo_criteria(pb, logpf, t, (double)betaf, crit);
             double cur = crit[3];
             float dif = cur != 0 ? (float)fabs((cur - oldcrit) / cur) : FLT_MAX;
             converged = dif < pb->conv_thr;
         } else if (pb->dolog) {
-            nemo_criteria(pb, logpf, t, beta, crit);
+            nemo_criteria(pb, logpf, t, (double)betaf, crit);
         }
     }
     iter -= 1;
@@ -397,8 +471,8 @@ int nemo_fit(const nemo_problem *pb0, float *prop, float *center, float *disp,
         nemo_mstep(pb, t, prop, center, disp, NULL, NULL);
         nemo_logpf(pb, prop, center, disp, logpf);
     }
-    nemo_criteria(pb, logpf, t, beta, crit);
-    if (label && pb->algo != NEMO_ALGO_NCEM) { /* MAP of the fuzzy result (first max) */
+    nemo_criteria(pb, logpf, t, (double)betaf, crit);
+    if (label) { /* MAP (first max); for ncem the one-hot index */
         for (int i = 0; i < n; i++) {
             int km = 0;
             for (int k = 1; k < K; k++) if (t[(size_t)i * K + k] > t[(size_t)i * K + km]) km = k;
@@ -408,6 +482,105 @@ int nemo_fit(const nemo_problem *pb0, float *prop, float *center, float *disp,
     res->status = status; res->iters = iter; res->converged = converged;
     res->U = crit[0]; res->D = crit[1]; res->L = crit[2]; res->M = crit[3];
     res->Z = crit[4]; res->G = crit[5];
+    if (beta_out) *beta_out = betaf;
     free(logpf); free(told);
     return status;
+}
+
+/* ClassifyByNemOneBeta INIT_PARAM_FILE branch (nem_alg.c:1151-1169):
+ * ComputePartitionFromPara(Needinit=1) (nem_alg.c:1951-1989) then NemAlgo (1746-1879). */
+int nemo_fit(const nemo_problem *pb0, float *prop, float *center, float *disp,
+             float *t, int32_t *label, nemo_result *res)
+{
+    return nemo_fit_ex(pb0, 0, NULL, prop, center, disp, t, label, res, NULL);
+}
+
+/* ------------------------------------------------------------------ beta heuristics */
+/* ClassifyByNemHeuBeta (nem_alg.c:731-992), BETA_HEUD (mode 0, Hathaway criterion D: stop at the
+ * first drop of its slope below -ddrop*N, else threshold its total loss) and BETA_HEUL (mode 1,
+ * mixture likelihood L: stop when it falls lloss*N under its maximum).  One complete fit per
+ * tested beta = 0, step, 2 step ... <= max, each from the all-zero classification but from the
+ * PARAMETERS THE PREVIOUS FIT LEFT (StatModelP->Para is in/out, 826-833); a fit that ends with an
+ * empty class is skipped.  Final fit at the estimated beta: from the classification saved before
+ * the drop (InitMode = INIT_FILE, 958-963), or -- D heuristic without a detected drop -- again
+ * from the all-zero classification (952-954).  Criteria compared in float like criV/slopes.
+ * trace (nullable, cap entries each): tested betas and their criterion. */
+int nemo_fit_heuristic(const nemo_problem *pb0, int mode, const nemo_heu *hp, float *prop,
+                       float *center, float *disp, float *t, int32_t *label, nemo_result *res,
+                       float *beta_est, int *n_tested, float *beta_trace, float *crit_trace,
+                       int cap)
+{
+    nemo_problem pb = *pb0;
+    int n = pb.n, K = pb.k;
+    size_t nk = (size_t)n * K;
+    int nbtamax = (int)(hp->max / hp->step) + 1;
+    float *btaV = calloc(nbtamax + 2, sizeof(float)), *criV = calloc(nbtamax + 2, sizeof(float));
+    float *best = calloc(nk, sizeof(float));
+    int nbta = 0, stop = 0, Dincreas = 0, Ddrop = 0, Lfound = 0;
+    float Dmin = 0.0f, prevSlope = NAN, thisSlope = NAN, Lmax = NAN, btaEst = NAN;
+    float DdropThres = -hp->ddrop * n, LlossThres = hp->lloss * n;
+
+    for (float bt = 0.0f; bt <= hp->max && !stop; bt += hp->step) {
+        pb.beta = bt;
+        if (nemo_fit_ex(&pb, 0, NULL, prop, center, disp, t, label, res, NULL) != NEMO_OK) continue;
+        if (nbta > nbtamax) break;                 /* cannot happen (float steps), guards the arrays */
+        nbta++;
+        btaV[nbta] = bt;
+        if (mode == 0) {
+            criV[nbta] = (float)res->D;
+            if (criV[nbta] < Dmin) Dmin = criV[nbta];
+            if (nbta >= 2) {
+                prevSlope = thisSlope;
+                thisSlope = (criV[nbta] - criV[nbta - 1]) / (btaV[nbta] - btaV[nbta - 1]);
+                if (thisSlope >= 0.5 * n) Dincreas = 1;
+            }
+            if (nbta >= 3) {
+                if (!Ddrop && !Dincreas) {
+                    if ((thisSlope - prevSlope) < DdropThres) {
+                        Ddrop = 1; stop = 1;
+                        btaEst = btaV[nbta - 1];
+                    } else
+                        memcpy(best, t, sizeof(float) * nk);
+                }
+            } else
+                memcpy(best, t, sizeof(float) * nk);
+        } else {
+            criV[nbta] = (float)res->L;
+            if (nbta < 2) {
+                Lmax = criV[nbta];
+                memcpy(best, t, sizeof(float) * nk);
+            } else {
+                if (criV[nbta] > Lmax) Lmax = criV[nbta];
+                if (!Lfound) {
+                    if (criV[nbta] < Lmax - LlossThres) {
+                        Lfound = 1; stop = 1;
+                        btaEst = btaV[nbta - 1];
+                    } else
+                        memcpy(best, t, sizeof(float) * nk);
+                }
+            }
+        }
+    }
+    int from_partition;
+    if (mode == 0 && !Ddrop) {
+        float DThres = criV[1] - (criV[1] - Dmin) * hp->dloss;
+        int ibta, found = 0;
+        for (ibta = 1; ibta <= nbta && !found; ibta++) found = criV[ibta] <= DThres;
+        btaEst = found ? btaV[ibta - 2] : 0.0f;    /* "heuristic failed to detect beta" */
+        from_partition = 0;
+    } else {
+        memcpy(t, best, sizeof(float) * nk);
+        from_partition = 1;
+    }
+    if (mode == 1 && !Lfound) btaEst = btaV[nbta];
+    if (n_tested) *n_tested = nbta;
+    for (int i = 0; i < nbta && i < cap; i++) {
+        if (beta_trace) beta_trace[i] = btaV[i + 1];
+        if (crit_trace) crit_trace[i] = criV[i + 1];
+    }
+    if (beta_est) *beta_est = btaEst;
+    pb.beta = btaEst;
+    int rc = nemo_fit_ex(&pb, from_partition, NULL, prop, center, disp, t, label, res, NULL);
+    free(btaV); free(criV); free(best);
+    return rc;
 }

@@ -44,6 +44,21 @@ typedef struct {
 int nemo_fit(const nemo_problem *pb, float *prop, float *center, float *disp,
              float *t, int32_t *label, nemo_result *res);
 
+/* beta estimation (reachable in the reference through the CLI only) */
+typedef struct { int n_iter; float conv_thr, step; } nemo_psgrad;     /* BtaPsGradT, nem_typ.h:300-308 */
+typedef struct { float step, max, ddrop, dloss, lloss; } nemo_heu;    /* nem_typ.h:319-323 */
+float nemo_estim_beta(const nemo_problem *pb, const nemo_psgrad *g, const float *t, float beta,
+                      double *out3 /*crit grad dsec, nullable*/);
+/* from_partition: t holds the starting classification (INIT_FILE); g != NULL: BETA_PSGRAD */
+int nemo_fit_ex(const nemo_problem *pb, int from_partition, const nemo_psgrad *g, float *prop,
+                float *center, float *disp, float *t, int32_t *label, nemo_result *res,
+                float *beta_out);
+/* mode 0 = heu_d, 1 = heu_l (ClassifyByNemHeuBeta, nem_alg.c:731-992) */
+int nemo_fit_heuristic(const nemo_problem *pb, int mode, const nemo_heu *hp, float *prop,
+                       float *center, float *disp, float *t, int32_t *label, nemo_result *res,
+                       float *beta_est, int *n_tested, float *beta_trace, float *crit_trace,
+                       int cap);
+
 /* Stage functions (same arithmetic as nemo_fit uses), for per-kernel parity tests. */
 void nemo_pack(const uint8_t *x, int n, int d, int words_per_row, uint32_t *out);
 void nemo_hamming(const nemo_problem *pb, const float *center, const float *disp,

@@ -152,6 +152,67 @@ class Problem:
                    dict(U=r.U, D=r.D, L=r.L, M=r.M, Z=r.Z, G=r.G), r.n_allnul, r.n_ties)
 
 
+    # -- beta estimation ------------------------------------------------------
+    def estim_beta(self, t, beta, n_iter=1, conv_thr=0.001, step=0.0):
+        """EstimBeta BETA_PSGRAD (nem_alg.c:2120-2230) -> (new beta, dict(crit, grad, dsec))."""
+        g = _PsGrad(int(n_iter), float(conv_thr), float(step))
+        t = _f32(t)
+        out = np.zeros(3, dtype=np.float64)
+        f = lib().nemo_estim_beta
+        f.restype = C.c_float
+        b = f(C.byref(self.c), C.byref(g), _p(t), C.c_float(float(beta)), _p(out))
+        return float(b), dict(zip(("crit", "grad", "dsec"), out))
+
+    def fit_ex(self, prop, center, disp, t_init=None, psgrad=None) -> Fit:
+        """nemo_fit_ex: optional starting classification (INIT_FILE) and psgrad=(nit, conv, step)."""
+        prop, center, disp = _f32(prop).copy(), _f32(center).copy(), _f32(disp).copy()
+        t = np.zeros((self.n, self.k), dtype=np.float32) if t_init is None else _f32(t_init).copy()
+        label = np.zeros(self.n, dtype=np.int32)
+        r = _Result()
+        g = None if psgrad is None else _PsGrad(int(psgrad[0]), float(psgrad[1]), float(psgrad[2]))
+        bo = C.c_float(0.0)
+        lib().nemo_fit_ex(C.byref(self.c), int(t_init is not None),
+                          None if g is None else C.byref(g), _p(prop), _p(center), _p(disp),
+                          _p(t), _p(label), C.byref(r), C.byref(bo))
+        f = Fit(r.status, r.iters, bool(r.converged), t, label, prop,
+                center.reshape(self.k, self.d), disp.reshape(self.k, self.d),
+                dict(U=r.U, D=r.D, L=r.L, M=r.M, Z=r.Z, G=r.G), r.n_allnul, r.n_ties)
+        f.beta = float(bo.value)
+        return f
+
+    def fit_heuristic(self, prop, center, disp, mode="heu_d", step=0.1, bmax=2.0, ddrop=0.8,
+                      dloss=0.5, lloss=0.02) -> Fit:
+        """ClassifyByNemHeuBeta (nem_alg.c:731-992); Fit gains beta, beta_tested, crit_tested."""
+        prop, center, disp = _f32(prop).copy(), _f32(center).copy(), _f32(disp).copy()
+        t = np.zeros((self.n, self.k), dtype=np.float32)
+        label = np.zeros(self.n, dtype=np.int32)
+        r = _Result()
+        hp = _Heu(float(step), float(bmax), float(ddrop), float(dloss), float(lloss))
+        cap = int(bmax / step) + 3
+        bt = np.zeros(cap, dtype=np.float32)
+        ct = np.zeros(cap, dtype=np.float32)
+        be, nt = C.c_float(0.0), C.c_int(0)
+        lib().nemo_fit_heuristic(C.byref(self.c), {"heu_d": 0, "heu_l": 1}[mode], C.byref(hp),
+                                 _p(prop), _p(center), _p(disp), _p(t), _p(label), C.byref(r),
+                                 C.byref(be), C.byref(nt), _p(bt), _p(ct), cap)
+        f = Fit(r.status, r.iters, bool(r.converged), t, label, prop,
+                center.reshape(self.k, self.d), disp.reshape(self.k, self.d),
+                dict(U=r.U, D=r.D, L=r.L, M=r.M, Z=r.Z, G=r.G), r.n_allnul, r.n_ties)
+        f.beta = float(be.value)
+        f.beta_tested = bt[:nt.value].copy()
+        f.crit_tested = ct[:nt.value].copy()
+        return f
+
+
+class _PsGrad(C.Structure):
+    _fields_ = [("n_iter", C.c_int), ("conv_thr", C.c_float), ("step", C.c_float)]
+
+
+class _Heu(C.Structure):
+    _fields_ = [("step", C.c_float), ("max", C.c_float), ("ddrop", C.c_float),
+                ("dloss", C.c_float), ("lloss", C.c_float)]
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
@@ -195,10 +256,15 @@ def run_ref_cli(base, k=3, algo="ncem", beta=0.5, conv="clas", thr=1e-8, fmt="fu
 
 def run_ref_harness(base, out_prefix, k=3, algo="ncem", beta=0.5, conv="clas", thr=1e-8,
                     it_max=100, family="bern", prop="pk", disp="sk_", init=2, update="seq",
-                    tie="first", seed=42, timeout=3600):
-    """ClassifyByNem with the hidden knobs; returns dict(cm, prop, center, disp, crit, iters)."""
+                    tie="first", seed=42, timeout=3600, beta_mode="fix", beta_params=()):
+    """ClassifyByNem with the hidden knobs; returns dict(cm, prop, center, disp, crit, iters).
+    beta_mode fix|psgrad|heu_d|heu_l with beta_params (nit, conv, step) or (bstep, bmax, ddrop,
+    dloss, lloss) -- the CLI's -B/-G/-H (nem_hlp.c:220-245)."""
     args = [REF_HARNESS, base, str(k), algo, repr(float(beta)), conv, repr(float(thr)),
             str(it_max), family, prop, disp, str(init), update, tie, str(seed), out_prefix]
+    if beta_mode != "fix":
+        args += [beta_mode] + [repr(float(v)) if not isinstance(v, int) else str(v)
+                               for v in beta_params]
     subprocess.run(args, check=True, timeout=timeout, capture_output=True)
     with open(base + ".str") as f:
         _, n, d = f.read().split()[:3]
@@ -207,10 +273,12 @@ def run_ref_harness(base, out_prefix, k=3, algo="ncem", beta=0.5, conv="clas", t
     par = np.fromfile(out_prefix + ".par.f32", dtype=np.float32)
     vals = open(out_prefix + ".txt").read().split()
     txt = open(out_prefix + ".stderr").read()
-    m = re.search(r"NEM (converged|did not converge) after (\d+) iterations", txt)
+    m = re.findall(r"NEM (converged|did not converge) after (\d+) iterations", txt)
     return dict(cm=cm, prop=par[:k], center=par[k:k + k * d].reshape(k, d),
                 disp=par[k + k * d:].reshape(k, d), status=int(vals[0]),
-                crit=dict(zip("UDLMZG", [float(v) for v in vals[1:]])),
-                iters=int(m.group(2)) if m else None,
-                converged=(m.group(1) == "converged") if m else None,
+                crit=dict(zip("UDLMZG", [float(v) for v in vals[1:7]])),
+                beta=float(vals[7]) if len(vals) > 7 else None,
+                beta_tested=[float(v) for v in re.findall(r"Testing beta = +([-0-9.]+)", txt)],
+                iters=int(m[-1][1]) if m else None,
+                converged=(m[-1][0] == "converged") if m else None,
                 density_zero=("density = 0" in txt))

@@ -17,9 +17,13 @@
  *
  * usage: nem_ref_harness base K algo beta conv thr itmax family prop disp init
  *                        update(seq|para) tie(random|first) seed out_prefix
+ *                        [betamode(fix|psgrad|heu_d|heu_l)  [p1 p2 p3 p4 p5]]
+ *        betamode (StatModelT.Spec.BetaModel, nem_typ.h:128-135; the CLI's -B, nem_hlp.c:220-225)
+ *        with psgrad: p1..p3 = nit conv step (-G, BtaPsGradT nem_typ.h:300-308)
+ *        with heu_*:  p1..p5 = bstep bmax ddrop dloss lloss (-H, nem_typ.h:319-323)
  * writes out_prefix.cm.f32   raw float32 ClassifM [N*K]
  *        out_prefix.par.f32  raw float32: Prop_K[K] Center_KD[K*D] Disp_KD[K*D]
- *        out_prefix.txt      "status iterations? U D L M Z G"
+ *        out_prefix.txt      "status U D L M Z G beta"   (beta = StatModelT.Para.Beta on return)
  */
 #include "nem_typ.h"
 #include "nem_alg.h"
@@ -89,6 +93,18 @@ int main(int argc, char **argv)
     P.MissMode = DEFAULT_MISSING; P.ParamFileMode = NO_PARAM_FILE;
     P.SortedVar = DEFAULT_SORTEDVAR; P.NeighSpec = NEIGH_FILE;
     P.VisitOrder = ORDER_DIRECT; P.Debug = FALSE;
+    if (argc > 16) {
+        M.Spec.BetaModel = find(argv[16], BtaStrVC, BETA_NB);
+        if (M.Spec.BetaModel == BETA_PSGRAD && argc > 19) {
+            P.BtaPsGrad.NbIter = atoi(argv[17]); P.BtaPsGrad.ConvThres = (float)atof(argv[18]);
+            P.BtaPsGrad.Step = (float)atof(argv[19]);
+        }
+        if ((M.Spec.BetaModel == BETA_HEUD || M.Spec.BetaModel == BETA_HEUL) && argc > 21) {
+            P.BtaHeuStep = (float)atof(argv[17]); P.BtaHeuMax = (float)atof(argv[18]);
+            P.BtaHeuDDrop = (float)atof(argv[19]); P.BtaHeuDLoss = (float)atof(argv[20]);
+            P.BtaHeuLLoss = (float)atof(argv[21]);
+        }
+    }
 
     /* .str : "S|N  N  D" */
     int N, D; char type[64];
@@ -187,7 +203,8 @@ int main(int argc, char **argv)
     fclose(f);
     snprintf(name, sizeof name, "%s.txt", outp);
     f = fopen(name, "w");
-    fprintf(f, "%d %.9g %.9g %.9g %.9g %.9g %.9g\n", sts, C.U, C.D, C.L, C.M, C.Z, C.G);
+    fprintf(f, "%d %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", sts, C.U, C.D, C.L, C.M, C.Z, C.G,
+            M.Para.Beta);
     fclose(f);
     fclose(out_stderr);
     return 0;

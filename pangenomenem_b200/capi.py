@@ -32,7 +32,8 @@ class Options(C.Structure):
                 ("prop", C.c_int32), ("disp", C.c_int32), ("it_max", C.c_int32),
                 ("param_fixed", C.c_int32), ("dolog", C.c_int32), ("sweep_impl", C.c_int32),
                 ("profile", C.c_int32), ("beta", C.c_float), ("conv_thr", C.c_float),
-                ("reserved", C.c_int32 * 8)]
+                ("beta_mode", C.c_int32), ("grad_n_iter", C.c_int32), ("grad_conv", C.c_float),
+                ("grad_step", C.c_float), ("reserved", C.c_int32 * 4)]
 
 
 class Result(C.Structure):
@@ -48,7 +49,8 @@ class Result(C.Structure):
                 ("n_criteria", C.c_int32), ("best_start", C.c_int32), ("n_success", C.c_int32),
                 ("ms_density_cached", C.c_float), ("ms_mstep_delta", C.c_float),
                 ("n_density_cached", C.c_int32), ("n_mstep_delta", C.c_int32),
-                ("exchanges", C.c_int64), ("n_kept", C.c_int64)]
+                ("exchanges", C.c_int64), ("n_kept", C.c_int64),
+                ("beta", C.c_float), ("n_beta_tested", C.c_int32)]
 
 
 class BatchStats(C.Structure):
@@ -70,7 +72,16 @@ def pack_mask(mask, d: int) -> np.ndarray:
 
 class Extra(C.Structure):
     _fields_ = [("update", C.c_int32), ("sweep_impl", C.c_int32), ("device", C.c_int32),
-                ("n_random_inits", C.c_int32), ("seed", C.c_int64), ("reserved", C.c_int32 * 8)]
+                ("n_random_inits", C.c_int32), ("seed", C.c_int64),
+                ("beta_mode", C.c_int32), ("grad_n_iter", C.c_int32), ("grad_conv", C.c_float),
+                ("grad_step", C.c_float), ("heu_step", C.c_float), ("heu_max", C.c_float),
+                ("heu_ddrop", C.c_float), ("heu_dloss", C.c_float), ("heu_lloss", C.c_float),
+                ("reserved", C.c_int32 * 7)]
+
+
+class BetaHeuristic(C.Structure):
+    _fields_ = [("step", C.c_float), ("max", C.c_float), ("ddrop", C.c_float),
+                ("dloss", C.c_float), ("lloss", C.c_float)]
 
 
 class Comm(C.Structure):
@@ -130,10 +141,15 @@ def _f32(a):
 
 def make_options(k=3, algo="ncem", update="seq", conv="clas", conv_thr=1e-8, prop="pk",
                  disp="sk_", it_max=100, beta=0.5, param_fixed=False, dolog=False,
-                 sweep_impl="auto", profile=False) -> Options:
-    return Options(k, ALGO[algo], UPDATE[update], CONV[conv], PROP[prop], DISP[disp], int(it_max),
-                   int(param_fixed), int(dolog), SWEEP[sweep_impl], int(profile), float(beta),
-                   float(conv_thr))
+                 sweep_impl="auto", profile=False, psgrad=None) -> Options:
+    """psgrad = (n_iter, conv, step): beta re-estimated after every M-step (BETA_PSGRAD)."""
+    o = Options(k, ALGO[algo], UPDATE[update], CONV[conv], PROP[prop], DISP[disp], int(it_max),
+                int(param_fixed), int(dolog), SWEEP[sweep_impl], int(profile), float(beta),
+                float(conv_thr))
+    if psgrad is not None:
+        o.beta_mode, o.grad_n_iter = 1, int(psgrad[0])
+        o.grad_conv, o.grad_step = float(psgrad[1]), float(psgrad[2])
+    return o
 
 
 @dataclass
@@ -157,6 +173,10 @@ class Fit:
     n_kept: int = 0
     best_start: int = 0
     n_success: int = 0
+    beta: float = 0.0
+    n_beta_tested: int = 0
+    beta_tested: np.ndarray | None = None
+    crit_tested: np.ndarray | None = None
 
 
 class Engine:
@@ -282,12 +302,34 @@ class Engine:
                                                _p(_f32(disp_sample)), _p(prop), _p(center), _p(disp)))
         return prop, center, disp
 
-    def fit(self, prop0, center0, disp0, n_random_starts=0, seed=42, random_workers=0, **kw) -> Fit:
-        """theta0 = (prop0[K], center0[K,D], disp0[K,D]); kw = make_options() fields."""
+    def fit(self, prop0, center0, disp0, n_random_starts=0, seed=42, random_workers=0,
+            t_init=None, heuristic=None, **kw) -> Fit:
+        """theta0 = (prop0[K], center0[K,D], disp0[K,D]); kw = make_options() fields.
+        t_init[N,K]: start from this classification (nemb_fit_from_partition, theta0 ignored).
+        heuristic = dict(mode="heu_d"|"heu_l", step=, max=, ddrop=, dloss=, lloss=): estimate beta
+        with nemb_fit_beta_heuristic."""
         o = make_options(**kw)
         prop, center, disp = _f32(prop0).copy(), _f32(center0).copy(), _f32(disp0).copy()
         r = Result()
-        if n_random_starts and random_workers:
+        bt = ct = None
+        if heuristic is not None:
+            hz = dict(heuristic)
+            mode = {"heu_d": 2, "heu_l": 3}[hz.pop("mode", "heu_d")]
+            hp = BetaHeuristic(float(hz.get("step", 0)), float(hz.get("max", 0)),
+                               float(hz.get("ddrop", 0)), float(hz.get("dloss", 0)),
+                               float(hz.get("lloss", 0)))
+            cap = int((hp.max or 2.0) / (hp.step or 0.1)) + 3
+            bt = np.zeros(cap, dtype=np.float32)
+            ct = np.zeros(cap, dtype=np.float32)
+            rc = self.lib.nemb_fit_beta_heuristic(self.h, C.byref(o), mode, C.byref(hp), _p(prop),
+                                                  _p(center), _p(disp), C.byref(r), _p(bt), _p(ct),
+                                                  cap)
+        elif t_init is not None:
+            t0 = _f32(t_init)
+            assert t0.shape == (self.n, o.k)
+            rc = self.lib.nemb_fit_from_partition(self.h, C.byref(o), _p(t0), _p(prop), _p(center),
+                                                  _p(disp), C.byref(r))
+        elif n_random_starts and random_workers:
             rc = self.lib.nemb_fit_random_workers(self.h, C.byref(o), int(n_random_starts), C.c_int64(seed),
                                                   int(random_workers), _p(prop), _p(center), _p(disp),
                                                   C.byref(r))
@@ -307,7 +349,18 @@ class Engine:
                    dict(density=r.n_density, sweep=r.n_sweep, mstep=r.n_mstep,
                         criteria=r.n_criteria, density_cached=r.n_density_cached,
                         mstep_delta=r.n_mstep_delta), r.empty_class, r.exchanges, r.n_kept, r.best_start,
-                   r.n_success)
+                   r.n_success, r.beta, r.n_beta_tested,
+                   None if bt is None else bt[:min(r.n_beta_tested, bt.shape[0])].copy(),
+                   None if ct is None else ct[:min(r.n_beta_tested, ct.shape[0])].copy())
+
+    def estim_beta(self, t, beta, **kw):
+        """EstimBeta on the classification t[N,K] -> (new beta, dict(crit, grad, dsec))."""
+        o = make_options(**kw)
+        t = _f32(t)
+        b = C.c_float(float(beta))
+        out = np.zeros(3, dtype=np.float64)
+        self._check(self.lib.nemb_stage_estim_beta(self.h, C.byref(o), _p(t), C.byref(b), _p(out)))
+        return float(b.value), dict(zip(("crit", "grad", "dsec"), out))
 
     def posteriors(self, k=None):
         k = k or self.k
@@ -501,10 +554,15 @@ def nem(Fname, nk, algo, beta, convergence, convergence_th, format, it_max, dolo
 
 def nem_ex(Fname, nk, algo, beta, convergence, convergence_th, format, it_max, dolog, model_family,
            proportion, dispersion, init_mode, update="seq", sweep_impl="auto", device=-1,
-           n_random_inits=0, seed=0) -> int:
+           n_random_inits=0, seed=0, beta_mode="fix", psgrad=(0, 0.0, 0.0),
+           heuristic=(0.0, 0.0, 0.0, 0.0, 0.0)) -> int:
+    """nem_b200_ex: nem() plus the knobs the reference's CLI has (-U, -S, -B fix|psgrad|heu_d|heu_l,
+    -G nit conv step, -H bstep bmax ddrop dloss lloss; zeros = the reference's defaults)."""
     def b(v):
         return v if isinstance(v, bytes) else str(v).encode()
-    ex = Extra(UPDATE[update], SWEEP[sweep_impl], int(device), int(n_random_inits), int(seed))
+    ex = Extra(UPDATE[update], SWEEP[sweep_impl], int(device), int(n_random_inits), int(seed),
+               {"fix": 0, "psgrad": 1, "heu_d": 2, "heu_l": 3}[beta_mode], int(psgrad[0]),
+               float(psgrad[1]), float(psgrad[2]), *[float(v) for v in heuristic])
     return load_library().nem_b200_ex(b(Fname), int(nk), b(algo), float(beta), b(convergence),
                                       float(convergence_th), b(format), int(it_max),
                                       int(bool(dolog)), b(model_family), b(proportion),

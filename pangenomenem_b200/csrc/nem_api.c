@@ -179,6 +179,15 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
                       "(1 = random starts, 2 = parameter file)\n", init_mode);
         bad = 1;
     }
+    if (ex.beta_mode < NEMB_BETA_FIX || ex.beta_mode > NEMB_BETA_HEUL) {
+        fprintf(ferr, " Unknown beta estimation mode %d\n", ex.beta_mode); bad = 1;
+    } else if (ex.beta_mode >= NEMB_BETA_HEUD && init_mode != 2) {
+        fprintf(ferr, " The beta heuristics need the parameter file initialisation (init_mode 2) in the B200 engine\n");
+        bad = 1;
+    } else if (ex.beta_mode != NEMB_BETA_FIX && init_mode != 2) {
+        fprintf(ferr, " Beta estimation needs the parameter file initialisation (init_mode 2) in the B200 engine\n");
+        bad = 1;
+    }
     if (bad) return finish(ferr, own_err, EXIT_E_ARGS_);
 
     /* ---- files */
@@ -254,6 +263,11 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
     o.k = nk; o.algo = a; o.update = ex.update; o.conv = cv; o.prop = pr; o.disp = di;
     o.it_max = it_max; o.param_fixed = (init_mode == 2 && flag == 2); o.dolog = dolog != 0;
     o.sweep_impl = ex.sweep_impl; o.beta = beta; o.conv_thr = convergence_th;
+    const int beta_mode = type == 'S' ? ex.beta_mode : NEMB_BETA_FIX;
+    if (beta_mode == NEMB_BETA_PSGRAD) {
+        o.beta_mode = NEMB_BETA_PSGRAD; o.grad_n_iter = ex.grad_n_iter;
+        o.grad_conv = ex.grad_conv; o.grad_step = ex.grad_step;
+    }
     nemb_result res;
     L.ferr = ferr; L.k = nk; L.d = d; L.n = n; L.beta = beta_eff;
     if (dolog) {                                                /* StartLogFile, nem_alg.c:1478-1498 */
@@ -271,7 +285,22 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
         fprintf(ferr, "Initializing parameters from given value\n");
         if (L.flog) fprintf(L.flog, "Initializing parameters from given value :\n");
         fprintf(ferr, "  Iterations : %4d ", 0);
-        rc = nemb_fit_logged(h, &o, prop, center, disp, &res, dolog ? log_iteration : NULL, &L);
+        if (beta_mode >= NEMB_BETA_HEUD) {
+            /* ClassifyByNemHeuBeta (nem_alg.c:731-992); the .log keeps the header only (the
+             * reference rewrites it for every tested beta, 1014-1023) */
+            nemb_beta_heuristic hp = {ex.heu_step, ex.heu_max, ex.heu_ddrop, ex.heu_dloss, ex.heu_lloss};
+            float bt[64], ct[64];
+            fprintf(ferr, "\n* * Starting heuristic * *\n");
+            rc = nemb_fit_beta_heuristic(h, &o, beta_mode, &hp, prop, center, disp, &res, bt, ct, 64);
+            if (rc == NEMB_OK || rc == NEMB_W_EMPTYCLASS) {
+                for (int i = 0; i < res.n_beta_tested && i < 64; i++)
+                    fprintf(ferr, " * * Tested beta = %5.2f : %s = %10.1f * *\n", (double)bt[i],
+                            beta_mode == NEMB_BETA_HEUD ? "D" : "L", (double)ct[i]);
+                fprintf(ferr, "\n * * *  Estimated beta : %3.2f * * *\n", (double)res.beta);
+            }
+        } else
+            rc = nemb_fit_logged(h, &o, prop, center, disp, &res, dolog ? log_iteration : NULL, &L);
+        if (rc == NEMB_OK || rc == NEMB_W_EMPTYCLASS) beta_eff = res.beta;
     } else {
         fprintf(ferr, "Random initial partitions (%d starts)\n", ex.n_random_inits ? ex.n_random_inits : 50);
         rc = nemb_fit_random(h, &o, ex.n_random_inits, ex.seed, prop, center, disp, &res);
@@ -310,7 +339,7 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
     if (rc != NEMB_OK) { code = map_status(rc); goto done; }
     snprintf(path, sizeof path, "%s.mf", Fname);
     double crit4[4] = {res.U, res.D, res.L, res.M};
-    if ((rc = nemio_write_mf(path, ferr, nk, d, crit4, beta_eff, prop, center, disp)) != NEMB_OK) {
+    if ((rc = nemio_write_mf_mode(path, ferr, nk, d, crit4, beta_eff, beta_mode, prop, center, disp)) != NEMB_OK) {
         code = map_status(rc); goto done;
     }
     fprintf(ferr, "NEM completed, classification in %s\n", outname);

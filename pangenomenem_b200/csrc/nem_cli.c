@@ -6,8 +6,10 @@
  * Supported: -a {nem ncem}  -b beta  -c {none clas crit} [thr]  -f {hard fuzzy}  -i itmax
  *            -l {y n}  -m bern {p_ pk} {s__ sk_ s_d skd}  -s m <ignored file, uses file.m> | -s r <n>
  *            -t first  -U {seq para}  -S seed  -W {auto level spec}  -g device
- * Anything else of the 1.08 syntax (gem, norm/lapl, beta estimation, image data, -o) is off the
- * PPanGGOLiN path and is rejected.
+ *            -B {fix psgrad heu_d heu_l}  -G nit conv step rand  -H bstep bmax ddrop dloss lloss
+ *            (beta estimation, nem_hlp.c:220-245; `rand` must be 0)
+ * Anything else of the 1.08 syntax (gem, norm/lapl, image data, -o) is off the PPanGGOLiN path
+ * and is rejected.
  */
 #include "nem_b200.h"
 
@@ -21,6 +23,7 @@ static int usage(const char *argv0)
             "usage: %s file K [-a nem|ncem] [-b beta] [-c none|clas|crit thr] [-f hard|fuzzy]\n"
             "          [-i itmax] [-l y|n] [-m bern p_|pk s__|sk_|s_d|skd] [-s m file | -s r n]\n"
             "          [-t first] [-U seq|para] [-S seed] [-W auto|level|spec] [-g device]\n"
+            "          [-B fix|psgrad|heu_d|heu_l] [-G nit conv step 0] [-H bstep bmax ddrop dloss lloss]\n"
             "%s\n", argv0, nemb_version());
     return 2;
 }
@@ -57,6 +60,19 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-S")) ex.seed = atoll(ARG());
         else if (!strcmp(a, "-W")) { const char *w = ARG(); ex.sweep_impl = !strcmp(w, "level") ? 1 : !strcmp(w, "spec") ? 2 : 0; }
         else if (!strcmp(a, "-g")) ex.device = atoi(ARG());
+        else if (!strcmp(a, "-B")) {
+            const char *b = ARG();
+            ex.beta_mode = !strcmp(b, "fix") ? 0 : !strcmp(b, "psgrad") ? 1 : !strcmp(b, "heu_d") ? 2 : !strcmp(b, "heu_l") ? 3 : -1;
+            if (ex.beta_mode < 0) { fprintf(stderr, "unknown beta estimation mode %s\n", b); return 2; }
+        }
+        else if (!strcmp(a, "-G")) {
+            ex.grad_n_iter = atoi(ARG()); ex.grad_conv = (float)atof(ARG()); ex.grad_step = (float)atof(ARG());
+            if (atoi(ARG()) != 0) { fprintf(stderr, "-G ... rand: a random initial beta is not available\n"); return 2; }
+        }
+        else if (!strcmp(a, "-H")) {
+            ex.heu_step = (float)atof(ARG()); ex.heu_max = (float)atof(ARG()); ex.heu_ddrop = (float)atof(ARG());
+            ex.heu_dloss = (float)atof(ARG()); ex.heu_lloss = (float)atof(ARG());
+        }
         else if (!strcmp(a, "-v")) { printf("%s\n", nemb_version()); return 0; }
         else { fprintf(stderr, "option %s is not available in the B200 engine\n", a); return usage(argv[0]); }
 #undef ARG

@@ -247,6 +247,12 @@ int  nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, nemk_lpsrc
                            double *partials, int nblocks);
 void nemk_criteria_final(nemk_stream s, int nblocks_total, const double *partials, double beta,
                          double *crit6);
+/* EstimBeta (nem_alg.c:2120-2230): same walk, partial rows = (crit, grad, dsec, 0); finish with
+ * nemk_criteria_final(beta = NaN) which then stores the raw sums in crit6[0..3] */
+int  nemk_betagrad_partial(nemk_stream s, int k, int row0, int n_loc, const int32_t *row_ptr,
+                           const int32_t *col, const float *wgt, double beta, const uint8_t *lab,
+                           const float *t, const int32_t *heavy, int n_heavy, double *partials,
+                           int nblocks);
 
 /* ---- row-sharded sweep, sparse label exchange (nem_kernels.cu "SPARSE label exchange"): a block is
  * 2 + 2*cap int32 words; blocks = the all-gathered [world] blocks.  After nemk_delta_apply

@@ -1041,6 +1041,52 @@ static int run_criteria(nemb_handle *h, const nemb_options *o, double beta, doub
     return NEMB_OK;
 }
 
+/* EstimBeta, BETA_PSGRAD (nem_alg.c:2120-2230): gradient ascent on the log pseudo-likelihood of
+ * the current classification (the one the M-step just used).  The site sums run on the device
+ * (float64, fixed two-stage order: the criteria kernel's walk); beta and its update are float on
+ * the host like *BetaP.  One stream synchronisation per gradient iteration: this mode is off the
+ * PPanGGOLiN path (the reference reaches it through its CLI only, nem_hlp.c:220-236). */
+static int run_estim_beta(nemb_handle *h, const nemb_options *o, float *beta_io, double *sums3)
+{
+    int rc;
+    if (!h->spatial) return NEMB_OK;                    /* TYPE_NONSPATIAL: nem_alg.c:2150-2151 */
+    int nit = o->grad_n_iter > 0 ? o->grad_n_iter : 1;                 /* nem_typ.h:76 */
+    float cvt = o->grad_conv > 0.f ? o->grad_conv : 0.001f;            /* nem_typ.h:77 */
+    float beta = *beta_io;
+    int npt = h->n_glob, conv = 0;
+    size_t mine = (size_t)h->rank * h->crit_blocks * 4;
+    double sums[4] = {0, 0, 0, 0};
+    for (int it = 0; it < nit && !conv; it++) {
+        nemk_betagrad_partial(h->stream, o->k, h->row0, h->n, h->d_row_ptr, h->d_col, h->d_wgt,
+                              (double)beta, h->state_labels ? h->d_lab[h->cur] : NULL,
+                              h->state_labels ? NULL : h->d_t[h->cur], h->d_heavy, h->n_heavy,
+                              h->d_crit_partials + mine, h->crit_blocks);
+        if (h->world > 1 && (rc = gather(h, h->d_crit_partials + mine, h->d_crit_partials,
+                                         sizeof(double) * 4 * h->crit_blocks)) != NEMB_OK) return rc;
+        nemk_criteria_final(h->stream, h->crit_blocks * h->world, h->d_crit_partials, (double)NAN,
+                            h->d_status->crit_before);
+        h->launches += 2;
+        CKK();
+        CK(cudaMemcpyAsync(sums, h->d_status->crit_before, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float grad = (float)sums[1], dsec = (float)sums[2];
+        if (o->grad_step <= 0.0f) {                     /* nem_alg.c:2194-2200 */
+            dsec = dsec * 4;
+            if (dsec < (float)(npt / 10)) dsec = (float)(npt / 10);
+            beta += grad / dsec;
+        } else {
+            beta += grad * (o->grad_step / npt);
+        }
+        conv = fabsf(grad) < (cvt * npt);
+    }
+    if (sums3) { sums3[0] = sums[0]; sums3[1] = sums[1]; sums3[2] = sums[2]; }
+    if (beta > 5.0f) beta = 5.0f;                       /* MAX_BETA / MIN_BETA, nem_alg.c:84-85 */
+    else if (beta < -5.0f) beta = -5.0f;
+    else if (isnan(beta)) beta = 0.0f;
+    *beta_io = beta;
+    return NEMB_OK;
+}
+
 static int check_options(nemb_handle *h, const nemb_options *o)
 {
     if (!h->loaded) return fail(h, NEMB_E_ARG, "no pangenome loaded");
@@ -1051,6 +1097,8 @@ static int check_options(nemb_handle *h, const nemb_options *o)
     if (o->conv != NEMB_CONV_NONE && !(o->conv_thr > 0)) return fail(h, NEMB_E_ARG, "conv threshold must be > 0");
     if (o->prop < 0 || o->prop > 1 || o->disp < 0 || o->disp > 3) return fail(h, NEMB_E_ARG, "bad model");
     if (o->it_max < 0) return fail(h, NEMB_E_ARG, "it_max must be >= 0");
+    if (o->beta_mode != NEMB_BETA_FIX && o->beta_mode != NEMB_BETA_PSGRAD)
+        return fail(h, NEMB_E_ARG, "beta_mode %d: the heuristics are nemb_fit_beta_heuristic()", o->beta_mode);
     if (h->world > 1 && h->spatial && o->update == NEMB_UPDATE_SEQ) {
         if (o->algo == NEMB_ALGO_NEM)
             return fail(h, NEMB_E_ARG, "row shards: the sequential fuzzy sweep is single-GPU only (use update=para)");
@@ -1082,11 +1130,19 @@ static int init_state(nemb_handle *h, const nemb_options *o)
 }
 
 /* EM from the theta already resident on the device (d_prop/d_center/d_disp). */
+static int upload_state(nemb_handle *h, const nemb_options *o, const float *t);
+
+/* t_init != NULL: INIT_FILE (nem_alg.c:1091-1113) -- NemAlgo starts from that classification, the
+ * two initial sweeps are not run and theta comes from the first M-step. */
 static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_result *res,
-                   nemb_iter_cb cb, void *user, float *prop, float *center, float *disp)
+                   nemb_iter_cb cb, void *user, float *prop, float *center, float *disp,
+                   const float *t_init)
 {
-    int k = o->k, rc, flipped;
-    double beta = h->spatial ? (double)o->beta : 0.0;   /* nem_exe.c:570-574 */
+    int k = o->k, rc, flipped = 0;
+    float betaf = h->spatial ? o->beta : 0.0f;          /* nem_exe.c:570-574 */
+    double beta = (double)betaf;
+    double swept_beta = NAN;                            /* beta of the previous sweep */
+    const int psgrad = o->beta_mode == NEMB_BETA_PSGRAD && h->spatial;
     int uniform_m = o->param_fixed ? uniform0 : (o->disp == NEMB_DISP_K_ || o->disp == NEMB_DISP___);   /* 1: theta lives on the device */
     int want_crit_each = o->dolog || o->conv == NEMB_CONV_CRIT;
     int lean = o->algo == NEMB_ALGO_NCEM && !getenv("NEM_B200_KEEP_LOGPF");
@@ -1094,6 +1150,9 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     float *nk_host = cb ? malloc(sizeof(float) * k) : NULL;
 
     if ((rc = init_state(h, o)) != NEMB_OK) return rc;
+    if (t_init) {
+        if ((rc = upload_state(h, o, t_init)) != NEMB_OK) return rc;
+    } else {
     if ((rc = run_tables(h, k, 0)) != NEMB_OK) return rc;
     if ((rc = run_density(h, k, uniform0, NULL, lean)) != NEMB_OK) return rc;
     /* ComputePartitionFromPara(Needinit=1): blind sweep then beta sweep (nem_alg.c:1970-1981) */
@@ -1101,8 +1160,10 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
     if ((rc = run_sweep(h, o, beta, &flipped, NULL, NULL)) != NEMB_OK) return rc;
     if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
+    swept_beta = beta;
+    }
     double oldcrit = 0.0;
-    if (o->dolog || cb || o->it_max == 0) {
+    if (!t_init && (o->dolog || cb || o->it_max == 0)) {
         if ((rc = read_status(h)) != NEMB_OK) return rc;
         h->fixup_rounds += h->h_status->cnt.nfix;
         res->n_allnul = h->h_status->cnt.allnul;
@@ -1123,7 +1184,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     int iter = 0, enq = 0, converged = 0, status = NEMB_OK, empty = 0;
     int flips[2] = {0, 0};
     unsigned long long seqs[2] = {0, 0};
-    int can_spec = !o->dolog && !cb && !want_crit_each && !h->profile && h->world == 1 &&
+    int can_spec = !o->dolog && !cb && !want_crit_each && !h->profile && h->world == 1 && !psgrad &&
                    o->algo == NEMB_ALGO_NCEM && !o->param_fixed && !getenv("NEM_B200_NO_SPEC");
     while (iter < o->it_max && !converged && status == NEMB_OK) {
         int want = iter + 1;
@@ -1132,10 +1193,15 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
             want++;
         for (; enq < want; enq++) {
             if (!o->param_fixed && (rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
+            if (psgrad) {            /* EstimBeta follows the M-step (nem_alg.c:1810-1812) */
+                if ((rc = run_estim_beta(h, o, &betaf, NULL)) != NEMB_OK) return rc;
+                beta = (double)betaf;
+            }
             if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
             if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
             int status_read = 0;
-            h->sweep_same_beta = 1;   /* the previous sweep used this beta: cached margins may apply */
+            h->sweep_same_beta = swept_beta == beta;   /* the previous sweep used this beta: cached margins may apply */
+            swept_beta = beta;
             if ((rc = run_sweep(h, o, beta, &flipped, (want_crit_each || cb) ? NULL : o, &status_read)) != NEMB_OK) return rc;
             if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
             if (cb) {
@@ -1200,6 +1266,14 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
         res->n_allnul = h->h_status->cnt.allnul;
         res->n_ties = h->h_status->cnt.ties;
     }
+    res->beta = betaf;
+    if (t_init && status == NEMB_W_EMPTYCLASS && iter == 1) {
+        /* MakeParaFromLabeled: "Class %d has no labeled observation" (nem_alg.c:1338-1345) --
+         * NemAlgo is not entered */
+        res->status = status; res->iters = 0; res->empty_class = empty;
+        free(nk_host);
+        return NEMB_OK;
+    }
     if (iter == 0) { /* nem_alg.c:1845-1851 */
         if ((rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
         if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
@@ -1240,13 +1314,27 @@ static void collect_profile(nemb_handle *h, nemb_result *res, cudaEvent_t e0, cu
     }
 }
 
-int nemb_fit_logged(nemb_handle *h, const nemb_options *o, float *prop, float *center, float *disp,
-                    nemb_result *res, nemb_iter_cb cb, void *user)
+static int fit_common(nemb_handle *h, const nemb_options *o, float *prop, float *center, float *disp,
+                      nemb_result *res, nemb_iter_cb cb, void *user, const float *t_init)
 {
     if (!h || !o || !prop || !center || !disp || !res) return NEMB_E_ARG;
     int rc;
     CK(cudaSetDevice(h->device));
     if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if (t_init) {
+        if ((rc = need_single(h, "nemb_fit_from_partition")) != NEMB_OK) return rc;
+        if (o->param_fixed) return fail(h, NEMB_E_ARG, "a starting classification needs the M-step (param_fixed = 0)");
+        if (o->algo == NEMB_ALGO_NCEM) {      /* hardened rows (nem_alg.c:2385-2391) */
+            for (int i = 0; i < h->n; i++) {
+                int ones = 0, other = 0;
+                for (int c = 0; c < o->k; c++) {
+                    float v = t_init[(size_t)i * o->k + c];
+                    if (v == 1.0f) ones++; else if (v != 0.0f) other++;
+                }
+                if (ones != 1 || other) return fail(h, NEMB_E_ARG, "ncem: row %d of the starting classification is not one-hot", i);
+            }
+        }
+    }
     if ((rc = ensure_k(h, o->k)) != NEMB_OK) return rc;
     memset(res, 0, sizeof *res);
     h->launches = 0; h->fixup_rounds = 0; h->exchanges = 0; h->profile = o->profile; h->ev_n = 0;
@@ -1255,11 +1343,14 @@ int nemb_fit_logged(nemb_handle *h, const nemb_options *o, float *prop, float *c
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, h->stream));
-    CK(cudaMemcpyAsync(h->d_prop, prop, sizeof(float) * o->k, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_center, center, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_disp, disp, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
-    int uniform0 = theta_uniform(o->k, h->d, center, disp);
-    rc = em_core(h, o, uniform0, res, cb, user, prop, center, disp);
+    int uniform0 = 0;
+    if (!t_init) {
+        CK(cudaMemcpyAsync(h->d_prop, prop, sizeof(float) * o->k, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_center, center, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_disp, disp, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
+        uniform0 = theta_uniform(o->k, h->d, center, disp);
+    }
+    rc = em_core(h, o, uniform0, res, cb, user, prop, center, disp, t_init);
     cudaEventRecord(e1, h->stream);
     cudaStreamSynchronize(h->stream);
     if (rc == NEMB_OK) collect_profile(h, res, e0, e1);
@@ -1268,10 +1359,135 @@ int nemb_fit_logged(nemb_handle *h, const nemb_options *o, float *prop, float *c
     return res->status;
 }
 
+int nemb_fit_logged(nemb_handle *h, const nemb_options *o, float *prop, float *center, float *disp,
+                    nemb_result *res, nemb_iter_cb cb, void *user)
+{
+    return fit_common(h, o, prop, center, disp, res, cb, user, NULL);
+}
+
 int nemb_fit(nemb_handle *h, const nemb_options *o, float *prop, float *center, float *disp,
              nemb_result *res)
 {
-    return nemb_fit_logged(h, o, prop, center, disp, res, NULL, NULL);
+    return fit_common(h, o, prop, center, disp, res, NULL, NULL, NULL);
+}
+
+int nemb_fit_from_partition(nemb_handle *h, const nemb_options *o, const float *t_init, float *prop,
+                            float *center, float *disp, nemb_result *res)
+{
+    if (!t_init) return NEMB_E_ARG;
+    return fit_common(h, o, prop, center, disp, res, NULL, NULL, t_init);
+}
+
+/* ClassifyByNemHeuBeta (nem_alg.c:731-992).  Host control flow over complete fits; the float
+ * arithmetic on the criteria (criV, slopes, thresholds) repeats the reference's. */
+int nemb_fit_beta_heuristic(nemb_handle *h, const nemb_options *o, int mode,
+                            const nemb_beta_heuristic *hp0, float *prop, float *center, float *disp,
+                            nemb_result *res, float *beta_trace, float *crit_trace, int cap)
+{
+    if (!h || !o || !prop || !center || !disp || !res) return NEMB_E_ARG;
+    if (mode != NEMB_BETA_HEUD && mode != NEMB_BETA_HEUL) return fail(h, NEMB_E_ARG, "heuristic mode must be heu_d or heu_l");
+    if (o->beta_mode != NEMB_BETA_FIX) return fail(h, NEMB_E_ARG, "a beta heuristic cannot be combined with psgrad");
+    if (o->param_fixed) return fail(h, NEMB_E_ARG, "the beta heuristics need the M-step (param_fixed = 0)");
+    int rc;
+    if ((rc = need_single(h, "nemb_fit_beta_heuristic")) != NEMB_OK) return rc;
+    nemb_beta_heuristic hp = {0.1f, 2.0f, 0.8f, 0.5f, 0.02f};            /* nem_typ.h:71-75 */
+    if (hp0) {
+        if (hp0->step > 0) hp.step = hp0->step;
+        if (hp0->max > 0) hp.max = hp0->max;
+        if (hp0->ddrop > 0) hp.ddrop = hp0->ddrop;
+        if (hp0->dloss > 0) hp.dloss = hp0->dloss;
+        if (hp0->lloss > 0) hp.lloss = hp0->lloss;
+    }
+    const int n = h->n, k = o->k;
+    const size_t nk = (size_t)n * k;
+    int nbtamax = (int)(hp.max / hp.step) + 1;
+    if (nbtamax < 1 || nbtamax > (1 << 20)) return fail(h, NEMB_E_ARG, "heuristic: bad step/max");
+    float *btaV = calloc((size_t)nbtamax + 2, sizeof(float)), *criV = calloc((size_t)nbtamax + 2, sizeof(float));
+    float *best = malloc(sizeof(float) * nk);
+    if (!btaV || !criV || !best) { free(btaV); free(criV); free(best); return fail(h, NEMB_E_MEMORY, "heuristic: host memory"); }
+    int nbta = 0, stop = 0, Dincreas = 0, Ddrop = 0, Lfound = 0, have_best = 0;
+    float Dmin = 0.0f, prevSlope = NAN, thisSlope = NAN, Lmax = NAN, btaEst = NAN;
+    const float DdropThres = -hp.ddrop * n, LlossThres = hp.lloss * n;
+    nemb_options ob = *o;
+    int64_t launches = 0, fixups = 0, kept = 0;
+    float ms = 0.f;
+    rc = NEMB_OK;
+#define SAVE_BEST() do { if ((rc = nemb_get_posteriors(h, best)) != NEMB_OK) goto done; have_best = 1; } while (0)
+    for (float bt = 0.0f; bt <= hp.max && !stop; bt += hp.step) {
+        ob.beta = bt;
+        int frc = fit_common(h, &ob, prop, center, disp, res, NULL, NULL, NULL);
+        launches += res->kernel_launches; fixups += res->fixup_rounds; kept += res->n_kept; ms += res->fit_ms;
+        if (frc != NEMB_OK) {                /* an empty class skips this beta (nem_alg.c:836-838) */
+            if (frc != NEMB_W_EMPTYCLASS) { rc = frc; goto done; }
+            continue;
+        }
+        if (nbta > nbtamax) break;
+        nbta++;
+        btaV[nbta] = bt;
+        if (mode == NEMB_BETA_HEUD) {
+            criV[nbta] = (float)res->D;
+            if (criV[nbta] < Dmin) Dmin = criV[nbta];
+            if (nbta >= 2) {
+                prevSlope = thisSlope;
+                thisSlope = (criV[nbta] - criV[nbta - 1]) / (btaV[nbta] - btaV[nbta - 1]);
+                if (thisSlope >= 0.5 * n) Dincreas = 1;
+            }
+            if (nbta >= 3) {
+                if (!Ddrop && !Dincreas) {
+                    if ((thisSlope - prevSlope) < DdropThres) { Ddrop = 1; stop = 1; btaEst = btaV[nbta - 1]; }
+                    else SAVE_BEST();
+                }
+            } else SAVE_BEST();
+        } else {
+            criV[nbta] = (float)res->L;
+            if (nbta < 2) { Lmax = criV[nbta]; SAVE_BEST(); }
+            else {
+                if (criV[nbta] > Lmax) Lmax = criV[nbta];
+                if (!Lfound) {
+                    if (criV[nbta] < Lmax - LlossThres) { Lfound = 1; stop = 1; btaEst = btaV[nbta - 1]; }
+                    else SAVE_BEST();
+                }
+            }
+        }
+    }
+#undef SAVE_BEST
+    {
+        int from_partition;
+        if (mode == NEMB_BETA_HEUD && !Ddrop) {        /* loss thresholding (nem_alg.c:931-954) */
+            float DThres = criV[1] - (criV[1] - Dmin) * hp.dloss;
+            int ibta, found = 0;
+            for (ibta = 1; ibta <= nbta && !found; ibta++) found = criV[ibta] <= DThres;
+            btaEst = found ? btaV[ibta - 2] : 0.0f;    /* "heuristic failed to detect beta" */
+            from_partition = 0;
+        } else
+            from_partition = have_best;                /* restore the saved classification, INIT_FILE */
+        if (mode == NEMB_BETA_HEUL && !Lfound) btaEst = btaV[nbta];
+        if (isnan(btaEst)) btaEst = 0.0f;              /* every tested beta failed */
+        for (int i = 0; i < nbta && i < cap; i++) {
+            if (beta_trace) beta_trace[i] = btaV[i + 1];
+            if (crit_trace) crit_trace[i] = criV[i + 1];
+        }
+        ob.beta = btaEst;
+        rc = fit_common(h, &ob, prop, center, disp, res, NULL, NULL, from_partition ? best : NULL);
+        res->kernel_launches += launches; res->fixup_rounds += fixups; res->n_kept += kept; res->fit_ms += ms;
+        res->n_beta_tested = nbta;
+    }
+done:
+    free(btaV); free(criV); free(best);
+    return rc;
+}
+
+int nemb_stage_estim_beta(nemb_handle *h, const nemb_options *o, const float *t, float *beta_io,
+                          double *sums3)
+{
+    if (!h || !o || !t || !beta_io) return NEMB_E_ARG;
+    int rc;
+    CK(cudaSetDevice(h->device));
+    if ((rc = check_options(h, o)) != NEMB_OK) return rc;
+    if ((rc = ensure_k(h, o->k)) != NEMB_OK) return rc;
+    h->profile = 0;
+    if ((rc = upload_state(h, o, t)) != NEMB_OK) return rc;
+    return run_estim_beta(h, o, beta_io, sums3);
 }
 
 /* ------------------------------------------------------------------ results */

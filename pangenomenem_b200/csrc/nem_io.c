@@ -468,13 +468,22 @@ int nemio_write_cf(const char *path, FILE *err, int n, const int32_t *label)
 int nemio_write_mf(const char *path, FILE *err, int k, int d, const double crit[4], float beta,
                    const float *prop, const float *center, const float *disp)
 {
+    return nemio_write_mf_mode(path, err, k, d, crit, beta, 0, prop, center, disp);
+}
+
+int nemio_write_mf_mode(const char *path, FILE *err, int k, int d, const double crit[4], float beta,
+                        int beta_mode, const float *prop, const float *center, const float *disp)
+{
+    /* BetaDesVC, nem_typ.h:540-543 */
+    static const char *const beta_des[4] = {"fixed", "pseudo-likelihood gradient",
+                                            "heuristic Hathaway crit", "heuristic mixture likelihood"};
     FILE *f = fopen(path, "w");
     if (!f) { fprintf(err, "Could not open file '%s' in write mode\n", path); return NEMB_E_FILE; }
     /* nem_exe.c:1708-1773; criteria are float in the reference (CriterT), error rate is NaN */
     fprintf(f, "Criteria U=NEM, D=Hathaway, L=mixture, M=markov ps-like, error\n\n");
     fprintf(f, "  %g    %g    %g    %g   %g\n\n", (double)(float)crit[0], (double)(float)crit[1],
             (double)(float)crit[2], (double)(float)crit[3], (double)NAN);
-    fprintf(f, "Beta (%s)\n", "fixed");
+    fprintf(f, "Beta (%s)\n", beta_des[beta_mode >= 0 && beta_mode < 4 ? beta_mode : 0]);
     fprintf(f, "  %6.4f\n", (double)beta);
     fprintf(f, "Mu (%d), Pk, and disp (%d) of the %d classes\n\n", d, d, k);
     for (int c = 0; c < k; c++) {

@@ -21,4 +21,8 @@ int nemio_write_uf(const char *path, FILE *err, int n, int k, const float *t);
 int nemio_write_cf(const char *path, FILE *err, int n, const int32_t *label);
 int nemio_write_mf(const char *path, FILE *err, int k, int d, const double crit_udlm[4], float beta,
                    const float *prop, const float *center, const float *disp);
+/* beta_mode 0..3 = fix, psgrad, heu_d, heu_l: the "Beta (...)" line (nem_exe.c:1714) */
+int nemio_write_mf_mode(const char *path, FILE *err, int k, int d, const double crit_udlm[4],
+                        float beta, int beta_mode, const float *prop, const float *center,
+                        const float *disp);
 #endif

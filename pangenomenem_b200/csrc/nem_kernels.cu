@@ -1929,9 +1929,35 @@ static __device__ __forceinline__ void crit_site(int K, const double *__restrict
     cZ -= zmx + log(zs);
 }
 
+// EstimBeta's per-site terms (nem_alg.c:2163-2191): log pseudo-likelihood of the classification
+// under the Potts prior, its first derivative in beta and minus its second derivative.  The
+// softmax moments of c_ik = ctx[k] are taken relative to max_k(beta c_ik): the reference's values
+// wherever its float exp() does not overflow.
+template <int KT>
+static __device__ __forceinline__ void grad_site(int K, const double *ctx, const float *ti, double beta,
+                                                 double &crit, double &grad, double &dsec) {
+    double mx = neg_inf();
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+        if (k < K) mx = fmax(mx, beta * ctx[k]);
+    double se = 0, sce = 0, sc2e = 0, stc = 0;
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        if (k < K) {
+            double e = exp(beta * ctx[k] - mx);
+            se += e; sce += ctx[k] * e; sc2e += ctx[k] * ctx[k] * e;
+            stc += (double)ti[k] * ctx[k];
+        }
+    }
+    crit += beta * stc - (mx + log(se));
+    grad += stc - sce / se;
+    dsec += (sc2e * se - sce * sce) / (se * se);
+}
+
 // blocks [0, heavy_blocks): hubs of the (index-sorted) heavy list, one warp per site;
 // the other blocks: the remaining sites, one thread per site.  Fixed assignment => deterministic.
-template <int KT>
+// GRAD: the same walk accumulates EstimBeta's (crit, grad, dsec) instead of (D, G, L, Z).
+template <int KT, bool GRAD>
 __global__ void __launch_bounds__(256)
 k_criteria_partial(int K, int row0, int n_loc, const nemk_lpsrc lps,
                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
@@ -1953,9 +1979,12 @@ k_criteria_partial(int K, int row0, int n_loc, const nemk_lpsrc lps,
 #pragma unroll
             for (int k = 0; k < KT; k++) ti[k] = (l == (unsigned)k) ? 1.f : 0.f;
             if (lane == 0) {
-                double lpv[KT];
-                load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
-                crit_site<KT>(K, lpv, ctx, ti, beta, cD, cG, cL, cZ);
+                if (GRAD) grad_site<KT>(K, ctx, ti, beta, cD, cG, cL);
+                else {
+                    double lpv[KT];
+                    load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+                    crit_site<KT>(K, lpv, ctx, ti, beta, cD, cG, cL, cZ);
+                }
             }
         }
     } else {
@@ -1991,9 +2020,12 @@ k_criteria_partial(int K, int row0, int n_loc, const nemk_lpsrc lps,
 #pragma unroll
                 for (int k = 0; k < KT; k++) ti[k] = (k < K) ? t[(size_t)i * K + k] : 0.f;
             }
-            double lpv[KT];
-            load_lp<KT>(lps, K, (size_t)il, lpv);
-            crit_site<KT>(K, lpv, ctx, ti, beta, cD, cG, cL, cZ);
+            if (GRAD) grad_site<KT>(K, ctx, ti, beta, cD, cG, cL);
+            else {
+                double lpv[KT];
+                load_lp<KT>(lps, K, (size_t)il, lpv);
+                crit_site<KT>(K, lpv, ctx, ti, beta, cD, cG, cL, cZ);
+            }
         }
     }
     cD = block_sum<256>(cD, sh);
@@ -2015,7 +2047,10 @@ k_criteria_final(int nblocks, const double *__restrict__ partials, double beta, 
         for (int q = 0; q < 4; q++) v[q] += partials[b * 4 + q];
 #pragma unroll
     for (int q = 0; q < 4; q++) v[q] = block_sum<256>(v[q], sh);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && beta != beta) {   // NaN beta = raw sums (EstimBeta's crit, grad, dsec)
+#pragma unroll
+        for (int q = 0; q < 4; q++) crit6[q] = v[q];
+    } else if (threadIdx.x == 0) {
         double D = v[0], G = v[1], L = v[2], Z = v[3];
         crit6[0] = D + 0.5 * beta * G;
         crit6[1] = D; crit6[2] = L;
@@ -2703,9 +2738,26 @@ extern "C" int nemk_criteria_partial(nemk_stream s, int k, int row0, int n_loc, 
     int hb = (row_ptr && lab && heavy && n_heavy > 0) ? cdiv((long long)n_heavy * 32, 256) : 0;
     if (hb > nblocks / 2) hb = nblocks / 2;
     if (nblocks < 2) hb = 0;
-    DISPATCH_K(k, (k_criteria_partial<KT><<<nblocks, 256, 0, S(s)>>>(k, row0, n_loc, lps, row_ptr,
-                                                                    col, wgt, beta, lab, t, heavy,
-                                                                    n_heavy, hb, partials)));
+    DISPATCH_K(k, (k_criteria_partial<KT, false><<<nblocks, 256, 0, S(s)>>>(k, row0, n_loc, lps, row_ptr,
+                                                                           col, wgt, beta, lab, t, heavy,
+                                                                           n_heavy, hb, partials)));
+    note_launch();
+    return nblocks;
+}
+// EstimBeta's sums (nem_alg.c:2157-2191) with the criteria kernel's walk; the 4th column is 0.
+// Finish with nemk_criteria_final(beta = NaN): out[0..2] = crit, grad, dsec.
+extern "C" int nemk_betagrad_partial(nemk_stream s, int k, int row0, int n_loc, const int32_t *row_ptr,
+                                     const int32_t *col, const float *wgt, double beta,
+                                     const uint8_t *lab, const float *t, const int32_t *heavy,
+                                     int n_heavy, double *partials, int nblocks) {
+    int hb = (row_ptr && lab && heavy && n_heavy > 0) ? cdiv((long long)n_heavy * 32, 256) : 0;
+    if (hb > nblocks / 2) hb = nblocks / 2;
+    if (nblocks < 2) hb = 0;
+    nemk_lpsrc lps;
+    memset(&lps, 0, sizeof lps);
+    DISPATCH_K(k, (k_criteria_partial<KT, true><<<nblocks, 256, 0, S(s)>>>(k, row0, n_loc, lps, row_ptr,
+                                                                          col, wgt, beta, lab, t, heavy,
+                                                                          n_heavy, hb, partials)));
     note_launch();
     return nblocks;
 }

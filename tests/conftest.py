@@ -54,7 +54,10 @@ def rel_close(a, b, rtol, atol=0.0):
 
 # ------------------------------------------------------------------ golden fixtures
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+_ALL_GOLDEN = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+GOLDEN_CASES = [n for n in _ALL_GOLDEN if not n.startswith("beta_")]
+# beta estimation runs of the reference (psgrad / heu_d / heu_l through the harness)
+BETA_GOLDEN_CASES = [n for n in _ALL_GOLDEN if n.startswith("beta_")]
 
 
 class Golden:
@@ -77,6 +80,11 @@ class Golden:
         self.crit = dict(zip("UDLMZG", z["ref_crit"].tolist()))
         self.iters, self.converged = int(z["ref_iters"]), bool(z["ref_converged"])
         self.label = self.cm.argmax(axis=1)
+        self.beta_mode = str(z["beta_mode"]) if "beta_mode" in z.files else "fix"
+        if self.beta_mode != "fix":
+            self.beta_params = z["beta_params"].tolist()
+            self.ref_beta = float(z["ref_beta"])
+            self.ref_beta_tested = z["ref_beta_tested"].tolist()
 
     def write_files(self, base):
         """The exact input files the reference was run on."""

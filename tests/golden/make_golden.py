@@ -54,21 +54,51 @@ CASES = {
                            dict(algo="ncem", beta=0.5, disp="sk_", prop="pk", it_max=100)),
 }
 
+# beta estimation (the reference reaches it through its CLI's -B/-G/-H only):
+# name: (n, d, seed, graph, weighted, options, beta_mode, beta_params)
+# psgrad cases are unweighted: with co-presence weights the reference's float exp(beta * ctx)
+# overflows, its gradient is NaN and it resets beta to 0 (nem_alg.c:2172-2191, 2222-2225)
+BETA_CASES = {
+    "beta_psgrad_ncem": (1000, 40, 21, "pangenome", False,
+                         dict(algo="ncem", beta=0.5, disp="sk_", prop="pk", it_max=100),
+                         "psgrad", (1, 0.001, 0.0)),
+    "beta_psgrad_nem": (800, 36, 22, "pangenome", False,
+                        dict(algo="nem", beta=0.3, disp="sk_", prop="pk", it_max=10),
+                        "psgrad", (5, 0.001, 0.0)),
+    "beta_psgrad_step": (900, 33, 23, "random", False,
+                         dict(algo="ncem", beta=0.2, disp="skd", prop="pk", it_max=100),
+                         "psgrad", (3, 0.001, 0.5)),
+    "beta_heu_d": (1000, 40, 24, "pangenome", True,
+                   dict(algo="ncem", beta=0.5, disp="sk_", prop="pk", it_max=100),
+                   "heu_d", (0.1, 2.0, 0.8, 0.5, 0.02)),
+    "beta_heu_l": (1000, 40, 25, "pangenome", True,
+                   dict(algo="ncem", beta=0.5, disp="sk_", prop="pk", it_max=100),
+                   "heu_l", (0.1, 2.0, 0.8, 0.5, 0.02)),
+    "beta_heu_d_nem": (800, 36, 26, "pangenome", False,
+                       dict(algo="nem", beta=0.5, disp="sk_", prop="pk", it_max=6),
+                       "heu_d", (0.25, 1.0, 0.8, 0.5, 0.002)),
+}
+
 
 def main() -> None:
     nemo.build(ref=True)
     if not nemo.have_ref():
         raise SystemExit("oracle/_ref is not built (needs /root/reference)")
-    for name, (n, d, seed, graph, weighted, opt) in CASES.items():
+    todo = {k: v + ("fix", ()) for k, v in CASES.items()}
+    todo.update(BETA_CASES)
+    for name, (n, d, seed, graph, weighted, opt, beta_mode, beta_params) in todo.items():
         pg = synth.make_pangenome(n, d, seed=seed, graph=graph, weighted=weighted)
         spatial = graph != "none"
         with tempfile.TemporaryDirectory() as tmp:
             base = os.path.join(tmp, "nem_file")
             synth.write_nem_files(base, pg, spatial=spatial, weighted_flag=1 if weighted else 0)
             ref = nemo.run_ref_harness(base, os.path.join(tmp, "out"), k=3, tie="first", seed=42,
-                                       **opt)
+                                       beta_mode=beta_mode, beta_params=beta_params, **opt)
             cli = {}
-            if opt.get("update", "seq") == "seq":
+            if beta_mode != "fix":
+                cli = dict(beta_mode=beta_mode, beta_params=np.array(beta_params, dtype=np.float64),
+                           ref_beta=ref["beta"], ref_beta_tested=np.array(ref["beta_tested"]))
+            elif opt.get("update", "seq") == "seq":
                 rc, _, _ = nemo.run_ref_cli(base, k=3, algo=opt["algo"], beta=opt["beta"],
                                             it_max=opt["it_max"], dolog=1, prop=opt["prop"],
                                             disp=opt["disp"])

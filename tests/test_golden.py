@@ -37,3 +37,42 @@ def test_reference_uf_text_matches_its_own_posteriors(name):
         assert (uf.argmax(axis=1) != g.label).sum() <= 2     # exact ties only
     else:
         assert np.abs(uf - g.cm).max() < 2e-3
+
+
+# ------------------------------------------------------------------ beta estimation
+def _beta_fit(oracle, g):
+    pb = oracle.Problem(g.x, g.row_ptr, g.col, g.wgt, **g.opt)
+    th = oracle.default_theta(3, g.d)
+    if g.beta_mode == "psgrad":
+        nit, conv, step = g.beta_params
+        return pb.fit_ex(*th, psgrad=(int(nit), conv, step))
+    step, bmax, ddrop, dloss, lloss = g.beta_params
+    return pb.fit_heuristic(*th, mode=g.beta_mode, step=step, bmax=bmax, ddrop=ddrop, dloss=dloss,
+                            lloss=lloss)
+
+
+from conftest import BETA_GOLDEN_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", BETA_GOLDEN_CASES)
+def test_oracle_reproduces_reference_beta_estimation(oracle, name):
+    """psgrad (EstimBeta, nem_alg.c:2120-2230) and the two heuristics (ClassifyByNemHeuBeta,
+    nem_alg.c:731-992) against the reference harness run with BetaModel set: the estimated beta
+    (1e-5: the reference sums the gradient in float32), the betas it tested, and the final fit."""
+    g = Golden(name)
+    fit = _beta_fit(oracle, g)
+    assert fit.status == 0
+    assert abs(fit.beta - g.ref_beta) <= 1e-5 * max(1.0, abs(g.ref_beta)), (fit.beta, g.ref_beta)
+    if g.beta_mode != "psgrad":
+        assert np.allclose(fit.beta_tested, g.ref_beta_tested, atol=6e-3)   # "%5.2f" in the log
+    if g.opt["algo"] == "nem":
+        assert fit.iters == g.iters and fit.converged == g.converged   # it_max cuts these runs
+        assert np.abs(fit.t - g.cm).max() < 2e-3
+    else:
+        check_against_reference(g, fit.t, fit.label, fit.prop, fit.center, fit.disp, fit.crit,
+                                fit.iters, fit.converged)
+
+
+def test_beta_golden_set_covers_the_modes():
+    modes = {Golden(n).beta_mode for n in BETA_GOLDEN_CASES}
+    assert modes == {"psgrad", "heu_d", "heu_l"}

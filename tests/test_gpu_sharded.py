@@ -99,6 +99,19 @@ def test_sharded_para_update(oracle, algo, disp):
             assert rel_close(fit.crit[key], ref.crit[key], 1e-6), key
 
 
+def test_sharded_psgrad(oracle):
+    """BETA_PSGRAD on row shards: the pseudo-likelihood sums are per-rank partial rows gathered
+    and added in rank order, so every rank derives the same beta as one GPU and the oracle."""
+    pg = make_case(6001, 40, seed=10)
+    theta = oracle.default_theta(3, pg.d)
+    kw = dict(k=3, algo="ncem", update="seq", disp="sk_", prop="pk", beta=0.3, it_max=30)
+    ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit_ex(*theta, psgrad=(2, 0.001, 0.0))
+    for fit, lab, _ in run_sharded(pg, 3, theta, psgrad=(2, 0.001, 0.0), **kw):
+        assert fit.status == 0 and fit.iters == ref.iters and fit.converged == ref.converged
+        assert rel_close(fit.beta, ref.beta, 1e-6)
+        assert np.array_equal(lab, ref.label)
+
+
 def test_sharded_nonspatial_and_empty_rank(oracle):
     """Type N data (no graph) and more ranks than rows-per-shard allows (an empty last rank)."""
     pg = make_case(9, 20, seed=1, graph="none")
