@@ -51,8 +51,8 @@ def test_estim_beta_stage_matches_oracle(engine, oracle, algo, weighted):
     co-presence weights ~D) are where the reference's float exp() overflows; both sides use the
     shifted soft-max there."""
     pg = make_case(5000, 60, seed=3, weighted=weighted)
-    kw = dict(k=3, algo=algo, beta=0.5, it_max=3)
-    pb = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw)
+    kw = dict(k=3, algo=algo, it_max=3)
+    pb = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, beta=0.5, **kw)
     o = pb.fit(*oracle.default_theta(3, pg.d))
     engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
     for beta0, nit, step in [(0.5, 1, 0.0), (0.0, 4, 0.0), (1.0, 3, 0.5), (-0.2, 2, 0.0)]:
@@ -132,7 +132,7 @@ def test_fit_from_partition_edge_cases(engine, oracle):
     t0 = np.zeros((pg.n, 3), dtype=np.float32)
     t0[:, 0] = 1.0                                      # classes 2 and 3 have no family
     fit = engine.fit(*th, t_init=t0)
-    assert fit.status == 1 and fit.iters == 0 and fit.empty_class == 2
+    assert fit.status == 1 and fit.iters == 0 and fit.empty_class == 3   # the last empty class, nem_mod.c:1404-1409
     o = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt).fit_ex(*th, t_init=t0)
     assert o.status == 1 and o.iters == 0
     t0[5] = (0.5, 0.5, 0.0)                             # ncem wants hardened rows
