@@ -79,8 +79,27 @@ static inline int next_token(cursor *c, const char **tok, size_t *len)
     return 1;
 }
 
+/* plain decimal tokens (what PPanGGOLiN writes: ids, counts, integer coverages) are converted
+ * in place; anything else goes through strtol / strtof like the reference's fscanf */
+static inline int tok_digits(const char *t, size_t len, long *out)
+{
+    size_t i = 0;
+    int neg = 0;
+    if (len > 1 && (t[0] == '-' || t[0] == '+')) { neg = t[0] == '-'; i = 1; }
+    if (len - i == 0 || len - i > 15) return 0;
+    long v = 0;
+    for (; i < len; i++) {
+        unsigned dgt = (unsigned)(t[i] - '0');
+        if (dgt > 9) return 0;
+        v = v * 10 + (long)dgt;
+    }
+    *out = neg ? -v : v;
+    return 1;
+}
+
 static int tok_int(const char *t, size_t len, long *out)
 {
+    if (tok_digits(t, len, out)) return 1;
     char buf[64];
     if (len == 0 || len >= sizeof buf) return 0;
     memcpy(buf, t, len); buf[len] = 0;
@@ -94,6 +113,8 @@ static int tok_int(const char *t, size_t len, long *out)
 
 static int tok_float(const char *t, size_t len, float *out)
 {
+    long iv;
+    if (tok_digits(t, len, &iv)) { *out = (float)iv; return 1; }   /* < 10^15: one correct rounding, as strtof */
     char buf[128];
     if (len == 0 || len >= sizeof buf) return 0;
     memcpy(buf, t, len); buf[len] = 0;
@@ -166,12 +187,47 @@ typedef struct {
     const char *src; int d, wpr, r0, r1; uint32_t *out; int bad;
 } dat_job;
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+static uint8_t even_bits_lut[256];      /* bits 0,2,4,6 of the index packed into bits 0..3 */
+static pthread_once_t even_bits_once = PTHREAD_ONCE_INIT;
+static void even_bits_init(void)
+{
+    for (int v = 0; v < 256; v++)
+        even_bits_lut[v] = (uint8_t)((v & 1) | ((v >> 1) & 2) | ((v >> 2) & 4) | ((v >> 3) & 8));
+}
+/* 32 cells = 64 bytes "c s c s ..." -> one word; *bad is raised unless every c is '0'/'1' and
+ * every s is white space (space or \t..\r) */
+static inline uint32_t dat_word_sse2(const unsigned char *q, unsigned *bad)
+{
+    const __m128i one = _mm_set1_epi8('1'), even = _mm_set1_epi16(0x00ff), lsb = _mm_set1_epi16(0x0001);
+    const __m128i sp = _mm_set1_epi8(' '), nine = _mm_set1_epi8(9), four = _mm_set1_epi8(4);
+    uint32_t word = 0;
+    unsigned ok = 0xffffu;
+    for (int part = 0; part < 4; part++) {
+        __m128i v = _mm_loadu_si128((const __m128i *)(q + 16 * part));
+        unsigned m1 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, one));           /* byte == '1' */
+        __m128i cell_ok = _mm_cmpeq_epi8(_mm_or_si128(v, lsb), one);                /* even bytes: '0' | 1 == '1' */
+        __m128i off = _mm_sub_epi8(v, nine);                                        /* odd bytes: \t..\r or ' ' */
+        __m128i ws_ok = _mm_or_si128(_mm_cmpeq_epi8(_mm_min_epu8(off, four), off), _mm_cmpeq_epi8(v, sp));
+        __m128i good = _mm_or_si128(_mm_and_si128(cell_ok, even), _mm_andnot_si128(even, ws_ok));
+        ok &= (unsigned)_mm_movemask_epi8(good);
+        word |= (uint32_t)(even_bits_lut[m1 & 0xff] | (even_bits_lut[m1 >> 8] << 4)) << (8 * part);
+    }
+    *bad |= ok ^ 0xffffu;
+    return word;
+}
+#endif
+
 /* fast path: PPanGGOLiN's exact layout, one char per cell + one separator (ppanggolin.py:850) */
 static void *dat_worker(void *arg)
 {
     dat_job *j = arg;
     int d = j->d, wpr = j->wpr;
     size_t stride = (size_t)2 * d;
+#if defined(__SSE2__)
+    pthread_once(&even_bits_once, even_bits_init);
+#endif
     for (int r = j->r0; r < j->r1; r++) {
         const unsigned char *p = (const unsigned char *)j->src + (size_t)r * stride;
         uint32_t *o = j->out + (size_t)r * wpr;
@@ -180,6 +236,9 @@ static void *dat_worker(void *arg)
             int nb = d - w * 32 < 32 ? d - w * 32 : 32;
             uint32_t word = 0;
             const unsigned char *q = p + (size_t)w * 64;
+#if defined(__SSE2__)
+            if (nb == 32) { o[w] = dat_word_sse2(q, &bad); continue; }
+#endif
             for (int b = 0; b < nb; b++) {
                 unsigned ch = q[2 * b];
                 bad |= (ch | 1u) ^ '1';

@@ -149,3 +149,31 @@ def test_golden_input_files_round_trip(tmp_path, capi, oracle):
     assert np.array_equal(hp["x_packed"], oracle.pack(g.x, hp["wpr"]))
     assert np.array_equal(hp["row_ptr"], g.row_ptr) and np.array_equal(hp["col"], g.col)
     assert np.array_equal(hp["wgt"], g.wgt)
+
+
+def test_dat_fast_path_validates_every_byte(tmp_path, capi):
+    """The vectorised fixed-layout reader (one char per cell + one separator, what
+    ppanggolin.py:850 writes) must accept any white-space separator and reject anything else by
+    falling back to the tokenizer, which reports the offending value (multi-threaded: n >= 4096)."""
+    from pangenomenem_b200 import synth
+    pg = make_case(5000, 70, seed=4, graph="none")
+    base = _write(tmp_path, pg, spatial=False)
+    want = synth.pack_rows(pg.x, capi.read_files(base, k=0)["wpr"])
+    raw = bytearray(open(base + ".dat", "rb").read())
+    stride = 2 * pg.d
+    for r, c in [(0, 0), (17, 31), (4999, 69), (2500, 64)]:      # separators -> space / CR
+        raw[r * stride + 2 * c + 1] = ord(" ") if c % 2 else ord("\r")
+    open(base + ".dat", "wb").write(bytes(raw))
+    assert np.array_equal(capi.read_files(base, k=0)["x_packed"], want)
+    for pos, ch in [((3000, 40), b"2"), ((4100, 3), b"x"), ((10, 69), b"\t")]:
+        bad = bytearray(raw)
+        bad[pos[0] * stride + 2 * pos[1]] = ch[0]                # a cell that is not 0 / 1
+        open(base + ".dat", "wb").write(bytes(bad))
+        with pytest.raises(capi.NemError) as ei:
+            capi.read_files(base, k=0)
+        assert ei.value.code == 3
+    bad = bytearray(raw)
+    bad[1234 * stride + 2 * 33 + 1] = ord("1")                   # a separator that is a digit
+    open(base + ".dat", "wb").write(bytes(bad))
+    with pytest.raises(capi.NemError):
+        capi.read_files(base, k=0)
