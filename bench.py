@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- NEM family-iterations/s on B200 (BASELINE.json metric) + roofline + CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1|c5|dropin] [--impl reference]
 
 One "step" = one complete NEM fit (blind sweep, beta sweep, EM iterations until the `clas`
 convergence test, final criteria) of the synthetic pangenome, run exactly as PPanGGOLiN runs it
@@ -212,6 +212,54 @@ def main_reference(args):
         "e2e": {"value": v, "unit": "family-iterations/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def main_dropin(args):
+    """--workload dropin: the call PPanGGOLiN makes (ppanggolin.py:1814-1826) -- nem() on the text
+    files it writes (C2 shape: 100 000 families x 500 genomes, with a pangenome-like .nei,
+    beta = 0.5), wall seconds of the whole call: parse .str/.dat/.nei/.m, upload, fit, write
+    .uf/.mf.  Ours in-process through the C ABI (first call = CUDA context creation included, then
+    warm calls); the unmodified reference (oracle/_ref/nem_ref_cli) once on the same files.  Not
+    the round's headline metric: it shows what a drop-in user sees, where text I/O dominates."""
+    from oracle import nemo
+    from pangenomenem_b200 import capi, synth
+    n, d, beta = (args.rows or 100_000), 500, 0.5
+    tmp = tempfile.mkdtemp(prefix="nem_dropin_")
+    base = os.path.join(tmp, "nem_file")
+    pg = synth.make_pangenome(n, d, seed=42)
+    synth.write_nem_files(base, pg)
+    call = dict(Fname=base.encode(), nk=3, algo=b"ncem", beta=beta, convergence=b"clas",
+                convergence_th=1e-8, format=b"fuzzy", it_max=100, dolog=False, model_family=b"bern",
+                proportion=b"pk", dispersion=b"sk_", init_mode=2)
+    times = []
+    for _ in range(1 + args.warmup + args.steps):
+        for ext in (".uf", ".mf"):
+            if os.path.exists(base + ext):
+                os.remove(base + ext)
+        t0 = time.time()
+        rc = capi.nem(**call)
+        times.append(time.time() - t0)
+        assert rc == 0 and os.path.exists(base + ".uf"), rc
+    uf = synth.read_uf(base + ".uf", 3)
+    warm = times[1 + args.warmup:]
+    line = {"metric": "nem() drop-in call on PPanGGOLiN's files, wall seconds", "value": float(np.mean(warm)),
+            "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": False, "data": "synthetic",
+            "config": {"workload": "dropin: %d families x %d genomes, K=3, beta=%.1f, ncem seq bern pk sk_, "
+                                   "text files .str/.dat/.nei/.m in, .uf/.mf out" % (n, d, beta),
+                       "dat_bytes": os.path.getsize(base + ".dat"), "nei_bytes": os.path.getsize(base + ".nei")},
+            "first_call_s": times[0], "warm_calls_s": warm, "host_threads": os.cpu_count()}
+    if nemo.have_ref() and not args.no_cpu:
+        os.rename(base + ".uf", base + ".ours.uf")
+        t0 = time.time()
+        rc, _, _ = nemo.run_ref_cli(base, beta=beta, dolog=0)
+        t_ref = time.time() - t0
+        line["reference"] = {"seconds": t_ref, "rc": rc, "cores": 1,
+                             "what": "oracle/_ref/nem_ref_cli (unmodified reference nem()), same files and arguments"}
+        if rc == 0 and os.path.exists(base + ".uf"):
+            ref = synth.read_uf(base + ".uf", 3)
+            line["reference"]["labels_differ"] = int((ref.argmax(axis=1) != uf.argmax(axis=1)).sum())
+    print(json.dumps(line))
 
 
 def workload_name(w):
@@ -632,7 +680,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["dropin"])
     ap.add_argument("--rows", type=int, default=0, help="override the number of families (debug)")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1: one row-sharded pangenome of N x families (default) or N independent replicas")
@@ -644,6 +692,8 @@ def main():
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         main_reference(args)
+    elif args.workload == "dropin":
+        main_dropin(args)
     elif args.workload == "c5":
         main_c5(args)
     else:

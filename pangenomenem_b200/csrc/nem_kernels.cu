@@ -1041,6 +1041,32 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
 // the fixed point reached is the sequential sweep's result whatever the interleaving.
 // The first rounds (long work lists) run grid-wide, one launch per round; the tail runs in one
 // CTA that loops until the list is empty.
+// mark_readers for the chase (below): the LOWEST later reader this call claimed (dirty 0 -> 1) is
+// handed back instead of being queued; every other claimed reader goes to the work list.
+static __device__ __forceinline__ int mark_readers_keep_one(int i, const int32_t *__restrict__ rrow_ptr,
+                                                            const int32_t *__restrict__ rcol,
+                                                            int32_t *dirty, int32_t *wl, int32_t *wl_count,
+                                                            int row0, int row1, uint8_t *stale_next) {
+    int lo = rrow_ptr[i], hi = rrow_ptr[i + 1], keep = -1;
+    for (int e = lo; e < hi; e++) {
+        int j = rcol[e];
+        if (stale_next && j <= i && j >= row0 && j < row1) stale_next[j] = 1;
+        if (j > i && j >= row0 && j < row1 && atomicExch(&dirty[j], 1) == 0) {
+            if (keep < 0) keep = j;
+            else if (j < keep) { wl[atomicAdd(wl_count, 1)] = keep; keep = j; }
+            else wl[atomicAdd(wl_count, 1)] = j;
+        }
+    }
+    return keep;
+}
+
+// Re-evaluate site i.  CHASE (mg.chase > 0): in a pangenome the later readers of a site are its
+// chromosome successors, so a label change propagates along chains i -> i+1 -> ...; walking such a
+// chain one link per ROUND costs a grid/cluster barrier (~3 us) per link.  Any interleaving of the
+// re-evaluations reaches the same fixed point as long as the dirty-flag protocol holds (clear
+// before reading, publish before claiming readers), so the thread that changed i may evaluate a
+// reader it has just claimed right away: the chain is walked at the latency of its dependent
+// loads only.  Hubs and links beyond mg.chase are queued as before.
 template <int KT>
 static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row1,
                                                  const nemk_lpsrc &lps,
@@ -1053,23 +1079,37 @@ static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row
                                                  const int32_t *__restrict__ rrow_ptr,
                                                  const int32_t *__restrict__ rcol,
                                                  const nemk_margins &mg, double thr_store) {
-    atomicExch(&dirty[i], 0);
-    __threadfence();
-    double ctx[KT];
-    ctx_labels<KT>(K, i, row_ptr, col, wgt,
-                   [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
-    int flags;
-    double lpv[KT], margin;
-    load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
-    int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
-    store_margin(mg, i - row0, margin, thr_store);   // the LAST evaluation of a site is its final one
-    int was = __ldcg(lab_cur + i);
-    if (km == was) return 0;
-    lab_cur[i] = (uint8_t)km;
-    __threadfence();
-    mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1, mg.stale_next);
-    int old = lab_old[i];
-    return (km != old) - (was != old);
+    int delta = 0;
+    for (int link = 0;; link++) {
+        atomicExch(&dirty[i], 0);
+        __threadfence();
+        double ctx[KT];
+        ctx_labels<KT>(K, i, row_ptr, col, wgt,
+                       [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
+        int flags;
+        double lpv[KT], margin;
+        load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+        int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
+        store_margin(mg, i - row0, margin, thr_store);   // the LAST evaluation of a site is its final one
+        int was = __ldcg(lab_cur + i);
+        if (km == was) return delta;
+        lab_cur[i] = (uint8_t)km;
+        __threadfence();
+        int old = lab_old[i];
+        delta += (km != old) - (was != old);
+        if (link >= mg.chase) {
+            mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1, mg.stale_next);
+            return delta;
+        }
+        int nxt = mark_readers_keep_one(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1,
+                                        mg.stale_next);
+        if (nxt < 0) return delta;
+        if (row_ptr[nxt + 1] - row_ptr[nxt] > HEAVY_DEG) {   // hubs are evaluated by a whole warp
+            next_list[atomicAdd(next_cnt, 1)] = nxt;
+            return delta;
+        }
+        i = nxt;
+    }
 }
 
 // the same for a hub, by a whole warp (every lane returns the same delta)

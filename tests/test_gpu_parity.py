@@ -384,6 +384,36 @@ def test_margin_cache_is_exact_on_long_fits(engine, oracle, graph, beta, disp, m
         assert got.n_ties == ref.n_ties and got.n_allnul == ref.n_allnul
 
 
+@pytest.mark.parametrize("graph,beta", [("pangenome", 0.5), ("chain", 2.0), ("random", 1.0)])
+def test_chain_chasing_is_exact(engine, oracle, graph, beta, monkeypatch):
+    """Fix-up rounds: the thread that changed a site's label goes on with the reader it claimed
+    (nem_kernels.cu fixup_site, nemk_margins.chase) instead of queueing it for the next round.
+    Same fixed point = same labels as the oracle's in-order sweep, with fewer rounds; a chain
+    graph with a strong beta is the worst case (one long domino line)."""
+    pg = make_case(40000, 48, seed=29, graph=graph)
+    theta = oracle.default_theta(3, pg.d, low_disp=0.25)
+    kw = dict(k=3, algo="ncem", update="seq", disp="sk_", prop="pk", beta=beta, it_max=40)
+    ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(*theta)
+    engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
+    rounds = {}
+    for off in ("", "1"):
+        if off:
+            monkeypatch.setenv("NEM_B200_NO_CHASE", off)
+        else:
+            monkeypatch.delenv("NEM_B200_NO_CHASE", raising=False)
+        for margins_off in ("", "1"):
+            if margins_off:
+                monkeypatch.setenv("NEM_B200_NO_MARGINS", "1")
+            else:
+                monkeypatch.delenv("NEM_B200_NO_MARGINS", raising=False)
+            got = engine.fit(*theta, **kw)
+            assert got.iters == ref.iters and got.converged == ref.converged
+            assert np.array_equal(engine.labels(), ref.label), int((engine.labels() != ref.label).sum())
+            assert np.array_equal(got.disp, ref.disp) and got.n_ties == ref.n_ties
+        rounds[off] = got.fixup_rounds
+    assert rounds[""] <= rounds["1"], rounds
+
+
 def test_fractional_weights_keep_the_file_order(engine, oracle):
     """Non-integer edge weights: the fp64 context sums depend on the order, so the engine must add
     them in file order like SumNeighsOfClass (nem_alg.c:2865-2875), hubs included."""
