@@ -453,6 +453,8 @@ def main_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host staging buffers must sit on the socket next to this rank's GPU (see the helper)
+    numa = sharded.bind_to_gpu_numa(local) if not os.environ.get("NEM_BENCH_NO_NUMA") else {"bound": False, "off": True}
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own banner/diagnostics go to stderr
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -561,7 +563,9 @@ def main_ours(args):
     for _ in range(1):                   # one untimed pass: first-touch allocations
         eng.load_shard(xhu, n_glob, plan.row0, d, row_ptr, col, wgt)
         eng.fit(*theta0, **opts)
-    lab_host = None
+    # every rank reads back the labels of ITS OWN families (all of them on one GPU), into a buffer
+    # it keeps across steps like the long-lived caller above
+    lab_host = np.empty(plan.n_loc, dtype=np.int32)
     barrier()
     e0 = time.time()
     e_iters = 0
@@ -571,15 +575,15 @@ def main_ours(args):
         eng.load_shard(xhu, n_glob, plan.row0, d, row_ptr, col, wgt)
         tb = time.time()
         f = eng.fit(*theta0, **opts)
-        lab_host = eng.labels()
+        eng.labels(plan.row0, plan.n_loc, out=lab_host)
         t_load += tb - ta; t_fit += time.time() - tb
         e_iters += f.iters
     barrier()
     e_wall = time.time() - e0
-    e2e_same = bool(np.array_equal(lab_host, lab_resident))
+    e2e_same = bool(np.array_equal(lab_host, lab_resident[plan.rows]))
     depth = eng.dims()["depth"] if mode != "sharded" else 0      # builds the level schedule: untimed
     h2d = x_bytes + (0 if col is None else (n_glob + 1) * 4 + nnz * 8) + (K + 2 * K * d) * 4
-    d2h = n_glob + (K + 2 * K * d) * 4 + 256
+    d2h = plan.n_loc + (K + 2 * K * d) * 4 + 256
 
     # ---- max over ranks
     t_dev = torch.tensor([dev_ms, e_wall * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
@@ -638,11 +642,13 @@ def main_ours(args):
             "gpu_launches": int(launches_all),
             "wall_ms_per_step": wall_ms_max / args.steps,
             "e2e": {"value": e_fam_iters / (e_ms_max * 1e-3), "unit": "family-iterations/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+                    "h2d_bytes_per_rank": int(h2d), "d2h_bytes_per_rank": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e_ms_max / e2e_steps,
                     "load_ms": t_load * 1e3 / e2e_steps, "fit_ms": t_fit * 1e3 / e2e_steps,
                     "labels_equal_resident_fit": e2e_same,
-                    "what": "nemb_load_shard(host pinned X + CSR: H2D, device-side graph validation) + nemb_fit + nemb_get_labels"},
+                    "host_numa_binding": numa,
+                    "what": "per rank: nemb_load_shard(host pinned X shard + global CSR: H2D, device-side graph validation) + nemb_fit + nemb_get_labels_rows(own families); *_per_step = summed over the ranks"},
             "roofline": {"bound": "hbm", "kernel": "k_density_tma (E-step Bernoulli log-likelihood, popcount path)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

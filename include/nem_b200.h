@@ -263,6 +263,9 @@ int nemb_fit_random_workers(nemb_handle *h, const nemb_options *opt, int n_start
 /* n = the GLOBAL number of families (every rank of a sharded fit holds all labels) */
 int nemb_get_posteriors(nemb_handle *h, float *t_out /*[n*k]*/);
 int nemb_get_labels(nemb_handle *h, int32_t *label_out /*[n]*/);   /* MAP, first maximum */
+/* the same for families [first, first + count) only -- a rank of a sharded fit reads back its
+ * own rows (nemb_shard_range) instead of the whole pangenome */
+int nemb_get_labels_rows(nemb_handle *h, int first, int count, int32_t *label_out /*[count]*/);
 
 /* loader products, for bit-exact packing / indexing tests */
 int nemb_get_dims(const nemb_handle *h, int *n, int *d, int *words_per_row, int *nwt,

@@ -368,10 +368,15 @@ class Engine:
         self._check(self.lib.nemb_get_posteriors(self.h, _p(out)))
         return out
 
-    def labels(self):
-        out = np.zeros(self.n, dtype=np.int32)
-        self._check(self.lib.nemb_get_labels(self.h, _p(out)))
-        return out
+    def labels(self, first: int = 0, count: int | None = None, out: np.ndarray | None = None):
+        """MAP labels of families [first, first + count) (default: all); `out` (int32, C order)
+        is reused when given -- a long-lived caller avoids a fresh 4N-byte array per call."""
+        count = self.n - first if count is None else count
+        if out is None:
+            out = np.empty(count, dtype=np.int32)
+        assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape[0] >= count
+        self._check(self.lib.nemb_get_labels_rows(self.h, int(first), int(count), _p(out)))
+        return out[:count]
 
     # ---- resample driver (include/nem_b200.h layer 4)
     def subsample_into(self, dst: "Engine", genome_mask, edge_presence_dev: int = 0):

@@ -1509,9 +1509,11 @@ int nemb_get_posteriors(nemb_handle *h, float *t_out)
     return NEMB_OK;
 }
 
-int nemb_get_labels(nemb_handle *h, int32_t *label_out)
+int nemb_get_labels_rows(nemb_handle *h, int first, int count, int32_t *label_out)
 {
     if (!h || !label_out || !h->k_alloc) return NEMB_E_ARG;
+    if (first < 0 || count < 0 || (int64_t)first + count > h->n_glob)
+        return fail(h, NEMB_E_ARG, "label rows [%d, %d) outside 0..%d", first, first + count, h->n_glob);
     CK(cudaSetDevice(h->device));
     uint8_t *src = h->d_lab[h->cur];
     int n = h->n_glob;
@@ -1520,17 +1522,24 @@ int nemb_get_labels(nemb_handle *h, int32_t *label_out)
         nemk_t_to_labels(h->stream, h->k_alloc, n, h->d_t[h->cur], src);
         CKK();
     }
-    if (h->h_lab_cap < (size_t)n) {      /* pinned staging, grow-only */
+    if (count == 0) return NEMB_OK;
+    if (h->h_lab_cap < (size_t)count) {      /* pinned staging, grow-only */
         if (h->h_lab_stage) cudaFreeHost(h->h_lab_stage);
         h->h_lab_stage = NULL; h->h_lab_cap = 0;
-        CK(cudaMallocHost((void **)&h->h_lab_stage, (size_t)n + 64));
-        h->h_lab_cap = (size_t)n + 64;
+        CK(cudaMallocHost((void **)&h->h_lab_stage, (size_t)count + 64));
+        h->h_lab_cap = (size_t)count + 64;
     }
     const uint8_t *tmp = h->h_lab_stage;
-    CK(cudaMemcpyAsync(h->h_lab_stage, src, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_lab_stage, src + first, (size_t)count, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < n; i++) label_out[i] = tmp[i] == 255 ? -1 : (int32_t)tmp[i];
+    for (int i = 0; i < count; i++) label_out[i] = tmp[i] == 255 ? -1 : (int32_t)tmp[i];
     return NEMB_OK;
+}
+
+int nemb_get_labels(nemb_handle *h, int32_t *label_out)
+{
+    if (!h) return NEMB_E_ARG;
+    return nemb_get_labels_rows(h, 0, h->n_glob, label_out);
 }
 
 /* n = rows this rank holds; depth = Gauss-Seidel DAG depth (builds the level schedule on first

@@ -59,6 +59,36 @@ def cut_edges(row_ptr: np.ndarray, col: np.ndarray, world: int) -> int:
     return int(np.count_nonzero(src // shard_len != col // shard_len))
 
 
+def bind_to_gpu_numa(gpu_index: int) -> dict:
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal CPU set), BEFORE it
+    allocates pinned host buffers: cudaHostAlloc places pages on the calling thread's NUMA node,
+    and on a two-socket 8-GPU box every rank that stages its shard on the wrong socket pulls it
+    over the inter-socket link -- measured: host->device 54 GB/s per GPU at 1-2 ranks, 23 GB/s at
+    8 ranks without binding.  Returns what was done (for the bench line); never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = ideal & allowed
+        info.update(ideal_cpus=len(ideal), allowed_cpus=len(allowed))
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus), first_cpu=min(cpus))
+        try:
+            info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+    except Exception as exc:                      # no NVML / restricted container: run unbound
+        info["error"] = f"{type(exc).__name__}: {exc}"[:120]
+    return info
+
+
 def exchange_unique_id(dist, src: int = 0, device=None) -> bytes:
     """Rank `src` draws the NCCL unique id; every rank returns the same 128 bytes."""
     import torch
