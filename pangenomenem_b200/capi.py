@@ -269,7 +269,7 @@ class Engine:
 
     def graph(self):
         dm = self.dims()
-        rp = np.zeros(dm["n"] + 1, dtype=np.int32)
+        rp = np.zeros(self.n + 1, dtype=np.int32)      # the GLOBAL graph, also on a row shard
         cl = np.zeros(dm["nnz"], dtype=np.int32)
         wg = np.zeros(dm["nnz"], dtype=np.float32)
         self._check(self.lib.nemb_get_graph(self.h, _p(rp), _p(cl), _p(wg)))

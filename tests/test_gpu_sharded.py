@@ -14,7 +14,7 @@ from conftest import make_case, rel_close
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
-def run_sharded(pg, world, theta, **kw):
+def run_sharded(pg, world, theta, check_graph=False, **kw):
     from pangenomenem_b200 import capi, sharded, synth
     xp = synth.pack_rows(pg.x)
     comms = capi.local_comms(world)
@@ -27,6 +27,10 @@ def run_sharded(pg, world, theta, **kw):
             p = sharded.plan(pg.n, world, rank)
             fit = sharded.fit_sharded(eng, xp[p.rows], pg.n, pg.d, pg.row_ptr, pg.col, pg.wgt, theta,
                                       rank, world, **kw)
+            if check_graph:                      # the CSR as resident on this rank
+                rp, cl, wg = eng.graph()
+                assert np.array_equal(rp, pg.row_ptr) and np.array_equal(cl, pg.col)
+                assert np.array_equal(wg, pg.wgt)
             out[rank] = (fit, eng.labels(), eng.posteriors())
             eng.close()
         except Exception as exc:  # a dead rank would deadlock the others at the next barrier
@@ -97,6 +101,22 @@ def test_sharded_para_update(oracle, algo, disp):
             assert rel_close(fit.disp, ref.disp, 1e-6) and rel_close(fit.prop, ref.prop, 1e-6)
         for key in "UDL":
             assert rel_close(fit.crit[key], ref.crit[key], 1e-6), key
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_graph_upload_in_slices(oracle, world, monkeypatch):
+    """The replicated graph goes up in one slice per rank + an all-gather (nem_fit.c
+    upload_replicated) once it is large; forced here for small arrays with lengths that do not
+    divide by the rank count: the resident CSR and the fit must be what the plain upload gives."""
+    monkeypatch.setenv("NEM_B200_SLICED_UPLOAD_MIN", "1")
+    pg = make_case(5003, 40, seed=14)
+    theta = oracle.default_theta(3, pg.d)
+    kw = dict(k=3, algo="ncem", update="seq", disp="sk_", prop="pk", beta=0.5, it_max=50)
+    ref = oracle.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, **kw).fit(*theta)
+    for fit, lab, _ in run_sharded(pg, world, theta, check_graph=True, **kw):
+        assert fit.status == 0 and fit.iters == ref.iters
+        assert np.array_equal(lab, ref.label)
+        assert np.array_equal(fit.disp, ref.disp)
 
 
 def test_sharded_psgrad(oracle):
