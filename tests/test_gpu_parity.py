@@ -384,6 +384,25 @@ def test_margin_cache_is_exact_on_long_fits(engine, oracle, graph, beta, disp, m
         assert got.n_ties == ref.n_ties and got.n_allnul == ref.n_allnul
 
 
+def test_label_rows_getter(engine, oracle):
+    """nemb_get_labels_rows: any row range equals the slice of the full read-back; ranges outside
+    the pangenome are refused; a caller-owned buffer is filled in place."""
+    from pangenomenem_b200 import capi
+    pg = make_case(3001, 40, seed=31)
+    engine.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
+    engine.fit(*oracle.default_theta(3, pg.d), k=3, algo="ncem", beta=0.5, it_max=20)
+    full = engine.labels()
+    assert full.shape == (pg.n,) and full.min() >= 0 and full.max() <= 2
+    for first, count in [(0, 1), (1, 31), (1000, 2001), (3000, 1), (17, 0)]:
+        assert np.array_equal(engine.labels(first, count), full[first:first + count])
+    buf = np.full(64, -7, dtype=np.int32)
+    got = engine.labels(100, 50, out=buf)
+    assert np.array_equal(got, full[100:150]) and np.all(buf[50:] == -7)
+    for first, count in [(-1, 5), (3000, 2), (0, pg.n + 1)]:
+        with pytest.raises(capi.NemError):
+            engine.labels(first, count)
+
+
 @pytest.mark.parametrize("graph,beta", [("pangenome", 0.5), ("chain", 2.0), ("random", 1.0)])
 def test_chain_chasing_is_exact(engine, oracle, graph, beta, monkeypatch):
     """Fix-up rounds: the thread that changed a site's label goes on with the reader it claimed
