@@ -20,6 +20,7 @@
 #include "nem_io.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -120,6 +121,55 @@ static int map_status(int nemb)
     }
 }
 
+/* ------------------------------------------------------------------ engine handle of nem()
+ * PPanGGOLiN calls nem() again and again from one process (the chunk loop ppanggolin.py:1045-1095,
+ * the evolution-curve workers command_line.py:262-281).  Creating an engine per call costs more
+ * than the fit itself (device buffers, pinned status blocks, streams: ~45 ms of an 81 ms call on
+ * 100 000 x 500), so one engine per process and device is kept between calls -- its buffers are
+ * grow-only.  A second concurrent call (threads) or a call from a forked child gets a private
+ * engine for the call.  NEM_B200_NO_HANDLE_CACHE=1 restores create/destroy per call. */
+static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
+static nemb_handle *g_cache_h;
+static int g_cache_dev = -2, g_cache_busy;
+static pid_t g_cache_pid;
+
+static int acquire_engine(int device, nemb_handle **out, int *cached)
+{
+    *cached = 0;
+    if (device < 0) {                                   /* same rule as nemb_create */
+        const char *env = getenv("NEM_B200_DEVICE");
+        if (env && *env) device = atoi(env);
+    }
+    if (!getenv("NEM_B200_NO_HANDLE_CACHE")) {
+        pthread_mutex_lock(&g_cache_mu);
+        if (g_cache_h && g_cache_pid != getpid()) {     /* forked child: the parent's context is */
+            g_cache_h = NULL; g_cache_busy = 0;         /* not ours -- forget it, do not free it */
+        }
+        if (!g_cache_busy) {
+            if (g_cache_h && g_cache_dev != device) { nemb_destroy(g_cache_h); g_cache_h = NULL; }
+            int rc = NEMB_OK;
+            if (!g_cache_h) {
+                rc = nemb_create(&g_cache_h, device);
+                g_cache_dev = device; g_cache_pid = getpid();
+            }
+            if (rc == NEMB_OK) { g_cache_busy = 1; *out = g_cache_h; *cached = 1; }
+            pthread_mutex_unlock(&g_cache_mu);
+            return rc;
+        }
+        pthread_mutex_unlock(&g_cache_mu);
+    }
+    return nemb_create(out, device);
+}
+
+static void release_engine(nemb_handle *h, int cached)
+{
+    if (!h) return;
+    if (!cached) { nemb_destroy(h); return; }
+    pthread_mutex_lock(&g_cache_mu);
+    g_cache_busy = 0;
+    pthread_mutex_unlock(&g_cache_mu);
+}
+
 int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float beta,
                 const char *convergence, const float convergence_th, const char *format,
                 const int it_max, const int dolog, const char *model_family,
@@ -209,6 +259,7 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
     float *t = NULL;
     int32_t *label = NULL;
     nemb_handle *h = NULL;
+    int h_cached = 0;
     int code = EXIT_OK_, flag = 1, max_neigh = 0;
     log_ctx L;
     memset(&L, 0, sizeof L);
@@ -252,7 +303,7 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
     fprintf(ferr, "\n");
 
     /* ---- engine */
-    if ((rc = nemb_create(&h, ex.device)) != NEMB_OK) { code = map_status(rc); goto done; }
+    if ((rc = acquire_engine(ex.device, &h, &h_cached)) != NEMB_OK) { code = map_status(rc); goto done; }
     if ((rc = nemb_load_packed(h, n, d, wpr, xp, row_ptr, col, wgt)) != NEMB_OK) {
         fprintf(ferr, "%s\n", nemb_last_error(h));
         code = map_status(rc); goto done;
@@ -348,7 +399,7 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
 
 done:
     if (L.flog) fclose(L.flog);
-    if (h) nemb_destroy(h);
+    release_engine(h, h_cached);
     free(xp); free(row_ptr); free(col); free(wgt); free(prop); free(center); free(disp);
     free(t); free(label);
     return finish(ferr, own_err, code);

@@ -381,6 +381,155 @@ bad:
 #undef NEED_TOKEN
 }
 
+/* ------------------------------------------------------------------ .nei, line-structured fast path
+ * PPanGGOLiN writes one record per line (ppanggolin.py:862-888).  When every non-blank line holds
+ * exactly one record -- id, nb, nb neighbour ids and, in a weighted file, nb weights -- the lines
+ * are split over the host threads; each thread parses its lines into its own pool and the pools
+ * are merged in file order ("the last record of a point wins", like the sequential reader).  Any
+ * line that does not fit (a record spanning lines, a short line, a bad token) makes the caller
+ * fall back to the sequential token reader, which has the reference's fscanf semantics and
+ * reports the error. */
+typedef struct { int32_t id, nv; int64_t off; } nei_rec;
+typedef struct {
+    const char *beg, *end; int n, weighted;
+    nei_rec *rec; size_t nrec, rec_cap;
+    int32_t *pc; float *pw; size_t used, cap;
+    int fallback;
+} nei_job;
+
+static void *nei_worker(void *arg)
+{
+    nei_job *j = arg;
+    const char *p = j->beg;
+    while (p < j->end) {
+        const char *eol = memchr(p, '\n', (size_t)(j->end - p));
+        if (!eol) eol = j->end;
+        cursor c = {p, eol, p, 0};                    /* p, end, base, len: one line */
+        p = eol < j->end ? eol + 1 : j->end;
+        const char *t; size_t len; long id, nb;
+        if (!next_token(&c, &t, &len)) continue;      /* blank line */
+        if (!tok_int(t, len, &id) || !next_token(&c, &t, &len) || !tok_int(t, len, &nb) ||
+            id < 1 || id > j->n || nb < 0 || nb > (1 << 28)) { j->fallback = 1; return NULL; }
+        if (j->used + (size_t)nb > j->cap) {
+            size_t cap = j->cap ? j->cap : 4096;
+            while (j->used + (size_t)nb > cap) cap *= 2;
+            int32_t *pc = realloc(j->pc, cap * sizeof(int32_t));
+            float *pw = pc ? realloc(j->pw, cap * sizeof(float)) : NULL;
+            if (pc) j->pc = pc;
+            if (pw) j->pw = pw;
+            if (!pc || !pw) { j->fallback = 1; return NULL; }
+            j->cap = cap;
+        }
+        size_t s0 = j->used;
+        for (long q = 0; q < nb; q++) {
+            long nbr;
+            if (!next_token(&c, &t, &len) || !tok_int(t, len, &nbr)) { j->fallback = 1; return NULL; }
+            j->pc[s0 + q] = nbr < INT32_MIN || nbr > INT32_MAX ? 0 : (int32_t)nbr;
+            j->pw[s0 + q] = 1.0f;
+        }
+        if (j->weighted)
+            for (long q = 0; q < nb; q++) {
+                float w;
+                if (!next_token(&c, &t, &len) || !tok_float(t, len, &w)) { j->fallback = 1; return NULL; }
+                j->pw[s0 + q] = w;
+            }
+        if (next_token(&c, &t, &len)) { j->fallback = 1; return NULL; }   /* trailing tokens */
+        size_t nv = 0;
+        for (long q = 0; q < nb; q++) {
+            int32_t nbr = j->pc[s0 + q]; float w = j->pw[s0 + q];
+            if (nbr >= 1 && nbr <= j->n && w != 0.0f) { j->pc[s0 + nv] = nbr - 1; j->pw[s0 + nv] = w; nv++; }
+        }
+        if (j->nrec == j->rec_cap) {
+            size_t cap = j->rec_cap ? 2 * j->rec_cap : 4096;
+            nei_rec *r = realloc(j->rec, cap * sizeof(nei_rec));
+            if (!r) { j->fallback = 1; return NULL; }
+            j->rec = r; j->rec_cap = cap;
+        }
+        j->rec[j->nrec++] = (nei_rec){(int32_t)id, (int32_t)nv, (int64_t)s0};
+        j->used = s0 + nv;
+    }
+    return NULL;
+}
+
+/* returns 1 when the CSR was built, 0 when the caller must use the sequential reader, < 0 = -NEMB_E_* */
+static int nei_read_lines(const char *beg, const char *end, int n, int weighted, int n_threads,
+                          int32_t **row_ptr_out, int32_t **col_out, float **wgt_out, int *max_neigh)
+{
+    if (n_threads > 64) n_threads = 64;
+    if (n_threads < 1 || end - beg < (1 << 16)) n_threads = 1;
+    nei_job jobs[64];
+    pthread_t th[64];
+    int started[64] = {0};
+    const char *cut = beg;
+    for (int t = 0; t < n_threads; t++) {
+        const char *stop = end;
+        if (t + 1 < n_threads) {
+            stop = beg + (size_t)(end - beg) * (size_t)(t + 1) / (size_t)n_threads;
+            if (stop < cut) stop = cut;
+            const char *nl = memchr(stop, '\n', (size_t)(end - stop));
+            stop = nl ? nl + 1 : end;
+        }
+        memset(&jobs[t], 0, sizeof jobs[t]);
+        jobs[t].beg = cut; jobs[t].end = stop; jobs[t].n = n; jobs[t].weighted = weighted;
+        cut = stop;
+    }
+    for (int t = 1; t < n_threads; t++) started[t] = pthread_create(&th[t], NULL, nei_worker, &jobs[t]) == 0;
+    nei_worker(&jobs[0]);
+    for (int t = 1; t < n_threads; t++) {
+        if (started[t]) pthread_join(th[t], NULL);
+        else nei_worker(&jobs[t]);
+    }
+    int ret = 1;
+    for (int t = 0; t < n_threads; t++) if (jobs[t].fallback) ret = 0;
+    int32_t *rp = NULL, *cl = NULL; float *wg = NULL;
+    int32_t *last_t = NULL; int64_t *last_r = NULL;
+    if (ret == 1) {
+        last_t = malloc(sizeof(int32_t) * (size_t)n);
+        last_r = malloc(sizeof(int64_t) * (size_t)n);
+        rp = malloc(sizeof(int32_t) * ((size_t)n + 1));
+        if (!last_t || !last_r || !rp) ret = -NEMB_E_MEMORY;
+    }
+    if (ret == 1) {
+        for (int i = 0; i < n; i++) last_t[i] = -1;
+        for (int t = 0; t < n_threads; t++)
+            for (size_t r = 0; r < jobs[t].nrec; r++) {
+                int id = jobs[t].rec[r].id - 1;
+                last_t[id] = t; last_r[id] = (int64_t)r;
+            }
+        int64_t nnz = 0;
+        int mx = 0;
+        for (int i = 0; i < n; i++) {
+            rp[i] = (int32_t)nnz;
+            if (last_t[i] >= 0) {
+                int nv = jobs[last_t[i]].rec[last_r[i]].nv;
+                nnz += nv;
+                if (nv > mx) mx = nv;
+            }
+            if (nnz > 2147483647LL) { ret = -NEMB_E_FILE; break; }
+        }
+        if (ret == 1) {
+            rp[n] = (int32_t)nnz;
+            cl = malloc(sizeof(int32_t) * (size_t)(nnz ? nnz : 1));
+            wg = malloc(sizeof(float) * (size_t)(nnz ? nnz : 1));
+            if (!cl || !wg) ret = -NEMB_E_MEMORY;
+        }
+        if (ret == 1) {
+            for (int i = 0; i < n; i++) {
+                if (last_t[i] < 0) continue;
+                const nei_job *j = &jobs[last_t[i]];
+                const nei_rec *r = &j->rec[last_r[i]];
+                memcpy(cl + rp[i], j->pc + r->off, sizeof(int32_t) * (size_t)r->nv);
+                memcpy(wg + rp[i], j->pw + r->off, sizeof(float) * (size_t)r->nv);
+            }
+            *row_ptr_out = rp; *col_out = cl; *wgt_out = wg; *max_neigh = mx;
+            rp = NULL; cl = NULL; wg = NULL;
+        }
+    }
+    free(rp); free(cl); free(wg); free(last_t); free(last_r);
+    for (int t = 0; t < n_threads; t++) { free(jobs[t].rec); free(jobs[t].pc); free(jobs[t].pw); }
+    return ret;
+}
+
 /* ------------------------------------------------------------------ .nei -> CSR */
 int nemio_read_nei(const char *base, FILE *err, int n, int32_t **row_ptr_out, int32_t **col_out,
                    float **wgt_out, int *max_neigh, char *comment, int comment_len)
@@ -397,6 +546,17 @@ int nemio_read_nei(const char *base, FILE *err, int n, int32_t **row_ptr_out, in
     const char *t; size_t len; long v;
     int weighted = 0, rc = NEMB_OK;
     if (next_token(&c, &t, &len) && tok_int(t, len, &v)) weighted = v != 0;
+    {
+        long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+        int fast = nei_read_lines(c.p, c.end, n, weighted, ncpu > 16 ? 16 : (int)ncpu, row_ptr_out,
+                                  col_out, wgt_out, max_neigh);
+        if (fast == 1) { unmap_file(&c); return NEMB_OK; }
+        if (fast < 0) {
+            if (fast == -NEMB_E_FILE) fprintf(err, "neighbourhood too large\n");
+            unmap_file(&c);
+            return -fast;
+        }
+    }
 
     /* records land in a scratch pool; start[i]/cnt[i] point at the LAST record of point i */
     size_t cap = 1 << 16, used = 0;

@@ -177,3 +177,45 @@ def test_dat_fast_path_validates_every_byte(tmp_path, capi):
     open(base + ".dat", "wb").write(bytes(bad))
     with pytest.raises(capi.NemError):
         capi.read_files(base, k=0)
+
+
+def test_nei_threaded_reader_matches_the_sequential_semantics(tmp_path, capi):
+    """.nei files above 64 KB are parsed line by line on several threads (nem_io.c
+    nei_read_lines); whatever the fast path cannot prove line-structured goes to the sequential
+    token reader (the reference's fscanf semantics, ReadPtsNeighs nem_exe.c:1342-1478).  Shuffled
+    records, repeated records (the last one wins), a record broken over two lines and a short
+    record must all behave as before."""
+    pg = make_case(20000, 12, seed=6, graph="pangenome")
+    base = _write(tmp_path, pg)
+    assert os.path.getsize(base + ".nei") > (1 << 16)
+    hp = capi.read_files(base, k=0)
+    assert np.array_equal(hp["row_ptr"], pg.row_ptr) and np.array_equal(hp["col"], pg.col)
+    assert np.array_equal(hp["wgt"], pg.wgt)
+    lines = open(base + ".nei").read().split("\n")
+    head, recs = lines[0], [l for l in lines[1:] if l]
+    rng = np.random.default_rng(0)
+    shuffled = [recs[i] for i in rng.permutation(len(recs))]
+    open(base + ".nei", "w").write("\n".join([head] + shuffled) + "\n")
+    hp = capi.read_files(base, k=0)
+    assert np.array_equal(hp["row_ptr"], pg.row_ptr) and np.array_equal(hp["col"], pg.col)
+    # a stale first record for three points: the later (real) record wins, wherever the threads cut
+    stale = ["5\t1\t6\t9", "12000\t2\t1\t2\t3\t3", "19999\t0"]
+    open(base + ".nei", "w").write("\n".join([head] + stale + ["", "  "] + recs) + "\n")
+    hp = capi.read_files(base, k=0)
+    assert np.array_equal(hp["row_ptr"], pg.row_ptr) and np.array_equal(hp["wgt"], pg.wgt)
+    # one record broken over two lines: not line-structured -> sequential reader, same CSR
+    k = 7000
+    toks = recs[k].split("\t")
+    broken = recs[:k] + ["\t".join(toks[:3]), "\t".join(toks[3:])] + recs[k + 1:]
+    open(base + ".nei", "w").write("\n".join([head] + broken) + "\n")
+    hp = capi.read_files(base, k=0)
+    assert np.array_equal(hp["row_ptr"], pg.row_ptr) and np.array_equal(hp["col"], pg.col)
+    # a record that announces more neighbours than it lists swallows the next line's tokens in
+    # the reference too; here it ends the file early -> error, not a crash
+    toks = recs[-1].split("\t")
+    short = recs[:-1] + ["\t".join(toks[:2] + toks[2:3])]
+    if int(toks[1]) > 1:
+        open(base + ".nei", "w").write("\n".join([head] + short) + "\n")
+        with pytest.raises(capi.NemError) as ei:
+            capi.read_files(base, k=0)
+        assert ei.value.code == 3
