@@ -813,12 +813,17 @@ static int read_status(nemb_handle *h)
 
 /* jacobi round 0 left the first work list in list 0 / counter 0: three grid-wide rounds, then
  * one CTA walks the tail to exhaustion (and leaves the four counters at 0) */
-enum { GRID_ROUNDS = 3, SHORT_LIST = 32768, CHASE_LINKS = 64 };
+enum { GRID_ROUNDS = 3, SHORT_LIST = 32768, MEDIUM_LIST = 32768, CHASE_LINKS = 64 };
 static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, uint8_t *out,
                          const int32_t *rp, const int32_t *skip, const nemk_iter_end_args *fused)
 {
-    /* few labels moved last iteration => the work lists are short: the tail cluster walks them all */
-    int grid_rounds = (h->last_changed >= 0 && h->last_changed < SHORT_LIST) ? 0 : GRID_ROUNDS;
+    /* few labels moved last iteration => the work lists are short: the tail cluster (8 CTAs) walks
+     * them all; a medium list gets ONE grid-wide round first (the whole GPU takes the bulk, the
+     * tail the rest); long or unknown lists get GRID_ROUNDS */
+    static int medium = -1;
+    if (medium < 0) { const char *e = getenv("NEM_B200_MEDIUM_LIST"); medium = e && *e ? atoi(e) : MEDIUM_LIST; }
+    int grid_rounds = (h->last_changed >= 0 && h->last_changed < SHORT_LIST)
+                          ? (h->last_changed >= medium ? 1 : 0) : GRID_ROUNDS;
     for (int r = 0; r < grid_rounds; r++)
         nemk_sweep_ncem_fixup_round(h->stream, k, h->row0, h->n, lpsrc(h), rp, h->d_col, h->d_wgt,
                                     beta, in, out, h->d_dirty, h->d_wl[0], h->d_wl[1],

@@ -735,20 +735,38 @@ static __device__ __forceinline__ void store_margin(const nemk_margins &mg, int 
 // Speculative sequential sweep bookkeeping: every site that READS i and is visited later
 // (larger index) must be re-evaluated when i's label moves.  dirty[] de-duplicates, wl[] is
 // the work list of the next round.
+// The claims (atomicExch on dirty[]) of four readers are issued back to back and only then
+// looked at, and the work-list slots of a group come from ONE atomicAdd: a thread pays one L2
+// round trip per four readers instead of two per reader (the fix-up tail is a chain of such
+// dependent round trips).
 static __device__ __forceinline__ void mark_readers(int i, const int32_t *__restrict__ rrow_ptr,
                                                     const int32_t *__restrict__ rcol,
                                                     int32_t *dirty, int32_t *wl, int32_t *wl_count,
                                                     int row0, int row1, uint8_t *stale_next = nullptr) {
     int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
-    for (int e = lo; e < hi; e++) {
-        int j = rcol[e];
-        // readers visited before i (or i itself) keep this sweep's evaluation, which saw i's OLD
-        // label: their cached margin is void for the next sweep
-        if (stale_next && j <= i && j >= row0 && j < row1) stale_next[j] = 1;
-        // only sites this rank owns ([row0,row1), the whole graph on one GPU) are queued here;
-        // the owner of a remote reader queues it when it sees i's new label (k_mark_remote)
-        if (j > i && j >= row0 && j < row1 && atomicExch(&dirty[j], 1) == 0)
-            wl[atomicAdd(wl_count, 1)] = j;
+    for (int e = lo; e < hi; e += 4) {
+        int j[4], was[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) j[q] = e + q < hi ? rcol[e + q] : -1;
+        int nclaim = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            // only sites this rank owns ([row0,row1), the whole graph on one GPU) are queued here;
+            // the owner of a remote reader queues it when it sees i's new label (k_mark_remote)
+            const bool own = j[q] >= 0 && j[q] >= row0 && j[q] < row1;
+            // readers visited before i (or i itself) keep this sweep's evaluation, which saw i's
+            // OLD label: their cached margin is void for the next sweep
+            if (stale_next && own && j[q] <= i) stale_next[j[q]] = 1;
+            was[q] = (own && j[q] > i) ? atomicExch(&dirty[j[q]], 1) : 1;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) nclaim += was[q] == 0;
+        if (nclaim) {
+            int base = atomicAdd(wl_count, nclaim);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (was[q] == 0) wl[base++] = j[q];
+        }
     }
 }
 
@@ -1048,14 +1066,30 @@ static __device__ __forceinline__ int mark_readers_keep_one(int i, const int32_t
                                                             int32_t *dirty, int32_t *wl, int32_t *wl_count,
                                                             int row0, int row1, uint8_t *stale_next) {
     int lo = rrow_ptr[i], hi = rrow_ptr[i + 1], keep = -1;
-    for (int e = lo; e < hi; e++) {
-        int j = rcol[e];
-        if (stale_next && j <= i && j >= row0 && j < row1) stale_next[j] = 1;
-        if (j > i && j >= row0 && j < row1 && atomicExch(&dirty[j], 1) == 0) {
-            if (keep < 0) keep = j;
-            else if (j < keep) { wl[atomicAdd(wl_count, 1)] = keep; keep = j; }
-            else wl[atomicAdd(wl_count, 1)] = j;
+    for (int e = lo; e < hi; e += 4) {
+        int j[4], was[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) j[q] = e + q < hi ? rcol[e + q] : -1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool own = j[q] >= 0 && j[q] >= row0 && j[q] < row1;
+            if (stale_next && own && j[q] <= i) stale_next[j[q]] = 1;
+            was[q] = (own && j[q] > i) ? atomicExch(&dirty[j[q]], 1) : 1;
         }
+        int cand = keep, nclaim = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (was[q] == 0) { nclaim++; if (cand < 0 || j[q] < cand) cand = j[q]; }
+        // everything claimed so far except the lowest index goes to the work list
+        int nq = nclaim + (keep >= 0) - (cand >= 0);
+        if (nq > 0) {
+            int base = atomicAdd(wl_count, nq);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (was[q] == 0 && j[q] != cand) wl[base++] = j[q];
+            if (keep >= 0 && keep != cand) wl[base++] = keep;
+        }
+        keep = cand;
     }
     return keep;
 }
