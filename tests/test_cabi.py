@@ -113,3 +113,58 @@ def test_cython_dropin_module_has_the_reference_interface(tmp_path):
     finally:
         sys.path.pop(0)
         sys.modules.pop("nem", None)
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The Python bindings (capi.py) restate the structs of include/nem_b200.h by hand: compile a
+    probe against the header and compare sizes and the offsets of the last fields, so that a field
+    added on one side only cannot go unnoticed."""
+    import ctypes as C
+    import subprocess
+    from pangenomenem_b200 import capi
+    src = tmp_path / "probe.c"
+    src.write_text(r'''
+#include "nem_b200.h"
+#include <stddef.h>
+#include <stdio.h>
+int main(void) {
+    printf("%zu %zu %zu %zu\n", sizeof(nemb_options), offsetof(nemb_options, beta_mode),
+           offsetof(nemb_options, grad_step), offsetof(nemb_options, reserved));
+    printf("%zu %zu %zu %zu\n", sizeof(nemb_result), offsetof(nemb_result, n_kept),
+           offsetof(nemb_result, beta), offsetof(nemb_result, n_beta_tested));
+    printf("%zu %zu %zu %zu\n", sizeof(nem_b200_extra), offsetof(nem_b200_extra, seed),
+           offsetof(nem_b200_extra, beta_mode), offsetof(nem_b200_extra, heu_lloss));
+    printf("%zu %zu\n", sizeof(nemb_beta_heuristic), sizeof(nemb_batch_stats));
+    printf("%zu %zu\n", sizeof(nemb_host_problem), offsetof(nemb_host_problem, disp));
+    return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    rows = [[int(v) for v in line.split()] for line in
+            subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()]
+    o, r, e = capi.Options, capi.Result, capi.Extra
+    assert rows[0] == [C.sizeof(o), o.beta_mode.offset, o.grad_step.offset, o.reserved.offset]
+    assert rows[1] == [C.sizeof(r), r.n_kept.offset, r.beta.offset, r.n_beta_tested.offset]
+    assert rows[2] == [C.sizeof(e), e.seed.offset, e.beta_mode.offset, e.heu_lloss.offset]
+    assert rows[3] == [C.sizeof(capi.BetaHeuristic), C.sizeof(capi.BatchStats)]
+    assert rows[4] == [C.sizeof(capi.HostProblem), capi.HostProblem.disp.offset]
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference on the CPU-runnable config: one JSON line with the keys the
+    driver reads (runs the compiled reference when oracle/_ref exists, else the C port)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cp = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
+                         "--workload", "c1", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=600)
+    assert cp.returncode == 0, cp.stderr[-2000:]
+    line = json.loads(cp.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["metric"] == "NEM family-iterations/s" and line["unit"] == "family-iterations/s"
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
