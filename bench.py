@@ -581,6 +581,17 @@ def main_ours(args):
     barrier()
     e_wall = time.time() - e0
     e2e_same = bool(np.array_equal(lab_host, lab_resident[plan.rows]))
+    # ---- full-size property check (untimed): a converged ncem fit is a fixed point of NemAlgo --
+    #      restarted from its own partition (nemb_fit_from_partition, the reference's INIT_FILE
+    #      branch) it must stop after ONE iteration with every label unchanged
+    props = None
+    if world == 1:
+        f2 = eng.fit(*theta0, t_init=eng.posteriors(K), **opts)
+        lab2 = eng.labels()
+        props = {"refit_from_final_partition": {"iters": f2.iters, "converged": bool(f2.converged),
+                                                "labels_unchanged": bool(np.array_equal(lab2, lab_resident))},
+                 "class_sizes": np.bincount(lab_resident, minlength=K).tolist(),
+                 "class_sizes_sum_to_n": bool(np.bincount(lab_resident, minlength=K).sum() == n)}
     depth = eng.dims()["depth"] if mode != "sharded" else 0      # builds the level schedule: untimed
     h2d = x_bytes + (0 if col is None else (n_glob + 1) * 4 + nnz * 8) + (K + 2 * K * d) * 4
     d2h = plan.n_loc + (K + 2 * K * d) * 4 + 256
@@ -672,6 +683,8 @@ def main_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if props is not None:
+            line["full_size_properties"] = props
         print(json.dumps(line))
     eng.close()
     if comm:
