@@ -525,6 +525,7 @@ def main_ours(args):
 
     for _ in range(args.warmup):
         one_fit(False)
+    lab_warm = eng.labels()              # the timed fits below must reproduce these labels
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -590,6 +591,7 @@ def main_ours(args):
         lab2 = eng.labels()
         props = {"refit_from_final_partition": {"iters": f2.iters, "converged": bool(f2.converged),
                                                 "labels_unchanged": bool(np.array_equal(lab2, lab_resident))},
+                 "labels_repeatable_across_fits": bool(np.array_equal(lab_warm, lab_resident)),
                  "class_sizes": np.bincount(lab_resident, minlength=K).tolist(),
                  "class_sizes_sum_to_n": bool(np.bincount(lab_resident, minlength=K).sum() == n)}
     depth = eng.dims()["depth"] if mode != "sharded" else 0      # builds the level schedule: untimed

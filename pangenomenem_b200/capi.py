@@ -10,7 +10,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libnem_b200.so")
+# NEM_B200_LIB: an alternative build of the same library (tuning experiments); never a fallback
+LIB_PATH = os.environ.get("NEM_B200_LIB") or os.path.join(PKG, "libnem_b200.so")
 
 ALGO = {"nem": 0, "ncem": 1}
 UPDATE = {"seq": 0, "para": 1}

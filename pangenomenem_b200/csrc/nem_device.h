@@ -50,9 +50,6 @@ typedef struct {
     uint8_t *stale_cur;    /* [lab_len] set during the previous sweep, consumed (cleared) by this one */
     uint8_t *stale_next;   /* [lab_len] set by this sweep's label changes */
     int32_t  on;           /* host: this sweep may skip (same beta as the previous sweep) */
-    int32_t  chase;        /* fix-up rounds: a thread whose site changed label goes on with the lowest
-                              later reader it claimed instead of queueing it for the next round, for
-                              at most this many links (0 = off).  Independent of m. */
 } nemk_margins;
 
 /* Device scalars of one sweep / one iteration (host reads them back in one copy). */

@@ -813,7 +813,7 @@ static int read_status(nemb_handle *h)
 
 /* jacobi round 0 left the first work list in list 0 / counter 0: three grid-wide rounds, then
  * one CTA walks the tail to exhaustion (and leaves the four counters at 0) */
-enum { GRID_ROUNDS = 3, SHORT_LIST = 32768, MEDIUM_LIST = 32768, CHASE_LINKS = 64 };
+enum { GRID_ROUNDS = 3, SHORT_LIST = 32768, MEDIUM_LIST = 32768 };
 static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, uint8_t *out,
                          const int32_t *rp, const int32_t *skip, const nemk_iter_end_args *fused)
 {
@@ -849,7 +849,6 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
     *flipped = 0;
     if (status_read) *status_read = 0;
     memset(&h->mg, 0, sizeof h->mg);
-    h->mg.chase = getenv("NEM_B200_NO_CHASE") ? 0 : CHASE_LINKS;
     CK(cudaMemsetAsync(&h->d_status->cnt, 0, sizeof(nemk_counters), h->stream));
     STAGE_BEGIN(ST_SWEEP);
     if (o->algo == NEMB_ALGO_NCEM) {

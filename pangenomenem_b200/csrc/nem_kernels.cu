@@ -13,6 +13,14 @@
 // tensor cores by design (K=3 gives ~3 popc per 4 bytes of X).
 #include "nem_device.h"
 
+// compile-time tuning knobs (defaults = the measured configuration)
+#ifndef FX_CLUSTER
+#define FX_CLUSTER 8   // CTAs of the fix-up tail's cluster (> 8 needs the non-portable opt-in)
+#endif
+#ifndef JAC_MINB
+#define JAC_MINB 1     // min resident CTAs per SM asked of the dense sweep round (register cap)
+#endif
+
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <math_constants.h>
@@ -902,7 +910,7 @@ static __device__ __forceinline__ void mark_readers_warp(int i, const int32_t *_
 // Rows [row0, row0+n_loc) of the GLOBAL graph are this rank's (row0 = 0, n_loc = N on one GPU);
 // labels, CSR, dirty flags and work lists are indexed by global family id, logpf by local row.
 template <int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, JAC_MINB)
 k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
                     const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                     const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_in,
@@ -1059,48 +1067,13 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
 // the fixed point reached is the sequential sweep's result whatever the interleaving.
 // The first rounds (long work lists) run grid-wide, one launch per round; the tail runs in one
 // CTA that loops until the list is empty.
-// mark_readers for the chase (below): the LOWEST later reader this call claimed (dirty 0 -> 1) is
-// handed back instead of being queued; every other claimed reader goes to the work list.
-static __device__ __forceinline__ int mark_readers_keep_one(int i, const int32_t *__restrict__ rrow_ptr,
-                                                            const int32_t *__restrict__ rcol,
-                                                            int32_t *dirty, int32_t *wl, int32_t *wl_count,
-                                                            int row0, int row1, uint8_t *stale_next) {
-    int lo = rrow_ptr[i], hi = rrow_ptr[i + 1], keep = -1;
-    for (int e = lo; e < hi; e += 4) {
-        int j[4], was[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) j[q] = e + q < hi ? rcol[e + q] : -1;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const bool own = j[q] >= 0 && j[q] >= row0 && j[q] < row1;
-            if (stale_next && own && j[q] <= i) stale_next[j[q]] = 1;
-            was[q] = (own && j[q] > i) ? atomicExch(&dirty[j[q]], 1) : 1;
-        }
-        int cand = keep, nclaim = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (was[q] == 0) { nclaim++; if (cand < 0 || j[q] < cand) cand = j[q]; }
-        // everything claimed so far except the lowest index goes to the work list
-        int nq = nclaim + (keep >= 0) - (cand >= 0);
-        if (nq > 0) {
-            int base = atomicAdd(wl_count, nq);
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (was[q] == 0 && j[q] != cand) wl[base++] = j[q];
-            if (keep >= 0 && keep != cand) wl[base++] = keep;
-        }
-        keep = cand;
-    }
-    return keep;
-}
-
-// Re-evaluate site i.  CHASE (mg.chase > 0): in a pangenome the later readers of a site are its
-// chromosome successors, so a label change propagates along chains i -> i+1 -> ...; walking such a
-// chain one link per ROUND costs a grid/cluster barrier (~3 us) per link.  Any interleaving of the
-// re-evaluations reaches the same fixed point as long as the dirty-flag protocol holds (clear
-// before reading, publish before claiming readers), so the thread that changed i may evaluate a
-// reader it has just claimed right away: the chain is walked at the latency of its dependent
-// loads only.  Hubs and links beyond mg.chase are queued as before.
+// Re-evaluate site i.  NOTE (kept as a warning): letting the thread that changed i go straight on
+// with a reader it has just claimed ("chasing" the chain i -> i+1 -> ... inside one round) is NOT
+// safe: the claimed reader may be in the middle of its evaluation by another thread of the same
+// round (it cleared its flag before reading), and the two evaluations would race on lab_cur[j] --
+// the stale one can land last and nobody re-queues j.  Rounds separated by a barrier are what
+// guarantees that a site is evaluated by one thread at a time; measured, the chase bought nothing
+// anyway (the tail is bound by the dependent loads of a link, not by the barriers).
 template <int KT>
 static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row1,
                                                  const nemk_lpsrc &lps,
@@ -1113,37 +1086,23 @@ static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row
                                                  const int32_t *__restrict__ rrow_ptr,
                                                  const int32_t *__restrict__ rcol,
                                                  const nemk_margins &mg, double thr_store) {
-    int delta = 0;
-    for (int link = 0;; link++) {
-        atomicExch(&dirty[i], 0);
-        __threadfence();
-        double ctx[KT];
-        ctx_labels<KT>(K, i, row_ptr, col, wgt,
-                       [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
-        int flags;
-        double lpv[KT], margin;
-        load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
-        int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
-        store_margin(mg, i - row0, margin, thr_store);   // the LAST evaluation of a site is its final one
-        int was = __ldcg(lab_cur + i);
-        if (km == was) return delta;
-        lab_cur[i] = (uint8_t)km;
-        __threadfence();
-        int old = lab_old[i];
-        delta += (km != old) - (was != old);
-        if (link >= mg.chase) {
-            mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1, mg.stale_next);
-            return delta;
-        }
-        int nxt = mark_readers_keep_one(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1,
-                                        mg.stale_next);
-        if (nxt < 0) return delta;
-        if (row_ptr[nxt + 1] - row_ptr[nxt] > HEAVY_DEG) {   // hubs are evaluated by a whole warp
-            next_list[atomicAdd(next_cnt, 1)] = nxt;
-            return delta;
-        }
-        i = nxt;
-    }
+    atomicExch(&dirty[i], 0);
+    __threadfence();
+    double ctx[KT];
+    ctx_labels<KT>(K, i, row_ptr, col, wgt,
+                   [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
+    int flags;
+    double lpv[KT], margin;
+    load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+    int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
+    store_margin(mg, i - row0, margin, thr_store);   // the LAST evaluation of a site is its final one
+    int was = __ldcg(lab_cur + i);
+    if (km == was) return 0;
+    lab_cur[i] = (uint8_t)km;
+    __threadfence();
+    mark_readers(i, rrow_ptr, rcol, dirty, next_list, next_cnt, row0, row1, mg.stale_next);
+    int old = lab_old[i];
+    return (km != old) - (was != old);
 }
 
 // the same for a hub, by a whole warp (every lane returns the same delta)
@@ -1251,7 +1210,7 @@ static __device__ void iter_end_body(int world, const nemk_counters *cnt_all,
 // Tail of the fix-up rounds in ONE launch: a thread-block cluster of FX_CLUSTER CTAs loops over the
 // rounds with a hardware cluster barrier between them (release/acquire at cluster scope, after a
 // device fence for the label/work-list stores) until the work list is empty.
-#define FX_CLUSTER 8
+/* FX_CLUSTER: CTAs of the cluster (compile-time knob, top of the file) */
 template <int KT>
 __global__ void __cluster_dims__(FX_CLUSTER, 1, 1) __launch_bounds__(1024)
 k_sweep_ncem_fixup(int K, int row0, int row1, const nemk_lpsrc lps,
@@ -2587,6 +2546,9 @@ extern "C" void nemk_sweep_ncem_fixup(nemk_stream s, int k, int row0, int n_loc,
         note_launch();
         return;
     }
+#if FX_CLUSTER > 8
+    DISPATCH_K(k, (cudaFuncSetAttribute(k_sweep_ncem_fixup<KT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)));
+#endif
     DISPATCH_K(k, (k_sweep_ncem_fixup<KT><<<FX_CLUSTER, 1024, 0, S(s)>>>(
                       k, row0, row0 + n_loc, lps, row_ptr, col, wgt, beta, lab_old, lab_cur, dirty,
                       wl_a, wl_b, wl_cnt, round, rrow_ptr, rcol, cnt, skip, fa, mg)));
