@@ -20,6 +20,14 @@
 #ifndef JAC_MINB
 #define JAC_MINB 1     // min resident CTAs per SM asked of the dense sweep round (register cap)
 #endif
+#ifndef JAC_SPT
+#define JAC_SPT 4      // sub-tiles of 256 sites per CTA of the dense sweep round (sites per thread)
+#endif
+#ifndef JAC_MINB_SMALLK
+#define JAC_MINB_SMALLK 6   // K <= 4 (the pangenome case): 40 registers, six CTAs per SM
+#endif
+#define JAC_TILE (256 * JAC_SPT)
+#define JAC_SPARSE_MAX 256   // at most this many sites left in a CTA: compacted path
 
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
@@ -910,7 +918,7 @@ static __device__ __forceinline__ void mark_readers_warp(int i, const int32_t *_
 // Rows [row0, row0+n_loc) of the GLOBAL graph are this rank's (row0 = 0, n_loc = N on one GPU);
 // labels, CSR, dirty flags and work lists are indexed by global family id, logpf by local row.
 template <int KT>
-__global__ void __launch_bounds__(256, JAC_MINB)
+__global__ void __launch_bounds__(256, KT <= 4 ? JAC_MINB_SMALLK : JAC_MINB)
 k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
                     const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                     const float *__restrict__ wgt, double beta, const uint8_t *__restrict__ lab_in,
@@ -924,9 +932,10 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
     int changed = 0, flags = 0, kept_site = 0;
     if ((int)blockIdx.x >= heavy_blocks && copy_ranks > 1) {
         // row shards: the other ranks' labels start the sweep at their previous value
-        int q = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x;
-        if (q < shard_len) {
-            int mine = row0 / shard_len;
+        const int mine = row0 / shard_len;
+        for (int s = 0; s < JAC_SPT; s++) {
+            int q = (blockIdx.x - heavy_blocks) * JAC_TILE + s * 256 + threadIdx.x;
+            if (q >= shard_len) break;
             for (int r = 0; r < copy_ranks; r++)
                 if (r != mine) lab_out[(size_t)r * shard_len + q] = lab_in[(size_t)r * shard_len + q];
         }
@@ -963,35 +972,64 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
         }
         return;
     }
+    // Light sites: a CTA covers JAC_SPT sub-tiles of 256 consecutive sites; thread t owns site t of
+    // every sub-tile.  The margin test of all its sites is issued at once (3 * JAC_SPT independent
+    // loads in flight per thread), so the dense round is ~one wave of CTAs instead of four chains
+    // of dependent latencies back to back.
     __shared__ float s_w[8][COOP_CHUNK];
     __shared__ uint8_t s_l[8][COOP_CHUNK];
-    __shared__ int s_act[256];
+    __shared__ int s_act[JAC_TILE];
     __shared__ int s_nact;
-    int il = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x;
-    int i = row0 + il;
+    const int tile0 = (blockIdx.x - heavy_blocks) * JAC_TILE;
     const int32_t *rp = beta != 0.0 ? row_ptr : nullptr;
-    const bool valid = il < n_loc;
-    // margin cache: the site keeps its label when its stored margin exceeds everything theta
-    // can have moved since and no later-or-equal neighbour changed in the previous sweep
-    const bool keep = valid && may_skip && !mg.stale_cur[i] && (double)mg.m[il] > thr.test &&
-                      lab_in[i] != 255;
-    const bool act = valid && !keep;
-    kept_site = keep;
-    if (keep) lab_out[i] = lab_in[i];
-    // How many sites of this CTA are left?  Few (steady state: a few per cent): compact them so
-    // that one or two warps walk the dependent loads and the others retire at once.  Many: the
-    // warp-cooperative segment path below.
+    unsigned actm = 0u;   // bit s: this thread's site of sub-tile s has to be evaluated
     int sparse = 0;
     if (may_skip) {
+        // margin cache: the site keeps its label when its stored margin exceeds everything theta
+        // can have moved since and no later-or-equal neighbour changed in the previous sweep
+        uint8_t st[JAC_SPT], lb[JAC_SPT];
+        float mv[JAC_SPT];
+#pragma unroll
+        for (int s = 0; s < JAC_SPT; s++) {
+            const int sl = tile0 + s * 256 + (int)threadIdx.x;
+            const bool valid = sl < n_loc;
+            st[s] = valid ? mg.stale_cur[row0 + sl] : (uint8_t)1;
+            mv[s] = valid ? mg.m[sl] : 0.f;
+            lb[s] = valid ? lab_in[row0 + sl] : (uint8_t)255;
+        }
         if (threadIdx.x == 0) s_nact = 0;
         __syncthreads();
-        unsigned ba = __ballot_sync(FULL, act);
+        unsigned ba[JAC_SPT];
+        int wtotal = 0;
+#pragma unroll
+        for (int s = 0; s < JAC_SPT; s++) {
+            const int sl = tile0 + s * 256 + (int)threadIdx.x;
+            const bool valid = sl < n_loc;
+            const bool keep = valid && !st[s] && (double)mv[s] > thr.test && lb[s] != 255;
+            if (keep) lab_out[row0 + sl] = lb[s];
+            kept_site += keep;
+            if (valid && !keep) actm |= 1u << s;
+            ba[s] = __ballot_sync(FULL, valid && !keep);
+            wtotal += __popc(ba[s]);
+        }
+        // How many sites of this CTA are left?  Few (steady state: a few per cent): compact them so
+        // that a few warps walk the dependent loads and the others retire at once.  Many: the
+        // warp-cooperative segment path below.
         int base = 0;
-        if (lane == 0 && ba) base = atomicAdd(&s_nact, __popc(ba));
+        if (lane == 0 && wtotal) base = atomicAdd(&s_nact, wtotal);
         base = __shfl_sync(FULL, base, 0);
-        if (act) s_act[base + __popc(ba & ((1u << lane) - 1u))] = il;
+#pragma unroll
+        for (int s = 0; s < JAC_SPT; s++) {
+            if ((actm >> s) & 1u)
+                s_act[base + __popc(ba[s] & ((1u << lane) - 1u))] = tile0 + s * 256 + (int)threadIdx.x;
+            base += __popc(ba[s]);
+        }
         __syncthreads();
-        sparse = s_nact <= 64;
+        sparse = s_nact <= JAC_SPARSE_MAX;
+    } else {
+#pragma unroll
+        for (int s = 0; s < JAC_SPT; s++)
+            if (tile0 + s * 256 + (int)threadIdx.x < n_loc) actm |= 1u << s;
     }
     if (sparse) {
         const int nact = s_nact;
@@ -1015,11 +1053,15 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
             if (fl & 2) atomicAdd(&cnt->ties, 1);
         }
         if (changed) atomicAdd(&cnt->changed, changed);
-        unsigned bk2 = __ballot_sync(FULL, kept_site);
-        if (lane == 0 && bk2) atomicAdd(&cnt->kept, __popc(bk2));
+        kept_site = __reduce_add_sync(FULL, kept_site);
+        if (lane == 0 && kept_site) atomicAdd(&cnt->kept, kept_site);
         return;
     }
-    if (il - lane < n_loc) {   // warps entirely out of range have nothing to do
+    int nallnul = 0, nties = 0;
+    for (int s = 0; s < JAC_SPT; s++) {
+        const int il = tile0 + s * 256 + (int)threadIdx.x, i = row0 + il;
+        if (il - lane >= n_loc) break;   // warps entirely out of range have nothing to do
+        const bool act = (actm >> s) & 1u;
         int lo = 0, hi = 0;
         if (rp && act) { lo = rp[i]; hi = rp[i + 1]; }
         const bool is_heavy = heavy_blocks && (hi - lo > HEAVY_DEG);
@@ -1036,23 +1078,29 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
         }
         if (act && !is_heavy) {
             double lpv[KT], margin;
+            int fl;
             load_lp<KT>(lps, K, (size_t)il, lpv);
-            int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
+            int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
             lab_out[i] = (uint8_t)km;
             store_margin(mg, il, margin, thr.store);
             if (mg.m && mg.stale_cur[i]) mg.stale_cur[i] = 0;
-            changed = (km != (int)lab_in[i]);
-            if (changed && dirty)
+            const int ch = (km != (int)lab_in[i]);
+            if (ch && dirty)
                 mark_readers(i, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc, mg.stale_next);
+            changed += ch;
+            nallnul += fl & 1;
+            nties += (fl >> 1) & 1;
         }
     }
-    unsigned bc = __ballot_sync(FULL, changed), bn = __ballot_sync(FULL, flags & 1),
-             bt = __ballot_sync(FULL, flags & 2), bk = __ballot_sync(FULL, kept_site);
+    changed = __reduce_add_sync(FULL, changed);
+    nallnul = __reduce_add_sync(FULL, nallnul);
+    nties = __reduce_add_sync(FULL, nties);
+    kept_site = __reduce_add_sync(FULL, kept_site);
     if (lane == 0) {
-        if (bc) atomicAdd(&cnt->changed, __popc(bc));
-        if (bn) atomicAdd(&cnt->allnul, __popc(bn));
-        if (bt) atomicAdd(&cnt->ties, __popc(bt));
-        if (bk) atomicAdd(&cnt->kept, __popc(bk));
+        if (changed) atomicAdd(&cnt->changed, changed);
+        if (nallnul) atomicAdd(&cnt->allnul, nallnul);
+        if (nties) atomicAdd(&cnt->ties, nties);
+        if (kept_site) atomicAdd(&cnt->kept, kept_site);
     }
 }
 
@@ -2511,7 +2559,7 @@ extern "C" void nemk_sweep_ncem_jacobi(nemk_stream s, int k, int row0, int n_loc
     if (n_loc <= 0 && copy_ranks <= 1) return;
     int hb = (row_ptr && beta != 0.0 && heavy && n_loc > 0) ? cdiv((long long)n_heavy * 32, 256) : 0;
     int cover = copy_ranks > 1 && shard_len > n_loc ? shard_len : n_loc;   // the copy spans a full slice
-    DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<hb + cdiv(cover, 256), 256, 0, S(s)>>>(
+    DISPATCH_K(k, (k_sweep_ncem_jacobi<KT><<<hb + cdiv(cover, JAC_TILE), 256, 0, S(s)>>>(
                       k, row0, n_loc, lps, row_ptr, col, wgt, beta, lab_in, lab_out, dirty, wl,
                       wl_count, rrow_ptr, rcol, heavy, n_heavy, hb, cnt, skip, copy_ranks,
                       shard_len, mg)));
