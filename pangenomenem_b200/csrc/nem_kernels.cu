@@ -26,8 +26,13 @@
 #ifndef JAC_MINB_SMALLK
 #define JAC_MINB_SMALLK 6   // K <= 4 (the pangenome case): 40 registers, six CTAs per SM
 #endif
+#ifndef FIXUP_HOIST
+#define FIXUP_HOIST 1  // fix-up rounds: label-independent loads issued before the dirty-flag fence
+#endif
 #define JAC_TILE (256 * JAC_SPT)
+#ifndef JAC_SPARSE_MAX
 #define JAC_SPARSE_MAX 256   // at most this many sites left in a CTA: compacted path
+#endif
 
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
@@ -43,6 +48,9 @@
 #define FULL 0xffffffffu
 
 static __device__ __forceinline__ double neg_inf() { return -CUDART_INF; }
+static __device__ __forceinline__ void prefetch_l1(const void *p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 
 // log p_k f_k(x_i) of the popcount path from the Hamming count (ComputePkFkiM nem_alg.c:2260-2285 +
 // DensBernoulli nem_mod.c:649-674).  ONE expression shared by the density epilogues, the cached
@@ -1038,14 +1046,15 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
             const bool hv = heavy_blocks && rp && (rp[si + 1] - rp[si] > HEAVY_DEG);
             if (hv) continue;   // evaluated by the hub blocks
             double ctx[KT], lpv[KT], margin;
+            load_lp<KT>(lps, K, (size_t)sl, lpv);   // requested before the neighbour walk, not after
+            const int lin = (int)lab_in[si];
             ctx_labels<KT>(K, si, rp, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx);
-            load_lp<KT>(lps, K, (size_t)sl, lpv);
             int fl;
             int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
             lab_out[si] = (uint8_t)km;
             store_margin(mg, sl, margin, thr.store);
             if (mg.stale_cur[si]) mg.stale_cur[si] = 0;
-            int ch = (km != (int)lab_in[si]);
+            int ch = (km != lin);
             if (ch && dirty)
                 mark_readers(si, rrow_ptr, rcol, dirty, wl, wl_count, row0, row0 + n_loc, mg.stale_next);
             changed += ch;          // a thread may take several sites here: counted directly
@@ -1065,9 +1074,10 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
         int lo = 0, hi = 0;
         if (rp && act) { lo = rp[i]; hi = rp[i + 1]; }
         const bool is_heavy = heavy_blocks && (hi - lo > HEAVY_DEG);
-        double ctx[KT];
+        double ctx[KT], lpv[KT];
 #pragma unroll
         for (int k = 0; k < KT; k++) ctx[k] = 0.0;
+        if (act) load_lp<KT>(lps, K, (size_t)il, lpv);   // requested before the neighbour walk
         if (rp) {
             int seg_lo = __reduce_min_sync(FULL, act ? lo : 0x7fffffff);
             int seg_hi = __reduce_max_sync(FULL, act ? hi : 0);
@@ -1077,9 +1087,8 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
                                     s_l[threadIdx.x >> 5], ctx);
         }
         if (act && !is_heavy) {
-            double lpv[KT], margin;
+            double margin;
             int fl;
-            load_lp<KT>(lps, K, (size_t)il, lpv);
             int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
             lab_out[i] = (uint8_t)km;
             store_margin(mg, il, margin, thr.store);
@@ -1134,17 +1143,34 @@ static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row
                                                  const int32_t *__restrict__ rrow_ptr,
                                                  const int32_t *__restrict__ rcol,
                                                  const nemk_margins &mg, double thr_store) {
+    // Everything that does not depend on the neighbours' labels is requested BEFORE the flag is
+    // cleared, so that it travels together with the fence instead of after it: the site's own
+    // current label (only this thread writes lab_cur[i] during the round), its data term (constant
+    // during a sweep) and the first sectors of its neighbour list (immutable; prefetched into L1).
+    if (FIXUP_HOIST && row_ptr) {
+        const int lo = row_ptr[i], hi = row_ptr[i + 1];
+        if (lo < hi) {
+            prefetch_l1(col + lo); prefetch_l1(wgt + lo);
+            prefetch_l1(col + hi - 1); prefetch_l1(wgt + hi - 1);
+        }
+    }
+    int was = 0;
+    double lpv[KT];
+    if (FIXUP_HOIST) {
+        was = __ldcg(lab_cur + i);
+        load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+    }
     atomicExch(&dirty[i], 0);
     __threadfence();
     double ctx[KT];
     ctx_labels<KT>(K, i, row_ptr, col, wgt,
                    [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
     int flags;
-    double lpv[KT], margin;
-    load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+    double margin;
+    if (!FIXUP_HOIST) load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
     int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
     store_margin(mg, i - row0, margin, thr_store);   // the LAST evaluation of a site is its final one
-    int was = __ldcg(lab_cur + i);
+    if (!FIXUP_HOIST) was = __ldcg(lab_cur + i);
     if (km == was) return 0;
     lab_cur[i] = (uint8_t)km;
     __threadfence();
@@ -1167,6 +1193,9 @@ static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, in
                                                       const int32_t *__restrict__ rcol,
                                                       const nemk_margins &mg, double thr_store) {
     const int lane = threadIdx.x & 31;
+    double lpv[KT];
+    int was = (int)__ldcg(lab_cur + i);   // only this warp writes lab_cur[i] during the round
+    load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
     if (lane == 0) { atomicExch(&dirty[i], 0); __threadfence(); }
     __syncwarp();
     double ctx[KT];
@@ -1174,11 +1203,10 @@ static __device__ __forceinline__ int fixup_site_warp(int K, int i, int row0, in
                         [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx,
                         lps.wsum_any_order != 0);
     int flags;
-    double lpv[KT], margin;
-    load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
+    double margin;
     int km = site_argmax<KT>(K, lpv, ctx, beta, flags, margin);
     if (lane == 0) store_margin(mg, i - row0, margin, thr_store);
-    int was = __shfl_sync(FULL, (int)__ldcg(lab_cur + i), 0);
+    was = __shfl_sync(FULL, was, 0);
     if (km == was) return 0;
     if (lane == 0) { lab_cur[i] = (uint8_t)km; __threadfence(); }
     __syncwarp();
@@ -1903,21 +1931,51 @@ static __device__ __forceinline__ float iner_of(double s, double n, bool nonempt
     return (float)(s * fabs(1.0 - (double)mu) + (n - s) * fabs((double)mu));
 }
 
-// sum of v[0..NV) over the cluster; every thread of every CTA gets the totals (rank order)
-template <int NV, int TH>
+// sum of v[0..NV) over the cluster: block sums (the fixed shuffle tree + fixed smem order of
+// block_sum, all NV values through ONE pair of block barriers), left in each CTA's `slot`, then
+// added in CTA-rank order by the threads that `need` the totals -- the CL remote reads of a value
+// are independent loads issued back to back (CL is a compile-time constant), not a chain.
+template <int NV, int TH, int CL>
 static __device__ __forceinline__ void cluster_sum(cg::cluster_group &cluster, double (&v)[NV],
-                                                   double *sh /*[32]*/, double *slot /*[NV] smem*/) {
+                                                   double *sh /*[NV * 32]*/, double *slot /*[NV] smem*/,
+                                                   bool need) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
     for (int q = 0; q < NV; q++) {
-        double r = block_sum<TH>(v[q], sh);
-        if (threadIdx.x == 0) slot[q] = r;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(FULL, v[q], o);
+    }
+    __syncthreads();   // sh may still be read from a previous sum
+    if (l == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; q++) sh[q * 32 + w] = v[q];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            double r = (l < TH / 32) ? sh[q * 32 + l] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+            if (l == 0) slot[q] = r;
+        }
     }
     cluster.sync();
+    if (need) {
+        double part[NV][CL];
 #pragma unroll
-    for (int q = 0; q < NV; q++) {
-        double t = 0.0;
-        for (unsigned r = 0; r < cluster.num_blocks(); r++) t += cluster.map_shared_rank(slot, r)[q];
-        v[q] = t;
+        for (int r = 0; r < CL; r++) {
+            const double *rs = cluster.map_shared_rank(slot, r);
+#pragma unroll
+            for (int q = 0; q < NV; q++) part[q][r] = rs[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < CL; r++) t += part[q][r];
+            v[q] = t;
+        }
     }
     cluster.sync();   // slots may be rewritten
 }
@@ -1931,7 +1989,7 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
                         float *prop, float *center, float *disp, nemk_coef *coef,
                         uint32_t *mask_xor, uint32_t *mask_valid, uint32_t *mask_f0,
                         uint32_t *mask_f1, double *delta) {
-    __shared__ double sh[32];
+    __shared__ double sh[5 * 32];
     __shared__ double slot[8];
     __shared__ float nkf[NEMB_MAX_K];
     __shared__ double nkd[NEMB_MAX_K];
@@ -1996,7 +2054,7 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
                 }
             }
         }
-        cluster_sum<1, TH>(cluster, v, sh, slot);
+        cluster_sum<1, TH, CL>(cluster, v, sh, slot, true);
         if (disp_model == 0 || nkf[k] > 0.f) {
             float dk = __fdiv_rn((float)v[0], (float)sn);
             for (int j = j_lo + tid; j < j_hi; j += TH) disp[(size_t)k * D + j] = dk;
@@ -2018,7 +2076,7 @@ k_mstep_finalize_tables(int K, int N, int D, int wpr, int prop_model, int disp_m
         }
     if (p.mu_moved) atomicOr(&coef->mu_changed, 1);   // preset by the launcher (0, or 1 = forced)
     double v[5] = {p.base_u, p.base_g, (double)p.notok, (double)p.n_valid, (double)p.n_x1};
-    cluster_sum<5, TH>(cluster, v, sh, slot);
+    cluster_sum<5, TH, CL>(cluster, v, sh, slot, part == 0 && tid == 0);
     if (part == 0 && tid == 0)
         tables_commit(k, K, D, prop, coef, delta, cc, v[0], v[1], v[2] == 0.0, (int)v[3], (int)v[4], true);
 }
