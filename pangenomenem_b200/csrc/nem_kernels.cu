@@ -27,7 +27,7 @@
 #define JAC_MINB_SMALLK 6   // K <= 4 (the pangenome case): 40 registers, six CTAs per SM
 #endif
 #ifndef FIXUP_HOIST
-#define FIXUP_HOIST 1  // fix-up rounds: label-independent loads issued before the dirty-flag fence
+#define FIXUP_HOIST 0  // fix-up rounds: label-independent loads issued before the dirty-flag fence (measured neutral on C4)
 #endif
 #define JAC_TILE (256 * JAC_SPT)
 #ifndef JAC_SPARSE_MAX
