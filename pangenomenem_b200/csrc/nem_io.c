@@ -409,7 +409,8 @@ static void *nei_worker(void *arg)
         const char *t; size_t len; long id, nb;
         if (!next_token(&c, &t, &len)) continue;      /* blank line */
         if (!tok_int(t, len, &id) || !next_token(&c, &t, &len) || !tok_int(t, len, &nb) ||
-            id < 1 || id > j->n || nb < 0 || nb > (1 << 28)) { j->fallback = 1; return NULL; }
+            id < 1 || id > j->n || nb < 0 || nb > (1 << 28) ||
+            nb > (long)(c.end - c.p)) { j->fallback = 1; return NULL; }   /* nb tokens cannot fit on the line */
         if (j->used + (size_t)nb > j->cap) {
             size_t cap = j->cap ? j->cap : 4096;
             while (j->used + (size_t)nb > cap) cap *= 2;
@@ -518,6 +519,7 @@ static int nei_read_lines(const char *beg, const char *end, int n, int weighted,
                 if (last_t[i] < 0) continue;
                 const nei_job *j = &jobs[last_t[i]];
                 const nei_rec *r = &j->rec[last_r[i]];
+                if (r->nv == 0) continue;   /* a thread without entries has no pool */
                 memcpy(cl + rp[i], j->pc + r->off, sizeof(int32_t) * (size_t)r->nv);
                 memcpy(wg + rp[i], j->pw + r->off, sizeof(float) * (size_t)r->nv);
             }
@@ -575,11 +577,17 @@ int nemio_read_nei(const char *base, FILE *err, int n, int32_t **row_ptr_out, in
             fprintf(err, "Error in neighb. file l.%d : point id %ld out of 1..%d\n", line, id, n);
             rc = NEMB_E_FILE; goto out;
         }
+        if (nb > (long)(c.end - c.p)) {   /* more neighbours announced than bytes left in the file */
+            fprintf(err, "Error in neighb. file l.%d : neighbor %ld\n", line, (long)(c.end - c.p));
+            rc = NEMB_E_FILE; goto out;
+        }
         if (used + (size_t)nb > cap) {
             while (used + (size_t)nb > cap) cap *= 2;
-            pool_c = realloc(pool_c, cap * sizeof(int32_t));
-            pool_w = realloc(pool_w, cap * sizeof(float));
-            if (!pool_c || !pool_w) { rc = NEMB_E_MEMORY; goto out; }
+            int32_t *nc = realloc(pool_c, cap * sizeof(int32_t));
+            if (nc) pool_c = nc;
+            float *nw = nc ? realloc(pool_w, cap * sizeof(float)) : NULL;
+            if (nw) pool_w = nw;
+            if (!nc || !nw) { rc = NEMB_E_MEMORY; goto out; }
         }
         size_t s0 = used;
         for (long q = 0; q < nb; q++) {
@@ -588,7 +596,7 @@ int nemio_read_nei(const char *base, FILE *err, int n, int32_t **row_ptr_out, in
                 fprintf(err, "Error in neighb. file l.%d : neighbor %ld\n", line, q);
                 rc = NEMB_E_FILE; goto out;
             }
-            pool_c[s0 + q] = (int32_t)nbr;
+            pool_c[s0 + q] = nbr < INT32_MIN || nbr > INT32_MAX ? 0 : (int32_t)nbr;   /* out of 1..n: skipped below */
             pool_w[s0 + q] = 1.0f;
         }
         if (weighted) {
