@@ -29,6 +29,9 @@
 #ifndef FIXUP_HOIST
 #define FIXUP_HOIST 0  // fix-up rounds: label-independent loads issued before the dirty-flag fence (measured neutral on C4)
 #endif
+#ifndef FIXUP_ACQ
+#define FIXUP_ACQ 0    // fix-up rounds: flag clear as an ACQUIRE exchange instead of exchange + fence (untested knob)
+#endif
 #define JAC_TILE (256 * JAC_SPT)
 #ifndef JAC_SPARSE_MAX
 #define JAC_SPARSE_MAX 256   // at most this many sites left in a CTA: compacted path
@@ -1160,8 +1163,21 @@ static __device__ __forceinline__ int fixup_site(int K, int i, int row0, int row
         was = __ldcg(lab_cur + i);
         load_lp<KT>(lps, K, (size_t)(i - row0), lpv);
     }
+#if FIXUP_ACQ
+    // Every access to dirty[] is a read-modify-write, so the flag's modification order is total:
+    // either the changer's claim (store label; fence; exchange 1) precedes this exchange -- then
+    // this ACQUIRE exchange synchronises with it and the label loads below see the new label -- or
+    // it follows, finds 0 and re-queues the site.  No full fence on this side.
+    {
+        int32_t was_flag;
+        asm volatile("atom.acquire.gpu.global.exch.b32 %0, [%1], %2;"
+                     : "=r"(was_flag) : "l"(dirty + i), "r"(0) : "memory");
+        (void)was_flag;
+    }
+#else
     atomicExch(&dirty[i], 0);
     __threadfence();
+#endif
     double ctx[KT];
     ctx_labels<KT>(K, i, row_ptr, col, wgt,
                    [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
