@@ -219,3 +219,20 @@ def test_nei_threaded_reader_matches_the_sequential_semantics(tmp_path, capi):
         with pytest.raises(capi.NemError) as ei:
             capi.read_files(base, k=0)
         assert ei.value.code == 3
+
+
+def test_uf_writer_rounds_like_printf(tmp_path, capi):
+    """The .uf writer formats " %5.3f " without printf (nem_exe.c:1677): same bytes as printf on
+    random posteriors, on every k/2000 tie candidate and its float neighbours, and at the ends."""
+    rng = np.random.default_rng(0)
+    grid = (np.arange(0, 2001, dtype=np.float64) / 2000).astype(np.float32)
+    v = np.concatenate([
+        rng.random(60000, dtype=np.float32), grid, np.nextafter(grid, np.float32(0)),
+        np.nextafter(grid, np.float32(2)),
+        np.array([0, 1, 1e-45, 1e-30, 0.0005, 0.00049999, 0.9995, 0.99949999, 0.99999994, 0.0625,
+                  0.1875, 0.3125], dtype=np.float32)])
+    v = v[:len(v) // 3 * 3].reshape(-1, 3)
+    capi.write_uf(str(tmp_path / "o.uf"), v)
+    got = open(tmp_path / "o.uf").read().split("\n")
+    exp = ["".join(" %5.3f " % float(x) for x in r) for r in v]
+    assert got[:len(exp)] == exp
