@@ -168,3 +168,25 @@ def test_reference_arm_prints_the_contract_line():
     assert line["metric"] == "NEM family-iterations/s" and line["unit"] == "family-iterations/s"
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_built_library_uses_the_blackwell_copy_and_barrier_units():
+    """SASS of the in-tree sm_100a library: the density kernel moves its tiles with bulk
+    asynchronous copies completing on mbarriers (UBLKCP + SYNCS), the fix-up tail and the finalize
+    kernel synchronise their thread-block clusters in hardware (UCGABAR) -- profiles/r1_sass_evidence.txt."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    from pangenomenem_b200 import capi
+    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    blocks = sass.split("Function : ")
+    def body(tag):
+        hits = [b for b in blocks if b.split("\n", 1)[0].startswith(tag)]
+        assert hits, tag
+        return "\n".join(hits)
+    den = body("_Z13k_density_tma")
+    assert "UBLKCP" in den and "SYNCS" in den and "POPC" in den
+    assert "UCGABAR" in body("_Z18k_sweep_ncem_fixup")
+    assert "UCGABAR" in body("_Z23k_mstep_finalize_tables")
