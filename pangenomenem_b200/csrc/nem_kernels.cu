@@ -32,6 +32,9 @@
 #ifndef FIXUP_ACQ
 #define FIXUP_ACQ 0    // fix-up rounds: flag clear as an ACQUIRE exchange instead of exchange + fence (untested knob)
 #endif
+#ifndef JAC_HUB_GUARD
+#define JAC_HUB_GUARD 0   // dense round: light threads never copy a hub's label (see the kernel); not yet run on a GPU
+#endif
 #define JAC_TILE (256 * JAC_SPT)
 #ifndef JAC_SPARSE_MAX
 #define JAC_SPARSE_MAX 256   // at most this many sites left in a CTA: compacted path
@@ -1000,6 +1003,14 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
         // can have moved since and no later-or-equal neighbour changed in the previous sweep
         uint8_t st[JAC_SPT], lb[JAC_SPT];
         float mv[JAC_SPT];
+#if JAC_HUB_GUARD
+        // A hub's label, margin and stale flag belong to its warp in the hub blocks, which may have
+        // evaluated the site and cleared its flag before this thread looks: a "kept" hub is not
+        // copied here (the hub warp writes lab_out in every case), or a late copy of the old label
+        // could land on top of the new one.
+        unsigned hubm = 0u;
+        const bool hubs = heavy_blocks && rp;
+#endif
 #pragma unroll
         for (int s = 0; s < JAC_SPT; s++) {
             const int sl = tile0 + s * 256 + (int)threadIdx.x;
@@ -1007,6 +1018,9 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
             st[s] = valid ? mg.stale_cur[row0 + sl] : (uint8_t)1;
             mv[s] = valid ? mg.m[sl] : 0.f;
             lb[s] = valid ? lab_in[row0 + sl] : (uint8_t)255;
+#if JAC_HUB_GUARD
+            if (hubs && valid && rp[row0 + sl + 1] - rp[row0 + sl] > HEAVY_DEG) hubm |= 1u << s;
+#endif
         }
         if (threadIdx.x == 0) s_nact = 0;
         __syncthreads();
@@ -1017,7 +1031,11 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
             const int sl = tile0 + s * 256 + (int)threadIdx.x;
             const bool valid = sl < n_loc;
             const bool keep = valid && !st[s] && (double)mv[s] > thr.test && lb[s] != 255;
+#if JAC_HUB_GUARD
+            if (keep && !((hubm >> s) & 1u)) lab_out[row0 + sl] = lb[s];
+#else
             if (keep) lab_out[row0 + sl] = lb[s];
+#endif
             kept_site += keep;
             if (valid && !keep) actm |= 1u << s;
             ba[s] = __ballot_sync(FULL, valid && !keep);
