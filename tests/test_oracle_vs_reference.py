@@ -83,3 +83,47 @@ def test_reference_underflow_is_gated_not_copied(tmp_path, ref):
     o = ref.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, it_max=3, conv="none").fit(*ref.default_theta(3, pg.d))
     assert r["density_zero"]
     assert o.n_allnul == 0 and np.isfinite(o.crit["L"])
+
+
+def test_reference_context_overflow_is_gated_not_copied(tmp_path, ref):
+    """The reference evaluates p_k f_k exp(beta ctx_k) in the linear domain (nem_alg.c:2589-2613):
+    with co-presence weights of a few hundred genomes, beta*ctx passes log(DBL_MAX) = 709.8, the
+    numerator is inf, the posterior inf/inf = NaN and ComputeMAP (nem_alg.c:590-645) keeps class 0
+    whatever the data.  With PPanGGOLiN's class order the overflowing class IS class 0 (persistent),
+    so the accident is invisible; with the persistent class last the reference mislabels those
+    families and never converges.  The log-domain restatement (and the CUDA engine) stay finite:
+    found by a randomised oracle-vs-reference campaign at the end of round 1."""
+    from pangenomenem_b200 import synth
+    pg = make_case(600, 40, seed=9, graph="chain")
+    pg = synth.Pangenome(x=pg.x, row_ptr=pg.row_ptr, col=pg.col,
+                         wgt=(pg.wgt * np.float32(12)).astype(np.float32), latent=pg.latent)
+    kw = dict(algo="ncem", beta=1.0, disp="sk_", prop="pk", it_max=30, update="seq")
+
+    def both(theta, m_text, sub):
+        base = str(tmp_path / sub / "nem_file")
+        synth.write_nem_files(base, pg, m_text=m_text)
+        r = ref.run_ref_harness(base, str(tmp_path / sub / "out"), k=3, tie="first", **kw)
+        o = ref.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, k=3, **kw).fit(*theta)
+        assert r["status"] == 0 and not r["density_zero"]       # the reference does not notice
+        ctx = np.zeros((pg.n, 3))
+        for i in range(pg.n):
+            for e in range(pg.row_ptr[i], pg.row_ptr[i + 1]):
+                ctx[i, o.label[pg.col[e]]] += pg.wgt[e]
+        over = kw["beta"] * ctx.max(axis=1) > 709.0
+        return r, o, over
+
+    p, c, s = ref.default_theta(3, pg.d)
+    r, o, over = both((p, c, s), None, "first")
+    assert over.sum() > 50                                        # the overflow is there ...
+    assert np.array_equal(o.label, r["cm"].argmax(axis=1))       # ... and lands on class 0 by luck
+    assert o.iters == r["iters"] and o.converged and r["converged"]
+
+    p2, c2, s2 = p[::-1].copy(), c[::-1].copy(), s[::-1].copy()   # cloud, shell, persistent
+    p2[2] = np.float32(np.float32(1.0) - p2[0]) - p2[1]           # as ReadParamFile rebuilds the last one
+    r, o, over = both((p2, c2, s2), synth.m_line(1, p2, c2, s2), "last")
+    diff = o.label != r["cm"].argmax(axis=1)
+    assert o.converged and not r["converged"]
+    assert diff.sum() > 50 and (diff & over).sum() > 0.7 * diff.sum()
+    # the restatement's partition is the first run's with the class names permuted
+    first = ref.Problem(pg.x, pg.row_ptr, pg.col, pg.wgt, k=3, **kw).fit(p, c, s)
+    assert np.array_equal(2 - o.label, first.label)
