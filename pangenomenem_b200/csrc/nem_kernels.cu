@@ -33,7 +33,9 @@
 #define FIXUP_ACQ 0    // fix-up rounds: flag clear as an ACQUIRE exchange instead of exchange + fence (untested knob)
 #endif
 #ifndef JAC_HUB_GUARD
-#define JAC_HUB_GUARD 0   // dense round: light threads never copy a hub's label (see the kernel); not yet run on a GPU
+#define JAC_HUB_GUARD 1   // dense round: light threads never copy a hub's label (see the kernel).  Default since the
+                          // end of round 1 (the race it closes is real: tests/test_sweep_protocol_model.py); the
+                          // GPU-measured numbers under profiles/r1_* are of the =0 build, same registers/spills
 #endif
 #define JAC_TILE (256 * JAC_SPT)
 #ifndef JAC_SPARSE_MAX

@@ -127,3 +127,74 @@ def test_the_model_catches_the_chase_race():
             got, _ = speculative(adj, lp, old, 1.0, rng, chase=True)
             bad += not np.array_equal(got, ref)
     assert bad > 0
+
+
+# ---- the margin-cached dense round looks at a hub twice (k_sweep_ncem_jacobi): its warp in the hub
+# blocks and the light thread of its index.  Memory operations of the two visitors, in program
+# order; every interleaving of the two sequences is enumerated.
+def _hub_visitors(guard):
+    """Generators over one hub's shared cells.  mem: stale, margin, lab_in, lab_out."""
+    def hub_warp(mem, evaluate, thr):
+        st = mem["stale"]; yield                      # noqa: E702  (one operation per step)
+        m = mem["margin"]; yield                      # noqa: E702
+        if not st and m > thr:
+            mem["lab_out"] = mem["lab_in"]; yield     # noqa: E702  kept: copy
+            return
+        km, margin = evaluate()
+        mem["lab_out"] = km; yield                    # noqa: E702
+        mem["margin"] = margin; yield                 # noqa: E702
+        mem["stale"] = 0; yield                       # noqa: E702
+
+    def light_thread(mem, evaluate, thr):
+        st = mem["stale"]; yield                      # noqa: E702
+        m = mem["margin"]; yield                      # noqa: E702
+        lb = mem["lab_in"]; yield                     # noqa: E702
+        keep = (not st) and m > thr
+        if keep and not guard:                        # JAC_HUB_GUARD: a kept hub is not copied here
+            mem["lab_out"] = lb; yield                # noqa: E702
+        # not kept: the site is a hub, the light paths skip it (is_heavy / hv)
+    return hub_warp, light_thread
+
+
+def _interleavings(na, nb):
+    from itertools import combinations
+    for pos in combinations(range(na + nb), na):
+        s = ["b"] * (na + nb)
+        for p in pos:
+            s[p] = "a"
+        yield s
+
+
+def _run_hub_round(guard, schedule, stale0, margin0, old, new, new_margin, thr):
+    mem = {"stale": stale0, "margin": margin0, "lab_in": old, "lab_out": None}
+    hub_warp, light_thread = _hub_visitors(guard)
+    gens = {"a": hub_warp(mem, lambda: (new, new_margin), thr),
+            "b": light_thread(mem, lambda: (new, new_margin), thr)}
+    done = set()
+    for who in schedule + ["a"] * 8 + ["b"] * 8:                # the tail drains whoever is left
+        if who in done:
+            continue
+        try:
+            next(gens[who])
+        except StopIteration:
+            done.add(who)
+    return mem["lab_out"]
+
+
+@pytest.mark.parametrize("stale0,margin0", [(1, 5.0), (0, 0.5), (1, 0.5), (0, 5.0)])
+def test_hub_guard_every_interleaving_keeps_the_hub_warps_label(stale0, margin0):
+    """With the guard (the default build) the label in lab_out is the hub warp's in every schedule:
+    the new label when the warp had to evaluate, the old one when the margin test kept the site."""
+    thr, old, new = 1.0, 0, 2
+    expect = old if (not stale0 and margin0 > thr) else new
+    for sched in _interleavings(6, 5):
+        assert _run_hub_round(True, sched, stale0, margin0, old, new, 9.0, thr) == expect
+
+
+def test_the_model_catches_the_hub_copy_race():
+    """Without the guard a light thread that looks after the hub warp has stored a large margin
+    and cleared the flag copies the OLD label over the new one (the hole DESIGN.md 2.2 described)."""
+    thr, old, new = 1.0, 0, 2
+    bad = sum(_run_hub_round(False, s, 1, 5.0, old, new, 9.0, thr) != new
+              for s in _interleavings(6, 5))
+    assert bad > 0
