@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Probe for the hub copy race of the margin-cached dense sweep round (DESIGN.md section 2.2,
 knob JAC_HUB_GUARD).  NOT part of the test suite: written without a GPU at the end of round 1, to
-be run on a B200 with the knob off and on.
+be run on a B200 against a -DJAC_HUB_GUARD=0 variant and the default build (guard on).
 
     python profiles/ab/hub_race_probe.py [--families 600000] [--seeds 6]
 
