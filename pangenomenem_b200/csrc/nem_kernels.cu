@@ -964,7 +964,12 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
         if (wid >= n_heavy) return;
         int i = heavy[wid], il = i - row0;
         if (may_skip && !mg.stale_cur[i] && (double)mg.m[il] > thr.test && lab_in[i] != 255) {
-            if (lane == 0) lab_out[i] = lab_in[i];   // margin > possible move, context unchanged
+            if (lane == 0) {
+                lab_out[i] = lab_in[i];   // margin > possible move, context unchanged
+#if JAC_HUB_GUARD
+                atomicAdd(&cnt->kept, 1);   // hubs are counted here, not by the light threads
+#endif
+            }
             return;
         }
         double ctx[KT];
@@ -1035,10 +1040,11 @@ k_sweep_ncem_jacobi(int K, int row0, int n_loc, const nemk_lpsrc lps,
             const bool keep = valid && !st[s] && (double)mv[s] > thr.test && lb[s] != 255;
 #if JAC_HUB_GUARD
             if (keep && !((hubm >> s) & 1u)) lab_out[row0 + sl] = lb[s];
+            kept_site += keep && !((hubm >> s) & 1u);
 #else
             if (keep) lab_out[row0 + sl] = lb[s];
-#endif
             kept_site += keep;
+#endif
             if (valid && !keep) actm |= 1u << s;
             ba[s] = __ballot_sync(FULL, valid && !keep);
             wtotal += __popc(ba[s]);
