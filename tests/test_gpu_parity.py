@@ -442,7 +442,8 @@ def test_large_fit_is_exact_and_repeatable(engine, oracle):
 
 def test_fractional_weights_keep_the_file_order(engine, oracle):
     """Non-integer edge weights: the fp64 context sums depend on the order, so the engine must add
-    them in file order like SumNeighsOfClass (nem_alg.c:2865-2875), hubs included."""
+    them in file order like SumNeighsOfClass (nem_alg.c:2865-2875).  (This pangenome has no family
+    with more than 16 neighbours; the warp-per-hub sums are in test_gpu_zhub_guard.py.)"""
     pg = make_case(12000, 48, seed=23, graph="pangenome")
     rng = np.random.default_rng(5)
     wgt = (pg.wgt * rng.uniform(0.05, 1.0, size=pg.wgt.shape)).astype(np.float32)
