@@ -22,6 +22,11 @@
  *     like ClassifM,
  *   - MAP ties go to the first maximum (TIE_FIRST, nem_alg.c:641; the reference's default
  *     TIE_RANDOM is seeded by the wall clock, nem_exe.c:353,621, and cannot be reproduced).
+ *
+ * OpenMP: only loops whose iterations are independent (one family per iteration, every sum
+ * inside it in the same order as the sequential loop) or whose sums are exact integers (the
+ * ncem statistics: t in {0,1}) are threaded, so the results do not depend on the thread count;
+ * it lets the whole-fit parity tests run at the BASELINE shapes (250 000 x 1000, D = 5000).
  */
 #include "nem_oracle.h"
 
@@ -90,6 +95,7 @@ void nemo_hamming(const nemo_problem *pb, const float *center, const float *disp
     class_tab tb; tab_alloc(&tb, d);
     for (int k = 0; k < K; k++) {
         tab_fill(&tb, d, center + (size_t)k * d, disp + (size_t)k * d);
+#pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) {
             const uint8_t *xi = pb->x + (size_t)i * d;
             int32_t s = 0;
@@ -111,6 +117,7 @@ void nemo_logpf(const nemo_problem *pb, const float *prop, const float *center,
         double pk = prop[k];
         double lp = (pk > NEMO_EPSILON) ? log(pk) : -INFINITY; /* nem_alg.c:2265-2271 */
         tab_fill(&tb, d, center + (size_t)k * d, disp + (size_t)k * d);
+#pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) {
             const uint8_t *xi = pb->x + (size_t)i * d;
             double dk = 0.0; int nul = 0;
@@ -210,6 +217,31 @@ int nemo_mstep(const nemo_problem *pb, const float *t, float *prop, float *cente
 {
     int n = pb->n, d = pb->d, K = pb->k, status = NEMO_OK;
     double *nk = calloc(K, sizeof(double)), *s = calloc((size_t)K * d, sizeof(double));
+    int hard = 1;   /* every t_ik is 0 or 1: n_k and S_kd are integer counts, exact in any order */
+    for (size_t q = 0; q < (size_t)n * K && hard; q++) hard = t[q] == 0.0f || t[q] == 1.0f;
+    if (hard && (double)n < 9.0e15) {
+#pragma omp parallel
+        {
+            double *nk_t = calloc(K, sizeof(double)), *s_t = calloc((size_t)K * d, sizeof(double));
+#pragma omp for schedule(static) nowait
+            for (int i = 0; i < n; i++) {
+                const uint8_t *xi = pb->x + (size_t)i * d;
+                const float *ti = t + (size_t)i * K;
+                for (int k = 0; k < K; k++) {
+                    if (ti[k] == 0.0f) continue;
+                    nk_t[k] += 1.0;
+                    double *sk = s_t + (size_t)k * d;
+                    for (int j = 0; j < d; j++) sk[j] += (double)xi[j];
+                }
+            }
+#pragma omp critical
+            {
+                for (int k = 0; k < K; k++) nk[k] += nk_t[k];
+                for (size_t q = 0; q < (size_t)K * d; q++) s[q] += s_t[q];
+            }
+            free(nk_t); free(s_t);
+        }
+    } else
     for (int i = 0; i < n; i++) {
         const uint8_t *xi = pb->x + (size_t)i * d;
         const float *ti = t + (size_t)i * K;

@@ -13,6 +13,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """On a machine WITHOUT an NVIDIA driver (no /dev/nvidiactl: this build container, CPU-only CI)
+    the `gpu` tests are skipped instead of erroring out of nemb_create.  Where a driver exists they
+    always run, so a broken CUDA path on a GPU box fails loudly (the library has no CPU fallback)."""
+    if os.path.exists("/dev/nvidiactl") or os.environ.get("NEM_B200_FORCE_GPU_TESTS"):
+        return
+    skip = pytest.mark.skip(reason="no NVIDIA driver on this machine (gpu tests run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import nemo
