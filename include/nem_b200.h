@@ -130,6 +130,9 @@ typedef struct {
     float   beta;         /* beta of the last sweep and of the criteria (ModelParaT.Beta on return):
                              the option's, or the estimate of psgrad / of a heuristic */
     int32_t n_beta_tested;   /* nemb_fit_beta_heuristic: fits that ended without an empty class */
+    /* persistent EM kernel (one cooperative launch per fit): launches of it, the
+     * device-wide barriers they executed, the X passes and X^T recounts done inside them */
+    int32_t pk_launches, pk_barriers, pk_x_passes, pk_recounts;
 } nemb_result;
 
 /* Per-iteration trace for the .log writer (nem_alg.c:1995-2052, 2620-2646). */

@@ -44,7 +44,7 @@ def _run(cmd, verbose):
 def build_all(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(ROOT, "include", "nem_b200.h")] + [
-        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     objs = []
     for f in CU_SOURCES:
         src, obj = os.path.join(CSRC, f), os.path.join(OBJ, f + ".o")

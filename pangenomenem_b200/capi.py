@@ -51,7 +51,9 @@ class Result(C.Structure):
                 ("ms_density_cached", C.c_float), ("ms_mstep_delta", C.c_float),
                 ("n_density_cached", C.c_int32), ("n_mstep_delta", C.c_int32),
                 ("exchanges", C.c_int64), ("n_kept", C.c_int64),
-                ("beta", C.c_float), ("n_beta_tested", C.c_int32)]
+                ("beta", C.c_float), ("n_beta_tested", C.c_int32),
+                ("pk_launches", C.c_int32), ("pk_barriers", C.c_int32),
+                ("pk_x_passes", C.c_int32), ("pk_recounts", C.c_int32)]
 
 
 class BatchStats(C.Structure):
@@ -178,6 +180,7 @@ class Fit:
     n_beta_tested: int = 0
     beta_tested: np.ndarray | None = None
     crit_tested: np.ndarray | None = None
+    pk: dict = field(default_factory=dict)   # persistent EM kernel: launches, barriers, x_passes, recounts
 
 
 class Engine:
@@ -352,7 +355,9 @@ class Engine:
                         mstep_delta=r.n_mstep_delta), r.empty_class, r.exchanges, r.n_kept, r.best_start,
                    r.n_success, r.beta, r.n_beta_tested,
                    None if bt is None else bt[:min(r.n_beta_tested, bt.shape[0])].copy(),
-                   None if ct is None else ct[:min(r.n_beta_tested, ct.shape[0])].copy())
+                   None if ct is None else ct[:min(r.n_beta_tested, ct.shape[0])].copy(),
+                   dict(launches=r.pk_launches, barriers=r.pk_barriers, x_passes=r.pk_x_passes,
+                        recounts=r.pk_recounts))
 
     def estim_beta(self, t, beta, **kw):
         """EstimBeta on the classification t[N,K] -> (new beta, dict(crit, grad, dsec))."""

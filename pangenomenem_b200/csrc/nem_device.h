@@ -292,6 +292,70 @@ void nemk_sub_fill(nemk_stream s, int n, const int32_t *row_ptr, const int32_t *
 void nemk_sub_vote(nemk_stream s, int n_eff, const int32_t *index, const uint8_t *lab, int c0,
                    int c1, int c2, int all_u, int32_t *votes);
 
+
+/* ---- persistent EM kernel (nem_persist.cuh): ONE cooperative launch runs the whole ncem fit on the
+ * popcount density path -- tables, densities, the two initial sweeps, then per EM iteration the
+ * incremental (or full) M-step statistics, the closed forms + tables, the density pass, the
+ * speculative sequential sweep (margin test, evaluation, fix-up rounds) and the convergence test
+ * -- with a device-wide barrier between phases instead of a launch, and no host round trip until
+ * the fit is over.  A problem too large for the in-kernel (L2-sized) X / X^T passes leaves the
+ * kernel for exactly those two HBM-bound passes (exit codes below) and re-enters it. */
+enum { NEMK_PK_ENTRY_INIT = 0,        /* tables of the theta in prop/center/disp, then the fit */
+       NEMK_PK_ENTRY_INIT_SWEEPS = 1, /* densities ready (host ran the X pass): blind + beta sweep */
+       NEMK_PK_ENTRY_MSTEP = 2,       /* start of an EM iteration */
+       NEMK_PK_ENTRY_FINALIZE = 3,    /* statistics ready (host ran the full recount) */
+       NEMK_PK_ENTRY_SWEEP = 4 };     /* densities of this iteration ready (host ran the X pass) */
+enum { NEMK_PK_EXIT_DONE = 0, NEMK_PK_EXIT_NEED_DENSITY = 1, NEMK_PK_EXIT_NEED_RECOUNT = 2 };
+
+typedef struct {
+    int32_t exit_code, resume_entry;    /* NEED_*: run the pass, re-enter at resume_entry */
+    int32_t iters, converged, empty_class;
+    int32_t cur, stale_par, last_changed, stats_valid, cnt_par;
+    int32_t n_allnul, n_ties;           /* of the last sweep */
+    int32_t sweeps, x_passes, recounts, barriers;
+    long long kept, fixup_rounds;       /* summed over the sweeps of this launch */
+    unsigned long long seq;             /* written last, after a system-wide fence */
+} nemk_persist_out;
+
+typedef struct {
+    /* problem (one GPU: row0 = 0, n = all families) */
+    int32_t K, n, D, wpr, nwt;
+    int32_t prop_model, disp_model, conv, it_max;
+    float   conv_thr;
+    double  beta;
+    int32_t seq_sweep;        /* graph + beta != 0 + update=seq: speculative sequential sweep */
+    int32_t use_graph;        /* graph + beta != 0 (update=para: one Jacobi round per sweep) */
+    int32_t n_heavy, wsum_any_order, use_margins;
+    int32_t x_in_kernel;      /* X and X^T passes may run inside the kernel (L2-sized problem) */
+    int32_t init_from_pop;    /* ENTRY_INIT: every class of theta0 has a constant centre */
+    /* entry state */
+    int32_t entry, iter0, cur, stale_par, stats_valid, last_changed, margins_on, cnt_par;
+    unsigned long long seq;
+    /* buffers (device) */
+    const uint32_t *x, *xt;
+    const int32_t *pop;
+    const int32_t *row_ptr, *col, *rrow_ptr, *rcol, *heavy;
+    const float *wgt;
+    float *prop, *center, *disp;
+    nemk_coef *coef;
+    uint32_t *mxor, *mval, *f0, *f1, *cm;
+    double *delta;
+    int32_t *ham, *stat;      /* stat = S[K*D] then n[K] */
+    uint8_t *lab[2], *stale[2];
+    float *margin;
+    int32_t *dirty, *wl[2], *wl_cnt;   /* wl_cnt[8]: [0..3] rotating fix-up counters, [4] delta list */
+    int32_t *hub_list;        /* [n_heavy] active hubs of a margin-cached round */
+    int32_t *scratch;         /* [16] ints, zero at rest: [0] active light sites [1] active hubs */
+    nemk_counters *cnt2;      /* [2] alternating per-sweep counter blocks, zero at entry */
+    unsigned *bar;            /* [2] device-wide barrier state (count, generation) */
+    nemk_persist_out *out;    /* mapped pinned host memory */
+} nemk_persist_args;
+
+/* grid the cooperative launch may use for this K (CTAs), 0 = unsupported device */
+int  nemk_persist_max_grid(int k);
+/* enqueue the kernel with `grid` CTAs (<= nemk_persist_max_grid) */
+void nemk_persist_launch(nemk_stream s, const nemk_persist_args *a, int grid);
+
 /* ---- helpers */
 void nemk_labels_to_t(nemk_stream s, int k, int n, const uint8_t *lab, float *t);
 void nemk_t_to_labels(nemk_stream s, int k, int n, const float *t, uint8_t *lab);

@@ -145,12 +145,13 @@ void nemb_destroy(nemb_handle *h)
     dbuf *all[] = {&h->b_x, &h->b_xt, &h->b_row_ptr, &h->b_col, &h->b_wgt, &h->b_rrow_ptr,
                    &h->b_rcol, &h->b_sites, &h->b_level_ptr, &h->b_flags, &h->b_heavy, &h->b_sub, &h->b_index, &h->b_pop,
                    &h->b_slab, &h->b_t[0],
-                   &h->b_t[1], &h->b_nem};
+                   &h->b_t[1], &h->b_nem, &h->b_pk};
     for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) release(all[i]);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_cnt_all) cudaFreeHost(h->h_cnt_all);
     if (h->h_empty) cudaFreeHost(h->h_empty);
     if (h->ring) cudaFreeHost(h->ring);
+    if (h->pk_out) cudaFreeHost(h->pk_out);
     if (h->h_lab_stage) cudaFreeHost(h->h_lab_stage);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 16; i++) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
@@ -667,6 +668,26 @@ static int ensure_pop(nemb_handle *h)
     return NEMB_OK;
 }
 
+/* ------------------------------------------------------------------ environment knobs */
+static int env_flag(const char *name) { const char *e = getenv(name); return e && *e; }
+static void read_env_knobs(nemb_handle *h)
+{
+    const char *e;
+    h->no_persist = env_flag("NEM_B200_NO_PERSIST");
+    h->keep_logpf = env_flag("NEM_B200_KEEP_LOGPF");
+    h->no_margins = env_flag("NEM_B200_NO_MARGINS");
+    h->no_popcache = env_flag("NEM_B200_NO_POPCACHE");
+    h->no_spec = env_flag("NEM_B200_NO_SPEC");
+    h->full_mstep = env_flag("NEM_B200_FULL_MSTEP");
+    h->full_exchange = env_flag("NEM_B200_FULL_EXCHANGE");
+    e = getenv("NEM_B200_MEDIUM_LIST");
+    h->medium_list = e && *e ? atoi(e) : 32768;
+    e = getenv("NEM_B200_PK_GRID");
+    h->pk_grid_env = e && *e ? atoi(e) : 0;
+    e = getenv("NEM_B200_PK_XLIMIT");           /* bytes of X the in-kernel X / X^T passes accept */
+    h->pk_xlimit = e && *e ? (size_t)strtoull(e, NULL, 10) : ((size_t)64 << 20);
+}
+
 /* ------------------------------------------------------------------ steps of one fit */
 static nemk_lpsrc lpsrc(const nemb_handle *h)
 {
@@ -692,7 +713,7 @@ static int run_tables(nemb_handle *h, int k, int next_uniform)
  * separate cached-rebuild launch exists */
 static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming, int lean)
 {
-    if (uniform == 2 && lean && d_hamming == NULL && !getenv("NEM_B200_NO_POPCACHE")) {
+    if (uniform == 2 && lean && d_hamming == NULL && !h->no_popcache) {
         /* every class has a constant centre: H from the cached row popcounts, X is not read */
         int rc = ensure_pop(h);
         if (rc != NEMB_OK) return rc;
@@ -820,8 +841,7 @@ static void local_fixups(nemb_handle *h, int k, double beta, const uint8_t *in, 
     /* few labels moved last iteration => the work lists are short: the tail cluster (8 CTAs) walks
      * them all; a medium list gets ONE grid-wide round first (the whole GPU takes the bulk, the
      * tail the rest); long or unknown lists get GRID_ROUNDS */
-    static int medium = -1;
-    if (medium < 0) { const char *e = getenv("NEM_B200_MEDIUM_LIST"); medium = e && *e ? atoi(e) : MEDIUM_LIST; }
+    const int medium = h->medium_list;
     int grid_rounds = (h->last_changed >= 0 && h->last_changed < SHORT_LIST)
                           ? (h->last_changed >= medium ? 1 : 0) : GRID_ROUNDS;
     for (int r = 0; r < grid_rounds; r++)
@@ -868,7 +888,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
         } else if (impl == NEMB_SWEEP_SPEC) {
             /* margin cache (one GPU, Hamming-count scores): sites whose margin exceeds what theta
              * can have moved and whose later neighbours kept their label are copied, not evaluated */
-            if (h->world == 1 && h->lp_from_ham && !getenv("NEM_B200_NO_MARGINS")) {
+            if (h->world == 1 && h->lp_from_ham && !h->no_margins) {
                 h->mg.m = h->d_margin;
                 h->mg.stale_cur = h->d_stale[h->stale_par];
                 h->mg.stale_next = h->d_stale[h->stale_par ^ 1];
@@ -910,7 +930,7 @@ static int run_sweep(nemb_handle *h, const nemb_options *o, double beta, int *fl
                      * (family, label) pairs instead of whole slices.  `seen` holds, on every
                      * rank, the labels as of the previous exchange (== the input labels at the
                      * start of a sweep). */
-                    int sparse = !getenv("NEM_B200_FULL_EXCHANGE") &&
+                    int sparse = !h->full_exchange &&
                                  (guard > 0 || (h->last_changed >= 0 && h->last_changed <= DELTA_CAP));
                     int settled = -1;
                     if (sparse) {
@@ -992,7 +1012,7 @@ static int run_mstep(nemb_handle *h, const nemb_options *o, int next_uniform)
     int k = o->k, rc;
     size_t kd = (size_t)k * h->d, stat = kd + k;
     int incremental = o->algo == NEMB_ALGO_NCEM && h->stats_valid && h->prev_valid && h->last_changed >= 0 &&
-                      h->last_changed <= h->n / 8 && !getenv("NEM_B200_FULL_MSTEP");
+                      h->last_changed <= h->n / 8 && !h->full_mstep;
     STAGE_BEGIN(incremental ? ST_MSTEP_DELTA : ST_MSTEP);
     if (o->algo == NEMB_ALGO_NCEM) {
         /* exact integer counts S_kd, n_k of this rank's rows: a full recount through X^T, or --
@@ -1115,6 +1135,7 @@ static int run_estim_beta(nemb_handle *h, const nemb_options *o, float *beta_io,
 
 static int check_options(nemb_handle *h, const nemb_options *o)
 {
+    read_env_knobs(h);
     if (!h->loaded) return fail(h, NEMB_E_ARG, "no pangenome loaded");
     if (o->k < 1 || o->k > NEMB_MAX_K) return fail(h, NEMB_E_ARG, "k must be in 1..%d (here %d)", NEMB_MAX_K, o->k);
     if (o->algo != NEMB_ALGO_NEM && o->algo != NEMB_ALGO_NCEM) return fail(h, NEMB_E_ARG, "bad algo %d", o->algo);
@@ -1155,11 +1176,194 @@ static int init_state(nemb_handle *h, const nemb_options *o)
     return NEMB_OK;
 }
 
+/* ------------------------------------------------------------------ persistent EM kernel */
+/* Which fits run as ONE cooperative launch (nem_persist.cuh): ncem on the popcount density path
+ * with the per-class dispersion models, one GPU, started from theta -- PPanGGOLiN's call
+ * (ppanggolin.py:1814-1826) without the per-iteration log.  Everything else keeps the
+ * launch-per-stage loop of em_core. */
+static int persist_eligible(nemb_handle *h, const nemb_options *o, int uniform0, int has_cb,
+                            const float *t_init)
+{
+    if (h->world != 1 || t_init || has_cb || o->dolog || h->no_persist) return 0;
+    if (o->algo != NEMB_ALGO_NCEM || o->param_fixed || o->conv == NEMB_CONV_CRIT) return 0;
+    if (o->beta_mode == NEMB_BETA_PSGRAD && h->spatial) return 0;
+    if (uniform0 < 1 || !(o->disp == NEMB_DISP_K_ || o->disp == NEMB_DISP___)) return 0;
+    if (o->sweep_impl != NEMB_SWEEP_AUTO && o->sweep_impl != NEMB_SWEEP_SPEC) return 0;
+    if (h->keep_logpf) return 0;
+    return nemk_persist_max_grid(o->k) > 0;
+}
+
+static int ensure_persist(nemb_handle *h)
+{
+    if (!h->pk_out) {
+        CK(cudaHostAlloc((void **)&h->pk_out, sizeof(nemk_persist_out), cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h->pk_out, 0, sizeof(nemk_persist_out));
+        CK(cudaHostGetDevicePointer((void **)&h->d_pk_out, h->pk_out, 0));
+    }
+    size_t off = 0;
+    size_t o_hub = carve(&off, sizeof(int32_t) * ((size_t)h->n_heavy + 1));
+    size_t o_scr = carve(&off, sizeof(int32_t) * 16);
+    size_t o_cnt = carve(&off, sizeof(nemk_counters) * 2);
+    size_t o_bar = carve(&off, sizeof(unsigned) * 4);
+    int fresh = h->b_pk.cap < off;
+    int rc = reserve(h, &h->b_pk, off);
+    if (rc != NEMB_OK) return rc;
+    char *base = h->b_pk.p;
+    h->d_pk_hub = (int32_t *)(base + o_hub);
+    int32_t *scr = (int32_t *)(base + o_scr);
+    nemk_counters *cnt2 = (nemk_counters *)(base + o_cnt);
+    unsigned *bar = (unsigned *)(base + o_bar);
+    if (fresh || scr != h->d_pk_scratch || cnt2 != h->d_pk_cnt2 || bar != h->d_pk_bar) {
+        /* zero at rest: the kernel leaves its counters, lists and the barrier clean */
+        CK(cudaMemsetAsync(base + o_scr, 0, off - o_scr, h->stream));
+        h->pk_cnt_par = 0;
+    }
+    h->d_pk_scratch = scr; h->d_pk_cnt2 = cnt2; h->d_pk_bar = bar;
+    return NEMB_OK;
+}
+
+static int wait_persist(nemb_handle *h, unsigned long long seq)
+{
+    volatile nemk_persist_out *s = h->pk_out;
+    for (unsigned spins = 1; s->seq != seq; spins++) {
+        if ((spins & 0xfff) == 0) {
+            cudaError_t e = cudaStreamQuery(h->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return fail(h, NEMB_E_CUDA, "device error inside the persistent EM kernel: %s", cudaGetErrorString(e));
+            if (e == cudaSuccess && s->seq != seq)
+                return fail(h, NEMB_E_BUG, "persistent EM kernel ended without status %llu (slot holds %llu)", seq,
+                            (unsigned long long)s->seq);
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if (h->poll_relaxed && spins > 64) {
+            struct timespec ts = {0, 2000};
+            nanosleep(&ts, NULL);
+        } else if ((spins & 0xff) == 0) sched_yield();
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return NEMB_OK;
+}
+
+static int run_density(nemb_handle *h, int k, int uniform, int32_t *d_hamming, int lean);
+
+/* the whole fit up to (not including) the final criteria; fills iter / converged / status / empty
+ * the way em_core's loop does */
+static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_result *res,
+                      int *iter_out, int *converged_out, int *status_out, int *empty_out)
+{
+    int k = o->k, rc;
+    const float betaf = h->spatial ? o->beta : 0.0f;          /* nem_exe.c:570-574 */
+    const size_t kd = (size_t)k * h->d;
+    if ((rc = ensure_persist(h)) != NEMB_OK) return rc;
+    nemk_persist_args a;
+    memset(&a, 0, sizeof a);
+    a.K = k; a.n = h->n; a.D = h->d; a.wpr = h->wpr; a.nwt = h->nwt;
+    a.prop_model = o->prop; a.disp_model = o->disp; a.conv = o->conv; a.it_max = o->it_max;
+    a.conv_thr = o->conv_thr;
+    a.beta = (double)betaf;
+    a.use_graph = h->spatial && a.beta != 0.0;
+    a.seq_sweep = a.use_graph && o->update == NEMB_UPDATE_SEQ;
+    a.n_heavy = h->n_heavy; a.wsum_any_order = h->wgt_integral;
+    a.use_margins = !h->no_margins;
+    size_t xbytes = sizeof(uint32_t) * (size_t)h->n * h->wpr;
+    a.x_in_kernel = xbytes <= h->pk_xlimit;
+    a.init_from_pop = uniform0 == 2 && !h->no_popcache;
+    if (a.init_from_pop && (rc = ensure_pop(h)) != NEMB_OK) return rc;
+    if (a.x_in_kernel && (rc = ensure_xt(h)) != NEMB_OK) return rc;
+    a.x = h->d_x; a.xt = h->d_xt; a.pop = h->d_pop;
+    a.row_ptr = h->d_row_ptr; a.col = h->d_col; a.rrow_ptr = h->d_rrow_ptr; a.rcol = h->d_rcol;
+    a.heavy = h->d_heavy; a.wgt = h->d_wgt;
+    a.prop = h->d_prop; a.center = h->d_center; a.disp = h->d_disp; a.coef = h->d_coef;
+    a.mxor = h->d_mxor; a.mval = h->d_mval; a.f0 = h->d_f0; a.f1 = h->d_f1; a.cm = h->d_cm;
+    a.delta = h->d_delta; a.ham = h->d_ham; a.stat = h->d_stat_loc;
+    a.lab[0] = h->d_lab[0]; a.lab[1] = h->d_lab[1];
+    a.stale[0] = h->d_stale[0]; a.stale[1] = h->d_stale[1];
+    a.margin = h->d_margin; a.dirty = h->d_dirty; a.wl[0] = h->d_wl[0]; a.wl[1] = h->d_wl[1];
+    a.wl_cnt = h->d_wl_counts;
+    a.hub_list = h->d_pk_hub; a.scratch = h->d_pk_scratch; a.cnt2 = h->d_pk_cnt2; a.bar = h->d_pk_bar;
+    a.out = h->d_pk_out;
+    /* host state of a fresh fit (the kernel's prep phase writes the device side) */
+    h->cur = 0; h->state_labels = 1;
+    h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1; h->prev_valid = 0;
+    h->stale_par = 0; h->sweep_same_beta = 0; h->lp_from_ham = 1;
+    memset(&h->mg, 0, sizeof h->mg);
+    a.entry = NEMK_PK_ENTRY_INIT; a.iter0 = 0; a.cur = 0; a.stale_par = 0; a.stats_valid = 0;
+    a.last_changed = -1; a.margins_on = 0;
+    int grid = nemk_persist_max_grid(k);
+    int want = (h->n + 511) / 512;
+    if (want < 16) want = 16;
+    if (h->pk_grid_limit > 0 && want > h->pk_grid_limit) want = h->pk_grid_limit;
+    if (h->pk_grid_env > 0) want = h->pk_grid_env;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    int done = 0, guard = 0;
+    nemk_persist_out out;
+    memset(&out, 0, sizeof out);
+    while (!done) {
+        if (++guard > 4 * (o->it_max + 4)) return fail(h, NEMB_E_BUG, "persistent EM kernel keeps leaving");
+        a.cnt_par = h->pk_cnt_par;
+        a.seq = ++h->pk_seq;
+        nemk_persist_launch(h->stream, &a, grid);
+        h->launches++;
+        res->pk_launches++;
+        CKK();
+        if ((rc = wait_persist(h, a.seq)) != NEMB_OK) return rc;
+        memcpy(&out, (const void *)h->pk_out, sizeof out);
+        h->pk_cnt_par = out.cnt_par;
+        h->cur = out.cur; h->stale_par = out.stale_par; h->last_changed = out.last_changed;
+        h->stats_valid = out.stats_valid; h->prev_valid = out.sweeps > 0 || a.entry != NEMK_PK_ENTRY_INIT;
+        h->ham_valid = 1;
+        h->fixup_rounds += out.fixup_rounds;
+        res->n_kept += out.kept;
+        res->pk_barriers += out.barriers; res->pk_x_passes += out.x_passes; res->pk_recounts += out.recounts;
+        if (out.sweeps > 0) { res->n_allnul = out.n_allnul; res->n_ties = out.n_ties; }
+        if (out.exit_code == NEMK_PK_EXIT_DONE) { done = 1; break; }
+        a.entry = out.resume_entry; a.iter0 = out.iters; a.cur = out.cur; a.stale_par = out.stale_par;
+        a.stats_valid = out.stats_valid; a.last_changed = out.last_changed;
+        a.margins_on = out.sweeps > 0 || a.margins_on;
+        if (out.exit_code == NEMK_PK_EXIT_NEED_DENSITY) {
+            /* the class masks moved and X does not fit the L2: the TMA-tiled X pass (HBM-bound) */
+            if ((rc = run_density(h, k, 1, NULL, 1)) != NEMB_OK) return rc;
+            res->pk_x_passes++;
+        } else if (out.exit_code == NEMK_PK_EXIT_NEED_RECOUNT) {
+            /* full recount of S = X^T T through the transposed bits (HBM-bound) */
+            if ((rc = ensure_xt(h)) != NEMB_OK) return rc;
+            STAGE_BEGIN(ST_MSTEP);
+            nemk_label_masks(h->stream, k, h->n, h->nwt, h->d_lab[h->cur], h->d_cm, h->d_stat_loc + kd,
+                             NULL, &h->d_coef->halt);
+            nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_stat_loc, &h->d_coef->halt);
+            CK(cudaMemsetAsync(&h->d_coef->uniform_ok, 1, sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(&h->d_coef->mu_changed, 0, sizeof(int32_t), h->stream));
+            STAGE_END();
+            h->launches += 2;
+            res->pk_recounts++;
+            CKK();
+        } else
+            return fail(h, NEMB_E_BUG, "persistent EM kernel: unknown exit code %d", out.exit_code);
+    }
+    h->sweep_same_beta = 1;
+    *iter_out = out.iters; *converged_out = out.converged; *empty_out = out.empty_class;
+    *status_out = out.empty_class ? NEMB_W_EMPTYCLASS : NEMB_OK;
+    return NEMB_OK;
+}
+
 /* EM from the theta already resident on the device (d_prop/d_center/d_disp). */
 static int upload_state(nemb_handle *h, const nemb_options *o, const float *t);
 
 /* t_init != NULL: INIT_FILE (nem_alg.c:1091-1113) -- NemAlgo starts from that classification, the
  * two initial sweeps are not run and theta comes from the first M-step. */
+/* CK / CKK inside em_core leave through its cleanup label */
+#define CKO(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            rc = fail(h, e_ == cudaErrorMemoryAllocation ? NEMB_E_MEMORY : NEMB_E_CUDA,    \
+                      "%s: %s", #call, cudaGetErrorString(e_));                            \
+            goto out;                                                                      \
+        }                                                                                  \
+    } while (0)
 static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_result *res,
                    nemb_iter_cb cb, void *user, float *prop, float *center, float *disp,
                    const float *t_init)
@@ -1171,26 +1375,37 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     const int psgrad = o->beta_mode == NEMB_BETA_PSGRAD && h->spatial;
     int uniform_m = o->param_fixed ? uniform0 : (o->disp == NEMB_DISP_K_ || o->disp == NEMB_DISP___);   /* 1: theta lives on the device */
     int want_crit_each = o->dolog || o->conv == NEMB_CONV_CRIT;
-    int lean = o->algo == NEMB_ALGO_NCEM && !getenv("NEM_B200_KEEP_LOGPF");
+    int lean = o->algo == NEMB_ALGO_NCEM && !h->keep_logpf;
     size_t kd = (size_t)k * h->d;
     float *nk_host = cb ? malloc(sizeof(float) * k) : NULL;
+    int iter = 0, enq = 0, converged = 0, status = NEMB_OK, empty = 0;
+    int flips[2] = {0, 0};
+    unsigned long long seqs[2] = {0, 0};
+    double oldcrit = 0.0;
+    int can_spec;
+    /* one cooperative launch for the whole fit where it applies (nem_persist.cuh) */
+    const int persist = lean && persist_eligible(h, o, uniform0, cb != NULL, t_init);
+    if (cb && !nk_host) { rc = fail(h, NEMB_E_MEMORY, "host memory"); goto out; }
+    if (persist) {
+        if ((rc = em_persist(h, o, uniform0, res, &iter, &converged, &status, &empty)) != NEMB_OK) goto out;
+        goto tail;
+    }
 
-    if ((rc = init_state(h, o)) != NEMB_OK) return rc;
+    if ((rc = init_state(h, o)) != NEMB_OK) goto out;
     if (t_init) {
-        if ((rc = upload_state(h, o, t_init)) != NEMB_OK) return rc;
+        if ((rc = upload_state(h, o, t_init)) != NEMB_OK) goto out;
     } else {
-    if ((rc = run_tables(h, k, 0)) != NEMB_OK) return rc;
-    if ((rc = run_density(h, k, uniform0, NULL, lean)) != NEMB_OK) return rc;
+    if ((rc = run_tables(h, k, 0)) != NEMB_OK) goto out;
+    if ((rc = run_density(h, k, uniform0, NULL, lean)) != NEMB_OK) goto out;
     /* ComputePartitionFromPara(Needinit=1): blind sweep then beta sweep (nem_alg.c:1970-1981) */
-    if ((rc = run_sweep(h, o, 0.0, &flipped, NULL, NULL)) != NEMB_OK) return rc;
-    if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
-    if ((rc = run_sweep(h, o, beta, &flipped, NULL, NULL)) != NEMB_OK) return rc;
-    if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
+    if ((rc = run_sweep(h, o, 0.0, &flipped, NULL, NULL)) != NEMB_OK) goto out;
+    if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) goto out;
+    if ((rc = run_sweep(h, o, beta, &flipped, NULL, NULL)) != NEMB_OK) goto out;
+    if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) goto out;
     swept_beta = beta;
     }
-    double oldcrit = 0.0;
     if (!t_init && (o->dolog || cb || o->it_max == 0)) {
-        if ((rc = read_status(h)) != NEMB_OK) return rc;
+        if ((rc = read_status(h)) != NEMB_OK) goto out;
         h->fixup_rounds += h->h_status->cnt.nfix;
         res->n_allnul = h->h_status->cnt.allnul;
         res->n_ties = h->h_status->cnt.ties;
@@ -1207,40 +1422,37 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
      * NEXT iteration is enqueued before this one's status is known.  If this one ends the fit, the
      * device halt flag turns every kernel of the speculative iteration into a no-op and its
      * host-side effects (buffer flip) are undone below. */
-    int iter = 0, enq = 0, converged = 0, status = NEMB_OK, empty = 0;
-    int flips[2] = {0, 0};
-    unsigned long long seqs[2] = {0, 0};
-    int can_spec = !o->dolog && !cb && !want_crit_each && !h->profile && h->world == 1 && !psgrad &&
-                   o->algo == NEMB_ALGO_NCEM && !o->param_fixed && !getenv("NEM_B200_NO_SPEC");
+    can_spec = !o->dolog && !cb && !want_crit_each && !h->profile && h->world == 1 && !psgrad &&
+                   o->algo == NEMB_ALGO_NCEM && !o->param_fixed && !h->no_spec;
     while (iter < o->it_max && !converged && status == NEMB_OK) {
         int want = iter + 1;
         if (can_spec && want < o->it_max && h->stats_valid && h->last_changed >= 0 &&
             h->last_changed <= h->n / 8)
             want++;
         for (; enq < want; enq++) {
-            if (!o->param_fixed && (rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
+            if (!o->param_fixed && (rc = run_mstep(h, o, uniform_m)) != NEMB_OK) goto out;
             if (psgrad) {            /* EstimBeta follows the M-step (nem_alg.c:1810-1812) */
-                if ((rc = run_estim_beta(h, o, &betaf, NULL)) != NEMB_OK) return rc;
+                if ((rc = run_estim_beta(h, o, &betaf, NULL)) != NEMB_OK) goto out;
                 beta = (double)betaf;
             }
-            if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
-            if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) return rc;
+            if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) goto out;
+            if (o->dolog && (rc = run_criteria(h, o, beta, h->d_status->crit_before)) != NEMB_OK) goto out;
             int status_read = 0;
             h->sweep_same_beta = swept_beta == beta;   /* the previous sweep used this beta: cached margins may apply */
             swept_beta = beta;
-            if ((rc = run_sweep(h, o, beta, &flipped, (want_crit_each || cb) ? NULL : o, &status_read)) != NEMB_OK) return rc;
-            if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
+            if ((rc = run_sweep(h, o, beta, &flipped, (want_crit_each || cb) ? NULL : o, &status_read)) != NEMB_OK) goto out;
+            if (want_crit_each && (rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) goto out;
             if (cb) {
-                CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+                CKO(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
+                CKO(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+                CKO(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
             }
             flips[enq & 1] = flipped;
             if (status_read && !want_crit_each && !cb) seqs[enq & 1] = h->seq;   /* the sweep's last status */
-            else if ((rc = publish_status(h, o, &seqs[enq & 1])) != NEMB_OK) return rc;
+            else if ((rc = publish_status(h, o, &seqs[enq & 1])) != NEMB_OK) goto out;
         }
-        if ((rc = wait_status(h, seqs[iter & 1])) != NEMB_OK) return rc;
-        if (cb) CK(cudaStreamSynchronize(h->stream));   /* theta copies of this iteration */
+        if ((rc = wait_status(h, seqs[iter & 1])) != NEMB_OK) goto out;
+        if (cb) CKO(cudaStreamSynchronize(h->stream));   /* theta copies of this iteration */
         flipped = flips[iter & 1];
         iter++;
         h->last_changed = o->algo == NEMB_ALGO_NCEM ? h->h_status->cnt.changed : -1;
@@ -1269,11 +1481,11 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
                 for (int c = 0; c < k; c++) nk_host[c] = NAN;
             } else if (o->algo == NEMB_ALGO_NCEM) {
                 int32_t ni[NEMB_MAX_K];
-                CK(cudaMemcpy(ni, (h->world > 1 ? h->d_stat_int : h->d_stat_loc) + kd, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
+                CKO(cudaMemcpy(ni, (h->world > 1 ? h->d_stat_int : h->d_stat_loc) + kd, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));
                 for (int c = 0; c < k; c++) nk_host[c] = (float)ni[c];
             } else {
                 double nd[NEMB_MAX_K];
-                CK(cudaMemcpy(nd, h->d_stat_dbl + kd, sizeof(double) * k, cudaMemcpyDeviceToHost));
+                CKO(cudaMemcpy(nd, h->d_stat_dbl + kd, sizeof(double) * k, cudaMemcpyDeviceToHost));
                 for (int c = 0; c < k; c++) nk_host[c] = (float)nd[c];
             }
             cb(user, iter, h->h_status->crit_before, h->h_status->crit_after, prop, center, disp, nk_host);
@@ -1282,13 +1494,14 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     if (enq > iter) {
         /* the speculative iteration behind the last one: a no-op on the device if the fit ended
          * (halt), otherwise (it_max cannot be hit here: want < it_max) it must not exist */
-        if (!(converged || status != NEMB_OK)) return fail(h, NEMB_E_BUG, "speculative iteration left over");
+        if (!(converged || status != NEMB_OK)) { rc = fail(h, NEMB_E_BUG, "speculative iteration left over"); goto out; }
         if (flips[(enq - 1) & 1]) h->cur ^= 1;
     }
+tail:
     if (h->world > 1 && status == NEMB_OK && iter > 0) {
         /* row shards: the per-iteration statuses of the speculative sweep carry this rank's
          * all-null / tie counters only; one counter all-gather gives the totals of the last sweep */
-        if ((rc = read_status(h)) != NEMB_OK) return rc;
+        if ((rc = read_status(h)) != NEMB_OK) goto out;
         res->n_allnul = h->h_status->cnt.allnul;
         res->n_ties = h->h_status->cnt.ties;
     }
@@ -1297,26 +1510,28 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
         /* MakeParaFromLabeled: "Class %d has no labeled observation" (nem_alg.c:1338-1345) --
          * NemAlgo is not entered */
         res->status = status; res->iters = 0; res->empty_class = empty;
-        free(nk_host);
-        return NEMB_OK;
+        rc = NEMB_OK;
+        goto out;
     }
     if (iter == 0) { /* nem_alg.c:1845-1851 */
-        if ((rc = run_mstep(h, o, uniform_m)) != NEMB_OK) return rc;
-        if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) return rc;
+        if ((rc = run_mstep(h, o, uniform_m)) != NEMB_OK) goto out;
+        if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) goto out;
     }
-    if ((rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) return rc;
-    CK(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if ((rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) goto out;
+    CKO(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
+    CKO(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+    CKO(cudaMemcpyAsync(disp, h->d_disp, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
+    CKO(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
+    CKO(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CKO(cudaStreamSynchronize(h->stream));
     if (iter == 0 && *h->h_empty) { status = NEMB_W_EMPTYCLASS; empty = *h->h_empty; }
     res->status = status; res->iters = iter; res->converged = converged; res->empty_class = empty;
     const double *c6 = h->h_status->crit_after;
     res->U = c6[0]; res->D = c6[1]; res->L = c6[2]; res->M = c6[3]; res->Z = c6[4]; res->G = c6[5];
+    rc = NEMB_OK;
+out:
     free(nk_host);
-    return NEMB_OK;
+    return rc;
 }
 
 static void collect_profile(nemb_handle *h, nemb_result *res, cudaEvent_t e0, cudaEvent_t e1)

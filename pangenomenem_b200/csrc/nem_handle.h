@@ -97,6 +97,20 @@ struct nemb_handle {
     int32_t *h_empty;
     nemk_host_status *ring, *d_ring;          /* mapped pinned status slots, host / device view */
     unsigned long long seq;                   /* last sequence number handed to nemk_iter_end */
+    /* persistent EM kernel: scratch (hub list, counters, barrier), mapped status block */
+    dbuf b_pk;
+    int32_t *d_pk_hub, *d_pk_scratch;
+    nemk_counters *d_pk_cnt2;
+    unsigned *d_pk_bar;
+    nemk_persist_out *pk_out, *d_pk_out;
+    unsigned long long pk_seq;
+    int pk_cnt_par, pk_ready_n, pk_ready_heavy;
+    int pk_grid_limit;     /* > 0: CTAs a fit of this handle may use (concurrent fits share the GPU) */
+    /* environment knobs (tests / A-B runs), read ONCE per fit by read_env_knobs() instead of a
+     * getenv() per sweep */
+    int no_persist, keep_logpf, no_margins, no_popcache, no_spec, full_mstep, full_exchange;
+    int medium_list, pk_grid_env;
+    size_t pk_xlimit;      /* X up to this many bytes: the X / X^T passes run inside the persistent kernel */
     /* fit bookkeeping */
     int64_t launches, fixup_rounds, exchanges;
     int profile;

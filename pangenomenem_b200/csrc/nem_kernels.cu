@@ -1805,15 +1805,14 @@ k_changed_rows16(int n, const uint8_t *__restrict__ lab, const uint8_t *__restri
 // column of genome 32w+b, which meets the rows' old/new class masks by popcount.  Items are spread
 // over the whole grid, so a few hundred changed rows cost microseconds.
 #define DELTA_CHUNK 4
+// the items of the incremental update, spread over the warps of the whole grid (shared by the
+// standalone kernel and the persistent EM kernel)
 template <int KT>
-__global__ void __launch_bounds__(256)
-k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8_t *__restrict__ lab,
-              const uint8_t *__restrict__ lab_m, const int32_t *__restrict__ list,
-              const int32_t *__restrict__ count, int32_t *S, int32_t *nk,
-              const int32_t *__restrict__ halt) {
-    if (halt && *halt) return;
+static __device__ __forceinline__ void mstep_delta_items(int K, int D, int wpr, const uint32_t *x,
+                                                         const uint8_t *lab, const uint8_t *lab_m,
+                                                         const int32_t *list, int total, int32_t *S,
+                                                         int32_t *nk) {
     const int lane = threadIdx.x & 31;
-    const int total = *count;
     const int groups = (total + 31) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
     const int wreal = (D + 31) >> 5;
     const int chunks = (wreal + DELTA_CHUNK - 1) / DELTA_CHUNK;
@@ -1868,6 +1867,16 @@ k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8
             }
         }
     }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8_t *__restrict__ lab,
+              const uint8_t *__restrict__ lab_m, const int32_t *__restrict__ list,
+              const int32_t *__restrict__ count, int32_t *S, int32_t *nk,
+              const int32_t *__restrict__ halt) {
+    if (halt && *halt) return;
+    mstep_delta_items<KT>(K, D, wpr, x, lab, lab_m, list, *count, S, nk);
 }
 
 // nem (fuzzy): partial sums over a chunk of families, thread = genome, fp64, fixed order.
@@ -2467,9 +2476,14 @@ __global__ void k_t_to_labels(int K, int n, const float *__restrict__ t, uint8_t
     lab[i] = (mx > 0.f) ? (uint8_t)km : (uint8_t)255;  // all-zero row = unlabelled (calloc'd ClassifM)
 }
 
+#include "nem_persist.cuh"
+
 // =============================================================================================
 // launch layer
 // =============================================================================================
+#ifdef NEMK_DEV_K3   /* development builds: K = 3 only (compile time) */
+#define DISPATCH_K(K, CALL) do { constexpr int KT = 3; CALL; } while (0)
+#else
 #define DISPATCH_K(K, CALL)                      \
     do {                                         \
         if ((K) <= 2) { constexpr int KT = 2; CALL; }        \
@@ -2478,6 +2492,7 @@ __global__ void k_t_to_labels(int K, int n, const float *__restrict__ t, uint8_t
         else if ((K) <= 8) { constexpr int KT = 8; CALL; }   \
         else { constexpr int KT = 16; CALL; }                \
     } while (0)
+#endif
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -3011,4 +3026,31 @@ extern "C" void nemk_t_to_labels(nemk_stream s, int k, int n, const float *t, ui
 }
 extern "C" void nemk_fill_u8(nemk_stream s, uint8_t *p, int v, size_t n) {
     cudaMemsetAsync(p, v, n, S(s));
+}
+
+// ---- persistent EM kernel (nem_persist.cuh)
+template <int KT>
+static int persist_max_grid_t() {
+    int dev = 0, coop = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_em_persist<KT>, PK_THREADS, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return per_sm * num_sms();
+}
+extern "C" int nemk_persist_max_grid(int k) {
+    static int cache[5] = {-1, -1, -1, -1, -1};
+    int slot = k <= 2 ? 0 : k == 3 ? 1 : k == 4 ? 2 : k <= 8 ? 3 : 4;
+    if (cache[slot] < 0) DISPATCH_K(k, (cache[slot] = persist_max_grid_t<KT>()));
+    return cache[slot];
+}
+extern "C" void nemk_persist_launch(nemk_stream s, const nemk_persist_args *a, int grid) {
+    nemk_persist_args copy = *a;
+    void *params[1] = {&copy};
+    DISPATCH_K(a->K, (cudaLaunchCooperativeKernel((void *)k_em_persist<KT>, dim3(grid), dim3(PK_THREADS),
+                                                  params, 0, S(s))));
+    note_launch();
 }
