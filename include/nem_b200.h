@@ -224,6 +224,14 @@ int nemb_fit_random(nemb_handle *h, const nemb_options *opt, int n_starts, int64
  * the first EstimPara of NemAlgo); a class without any family ends the call with
  * NEMB_W_EMPTYCLASS ("Class %d has no labeled observation", nem_alg.c:1338-1345).
  * prop/center/disp are outputs only.  Single GPU. */
+/* Phase profile of the persistent EM kernel during the last fit: nanoseconds CTA 0 spent in
+ * 0 init, 1 changed-rows scan, 2 delta statistics, 3 full recount, 4 closed forms + tables,
+ * 5 X pass, 6 margin test, 7 active-list evaluation, 8 dense Jacobi round, 9 fix-up rounds
+ * (barrier waits included); [10] = fix-up rounds executed. */
+int nemb_get_persist_profile(nemb_handle *h, unsigned long long out12[12]);
+/* Per EM iteration (first 12 of the last launch): ns of scan, delta/recount, closed forms, margin
+ * test, evaluation, fix-up rounds; active sites of the evaluation (-1 = dense round); rounds. */
+int nemb_get_persist_trace(nemb_handle *h, long long out96[96]);
 int nemb_fit_from_partition(nemb_handle *h, const nemb_options *opt, const float *t_init,
                             float *prop, float *center, float *disp, nemb_result *res);
 

@@ -374,6 +374,27 @@ class Engine:
         self._check(self.lib.nemb_get_posteriors(self.h, _p(out)))
         return out
 
+    PK_PHASES = ("init", "scan", "delta", "recount", "finalize", "xpass", "margin_test", "eval_list",
+                 "eval_dense", "fixup")
+
+    def persist_profile(self) -> dict:
+        """Per-phase microseconds of the persistent EM kernel during the last fit (CTA 0's clock,
+        barrier waits included) + the number of fix-up rounds."""
+        buf = (C.c_ulonglong * 12)()
+        self._check(self.lib.nemb_get_persist_profile(self.h, buf))
+        d = {name: buf[i] / 1e3 for i, name in enumerate(self.PK_PHASES)}
+        d["fixup_rounds"] = int(buf[10])
+        return d
+
+    def persist_trace(self) -> np.ndarray:
+        """[12, 8] per-iteration trace of the last persistent launch: us of scan, delta/recount,
+        finalize, margin test, evaluation, fix-up; active sites (-1 dense); fix-up rounds."""
+        buf = (C.c_longlong * 96)()
+        self._check(self.lib.nemb_get_persist_trace(self.h, buf))
+        t = np.array(buf[:], dtype=np.float64).reshape(12, 8)
+        t[:, :6] /= 1e3
+        return t
+
     def labels(self, first: int = 0, count: int | None = None, out: np.ndarray | None = None):
         """MAP labels of families [first, first + count) (default: all); `out` (int32, C order)
         is reused when given -- a long-lived caller avoids a fresh 4N-byte array per call."""

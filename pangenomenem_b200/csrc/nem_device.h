@@ -310,10 +310,19 @@ enum { NEMK_PK_EXIT_DONE = 0, NEMK_PK_EXIT_NEED_DENSITY = 1, NEMK_PK_EXIT_NEED_R
 typedef struct {
     int32_t exit_code, resume_entry;    /* NEED_*: run the pass, re-enter at resume_entry */
     int32_t iters, converged, empty_class;
-    int32_t cur, stale_par, last_changed, stats_valid, cnt_par;
+    int32_t cur, stale_par, last_changed, stats_valid, cnt_par, delta_mode;
     int32_t n_allnul, n_ties;           /* of the last sweep */
     int32_t sweeps, x_passes, recounts, barriers;
     long long kept, fixup_rounds;       /* summed over the sweeps of this launch */
+    /* nanoseconds CTA 0 spent in each phase, barrier waits included (globaltimer): 0 init (prep,
+     * tables, first densities) 1 changed-rows scan 2 delta statistics 3 full recount 4 closed forms
+     * + tables 5 X pass 6 margin test 7 evaluation of the active list 8 dense Jacobi round
+     * 9 fix-up rounds 10 fix-up rounds executed (count) 11 spare */
+    unsigned long long phase_ns[12];
+    /* the same per EM iteration (first 12 iterations of the launch): [it][0..5] = ns of scan, delta
+     * (or recount), finalize, margin test, evaluation, fix-up rounds; [it][6] = active sites of the
+     * evaluation (-1: dense round), [it][7] = fix-up rounds */
+    long long trace[12][8];
     unsigned long long seq;             /* written last, after a system-wide fence */
 } nemk_persist_out;
 
@@ -329,7 +338,8 @@ typedef struct {
     int32_t x_in_kernel;      /* X and X^T passes may run inside the kernel (L2-sized problem) */
     int32_t init_from_pop;    /* ENTRY_INIT: every class of theta0 has a constant centre */
     /* entry state */
-    int32_t entry, iter0, cur, stale_par, stats_valid, last_changed, margins_on, cnt_par;
+    int32_t entry, iter0, cur, stale_par, stats_valid, last_changed, margins_on, cnt_par, delta_mode;
+    int32_t n_allnul, n_ties;   /* of the last sweep so far (carried over a re-entry) */
     unsigned long long seq;
     /* buffers (device) */
     const uint32_t *x, *xt;
@@ -343,9 +353,13 @@ typedef struct {
     int32_t *ham, *stat;      /* stat = S[K*D] then n[K] */
     uint8_t *lab[2], *stale[2];
     float *margin;
-    int32_t *dirty, *wl[2], *wl_cnt;   /* wl_cnt[8]: [0..3] rotating fix-up counters, [4] delta list */
-    int32_t *hub_list;        /* [n_heavy] active hubs of a margin-cached round */
-    int32_t *scratch;         /* [16] ints, zero at rest: [0] active light sites [1] active hubs */
+    int32_t *dirty, *wl[2], *wl_cnt;   /* wl_cnt[8]: [0..3] rotating fix-up counters, [4] changed rows */
+    int32_t *hub_list;        /* unused (kept for layout) */
+    int32_t *wlist[2];        /* fix-up work lists (duplicates allowed), wl_cap entries each */
+    int32_t wl_cap, pad0;
+    uint8_t *evflag;          /* [n] flags of every site's LAST evaluation: bit0 all-null, bit1 tie */
+    int32_t *scratch;         /* [16] ints, zero at rest: [3] all-null rows [4] ties of the last sweep,
+                                 [8..11] overflow flags of the rotating work lists */
     nemk_counters *cnt2;      /* [2] alternating per-sweep counter blocks, zero at entry */
     unsigned *bar;            /* [2] device-wide barrier state (count, generation) */
     nemk_persist_out *out;    /* mapped pinned host memory */

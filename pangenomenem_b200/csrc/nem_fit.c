@@ -1201,7 +1201,10 @@ static int ensure_persist(nemb_handle *h)
         CK(cudaHostGetDevicePointer((void **)&h->d_pk_out, h->pk_out, 0));
     }
     size_t off = 0;
-    size_t o_hub = carve(&off, sizeof(int32_t) * ((size_t)h->n_heavy + 1));
+    size_t cap = (size_t)(h->nnz > h->n ? h->nnz : h->n) + 64;   /* work-list entries (duplicates allowed) */
+    size_t o_wl0 = carve(&off, sizeof(int32_t) * cap), o_wl1 = carve(&off, sizeof(int32_t) * cap);
+    size_t o_evf = carve(&off, (size_t)h->n + 64);
+    size_t o_hub = carve(&off, sizeof(int32_t) * 4);
     size_t o_scr = carve(&off, sizeof(int32_t) * 16);
     size_t o_cnt = carve(&off, sizeof(nemk_counters) * 2);
     size_t o_bar = carve(&off, sizeof(unsigned) * 4);
@@ -1210,6 +1213,9 @@ static int ensure_persist(nemb_handle *h)
     if (rc != NEMB_OK) return rc;
     char *base = h->b_pk.p;
     h->d_pk_hub = (int32_t *)(base + o_hub);
+    h->d_pk_wl[0] = (int32_t *)(base + o_wl0); h->d_pk_wl[1] = (int32_t *)(base + o_wl1);
+    h->d_pk_evflag = (uint8_t *)(base + o_evf);
+    h->pk_wl_cap = (int)(cap > 0x7fffffff ? 0x7fffffff : cap);
     int32_t *scr = (int32_t *)(base + o_scr);
     nemk_counters *cnt2 = (nemk_counters *)(base + o_cnt);
     unsigned *bar = (unsigned *)(base + o_bar);
@@ -1282,6 +1288,7 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     a.stale[0] = h->d_stale[0]; a.stale[1] = h->d_stale[1];
     a.margin = h->d_margin; a.dirty = h->d_dirty; a.wl[0] = h->d_wl[0]; a.wl[1] = h->d_wl[1];
     a.wl_cnt = h->d_wl_counts;
+    a.wlist[0] = h->d_pk_wl[0]; a.wlist[1] = h->d_pk_wl[1]; a.wl_cap = h->pk_wl_cap; a.evflag = h->d_pk_evflag;
     a.hub_list = h->d_pk_hub; a.scratch = h->d_pk_scratch; a.cnt2 = h->d_pk_cnt2; a.bar = h->d_pk_bar;
     a.out = h->d_pk_out;
     /* host state of a fresh fit (the kernel's prep phase writes the device side) */
@@ -1299,6 +1306,7 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     int done = 0, guard = 0;
+    memset(h->pk_phase_ns, 0, sizeof h->pk_phase_ns);
     nemk_persist_out out;
     memset(&out, 0, sizeof out);
     while (!done) {
@@ -1312,16 +1320,19 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         if ((rc = wait_persist(h, a.seq)) != NEMB_OK) return rc;
         memcpy(&out, (const void *)h->pk_out, sizeof out);
         h->pk_cnt_par = out.cnt_par;
+        for (int q = 0; q < 12; q++) h->pk_phase_ns[q] += out.phase_ns[q];
+        memcpy(h->pk_trace, out.trace, sizeof h->pk_trace);
         h->cur = out.cur; h->stale_par = out.stale_par; h->last_changed = out.last_changed;
         h->stats_valid = out.stats_valid; h->prev_valid = out.sweeps > 0 || a.entry != NEMK_PK_ENTRY_INIT;
         h->ham_valid = 1;
         h->fixup_rounds += out.fixup_rounds;
         res->n_kept += out.kept;
         res->pk_barriers += out.barriers; res->pk_x_passes += out.x_passes; res->pk_recounts += out.recounts;
-        if (out.sweeps > 0) { res->n_allnul = out.n_allnul; res->n_ties = out.n_ties; }
+        res->n_allnul = out.n_allnul; res->n_ties = out.n_ties;
         if (out.exit_code == NEMK_PK_EXIT_DONE) { done = 1; break; }
         a.entry = out.resume_entry; a.iter0 = out.iters; a.cur = out.cur; a.stale_par = out.stale_par;
         a.stats_valid = out.stats_valid; a.last_changed = out.last_changed;
+        a.delta_mode = out.delta_mode; a.n_allnul = out.n_allnul; a.n_ties = out.n_ties;
         a.margins_on = out.sweeps > 0 || a.margins_on;
         if (out.exit_code == NEMK_PK_EXIT_NEED_DENSITY) {
             /* the class masks moved and X does not fit the L2: the TMA-tiled X pass (HBM-bound) */
@@ -1344,6 +1355,9 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
             return fail(h, NEMB_E_BUG, "persistent EM kernel: unknown exit code %d", out.exit_code);
     }
     h->sweep_same_beta = 1;
+    /* the kernel's incremental statistics follow its own convention (they may already include the
+     * last sweep's moves): a launch-per-stage M-step after it must recount */
+    h->stats_valid = 0;
     *iter_out = out.iters; *converged_out = out.converged; *empty_out = out.empty_class;
     *status_out = out.empty_class ? NEMB_W_EMPTYCLASS : NEMB_OK;
     return NEMB_OK;
@@ -1729,6 +1743,23 @@ int nemb_stage_estim_beta(nemb_handle *h, const nemb_options *o, const float *t,
     h->profile = 0;
     if ((rc = upload_state(h, o, t)) != NEMB_OK) return rc;
     return run_estim_beta(h, o, beta_io, sums3);
+}
+
+/* nanoseconds CTA 0 of the persistent EM kernel spent per phase during the last fit (nem_device.h
+ * nemk_persist_out.phase_ns; entry 10 = fix-up rounds executed) */
+int nemb_get_persist_profile(nemb_handle *h, unsigned long long out12[12])
+{
+    if (!h || !out12) return NEMB_E_ARG;
+    memcpy(out12, h->pk_phase_ns, sizeof h->pk_phase_ns);
+    return NEMB_OK;
+}
+
+/* per-iteration trace of the last launch of the persistent kernel (nemk_persist_out.trace) */
+int nemb_get_persist_trace(nemb_handle *h, long long out96[96])
+{
+    if (!h || !out96) return NEMB_E_ARG;
+    memcpy(out96, h->pk_trace, sizeof h->pk_trace);
+    return NEMB_OK;
 }
 
 /* ------------------------------------------------------------------ results */

@@ -99,12 +99,16 @@ struct nemb_handle {
     unsigned long long seq;                   /* last sequence number handed to nemk_iter_end */
     /* persistent EM kernel: scratch (hub list, counters, barrier), mapped status block */
     dbuf b_pk;
-    int32_t *d_pk_hub, *d_pk_scratch;
+    int32_t *d_pk_hub, *d_pk_scratch, *d_pk_wl[2];
+    uint8_t *d_pk_evflag;
+    int pk_wl_cap;
     nemk_counters *d_pk_cnt2;
     unsigned *d_pk_bar;
     nemk_persist_out *pk_out, *d_pk_out;
     unsigned long long pk_seq;
     int pk_cnt_par, pk_ready_n, pk_ready_heavy;
+    long long pk_trace[12][8];            /* per-iteration trace of the LAST launch of the last fit */
+    unsigned long long pk_phase_ns[12];   /* of the last fit (nemk_persist_out.phase_ns, summed over its launches) */
     int pk_grid_limit;     /* > 0: CTAs a fit of this handle may use (concurrent fits share the GPU) */
     /* environment knobs (tests / A-B runs), read ONCE per fit by read_env_knobs() instead of a
      * getenv() per sweep */

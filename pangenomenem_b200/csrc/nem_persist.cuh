@@ -8,9 +8,9 @@
 // device-wide barrier (all CTAs are co-resident: cooperative launch), not by a kernel launch:
 //
 //   init      prep | tables(theta0) | H from row popcounts or X pass | blind sweep | beta sweep
-//   iteration [scan changed rows | delta statistics]  or  [zero | class masks | X^T recount]
+//   iteration [changed rows: scan + statistics update]  or  [zero | class masks | X^T recount]
 //             | closed forms + tables (one CTA per class) | X pass when the class masks moved
-//             | margin test -> active list | evaluate (Jacobi) | fix-up rounds ... | decide
+//             | margin test + evaluation of what is left (Jacobi) | fix-up rounds ... | scan
 //
 // Every CTA takes the same decisions from the same device counters (read after a barrier), so
 // there is no host round trip inside a fit.  Problems whose X does not fit the L2 leave the kernel
@@ -18,44 +18,110 @@
 // NEMK_PK_EXIT_NEED_DENSITY / NEED_RECOUNT.
 //
 // Memory visibility: data another CTA wrote in an earlier phase is read with ordinary loads after
-// the barrier (fence + atomic arrival + fence, the cooperative-groups grid-sync pattern); nothing
-// mutable is read through __ldg / const __restrict__ kernel parameters here (the kernel takes ONE
-// by-value struct, so the compiler cannot infer non-coherent loads), and lab_cur inside a fix-up
-// round is read with __ldcg like in the standalone kernels.
+// the barrier (fence + atomic arrival + fence, the cooperative-groups grid-sync pattern; the
+// gpu-scope fence also drops the SM's L1); nothing mutable is read through __ldg / const
+// __restrict__ kernel parameters here (the kernel takes ONE by-value struct, so the compiler cannot
+// infer non-coherent loads), and labels that move INSIDE a fix-up round are read with __ldcg.
+//
+// Fix-up rounds without flags or fences (measured: a gpu-scope fence per site costs more than the
+// evaluation, profiles/r2_pk_phases_*.txt).  The in-place index-order sweep (UPDATE_SEQ,
+// nem_alg.c:2378-2383) is the unique solution of cur_i = F_i(cur_j, j<i; old_j, j>=i).  Round 0
+// evaluates F with old labels everywhere; every evaluation that CHANGES a label appends all later
+// readers of the site to the next round's list -- no de-duplication, a site may be listed (and
+// evaluated) several times in a round.  Invariant after the barrier that ends round r: a site is
+// either in the next list or none of its lower inputs moved during round r, in which case every
+// evaluation of it in round r saw the same inputs and left the same label, F_i(current inputs).
+// An empty list therefore means the fixed point = the sequential sweep's labels, whatever the
+// interleaving; a racing duplicate can only cause a redundant evaluation, never a lost update,
+// because the site whose store caused the race listed the reader again.  The number of labels that
+// differ from the sweep's input is counted afterwards by the scan that also feeds the M-step.
 
 #define PK_THREADS 512
+#define PK_SPARSE_DELTA 2048   // at most this many rows changed last sweep: their statistics are
+                               // updated by the warps that find them, without a list + barrier
 
+// device-wide barrier: one atomic per CTA on a counter whose top bit flips when all have arrived
+// (the cooperative-groups scheme; 1.2 us for 296 CTAs on B200, profiles/pk_barrier_bench.cu)
 static __device__ __forceinline__ void pk_grid_sync(unsigned *bar, unsigned nblocks) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        volatile unsigned *vgen = bar + 1;
-        const unsigned gen = *vgen;     // cannot advance before this CTA arrives
+        const unsigned add = blockIdx.x == 0 ? 0x80000000u - (nblocks - 1u) : 1u;
         __threadfence();                // release: this CTA's stores of the phase
-        if (atomicAdd(bar, 1u) == nblocks - 1u) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*vgen == gen) { }
-        }
-        __threadfence();                // acquire: the other CTAs' stores
+        const unsigned old = atomicAdd(bar, add);
+        while ((((old ^ *(volatile unsigned *)bar) & 0x80000000u) == 0u)) { }
+        __threadfence();                // acquire: the other CTAs' stores (drops this SM's L1)
     }
     __syncthreads();
 }
 
-struct PkSweepCnt { int changed, allnul, ties; };
+// phase timer of CTA 0 / thread 0 (nemk_persist_out.phase_ns)
+static __device__ __forceinline__ unsigned long long pk_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct PkProf { unsigned long long t_last, ns[12]; long long *trace; };   // trace: row of the current iteration or NULL
+static __device__ __forceinline__ int pk_trace_col(int idx) {   // phase index -> trace column
+    return idx == 1 ? 0 : (idx == 2 || idx == 3) ? 1 : idx == 4 ? 2 : idx == 6 ? 3 : (idx == 7 || idx == 8) ? 4 : idx == 9 ? 5 : -1;
+}
+#define PK_MARK(P, IDX) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_ = pk_now(); \
+    (P).ns[IDX] += t_ - (P).t_last; \
+    if ((P).trace && pk_trace_col(IDX) >= 0) (P).trace[pk_trace_col(IDX)] += (long long)(t_ - (P).t_last); \
+    (P).t_last = t_; } } while (0)
 
-// ---- one site of a Jacobi round taken from a list (margin-cached round): every input is an OLD
-// label, the new one goes to lab_out; a change queues the later readers for the fix-up rounds
+// where the evaluations of a sweep append the sites that must be (re-)evaluated in the next round
+struct PkNext { int32_t *list, *cnt, *ovf; int cap; };
+
+// label of site i moved: every later reader goes to the next round (no de-duplication), earlier-or-
+// equal readers keep this sweep's evaluation, which saw the OLD label: their cached margin is void
+static __device__ __forceinline__ void pk_push_readers(int i, const int32_t *rrow_ptr, const int32_t *rcol,
+                                                       const PkNext &nx, uint8_t *stale_next) {
+    const int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
+    for (int e = lo; e < hi; e += 8) {
+        int j[8], nl = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) j[q] = e + q < hi ? rcol[e + q] : -1;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (j[q] < 0) continue;
+            if (j[q] <= i) { if (stale_next) stale_next[j[q]] = 1; }
+            else nl++;
+        }
+        if (nl) {
+            int base = atomicAdd(nx.cnt, nl);
+            if (base + nl > nx.cap) { *nx.ovf = 1; continue; }   // the next round then takes every site
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (j[q] > i) nx.list[base++] = j[q];
+        }
+    }
+}
+static __device__ __forceinline__ void pk_push_readers_warp(int i, const int32_t *rrow_ptr, const int32_t *rcol,
+                                                            const PkNext &nx, uint8_t *stale_next) {
+    const int lane = threadIdx.x & 31;
+    const int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
+    for (int e0 = lo; e0 < hi; e0 += 32) {
+        const int e = e0 + lane;
+        const int j = e < hi ? rcol[e] : -1;
+        if (j >= 0 && j <= i && stale_next) stale_next[j] = 1;
+        const unsigned later = __ballot_sync(FULL, j > i);
+        if (!later) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(nx.cnt, __popc(later));
+        base = __shfl_sync(FULL, base, 0);
+        if (base + __popc(later) > nx.cap) { if (lane == 0) *nx.ovf = 1; continue; }
+        if (j > i) nx.list[base + __popc(later & ((1u << lane) - 1u))] = j;
+    }
+}
+
+// ---- one site of the Jacobi round (every input is an OLD label), new label to lab_out
 template <int KT>
-static __device__ __forceinline__ void pk_eval_site(int K, int i, const nemk_lpsrc &lps,
-                                                    const int32_t *rp, const int32_t *col,
-                                                    const float *wgt, double beta,
-                                                    const uint8_t *lab_in, uint8_t *lab_out,
-                                                    int32_t *dirty, int32_t *wl, int32_t *wl_count,
-                                                    const int32_t *rrow_ptr, const int32_t *rcol, int n,
-                                                    const nemk_margins &mg, double thr_store,
-                                                    PkSweepCnt &c) {
+static __device__ __forceinline__ void pk_jac_site(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
+                                                   const int32_t *col, const float *wgt, double beta,
+                                                   const uint8_t *lab_in, uint8_t *lab_out, bool seq,
+                                                   const int32_t *rrow_ptr, const int32_t *rcol,
+                                                   const PkNext &nx, const nemk_margins &mg,
+                                                   double thr_store, uint8_t *evflag) {
     double ctx[KT], lpv[KT], margin;
     load_lp<KT>(lps, K, (size_t)i, lpv);
     const int lin = (int)lab_in[i];
@@ -63,82 +129,115 @@ static __device__ __forceinline__ void pk_eval_site(int K, int i, const nemk_lps
     int fl;
     const int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
     lab_out[i] = (uint8_t)km;
+    evflag[i] = (uint8_t)fl;
     store_margin(mg, i, margin, thr_store);
     if (mg.m) mg.stale_cur[i] = 0;
-    if (km != lin) {
-        c.changed++;
-        if (dirty) mark_readers(i, rrow_ptr, rcol, dirty, wl, wl_count, 0, n, mg.stale_next);
-    }
-    c.allnul += fl & 1;
-    c.ties += (fl >> 1) & 1;
+    if (seq && km != lin) pk_push_readers(i, rrow_ptr, rcol, nx, mg.stale_next);
 }
 
-// the same for a hub, by a whole warp (counters on lane 0)
+// a hub of the Jacobi round, by a whole warp (update=para only: the sequential sweep defers its hubs
+// to the first fix-up round, which spreads them one per warp)
 template <int KT>
-static __device__ __forceinline__ void pk_eval_hub(int K, int i, const nemk_lpsrc &lps,
-                                                   const int32_t *rp, const int32_t *col,
-                                                   const float *wgt, double beta,
-                                                   const uint8_t *lab_in, uint8_t *lab_out,
-                                                   int32_t *dirty, int32_t *wl, int32_t *wl_count,
-                                                   const int32_t *rrow_ptr, const int32_t *rcol, int n,
-                                                   const nemk_margins &mg, double thr_store,
-                                                   PkSweepCnt &c) {
-    const int lane = threadIdx.x & 31;
+static __device__ __forceinline__ void pk_jac_hub(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
+                                                  const int32_t *col, const float *wgt, double beta,
+                                                  const uint8_t *lab_in, uint8_t *lab_out, uint8_t *evflag) {
     double ctx[KT], lpv[KT], margin;
     load_lp<KT>(lps, K, (size_t)i, lpv);
     ctx_labels_warp<KT>(K, i, rp, col, wgt, [&](int j) { return (unsigned)lab_in[j]; }, ctx,
                         lps.wsum_any_order != 0);
     int fl;
     const int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
-    const int ch = km != (int)lab_in[i];
+    if ((threadIdx.x & 31) == 0) { lab_out[i] = (uint8_t)km; evflag[i] = (uint8_t)fl; }
+}
+
+// ---- re-evaluation of site i in a fix-up round: lower inputs are CURRENT labels (they move during
+// the round: __ldcg), the others old
+template <int KT>
+static __device__ __forceinline__ void pk_fix_site(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
+                                                   const int32_t *col, const float *wgt, double beta,
+                                                   const uint8_t *lab_old, uint8_t *lab_cur,
+                                                   const int32_t *rrow_ptr, const int32_t *rcol,
+                                                   const PkNext &nx, const nemk_margins &mg,
+                                                   double thr_store, uint8_t *evflag) {
+    double ctx[KT], lpv[KT], margin;
+    const int was = (int)__ldcg(lab_cur + i);
+    load_lp<KT>(lps, K, (size_t)i, lpv);
+    ctx_labels<KT>(K, i, rp, col, wgt,
+                   [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx);
+    int fl;
+    const int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
+    store_margin(mg, i, margin, thr_store);     // the LAST evaluation of a site is its final one
+    evflag[i] = (uint8_t)fl;
+    if (km == was) return;
+    lab_cur[i] = (uint8_t)km;
+    pk_push_readers(i, rrow_ptr, rcol, nx, mg.stale_next);
+}
+template <int KT>
+static __device__ __forceinline__ void pk_fix_hub(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
+                                                  const int32_t *col, const float *wgt, double beta,
+                                                  const uint8_t *lab_old, uint8_t *lab_cur,
+                                                  const int32_t *rrow_ptr, const int32_t *rcol,
+                                                  const PkNext &nx, const nemk_margins &mg,
+                                                  double thr_store, uint8_t *evflag) {
+    const int lane = threadIdx.x & 31;
+    double ctx[KT], lpv[KT], margin;
+    int was = (int)__ldcg(lab_cur + i);
+    load_lp<KT>(lps, K, (size_t)i, lpv);
+    ctx_labels_warp<KT>(K, i, rp, col, wgt,
+                        [&](int j) { return (unsigned)(j < i ? __ldcg(lab_cur + j) : lab_old[j]); }, ctx,
+                        lps.wsum_any_order != 0);
+    int fl;
+    const int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
+    was = __shfl_sync(FULL, was, 0);
     if (lane == 0) {
-        lab_out[i] = (uint8_t)km;
         store_margin(mg, i, margin, thr_store);
-        if (mg.m) mg.stale_cur[i] = 0;
-        c.changed += ch;
-        c.allnul += fl & 1;
-        c.ties += (fl >> 1) & 1;
+        evflag[i] = (uint8_t)fl;
+        if (km != was) lab_cur[i] = (uint8_t)km;
     }
-    if (ch && dirty) mark_readers_warp(i, rrow_ptr, rcol, dirty, wl, wl_count, 0, n, mg.stale_next);
+    if (km != was) pk_push_readers_warp(i, rrow_ptr, rcol, nx, mg.stale_next);
 }
 
 // ---- one E-step sweep (ComputePartitionNEM nem_alg.c:2330-2405 for ncem).  All CTAs call it.
 // use_graph: context term on; seq: in-place index-order semantics through the speculative fixed
-// point; margins (mg.m != NULL) only with seq.  Returns the number of labels that
-// differ from lab_in (every thread gets the same value).
+// point; margins (mg.m != NULL) only with seq.  cnt->kept receives the sites the margin cache
+// saved.  The caller counts the changed labels afterwards (pk_scan).
 template <int KT>
-static __device__ int pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lps, double beta,
+static __device__ void pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lps, double beta,
                                bool use_graph, bool seq, const uint8_t *lab_in, uint8_t *lab_out,
                                nemk_margins mg, nemk_counters *cnt, nemk_counters *cnt_next,
                                float *s_w, uint8_t *s_l, int &barriers, long long &kept_total,
-                               int &nfix_total) {
+                               int &nfix_total, PkProf &prof) {
     const int K = a.K, n = a.n;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nwarps = nthreads >> 5, gwarp = gtid >> 5;
     const int32_t *rp = use_graph ? a.row_ptr : nullptr;
-    int32_t *dirty = seq ? a.dirty : nullptr;
-    int32_t *wl0 = a.wl[0], *wl_cnt = a.wl_cnt;
+    int32_t *wl_cnt = a.wl_cnt, *ovf = a.scratch + 8;
     const SweepThr thr = sweep_thr(K, lps.coef, mg);
     const bool may_skip = mg.m && thr.test < CUDART_INF;
-    PkSweepCnt c = {0, 0, 0};
+    const bool hubs = rp && a.n_heavy > 0;
+    const PkNext nx0 = {a.wlist[0], &wl_cnt[0], &ovf[0], a.wl_cap};   // the list of fix-up round 0
     int kept = 0;
+    // counters of the last scan: every CTA read them right after the scan's barrier and has passed
+    // another barrier since (closed forms); the next scan starts after this sweep's barriers
+    if (gtid == 0) { wl_cnt[4] = 0; a.scratch[3] = 0; a.scratch[4] = 0; }
 
     if (may_skip) {
-        // ---- phase: margin test of every site (streaming: 6 bytes per site, nothing dependent).
-        // A site whose stored margin exceeds what theta can have moved and none of whose
-        // later-or-equal neighbours changed in the previous sweep keeps its label; the others go
-        // to the active lists (light sites: wl[1], hubs: hub_list).
-        int32_t *al = a.wl[1], *al_cnt = a.scratch;
+        // ---- phase: margin test + evaluation, one warp per 128 consecutive sites.  A site whose
+        // stored margin exceeds what theta can have moved and none of whose later-or-equal
+        // neighbours changed in the previous sweep keeps its label (6 streamed bytes per site);
+        // the warp compacts what is left and evaluates it at once (no list, no barrier, and ONE
+        // visitor per site).  Active hubs are deferred to the first fix-up round.
+        int *sm_act = reinterpret_cast<int *>(s_w) + wib * COOP_CHUNK;
         const int ngroups = (n + 3) >> 2;
-        for (int g0 = (gtid & ~31); g0 < ngroups; g0 += nthreads) {
+        int nact = 0;
+        for (int g0 = gwarp * 32; g0 < ngroups; g0 += nwarps * 32) {
             const int g = g0 + lane, i0 = g * 4;
             unsigned actm = 0u, hubm = 0u;
-            int nv = 0;
             if (g < ngroups) {
                 uint8_t st[4], lb[4];
                 float mv[4];
-                nv = min(4, n - i0);
+                const int nv = min(4, n - i0);
                 if (nv == 4) {
                     const uchar4 s4 = *reinterpret_cast<const uchar4 *>(mg.stale_cur + i0);
                     const uchar4 l4 = *reinterpret_cast<const uchar4 *>(lab_in + i0);
@@ -146,14 +245,12 @@ static __device__ int pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lps
                     st[0] = s4.x; st[1] = s4.y; st[2] = s4.z; st[3] = s4.w;
                     lb[0] = l4.x; lb[1] = l4.y; lb[2] = l4.z; lb[3] = l4.w;
                     mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
-                    *reinterpret_cast<uchar4 *>(lab_out + i0) = l4;   // active sites are rewritten below
                 } else {
                     for (int q = 0; q < 4; q++) {
                         const bool v = q < nv;
                         st[q] = v ? mg.stale_cur[i0 + q] : (uint8_t)0;
                         lb[q] = v ? lab_in[i0 + q] : (uint8_t)0;
                         mv[q] = v ? mg.m[i0 + q] : CUDART_INF_F;
-                        if (v) lab_out[i0 + q] = lb[q];
                     }
                 }
 #pragma unroll
@@ -162,54 +259,78 @@ static __device__ int pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lps
                     if (q < nv && !keep) actm |= 1u << q;
                 }
                 kept += nv - __popc(actm);
-                if (actm && rp && a.n_heavy) {
+                if (actm && hubs) {
 #pragma unroll
                     for (int q = 0; q < 4; q++)
                         if (((actm >> q) & 1u) && rp[i0 + q + 1] - rp[i0 + q] > HEAVY_DEG) hubm |= 1u << q;
                 }
+                // labels of the kept sites and of the deferred hubs (old label until their round);
+                // the sites evaluated below are written by their evaluation only
+                const unsigned wr = (~actm | hubm) & ((1u << nv) - 1u);
+                if (wr == 0xfu) *reinterpret_cast<uchar4 *>(lab_out + i0) = make_uchar4(lb[0], lb[1], lb[2], lb[3]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if ((wr >> q) & 1u) lab_out[i0 + q] = lb[q];
+                }
+                if (hubm) {
+                    int base = atomicAdd(nx0.cnt, __popc(hubm));
+                    if (base + __popc(hubm) > nx0.cap) *nx0.ovf = 1;
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if ((hubm >> q) & 1u) { nx0.list[base++] = i0 + q; mg.stale_cur[i0 + q] = 0; }
+                    }
+                }
             }
-            // warp-aggregated append: one atomic per warp and list
-            const int cl = __popc(actm & ~hubm), chb = __popc(hubm);
-            int incl = cl, inch = chb;
+            const unsigned lm = actm & ~hubm;
+            const int c = __popc(lm);
+            int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, o), w = __shfl_up_sync(FULL, inch, o);
-                if (lane >= o) { incl += v; inch += w; }
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
             }
-            const int tl = __shfl_sync(FULL, incl, 31), th = __shfl_sync(FULL, inch, 31);
-            int bl = 0, bh = 0;
-            if (lane == 31) {
-                if (tl) bl = atomicAdd(&al_cnt[0], tl);
-                if (th) bh = atomicAdd(&al_cnt[1], th);
-            }
-            bl = __shfl_sync(FULL, bl, 31) + incl - cl;
-            bh = __shfl_sync(FULL, bh, 31) + inch - chb;
-            unsigned m = actm;
+            const int total = __shfl_sync(FULL, incl, 31);
+            if (!total) continue;
+            int pos = incl - c;
+            unsigned m = lm;
             while (m) {
                 const int q = __ffs(m) - 1;
                 m &= m - 1;
-                if ((hubm >> q) & 1u) a.hub_list[bh++] = i0 + q;
-                else al[bl++] = i0 + q;
+                sm_act[pos++] = i0 + q;
             }
+            __syncwarp();
+            for (int r = lane; r < total; r += 32)
+                pk_jac_site<KT>(K, sm_act[r], lps, rp, a.col, a.wgt, beta, lab_in, lab_out, seq, a.rrow_ptr,
+                                a.rcol, nx0, mg, thr.store, a.evflag);
+            __syncwarp();
+            nact += total;
         }
-        pk_grid_sync(a.bar, gridDim.x); barriers++;
-        // ---- phase: evaluate the active sites, spread evenly over the grid (hubs first)
-        const int nl = *(volatile int32_t *)&al_cnt[0], nh = *(volatile int32_t *)&al_cnt[1];
-        for (int wi = gwarp; wi < nh; wi += nwarps)
-            pk_eval_hub<KT>(K, a.hub_list[wi], lps, rp, a.col, a.wgt, beta, lab_in, lab_out, dirty, wl0,
-                            &wl_cnt[0], a.rrow_ptr, a.rcol, n, mg, thr.store, c);
-        for (int q = gtid; q < nl; q += nthreads)
-            pk_eval_site<KT>(K, al[q], lps, rp, a.col, a.wgt, beta, lab_in, lab_out, dirty, wl0,
-                             &wl_cnt[0], a.rrow_ptr, a.rcol, n, mg, thr.store, c);
+        if (lane == 0 && nact) atomicAdd(&a.scratch[5], nact);   // sites evaluated (trace)
     } else {
-        // ---- phase: dense Jacobi round, every site evaluated.  Hubs by one warp each (longest
-        // work first), then warps over 32 consecutive sites whose contiguous CSR segment is
-        // streamed cooperatively (ctx_labels_coop)
-        const bool hubs = rp && a.n_heavy > 0;
-        if (hubs)
+        // ---- phase: dense Jacobi round, every site evaluated.  Warps over 32 consecutive sites
+        // whose contiguous CSR segment is streamed cooperatively (ctx_labels_coop).  Hubs: the
+        // sequential sweep defers them to the first fix-up round (old label until then, one warp
+        // each there); update=para evaluates them here, one warp each.
+        if (gtid == 0 && prof.trace) prof.trace[6] = -1;
+        if (hubs && seq) {
+            for (int q0 = (gtid & ~31); q0 < a.n_heavy; q0 += nthreads) {
+                const int q = q0 + lane;
+                const bool v = q < a.n_heavy;
+                const int i = v ? a.heavy[q] : 0;
+                if (v) { lab_out[i] = lab_in[i]; if (mg.m) mg.stale_cur[i] = 0; }
+                const unsigned bm = __ballot_sync(FULL, v);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(nx0.cnt, __popc(bm));
+                base = __shfl_sync(FULL, base, 0);
+                if (base + __popc(bm) > nx0.cap) { if (lane == 0) *nx0.ovf = 1; }
+                else if (v) nx0.list[base + lane] = i;
+            }
+        } else if (hubs) {
             for (int wi = gwarp; wi < a.n_heavy; wi += nwarps)
-                pk_eval_hub<KT>(K, a.heavy[wi], lps, rp, a.col, a.wgt, beta, lab_in, lab_out, dirty,
-                                wl0, &wl_cnt[0], a.rrow_ptr, a.rcol, n, mg, thr.store, c);
+                pk_jac_hub<KT>(K, a.heavy[wi], lps, rp, a.col, a.wgt, beta, lab_in, lab_out, a.evflag);
+        }
         for (int base = gwarp * 32; base < n; base += nwarps * 32) {
             const int i = base + lane;
             const bool valid = i < n;
@@ -233,75 +354,205 @@ static __device__ int pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lps
                 int fl;
                 const int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
                 lab_out[i] = (uint8_t)km;
+                a.evflag[i] = (uint8_t)fl;
                 store_margin(mg, i, margin, thr.store);
                 if (mg.m) mg.stale_cur[i] = 0;
-                if (km != (int)lab_in[i]) {
-                    c.changed++;
-                    if (dirty) mark_readers(i, a.rrow_ptr, a.rcol, dirty, wl0, &wl_cnt[0], 0, n, mg.stale_next);
-                }
-                c.allnul += fl & 1;
-                c.ties += (fl >> 1) & 1;
+                if (seq && km != (int)lab_in[i]) pk_push_readers(i, a.rrow_ptr, a.rcol, nx0, mg.stale_next);
             }
         }
     }
     {
-        const int ch = __reduce_add_sync(FULL, c.changed), an = __reduce_add_sync(FULL, c.allnul);
-        const int ti = __reduce_add_sync(FULL, c.ties), kp = __reduce_add_sync(FULL, kept);
-        if (lane == 0) {
-            if (ch) atomicAdd(&cnt->changed, ch);
-            if (an) atomicAdd(&cnt->allnul, an);
-            if (ti) atomicAdd(&cnt->ties, ti);
-            if (kp) atomicAdd(&cnt->kept, kp);
-        }
+        const int kp = __reduce_add_sync(FULL, kept);
+        if (lane == 0 && kp) atomicAdd(&cnt->kept, kp);
     }
     pk_grid_sync(a.bar, gridDim.x); barriers++;
+    PK_MARK(prof, may_skip ? 7 : 8);
     if (gtid == 0) {
-        if (may_skip) { a.scratch[0] = 0; a.scratch[1] = 0; }   // consumed: zero at rest
-        // the counter block of the NEXT sweep: last read right after the previous sweep's final
-        // barrier, and every CTA has passed a barrier of this sweep since
+        // the counter block of the NEXT sweep: every CTA has passed a barrier since it last read it
         cnt_next->changed = 0; cnt_next->nfix = 0; cnt_next->allnul = 0; cnt_next->ties = 0;
         cnt_next->maxdiff = 0.f; cnt_next->pending = 0; cnt_next->changed_glob = 0; cnt_next->kept = 0;
+        if (may_skip) { if (prof.trace) prof.trace[6] = a.scratch[5]; a.scratch[5] = 0; }
     }
 
-    // ---- fix-up rounds (speculative sequential sweep): re-evaluate the sites one of whose
-    // lower-index inputs moved until the work list is empty; one barrier per round
+    // ---- fix-up rounds: the listed sites are re-evaluated (duplicates allowed) until no label
+    // moves; one barrier per round.  Round r reads list r&1 / counter r&3, appends to list (r+1)&1 /
+    // counter (r+1)&3 and clears counter (r+2)&3 (idle during the round).  Items are dealt
+    // round-robin over the warps so that a run of hubs lands on different warps.
     int rounds = 0;
     if (seq) {
-        int dchanged = 0;
         for (int round = 0;; round++) {
-            int32_t *cur_list = (round & 1) ? a.wl[1] : a.wl[0], *next_list = (round & 1) ? a.wl[0] : a.wl[1];
-            int32_t *next_cnt = &wl_cnt[(round + 1) & 3];
+            const int32_t *cur_list = a.wlist[round & 1];
+            const PkNext nx = {a.wlist[(round + 1) & 1], &wl_cnt[(round + 1) & 3], &ovf[(round + 1) & 3], a.wl_cap};
             const int count = *(volatile int32_t *)&wl_cnt[round & 3];
-            if (gtid == 0) wl_cnt[(round + 2) & 3] = 0;   // idle during this round
-            if (count == 0) break;
+            const bool all = *(volatile int32_t *)&ovf[round & 3] != 0;   // a list overflowed: every site
+            if (gtid == 0) { wl_cnt[(round + 2) & 3] = 0; ovf[(round + 2) & 3] = 0; }
+            const int items = all ? n : count;
+            if (items == 0) break;
             rounds++;
-            for (int base = (gtid & ~31); base < count; base += nthreads)
-                dchanged += fixup_items<KT>(K, base + lane, count, cur_list, 0, n, lps, rp, a.col, a.wgt,
-                                            beta, lab_in, lab_out, dirty, next_list, next_cnt,
-                                            a.rrow_ptr, a.rcol, mg, thr.store);
-            if (dchanged) { atomicAdd(&cnt->changed, dchanged); dchanged = 0; }
+            for (int base = gwarp; base < items; base += 32 * nwarps) {
+                const int idx = base + lane * nwarps;
+                const int i = idx < items ? (all ? idx : cur_list[idx]) : -1;
+                const bool hub = i >= 0 && (rp[i + 1] - rp[i] > HEAVY_DEG);
+                if (i >= 0 && !hub)
+                    pk_fix_site<KT>(K, i, lps, rp, a.col, a.wgt, beta, lab_in, lab_out, a.rrow_ptr, a.rcol, nx,
+                                    mg, thr.store, a.evflag);
+                unsigned hm = __ballot_sync(FULL, hub);
+                while (hm) {
+                    const int src = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    pk_fix_hub<KT>(K, __shfl_sync(FULL, i, src), lps, rp, a.col, a.wgt, beta, lab_in, lab_out,
+                                   a.rrow_ptr, a.rcol, nx, mg, thr.store, a.evflag);
+                }
+            }
             pk_grid_sync(a.bar, gridDim.x); barriers++;
         }
-        // every CTA has read the last (zero) count before anybody can append again: the next
-        // appends happen at least one barrier later (the next sweep's evaluation phase)
+        PK_MARK(prof, 9);
         if (gtid == 0) {
-            wl_cnt[0] = 0; wl_cnt[1] = 0; wl_cnt[2] = 0; wl_cnt[3] = 0;
+            prof.ns[10] += rounds;
+            if (prof.trace) prof.trace[7] = rounds;
+            // every CTA has read the last (zero) count before anybody can append again: the next
+            // appends happen at least one barrier later (the next sweep's evaluation phase)
+            for (int q = 0; q < 4; q++) { wl_cnt[q] = 0; ovf[q] = 0; }
             if (mg.m) const_cast<nemk_coef *>(lps.coef)->drift = thr.store;
         }
     }
     nfix_total += rounds;
-    const volatile nemk_counters *vc = cnt;
-    kept_total += vc->kept;
-    return vc->changed;
+    kept_total += ((const volatile nemk_counters *)cnt)->kept;
 }
 
-// ---- closed forms + tables of class k by ONE CTA (k_mstep_finalize_tables with block sums instead
-// of cluster sums; same float expressions: nem_mod.c:455-465, 965-1174, 1422-1479, 1646-1704)
+// ---- after a sweep: the rows whose label differs from the sweep's input.  Counts them (the
+// `clas` convergence test, nem_alg.c:2075-2089, and the size of the M-step's update), sums the
+// all-null / tie flags of every site's last evaluation, and feeds the incremental statistics:
+// mode 0 count only, 1 append the rows to `list` (the M-step updates S and n from the list after
+// the barrier, 32 rows per ballot transpose), 2 the warp that finds a row moves its bits from
+// S[old] to S[new] itself (few rows: no list, no barrier).  16 labels per lane.
+template <int KT>
+static __device__ void pk_scan(const nemk_persist_args &a, const uint8_t *lab, const uint8_t *lab_m,
+                               int mode, int32_t *list, int32_t *count) {
+    const int n = a.n, K = a.K, D = a.D, wreal = (D + 31) >> 5;
+    const int nthreads = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    const int ngroups = (n + 15) >> 4;
+    int32_t *S = a.stat, *nk = a.stat + (size_t)K * D;
+    int nul = 0, ties = 0;
+    for (int t0 = ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); t0 < ngroups; t0 += nthreads) {
+        const int t = t0 + lane, i0 = t * 16;
+        uint32_t dm = 0u;
+        if (t < ngroups) {
+            if (i0 + 16 <= n) {
+                const uint4 p = *(reinterpret_cast<const uint4 *>(lab) + t);
+                const uint4 q = *(reinterpret_cast<const uint4 *>(lab_m) + t);
+                const uint4 f = *(reinterpret_cast<const uint4 *>(a.evflag) + t);
+                dm = nonzero_bytes(p.x ^ q.x) | (nonzero_bytes(p.y ^ q.y) << 4) |
+                     (nonzero_bytes(p.z ^ q.z) << 8) | (nonzero_bytes(p.w ^ q.w) << 12);
+                nul += __popc(f.x & 0x01010101u) + __popc(f.y & 0x01010101u) + __popc(f.z & 0x01010101u) +
+                       __popc(f.w & 0x01010101u);
+                ties += __popc(f.x & 0x02020202u) + __popc(f.y & 0x02020202u) + __popc(f.z & 0x02020202u) +
+                        __popc(f.w & 0x02020202u);
+            } else {
+                for (int j = 0; i0 + j < n; j++) {
+                    dm |= (uint32_t)(lab[i0 + j] != lab_m[i0 + j]) << j;
+                    nul += a.evflag[i0 + j] & 1;
+                    ties += (a.evflag[i0 + j] >> 1) & 1;
+                }
+            }
+        }
+        const int c = __popc(dm);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (!total) continue;
+        int base = 0;
+        if (lane == 31) base = atomicAdd(count, total);
+        if (mode == 1) {
+            base = __shfl_sync(FULL, base, 31);
+            int pos = base + incl - c;
+            uint32_t m = dm;
+            while (m) {
+                list[pos++] = i0 + __ffs(m) - 1;
+                m &= m - 1;
+            }
+        } else if (mode == 2) {
+            // the warp moves every changed row of its 512 families itself (exact integer updates)
+            unsigned lanes = __ballot_sync(FULL, dm != 0u);
+            while (lanes) {
+                const int src = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
+                uint32_t m = __shfl_sync(FULL, dm, src);
+                const int r0 = __shfl_sync(FULL, i0, src);
+                while (m) {
+                    const int row = r0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const int lo = lab_m[row], ln = lab[row];
+                    if (lane == 0) { atomicAdd(&nk[lo], -1); atomicAdd(&nk[ln], 1); }
+                    const uint32_t *xr = a.x + (size_t)row * a.wpr;
+                    for (int w = lane; w < wreal; w += 32) {
+                        uint32_t bits = __ldg(xr + w);
+                        while (bits) {
+                            const int d = w * 32 + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            atomicAdd(&S[(size_t)lo * D + d], -1);
+                            atomicAdd(&S[(size_t)ln * D + d], 1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    nul = __reduce_add_sync(FULL, nul);
+    ties = __reduce_add_sync(FULL, ties);
+    if (lane == 0) {
+        if (nul) atomicAdd(&a.scratch[3], nul);
+        if (ties) atomicAdd(&a.scratch[4], ties);
+    }
+}
+
+// four block-wide double sums through ONE pair of block barriers (fixed shuffle tree + fixed
+// shared-memory order: deterministic)
+template <int TH>
+static __device__ __forceinline__ void pk_block_sum4(double (&v)[4], double *sh /*[4 * 32]*/) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(FULL, v[q], o);
+    __syncthreads();
+    if (l == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) sh[q * 32 + w] = v[q];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double r = (l < TH / 32) ? sh[q * 32 + l] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+            if (l == 0) sh[q * 32] = r;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = sh[q * 32];
+}
+
+// ---- closed forms + tables of class k by ONE CTA (same float expressions as
+// k_mstep_finalize_tables: nem_mod.c:455-465, 965-1174, 1422-1479, 1646-1704; DensBernoulli's terms
+// nem_mod.c:656-670).  This runs every EM iteration while the rest of the grid waits at the
+// barrier, so it is written for latency: the statistics of a thread's genomes are loaded together,
+// the centres stay in registers as 2-bit codes between the two passes (nothing written is read
+// back), the previous mask words are fetched up front (one pair per lane, handed to lane 0 by a
+// shuffle) and the four table sums share one pair of block barriers.  A class without families, or
+// more than 32 * TH genomes, takes the general code path.
 template <int TH>
 static __device__ void pk_finalize_class(int k, const nemk_persist_args &a, double *sh,
                                          float *nkf, double *nkd) {
-    const int K = a.K, D = a.D, N = a.n, tid = threadIdx.x;
-    const int32_t *s_int = a.stat, *nk_int = a.stat + (size_t)K * D;
+    const int K = a.K, D = a.D, N = a.n, tid = threadIdx.x, lane = tid & 31, wpr = a.wpr;
+    const int32_t *__restrict__ s_int = a.stat;
+    const int32_t *__restrict__ nk_int = a.stat + (size_t)K * D;
     float *center = a.center, *disp = a.disp;
     const int wreal = (D + 31) >> 5;
     __syncthreads();
@@ -319,6 +570,94 @@ static __device__ void pk_finalize_class(int k, const nemk_persist_args &a, doub
     }
     auto S_of = [&](int c, int j) -> double { return (double)s_int[(size_t)c * D + j]; };
     const bool nonempty = (double)nkf[k] > NEM_EPSILON;
+    const int niter = (D + TH - 1) / TH;           // genomes per thread
+    const bool fast = nonempty && niter <= 32 && (a.disp_model == 0 || a.disp_model == 1);
+    if (fast) {
+        // previous mask words of this warp's iterations: lane q fetches the pair of iteration q
+        uint32_t oldx = 0u, oldv = 0u;
+        {
+            const int j = lane * TH + (tid & ~31);
+            if (lane < niter && j < D) {
+                const size_t o = (size_t)k * wpr + (j >> 5);
+                oldx = a.mxor[o]; oldv = a.mval[o];
+            }
+        }
+        // pass A: centres (2-bit codes) and inertia, four genomes per thread in flight
+        unsigned long long codes = 0ull;
+        double v = 0.0, sn = 0.0;
+        const double half = 0.5 * nkd[k];
+        for (int q0 = 0; q0 < niter; q0 += 4) {
+            double s[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = (q0 + q) * TH + tid;
+                s[q] = (q0 + q < niter && j < D) ? (double)s_int[(size_t)k * D + j] : -1.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = (q0 + q) * TH + tid;
+                if (s[q] < 0.0) continue;
+                const unsigned code = s[q] > half ? 1u : (s[q] < half ? 0u : 2u);
+                codes |= (unsigned long long)code << (2 * (q0 + q));
+                center[(size_t)k * D + j] = code == 1u ? 1.0f : (code == 0u ? 0.0f : 0.5f);
+                if (a.disp_model == 1) v += (double)iner_of(s[q], nkd[k], true, 0.f);
+            }
+        }
+        if (a.disp_model == 1) sn = (double)nkf[k] * (double)D;
+        else {
+            // s__ pools the classes: every class's inertia (nem_mod.c:988-1015)
+            for (int c = 0; c < K; c++) {
+                if (nkf[c] > 0.f) {
+                    const bool ne = (double)nkf[c] > NEM_EPSILON;
+                    for (int j = tid; j < D; j += TH)
+                        v += (double)iner_of(S_of(c, j), nkd[c], ne, ne ? 0.f : center[(size_t)c * D + j]);
+                    sn += (double)nkf[c] * (double)D;
+                }
+            }
+        }
+        v = block_sum<TH>(v, sh);
+        const float dk = __fdiv_rn((float)v, (float)sn);
+        if (tid == 0)
+            a.prop[k] = a.prop_model == 1 ? __fdiv_rn(nkf[k], (float)N) : (float)(1.0 / (double)K);
+        const ClassCoef cc = class_coef(dk);
+        // pass B: dispersions, the per-genome table terms and the bit masks, from the codes
+        double sums[4] = {0.0, 0.0, 0.0, 0.0};   // base_u, base_g, n_valid, n_x1
+        int mu_moved = 0;
+        for (int q = 0; q < niter; q++) {
+            const int j = q * TH + tid;
+            const bool in = j < D;
+            const unsigned code = (unsigned)(codes >> (2 * q)) & 3u;
+            const int m0 = code == 1u, m1 = code == 0u;       // abs((int)(0 - mu)), abs((int)(1 - mu))
+            if (in) {
+                disp[(size_t)k * D + j] = dk;
+                const double cost0 = m0 * cc.a0 + cc.c0, cost1 = m1 * cc.a0 + cc.c0;
+                a.delta[(size_t)k * D + j] = cost1 - cost0;
+                sums[1] += cost0;
+                sums[0] += cc.c0;
+            }
+            const unsigned bx = __ballot_sync(FULL, in && code == 1u);
+            const unsigned bv = __ballot_sync(FULL, in && code != 2u);
+            const unsigned b0 = __ballot_sync(FULL, in && !cc.live0 && m0 != 0);
+            const unsigned b1 = __ballot_sync(FULL, in && !cc.live0 && m1 != 0);
+            const uint32_t ox = __shfl_sync(FULL, oldx, q), ov = __shfl_sync(FULL, oldv, q);
+            if (lane == 0 && (j >> 5) < wreal) {
+                const size_t o = (size_t)k * wpr + (j >> 5);
+                sums[2] += __popc(bv); sums[3] += __popc(bx);
+                if (ox != bx || ov != bv) mu_moved = 1;
+                a.mxor[o] = bx; a.mval[o] = bv; a.f0[o] = b0; a.f1[o] = b1;
+            }
+        }
+        for (int w = wreal + tid; w < wpr; w += TH) {
+            const size_t o = (size_t)k * wpr + w;
+            a.mxor[o] = 0u; a.mval[o] = 0u; a.f0[o] = 0u; a.f1[o] = 0u;
+        }
+        if (mu_moved) atomicOr(&a.coef->mu_changed, 1);
+        pk_block_sum4<TH>(sums, sh);
+        if (tid == 0)
+            tables_commit(k, K, D, a.prop, a.coef, a.delta, cc, sums[0], sums[1], true, (int)sums[2], (int)sums[3], true);
+        return;
+    }
+    // ---- general path
     if (nonempty)
         for (int j = tid; j < D; j += TH) {
             const double s = S_of(k, j), half = 0.5 * nkd[k];
@@ -365,17 +704,17 @@ static __device__ void pk_finalize_class(int k, const nemk_persist_args &a, doub
     __threadfence_block();
     __syncthreads();
     const ClassCoef cc = class_coef(__ldcg(&disp[(size_t)k * D]));
-    TablesPartial p = tables_words(k, D, a.wpr, 0, wreal, cc, center, disp, a.mxor, a.mval, a.f0, a.f1, a.delta);
-    for (int w = wreal + tid; w < a.wpr; w += TH) {
-        const size_t o = (size_t)k * a.wpr + w;
+    TablesPartial p = tables_words(k, D, wpr, 0, wreal, cc, center, disp, a.mxor, a.mval, a.f0, a.f1, a.delta);
+    for (int w = wreal + tid; w < wpr; w += TH) {
+        const size_t o = (size_t)k * wpr + w;
         a.mxor[o] = 0u; a.mval[o] = 0u; a.f0[o] = 0u; a.f1[o] = 0u;
     }
     if (p.mu_moved) atomicOr(&a.coef->mu_changed, 1);
-    const double base_u = block_sum<TH>(p.base_u, sh), base_g = block_sum<TH>(p.base_g, sh);
+    double sums[4] = {p.base_u, p.base_g, (double)p.n_valid, (double)p.n_x1};
     const double notok = block_sum<TH>((double)p.notok, sh);
-    const double nv = block_sum<TH>((double)p.n_valid, sh), nx = block_sum<TH>((double)p.n_x1, sh);
+    pk_block_sum4<TH>(sums, sh);
     if (tid == 0)
-        tables_commit(k, K, D, a.prop, a.coef, a.delta, cc, base_u, base_g, notok == 0.0, (int)nv, (int)nx, true);
+        tables_commit(k, K, D, a.prop, a.coef, a.delta, cc, sums[0], sums[1], notok == 0.0, (int)sums[2], (int)sums[3], true);
 }
 
 // tables of the theta the caller supplied (k_theta_tables), class k by one CTA
@@ -501,49 +840,11 @@ static __device__ void pk_recount(const nemk_persist_args &a) {
     }
 }
 
-// ---- scan of the rows whose label differs from the one the statistics describe (16 per thread)
-static __device__ void pk_scan_changed(int n, const uint8_t *lab, const uint8_t *lab_m, int32_t *list,
-                                       int32_t *count) {
-    const int nthreads = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
-    const int ngroups = (n + 15) >> 4;
-    for (int t0 = ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); t0 < ngroups; t0 += nthreads) {
-        const int t = t0 + lane, i0 = t * 16;
-        uint32_t dm = 0u;
-        if (t < ngroups) {
-            if (i0 + 16 <= n) {
-                const uint4 p = *(reinterpret_cast<const uint4 *>(lab) + t);
-                const uint4 q = *(reinterpret_cast<const uint4 *>(lab_m) + t);
-                dm = nonzero_bytes(p.x ^ q.x) | (nonzero_bytes(p.y ^ q.y) << 4) |
-                     (nonzero_bytes(p.z ^ q.z) << 8) | (nonzero_bytes(p.w ^ q.w) << 12);
-            } else {
-                for (int j = 0; i0 + j < n; j++) dm |= (uint32_t)(lab[i0 + j] != lab_m[i0 + j]) << j;
-            }
-        }
-        const int c = __popc(dm);
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(FULL, incl, 31);
-        if (!total) continue;
-        int base = 0;
-        if (lane == 31) base = atomicAdd(count, total);
-        base = __shfl_sync(FULL, base, 31);
-        int pos = base + incl - c;
-        while (dm) {
-            list[pos++] = i0 + __ffs(dm) - 1;
-            dm &= dm - 1;
-        }
-    }
-}
-
 // =============================================================================================
 template <int KT>
 __global__ void __launch_bounds__(PK_THREADS, 2)
 k_em_persist(const nemk_persist_args a) {
-    __shared__ double sh[32];
+    __shared__ double sh[5 * 32];
     __shared__ float nkf[NEMB_MAX_K];
     __shared__ double nkd[NEMB_MAX_K];
     __shared__ float s_w[(PK_THREADS / 32) * COOP_CHUNK];
@@ -558,9 +859,16 @@ k_em_persist(const nemk_persist_args a) {
     int state = a.entry, it = a.iter0, cur = a.cur, stale_par = a.stale_par;
     int stats_valid = a.stats_valid, last_changed = a.last_changed, margins_on = a.margins_on;
     int barriers = 0, sweeps = 0, x_passes = 0, recounts = 0, nfix = 0, cnt_par = a.cnt_par;
+    int delta_mode = a.delta_mode;      // what the last scan did with the changed rows (0 / 1 / 2)
     long long kept = 0;
     int exit_code = NEMK_PK_EXIT_DONE, resume = NEMK_PK_ENTRY_MSTEP, converged = 0, empty = 0;
-    int n_allnul = 0, n_ties = 0;
+    int n_allnul = a.n_allnul, n_ties = a.n_ties;
+    PkProf prof;
+    for (int q = 0; q < 12; q++) prof.ns[q] = 0;
+    prof.t_last = pk_now();
+    prof.trace = nullptr;
+    if (gtid == 0)
+        for (int q = 0; q < 12 * 8; q++) (&a.out->trace[0][0])[q] = 0;
 #define PK_SYNC() do { pk_grid_sync(a.bar, nb); barriers++; } while (0)
 
     // the entry codes plus the two initial sweeps as states of their own, so that the sweep has
@@ -574,13 +882,14 @@ k_em_persist(const nemk_persist_args a) {
                 reinterpret_cast<uint32_t *>(a.lab[0])[i] = 0xffffffffu;
                 reinterpret_cast<uint32_t *>(a.stale[0])[i] = 0u;
                 reinterpret_cast<uint32_t *>(a.stale[1])[i] = 0u;
+                reinterpret_cast<uint32_t *>(a.evflag)[i] = 0u;
             }
             if (gtid == 0) {
                 a.coef->uniform_ok = 1; a.coef->mu_changed = 1; a.coef->empty_class = 0; a.coef->halt = 0;
                 // zero at rest from here on (a launch-per-stage fit on the same handle does not keep
-                // the delta-list counter clean)
+                // the shared counters clean)
                 for (int q = 0; q < 8; q++) a.wl_cnt[q] = 0;
-                a.scratch[0] = 0; a.scratch[1] = 0;
+                for (int q = 0; q < 16; q++) a.scratch[q] = 0;
             }
             PK_SYNC();
             for (int k = blockIdx.x; k < K; k += gridDim.x) pk_tables_class<PK_THREADS>(k, a, sh);
@@ -606,29 +915,30 @@ k_em_persist(const nemk_persist_args a) {
                 exit_code = NEMK_PK_EXIT_NEED_DENSITY; resume = NEMK_PK_ENTRY_INIT_SWEEPS;
                 break;
             }
+            PK_MARK(prof, 0);
             state = S_BLIND;
         } else if (state == S_MSTEP) {
             if (it >= a.it_max) break;
+            prof.trace = (gtid == 0 && it - a.iter0 < 12) ? a.out->trace[it - a.iter0] : nullptr;
+            // statistics of the labels lab[cur]: already updated by the scan (delta_mode 2), updated
+            // from the scan's list (1), or recounted
             const bool incremental = stats_valid && last_changed >= 0 && last_changed <= n / 8;
-            if (incremental) {
-                // statistics describe lab[cur ^ 1] (the input of the last sweep)
-                if (gtid == 0) { a.coef->uniform_ok = 1; a.coef->mu_changed = 0; }
-                pk_scan_changed(n, a.lab[cur], a.lab[cur ^ 1], a.wl[1], &a.wl_cnt[4]);
-                PK_SYNC();
-                const int total = *(volatile int32_t *)&a.wl_cnt[4];
-                mstep_delta_items<KT>(K, D, a.wpr, a.x, a.lab[cur], a.lab[cur ^ 1], a.wl[1], total,
+            if (stats_valid && delta_mode == 2) {
+                // nothing left to do
+            } else if (incremental && delta_mode == 1) {
+                mstep_delta_items<KT>(K, D, a.wpr, a.x, a.lab[cur], a.lab[cur ^ 1], a.wlist[1], last_changed,
                                       a.stat, a.stat + (size_t)K * D);
                 PK_SYNC();
-                if (gtid == 0) a.wl_cnt[4] = 0;   // consumed
+                PK_MARK(prof, 2);
             } else if (a.x_in_kernel) {
                 for (int q = gtid; q < K * D + K; q += nthreads) a.stat[q] = 0;
-                if (gtid == 0) { a.coef->uniform_ok = 1; a.coef->mu_changed = 0; }
                 PK_SYNC();
                 pk_label_masks<KT>(a, a.lab[cur]);
                 PK_SYNC();
                 pk_recount<KT>(a);
                 recounts++;
                 PK_SYNC();
+                PK_MARK(prof, 3);
             } else {
                 exit_code = NEMK_PK_EXIT_NEED_RECOUNT; resume = NEMK_PK_ENTRY_FINALIZE;
                 break;
@@ -638,6 +948,7 @@ k_em_persist(const nemk_persist_args a) {
             stats_valid = 1;
             for (int k = blockIdx.x; k < K; k += gridDim.x) pk_finalize_class<PK_THREADS>(k, a, sh, nkf, nkd);
             PK_SYNC();
+            PK_MARK(prof, 4);
             const volatile nemk_coef *vc = a.coef;
             empty = vc->empty_class;
             if (empty) {   // nem_alg.c:1831-1838: the E-step is not run, the loop ends
@@ -650,6 +961,7 @@ k_em_persist(const nemk_persist_args a) {
                     pk_density_pass<KT>(a);
                     x_passes++;
                     PK_SYNC();
+                    PK_MARK(prof, 5);
                 } else {
                     exit_code = NEMK_PK_EXIT_NEED_DENSITY; resume = NEMK_PK_ENTRY_SWEEP;
                     break;
@@ -670,35 +982,48 @@ k_em_persist(const nemk_persist_args a) {
                 mg.on = state == S_BETA0 ? 0 : margins_on;
                 stale_par ^= 1;
             }
-            const int ch = pk_sweep<KT>(a, lps, blind ? 0.0 : a.beta, use_graph && !blind, seq && !blind,
-                                        a.lab[cur], a.lab[cur ^ 1], mg, cnt, cnt_next, s_w, s_l, barriers,
-                                        kept, nfix);
-            const volatile nemk_counters *vcn = cnt;
-            n_allnul = vcn->allnul; n_ties = vcn->ties;
+            pk_sweep<KT>(a, lps, blind ? 0.0 : a.beta, use_graph && !blind, seq && !blind, a.lab[cur],
+                         a.lab[cur ^ 1], mg, cnt, cnt_next, s_w, s_l, barriers, kept, nfix, prof);
             cur ^= 1;
             sweeps++;
             if (blind) { state = S_BETA0; continue; }
-            last_changed = ch;
             margins_on = 1;   // the next sweep uses the same beta
-            if (state == S_SWEEP) {
-                it++;
-                if (a.conv == 1) {   // HasConverged `clas` under ncem: no label changed
-                    const float md = ch ? 1.0f : 0.0f;
-                    if (md < a.conv_thr) { converged = 1; break; }
-                }
+            if (state == S_BETA0) {   // NemAlgo starts with a full recount: nothing to scan
+                if (gtid == 0) { a.coef->uniform_ok = 1; a.coef->mu_changed = 0; }   // presets of the next tables
+                last_changed = -1; delta_mode = 0;
+                state = S_MSTEP;
+                continue;
             }
+            // ---- the rows this sweep moved: count (convergence test), flags of the last evaluations,
+            // and the incremental statistics of the next M-step
+            const int want = (it + 1 >= a.it_max || !stats_valid) ? 0 : 1;
+            if (gtid == 0) { a.coef->uniform_ok = 1; a.coef->mu_changed = 0; }   // presets of the next tables
+            pk_scan<KT>(a, a.lab[cur], a.lab[cur ^ 1], want, a.wlist[1], &a.wl_cnt[4]);
+            PK_SYNC();
+            PK_MARK(prof, 1);
+            last_changed = *(volatile int32_t *)&a.wl_cnt[4];
+            n_allnul = *(volatile int32_t *)&a.scratch[3];
+            n_ties = *(volatile int32_t *)&a.scratch[4];
+            delta_mode = want;
+            if (want == 0) stats_valid = 0;     // the statistics no longer describe lab[cur ^ 1] + a list
+            it++;
             state = S_MSTEP;
+            if (a.conv == 1) {   // HasConverged `clas` under ncem: no label changed
+                const float md = last_changed ? 1.0f : 0.0f;
+                if (md < a.conv_thr) { converged = 1; break; }
+            }
         }
     }
     if (gtid == 0) {
         nemk_persist_out *o = a.out;
         o->exit_code = exit_code; o->resume_entry = resume;
         o->iters = it; o->converged = converged; o->empty_class = empty;
-        o->cnt_par = cnt_par;
+        o->cnt_par = cnt_par; o->delta_mode = delta_mode;
         o->cur = cur; o->stale_par = stale_par; o->last_changed = last_changed; o->stats_valid = stats_valid;
         o->n_allnul = n_allnul; o->n_ties = n_ties;
         o->sweeps = sweeps; o->x_passes = x_passes; o->recounts = recounts; o->barriers = barriers;
         o->kept = kept; o->fixup_rounds = nfix;
+        for (int q = 0; q < 12; q++) o->phase_ns[q] = prof.ns[q];
         __threadfence_system();
         *(volatile unsigned long long *)&o->seq = a.seq;
     }
