@@ -37,6 +37,9 @@ typedef struct {
      * were stored */
     double  dstep[NEMB_MAX_K];
     double  drift;
+    /* persistent EM kernel: class k's bit masks differ from the previous tables (written, not
+     * OR-ed, by the CTA that builds class k's tables: needs no reset between iterations) */
+    int32_t mu_moved_k[NEMB_MAX_K];
 } nemk_coef;
 
 /* Margin cache of the ncem speculative sweep (exact shortcut).  m[i] = (best - second best score
@@ -310,7 +313,7 @@ enum { NEMK_PK_EXIT_DONE = 0, NEMK_PK_EXIT_NEED_DENSITY = 1, NEMK_PK_EXIT_NEED_R
 typedef struct {
     int32_t exit_code, resume_entry;    /* NEED_*: run the pass, re-enter at resume_entry */
     int32_t iters, converged, empty_class;
-    int32_t cur, stale_par, last_changed, stats_valid, cnt_par, delta_mode;
+    int32_t cur, stale_par, last_changed, stats_valid, cnt_par, delta_mode, flags_stale, mu_changed;
     int32_t n_allnul, n_ties;           /* of the last sweep */
     int32_t sweeps, x_passes, recounts, barriers;
     long long kept, fixup_rounds;       /* summed over the sweeps of this launch */
@@ -338,7 +341,7 @@ typedef struct {
     int32_t x_in_kernel;      /* X and X^T passes may run inside the kernel (L2-sized problem) */
     int32_t init_from_pop;    /* ENTRY_INIT: every class of theta0 has a constant centre */
     /* entry state */
-    int32_t entry, iter0, cur, stale_par, stats_valid, last_changed, margins_on, cnt_par, delta_mode;
+    int32_t entry, iter0, cur, stale_par, stats_valid, last_changed, margins_on, cnt_par, delta_mode, flags_stale, mu_changed;
     int32_t n_allnul, n_ties;   /* of the last sweep so far (carried over a re-entry) */
     unsigned long long seq;
     /* buffers (device) */

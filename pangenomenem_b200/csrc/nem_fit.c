@@ -1320,8 +1320,13 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         if ((rc = wait_persist(h, a.seq)) != NEMB_OK) return rc;
         memcpy(&out, (const void *)h->pk_out, sizeof out);
         h->pk_cnt_par = out.cnt_par;
-        for (int q = 0; q < 12; q++) h->pk_phase_ns[q] += out.phase_ns[q];
+        /* the kernel counts SM cycles: convert with the SM clock (kHz) */
+        if (!h->sm_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device); h->sm_khz = khz > 0 ? khz : 1965000; }
+        for (int q = 0; q < 10; q++) h->pk_phase_ns[q] += out.phase_ns[q] * 1000000ull / (unsigned long long)h->sm_khz;
+        h->pk_phase_ns[10] += out.phase_ns[10];
         memcpy(h->pk_trace, out.trace, sizeof h->pk_trace);
+        for (int r = 0; r < 12; r++)
+            for (int q = 0; q < 6; q++) h->pk_trace[r][q] = h->pk_trace[r][q] * 1000000ll / (long long)h->sm_khz;
         h->cur = out.cur; h->stale_par = out.stale_par; h->last_changed = out.last_changed;
         h->stats_valid = out.stats_valid; h->prev_valid = out.sweeps > 0 || a.entry != NEMK_PK_ENTRY_INIT;
         h->ham_valid = 1;
@@ -1333,6 +1338,7 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         a.entry = out.resume_entry; a.iter0 = out.iters; a.cur = out.cur; a.stale_par = out.stale_par;
         a.stats_valid = out.stats_valid; a.last_changed = out.last_changed;
         a.delta_mode = out.delta_mode; a.n_allnul = out.n_allnul; a.n_ties = out.n_ties;
+        a.flags_stale = out.flags_stale; a.mu_changed = out.mu_changed;
         a.margins_on = out.sweeps > 0 || a.margins_on;
         if (out.exit_code == NEMK_PK_EXIT_NEED_DENSITY) {
             /* the class masks moved and X does not fit the L2: the TMA-tiled X pass (HBM-bound) */

@@ -101,7 +101,7 @@ struct nemb_handle {
     dbuf b_pk;
     int32_t *d_pk_hub, *d_pk_scratch, *d_pk_wl[2];
     uint8_t *d_pk_evflag;
-    int pk_wl_cap;
+    int pk_wl_cap, sm_khz;
     nemk_counters *d_pk_cnt2;
     unsigned *d_pk_bar;
     nemk_persist_out *pk_out, *d_pk_out;

@@ -37,8 +37,18 @@
 // differ from the sweep's input is counted afterwards by the scan that also feeds the M-step.
 
 #define PK_THREADS 512
-#define PK_SPARSE_DELTA 2048   // at most this many rows changed last sweep: their statistics are
-                               // updated by the warps that find them, without a list + barrier
+#ifndef PK_TRACK
+#define PK_TRACK 0
+#endif
+#define PK_TRACK_MAX 4096      // at most this many labels moved last sweep: the statistics follow the
+                               // label moves of this sweep at once (no scan / update phases)
+// PK_CHASE > 1 would let a fix-up evaluation that moved a label go straight on with the first later
+// reader instead of queueing it.  NOT exact (GPU test, round 2): another evaluation of that reader
+// that started before the move can store its stale label last, and nobody re-queues the reader.
+// Kept at 1 (= off) as a warning, like the note in nem_kernels.cu.
+#ifndef PK_CHASE
+#define PK_CHASE 1
+#endif
 
 // device-wide barrier: one atomic per CTA on a counter whose top bit flips when all have arrived
 // (the cooperative-groups scheme; 1.2 us for 296 CTAs on B200, profiles/pk_barrier_bench.cu)
@@ -55,11 +65,9 @@ static __device__ __forceinline__ void pk_grid_sync(unsigned *bar, unsigned nblo
 }
 
 // phase timer of CTA 0 / thread 0 (nemk_persist_out.phase_ns)
-static __device__ __forceinline__ unsigned long long pk_now() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
+// (SM cycle counter: CTA 0 never migrates; a %globaltimer read is far slower and would sit on the
+// critical path of every phase; the host converts with the SM clock rate)
+static __device__ __forceinline__ unsigned long long pk_now() { return (unsigned long long)clock64(); }
 struct PkProf { unsigned long long t_last, ns[12]; long long *trace; };   // trace: row of the current iteration or NULL
 static __device__ __forceinline__ int pk_trace_col(int idx) {   // phase index -> trace column
     return idx == 1 ? 0 : (idx == 2 || idx == 3) ? 1 : idx == 4 ? 2 : idx == 6 ? 3 : (idx == 7 || idx == 8) ? 4 : idx == 9 ? 5 : -1;
@@ -75,7 +83,10 @@ struct PkNext { int32_t *list, *cnt, *ovf; int cap; };
 // label of site i moved: every later reader goes to the next round (no de-duplication), earlier-or-
 // equal readers keep this sweep's evaluation, which saw the OLD label: their cached margin is void
 static __device__ __forceinline__ void pk_push_readers(int i, const int32_t *rrow_ptr, const int32_t *rcol,
-                                                       const PkNext &nx, uint8_t *stale_next) {
+                                                       const PkNext &nx, uint8_t *stale_next,
+                                                       int *chase = nullptr) {
+    // chase (nullable, in: -1): receives the FIRST later reader in row order, which is then not
+    // appended -- the caller goes on with it in the same round
     const int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
     for (int e = lo; e < hi; e += 8) {
         int j[8], nl = 0;
@@ -84,7 +95,8 @@ static __device__ __forceinline__ void pk_push_readers(int i, const int32_t *rro
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             if (j[q] < 0) continue;
-            if (j[q] <= i) { if (stale_next) stale_next[j[q]] = 1; }
+            if (j[q] <= i) { if (stale_next) stale_next[j[q]] = 1; j[q] = -1; }
+            else if (chase && *chase < 0) { *chase = j[q]; j[q] = -1; }
             else nl++;
         }
         if (nl) {
@@ -92,7 +104,7 @@ static __device__ __forceinline__ void pk_push_readers(int i, const int32_t *rro
             if (base + nl > nx.cap) { *nx.ovf = 1; continue; }   // the next round then takes every site
 #pragma unroll
             for (int q = 0; q < 8; q++)
-                if (j[q] > i) nx.list[base++] = j[q];
+                if (j[q] >= 0) nx.list[base++] = j[q];
         }
     }
 }
@@ -114,9 +126,51 @@ static __device__ __forceinline__ void pk_push_readers_warp(int i, const int32_t
     }
 }
 
+// label byte i := km, returns the label it REPLACED (CAS on the aligned word): with duplicates racing
+// in a fix-up round, the chain of replaced labels telescopes, so statistics moved "from the replaced
+// label to the new one" stay exact
+static __device__ __forceinline__ int pk_xchg_label(uint8_t *lab, int i, int km) {
+    unsigned *w = reinterpret_cast<unsigned *>(lab + (i & ~3));
+    const int sh = (i & 3) * 8;
+    unsigned old = __ldcg(w), assumed;
+    do {
+        assumed = old;
+        old = atomicCAS(w, assumed, (assumed & ~(0xffu << sh)) | ((unsigned)km << sh));
+    } while (old != assumed);
+    return (int)((old >> sh) & 0xffu);
+}
+
+// family `row` leaves class `from` for class `to`: its bits move between the integer statistics
+// S[from], S[to] and n (exact, order-free).  By a whole warp.
+static __device__ __forceinline__ void pk_move_row(const nemk_persist_args &a, int row, int from, int to) {
+    const int lane = threadIdx.x & 31, D = a.D, wreal = (D + 31) >> 5;
+    int32_t *S = a.stat, *nk = a.stat + (size_t)a.K * D;
+    if (lane == 0) { atomicAdd(&nk[from], -1); atomicAdd(&nk[to], 1); }
+    const uint32_t *xr = a.x + (size_t)row * a.wpr;
+    for (int w = lane; w < wreal; w += 32) {
+        uint32_t bits = __ldg(xr + w);
+        while (bits) {
+            const int d = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            atomicAdd(&S[(size_t)from * D + d], -1);
+            atomicAdd(&S[(size_t)to * D + d], 1);
+        }
+    }
+}
+// the rows whose lanes hold chg != 0 move from `from` to `to` (all lanes must call)
+static __device__ __forceinline__ void pk_move_rows_warp(const nemk_persist_args &a, int chg, int row,
+                                                        int from, int to) {
+    unsigned cm = __ballot_sync(FULL, chg != 0);
+    while (cm) {
+        const int src = __ffs(cm) - 1;
+        cm &= cm - 1;
+        pk_move_row(a, __shfl_sync(FULL, row, src), __shfl_sync(FULL, from, src), __shfl_sync(FULL, to, src));
+    }
+}
+
 // ---- one site of the Jacobi round (every input is an OLD label), new label to lab_out
 template <int KT>
-static __device__ __forceinline__ void pk_jac_site(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
+static __device__ __forceinline__ int pk_jac_site(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
                                                    const int32_t *col, const float *wgt, double beta,
                                                    const uint8_t *lab_in, uint8_t *lab_out, bool seq,
                                                    const int32_t *rrow_ptr, const int32_t *rcol,
@@ -133,6 +187,7 @@ static __device__ __forceinline__ void pk_jac_site(int K, int i, const nemk_lpsr
     store_margin(mg, i, margin, thr_store);
     if (mg.m) mg.stale_cur[i] = 0;
     if (seq && km != lin) pk_push_readers(i, rrow_ptr, rcol, nx, mg.stale_next);
+    return km != lin ? km + 1 : 0;      // 0 = unchanged, else new label + 1
 }
 
 // a hub of the Jacobi round, by a whole warp (update=para only: the sequential sweep defers its hubs
@@ -151,14 +206,17 @@ static __device__ __forceinline__ void pk_jac_hub(int K, int i, const nemk_lpsrc
 }
 
 // ---- re-evaluation of site i in a fix-up round: lower inputs are CURRENT labels (they move during
-// the round: __ldcg), the others old
+// the round: __ldcg), the others old.  Returns 0 when the label stands, else new label + 1;
+// `replaced` = the label the store replaced (track: exchanged, so racing duplicates telescope),
+// `chase` = the first later reader (not queued: the caller goes on with it in this round).
 template <int KT>
-static __device__ __forceinline__ void pk_fix_site(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
-                                                   const int32_t *col, const float *wgt, double beta,
-                                                   const uint8_t *lab_old, uint8_t *lab_cur,
-                                                   const int32_t *rrow_ptr, const int32_t *rcol,
-                                                   const PkNext &nx, const nemk_margins &mg,
-                                                   double thr_store, uint8_t *evflag) {
+static __device__ __forceinline__ int pk_fix_site(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
+                                                  const int32_t *col, const float *wgt, double beta,
+                                                  const uint8_t *lab_old, uint8_t *lab_cur,
+                                                  const int32_t *rrow_ptr, const int32_t *rcol,
+                                                  const PkNext &nx, const nemk_margins &mg,
+                                                  double thr_store, uint8_t *evflag, bool track,
+                                                  int &replaced, int &chase) {
     double ctx[KT], lpv[KT], margin;
     const int was = (int)__ldcg(lab_cur + i);
     load_lp<KT>(lps, K, (size_t)i, lpv);
@@ -168,17 +226,21 @@ static __device__ __forceinline__ void pk_fix_site(int K, int i, const nemk_lpsr
     const int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
     store_margin(mg, i, margin, thr_store);     // the LAST evaluation of a site is its final one
     evflag[i] = (uint8_t)fl;
-    if (km == was) return;
-    lab_cur[i] = (uint8_t)km;
-    pk_push_readers(i, rrow_ptr, rcol, nx, mg.stale_next);
+    chase = -1;
+    if (km == was) return 0;
+    if (track) replaced = pk_xchg_label(lab_cur, i, km);
+    else { lab_cur[i] = (uint8_t)km; replaced = was; }
+    pk_push_readers(i, rrow_ptr, rcol, nx, mg.stale_next, &chase);
+    return km + 1;
 }
+// a hub, by a whole warp; statistics and the net changed count included
 template <int KT>
-static __device__ __forceinline__ void pk_fix_hub(int K, int i, const nemk_lpsrc &lps, const int32_t *rp,
-                                                  const int32_t *col, const float *wgt, double beta,
-                                                  const uint8_t *lab_old, uint8_t *lab_cur,
+static __device__ __forceinline__ void pk_fix_hub(const nemk_persist_args &a, int K, int i, const nemk_lpsrc &lps,
+                                                  const int32_t *rp, const int32_t *col, const float *wgt,
+                                                  double beta, const uint8_t *lab_old, uint8_t *lab_cur,
                                                   const int32_t *rrow_ptr, const int32_t *rcol,
                                                   const PkNext &nx, const nemk_margins &mg,
-                                                  double thr_store, uint8_t *evflag) {
+                                                  double thr_store, uint8_t *evflag, bool track) {
     const int lane = threadIdx.x & 31;
     double ctx[KT], lpv[KT], margin;
     int was = (int)__ldcg(lab_cur + i);
@@ -189,12 +251,26 @@ static __device__ __forceinline__ void pk_fix_hub(int K, int i, const nemk_lpsrc
     int fl;
     const int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
     was = __shfl_sync(FULL, was, 0);
+    int replaced = was;
     if (lane == 0) {
         store_margin(mg, i, margin, thr_store);
         evflag[i] = (uint8_t)fl;
-        if (km != was) lab_cur[i] = (uint8_t)km;
+        if (km != was) {
+            if (track) replaced = pk_xchg_label(lab_cur, i, km);
+            else lab_cur[i] = (uint8_t)km;
+        }
     }
-    if (km != was) pk_push_readers_warp(i, rrow_ptr, rcol, nx, mg.stale_next);
+    if (km == was) return;
+    pk_push_readers_warp(i, rrow_ptr, rcol, nx, mg.stale_next);
+    if (track) {
+        replaced = __shfl_sync(FULL, replaced, 0);
+        if (replaced != km) {
+            pk_move_row(a, i, replaced, km);
+            const int old = (int)lab_old[i];
+            const int dn = (km != old) - (replaced != old);
+            if (lane == 0 && dn) atomicAdd(&a.scratch[6], dn);
+        }
+    }
 }
 
 // ---- one E-step sweep (ComputePartitionNEM nem_alg.c:2330-2405 for ncem).  All CTAs call it.
@@ -202,25 +278,38 @@ static __device__ __forceinline__ void pk_fix_hub(int K, int i, const nemk_lpsrc
 // point; margins (mg.m != NULL) only with seq.  cnt->kept receives the sites the margin cache
 // saved.  The caller counts the changed labels afterwards (pk_scan).
 template <int KT>
-static __device__ void pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lps, double beta,
+static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lps, double beta,
                                bool use_graph, bool seq, const uint8_t *lab_in, uint8_t *lab_out,
                                nemk_margins mg, nemk_counters *cnt, nemk_counters *cnt_next,
                                float *s_w, uint8_t *s_l, int &barriers, long long &kept_total,
-                               int &nfix_total, PkProf &prof) {
+                               int &nfix_total, PkProf &prof, bool track_ok, int mu_changed) {
     const int K = a.K, n = a.n;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nwarps = nthreads >> 5, gwarp = gtid >> 5;
     const int32_t *rp = use_graph ? a.row_ptr : nullptr;
     int32_t *wl_cnt = a.wl_cnt, *ovf = a.scratch + 8;
-    const SweepThr thr = sweep_thr(K, lps.coef, mg);
+    // (sweep_thr with the kernel's own copy of mu_changed: coef->mu_changed is only kept for the
+    // kernels that run outside, and nothing resets it between iterations here)
+    SweepThr thr;
+    thr.test = CUDART_INF; thr.store = 0.0;
+    if (mg.m && mg.on && !mu_changed) {
+        double step = 0.0;
+        for (int k = 0; k < K; k++) step = fmax(step, lps.coef->dstep[k]);
+        if (step < CUDART_INF) { thr.store = lps.coef->drift + 2.0 * step; thr.test = thr.store + 1e-6; }
+    }
     const bool may_skip = mg.m && thr.test < CUDART_INF;
     const bool hubs = rp && a.n_heavy > 0;
+    // track: the integer statistics S, n (which describe lab_in when the sweep starts) follow every
+    // label move of this sweep at once, so the next M-step needs neither a scan nor an update
+    // phase; only in margin-cached sweeps after a sweep that moved few labels (a row costs its set
+    // bits in atomics).  scratch[6] = net number of labels != lab_in.
+    const bool track = PK_TRACK && track_ok && may_skip;
     const PkNext nx0 = {a.wlist[0], &wl_cnt[0], &ovf[0], a.wl_cap};   // the list of fix-up round 0
     int kept = 0;
     // counters of the last scan: every CTA read them right after the scan's barrier and has passed
     // another barrier since (closed forms); the next scan starts after this sweep's barriers
-    if (gtid == 0) { wl_cnt[4] = 0; a.scratch[3] = 0; a.scratch[4] = 0; }
+    if (gtid == 0) { wl_cnt[4] = 0; a.scratch[3] = 0; a.scratch[4] = 0; a.scratch[6] = 0; a.scratch[7] = track; }
 
     if (may_skip) {
         // ---- phase: margin test + evaluation, one warp per 128 consecutive sites.  A site whose
@@ -301,9 +390,19 @@ static __device__ void pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
                 sm_act[pos++] = i0 + q;
             }
             __syncwarp();
-            for (int r = lane; r < total; r += 32)
-                pk_jac_site<KT>(K, sm_act[r], lps, rp, a.col, a.wgt, beta, lab_in, lab_out, seq, a.rrow_ptr,
-                                a.rcol, nx0, mg, thr.store, a.evflag);
+            for (int r0 = 0; r0 < total; r0 += 32) {
+                const int r = r0 + lane, site = r < total ? sm_act[r] : -1;
+                int res = 0;
+                if (site >= 0)
+                    res = pk_jac_site<KT>(K, site, lps, rp, a.col, a.wgt, beta, lab_in, lab_out, seq, a.rrow_ptr,
+                                          a.rcol, nx0, mg, thr.store, a.evflag);
+                if (track) {
+                    const int from = site >= 0 ? (int)lab_in[site] : 0;
+                    pk_move_rows_warp(a, res, site, from, res - 1);
+                    const int nch = __popc(__ballot_sync(FULL, res != 0));
+                    if (lane == 0 && nch) atomicAdd(&a.scratch[6], nch);
+                }
+            }
             __syncwarp();
             nact += total;
         }
@@ -391,17 +490,46 @@ static __device__ void pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
             rounds++;
             for (int base = gwarp; base < items; base += 32 * nwarps) {
                 const int idx = base + lane * nwarps;
-                const int i = idx < items ? (all ? idx : cur_list[idx]) : -1;
+                int i = idx < items ? (all ? idx : cur_list[idx]) : -1;
+                // hubs by the whole warp
                 const bool hub = i >= 0 && (rp[i + 1] - rp[i] > HEAVY_DEG);
-                if (i >= 0 && !hub)
-                    pk_fix_site<KT>(K, i, lps, rp, a.col, a.wgt, beta, lab_in, lab_out, a.rrow_ptr, a.rcol, nx,
-                                    mg, thr.store, a.evflag);
                 unsigned hm = __ballot_sync(FULL, hub);
                 while (hm) {
                     const int src = __ffs(hm) - 1;
                     hm &= hm - 1;
-                    pk_fix_hub<KT>(K, __shfl_sync(FULL, i, src), lps, rp, a.col, a.wgt, beta, lab_in, lab_out,
-                                   a.rrow_ptr, a.rcol, nx, mg, thr.store, a.evflag);
+                    pk_fix_hub<KT>(a, K, __shfl_sync(FULL, i, src), lps, rp, a.col, a.wgt, beta, lab_in, lab_out,
+                                   a.rrow_ptr, a.rcol, nx, mg, thr.store, a.evflag, track);
+                }
+                if (hub) i = -1;
+                // light sites by their lane; a site that moved goes on with its first later reader
+                // in the same round (the usual dependency is the next family along the chromosome)
+                // instead of paying a round per link
+                for (int step = 0; step < PK_CHASE; step++) {
+                    int res = 0, replaced = 0, chase = -1;
+                    if (i >= 0 && step > 0 && rp[i + 1] - rp[i] > HEAVY_DEG) {   // a chased hub: next round
+                        const int b = atomicAdd(nx.cnt, 1);
+                        if (b + 1 > nx.cap) *nx.ovf = 1; else nx.list[b] = i;
+                        i = -1;
+                    }
+                    if (i >= 0)
+                        res = pk_fix_site<KT>(K, i, lps, rp, a.col, a.wgt, beta, lab_in, lab_out, a.rrow_ptr, a.rcol,
+                                              nx, mg, thr.store, a.evflag, track, replaced, chase);
+                    if (track) {
+                        const int moved = res != 0 && replaced != res - 1;
+                        pk_move_rows_warp(a, moved, i, replaced, res - 1);
+                        if (moved) {
+                            const int old = (int)lab_in[i];
+                            const int dn = ((res - 1) != old) - (replaced != old);
+                            if (dn) atomicAdd(&a.scratch[6], dn);
+                        }
+                    }
+                    if (step + 1 == PK_CHASE && chase >= 0) {   // chain longer than the chase: queue it
+                        const int b = atomicAdd(nx.cnt, 1);
+                        if (b + 1 > nx.cap) *nx.ovf = 1; else nx.list[b] = chase;
+                        chase = -1;
+                    }
+                    i = res ? chase : -1;
+                    if (!__any_sync(FULL, i >= 0)) break;
                 }
             }
             pk_grid_sync(a.bar, gridDim.x); barriers++;
@@ -418,21 +546,21 @@ static __device__ void pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
     }
     nfix_total += rounds;
     kept_total += ((const volatile nemk_counters *)cnt)->kept;
+    return track;
 }
 
 // ---- after a sweep: the rows whose label differs from the sweep's input.  Counts them (the
 // `clas` convergence test, nem_alg.c:2075-2089, and the size of the M-step's update), sums the
 // all-null / tie flags of every site's last evaluation, and feeds the incremental statistics:
 // mode 0 count only, 1 append the rows to `list` (the M-step updates S and n from the list after
-// the barrier, 32 rows per ballot transpose), 2 the warp that finds a row moves its bits from
-// S[old] to S[new] itself (few rows: no list, no barrier).  16 labels per lane.
+// the barrier, 32 rows per ballot transpose).  16 labels per lane.  Sweeps that tracked their label
+// moves (pk_sweep `track`) need no scan; their flags are summed once, when the kernel is left.
 template <int KT>
 static __device__ void pk_scan(const nemk_persist_args &a, const uint8_t *lab, const uint8_t *lab_m,
                                int mode, int32_t *list, int32_t *count) {
-    const int n = a.n, K = a.K, D = a.D, wreal = (D + 31) >> 5;
+    const int n = a.n;
     const int nthreads = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
     const int ngroups = (n + 15) >> 4;
-    int32_t *S = a.stat, *nk = a.stat + (size_t)K * D;
     int nul = 0, ties = 0;
     for (int t0 = ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); t0 < ngroups; t0 += nthreads) {
         const int t = t0 + lane, i0 = t * 16;
@@ -474,31 +602,6 @@ static __device__ void pk_scan(const nemk_persist_args &a, const uint8_t *lab, c
             while (m) {
                 list[pos++] = i0 + __ffs(m) - 1;
                 m &= m - 1;
-            }
-        } else if (mode == 2) {
-            // the warp moves every changed row of its 512 families itself (exact integer updates)
-            unsigned lanes = __ballot_sync(FULL, dm != 0u);
-            while (lanes) {
-                const int src = __ffs(lanes) - 1;
-                lanes &= lanes - 1;
-                uint32_t m = __shfl_sync(FULL, dm, src);
-                const int r0 = __shfl_sync(FULL, i0, src);
-                while (m) {
-                    const int row = r0 + __ffs(m) - 1;
-                    m &= m - 1;
-                    const int lo = lab_m[row], ln = lab[row];
-                    if (lane == 0) { atomicAdd(&nk[lo], -1); atomicAdd(&nk[ln], 1); }
-                    const uint32_t *xr = a.x + (size_t)row * a.wpr;
-                    for (int w = lane; w < wreal; w += 32) {
-                        uint32_t bits = __ldg(xr + w);
-                        while (bits) {
-                            const int d = w * 32 + __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            atomicAdd(&S[(size_t)lo * D + d], -1);
-                            atomicAdd(&S[(size_t)ln * D + d], 1);
-                        }
-                    }
-                }
             }
         }
     }
@@ -651,10 +754,12 @@ static __device__ void pk_finalize_class(int k, const nemk_persist_args &a, doub
             const size_t o = (size_t)k * wpr + w;
             a.mxor[o] = 0u; a.mval[o] = 0u; a.f0[o] = 0u; a.f1[o] = 0u;
         }
-        if (mu_moved) atomicOr(&a.coef->mu_changed, 1);
+        const int any_moved = __syncthreads_or(mu_moved);
         pk_block_sum4<TH>(sums, sh);
-        if (tid == 0)
+        if (tid == 0) {
+            a.coef->mu_moved_k[k] = any_moved;
             tables_commit(k, K, D, a.prop, a.coef, a.delta, cc, sums[0], sums[1], true, (int)sums[2], (int)sums[3], true);
+        }
         return;
     }
     // ---- general path
@@ -709,12 +814,14 @@ static __device__ void pk_finalize_class(int k, const nemk_persist_args &a, doub
         const size_t o = (size_t)k * wpr + w;
         a.mxor[o] = 0u; a.mval[o] = 0u; a.f0[o] = 0u; a.f1[o] = 0u;
     }
-    if (p.mu_moved) atomicOr(&a.coef->mu_changed, 1);
+    const int any_moved = __syncthreads_or(p.mu_moved);
     double sums[4] = {p.base_u, p.base_g, (double)p.n_valid, (double)p.n_x1};
     const double notok = block_sum<TH>((double)p.notok, sh);
     pk_block_sum4<TH>(sums, sh);
-    if (tid == 0)
+    if (tid == 0) {
+        a.coef->mu_moved_k[k] = any_moved;
         tables_commit(k, K, D, a.prop, a.coef, a.delta, cc, sums[0], sums[1], notok == 0.0, (int)sums[2], (int)sums[3], true);
+    }
 }
 
 // tables of the theta the caller supplied (k_theta_tables), class k by one CTA
@@ -723,7 +830,6 @@ static __device__ void pk_tables_class(int k, const nemk_persist_args &a, double
     const ClassCoef cc = class_coef(a.disp[(size_t)k * a.D]);
     TablesPartial p = tables_words(k, a.D, a.wpr, 0, a.wpr, cc, a.center, a.disp, a.mxor, a.mval,
                                    a.f0, a.f1, a.delta);
-    if (p.mu_moved) atomicOr(&a.coef->mu_changed, 1);
     const double base_u = block_sum<TH>(p.base_u, sh), base_g = block_sum<TH>(p.base_g, sh);
     const double notok = block_sum<TH>((double)p.notok, sh);
     const double nv = block_sum<TH>((double)p.n_valid, sh), nx = block_sum<TH>((double)p.n_x1, sh);
@@ -859,7 +965,10 @@ k_em_persist(const nemk_persist_args a) {
     int state = a.entry, it = a.iter0, cur = a.cur, stale_par = a.stale_par;
     int stats_valid = a.stats_valid, last_changed = a.last_changed, margins_on = a.margins_on;
     int barriers = 0, sweeps = 0, x_passes = 0, recounts = 0, nfix = 0, cnt_par = a.cnt_par;
-    int delta_mode = a.delta_mode;      // what the last scan did with the changed rows (0 / 1 / 2)
+    int delta_mode = a.delta_mode;      // statistics vs lab[cur]: 0 stale (recount), 1 update from the scan's
+                                        // list pending, 2 current (the sweep tracked its label moves)
+    int flags_stale = a.flags_stale;    // n_allnul / n_ties do not describe the last sweep yet
+    int mu_changed = a.mu_changed;      // the class masks moved in the last tables (cached Hamming counts void)
     long long kept = 0;
     int exit_code = NEMK_PK_EXIT_DONE, resume = NEMK_PK_ENTRY_MSTEP, converged = 0, empty = 0;
     int n_allnul = a.n_allnul, n_ties = a.n_ties;
@@ -884,6 +993,7 @@ k_em_persist(const nemk_persist_args a) {
                 reinterpret_cast<uint32_t *>(a.stale[1])[i] = 0u;
                 reinterpret_cast<uint32_t *>(a.evflag)[i] = 0u;
             }
+            mu_changed = 1;
             if (gtid == 0) {
                 a.coef->uniform_ok = 1; a.coef->mu_changed = 1; a.coef->empty_class = 0; a.coef->halt = 0;
                 // zero at rest from here on (a launch-per-stage fit on the same handle does not keep
@@ -924,7 +1034,7 @@ k_em_persist(const nemk_persist_args a) {
             // from the scan's list (1), or recounted
             const bool incremental = stats_valid && last_changed >= 0 && last_changed <= n / 8;
             if (stats_valid && delta_mode == 2) {
-                // nothing left to do
+                // the sweep tracked its label moves: nothing left to do
             } else if (incremental && delta_mode == 1) {
                 mstep_delta_items<KT>(K, D, a.wpr, a.x, a.lab[cur], a.lab[cur ^ 1], a.wlist[1], last_changed,
                                       a.stat, a.stat + (size_t)K * D);
@@ -945,18 +1055,21 @@ k_em_persist(const nemk_persist_args a) {
             }
             state = S_FINALIZE;
         } else if (state == S_FINALIZE) {
-            stats_valid = 1;
+            stats_valid = 1; delta_mode = 2;    // S and n describe lab[cur] (updated, recounted, or tracked)
             for (int k = blockIdx.x; k < K; k += gridDim.x) pk_finalize_class<PK_THREADS>(k, a, sh, nkf, nkd);
             PK_SYNC();
             PK_MARK(prof, 4);
             const volatile nemk_coef *vc = a.coef;
             empty = vc->empty_class;
+            mu_changed = 0;
+            for (int k = 0; k < K; k++) mu_changed |= vc->mu_moved_k[k];
+            if (gtid == 0) a.coef->mu_changed = mu_changed;     // for the kernels that run outside
             if (empty) {   // nem_alg.c:1831-1838: the E-step is not run, the loop ends
                 it++;
                 break;
             }
             state = S_SWEEP;
-            if (vc->mu_changed) {
+            if (mu_changed) {
                 if (a.x_in_kernel) {
                     pk_density_pass<KT>(a);
                     x_passes++;
@@ -982,30 +1095,42 @@ k_em_persist(const nemk_persist_args a) {
                 mg.on = state == S_BETA0 ? 0 : margins_on;
                 stale_par ^= 1;
             }
-            pk_sweep<KT>(a, lps, blind ? 0.0 : a.beta, use_graph && !blind, seq && !blind, a.lab[cur],
-                         a.lab[cur ^ 1], mg, cnt, cnt_next, s_w, s_l, barriers, kept, nfix, prof);
+            // (PK_TRACK: statistics follow the label moves inside the sweep -- measured slower than
+            // the scan + list update: moved rows cluster in a few warps and a row costs its set bits
+            // in atomics; kept as a compile-time knob)
+            const bool track_ok = PK_TRACK && state == S_SWEEP && stats_valid && delta_mode == 2 &&
+                                  it + 1 < a.it_max && last_changed >= 0 && last_changed <= PK_TRACK_MAX;
+            const bool tracked = pk_sweep<KT>(a, lps, blind ? 0.0 : a.beta, use_graph && !blind, seq && !blind,
+                                              a.lab[cur], a.lab[cur ^ 1], mg, cnt, cnt_next, s_w, s_l, barriers,
+                                              kept, nfix, prof, track_ok, mu_changed);
             cur ^= 1;
             sweeps++;
+            flags_stale = 1;
             if (blind) { state = S_BETA0; continue; }
             margins_on = 1;   // the next sweep uses the same beta
             if (state == S_BETA0) {   // NemAlgo starts with a full recount: nothing to scan
-                if (gtid == 0) { a.coef->uniform_ok = 1; a.coef->mu_changed = 0; }   // presets of the next tables
                 last_changed = -1; delta_mode = 0;
                 state = S_MSTEP;
                 continue;
             }
-            // ---- the rows this sweep moved: count (convergence test), flags of the last evaluations,
-            // and the incremental statistics of the next M-step
-            const int want = (it + 1 >= a.it_max || !stats_valid) ? 0 : 1;
-            if (gtid == 0) { a.coef->uniform_ok = 1; a.coef->mu_changed = 0; }   // presets of the next tables
-            pk_scan<KT>(a, a.lab[cur], a.lab[cur ^ 1], want, a.wlist[1], &a.wl_cnt[4]);
-            PK_SYNC();
-            PK_MARK(prof, 1);
-            last_changed = *(volatile int32_t *)&a.wl_cnt[4];
-            n_allnul = *(volatile int32_t *)&a.scratch[3];
-            n_ties = *(volatile int32_t *)&a.scratch[4];
-            delta_mode = want;
-            if (want == 0) stats_valid = 0;     // the statistics no longer describe lab[cur ^ 1] + a list
+            if (tracked) {
+                // the statistics followed the sweep: they describe lab[cur]; net number of moved labels
+                last_changed = *(volatile int32_t *)&a.scratch[6];
+                delta_mode = 2;
+            } else {
+                // ---- the rows this sweep moved: count (convergence test), flags of the last
+                // evaluations, and the list the next M-step updates its statistics from
+                const int want = (it + 1 >= a.it_max || !stats_valid) ? 0 : 1;
+                pk_scan<KT>(a, a.lab[cur], a.lab[cur ^ 1], want, a.wlist[1], &a.wl_cnt[4]);
+                PK_SYNC();
+                PK_MARK(prof, 1);
+                last_changed = *(volatile int32_t *)&a.wl_cnt[4];
+                n_allnul = *(volatile int32_t *)&a.scratch[3];
+                n_ties = *(volatile int32_t *)&a.scratch[4];
+                flags_stale = 0;
+                delta_mode = want;
+                if (want == 0) stats_valid = 0;   // neither current nor one list away from it
+            }
             it++;
             state = S_MSTEP;
             if (a.conv == 1) {   // HasConverged `clas` under ncem: no label changed
@@ -1014,11 +1139,20 @@ k_em_persist(const nemk_persist_args a) {
             }
         }
     }
+    if (exit_code == NEMK_PK_EXIT_DONE && flags_stale && sweeps > 0) {
+        // all-null rows / exact ties of the last sweep: flags of every site's last evaluation
+        // (scratch[3], [4] are zero: the sweep cleared them and no scan followed)
+        pk_scan<KT>(a, a.lab[cur], a.lab[cur], 0, nullptr, &a.wl_cnt[5]);
+        PK_SYNC();
+        n_allnul = *(volatile int32_t *)&a.scratch[3];
+        n_ties = *(volatile int32_t *)&a.scratch[4];
+        flags_stale = 0;
+    }
     if (gtid == 0) {
         nemk_persist_out *o = a.out;
         o->exit_code = exit_code; o->resume_entry = resume;
         o->iters = it; o->converged = converged; o->empty_class = empty;
-        o->cnt_par = cnt_par; o->delta_mode = delta_mode;
+        o->cnt_par = cnt_par; o->delta_mode = delta_mode; o->flags_stale = flags_stale; o->mu_changed = mu_changed;
         o->cur = cur; o->stale_par = stale_par; o->last_changed = last_changed; o->stats_valid = stats_valid;
         o->n_allnul = n_allnul; o->n_ties = n_ties;
         o->sweeps = sweeps; o->x_passes = x_passes; o->recounts = recounts; o->barriers = barriers;
