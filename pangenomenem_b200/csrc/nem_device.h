@@ -326,6 +326,10 @@ typedef struct {
      * (or recount), finalize, margin test, evaluation, fix-up rounds; [it][6] = active sites of the
      * evaluation (-1: dense round), [it][7] = fix-up rounds */
     long long trace[12][8];
+    /* final criteria U D L M Z G (ComputeCrit, nem_alg.c:2678-2757) when have_crit: computed by
+     * the kernel itself when it is left for good */
+    double crit[6];
+    int32_t have_crit, pad1;
     unsigned long long seq;             /* written last, after a system-wide fence */
 } nemk_persist_out;
 
@@ -364,6 +368,8 @@ typedef struct {
     int32_t *scratch;         /* [16] ints, zero at rest: [3] all-null rows [4] ties of the last sweep,
                                  [8..11] overflow flags of the rotating work lists */
     nemk_counters *cnt2;      /* [2] alternating per-sweep counter blocks, zero at entry */
+    double *crit_partials;    /* [grid][4] per-CTA partial sums of the final criteria */
+    int32_t want_crit, spatial;   /* evaluate the final criteria inside; the problem has a graph */
     unsigned *bar;            /* [2] device-wide barrier state (count, generation) */
     nemk_persist_out *out;    /* mapped pinned host memory */
 } nemk_persist_args;

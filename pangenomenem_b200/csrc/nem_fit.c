@@ -153,6 +153,7 @@ void nemb_destroy(nemb_handle *h)
     if (h->ring) cudaFreeHost(h->ring);
     if (h->pk_out) cudaFreeHost(h->pk_out);
     if (h->h_lab_stage) cudaFreeHost(h->h_lab_stage);
+    if (h->h_theta_stage) cudaFreeHost(h->h_theta_stage);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 16; i++) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
     for (int i = 0; i < h->ev_cap; i++) cudaEventDestroy(h->ev[i]);
@@ -1176,6 +1177,47 @@ static int init_state(nemb_handle *h, const nemb_options *o)
     return NEMB_OK;
 }
 
+/* theta (prop[K], center[K*D], disp[K*D]) lives in one span of the per-K slab: one copy each way
+ * through a pinned staging buffer instead of three pageable copies */
+static int theta_stage(nemb_handle *h, size_t bytes)
+{
+    if (h->h_theta_cap >= bytes) return NEMB_OK;
+    if (h->h_theta_stage) cudaFreeHost(h->h_theta_stage);
+    h->h_theta_stage = NULL; h->h_theta_cap = 0;
+    CK(cudaMallocHost((void **)&h->h_theta_stage, bytes + 256));
+    h->h_theta_cap = bytes + 256;
+    return NEMB_OK;
+}
+static int theta_h2d(nemb_handle *h, int k, const float *prop, const float *center, const float *disp)
+{
+    const size_t kd = (size_t)k * h->d;
+    const size_t o_c = (size_t)((char *)h->d_center - (char *)h->d_prop), o_d = (size_t)((char *)h->d_disp - (char *)h->d_prop);
+    const size_t span = o_d + sizeof(float) * kd;
+    int rc = theta_stage(h, span);
+    if (rc != NEMB_OK) return rc;
+    char *st = (char *)h->h_theta_stage;
+    memcpy(st, prop, sizeof(float) * k);
+    memcpy(st + o_c, center, sizeof(float) * kd);
+    memcpy(st + o_d, disp, sizeof(float) * kd);
+    CK(cudaMemcpyAsync(h->d_prop, st, span, cudaMemcpyHostToDevice, h->stream));
+    return NEMB_OK;
+}
+static int theta_d2h(nemb_handle *h, int k, float *prop, float *center, float *disp)
+{
+    const size_t kd = (size_t)k * h->d;
+    const size_t o_c = (size_t)((char *)h->d_center - (char *)h->d_prop), o_d = (size_t)((char *)h->d_disp - (char *)h->d_prop);
+    const size_t span = o_d + sizeof(float) * kd;
+    int rc = theta_stage(h, span);
+    if (rc != NEMB_OK) return rc;
+    char *st = (char *)h->h_theta_stage;
+    CK(cudaMemcpyAsync(st, h->d_prop, span, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(prop, st, sizeof(float) * k);
+    memcpy(center, st + o_c, sizeof(float) * kd);
+    memcpy(disp, st + o_d, sizeof(float) * kd);
+    return NEMB_OK;
+}
+
 /* ------------------------------------------------------------------ persistent EM kernel */
 /* Which fits run as ONE cooperative launch (nem_persist.cuh): ncem on the popcount density path
  * with the per-class dispersion models, one GPU, started from theta -- PPanGGOLiN's call
@@ -1208,6 +1250,7 @@ static int ensure_persist(nemb_handle *h)
     size_t o_scr = carve(&off, sizeof(int32_t) * 16);
     size_t o_cnt = carve(&off, sizeof(nemk_counters) * 2);
     size_t o_bar = carve(&off, sizeof(unsigned) * 4);
+    size_t o_crit = carve(&off, sizeof(double) * 4 * 2048);
     int fresh = h->b_pk.cap < off;
     int rc = reserve(h, &h->b_pk, off);
     if (rc != NEMB_OK) return rc;
@@ -1221,10 +1264,11 @@ static int ensure_persist(nemb_handle *h)
     unsigned *bar = (unsigned *)(base + o_bar);
     if (fresh || scr != h->d_pk_scratch || cnt2 != h->d_pk_cnt2 || bar != h->d_pk_bar) {
         /* zero at rest: the kernel leaves its counters, lists and the barrier clean */
-        CK(cudaMemsetAsync(base + o_scr, 0, off - o_scr, h->stream));
+        CK(cudaMemsetAsync(base + o_scr, 0, o_crit - o_scr, h->stream));
         h->pk_cnt_par = 0;
     }
     h->d_pk_scratch = scr; h->d_pk_cnt2 = cnt2; h->d_pk_bar = bar;
+    h->d_pk_crit = (double *)(base + o_crit);
     return NEMB_OK;
 }
 
@@ -1291,6 +1335,8 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     a.wlist[0] = h->d_pk_wl[0]; a.wlist[1] = h->d_pk_wl[1]; a.wl_cap = h->pk_wl_cap; a.evflag = h->d_pk_evflag;
     a.hub_list = h->d_pk_hub; a.scratch = h->d_pk_scratch; a.cnt2 = h->d_pk_cnt2; a.bar = h->d_pk_bar;
     a.out = h->d_pk_out;
+    a.crit_partials = h->d_pk_crit; a.want_crit = 1; a.spatial = h->spatial;
+    h->pk_have_crit = 0;
     /* host state of a fresh fit (the kernel's prep phase writes the device side) */
     h->cur = 0; h->state_labels = 1;
     h->ham_valid = 0; h->stats_valid = 0; h->last_changed = -1; h->prev_valid = 0;
@@ -1304,6 +1350,7 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     if (h->pk_grid_limit > 0 && want > h->pk_grid_limit) want = h->pk_grid_limit;
     if (h->pk_grid_env > 0) want = h->pk_grid_env;
     if (grid > want) grid = want;
+    if (grid > 2048) grid = 2048;      /* d_pk_crit rows */
     if (grid < 1) grid = 1;
     int done = 0, guard = 0;
     memset(h->pk_phase_ns, 0, sizeof h->pk_phase_ns);
@@ -1360,6 +1407,8 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         } else
             return fail(h, NEMB_E_BUG, "persistent EM kernel: unknown exit code %d", out.exit_code);
     }
+    h->pk_have_crit = out.have_crit;
+    memcpy(h->pk_crit, out.crit, sizeof h->pk_crit);
     h->sweep_same_beta = 1;
     /* the kernel's incremental statistics follow its own convention (they may already include the
      * last sweep's moves): a launch-per-stage M-step after it must recount */
@@ -1537,6 +1586,13 @@ tail:
         if ((rc = run_mstep(h, o, uniform_m)) != NEMB_OK) goto out;
         if ((rc = run_density(h, k, uniform_m, NULL, lean)) != NEMB_OK) goto out;
     }
+    if (persist && h->pk_have_crit) {
+        /* the kernel evaluated the criteria and reported the empty class: theta comes back in ONE
+         * copy through pinned memory */
+        if ((rc = theta_d2h(h, k, prop, center, disp)) != NEMB_OK) goto out;
+        memcpy(h->h_status->crit_after, h->pk_crit, sizeof h->pk_crit);
+        *h->h_empty = empty;
+    } else {
     if ((rc = run_criteria(h, o, beta, h->d_status->crit_after)) != NEMB_OK) goto out;
     CKO(cudaMemcpyAsync(prop, h->d_prop, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
     CKO(cudaMemcpyAsync(center, h->d_center, sizeof(float) * kd, cudaMemcpyDeviceToHost, h->stream));
@@ -1544,6 +1600,7 @@ tail:
     CKO(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(iter_status), cudaMemcpyDeviceToHost, h->stream));
     CKO(cudaMemcpyAsync(h->h_empty, &h->d_coef->empty_class, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CKO(cudaStreamSynchronize(h->stream));
+    }
     if (iter == 0 && *h->h_empty) { status = NEMB_W_EMPTYCLASS; empty = *h->h_empty; }
     res->status = status; res->iters = iter; res->converged = converged; res->empty_class = empty;
     const double *c6 = h->h_status->crit_after;
@@ -1600,15 +1657,12 @@ static int fit_common(nemb_handle *h, const nemb_options *o, float *prop, float 
     memset(res, 0, sizeof *res);
     h->launches = 0; h->fixup_rounds = 0; h->exchanges = 0; h->profile = o->profile; h->ev_n = 0;
     h->ev_last_density = h->ev_last_cached = -1;
-    size_t kd = (size_t)o->k * h->d;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, h->stream));
     int uniform0 = 0;
     if (!t_init) {
-        CK(cudaMemcpyAsync(h->d_prop, prop, sizeof(float) * o->k, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_center, center, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_disp, disp, sizeof(float) * kd, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = theta_h2d(h, o->k, prop, center, disp)) != NEMB_OK) return rc;
         uniform0 = theta_uniform(o->k, h->d, center, disp);
     }
     rc = em_core(h, o, uniform0, res, cb, user, prop, center, disp, t_init);

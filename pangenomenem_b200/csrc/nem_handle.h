@@ -104,6 +104,11 @@ struct nemb_handle {
     int pk_wl_cap, sm_khz;
     nemk_counters *d_pk_cnt2;
     unsigned *d_pk_bar;
+    double *d_pk_crit;          /* per-CTA partial sums of the in-kernel criteria */
+    int pk_have_crit;           /* the last persistent fit evaluated its final criteria itself */
+    double pk_crit[6];
+    float *h_theta_stage;       /* pinned staging of theta (one copy each way) */
+    size_t h_theta_cap;
     nemk_persist_out *pk_out, *d_pk_out;
     unsigned long long pk_seq;
     int pk_cnt_par, pk_ready_n, pk_ready_heavy;

@@ -946,6 +946,78 @@ static __device__ void pk_recount(const nemk_persist_args &a) {
     }
 }
 
+// ---- final criteria (ComputeCrit, nem_alg.c:2678-2757: D, G, L, Z per family, U = D + beta/2 G,
+// M = D + beta G + Z) from the hard labels, the densities of the last tables and the whole graph
+// (even when beta = 0): k_criteria_partial's walk -- hubs by a warp, the others 32 consecutive
+// sites per warp -- with per-CTA partial sums; CTA 0 adds them in CTA order after the barrier
+// (fixed order: reproducible for a given grid).
+template <int KT>
+static __device__ void pk_criteria_partial(const nemk_persist_args &a, const nemk_lpsrc &lps,
+                                           const uint8_t *lab, float *s_w, uint8_t *s_l, double *sh) {
+    const int K = a.K, n = a.n, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nwarps = nthreads >> 5, gwarp = gtid >> 5;
+    const int32_t *rp = a.spatial ? a.row_ptr : nullptr;
+    const bool hubs = rp && a.n_heavy > 0;
+    const double beta = a.beta;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};   // D G L Z
+    if (hubs)
+        for (int wi = gwarp; wi < a.n_heavy; wi += nwarps) {
+            const int i = a.heavy[wi];
+            double ctx[KT], lpv[KT];
+            float ti[KT];
+            ctx_labels_warp<KT>(K, i, rp, a.col, a.wgt, [&](int j) { return (unsigned)lab[j]; }, ctx,
+                                lps.wsum_any_order != 0);
+            const unsigned l = lab[i];
+#pragma unroll
+            for (int k = 0; k < KT; k++) ti[k] = (l == (unsigned)k) ? 1.f : 0.f;
+            if (lane == 0) {
+                load_lp<KT>(lps, K, (size_t)i, lpv);
+                crit_site<KT>(K, lpv, ctx, ti, beta, c[0], c[1], c[2], c[3]);
+            }
+        }
+    for (int base = gwarp * 32; base < n; base += nwarps * 32) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        int lo = 0, hi = 0;
+        if (rp && valid) { lo = rp[i]; hi = rp[i + 1]; }
+        const bool is_heavy = hubs && (hi - lo > HEAVY_DEG);
+        double ctx[KT], lpv[KT];
+        float ti[KT];
+#pragma unroll
+        for (int k = 0; k < KT; k++) ctx[k] = 0.0;
+        if (valid) load_lp<KT>(lps, K, (size_t)i, lpv);
+        if (rp) {
+            const int seg_lo = __reduce_min_sync(FULL, valid ? lo : 0x7fffffff);
+            const int seg_hi = __reduce_max_sync(FULL, valid ? hi : 0);
+            if (is_heavy) lo = hi = 0;
+            if (seg_lo < seg_hi)
+                ctx_labels_coop<KT>(lo, hi, seg_lo, seg_hi, a.col, a.wgt, lab, s_w + wib * COOP_CHUNK,
+                                    s_l + wib * COOP_CHUNK, ctx);
+        }
+        if (!valid || is_heavy) continue;
+        const unsigned l = lab[i];
+#pragma unroll
+        for (int k = 0; k < KT; k++) ti[k] = (l == (unsigned)k) ? 1.f : 0.f;
+        crit_site<KT>(K, lpv, ctx, ti, beta, c[0], c[1], c[2], c[3]);
+    }
+    pk_block_sum4<PK_THREADS>(c, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) a.crit_partials[(size_t)blockIdx.x * 4 + q] = c[q];
+    }
+}
+static __device__ void pk_criteria_final(const nemk_persist_args &a, double *sh, double *crit6) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += PK_THREADS)   // fixed assignment: deterministic
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] += a.crit_partials[(size_t)b * 4 + q];
+    pk_block_sum4<PK_THREADS>(v, sh);
+    const double D = v[0], G = v[1], L = v[2], Z = v[3], beta = a.beta;
+    crit6[0] = D + 0.5 * beta * G; crit6[1] = D; crit6[2] = L;
+    crit6[3] = D + beta * G + Z; crit6[4] = Z; crit6[5] = G;
+}
+
 // =============================================================================================
 template <int KT>
 __global__ void __launch_bounds__(PK_THREADS, 2)
@@ -1148,8 +1220,22 @@ k_em_persist(const nemk_persist_args a) {
         n_ties = *(volatile int32_t *)&a.scratch[4];
         flags_stale = 0;
     }
+    // the fit is over: the final criteria, from the densities of the last tables and the labels after
+    // the last sweep (nem_alg.c:1844-1853).  it == 0 (no EM iteration: the reference estimates
+    // theta once more first) is left to the host.
+    double crit6[6] = {0, 0, 0, 0, 0, 0};
+    int have_crit = 0;
+    if (exit_code == NEMK_PK_EXIT_DONE && a.want_crit && it > 0) {
+        pk_criteria_partial<KT>(a, lps, a.lab[cur], s_w, s_l, sh);
+        PK_SYNC();
+        if (blockIdx.x == 0) pk_criteria_final(a, sh, crit6);
+        have_crit = 1;
+        PK_MARK(prof, 11);
+    }
     if (gtid == 0) {
         nemk_persist_out *o = a.out;
+        for (int q = 0; q < 6; q++) o->crit[q] = crit6[q];
+        o->have_crit = have_crit;
         o->exit_code = exit_code; o->resume_entry = resume;
         o->iters = it; o->converged = converged; o->empty_class = empty;
         o->cnt_par = cnt_par; o->delta_mode = delta_mode; o->flags_stale = flags_stale; o->mu_changed = mu_changed;
