@@ -206,8 +206,13 @@ def main_reference(args):
         "unit": "family-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_steps * 1e3 / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "families": n, "genomes": d, "K": K,
-                   "beta": beta, "algo": "ncem", "update": "seq"},
+        "config": {"workload": workload_name(args.workload) + " -- measured on a BOUNDED SAMPLE of it: "
+                               + last["sample"].split(",")[0],
+                   "families": n, "genomes": d, "K": K, "beta": beta, "algo": "ncem", "update": "seq",
+                   "same_config_as_gpu_arm": False,
+                   "why": "the reference stores X as float[N*D] plus an int[N*D] sort index (40 GB at 1M x 5000) and "
+                          "takes ~7 s per iteration at 100k x 500 on one core: the full workload does not finish; "
+                          "per-family-iteration cost is what the sample measures"},
         "cpu_baseline": last,
         "e2e": {"value": v, "unit": "family-iterations/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -388,6 +393,70 @@ def main_c5(args):
         dist.destroy_process_group()
 
 
+
+# ----------------------------------------------------------------------------- extra measurements
+def timed_fits(torch, eng, theta0, opts, steps, warmup, stream, flush=None):
+    """W untimed fits then K fits between CUDA events on the engine's stream; returns
+    (device ms, EM iterations, kernel launches, last Fit)."""
+    for _ in range(warmup):
+        eng.fit(*theta0, **opts)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    fits = []
+    for s in range(steps):
+        if flush is not None:
+            flush.fill_(s & 0xff)
+        ev[s][0].record(stream)
+        fits.append(eng.fit(*theta0, **opts))
+        ev[s][1].record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    return ms, sum(f.iters for f in fits), sum(f.kernel_launches for f in fits), fits[-1]
+
+
+def small_workload_line(torch, capi, synth, synth_gpu, dev, local, name, steps=10, warmup=3):
+    """value + e2e of one of the L2-sized BASELINE configs (C1, C2, C3) on one GPU."""
+    n, d, beta, graph = WORKLOADS[name]
+    xdev, _ = synth_gpu.make_packed_on_device(n, d, seed=42, device=dev)
+    xh = xdev.cpu().numpy()
+    if beta != 0 and graph != "none":
+        row_ptr, col, wgt = synth_gpu.make_graph(n, xh, seed=42, kind=graph)
+    else:
+        row_ptr = col = wgt = None
+    theta0 = synth.default_theta(K, d)
+    opts = dict(k=K, algo="ncem", update="seq", beta=beta, conv="clas", conv_thr=1e-8, it_max=100,
+                prop="pk", disp="sk_", sweep_impl="auto")
+    stream = torch.cuda.current_stream()
+    eng = capi.Engine(local)
+    eng.set_stream(stream.cuda_stream)
+    eng.load_shard_device(xdev.data_ptr(), n, 0, n, d, xdev.shape[1], row_ptr, col, wgt)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    ms, iters, launches, f = timed_fits(torch, eng, theta0, opts, steps, warmup, stream, flush)
+    lab = eng.labels()
+    xhu = xh.view(np.uint32)
+    eng.load_shard(xhu, n, 0, d, row_ptr, col, wgt); eng.fit(*theta0, **opts)      # first-touch pass
+    lab_host = np.empty(n, dtype=np.int32)
+    torch.cuda.synchronize()
+    t0 = time.time(); e_iters = 0
+    for _ in range(3):
+        eng.load_shard(xhu, n, 0, d, row_ptr, col, wgt)
+        fe = eng.fit(*theta0, **opts)
+        eng.labels(0, n, out=lab_host)
+        e_iters += fe.iters
+    e_wall = time.time() - t0
+    eng.close()
+    del flush, xdev
+    wb, tk = 4 * ((d + 31) // 32), 4 * K
+    nnz = 0 if col is None else int(col.shape[0])
+    b_iter = 2 * n * wb + 5 * n * tk + 8 * nnz + 4 * (n + 1) + 2 * 4 * K * d
+    peak, _ = peaks()
+    return {"workload": workload_name(name), "value": n * iters / (ms * 1e-3), "unit": "family-iterations/s",
+            "ms_per_fit": ms / steps, "em_iterations_per_fit": f.iters, "kernel_launches_per_fit": launches / steps,
+            "persistent_kernel": f.pk, "steps": steps, "warmup": warmup,
+            "iteration_frac_of_hbm_roofline": b_iter * iters / (ms * 1e-3) / 1e9 / peak,
+            "e2e": {"value": n * e_iters / e_wall, "unit": "family-iterations/s", "ms_per_step": e_wall * 1e3 / 3,
+                    "labels_equal_resident_fit": bool(np.array_equal(lab_host, lab))},
+            "l2": "X fits the L2; 512 MB flush between timed fits"}
+
 # ----------------------------------------------------------------------------- our arm
 def build_global_graph(torch, dist, dev, rank, world, n_loc, xh, seed, kind):
     """Weak-scaling pangenome of world x n_loc families: every rank's shard carries its own
@@ -554,6 +623,8 @@ def main_ours(args):
         if flush is not None:
             flush.fill_(s & 0xff)
         fits.append(one_fit(True))
+    pk_prof = eng.persist_profile() if (fits and fits[-1].pk and fits[-1].pk.get("launches")) else None
+    pk_trace = eng.persist_trace().tolist() if pk_prof else None
     barrier()
 
     # ---- e2e through the C ABI with host buffers (pinned X), H2D + graph upload/validation +
@@ -594,6 +665,104 @@ def main_ours(args):
                  "labels_repeatable_across_fits": bool(np.array_equal(lab_warm, lab_resident)),
                  "class_sizes": np.bincount(lab_resident, minlength=K).tolist(),
                  "class_sizes_sum_to_n": bool(np.bincount(lab_resident, minlength=K).sum() == n)}
+    # ---- extra lines of the default single-GPU run: the exact shortcuts switched off,
+    #      a pangenome whose shell centre keeps moving, and the three L2-sized BASELINE configs
+    extras = {}
+    if world == 1 and not args.rows and not args.no_extras:
+        b_iter_x = 2 * n * wb + 5 * n * tk + 8 * nnz + 4 * (n_glob + 1) + 2 * 4 * K * d
+        peak_x, _ = peaks()
+        os.environ["NEM_B200_NO_SHORTCUTS"] = "1"
+        ms_ns, it_ns, ln_ns, f_ns = timed_fits(torch, eng, theta0, opts, 5, 2, stream, flush)
+        del os.environ["NEM_B200_NO_SHORTCUTS"]
+        same_ns = bool(np.array_equal(eng.labels(), lab_resident))
+        extras["value_no_shortcuts"] = {
+            "value": n * it_ns / (ms_ns * 1e-3), "unit": "family-iterations/s", "ms_per_fit": ms_ns / 5,
+            "em_iterations_per_fit": f_ns.iters, "x_passes_per_fit": f_ns.pk.get("x_passes", 0) if f_ns.pk else None,
+            "xt_recounts_per_fit": f_ns.pk.get("recounts", 0) if f_ns.pk else None,
+            "site_evaluations_saved_per_fit": f_ns.n_kept, "labels_equal_default_fit": same_ns,
+            "iteration_frac_of_hbm_roofline": b_iter_x * it_ns / (ms_ns * 1e-3) / 1e9 / peak_x,
+            "what": "NEM_B200_NO_SHORTCUTS=1: every EM iteration reads X (Hamming counts recomputed), recounts "
+                    "S = X^T T through the transposed bits and evaluates every site (margin cache off); same "
+                    "pangenome, same labels; the fraction is (iterations x the per-iteration algorithmic bytes of "
+                    "SURVEY 8d) / time / measured HBM peak"}
+        if args.workload == "c4":
+            xmv, _ = synth_gpu.make_packed_on_device(n, d, seed=43, device=dev, shell="moving")
+            xmh = xmv.cpu().numpy()
+            if beta != 0 and graph != "none":
+                rp2, c2, w2 = synth_gpu.make_graph(n, xmh, seed=43, kind=graph)
+            else:
+                rp2 = c2 = w2 = None
+            em = capi.Engine(local)
+            em.set_stream(stream.cuda_stream)
+            em.load_shard_device(xmv.data_ptr(), n, 0, n, d, xmv.shape[1], rp2, c2, w2)
+            ms_mv, it_mv, ln_mv, f_mv = timed_fits(torch, em, theta0, opts, 5, 2, stream, None)
+            nnz2 = 0 if c2 is None else int(c2.shape[0])
+            b_iter_m = 2 * n * wb + 5 * n * tk + 8 * nnz2 + 4 * (n + 1) + 2 * 4 * K * d
+            extras["moving_centres"] = {
+                "value": n * it_mv / (ms_mv * 1e-3), "unit": "family-iterations/s", "ms_per_fit": ms_mv / 5,
+                "em_iterations_per_fit": f_mv.iters, "converged": bool(f_mv.converged),
+                "x_passes_per_fit": f_mv.pk.get("x_passes", 0) if f_mv.pk else None,
+                "site_evaluations_saved_per_fit": f_mv.n_kept,
+                "iteration_frac_of_hbm_roofline": b_iter_m * it_mv / (ms_mv * 1e-3) / 1e9 / peak_x,
+                "what": "default engine (all shortcuts on) on a pangenome generated so that they pay least: every "
+                        "shell family has presence probability 1/2, the shell centre's majority votes sit on the "
+                        "boundary and flip from iteration to iteration (synth_gpu shell='moving', seed 43)"}
+            em.close()
+            del xmv
+            extras["other_workloads"] = {w: small_workload_line(torch, capi, synth, synth_gpu, dev, local, w)
+                                         for w in ("c1", "c2", "c3")}
+
+    # ---- N > 1: BASELINE config 4 as written -- ONE pangenome of `n` families in total, row-sharded
+    #      over the N GPUs (strong scaling), checked on rank 0 against the same fit on one GPU
+    strong = None
+    if mode == "sharded" and world > 1 and not args.no_extras:
+        xfull, _ = synth_gpu.make_packed_on_device(n, d, seed=4242, device=dev)       # same on every rank
+        xfh = xfull.cpu().numpy()
+        if beta != 0 and graph != "none":
+            rps, cs, ws = synth_gpu.make_graph(n, xfh, seed=4242, kind=graph)
+        else:
+            rps = cs = ws = None
+        ps = sharded.plan(n, world, rank)
+        es, comm_s = sharded.make_engine(dist, local)
+        es.set_stream(stream.cuda_stream)
+        xs = xfull[ps.row0:ps.row0 + ps.n_loc].contiguous()
+        es.load_shard_device(xs.data_ptr(), n, ps.row0, ps.n_loc, d, xfull.shape[1], rps, cs, ws)
+        for _ in range(max(2, args.warmup)):
+            es.fit(*theta0, **opts)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        s_it = 0
+        for q in range(args.steps):
+            evs[q][0].record(stream)
+            fs = es.fit(*theta0, **opts)
+            evs[q][1].record(stream)
+            s_it += fs.iters
+        barrier()
+        s_ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+        lab_s = es.labels()
+        t_s = torch.tensor([s_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        es.close()
+        capi.comm_destroy(comm_s)
+        if rank == 0:
+            one = capi.Engine(local)
+            one.set_stream(stream.cuda_stream)
+            one.load_shard_device(xfull.data_ptr(), n, 0, n, d, xfull.shape[1], rps, cs, ws)
+            ms1, it1, _, f1 = timed_fits(torch, one, theta0, opts, min(args.steps, 5), 2, stream, None)
+            lab1 = one.labels()
+            one.close()
+            strong = {"families_total": n, "families_per_gpu": ps.shard_len, "value": n * s_it / (float(t_s[0]) * 1e-3),
+                      "unit": "family-iterations/s", "ms_per_step": float(t_s[0]) / args.steps,
+                      "em_iterations_per_fit": fs.iters, "cut_edges": sharded.cut_edges(rps, cs, world) if rps is not None else 0,
+                      "single_gpu_ms_per_step": ms1 / min(args.steps, 5),
+                      "single_gpu_value": n * it1 / (ms1 * 1e-3),
+                      "identical_to_single_gpu_fit": bool(fs.iters == f1.iters and np.array_equal(lab_s, lab1)
+                                                          and np.array_equal(fs.center, f1.center)
+                                                          and np.array_equal(fs.disp, f1.disp)),
+                      "what": "BASELINE config 4 as written: ONE 1M-family x 5000-genome pangenome (seed 4242) split "
+                              "into contiguous row ranges over the GPUs; rank 0 also fits the whole pangenome on its "
+                              "own GPU and compares labels, theta and iteration count (real NCCL run)"}
+        del xfull
     depth = eng.dims()["depth"] if mode != "sharded" else 0      # builds the level schedule: untimed
     h2d = x_bytes + (0 if col is None else (n_glob + 1) * 4 + nnz * 8) + (K + 2 * K * d) * 4
     d2h = plan.n_loc + (K + 2 * K * d) * 4 + 256
@@ -641,7 +810,9 @@ def main_ours(args):
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 popcount + f64 log-domain posteriors",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "families": n_glob,
+            "config": {"workload": workload_name(args.workload) if n_glob == n else
+                       workload_name(args.workload).replace("%d families" % n, "%d families (%d per GPU, weak scaling)" % (n_glob, n)),
+                       "families": n_glob,
                        "families_per_gpu": n, "genomes": d, "K": K,
                        "beta": beta, "algo": "ncem", "update": "seq", "nnz": nnz,
                        "sweep_dag_depth": depth,
@@ -690,6 +861,29 @@ def main_ours(args):
                                        "achieved": b_iter / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else 0.0,
                                        "note": "whole fit time / EM iterations (includes init sweeps, host syncs)"}},
         }
+        line["persistent_kernel"] = {"launches_per_fit": f.pk.get("launches"), "device_barriers_per_fit": f.pk.get("barriers"),
+                                     "x_passes_inside": f.pk.get("x_passes"), "what": "csrc/nem_persist.cuh: one cooperative "
+                                     "launch runs the EM loop; a problem larger than the L2 leaves it for the TMA "
+                                     "density pass and the X^T recount"} if f.pk else None
+        if pk_prof:
+            sw_us = pk_prof["margin_test"] + pk_prof["eval_list"] + pk_prof["eval_dense"] + pk_prof["fixup"]
+            n_sw = f.iters + 2
+            line["roofline"]["sweep_avg_ms"] = sw_us / 1e3 / n_sw
+            line["roofline"]["sweep"].update({"avg_ms": sw_us / 1e3 / n_sw,
+                                              "achieved": sw_bytes / (sw_us / n_sw * 1e-6) / 1e9,
+                                              "frac": sw_bytes / (sw_us / n_sw * 1e-6) / 1e9 / peak,
+                                              "what": "phases of the persistent kernel that make up a sweep (margin test + "
+                                                      "evaluation + fix-up rounds, barrier waits included), averaged over the "
+                                                      "sweeps of a fit, against ITS algorithmic bytes 3*N*T + 8*nnz + 4*N"})
+            line["persistent_kernel"]["phase_us_per_fit"] = {k: round(v, 1) for k, v in pk_prof.items()}
+            line["persistent_kernel"]["per_iteration_us"] = {
+                "columns": ["scan", "delta_or_recount", "closed_forms", "margin_test", "evaluation", "fixup", "sites_evaluated", "fixup_rounds"],
+                "rows_last_launch": [[round(v, 1) for v in r] for r in pk_trace if sum(r[:6]) > 0]}
+        line.update(extras)
+        if strong is not None:
+            line["strong_scaling"] = strong
+            line["scaling_note"] = ("`value`/`scaling` = weak (%d families per GPU, %d in total); strong_scaling = "
+                                    "BASELINE config 4 as written (%d families in total)" % (n, n_glob, n))
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if props is not None:
@@ -713,6 +907,8 @@ def main():
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1: one row-sharded pangenome of N x families (default) or N independent replicas")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip value_no_shortcuts / moving_centres / other_workloads / strong_scaling")
     ap.add_argument("--runs", type=int, default=0, help="c5: number of independent fits (default 1024)")
     ap.add_argument("--workers", type=int, default=8, help="c5: worker streams per GPU")
     args = ap.parse_args()

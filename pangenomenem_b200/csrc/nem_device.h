@@ -370,6 +370,7 @@ typedef struct {
     nemk_counters *cnt2;      /* [2] alternating per-sweep counter blocks, zero at entry */
     double *crit_partials;    /* [grid][4] per-CTA partial sums of the final criteria */
     int32_t want_crit, spatial;   /* evaluate the final criteria inside; the problem has a graph */
+    int32_t no_shortcuts, pad2;   /* worst case: X pass and full X^T recount EVERY iteration (margin cache off too) */
     unsigned *bar;            /* [2] device-wide barrier state (count, generation) */
     nemk_persist_out *out;    /* mapped pinned host memory */
 } nemk_persist_args;

@@ -681,6 +681,10 @@ static void read_env_knobs(nemb_handle *h)
     h->no_spec = env_flag("NEM_B200_NO_SPEC");
     h->full_mstep = env_flag("NEM_B200_FULL_MSTEP");
     h->full_exchange = env_flag("NEM_B200_FULL_EXCHANGE");
+    /* worst case of the exact shortcuts (bench.py value_no_shortcuts): every iteration reads X (the
+     * cached Hamming counts are declared void), recounts S through X^T and evaluates every site */
+    h->no_shortcuts = env_flag("NEM_B200_NO_SHORTCUTS");
+    if (h->no_shortcuts) { h->no_margins = 1; h->full_mstep = 1; h->no_popcache = 1; }
     e = getenv("NEM_B200_MEDIUM_LIST");
     h->medium_list = e && *e ? atoi(e) : 32768;
     e = getenv("NEM_B200_PK_GRID");
@@ -700,7 +704,7 @@ static nemk_lpsrc lpsrc(const nemb_handle *h)
  * counts stay valid while the class bit masks do not move (k_theta_tables detects that) */
 static int run_tables(nemb_handle *h, int k, int next_uniform)
 {
-    int force = !(h->ham_valid && next_uniform);
+    int force = !(h->ham_valid && next_uniform) || h->no_shortcuts;
     h->tables_forced = force;
     nemk_theta_tables(h->stream, k, h->d, h->wpr, h->d_prop, h->d_center, h->d_disp, h->d_coef,
                       h->d_mxor, h->d_mval, h->d_f0, h->d_f1, h->d_delta, force);
@@ -1044,8 +1048,8 @@ static int run_mstep(nemb_handle *h, const nemb_options *o, int next_uniform)
         nemk_mstep_finalize_tables(h->stream, k, h->n_glob, h->d, h->wpr, o->prop, o->disp, stat_glob,
                                    stat_glob + kd, NULL, NULL, h->d_prop, h->d_center, h->d_disp,
                                    h->d_coef, h->d_mxor, h->d_mval, h->d_f0, h->d_f1, h->d_delta,
-                                   !(h->ham_valid && next_uniform));
-        h->tables_forced = !(h->ham_valid && next_uniform);
+                                   !(h->ham_valid && next_uniform) || h->no_shortcuts);
+        h->tables_forced = !(h->ham_valid && next_uniform) || h->no_shortcuts;
         h->launches++;
     } else {
         if ((rc = ensure_nem_scratch(h, k)) != NEMB_OK) return rc;
@@ -1336,6 +1340,7 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     a.hub_list = h->d_pk_hub; a.scratch = h->d_pk_scratch; a.cnt2 = h->d_pk_cnt2; a.bar = h->d_pk_bar;
     a.out = h->d_pk_out;
     a.crit_partials = h->d_pk_crit; a.want_crit = 1; a.spatial = h->spatial;
+    a.no_shortcuts = h->no_shortcuts;
     h->pk_have_crit = 0;
     /* host state of a fresh fit (the kernel's prep phase writes the device side) */
     h->cur = 0; h->state_labels = 1;

@@ -119,6 +119,7 @@ struct nemb_handle {
      * getenv() per sweep */
     int no_persist, keep_logpf, no_margins, no_popcache, no_spec, full_mstep, full_exchange;
     int medium_list, pk_grid_env;
+    int no_shortcuts;      /* NEM_B200_NO_SHORTCUTS: X pass + full recount every iteration, margin cache off */
     size_t pk_xlimit;      /* X up to this many bytes: the X / X^T passes run inside the persistent kernel */
     /* fit bookkeeping */
     int64_t launches, fixup_rounds, exchanges;

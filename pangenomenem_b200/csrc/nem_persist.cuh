@@ -1104,7 +1104,7 @@ k_em_persist(const nemk_persist_args a) {
             prof.trace = (gtid == 0 && it - a.iter0 < 12) ? a.out->trace[it - a.iter0] : nullptr;
             // statistics of the labels lab[cur]: already updated by the scan (delta_mode 2), updated
             // from the scan's list (1), or recounted
-            const bool incremental = stats_valid && last_changed >= 0 && last_changed <= n / 8;
+            const bool incremental = !a.no_shortcuts && stats_valid && last_changed >= 0 && last_changed <= n / 8;
             if (stats_valid && delta_mode == 2) {
                 // the sweep tracked its label moves: nothing left to do
             } else if (incremental && delta_mode == 1) {
@@ -1135,6 +1135,7 @@ k_em_persist(const nemk_persist_args a) {
             empty = vc->empty_class;
             mu_changed = 0;
             for (int k = 0; k < K; k++) mu_changed |= vc->mu_moved_k[k];
+            mu_changed |= a.no_shortcuts;
             if (gtid == 0) a.coef->mu_changed = mu_changed;     // for the kernels that run outside
             if (empty) {   // nem_alg.c:1831-1838: the E-step is not run, the loop ends
                 it++;
@@ -1192,7 +1193,7 @@ k_em_persist(const nemk_persist_args a) {
             } else {
                 // ---- the rows this sweep moved: count (convergence test), flags of the last
                 // evaluations, and the list the next M-step updates its statistics from
-                const int want = (it + 1 >= a.it_max || !stats_valid) ? 0 : 1;
+                const int want = (it + 1 >= a.it_max || !stats_valid || a.no_shortcuts) ? 0 : 1;
                 pk_scan<KT>(a, a.lab[cur], a.lab[cur ^ 1], want, a.wlist[1], &a.wl_cnt[4]);
                 PK_SYNC();
                 PK_MARK(prof, 1);

@@ -12,14 +12,21 @@ import torch
 from . import synth
 
 
-def make_packed_on_device(n: int, d: int, seed: int, device: torch.device):
-    """Returns (x_packed int32 [n, wpr] on `device`, latent int8 numpy [n])."""
+def make_packed_on_device(n: int, d: int, seed: int, device: torch.device, shell: str = "default"):
+    """Returns (x_packed int32 [n, wpr] on `device`, latent int8 numpy [n]).
+
+    shell="moving": every shell family has presence probability exactly 1/2, so the shell class's
+    per-genome majority votes sit on the boundary and its centre keeps flipping genomes from one EM
+    iteration to the next (the worst case of the cached-Hamming-count shortcut: an X pass per
+    iteration)."""
     rng = np.random.default_rng(seed)
     latent = synth.latent_classes(n, rng)
     q = np.empty(n, dtype=np.float32)
     q[latent == 0] = 0.97
     sh = latent == 1
     q[sh] = rng.uniform(0.2, 0.8, size=int(sh.sum())).astype(np.float32)
+    if shell == "moving":
+        q[sh] = 0.5
     q[latent == 2] = 0.03
     w = (d + 31) // 32
     wpr = (w + 3) // 4 * 4
