@@ -70,6 +70,13 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
                 const char *proportion, const char *dispersion, const int init_mode,
                 const nem_b200_extra *extra);
 
+/* Forked callers (ppanggolin.py:1039, command_line.py:262-281, 618): a process that was forked
+ * after CUDA had been initialised cannot use CUDA; nem() then forwards the call to a helper process
+ * (`nem_exe --serve`, started once per calling process).  nem_b200_helper_pid() = pid of the live
+ * helper of this process (0: none); nem_b200_serve() is the helper's loop. */
+int nem_b200_helper_pid(void);
+int nem_b200_serve(int fd_in, int fd_out);
+
 /* ---------------------------------------------------------------------------------------
  * 3. in-memory API
  * ------------------------------------------------------------------------------------- */

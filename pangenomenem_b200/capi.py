@@ -584,6 +584,12 @@ def nem(Fname, nk, algo, beta, convergence, convergence_th, format, it_max, dolo
                               b(model_family), b(proportion), b(dispersion), int(init_mode))
 
 
+def helper_pid() -> int:
+    """pid of the helper process that serves this process's nem() calls (0: none) -- a process
+    forked after CUDA was initialised cannot use CUDA itself (csrc/nem_api.c "forked callers")."""
+    return int(load_library().nem_b200_helper_pid())
+
+
 def nem_ex(Fname, nk, algo, beta, convergence, convergence_th, format, it_max, dolog, model_family,
            proportion, dispersion, init_mode, update="seq", sweep_impl="auto", device=-1,
            n_random_inits=0, seed=0, beta_mode="fix", psgrad=(0, 0.0, 0.0),

@@ -16,6 +16,7 @@
  *   - norm/lapl families, gem, init modes 0/3/4 and image data are off the PPanGGOLiN path
  *      and return EXIT_E_ARGS with a message.
  */
+#define _GNU_SOURCE   /* dladdr */
 #include "nem_b200.h"
 #include "nem_io.h"
 
@@ -26,6 +27,12 @@
 #include <string.h>
 #include <time.h>
 #include <unistd.h>
+#include <dlfcn.h>
+#include <errno.h>
+#include <signal.h>
+#include <spawn.h>
+#include <sys/types.h>
+#include <sys/wait.h>
 
 enum { EXIT_OK_ = 0, EXIT_W_RESULT_ = 1, EXIT_E_ARGS_ = 2, EXIT_E_FILE_ = 3, EXIT_E_MEMORY_ = 4,
        EXIT_E_SYSTEM_ = 5, EXIT_E_BUG_ = 6 };   /* ExitET, NEM/lib_io.h:22-34 */
@@ -170,6 +177,170 @@ static void release_engine(nemb_handle *h, int cached)
     pthread_mutex_unlock(&g_cache_mu);
 }
 
+
+/* ------------------------------------------------------------------ forked callers
+ * PPanGGOLiN calls nem() in the parent (ppanggolin.py:1125, 1207) and then again from forked pool
+ * workers (ppanggolin.py:1039; command_line.py:262-281, 618).  A CUDA context does not survive
+ * fork(), and the caller ignores nem()'s return value, so a failing child would silently turn every
+ * family into "undefined".  A process that inherited an initialised CUDA state therefore never
+ * touches CUDA: it starts ONE helper process (`nem_exe --serve`, next to this library; posix_spawn,
+ * i.e. fork + immediate exec) and forwards its nem() calls to it over a pipe pair.  The helper owns
+ * its own context and engine cache, so a pool worker pays the context creation once.
+ * NEM_B200_FORCE_HELPER=1 routes every call that way (tests). */
+extern char **environ;
+int nemb_i_cuda_owner_pid(void);
+static pthread_mutex_t g_helper_mu = PTHREAD_MUTEX_INITIALIZER;
+static pid_t g_helper_pid, g_helper_owner;
+static int g_helper_wr = -1, g_helper_rd = -1;
+
+#define NEM_HELPER_MAGIC 0x4e454d42
+typedef struct {
+    int32_t magic, nk, it_max, dolog, init_mode, has_extra;
+    float beta, thr;
+    int32_t len[7];          /* Fname algo convergence format family proportion dispersion */
+    nem_b200_extra extra;
+} helper_req;
+
+static int write_all(int fd, const void *p, size_t n)
+{
+    const char *c = p;
+    while (n) {
+        ssize_t w = write(fd, c, n);
+        if (w < 0) { if (errno == EINTR) continue; return -1; }
+        c += w; n -= (size_t)w;
+    }
+    return 0;
+}
+static int read_all(int fd, void *p, size_t n)
+{
+    char *c = p;
+    while (n) {
+        ssize_t r = read(fd, c, n);
+        if (r < 0) { if (errno == EINTR) continue; return -1; }
+        if (r == 0) return -1;
+        c += r; n -= (size_t)r;
+    }
+    return 0;
+}
+
+static int must_use_helper(void)
+{
+    const char *f = getenv("NEM_B200_FORCE_HELPER");
+    if (f && *f && getenv("NEM_B200_IS_HELPER") == NULL) return 1;
+    int owner = nemb_i_cuda_owner_pid();
+    return owner != 0 && owner != (int)getpid();
+}
+
+int nem_b200_helper_pid(void) { return g_helper_owner == getpid() ? (int)g_helper_pid : 0; }
+
+static void helper_close(void)
+{
+    if (g_helper_wr >= 0) close(g_helper_wr);
+    if (g_helper_rd >= 0) close(g_helper_rd);
+    g_helper_wr = g_helper_rd = -1;
+    if (g_helper_pid > 0 && g_helper_owner == getpid()) { int st; waitpid(g_helper_pid, &st, 0); }
+    g_helper_pid = 0;
+}
+static void helper_atexit(void) { if (g_helper_owner == getpid()) helper_close(); }
+
+static int helper_start(void)
+{
+    if (g_helper_pid > 0 && g_helper_owner == getpid()) return 0;
+    if (g_helper_owner != getpid()) {            /* descriptors inherited from the parent's helper */
+        if (g_helper_wr >= 0) close(g_helper_wr);
+        if (g_helper_rd >= 0) close(g_helper_rd);
+        g_helper_wr = g_helper_rd = -1; g_helper_pid = 0;
+    }
+    char path[4096];
+    Dl_info info;
+    const char *exe = getenv("NEM_B200_HELPER");
+    if (!exe || !*exe) {
+        if (!dladdr((void *)&helper_start, &info) || !info.dli_fname) return -1;
+        snprintf(path, sizeof path, "%s", info.dli_fname);
+        char *slash = strrchr(path, '/');
+        if (!slash) return -1;
+        snprintf(slash + 1, sizeof path - (size_t)(slash + 1 - path), "nem_exe");
+        exe = path;
+    }
+    int to[2], from[2];
+    if (pipe(to) || pipe(from)) return -1;
+    posix_spawn_file_actions_t fa;
+    posix_spawn_file_actions_init(&fa);
+    posix_spawn_file_actions_adddup2(&fa, to[0], 3);
+    posix_spawn_file_actions_adddup2(&fa, from[1], 4);
+    posix_spawn_file_actions_addclose(&fa, to[1]);
+    posix_spawn_file_actions_addclose(&fa, from[0]);
+    char *argv[] = {(char *)exe, (char *)"--serve", NULL};
+    /* the helper must use CUDA itself whatever this process was told */
+    size_t ne = 0;
+    while (environ[ne]) ne++;
+    char **env = malloc(sizeof(char *) * (ne + 2));
+    if (!env) return -1;
+    memcpy(env, environ, sizeof(char *) * ne);
+    env[ne] = (char *)"NEM_B200_IS_HELPER=1"; env[ne + 1] = NULL;
+    pid_t pid = 0;
+    int rc = posix_spawn(&pid, exe, &fa, NULL, argv, env);
+    free(env);
+    posix_spawn_file_actions_destroy(&fa);
+    close(to[0]); close(from[1]);
+    if (rc != 0) { close(to[1]); close(from[0]); fprintf(stderr, "nem_b200: cannot start the helper %s: %s\n", exe, strerror(rc)); return -1; }
+    static int registered;
+    if (!registered) { atexit(helper_atexit); registered = 1; }
+    signal(SIGPIPE, SIG_IGN);
+    g_helper_pid = pid; g_helper_owner = getpid(); g_helper_wr = to[1]; g_helper_rd = from[0];
+    return 0;
+}
+
+static int helper_call(const char *Fname, int nk, const char *algo, float beta, const char *conv, float thr,
+                       const char *format, int it_max, int dolog, const char *family, const char *prop,
+                       const char *disp, int init_mode, const nem_b200_extra *extra)
+{
+    const char *str[7] = {Fname, algo, conv, format, family, prop, disp};
+    helper_req rq;
+    memset(&rq, 0, sizeof rq);
+    rq.magic = NEM_HELPER_MAGIC; rq.nk = nk; rq.it_max = it_max; rq.dolog = dolog; rq.init_mode = init_mode;
+    rq.beta = beta; rq.thr = thr; rq.has_extra = extra != NULL;
+    if (extra) rq.extra = *extra;
+    for (int i = 0; i < 7; i++) rq.len[i] = str[i] ? (int32_t)strlen(str[i]) : -1;
+    int32_t rc = EXIT_E_SYSTEM_;
+    pthread_mutex_lock(&g_helper_mu);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (helper_start() != 0) break;
+        int bad = write_all(g_helper_wr, &rq, sizeof rq);
+        for (int i = 0; i < 7 && !bad; i++)
+            if (rq.len[i] > 0) bad = write_all(g_helper_wr, str[i], (size_t)rq.len[i]);
+        if (!bad) bad = read_all(g_helper_rd, &rc, sizeof rc);
+        if (!bad) break;
+        rc = EXIT_E_SYSTEM_;
+        helper_close();                 /* the helper died: one fresh start */
+    }
+    pthread_mutex_unlock(&g_helper_mu);
+    return rc;
+}
+
+/* `nem_exe --serve` (nem_cli.c): requests on descriptor 3, return codes on descriptor 4 */
+int nem_b200_serve(int fd_in, int fd_out)
+{
+    for (;;) {
+        helper_req rq;
+        if (read_all(fd_in, &rq, sizeof rq) != 0) return 0;        /* the caller is gone */
+        if (rq.magic != NEM_HELPER_MAGIC) return 2;
+        char *str[7];
+        for (int i = 0; i < 7; i++) {
+            str[i] = NULL;
+            if (rq.len[i] >= 0) {
+                if (rq.len[i] > (1 << 20)) return 2;
+                str[i] = calloc((size_t)rq.len[i] + 1, 1);
+                if (!str[i] || (rq.len[i] > 0 && read_all(fd_in, str[i], (size_t)rq.len[i]) != 0)) return 2;
+            }
+        }
+        int32_t rc = nem_b200_ex(str[0], rq.nk, str[1], rq.beta, str[2], rq.thr, str[3], rq.it_max, rq.dolog,
+                                 str[4], str[5], str[6], rq.init_mode, rq.has_extra ? &rq.extra : NULL);
+        for (int i = 0; i < 7; i++) free(str[i]);
+        if (write_all(fd_out, &rc, sizeof rc) != 0) return 0;
+    }
+}
+
 int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float beta,
                 const char *convergence, const float convergence_th, const char *format,
                 const int it_max, const int dolog, const char *model_family,
@@ -197,6 +368,9 @@ int nem_b200_ex(const char *Fname, const int nk, const char *algo, const float b
     }
 
     if (!Fname) return EXIT_E_ARGS_;
+    if (must_use_helper())
+        return helper_call(Fname, nk, algo, beta, convergence, convergence_th, format, it_max, dolog,
+                           model_family, proportion, dispersion, init_mode, extra);
     FILE *ferr = stderr;
     int own_err = 0;
     char path[4200];

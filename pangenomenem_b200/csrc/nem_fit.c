@@ -24,6 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 /* ------------------------------------------------------------------ errors */
 int nemb_i_fail(nemb_handle *h, int code, const char *fmt, ...)
@@ -58,10 +59,23 @@ int nemb_i_reserve(nemb_handle *h, dbuf *b, size_t bytes) { return reserve(h, b,
 static void release(dbuf *b) { if (b->p) cudaFree(b->p); b->p = NULL; b->cap = 0; }
 
 /* ------------------------------------------------------------------ lifetime */
+/* pid of the process in which THIS address space first touched CUDA (0: never).  A forked child
+ * inherits it, and with it a CUDA state it cannot use (CUDA does not survive fork): nem() then
+ * serves the child through a helper process (nem_api.c). */
+static pid_t g_cuda_pid;
+int nemb_i_cuda_owner_pid(void) { return (int)g_cuda_pid; }
+
 int nemb_create(nemb_handle **out, int device)
 {
     if (!out) return NEMB_E_ARG;
     *out = NULL;
+    if (g_cuda_pid && g_cuda_pid != getpid()) {
+        fprintf(stderr, "nem_b200: this process was forked from one that had already initialised CUDA; "
+                        "a CUDA context does not survive fork() -- use nem() (it serves forked callers "
+                        "through a helper process), or fork before the first engine call\n");
+        return NEMB_E_CUDA;
+    }
+    if (!g_cuda_pid) g_cuda_pid = getpid();
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) {
@@ -1485,7 +1499,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
         res->n_ties = h->h_status->cnt.ties;
         oldcrit = h->h_status->crit_after[3];
         if (cb) {
-            for (int c = 0; c < k; c++) nk_host[c] = NAN;
+            for (int c = 0; c < k; c++) nk_host[c] = 0.0f;   /* NbObs_KD not estimated yet: calloc zeros */
             cb(user, 0, h->h_status->crit_before, h->h_status->crit_after, prop, center, disp, nk_host);
         }
     }
@@ -1552,7 +1566,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
         if (want_crit_each) oldcrit = h->h_status->crit_after[3];
         if (cb) {
             if (o->param_fixed) {
-                for (int c = 0; c < k; c++) nk_host[c] = NAN;
+                for (int c = 0; c < k; c++) nk_host[c] = 0.0f;   /* NbObs_KD not estimated yet: calloc zeros */
             } else if (o->algo == NEMB_ALGO_NCEM) {
                 int32_t ni[NEMB_MAX_K];
                 CKO(cudaMemcpy(ni, (h->world > 1 ? h->d_stat_int : h->d_stat_loc) + kd, sizeof(int32_t) * k, cudaMemcpyDeviceToHost));

@@ -103,8 +103,11 @@ def main() -> None:
                                             it_max=opt["it_max"], dolog=1, prop=opt["prop"],
                                             disp=opt["disp"])
                 assert rc == 0, rc
+                # .log of the reference's own nem(dolog=1) call: header + one row per EM iteration
+                # (nem_alg.c:1478-1498, 1883-1946, 1995-2052, 2620-2646); its first line carries the date
                 cli = dict(uf_text=np.frombuffer(open(base + ".uf", "rb").read(), dtype=np.uint8),
-                           mf_text=np.frombuffer(open(base + ".mf", "rb").read(), dtype=np.uint8))
+                           mf_text=np.frombuffer(open(base + ".mf", "rb").read(), dtype=np.uint8),
+                           log_text=np.frombuffer(open(base + ".log", "rb").read(), dtype=np.uint8))
             files = {ext: np.frombuffer(open(base + "." + ext, "rb").read(), dtype=np.uint8)
                      for ext in (("str", "dat", "nei", "m") if spatial else ("str", "dat", "m"))}
         assert ref["status"] == 0 and not ref["density_zero"], name

@@ -98,3 +98,62 @@ def test_cython_nem_module_drives_the_engine(tmp_path):
     finally:
         sys.path.pop(0)
         sys.modules.pop("nem", None)
+
+
+def _log_rows(text):
+    """(header lines, table header, {iteration: tokens}) of a NEM .log; the first line is dated."""
+    lines = text.splitlines()
+    rows, head, table_head = {}, [], None
+    for ln in lines[1:]:
+        tok = ln.split()
+        if tok and tok[0] == "It":
+            table_head = ln
+        elif tok and tok[0].lstrip("-").isdigit() and len(tok) > 8:
+            rows[int(tok[0])] = tok
+        else:
+            head.append(ln)
+    return head, table_head, rows
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if Golden(n).text("log")])
+def test_nem_log_matches_the_reference_table(tmp_path, name):
+    """PPanGGOLiN always passes dolog=True (ppanggolin.py:1822) and points its users at
+    nem_file.log: the per-iteration table -- U and M before / after the sweep, error, beta, p_k,
+    mu_kd, eps_kd, n_kd (nem_alg.c:1478-1498, 1883-1946, 1995-2052, 2620-2646) -- must be the
+    reference's: same lines, same header, same columns; criteria within the reference's own
+    float32 rounding (its M is -inf: float zi overflows)."""
+    from pangenomenem_b200 import capi
+    g = Golden(name)
+    base = str(tmp_path / "run" / "nem_file")
+    g.write_files(base)
+    rc = capi.nem(Fname=base.encode(), nk=3, algo=g.opt["algo"].encode(), beta=g.opt["beta"],
+                  convergence=b"clas", convergence_th=1e-8, format=b"fuzzy", it_max=g.opt["it_max"],
+                  dolog=True, model_family=b"bern", proportion=g.opt["prop"].encode(),
+                  dispersion=g.opt["disp"].encode(), init_mode=2)
+    assert rc == 0
+    ours, ref = open(base + ".log").read(), g.text("log")
+    assert len(ours.splitlines()) == len(ref.splitlines())
+    h_o, th_o, r_o = _log_rows(ours)
+    h_r, th_r, r_r = _log_rows(ref)
+    assert h_o == h_r                      # "Criteria are multiplied by", "Initializing parameters ..." and blanks
+    assert th_o == th_r                    # the column header, character for character
+    assert sorted(r_o) == sorted(r_r) == list(range(0, g.iters + 1))
+    k, d = 3, g.d
+    for it in r_r:
+        a, b = r_o[it], r_r[it]
+        assert len(a) == len(b) == 1 + 6 + 1 + k + 3 * k * d, (it, len(a), len(b))
+        for col in (1, 4):                 # U * mult, %5.0f
+            assert abs(float(a[col]) - float(b[col])) <= max(1.5, 2e-3 * abs(float(b[col]))), (it, col, a[col], b[col])
+        for col in (2, 5):                 # M * mult: finite here, -inf (float overflow) in the reference
+            assert b[col] in ("-inf", "inf", "nan", "-nan") or \
+                abs(float(a[col]) - float(b[col])) <= max(1.5, 2e-3 * abs(float(b[col])))
+        assert a[3] == b[3] and a[6] == b[6]          # error rate: nan (no reference labels)
+        assert a[7] == b[7]                           # beta
+        p_o, p_r = np.array(a[8:8 + k], float), np.array(b[8:8 + k], float)
+        assert np.abs(p_o - p_r).max() <= 1.1e-3
+        o = 8 + k
+        assert a[o:o + k * d] == b[o:o + k * d]                                   # centres
+        e_o, e_r = np.array(a[o + k * d:o + 2 * k * d], float), np.array(b[o + k * d:o + 2 * k * d], float)
+        assert np.abs(e_o - e_r).max() <= 1.1e-3
+        n_o, n_r = np.array(a[o + 2 * k * d:], float), np.array(b[o + 2 * k * d:], float)
+        assert np.abs(n_o - n_r).max() <= (0.0 if g.opt["algo"] == "ncem" else 0.2)
