@@ -157,3 +157,39 @@ def test_nem_log_matches_the_reference_table(tmp_path, name):
         assert np.abs(e_o - e_r).max() <= 1.1e-3
         n_o, n_r = np.array(a[o + 2 * k * d:], float), np.array(b[o + 2 * k * d:], float)
         assert np.abs(n_o - n_r).max() <= (0.0 if g.opt["algo"] == "ncem" else 0.2)
+
+
+@pytest.mark.parametrize("q", [2, 4])
+def test_nem_random_starts_through_the_files(tmp_path, q, monkeypatch):
+    """partition_shell's call (ppanggolin.py:1207, 1826): nem(init_mode=1) with Q != 3 classes, no
+    .m file -- RandNemAlgo's 50 random starts (nem_alg.c:1574-1742).  The file route must give the
+    partition, theta and criteria of the in-memory random-start fit with the same seed."""
+    from pangenomenem_b200 import capi, synth
+    pg = synth.make_pangenome(3000, 60, seed=23)
+    base = str(tmp_path / "shell" / "nem_file")
+    synth.write_nem_files(base, pg)
+    if os.path.exists(base + ".m"):
+        os.remove(base + ".m")                     # init_mode=1 must not need it
+    monkeypatch.setenv("NEM_B200_SEED", "17")
+    rc = capi.nem(Fname=base.encode(), nk=q, algo=b"ncem", beta=0.5, convergence=b"clas",
+                  convergence_th=1e-8, format=b"fuzzy", it_max=100, dolog=True, model_family=b"bern",
+                  proportion=b"pk", dispersion=b"sk_", init_mode=1)
+    assert rc == 0
+    uf = synth.read_uf(base + ".uf", q)
+    mf = synth.read_mf(base + ".mf", q, pg.d)
+    assert uf.shape == (pg.n, q) and np.array_equal(uf.sum(axis=1), np.ones(pg.n))
+    eng = capi.Engine(0)
+    eng.load_dense(pg.x, pg.row_ptr, pg.col, pg.wgt)
+    theta = (np.full(q, 1.0 / q, np.float32), np.zeros((q, pg.d), np.float32), np.ones((q, pg.d), np.float32))
+    fit = eng.fit(*theta, k=q, algo="ncem", update="seq", disp="sk_", prop="pk", beta=0.5, it_max=100,
+                  n_random_starts=50, seed=17)
+    assert fit.status == 0 and fit.n_success >= 1
+    assert np.array_equal(uf.argmax(axis=1), eng.labels())
+    assert np.array_equal(mf["mu"], fit.center)
+    assert np.allclose(mf["eps"], fit.disp, rtol=1e-5) and np.allclose(mf["p"], fit.prop, rtol=2e-3, atol=1e-3)
+    for key in "UDL":
+        assert abs(mf[key] - fit.crit[key]) <= 1e-5 * abs(fit.crit[key])
+    assert len(np.unique(eng.labels())) == q       # every class is used (else W_EMPTYCLASS)
+    txt = open(base + ".stderr").read()
+    assert "Random initial partitions (50 starts)" in txt
+    eng.close()
