@@ -95,6 +95,11 @@ int nemb_nccl_unique_id(uint8_t id_out[128])
     return NEMB_OK;
 }
 
+/* one process and one GPU per rank: kernels of different ranks may wait on each other (the
+ * persistent row-sharded EM kernel); the in-process test double runs its ranks on ONE device, where
+ * they may be serialised, and must never do that */
+int nemb_i_comm_is_nccl(const nemb_comm *c) { return c && c->allgather == nccl_allgather_cb; }
+
 int nemb_comm_create_nccl(nemb_comm **out, const uint8_t id[128], int rank, int world)
 {
     if (!out || !id || world < 1 || rank < 0 || rank >= world) return NEMB_E_ARG;

@@ -308,13 +308,19 @@ enum { NEMK_PK_ENTRY_INIT = 0,        /* tables of the theta in prop/center/disp
        NEMK_PK_ENTRY_MSTEP = 2,       /* start of an EM iteration */
        NEMK_PK_ENTRY_FINALIZE = 3,    /* statistics ready (host ran the full recount) */
        NEMK_PK_ENTRY_SWEEP = 4 };     /* densities of this iteration ready (host ran the X pass) */
-enum { NEMK_PK_EXIT_DONE = 0, NEMK_PK_EXIT_NEED_DENSITY = 1, NEMK_PK_EXIT_NEED_RECOUNT = 2 };
+enum { NEMK_PK_EXIT_DONE = 0, NEMK_PK_EXIT_NEED_DENSITY = 1, NEMK_PK_EXIT_NEED_RECOUNT = 2,
+       NEMK_PK_EXIT_PEER_TIMEOUT = 3 };
+
+#define NEMK_PK_MAX_WORLD 8
 
 typedef struct {
     int32_t exit_code, resume_entry;    /* NEED_*: run the pass, re-enter at resume_entry */
     int32_t iters, converged, empty_class;
     int32_t cur, stale_par, last_changed, stats_valid, cnt_par, delta_mode, flags_stale, mu_changed;
     int32_t n_allnul, n_ties;           /* of the last sweep */
+    uint32_t xepoch;                    /* cross-rank barrier epoch when the kernel was left */
+    int32_t decide_pending, chg_local;
+    int32_t xerror;                     /* a cross-rank barrier timed out (a peer died) */
     int32_t sweeps, x_passes, recounts, barriers;
     long long kept, fixup_rounds;       /* summed over the sweeps of this launch */
     /* nanoseconds CTA 0 spent in each phase, barrier waits included (globaltimer): 0 init (prep,
@@ -346,6 +352,7 @@ typedef struct {
     int32_t init_from_pop;    /* ENTRY_INIT: every class of theta0 has a constant centre */
     /* entry state */
     int32_t entry, iter0, cur, stale_par, stats_valid, last_changed, margins_on, cnt_par, delta_mode, flags_stale, mu_changed;
+    int32_t decide_pending, chg_local;   /* row shards: a sweep's convergence test waits for the ranks' sum */
     int32_t n_allnul, n_ties;   /* of the last sweep so far (carried over a re-entry) */
     unsigned long long seq;
     /* buffers (device) */
@@ -371,6 +378,19 @@ typedef struct {
     double *crit_partials;    /* [grid][4] per-CTA partial sums of the final criteria */
     int32_t want_crit, spatial;   /* evaluate the final criteria inside; the problem has a graph */
     int32_t no_shortcuts, pad2;   /* worst case: X pass and full X^T recount EVERY iteration (margin cache off too) */
+    /* ---- row shards (world > 1): this rank owns the families [row0, row0 + n) of n_glob.  Labels,
+     * Hamming counts, margins, flags, CSR and work lists are indexed by GLOBAL family id; x, xt, pop
+     * and `stat` (this rank's S and n) by local row.  Every rank maps every rank's exchange block
+     * (CUDA IPC, peer memory over NVLink): label moves and re-evaluation requests are stored
+     * straight into the peers' blocks by the kernel, and the ranks meet at cross-rank barriers
+     * (epoch flags in the blocks) -- one per M-step, one or two per sweep. */
+    int32_t world, rank, row0, shard_len, n_glob, xcap;
+    uint32_t xepoch, pad3;            /* cross-rank barrier epoch at entry */
+    char *peer[NEMK_PK_MAX_WORLD];    /* exchange block of every rank (own included) */
+    long long off_lab[2], off_stale[2], off_xflag, off_tot, off_incnt, off_inbox, off_stat, off_crit;
+    int32_t stat_len, pad4;           /* ints a rank publishes per M-step: S[K*D], n[K], changed, all-null, ties, pad */
+    int32_t *out_cnt;                 /* [world] local: requests queued for every rank in this super-round */
+    int32_t *stat_glob;               /* [K*D + K] statistics summed over the ranks in rank order */
     unsigned *bar;            /* [2] device-wide barrier state (count, generation) */
     nemk_persist_out *out;    /* mapped pinned host memory */
 } nemk_persist_args;

@@ -166,6 +166,8 @@ void nemb_destroy(nemb_handle *h)
     if (h->h_empty) cudaFreeHost(h->h_empty);
     if (h->ring) cudaFreeHost(h->ring);
     if (h->pk_out) cudaFreeHost(h->pk_out);
+    for (int p = 0; p < NEMK_PK_MAX_WORLD; p++) if (h->xpeer[p] && p != h->rank) cudaIpcCloseMemHandle(h->xpeer[p]);
+    if (h->b_xblk.p) cudaFree(h->b_xblk.p);
     if (h->h_lab_stage) cudaFreeHost(h->h_lab_stage);
     if (h->h_theta_stage) cudaFreeHost(h->h_theta_stage);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -689,6 +691,7 @@ static void read_env_knobs(nemb_handle *h)
 {
     const char *e;
     h->no_persist = env_flag("NEM_B200_NO_PERSIST");
+    h->no_persist_shard = env_flag("NEM_B200_NO_PERSIST_SHARD");
     h->keep_logpf = env_flag("NEM_B200_KEEP_LOGPF");
     h->no_margins = env_flag("NEM_B200_NO_MARGINS");
     h->no_popcache = env_flag("NEM_B200_NO_POPCACHE");
@@ -1241,16 +1244,100 @@ static int theta_d2h(nemb_handle *h, int k, float *prop, float *center, float *d
  * with the per-class dispersion models, one GPU, started from theta -- PPanGGOLiN's call
  * (ppanggolin.py:1814-1826) without the per-iteration log.  Everything else keeps the
  * launch-per-stage loop of em_core. */
+int nemb_i_comm_is_nccl(const nemb_comm *c);
+
 static int persist_eligible(nemb_handle *h, const nemb_options *o, int uniform0, int has_cb,
                             const float *t_init)
 {
-    if (h->world != 1 || t_init || has_cb || o->dolog || h->no_persist) return 0;
+    if (t_init || has_cb || o->dolog || h->no_persist) return 0;
+    if (h->world > 1) {
+        /* row shards: the ranks' kernels wait on each other through peer memory, so every rank must
+         * own a GPU (NCCL communicator = one process per GPU), the shards must start on 16-family
+         * boundaries (vector label accesses), and the sweep must be the sequential one */
+        if (h->no_persist_shard || h->world > NEMK_PK_MAX_WORLD || !nemb_i_comm_is_nccl(h->comm)) return 0;
+        if (h->shard_len % 16 || !h->spatial || o->update != NEMB_UPDATE_SEQ) return 0;
+    }
     if (o->algo != NEMB_ALGO_NCEM || o->param_fixed || o->conv == NEMB_CONV_CRIT) return 0;
     if (o->beta_mode == NEMB_BETA_PSGRAD && h->spatial) return 0;
     if (uniform0 < 1 || !(o->disp == NEMB_DISP_K_ || o->disp == NEMB_DISP___)) return 0;
     if (o->sweep_impl != NEMB_SWEEP_AUTO && o->sweep_impl != NEMB_SWEEP_SPEC) return 0;
     if (h->keep_logpf) return 0;
     return nemk_persist_max_grid(o->k) > 0;
+}
+
+/* Row shards: lay out this rank's exchange block and map every peer's (CUDA IPC).  Collective: all
+ * ranks call it with the same K and pangenome.  Returns NEMB_OK with h->xblk_ok = 0 when peer
+ * memory is not available on this box (the caller then keeps the launch-per-stage loop; the
+ * verdict is the same on every rank). */
+static int ensure_xblk(nemb_handle *h, int k)
+{
+    if (h->xblk_ok && h->xblk_k == k && h->xblk_lab_len == h->lab_len) return NEMB_OK;
+    const int W = h->world;
+    const size_t L = ((size_t)h->lab_len + 255) & ~(size_t)255;
+    h->xcap = 1 << 16;
+    h->xstat_len = (int)(((size_t)k * h->d + k + 4 + 63) & ~(size_t)63);
+    size_t off = 0;
+    long long *o = h->xoff;
+    o[0] = (long long)carve(&off, L); o[1] = (long long)carve(&off, L);            /* lab[2] */
+    o[2] = (long long)carve(&off, L); o[3] = (long long)carve(&off, L);            /* stale[2] */
+    o[4] = (long long)carve(&off, sizeof(unsigned) * NEMK_PK_MAX_WORLD);           /* xflag */
+    o[5] = (long long)carve(&off, sizeof(int32_t) * 2 * NEMK_PK_MAX_WORLD);        /* tot */
+    o[6] = (long long)carve(&off, sizeof(int32_t) * 2 * NEMK_PK_MAX_WORLD);        /* incnt */
+    o[7] = (long long)carve(&off, sizeof(int32_t) * 2 * (size_t)W * h->xcap);      /* inbox */
+    o[8] = (long long)carve(&off, sizeof(int32_t) * (size_t)W * h->xstat_len);     /* stat */
+    o[9] = (long long)carve(&off, sizeof(double) * (size_t)W * 8);                 /* crit */
+    /* drop the mappings of a previous layout */
+    for (int p = 0; p < NEMK_PK_MAX_WORLD; p++) {
+        if (h->xpeer[p] && p != h->rank) cudaIpcCloseMemHandle(h->xpeer[p]);
+        h->xpeer[p] = NULL;
+    }
+    h->xblk_ok = 0;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->b_xblk.p) { cudaFree(h->b_xblk.p); h->b_xblk.p = NULL; h->b_xblk.cap = 0; }
+    CK(cudaMalloc(&h->b_xblk.p, off));
+    h->b_xblk.cap = off; h->xblk_bytes = off;
+    CK(cudaMemsetAsync(h->b_xblk.p, 0, off, h->stream));
+    /* handles (and a go/no-go flag) travel through the communicator's all-gather */
+    struct { cudaIpcMemHandle_t hd; int ok; int pad[15]; } mine, all[NEMK_PK_MAX_WORLD];
+    memset(&mine, 0, sizeof mine);
+    mine.ok = cudaIpcGetMemHandle(&mine.hd, h->b_xblk.p) == cudaSuccess;
+    if (!mine.ok) cudaGetLastError();
+    dbuf tmp = {NULL, 0};
+    int rc = reserve(h, &tmp, sizeof mine * (size_t)(W + 1));
+    if (rc != NEMB_OK) return rc;
+    char *d_all = tmp.p, *d_mine = d_all + sizeof mine * (size_t)h->rank;
+    CK(cudaMemcpyAsync(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = gather(h, d_mine, d_all, sizeof mine)) != NEMB_OK) { release(&tmp); return rc; }
+    CK(cudaMemcpyAsync(all, d_all, sizeof mine * (size_t)W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int ok = 1;
+    for (int p = 0; p < W; p++) ok &= all[p].ok;
+    for (int p = 0; p < W && ok; p++) {
+        if (p == h->rank) { h->xpeer[p] = h->b_xblk.p; continue; }
+        void *ptr = NULL;
+        if (cudaIpcOpenMemHandle(&ptr, all[p].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        } else
+            h->xpeer[p] = ptr;
+    }
+    /* second round: every rank must have mapped every block */
+    mine.ok = ok;
+    CK(cudaMemcpyAsync(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = gather(h, d_mine, d_all, sizeof mine)) != NEMB_OK) { release(&tmp); return rc; }
+    CK(cudaMemcpyAsync(all, d_all, sizeof mine * (size_t)W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    release(&tmp);
+    for (int p = 0; p < W; p++) ok &= all[p].ok;
+    h->xblk_ok = ok;
+    h->xblk_k = k; h->xblk_lab_len = h->lab_len;
+    h->pk_xepoch = 0;
+    if (!ok)
+        for (int p = 0; p < W; p++) {
+            if (h->xpeer[p] && p != h->rank) cudaIpcCloseMemHandle(h->xpeer[p]);
+            h->xpeer[p] = NULL;
+        }
+    return NEMB_OK;
 }
 
 static int ensure_persist(nemb_handle *h)
@@ -1269,6 +1356,7 @@ static int ensure_persist(nemb_handle *h)
     size_t o_cnt = carve(&off, sizeof(nemk_counters) * 2);
     size_t o_bar = carve(&off, sizeof(unsigned) * 4);
     size_t o_crit = carve(&off, sizeof(double) * 4 * 2048);
+    size_t o_outc = carve(&off, sizeof(int32_t) * 16);
     int fresh = h->b_pk.cap < off;
     int rc = reserve(h, &h->b_pk, off);
     if (rc != NEMB_OK) return rc;
@@ -1287,6 +1375,7 @@ static int ensure_persist(nemb_handle *h)
     }
     h->d_pk_scratch = scr; h->d_pk_cnt2 = cnt2; h->d_pk_bar = bar;
     h->d_pk_crit = (double *)(base + o_crit);
+    h->d_pk_out_cnt = (int32_t *)(base + o_outc);
     return NEMB_OK;
 }
 
@@ -1327,6 +1416,28 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     if ((rc = ensure_persist(h)) != NEMB_OK) return rc;
     nemk_persist_args a;
     memset(&a, 0, sizeof a);
+    a.world = 1;
+    a.evflag = h->d_pk_evflag;
+    a.margin = h->d_margin;
+    a.lab[0] = h->d_lab[0]; a.lab[1] = h->d_lab[1];
+    a.stale[0] = h->d_stale[0]; a.stale[1] = h->d_stale[1];
+    if (h->world > 1) {
+        /* labels and stale flags live in the exchange block the peers store into; margins, Hamming
+         * counts and evaluation flags stay rank-local, addressed by GLOBAL family id (-row0) */
+        char *blk = h->b_xblk.p;
+        a.world = h->world; a.rank = h->rank; a.row0 = h->row0; a.shard_len = h->shard_len;
+        a.n_glob = h->n_glob; a.xcap = h->xcap; a.xepoch = h->pk_xepoch;
+        for (int p = 0; p < h->world; p++) a.peer[p] = h->xpeer[p];
+        a.off_lab[0] = h->xoff[0]; a.off_lab[1] = h->xoff[1]; a.off_stale[0] = h->xoff[2]; a.off_stale[1] = h->xoff[3];
+        a.off_xflag = h->xoff[4]; a.off_tot = h->xoff[5]; a.off_incnt = h->xoff[6]; a.off_inbox = h->xoff[7];
+        a.off_stat = h->xoff[8]; a.off_crit = h->xoff[9];
+        a.stat_len = h->xstat_len; a.out_cnt = h->d_pk_out_cnt; a.stat_glob = h->d_stat_int;
+        h->d_lab[0] = (uint8_t *)(blk + h->xoff[0]); h->d_lab[1] = (uint8_t *)(blk + h->xoff[1]);
+        a.lab[0] = h->d_lab[0]; a.lab[1] = h->d_lab[1];
+        a.stale[0] = (uint8_t *)(blk + h->xoff[2]); a.stale[1] = (uint8_t *)(blk + h->xoff[3]);
+        a.margin = h->d_margin - h->row0;
+        a.evflag = h->d_pk_evflag - h->row0;
+    }
     a.K = k; a.n = h->n; a.D = h->d; a.wpr = h->wpr; a.nwt = h->nwt;
     a.prop_model = o->prop; a.disp_model = o->disp; a.conv = o->conv; a.it_max = o->it_max;
     a.conv_thr = o->conv_thr;
@@ -1336,7 +1447,7 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     a.n_heavy = h->n_heavy; a.wsum_any_order = h->wgt_integral;
     a.use_margins = !h->no_margins;
     size_t xbytes = sizeof(uint32_t) * (size_t)h->n * h->wpr;
-    a.x_in_kernel = xbytes <= h->pk_xlimit;
+    a.x_in_kernel = xbytes <= h->pk_xlimit && h->world == 1;
     a.init_from_pop = uniform0 == 2 && !h->no_popcache;
     if (a.init_from_pop && (rc = ensure_pop(h)) != NEMB_OK) return rc;
     if (a.x_in_kernel && (rc = ensure_xt(h)) != NEMB_OK) return rc;
@@ -1346,11 +1457,9 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     a.prop = h->d_prop; a.center = h->d_center; a.disp = h->d_disp; a.coef = h->d_coef;
     a.mxor = h->d_mxor; a.mval = h->d_mval; a.f0 = h->d_f0; a.f1 = h->d_f1; a.cm = h->d_cm;
     a.delta = h->d_delta; a.ham = h->d_ham; a.stat = h->d_stat_loc;
-    a.lab[0] = h->d_lab[0]; a.lab[1] = h->d_lab[1];
-    a.stale[0] = h->d_stale[0]; a.stale[1] = h->d_stale[1];
-    a.margin = h->d_margin; a.dirty = h->d_dirty; a.wl[0] = h->d_wl[0]; a.wl[1] = h->d_wl[1];
+    a.dirty = h->d_dirty; a.wl[0] = h->d_wl[0]; a.wl[1] = h->d_wl[1];
     a.wl_cnt = h->d_wl_counts;
-    a.wlist[0] = h->d_pk_wl[0]; a.wlist[1] = h->d_pk_wl[1]; a.wl_cap = h->pk_wl_cap; a.evflag = h->d_pk_evflag;
+    a.wlist[0] = h->d_pk_wl[0]; a.wlist[1] = h->d_pk_wl[1]; a.wl_cap = h->pk_wl_cap;
     a.hub_list = h->d_pk_hub; a.scratch = h->d_pk_scratch; a.cnt2 = h->d_pk_cnt2; a.bar = h->d_pk_bar;
     a.out = h->d_pk_out;
     a.crit_partials = h->d_pk_crit; a.want_crit = 1; a.spatial = h->spatial;
@@ -1400,11 +1509,15 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         res->n_kept += out.kept;
         res->pk_barriers += out.barriers; res->pk_x_passes += out.x_passes; res->pk_recounts += out.recounts;
         res->n_allnul = out.n_allnul; res->n_ties = out.n_ties;
+        h->pk_xepoch = out.xepoch;
+        if (out.exit_code == NEMK_PK_EXIT_PEER_TIMEOUT || out.xerror)
+            return fail(h, NEMB_E_CUDA, "row-sharded fit: rank %d waited for a peer that never arrived", h->rank);
         if (out.exit_code == NEMK_PK_EXIT_DONE) { done = 1; break; }
         a.entry = out.resume_entry; a.iter0 = out.iters; a.cur = out.cur; a.stale_par = out.stale_par;
         a.stats_valid = out.stats_valid; a.last_changed = out.last_changed;
         a.delta_mode = out.delta_mode; a.n_allnul = out.n_allnul; a.n_ties = out.n_ties;
         a.flags_stale = out.flags_stale; a.mu_changed = out.mu_changed;
+        a.xepoch = out.xepoch; a.decide_pending = out.decide_pending; a.chg_local = out.chg_local;
         a.margins_on = out.sweeps > 0 || a.margins_on;
         if (out.exit_code == NEMK_PK_EXIT_NEED_DENSITY) {
             /* the class masks moved and X does not fit the L2: the TMA-tiled X pass (HBM-bound) */
@@ -1414,7 +1527,7 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
             /* full recount of S = X^T T through the transposed bits (HBM-bound) */
             if ((rc = ensure_xt(h)) != NEMB_OK) return rc;
             STAGE_BEGIN(ST_MSTEP);
-            nemk_label_masks(h->stream, k, h->n, h->nwt, h->d_lab[h->cur], h->d_cm, h->d_stat_loc + kd,
+            nemk_label_masks(h->stream, k, h->n, h->nwt, h->d_lab[h->cur] + h->row0, h->d_cm, h->d_stat_loc + kd,
                              NULL, &h->d_coef->halt);
             nemk_mstep_ncem(h->stream, k, h->d, h->nwt, h->d_xt, h->d_cm, h->d_stat_loc, &h->d_coef->halt);
             CK(cudaMemsetAsync(&h->d_coef->uniform_ok, 1, sizeof(int32_t), h->stream));
@@ -1472,8 +1585,13 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
     double oldcrit = 0.0;
     int can_spec;
     /* one cooperative launch for the whole fit where it applies (nem_persist.cuh) */
-    const int persist = lean && persist_eligible(h, o, uniform0, cb != NULL, t_init);
+    int persist = lean && persist_eligible(h, o, uniform0, cb != NULL, t_init);
     if (cb && !nk_host) { rc = fail(h, NEMB_E_MEMORY, "host memory"); goto out; }
+    if (persist && h->world > 1) {
+        /* the peers' exchange blocks (CUDA IPC); without peer memory every rank falls back alike */
+        if ((rc = ensure_xblk(h, k)) != NEMB_OK) goto out;
+        if (!h->xblk_ok) persist = 0;
+    }
     if (persist) {
         if ((rc = em_persist(h, o, uniform0, res, &iter, &converged, &status, &empty)) != NEMB_OK) goto out;
         goto tail;
@@ -1586,7 +1704,7 @@ static int em_core(nemb_handle *h, const nemb_options *o, int uniform0, nemb_res
         if (flips[(enq - 1) & 1]) h->cur ^= 1;
     }
 tail:
-    if (h->world > 1 && status == NEMB_OK && iter > 0) {
+    if (h->world > 1 && !persist && status == NEMB_OK && iter > 0) {
         /* row shards: the per-iteration statuses of the speculative sweep carry this rank's
          * all-null / tie counters only; one counter all-gather gives the totals of the last sweep */
         if ((rc = read_status(h)) != NEMB_OK) goto out;

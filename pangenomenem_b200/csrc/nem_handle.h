@@ -121,6 +121,17 @@ struct nemb_handle {
     int medium_list, pk_grid_env;
     int no_shortcuts;      /* NEM_B200_NO_SHORTCUTS: X pass + full recount every iteration, margin cache off */
     size_t pk_xlimit;      /* X up to this many bytes: the X / X^T passes run inside the persistent kernel */
+    /* row shards, persistent kernel: this rank's exchange block (labels, stale flags, barrier flags,
+     * inboxes, staging areas) and the peers' blocks mapped through CUDA IPC */
+    dbuf b_xblk;
+    size_t xblk_bytes;
+    int xblk_k, xblk_lab_len, xblk_ok;      /* what the mapped blocks were laid out for; usable */
+    char *xpeer[NEMK_PK_MAX_WORLD];
+    long long xoff[12];                     /* off_lab[2], off_stale[2], xflag, tot, incnt, inbox, stat, crit */
+    int xstat_len, xcap;
+    unsigned pk_xepoch;
+    int32_t *d_pk_out_cnt;
+    int no_persist_shard;
     /* fit bookkeeping */
     int64_t launches, fixup_rounds, exchanges;
     int profile;

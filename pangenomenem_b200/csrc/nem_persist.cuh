@@ -64,6 +64,62 @@ static __device__ __forceinline__ void pk_grid_sync(unsigned *bar, unsigned nblo
     __syncthreads();
 }
 
+// ---- row shards: the exchange block of rank p (peer memory), typed views into it
+template <typename T>
+static __device__ __forceinline__ T *pk_peer(const nemk_persist_args &a, int p, long long off) {
+    return reinterpret_cast<T *>(a.peer[p] + off);
+}
+// cross-rank barrier.  All CTAs of all ranks call it the same number of times (every decision that
+// leads here is taken from numbers that are identical on every rank).  Local device-wide barrier
+// (every thread that stored into a peer's block fenced at system scope before), then thread 0
+// raises this rank's epoch flag in every peer's block and waits for theirs in its own, then a
+// second local barrier releases the grid.  A peer that never arrives (dead process) ends the wait
+// after ~4 s with *xerr set instead of hanging the GPU.
+static __device__ void pk_xbarrier(const nemk_persist_args &a, unsigned &epoch, int &xerr) {
+    pk_grid_sync(a.bar, gridDim.x);
+    epoch++;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int p = 0; p < a.world; p++)
+            if (p != a.rank) *(volatile unsigned *)(pk_peer<unsigned>(a, p, a.off_xflag) + a.rank) = epoch;
+        volatile unsigned *mine = pk_peer<unsigned>(a, a.rank, a.off_xflag);
+        const long long t0 = clock64();
+        for (int q = 0; q < a.world; q++) {
+            if (q == a.rank) continue;
+            while ((int)(mine[q] - epoch) < 0) {
+                if (clock64() - t0 > 8000000000ll) { *(volatile int *)&a.scratch[13] = 1; break; }
+                __nanosleep(40);
+            }
+        }
+        __threadfence_system();
+    }
+    pk_grid_sync(a.bar, gridDim.x);
+    if (*(volatile int *)&a.scratch[13]) xerr = 1;
+}
+// label of own family i := km in the label buffer `buf` of every OTHER rank
+static __device__ __forceinline__ void pk_push_label(const nemk_persist_args &a, int buf, int i, int km) {
+    for (int p = 0; p < a.world; p++)
+        if (p != a.rank) pk_peer<uint8_t>(a, p, a.off_lab[buf])[i] = (uint8_t)km;
+    __threadfence_system();
+}
+// family j of a LOWER rank read the old label of a family that moved: its cached margin is void for
+// its owner's next sweep
+static __device__ __forceinline__ void pk_push_stale(const nemk_persist_args &a, int buf, int j) {
+    pk_peer<uint8_t>(a, j / a.shard_len, a.off_stale[buf])[j] = 1;
+    __threadfence_system();
+}
+// family j, owned by another rank, must be re-evaluated there: into that rank's inbox segment of
+// this rank (parity = the super-round being built); counted locally, published at the barrier
+static __device__ __forceinline__ void pk_push_remote(const nemk_persist_args &a, int par, int j) {
+    const int owner = j / a.shard_len;
+    const int slot = atomicAdd(&a.out_cnt[owner], 1);
+    if (slot < a.xcap) {
+        pk_peer<int32_t>(a, owner, a.off_inbox)[((size_t)par * a.world + a.rank) * a.xcap + slot] = j;
+        __threadfence_system();
+    } else
+        a.scratch[12] = 1;      // overflow: every rank then re-evaluates all its families
+}
+
 // phase timer of CTA 0 / thread 0 (nemk_persist_out.phase_ns)
 // (SM cycle counter: CTA 0 never migrates; a %globaltimer read is far slower and would sit on the
 // critical path of every phase; the host converts with the SM clock rate)
@@ -78,7 +134,7 @@ static __device__ __forceinline__ int pk_trace_col(int idx) {   // phase index -
     (P).t_last = t_; } } while (0)
 
 // where the evaluations of a sweep append the sites that must be (re-)evaluated in the next round
-struct PkNext { int32_t *list, *cnt, *ovf; int cap; };
+struct PkNext { int32_t *list, *cnt, *ovf; int cap; const nemk_persist_args *a; int lo, hi, par, stale_buf; };   // [lo, hi) own families, par: inbox parity, stale_buf: index of stale_next
 
 // label of site i moved: every later reader goes to the next round (no de-duplication), earlier-or-
 // equal readers keep this sweep's evaluation, which saw the OLD label: their cached margin is void
@@ -95,7 +151,14 @@ static __device__ __forceinline__ void pk_push_readers(int i, const int32_t *rro
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             if (j[q] < 0) continue;
-            if (j[q] <= i) { if (stale_next) stale_next[j[q]] = 1; j[q] = -1; }
+            if (j[q] <= i) {
+                if (stale_next) {
+                    if (j[q] >= nx.lo) stale_next[j[q]] = 1;
+                    else pk_push_stale(*nx.a, nx.stale_buf, j[q]);     // a lower rank's family
+                }
+                j[q] = -1;
+            }
+            else if (j[q] >= nx.hi) { pk_push_remote(*nx.a, nx.par, j[q]); j[q] = -1; }   // another rank's family
             else if (chase && *chase < 0) { *chase = j[q]; j[q] = -1; }
             else nl++;
         }
@@ -114,8 +177,12 @@ static __device__ __forceinline__ void pk_push_readers_warp(int i, const int32_t
     const int lo = rrow_ptr[i], hi = rrow_ptr[i + 1];
     for (int e0 = lo; e0 < hi; e0 += 32) {
         const int e = e0 + lane;
-        const int j = e < hi ? rcol[e] : -1;
-        if (j >= 0 && j <= i && stale_next) stale_next[j] = 1;
+        int j = e < hi ? rcol[e] : -1;
+        if (j >= 0 && j <= i && stale_next) {
+            if (j >= nx.lo) stale_next[j] = 1;
+            else pk_push_stale(*nx.a, nx.stale_buf, j);
+        }
+        if (j >= nx.hi) { pk_push_remote(*nx.a, nx.par, j); j = -1; }
         const unsigned later = __ballot_sync(FULL, j > i);
         if (!later) continue;
         int base = 0;
@@ -226,11 +293,11 @@ static __device__ __forceinline__ int pk_fix_site(int K, int i, const nemk_lpsrc
     const int km = site_argmax<KT>(K, lpv, ctx, beta, fl, margin);
     store_margin(mg, i, margin, thr_store);     // the LAST evaluation of a site is its final one
     evflag[i] = (uint8_t)fl;
-    chase = -1;
+    chase = -1;      // (no chasing: see PK_CHASE above -- every later reader is queued)
     if (km == was) return 0;
     if (track) replaced = pk_xchg_label(lab_cur, i, km);
     else { lab_cur[i] = (uint8_t)km; replaced = was; }
-    pk_push_readers(i, rrow_ptr, rcol, nx, mg.stale_next, &chase);
+    pk_push_readers(i, rrow_ptr, rcol, nx, mg.stale_next);
     return km + 1;
 }
 // a hub, by a whole warp; statistics and the net changed count included
@@ -238,7 +305,7 @@ template <int KT>
 static __device__ __forceinline__ void pk_fix_hub(const nemk_persist_args &a, int K, int i, const nemk_lpsrc &lps,
                                                   const int32_t *rp, const int32_t *col, const float *wgt,
                                                   double beta, const uint8_t *lab_old, uint8_t *lab_cur,
-                                                  const int32_t *rrow_ptr, const int32_t *rcol,
+                                                  int out_buf, const int32_t *rrow_ptr, const int32_t *rcol,
                                                   const PkNext &nx, const nemk_margins &mg,
                                                   double thr_store, uint8_t *evflag, bool track) {
     const int lane = threadIdx.x & 31;
@@ -261,6 +328,7 @@ static __device__ __forceinline__ void pk_fix_hub(const nemk_persist_args &a, in
         }
     }
     if (km == was) return;
+    if (a.world > 1 && lane == 0) pk_push_label(a, out_buf, i, km);
     pk_push_readers_warp(i, rrow_ptr, rcol, nx, mg.stale_next);
     if (track) {
         replaced = __shfl_sync(FULL, replaced, 0);
@@ -277,13 +345,20 @@ static __device__ __forceinline__ void pk_fix_hub(const nemk_persist_args &a, in
 // use_graph: context term on; seq: in-place index-order semantics through the speculative fixed
 // point; margins (mg.m != NULL) only with seq.  cnt->kept receives the sites the margin cache
 // saved.  The caller counts the changed labels afterwards (pk_scan).
+// Row shards: this rank evaluates its own families [row0, row0 + n); a label that moves is stored
+// into every peer's copy of the output buffer at once, a later reader owned by another rank is
+// queued in that rank's inbox.  A rank runs its fix-up rounds to exhaustion with LOCAL barriers
+// only; the ranks then meet (one cross-rank barrier), and as long as some inbox is not empty they
+// start another cascade from their inboxes.  Any interleaving reaches the same fixed point (header).
 template <int KT>
 static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lps, double beta,
                                bool use_graph, bool seq, const uint8_t *lab_in, uint8_t *lab_out,
-                               nemk_margins mg, nemk_counters *cnt, nemk_counters *cnt_next,
-                               float *s_w, uint8_t *s_l, int &barriers, long long &kept_total,
-                               int &nfix_total, PkProf &prof, bool track_ok, int mu_changed) {
-    const int K = a.K, n = a.n;
+                               int out_buf, nemk_margins mg, int stale_next_buf, nemk_counters *cnt,
+                               nemk_counters *cnt_next, float *s_w, uint8_t *s_l, int &barriers,
+                               long long &kept_total, int &nfix_total, PkProf &prof, bool track_ok,
+                               int mu_changed, unsigned &xepoch, int &xerr) {
+    const int K = a.K, n = a.n, lo_i = a.row0, hi_i = a.row0 + a.n;
+    const bool sharded = a.world > 1;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nwarps = nthreads >> 5, gwarp = gtid >> 5;
@@ -301,11 +376,10 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
     const bool may_skip = mg.m && thr.test < CUDART_INF;
     const bool hubs = rp && a.n_heavy > 0;
     // track: the integer statistics S, n (which describe lab_in when the sweep starts) follow every
-    // label move of this sweep at once, so the next M-step needs neither a scan nor an update
-    // phase; only in margin-cached sweeps after a sweep that moved few labels (a row costs its set
-    // bits in atomics).  scratch[6] = net number of labels != lab_in.
-    const bool track = PK_TRACK && track_ok && may_skip;
-    const PkNext nx0 = {a.wlist[0], &wl_cnt[0], &ovf[0], a.wl_cap};   // the list of fix-up round 0
+    // label move of this sweep at once (compile-time knob PK_TRACK; one GPU only)
+    const bool track = PK_TRACK && track_ok && may_skip && !sharded;
+    int par = (int)(xepoch & 1u);      // inbox parity of the requests queued until the next cross-rank barrier
+    const PkNext nx0 = {a.wlist[0], &wl_cnt[0], &ovf[0], a.wl_cap, &a, lo_i, hi_i, par, stale_next_buf};
     int kept = 0;
     // counters of the last scan: every CTA read them right after the scan's barrier and has passed
     // another barrier since (closed forms); the next scan starts after this sweep's barriers
@@ -321,12 +395,12 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
         const int ngroups = (n + 3) >> 2;
         int nact = 0;
         for (int g0 = gwarp * 32; g0 < ngroups; g0 += nwarps * 32) {
-            const int g = g0 + lane, i0 = g * 4;
+            const int g = g0 + lane, i0 = lo_i + g * 4;
             unsigned actm = 0u, hubm = 0u;
             if (g < ngroups) {
                 uint8_t st[4], lb[4];
                 float mv[4];
-                const int nv = min(4, n - i0);
+                const int nv = min(4, hi_i - i0);
                 if (nv == 4) {
                     const uchar4 s4 = *reinterpret_cast<const uchar4 *>(mg.stale_cur + i0);
                     const uchar4 l4 = *reinterpret_cast<const uchar4 *>(lab_in + i0);
@@ -393,9 +467,11 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
             for (int r0 = 0; r0 < total; r0 += 32) {
                 const int r = r0 + lane, site = r < total ? sm_act[r] : -1;
                 int res = 0;
-                if (site >= 0)
+                if (site >= 0) {
                     res = pk_jac_site<KT>(K, site, lps, rp, a.col, a.wgt, beta, lab_in, lab_out, seq, a.rrow_ptr,
                                           a.rcol, nx0, mg, thr.store, a.evflag);
+                    if (res && sharded) pk_push_label(a, out_buf, site, res - 1);
+                }
                 if (track) {
                     const int from = site >= 0 ? (int)lab_in[site] : 0;
                     pk_move_rows_warp(a, res, site, from, res - 1);
@@ -427,12 +503,14 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
                 else if (v) nx0.list[base + lane] = i;
             }
         } else if (hubs) {
-            for (int wi = gwarp; wi < a.n_heavy; wi += nwarps)
-                pk_jac_hub<KT>(K, a.heavy[wi], lps, rp, a.col, a.wgt, beta, lab_in, lab_out, a.evflag);
+            for (int wi = gwarp; wi < a.n_heavy; wi += nwarps) {
+                const int i = a.heavy[wi];
+                pk_jac_hub<KT>(K, i, lps, rp, a.col, a.wgt, beta, lab_in, lab_out, a.evflag);
+            }
         }
-        for (int base = gwarp * 32; base < n; base += nwarps * 32) {
+        for (int base = lo_i + gwarp * 32; base < hi_i; base += nwarps * 32) {
             const int i = base + lane;
-            const bool valid = i < n;
+            const bool valid = i < hi_i;
             int lo = 0, hi = 0;
             if (rp && valid) { lo = rp[i]; hi = rp[i + 1]; }
             const bool is_heavy = hubs && (hi - lo > HEAVY_DEG);
@@ -448,6 +526,7 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
                     ctx_labels_coop<KT>(lo, hi, seg_lo, seg_hi, a.col, a.wgt, lab_in,
                                         s_w + wib * COOP_CHUNK, s_l + wib * COOP_CHUNK, ctx);
             }
+            int newlab = valid ? (int)lab_in[i] : 0;      // a deferred hub keeps its old label for now
             if (valid && !is_heavy) {
                 double margin;
                 int fl;
@@ -456,8 +535,32 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
                 a.evflag[i] = (uint8_t)fl;
                 store_margin(mg, i, margin, thr.store);
                 if (mg.m) mg.stale_cur[i] = 0;
-                if (seq && km != (int)lab_in[i]) pk_push_readers(i, a.rrow_ptr, a.rcol, nx0, mg.stale_next);
+                if (seq && km != newlab) pk_push_readers(i, a.rrow_ptr, a.rcol, nx0, mg.stale_next);
+                newlab = km;
             }
+            if (sharded) {
+                // the 32 labels of the warp go to every peer as whole words (8 stores per peer)
+                unsigned w = (unsigned)newlab & 0xffu;
+                w |= (__shfl_down_sync(FULL, (unsigned)newlab & 0xffu, 1) << 8);
+                w |= (__shfl_down_sync(FULL, (unsigned)newlab & 0xffu, 2) << 16);
+                w |= (__shfl_down_sync(FULL, (unsigned)newlab & 0xffu, 3) << 24);
+                if ((lane & 3) == 0 && valid) {
+                    if (i + 4 <= hi_i) {
+                        for (int p = 0; p < a.world; p++)
+                            if (p != a.rank) *reinterpret_cast<unsigned *>(pk_peer<uint8_t>(a, p, a.off_lab[out_buf]) + i) = w;
+                    } else {
+                        for (int q = 0; i + q < hi_i; q++)
+                            for (int p = 0; p < a.world; p++)
+                                if (p != a.rank) pk_peer<uint8_t>(a, p, a.off_lab[out_buf])[i + q] = (uint8_t)(w >> (8 * q));
+                    }
+                    __threadfence_system();
+                }
+            }
+        }
+        if (sharded && hubs && !seq) {
+            // update=para: the hubs were evaluated above by their warps; publish their labels
+            pk_grid_sync(a.bar, gridDim.x); barriers++;
+            for (int q = gtid; q < a.n_heavy; q += nthreads) pk_push_label(a, out_buf, a.heavy[q], lab_out[a.heavy[q]]);
         }
     }
     {
@@ -474,46 +577,59 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
     }
 
     // ---- fix-up rounds: the listed sites are re-evaluated (duplicates allowed) until no label
-    // moves; one barrier per round.  Round r reads list r&1 / counter r&3, appends to list (r+1)&1 /
-    // counter (r+1)&3 and clears counter (r+2)&3 (idle during the round).  Items are dealt
+    // moves; one LOCAL barrier per round.  Round r reads list r&1 / counter r&3, appends to list
+    // (r+1)&1 / counter (r+1)&3 and clears counter (r+2)&3 (idle during the round).  Items are dealt
     // round-robin over the warps so that a run of hubs lands on different warps.
     int rounds = 0;
-    if (seq) {
-        for (int round = 0;; round++) {
-            const int32_t *cur_list = a.wlist[round & 1];
-            const PkNext nx = {a.wlist[(round + 1) & 1], &wl_cnt[(round + 1) & 3], &ovf[(round + 1) & 3], a.wl_cap};
-            const int count = *(volatile int32_t *)&wl_cnt[round & 3];
-            const bool all = *(volatile int32_t *)&ovf[round & 3] != 0;   // a list overflowed: every site
-            if (gtid == 0) { wl_cnt[(round + 2) & 3] = 0; ovf[(round + 2) & 3] = 0; }
-            const int items = all ? n : count;
-            if (items == 0) break;
-            rounds++;
-            for (int base = gwarp; base < items; base += 32 * nwarps) {
-                const int idx = base + lane * nwarps;
-                int i = idx < items ? (all ? idx : cur_list[idx]) : -1;
-                // hubs by the whole warp
-                const bool hub = i >= 0 && (rp[i + 1] - rp[i] > HEAVY_DEG);
-                unsigned hm = __ballot_sync(FULL, hub);
-                while (hm) {
-                    const int src = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    pk_fix_hub<KT>(a, K, __shfl_sync(FULL, i, src), lps, rp, a.col, a.wgt, beta, lab_in, lab_out,
-                                   a.rrow_ptr, a.rcol, nx, mg, thr.store, a.evflag, track);
-                }
-                if (hub) i = -1;
-                // light sites by their lane; a site that moved goes on with its first later reader
-                // in the same round (the usual dependency is the next family along the chromosome)
-                // instead of paying a round per link
-                for (int step = 0; step < PK_CHASE; step++) {
-                    int res = 0, replaced = 0, chase = -1;
-                    if (i >= 0 && step > 0 && rp[i + 1] - rp[i] > HEAVY_DEG) {   // a chased hub: next round
-                        const int b = atomicAdd(nx.cnt, 1);
-                        if (b + 1 > nx.cap) *nx.ovf = 1; else nx.list[b] = i;
-                        i = -1;
+    if (seq || sharded) {
+        int round = 0, src_mode = 0, inbox_total = 0;    // src_mode: 0 local list, 1 inbox, 2 every own family
+        int in_pref[NEMK_PK_MAX_WORLD + 1];
+        for (int q = 0; q <= NEMK_PK_MAX_WORLD; q++) in_pref[q] = 0;
+        for (;;) {   // cascades, separated by cross-rank barriers (one cascade on one GPU)
+            for (;; round++) {
+                const int32_t *cur_list = a.wlist[round & 1];
+                const PkNext nx = {a.wlist[(round + 1) & 1], &wl_cnt[(round + 1) & 3], &ovf[(round + 1) & 3],
+                                   a.wl_cap, &a, lo_i, hi_i, par, stale_next_buf};
+                int count = 0;
+                bool all = src_mode == 2;
+                if (src_mode == 0) {
+                    count = seq ? *(volatile int32_t *)&wl_cnt[round & 3] : 0;
+                    all = *(volatile int32_t *)&ovf[round & 3] != 0;   // a list overflowed: every own family
+                } else if (src_mode == 1)
+                    count = inbox_total;
+                if (gtid == 0) { wl_cnt[(round + 2) & 3] = 0; ovf[(round + 2) & 3] = 0; }
+                const int items = all ? n : count;
+                if (items == 0) break;
+                rounds++;
+                const int32_t *inbox = pk_peer<int32_t>(a, a.rank, a.off_inbox) + (size_t)(par ^ 1) * a.world * a.xcap;
+                for (int base = gwarp; base < items; base += 32 * nwarps) {
+                    const int idx = base + lane * nwarps;
+                    int i = -1;
+                    if (idx < items) {
+                        if (all) i = lo_i + idx;
+                        else if (src_mode == 1) {
+                            int sseg = 0;
+                            while (idx >= in_pref[sseg + 1]) sseg++;
+                            i = inbox[(size_t)sseg * a.xcap + (idx - in_pref[sseg])];
+                        } else
+                            i = cur_list[idx];
                     }
-                    if (i >= 0)
+                    // hubs by the whole warp
+                    const bool hub = i >= 0 && (rp[i + 1] - rp[i] > HEAVY_DEG);
+                    unsigned hm = __ballot_sync(FULL, hub);
+                    while (hm) {
+                        const int src = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        pk_fix_hub<KT>(a, K, __shfl_sync(FULL, i, src), lps, rp, a.col, a.wgt, beta, lab_in, lab_out,
+                                       out_buf, a.rrow_ptr, a.rcol, nx, mg, thr.store, a.evflag, track);
+                    }
+                    if (hub) i = -1;
+                    int res = 0, replaced = 0, chase = -1;
+                    if (i >= 0) {
                         res = pk_fix_site<KT>(K, i, lps, rp, a.col, a.wgt, beta, lab_in, lab_out, a.rrow_ptr, a.rcol,
                                               nx, mg, thr.store, a.evflag, track, replaced, chase);
+                        if (res && sharded) pk_push_label(a, out_buf, i, res - 1);
+                    }
                     if (track) {
                         const int moved = res != 0 && replaced != res - 1;
                         pk_move_rows_warp(a, moved, i, replaced, res - 1);
@@ -523,16 +639,49 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
                             if (dn) atomicAdd(&a.scratch[6], dn);
                         }
                     }
-                    if (step + 1 == PK_CHASE && chase >= 0) {   // chain longer than the chase: queue it
-                        const int b = atomicAdd(nx.cnt, 1);
-                        if (b + 1 > nx.cap) *nx.ovf = 1; else nx.list[b] = chase;
-                        chase = -1;
-                    }
-                    i = res ? chase : -1;
-                    if (!__any_sync(FULL, i >= 0)) break;
                 }
+                pk_grid_sync(a.bar, gridDim.x); barriers++;
+                src_mode = 0;
             }
-            pk_grid_sync(a.bar, gridDim.x); barriers++;
+            if (!sharded) break;
+            // ---- the ranks meet: requests sent to every rank (their inbox counts) and this rank's
+            // total, stored into the peers' blocks; after the barrier every rank adds up the same
+            // totals.  Nothing in flight anywhere = the sweep is over.
+            if (gtid == 0) {
+                const int over = *(volatile int32_t *)&a.scratch[12];
+                int sent = 0;
+                for (int p = 0; p < a.world; p++) {
+                    int c = *(volatile int32_t *)&a.out_cnt[p];
+                    if (c > a.xcap) c = a.xcap;
+                    if (p != a.rank) {
+                        sent += c;
+                        pk_peer<int32_t>(a, p, a.off_incnt)[par * NEMK_PK_MAX_WORLD + a.rank] = c;
+                    }
+                    a.out_cnt[p] = 0;
+                }
+                for (int p = 0; p < a.world; p++)
+                    pk_peer<int32_t>(a, p, a.off_tot)[par * NEMK_PK_MAX_WORLD + a.rank] = over ? -1 : sent;
+                a.scratch[12] = 0;
+                __threadfence_system();
+            }
+            pk_xbarrier(a, xepoch, xerr);
+            barriers += 2;
+            if (xerr) break;
+            const volatile int32_t *tot = pk_peer<int32_t>(a, a.rank, a.off_tot) + par * NEMK_PK_MAX_WORLD;
+            const volatile int32_t *inc = pk_peer<int32_t>(a, a.rank, a.off_incnt) + par * NEMK_PK_MAX_WORLD;
+            int total = 0, over = 0;
+            for (int q = 0; q < a.world; q++) { const int t = tot[q]; if (t < 0) over = 1; else total += t; }
+            if (total == 0 && !over) break;
+            in_pref[0] = 0;
+            for (int q = 0; q < a.world; q++) in_pref[q + 1] = in_pref[q] + (q == a.rank ? 0 : inc[q]);
+            for (int q = a.world; q < NEMK_PK_MAX_WORLD; q++) in_pref[q + 1] = in_pref[a.world];
+            inbox_total = in_pref[a.world];
+            src_mode = over ? 2 : 1;
+            par ^= 1;            // == xepoch & 1: requests queued from now on go to the other inbox
+            if (inbox_total == 0 && !over) {
+                // nothing for this rank, but others work: it still takes part in the next meeting
+                src_mode = 0;
+            }
         }
         PK_MARK(prof, 9);
         if (gtid == 0) {
@@ -557,19 +706,22 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
 // moves (pk_sweep `track`) need no scan; their flags are summed once, when the kernel is left.
 template <int KT>
 static __device__ void pk_scan(const nemk_persist_args &a, const uint8_t *lab, const uint8_t *lab_m,
-                               int mode, int32_t *list, int32_t *count) {
-    const int n = a.n;
+                               int mode, int32_t *list, int32_t *count, int fix_buf) {
+    // row shards: own families only (row0 is a multiple of 16).  fix_buf >= 0: the peers' copies of
+    // label buffer fix_buf (the one the NEXT sweep writes) still hold, for this rank's families, the
+    // labels of one sweep ago: the rows that moved are brought up to date there.
+    const int n = a.n, lo_i = a.row0;
     const int nthreads = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
     const int ngroups = (n + 15) >> 4;
     int nul = 0, ties = 0;
     for (int t0 = ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); t0 < ngroups; t0 += nthreads) {
-        const int t = t0 + lane, i0 = t * 16;
+        const int t = t0 + lane, i0 = lo_i + t * 16;
         uint32_t dm = 0u;
         if (t < ngroups) {
-            if (i0 + 16 <= n) {
-                const uint4 p = *(reinterpret_cast<const uint4 *>(lab) + t);
-                const uint4 q = *(reinterpret_cast<const uint4 *>(lab_m) + t);
-                const uint4 f = *(reinterpret_cast<const uint4 *>(a.evflag) + t);
+            if (i0 + 16 <= lo_i + n) {
+                const uint4 p = *reinterpret_cast<const uint4 *>(lab + i0);
+                const uint4 q = *reinterpret_cast<const uint4 *>(lab_m + i0);
+                const uint4 f = *reinterpret_cast<const uint4 *>(a.evflag + i0);
                 dm = nonzero_bytes(p.x ^ q.x) | (nonzero_bytes(p.y ^ q.y) << 4) |
                      (nonzero_bytes(p.z ^ q.z) << 8) | (nonzero_bytes(p.w ^ q.w) << 12);
                 nul += __popc(f.x & 0x01010101u) + __popc(f.y & 0x01010101u) + __popc(f.z & 0x01010101u) +
@@ -577,12 +729,22 @@ static __device__ void pk_scan(const nemk_persist_args &a, const uint8_t *lab, c
                 ties += __popc(f.x & 0x02020202u) + __popc(f.y & 0x02020202u) + __popc(f.z & 0x02020202u) +
                         __popc(f.w & 0x02020202u);
             } else {
-                for (int j = 0; i0 + j < n; j++) {
+                for (int j = 0; i0 + j < lo_i + n; j++) {
                     dm |= (uint32_t)(lab[i0 + j] != lab_m[i0 + j]) << j;
                     nul += a.evflag[i0 + j] & 1;
                     ties += (a.evflag[i0 + j] >> 1) & 1;
                 }
             }
+        }
+        if (fix_buf >= 0 && dm) {
+            uint32_t m = dm;
+            while (m) {
+                const int i = i0 + __ffs(m) - 1;
+                m &= m - 1;
+                for (int p = 0; p < a.world; p++)
+                    if (p != a.rank) pk_peer<uint8_t>(a, p, a.off_lab[fix_buf])[i] = lab[i];
+            }
+            __threadfence_system();
         }
         const int c = __popc(dm);
         int incl = c;
@@ -653,9 +815,9 @@ static __device__ __forceinline__ void pk_block_sum4(double (&v)[4], double *sh 
 template <int TH>
 static __device__ void pk_finalize_class(int k, const nemk_persist_args &a, double *sh,
                                          float *nkf, double *nkd) {
-    const int K = a.K, D = a.D, N = a.n, tid = threadIdx.x, lane = tid & 31, wpr = a.wpr;
-    const int32_t *__restrict__ s_int = a.stat;
-    const int32_t *__restrict__ nk_int = a.stat + (size_t)K * D;
+    const int K = a.K, D = a.D, N = a.world > 1 ? a.n_glob : a.n, tid = threadIdx.x, lane = tid & 31, wpr = a.wpr;
+    const int32_t *__restrict__ s_int = a.world > 1 ? a.stat_glob : a.stat;      // summed over the ranks
+    const int32_t *__restrict__ nk_int = s_int + (size_t)K * D;
     float *center = a.center, *disp = a.disp;
     const int wreal = (D + 31) >> 5;
     __syncthreads();
@@ -976,9 +1138,9 @@ static __device__ void pk_criteria_partial(const nemk_persist_args &a, const nem
                 crit_site<KT>(K, lpv, ctx, ti, beta, c[0], c[1], c[2], c[3]);
             }
         }
-    for (int base = gwarp * 32; base < n; base += nwarps * 32) {
+    for (int base = a.row0 + gwarp * 32; base < a.row0 + n; base += nwarps * 32) {
         const int i = base + lane;
-        const bool valid = i < n;
+        const bool valid = i < a.row0 + n;
         int lo = 0, hi = 0;
         if (rp && valid) { lo = rp[i]; hi = rp[i + 1]; }
         const bool is_heavy = hubs && (hi - lo > HEAVY_DEG);
@@ -1007,15 +1169,45 @@ static __device__ void pk_criteria_partial(const nemk_persist_args &a, const nem
         for (int q = 0; q < 4; q++) a.crit_partials[(size_t)blockIdx.x * 4 + q] = c[q];
     }
 }
-static __device__ void pk_criteria_final(const nemk_persist_args &a, double *sh, double *crit6) {
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
+// this rank's sums D G L Z: its CTAs' partial rows added in CTA order (one CTA calls this)
+static __device__ void pk_criteria_rank_sums(const nemk_persist_args &a, double *sh, double (&v)[4]) {
+    for (int q = 0; q < 4; q++) v[q] = 0.0;
     for (int b = threadIdx.x; b < (int)gridDim.x; b += PK_THREADS)   // fixed assignment: deterministic
 #pragma unroll
         for (int q = 0; q < 4; q++) v[q] += a.crit_partials[(size_t)b * 4 + q];
     pk_block_sum4<PK_THREADS>(v, sh);
-    const double D = v[0], G = v[1], L = v[2], Z = v[3], beta = a.beta;
+}
+static __device__ __forceinline__ void pk_criteria_combine(double beta, const double *v, double *crit6) {
+    const double D = v[0], G = v[1], L = v[2], Z = v[3];
     crit6[0] = D + 0.5 * beta * G; crit6[1] = D; crit6[2] = L;
     crit6[3] = D + beta * G + Z; crit6[4] = Z; crit6[5] = G;
+}
+
+// ---- row shards, M-step: every rank stores its statistics (S, n and the number of its families
+// that moved) into its slot of every rank's staging area; after the cross-rank barrier every rank
+// adds the slots in RANK ORDER (integers: exact, and the same on every rank)
+static __device__ void pk_stats_publish(const nemk_persist_args &a, int changed_local) {
+    const int nstat = a.K * a.D + a.K;
+    const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int p = 0; p < a.world; p++) {
+        int32_t *dst = pk_peer<int32_t>(a, p, a.off_stat) + (size_t)a.rank * a.stat_len;
+        for (int q = gtid; q < nstat; q += nthreads) dst[q] = a.stat[q];
+        if (gtid == 0) dst[nstat] = changed_local;
+    }
+    __threadfence_system();
+}
+static __device__ int pk_stats_sum(const nemk_persist_args &a) {
+    const int nstat = a.K * a.D + a.K;
+    const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t *stage = pk_peer<int32_t>(a, a.rank, a.off_stat);
+    for (int q = gtid; q < nstat; q += nthreads) {
+        int v = 0;
+        for (int r = 0; r < a.world; r++) v += stage[(size_t)r * a.stat_len + q];
+        a.stat_glob[q] = v;
+    }
+    int changed = 0;
+    for (int r = 0; r < a.world; r++) changed += ((const volatile int32_t *)stage)[(size_t)r * a.stat_len + nstat];
+    return changed;
 }
 
 // =============================================================================================
@@ -1031,7 +1223,10 @@ k_em_persist(const nemk_persist_args a) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const unsigned nb = gridDim.x;
     nemk_lpsrc lps;
-    lps.logpf = nullptr; lps.ham = a.ham; lps.coef = a.coef; lps.wsum_any_order = a.wsum_any_order;
+    // (Hamming counts, margins and evaluation flags are stored for this rank's rows only; the host
+    // passes margin / evflag already shifted by -row0, the Hamming counts are shifted here, so that
+    // all of them are indexed by GLOBAL family id like the labels)
+    lps.logpf = nullptr; lps.ham = a.ham - (size_t)a.row0 * a.K; lps.coef = a.coef; lps.wsum_any_order = a.wsum_any_order;
     const bool use_graph = a.use_graph != 0, seq = a.seq_sweep != 0;
     const bool margins = seq && a.use_margins;
     int state = a.entry, it = a.iter0, cur = a.cur, stale_par = a.stale_par;
@@ -1042,6 +1237,10 @@ k_em_persist(const nemk_persist_args a) {
     int flags_stale = a.flags_stale;    // n_allnul / n_ties do not describe the last sweep yet
     int mu_changed = a.mu_changed;      // the class masks moved in the last tables (cached Hamming counts void)
     long long kept = 0;
+    const bool sharded = a.world > 1;
+    unsigned xepoch = a.xepoch;          // cross-rank barriers passed so far (all ranks count alike)
+    int xerr = 0, chg_local = a.chg_local, decide_pending = a.decide_pending;
+    const uint32_t *xg = a.x - (size_t)a.row0 * a.wpr;      // X row of GLOBAL family i = xg + i * wpr
     int exit_code = NEMK_PK_EXIT_DONE, resume = NEMK_PK_ENTRY_MSTEP, converged = 0, empty = 0;
     int n_allnul = a.n_allnul, n_ties = a.n_ties;
     PkProf prof;
@@ -1059,7 +1258,9 @@ k_em_persist(const nemk_persist_args a) {
     for (;;) {
         if (state == S_INIT) {
             // ---- prep: unlabelled state (the reference's calloc'd ClassifM), clean flags, presets
-            for (int i = gtid; i < (n + 3) / 4; i += nthreads) {
+            // (row shards: every rank clears its own copy of the whole-pangenome arrays)
+            const int n_all = sharded ? a.shard_len * a.world : n;
+            for (int i = gtid; i < (n_all + 3) / 4; i += nthreads) {
                 reinterpret_cast<uint32_t *>(a.lab[0])[i] = 0xffffffffu;
                 reinterpret_cast<uint32_t *>(a.stale[0])[i] = 0u;
                 reinterpret_cast<uint32_t *>(a.stale[1])[i] = 0u;
@@ -1072,8 +1273,15 @@ k_em_persist(const nemk_persist_args a) {
                 // the shared counters clean)
                 for (int q = 0; q < 8; q++) a.wl_cnt[q] = 0;
                 for (int q = 0; q < 16; q++) a.scratch[q] = 0;
+                if (sharded) for (int q = 0; q < a.world; q++) a.out_cnt[q] = 0;
             }
             PK_SYNC();
+            if (sharded) {
+                // no rank stores a label into a peer before every rank has left its previous fit
+                // and cleared its arrays
+                pk_xbarrier(a, xepoch, xerr); barriers += 2;
+                if (xerr) { exit_code = NEMK_PK_EXIT_PEER_TIMEOUT; break; }
+            }
             for (int k = blockIdx.x; k < K; k += gridDim.x) pk_tables_class<PK_THREADS>(k, a, sh);
             PK_SYNC();
             if (a.init_from_pop) {
@@ -1100,16 +1308,18 @@ k_em_persist(const nemk_persist_args a) {
             PK_MARK(prof, 0);
             state = S_BLIND;
         } else if (state == S_MSTEP) {
-            if (it >= a.it_max) break;
+            if (!decide_pending && it >= a.it_max) break;
             prof.trace = (gtid == 0 && it - a.iter0 < 12) ? a.out->trace[it - a.iter0] : nullptr;
-            // statistics of the labels lab[cur]: already updated by the scan (delta_mode 2), updated
-            // from the scan's list (1), or recounted
-            const bool incremental = !a.no_shortcuts && stats_valid && last_changed >= 0 && last_changed <= n / 8;
+            // statistics of the labels lab[cur]: already updated by the sweep (delta_mode 2), updated
+            // from the scan's list (1), or recounted.  Row shards always update from the list once a
+            // first recount exists (a uniform choice: every rank leaves the kernel, or none).
+            const int moved = sharded ? chg_local : last_changed;      // rows of THIS rank that moved
+            const bool incremental = !a.no_shortcuts && stats_valid && moved >= 0 && (sharded || moved <= n / 8);
             if (stats_valid && delta_mode == 2) {
                 // the sweep tracked its label moves: nothing left to do
             } else if (incremental && delta_mode == 1) {
-                mstep_delta_items<KT>(K, D, a.wpr, a.x, a.lab[cur], a.lab[cur ^ 1], a.wlist[1], last_changed,
-                                      a.stat, a.stat + (size_t)K * D);
+                mstep_delta_items<KT>(K, D, a.wpr, xg, a.lab[cur], a.lab[cur ^ 1], a.wlist[1], moved, a.stat,
+                                      a.stat + (size_t)K * D);
                 PK_SYNC();
                 PK_MARK(prof, 2);
             } else if (a.x_in_kernel) {
@@ -1128,6 +1338,24 @@ k_em_persist(const nemk_persist_args a) {
             state = S_FINALIZE;
         } else if (state == S_FINALIZE) {
             stats_valid = 1; delta_mode = 2;    // S and n describe lab[cur] (updated, recounted, or tracked)
+            if (sharded) {
+                // ---- the ranks' statistics meet: publish, cross-rank barrier, rank-ordered sum
+                pk_stats_publish(a, chg_local);
+                pk_xbarrier(a, xepoch, xerr); barriers += 2;
+                if (xerr) { exit_code = NEMK_PK_EXIT_PEER_TIMEOUT; break; }
+                const int chg_glob = pk_stats_sum(a);
+                PK_SYNC();
+                if (decide_pending) {        // the convergence test of the iteration whose sweep just ended
+                    decide_pending = 0;
+                    last_changed = chg_glob;
+                    it++;
+                    if (a.conv == 1) {
+                        const float md = last_changed ? 1.0f : 0.0f;
+                        if (md < a.conv_thr) { converged = 1; state = S_MSTEP; break; }
+                    }
+                    if (it >= a.it_max) { state = S_MSTEP; break; }
+                }
+            }
             for (int k = blockIdx.x; k < K; k += gridDim.x) pk_finalize_class<PK_THREADS>(k, a, sh, nkf, nkd);
             PK_SYNC();
             PK_MARK(prof, 4);
@@ -1173,9 +1401,11 @@ k_em_persist(const nemk_persist_args a) {
             // in atomics; kept as a compile-time knob)
             const bool track_ok = PK_TRACK && state == S_SWEEP && stats_valid && delta_mode == 2 &&
                                   it + 1 < a.it_max && last_changed >= 0 && last_changed <= PK_TRACK_MAX;
+            const int stale_next_buf = stale_par;       // after the flip above: index of mg.stale_next
             const bool tracked = pk_sweep<KT>(a, lps, blind ? 0.0 : a.beta, use_graph && !blind, seq && !blind,
-                                              a.lab[cur], a.lab[cur ^ 1], mg, cnt, cnt_next, s_w, s_l, barriers,
-                                              kept, nfix, prof, track_ok, mu_changed);
+                                              a.lab[cur], a.lab[cur ^ 1], cur ^ 1, mg, stale_next_buf, cnt, cnt_next,
+                                              s_w, s_l, barriers, kept, nfix, prof, track_ok, mu_changed, xepoch, xerr);
+            if (xerr) { exit_code = NEMK_PK_EXIT_PEER_TIMEOUT; break; }
             cur ^= 1;
             sweeps++;
             flags_stale = 1;
@@ -1193,8 +1423,8 @@ k_em_persist(const nemk_persist_args a) {
             } else {
                 // ---- the rows this sweep moved: count (convergence test), flags of the last
                 // evaluations, and the list the next M-step updates its statistics from
-                const int want = (it + 1 >= a.it_max || !stats_valid || a.no_shortcuts) ? 0 : 1;
-                pk_scan<KT>(a, a.lab[cur], a.lab[cur ^ 1], want, a.wlist[1], &a.wl_cnt[4]);
+                const int want = (sharded ? !stats_valid : (it + 1 >= a.it_max || !stats_valid)) || a.no_shortcuts ? 0 : 1;
+                pk_scan<KT>(a, a.lab[cur], a.lab[cur ^ 1], want, a.wlist[1], &a.wl_cnt[4], sharded ? (cur ^ 1) : -1);
                 PK_SYNC();
                 PK_MARK(prof, 1);
                 last_changed = *(volatile int32_t *)&a.wl_cnt[4];
@@ -1204,8 +1434,15 @@ k_em_persist(const nemk_persist_args a) {
                 delta_mode = want;
                 if (want == 0) stats_valid = 0;   // neither current nor one list away from it
             }
-            it++;
             state = S_MSTEP;
+            if (sharded) {
+                // the number of moved labels is this rank's: the test waits for the ranks' sum, which
+                // travels with the statistics (S_FINALIZE)
+                chg_local = last_changed;
+                decide_pending = 1;
+                continue;
+            }
+            it++;
             if (a.conv == 1) {   // HasConverged `clas` under ncem: no label changed
                 const float md = last_changed ? 1.0f : 0.0f;
                 if (md < a.conv_thr) { converged = 1; break; }
@@ -1215,7 +1452,7 @@ k_em_persist(const nemk_persist_args a) {
     if (exit_code == NEMK_PK_EXIT_DONE && flags_stale && sweeps > 0) {
         // all-null rows / exact ties of the last sweep: flags of every site's last evaluation
         // (scratch[3], [4] are zero: the sweep cleared them and no scan followed)
-        pk_scan<KT>(a, a.lab[cur], a.lab[cur], 0, nullptr, &a.wl_cnt[5]);
+        pk_scan<KT>(a, a.lab[cur], a.lab[cur], 0, nullptr, &a.wl_cnt[5], -1);
         PK_SYNC();
         n_allnul = *(volatile int32_t *)&a.scratch[3];
         n_ties = *(volatile int32_t *)&a.scratch[4];
@@ -1229,8 +1466,30 @@ k_em_persist(const nemk_persist_args a) {
     if (exit_code == NEMK_PK_EXIT_DONE && a.want_crit && it > 0) {
         pk_criteria_partial<KT>(a, lps, a.lab[cur], s_w, s_l, sh);
         PK_SYNC();
-        if (blockIdx.x == 0) pk_criteria_final(a, sh, crit6);
-        have_crit = 1;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (blockIdx.x == 0) pk_criteria_rank_sums(a, sh, v);
+        if (sharded) {
+            // the ranks' sums (and their all-null / tie counts) meet like the statistics do: slot of
+            // this rank in every rank's staging area, cross-rank barrier, rank-ordered sum
+            if (gtid == 0) {
+                for (int p = 0; p < a.world; p++) {
+                    double *dst = pk_peer<double>(a, p, a.off_crit) + (size_t)a.rank * 8;
+                    for (int q = 0; q < 4; q++) dst[q] = v[q];
+                    dst[4] = (double)n_allnul; dst[5] = (double)n_ties;
+                }
+                __threadfence_system();
+            }
+            pk_xbarrier(a, xepoch, xerr); barriers += 2;
+            if (xerr) exit_code = NEMK_PK_EXIT_PEER_TIMEOUT;
+            const volatile double *st = pk_peer<double>(a, a.rank, a.off_crit);
+            double w6[6] = {0, 0, 0, 0, 0, 0};
+            for (int r = 0; r < a.world; r++)
+                for (int q = 0; q < 6; q++) w6[q] += st[(size_t)r * 8 + q];
+            for (int q = 0; q < 4; q++) v[q] = w6[q];
+            n_allnul = (int)w6[4]; n_ties = (int)w6[5];
+        }
+        pk_criteria_combine(a.beta, v, crit6);
+        have_crit = exit_code == NEMK_PK_EXIT_DONE;
         PK_MARK(prof, 11);
     }
     if (gtid == 0) {
@@ -1242,6 +1501,7 @@ k_em_persist(const nemk_persist_args a) {
         o->cnt_par = cnt_par; o->delta_mode = delta_mode; o->flags_stale = flags_stale; o->mu_changed = mu_changed;
         o->cur = cur; o->stale_par = stale_par; o->last_changed = last_changed; o->stats_valid = stats_valid;
         o->n_allnul = n_allnul; o->n_ties = n_ties;
+        o->xepoch = xepoch; o->xerror = xerr; o->decide_pending = decide_pending; o->chg_local = chg_local;
         o->sweeps = sweeps; o->x_passes = x_passes; o->recounts = recounts; o->barriers = barriers;
         o->kept = kept; o->fixup_rounds = nfix;
         for (int q = 0; q < 12; q++) o->phase_ns[q] = prof.ns[q];

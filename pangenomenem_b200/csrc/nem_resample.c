@@ -186,6 +186,7 @@ typedef struct {
     int32_t *d_votes;
     int32_t *iters_out;
     int next;                 /* atomic run counter */
+    int pk_grid_limit;        /* CTAs a worker's persistent fit kernel may use */
     pthread_mutex_t mu;
     nemb_batch_stats st;
     char err[256];
@@ -197,6 +198,9 @@ static void *batch_worker(void *arg)
     nemb_handle *h = NULL;
     int rc = nemb_create(&h, c->src->device);
     if (rc == NEMB_OK && c->relaxed) { h->poll_relaxed = 1; prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0); }
+    /* the fits of concurrent workers are persistent cooperative kernels (one launch per fit): each
+     * takes its share of the SMs so that they run side by side instead of one after the other */
+    if (rc == NEMB_OK) h->pk_grid_limit = c->pk_grid_limit;
     float *theta = NULL;
     int cap_d = 0;
     nemb_batch_stats loc;
@@ -271,6 +275,11 @@ int nemb_resample_batch(nemb_handle *src, int n_runs, const uint32_t *genome_mas
     memset(&c, 0, sizeof c);
     c.src = src; c.n_runs = n_runs; c.wm = (src->d + 31) / 32; c.masks = genome_masks; c.betas = betas;
     c.opt = opt; c.edge_bits = edge_presence_dev; c.relaxed = relaxed; c.iters_out = iters_out; c.failed_rc = NEMB_OK;
+    {
+        const char *e = getenv("NEM_B200_BATCH_GRID");      /* CTAs per worker fit (0 = all) */
+        int total = nemk_persist_max_grid(opt->k);
+        c.pk_grid_limit = e && *e ? atoi(e) : (n_workers > 1 && total > 0 ? (total / n_workers < 16 ? 16 : total / n_workers) : 0);
+    }
     pthread_mutex_init(&c.mu, NULL);
     size_t vbytes = sizeof(int32_t) * 4 * (size_t)src->n;
     CK(cudaMalloc((void **)&c.d_votes, vbytes));

@@ -25,8 +25,12 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     report = []
-    for n, d, graph, algo, update in [(60001, 200, "pangenome", "ncem", "seq"),
+    # 64000 and 40000 families split on 16-family boundaries: the persistent row-sharded kernel
+    # (labels and requests through peer memory); 60001 does not: the launch-per-stage loop (NCCL)
+    for n, d, graph, algo, update in [(64000, 120, "pangenome", "ncem", "seq"),
+                                      (60001, 200, "pangenome", "ncem", "seq"),
                                       (40000, 96, "random", "ncem", "seq"),
+                                      (256000, 64, "pangenome", "ncem", "seq"),
                                       (30000, 64, "pangenome", "nem", "para")]:
         pg = synth.make_pangenome(n, d, seed=7, graph=graph)
         theta = synth.default_theta(3, d)
@@ -52,6 +56,8 @@ def main():
                   and all(abs(fit.crit[c] - ref.crit[c]) <= 1e-9 * abs(ref.crit[c]) for c in "UDL"))
             report.append(dict(n=n, d=d, graph=graph, algo=algo, update=update, world=world,
                                iters=fit.iters, ref_iters=ref.iters, exchanges=fit.exchanges,
+                               persistent_launches=fit.pk.get("launches"), barriers=fit.pk.get("barriers"),
+                               fit_ms=round(fit.fit_ms, 3), single_gpu_ms=round(ref.fit_ms, 3),
                                label_mismatches=int((lab != rlab).sum()), ok=bool(ok)))
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
