@@ -1269,9 +1269,11 @@ static int persist_eligible(nemb_handle *h, const nemb_options *o, int uniform0,
  * ranks call it with the same K and pangenome.  Returns NEMB_OK with h->xblk_ok = 0 when peer
  * memory is not available on this box (the caller then keeps the launch-per-stage loop; the
  * verdict is the same on every rank). */
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 static int ensure_xblk(nemb_handle *h, int k)
 {
     if (h->xblk_ok && h->xblk_k == k && h->xblk_lab_len == h->lab_len) return NEMB_OK;
+    const double t_begin = now_s();
     const int W = h->world;
     const size_t L = ((size_t)h->lab_len + 255) & ~(size_t)255;
     h->xcap = 1 << 16;
@@ -1321,6 +1323,15 @@ static int ensure_xblk(nemb_handle *h, int k)
         } else
             h->xpeer[p] = ptr;
     }
+    /* touch every peer block once from the host side of this context: the first access through a
+     * freshly opened mapping is slow (peer access is enabled lazily), and it must not happen inside
+     * the kernel, where a rank would keep its peers waiting at the first cross-rank barrier */
+    for (int p = 0; p < W && ok; p++) {
+        if (p == h->rank) continue;
+        unsigned probe = 0;
+        if (cudaMemcpyAsync(&probe, h->xpeer[p] + h->xoff[4], sizeof probe, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
     /* second round: every rank must have mapped every block */
     mine.ok = ok;
     CK(cudaMemcpyAsync(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
@@ -1330,6 +1341,9 @@ static int ensure_xblk(nemb_handle *h, int k)
     release(&tmp);
     for (int p = 0; p < W; p++) ok &= all[p].ok;
     h->xblk_ok = ok;
+    if (getenv("NEM_B200_DEBUG_SHARD"))
+        fprintf(stderr, "[nem_b200 rank %d] exchange blocks mapped: ok=%d, %.1f ms, %zu bytes\n", h->rank, ok,
+                1e3 * (now_s() - t_begin), off);
     h->xblk_k = k; h->xblk_lab_len = h->lab_len;
     h->pk_xepoch = 0;
     if (!ok)
@@ -1488,12 +1502,16 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         if (++guard > 4 * (o->it_max + 4)) return fail(h, NEMB_E_BUG, "persistent EM kernel keeps leaving");
         a.cnt_par = h->pk_cnt_par;
         a.seq = ++h->pk_seq;
+        const double t_launch = now_s();
         nemk_persist_launch(h->stream, &a, grid);
         h->launches++;
         res->pk_launches++;
         CKK();
         if ((rc = wait_persist(h, a.seq)) != NEMB_OK) return rc;
         memcpy(&out, (const void *)h->pk_out, sizeof out);
+        if (h->world > 1 && getenv("NEM_B200_DEBUG_SHARD"))
+            fprintf(stderr, "[nem_b200 rank %d] launch %d entry %d: %.2f ms, exit %d, epoch %u, %d barriers\n", h->rank,
+                    res->pk_launches, a.entry, 1e3 * (now_s() - t_launch), out.exit_code, out.xepoch, out.barriers);
         h->pk_cnt_par = out.cnt_par;
         /* the kernel counts SM cycles: convert with the SM clock (kHz) */
         if (!h->sm_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device); h->sm_khz = khz > 0 ? khz : 1965000; }
@@ -1511,7 +1529,9 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         res->n_allnul = out.n_allnul; res->n_ties = out.n_ties;
         h->pk_xepoch = out.xepoch;
         if (out.exit_code == NEMK_PK_EXIT_PEER_TIMEOUT || out.xerror)
-            return fail(h, NEMB_E_CUDA, "row-sharded fit: rank %d waited for a peer that never arrived", h->rank);
+            return fail(h, NEMB_E_CUDA, "row-sharded fit: rank %d waited for a peer that never arrived (epoch %u, "
+                        "iteration %d, %d sweeps and %d barriers into launch %d, entry %d)", h->rank, out.xepoch,
+                        out.iters, out.sweeps, out.barriers, res->pk_launches, a.entry);
         if (out.exit_code == NEMK_PK_EXIT_DONE) { done = 1; break; }
         a.entry = out.resume_entry; a.iter0 = out.iters; a.cur = out.cur; a.stale_par = out.stale_par;
         a.stats_valid = out.stats_valid; a.last_changed = out.last_changed;

@@ -82,6 +82,7 @@ static __device__ void pk_xbarrier(const nemk_persist_args &a, unsigned &epoch, 
         __threadfence_system();
         for (int p = 0; p < a.world; p++)
             if (p != a.rank) *(volatile unsigned *)(pk_peer<unsigned>(a, p, a.off_xflag) + a.rank) = epoch;
+        __threadfence_system();          // push the flags out before this thread starts polling
         volatile unsigned *mine = pk_peer<unsigned>(a, a.rank, a.off_xflag);
         const long long t0 = clock64();
         for (int q = 0; q < a.world; q++) {
@@ -574,6 +575,14 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
         cnt_next->changed = 0; cnt_next->nfix = 0; cnt_next->allnul = 0; cnt_next->ties = 0;
         cnt_next->maxdiff = 0.f; cnt_next->pending = 0; cnt_next->changed_glob = 0; cnt_next->kept = 0;
         if (may_skip) { if (prof.trace) prof.trace[6] = a.scratch[5]; a.scratch[5] = 0; }
+    }
+    if (sharded && !may_skip) {
+        // a dense round stored ALL labels into the peers: the fix-up rounds must not read a peer's
+        // family before its label of this round has arrived (a margin-cached round needs no such
+        // meeting: the peers' copies already hold the previous labels, and a label that moves
+        // comes with a request to re-evaluate its readers)
+        pk_xbarrier(a, xepoch, xerr); barriers += 2;
+        if (xerr) return false;
     }
 
     // ---- fix-up rounds: the listed sites are re-evaluated (duplicates allowed) until no label
@@ -1264,8 +1273,10 @@ k_em_persist(const nemk_persist_args a) {
                 reinterpret_cast<uint32_t *>(a.lab[0])[i] = 0xffffffffu;
                 reinterpret_cast<uint32_t *>(a.stale[0])[i] = 0u;
                 reinterpret_cast<uint32_t *>(a.stale[1])[i] = 0u;
-                reinterpret_cast<uint32_t *>(a.evflag)[i] = 0u;
             }
+            // (the evaluation flags exist for this rank's families only)
+            for (int i = gtid; i < (n + 3) / 4; i += nthreads)
+                reinterpret_cast<uint32_t *>(a.evflag + a.row0)[i] = 0u;
             mu_changed = 1;
             if (gtid == 0) {
                 a.coef->uniform_ok = 1; a.coef->mu_changed = 1; a.coef->empty_class = 0; a.coef->halt = 0;
@@ -1412,6 +1423,11 @@ k_em_persist(const nemk_persist_args a) {
             if (blind) { state = S_BETA0; continue; }
             margins_on = 1;   // the next sweep uses the same beta
             if (state == S_BETA0) {   // NemAlgo starts with a full recount: nothing to scan
+                if (sharded) {
+                    // ... but the peers' copies of the other label buffer must follow (pk_scan fix_buf)
+                    pk_scan<KT>(a, a.lab[cur], a.lab[cur ^ 1], 0, a.wlist[1], &a.wl_cnt[5], cur ^ 1);
+                    PK_SYNC();
+                }
                 last_changed = -1; delta_mode = 0;
                 state = S_MSTEP;
                 continue;

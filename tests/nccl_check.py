@@ -32,6 +32,10 @@ def main():
                                       (40000, 96, "random", "ncem", "seq"),
                                       (256000, 64, "pangenome", "ncem", "seq"),
                                       (30000, 64, "pangenome", "nem", "para")]:
+        only = os.environ.get("NCCL_CHECK_ONLY")
+        if only and str(n) not in only.split(","):
+            continue
+        print(f"[rank {rank}] case n={n} d={d} {graph} {algo} {update}", file=sys.stderr, flush=True)
         pg = synth.make_pangenome(n, d, seed=7, graph=graph)
         theta = synth.default_theta(3, d)
         kw = dict(k=3, algo=algo, update=update, disp="sk_", prop="pk", beta=0.5,
@@ -40,6 +44,7 @@ def main():
         xp = synth.pack_rows(pg.x)
         p = sharded.plan(n, world, rank)
         fit = sharded.fit_sharded(eng, xp[p.rows], n, d, pg.row_ptr, pg.col, pg.wgt, theta, rank, world, **kw)
+        print(f"[rank {rank}] fitted: iters={fit.iters} pk={fit.pk} ms={fit.fit_ms:.2f}", file=sys.stderr, flush=True)
         lab, t = eng.labels(), eng.posteriors()
         eng.close()
         capi.comm_destroy(comm)
