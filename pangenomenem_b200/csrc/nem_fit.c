@@ -129,7 +129,10 @@ int nemb_set_comm(nemb_handle *h, nemb_comm *comm)
 void nemb_shard_range(int n_glob, int world, int rank, int *shard_len, int *row0, int *n_loc)
 {
     if (world < 1) world = 1;
+    /* ceil(N / world) rounded up to 16 families when there are several ranks: a shard then starts on
+     * a 16-byte boundary of the label arrays (vector accesses of the persistent kernel) */
     int sl = (n_glob + world - 1) / world;
+    if (world > 1 && sl >= 1024) sl = (sl + 15) / 16 * 16;      /* (tiny pangenomes keep ceil(N / world)) */
     long long r0 = (long long)rank * sl;
     int nl = r0 >= n_glob ? 0 : (int)((long long)n_glob - r0 < sl ? (long long)n_glob - r0 : sl);
     if (shard_len) *shard_len = sl;
@@ -1286,7 +1289,7 @@ static int ensure_xblk(nemb_handle *h, int k)
     o[5] = (long long)carve(&off, sizeof(int32_t) * 2 * NEMK_PK_MAX_WORLD);        /* tot */
     o[6] = (long long)carve(&off, sizeof(int32_t) * 2 * NEMK_PK_MAX_WORLD);        /* incnt */
     o[7] = (long long)carve(&off, sizeof(int32_t) * 2 * (size_t)W * h->xcap);      /* inbox */
-    o[8] = (long long)carve(&off, sizeof(int32_t) * (size_t)W * h->xstat_len);     /* stat */
+    o[8] = (long long)carve(&off, sizeof(int32_t) * (size_t)h->xstat_len);         /* stat (this rank's) */
     o[9] = (long long)carve(&off, sizeof(double) * (size_t)W * 8);                 /* crit */
     /* drop the mappings of a previous layout */
     for (int p = 0; p < NEMK_PK_MAX_WORLD; p++) {
@@ -1446,6 +1449,8 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         a.off_xflag = h->xoff[4]; a.off_tot = h->xoff[5]; a.off_incnt = h->xoff[6]; a.off_inbox = h->xoff[7];
         a.off_stat = h->xoff[8]; a.off_crit = h->xoff[9];
         a.stat_len = h->xstat_len; a.out_cnt = h->d_pk_out_cnt; a.stat_glob = h->d_stat_int;
+        /* this rank's statistics live in its block (the peers read them after the M-step barrier) */
+        h->d_stat_loc = (int32_t *)(blk + h->xoff[8]);
         h->d_lab[0] = (uint8_t *)(blk + h->xoff[0]); h->d_lab[1] = (uint8_t *)(blk + h->xoff[1]);
         a.lab[0] = h->d_lab[0]; a.lab[1] = h->d_lab[1];
         a.stale[0] = (uint8_t *)(blk + h->xoff[2]); a.stale[1] = (uint8_t *)(blk + h->xoff[3]);

@@ -79,20 +79,21 @@ static __device__ void pk_xbarrier(const nemk_persist_args &a, unsigned &epoch, 
     pk_grid_sync(a.bar, gridDim.x);
     epoch++;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        __threadfence_system();
+        // (every thread that stored into a peer fenced at system scope itself, before the local
+        // barrier above: nothing of this rank is still in flight.  The flag goes out as a
+        // system-scope reduction -- a plain store may sit in a write buffer while this thread polls)
         for (int p = 0; p < a.world; p++)
-            if (p != a.rank) *(volatile unsigned *)(pk_peer<unsigned>(a, p, a.off_xflag) + a.rank) = epoch;
-        __threadfence_system();          // push the flags out before this thread starts polling
+            if (p != a.rank) atomicMax_system(pk_peer<unsigned>(a, p, a.off_xflag) + a.rank, epoch);
         volatile unsigned *mine = pk_peer<unsigned>(a, a.rank, a.off_xflag);
         const long long t0 = clock64();
         for (int q = 0; q < a.world; q++) {
             if (q == a.rank) continue;
             while ((int)(mine[q] - epoch) < 0) {
                 if (clock64() - t0 > 8000000000ll) { *(volatile int *)&a.scratch[13] = 1; break; }
-                __nanosleep(40);
             }
         }
-        __threadfence_system();
+        // what the peers stored lives in THIS rank's memory: dropping the SM's L1 (gpu-scope fence of
+        // the barrier below) is enough to read it
     }
     pk_grid_sync(a.bar, gridDim.x);
     if (*(volatile int *)&a.scratch[13]) xerr = 1;
@@ -113,7 +114,7 @@ static __device__ __forceinline__ void pk_push_stale(const nemk_persist_args &a,
 // this rank (parity = the super-round being built); counted locally, published at the barrier
 static __device__ __forceinline__ void pk_push_remote(const nemk_persist_args &a, int par, int j) {
     const int owner = j / a.shard_len;
-    const int slot = atomicAdd(&a.out_cnt[owner], 1);
+    const int slot = atomicAdd(pk_peer<int32_t>(a, a.rank, a.off_incnt) + par * NEMK_PK_MAX_WORLD + owner, 1);
     if (slot < a.xcap) {
         pk_peer<int32_t>(a, owner, a.off_inbox)[((size_t)par * a.world + a.rank) * a.xcap + slot] = j;
         __threadfence_system();
@@ -656,41 +657,49 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
             // ---- the ranks meet: requests sent to every rank (their inbox counts) and this rank's
             // total, stored into the peers' blocks; after the barrier every rank adds up the same
             // totals.  Nothing in flight anywhere = the sweep is over.
-            if (gtid == 0) {
-                const int over = *(volatile int32_t *)&a.scratch[12];
-                int sent = 0;
-                for (int p = 0; p < a.world; p++) {
-                    int c = *(volatile int32_t *)&a.out_cnt[p];
-                    if (c > a.xcap) c = a.xcap;
-                    if (p != a.rank) {
-                        sent += c;
-                        pk_peer<int32_t>(a, p, a.off_incnt)[par * NEMK_PK_MAX_WORLD + a.rank] = c;
-                    }
-                    a.out_cnt[p] = 0;
-                }
-                for (int p = 0; p < a.world; p++)
-                    pk_peer<int32_t>(a, p, a.off_tot)[par * NEMK_PK_MAX_WORLD + a.rank] = over ? -1 : sent;
-                a.scratch[12] = 0;
-                __threadfence_system();
-            }
+            // (counts stay in THIS rank's block -- row `par` of its out table, written by local
+            // atomics during the cascade -- and the peers read them after the barrier)
+            int32_t *my_out = pk_peer<int32_t>(a, a.rank, a.off_incnt) + par * NEMK_PK_MAX_WORLD;
+            if (gtid == 0 && *(volatile int32_t *)&a.scratch[12]) { my_out[a.rank] = -1; a.scratch[12] = 0; }
             pk_xbarrier(a, xepoch, xerr);
             barriers += 2;
             if (xerr) break;
-            const volatile int32_t *tot = pk_peer<int32_t>(a, a.rank, a.off_tot) + par * NEMK_PK_MAX_WORLD;
-            const volatile int32_t *inc = pk_peer<int32_t>(a, a.rank, a.off_incnt) + par * NEMK_PK_MAX_WORLD;
-            int total = 0, over = 0;
-            for (int q = 0; q < a.world; q++) { const int t = tot[q]; if (t < 0) over = 1; else total += t; }
+            // requests in flight anywhere (the same sum on every rank) and this rank's inbox counts:
+            // read through peer memory by ONE thread per CTA, handed to the others in shared memory
+            __shared__ int s_meet[NEMK_PK_MAX_WORLD + 2];
+            if (threadIdx.x == 0) {
+                int tot_ = 0, over_ = 0;
+                for (int q = 0; q < a.world; q++) {
+                    const int32_t *row = pk_peer<int32_t>(a, q, a.off_incnt) + par * NEMK_PK_MAX_WORLD;
+                    int mine_ = 0;
+                    for (int p = 0; p < a.world; p++) {
+                        int c = __ldcv(row + p);
+                        if (p == q) { if (c < 0) over_ = 1; continue; }
+                        if (c > a.xcap) c = a.xcap;
+                        tot_ += c;
+                        if (p == a.rank) mine_ = c;
+                    }
+                    s_meet[q] = q == a.rank ? 0 : mine_;
+                }
+                s_meet[NEMK_PK_MAX_WORLD] = tot_; s_meet[NEMK_PK_MAX_WORLD + 1] = over_;
+            }
+            __syncthreads();
+            const int total = s_meet[NEMK_PK_MAX_WORLD], over = s_meet[NEMK_PK_MAX_WORLD + 1];
+            int inc[NEMK_PK_MAX_WORLD];
+            for (int q = 0; q < NEMK_PK_MAX_WORLD; q++) inc[q] = q < a.world ? s_meet[q] : 0;
+            __syncthreads();
             if (total == 0 && !over) break;
             in_pref[0] = 0;
-            for (int q = 0; q < a.world; q++) in_pref[q + 1] = in_pref[q] + (q == a.rank ? 0 : inc[q]);
+            for (int q = 0; q < a.world; q++) in_pref[q + 1] = in_pref[q] + inc[q];
             for (int q = a.world; q < NEMK_PK_MAX_WORLD; q++) in_pref[q + 1] = in_pref[a.world];
             inbox_total = in_pref[a.world];
-            src_mode = over ? 2 : 1;
-            par ^= 1;            // == xepoch & 1: requests queued from now on go to the other inbox
-            if (inbox_total == 0 && !over) {
-                // nothing for this rank, but others work: it still takes part in the next meeting
-                src_mode = 0;
-            }
+            src_mode = over ? 2 : (inbox_total ? 1 : 0);   // nothing for this rank: it still meets again
+            // requests queued from now on go to the other inbox / counter row; that row was read by
+            // the peers two barriers ago at the latest
+            par ^= 1;
+            if (gtid == 0)
+                for (int q = 0; q < NEMK_PK_MAX_WORLD; q++) pk_peer<int32_t>(a, a.rank, a.off_incnt)[par * NEMK_PK_MAX_WORLD + q] = 0;
+            pk_grid_sync(a.bar, gridDim.x); barriers++;
         }
         PK_MARK(prof, 9);
         if (gtid == 0) {
@@ -1192,30 +1201,27 @@ static __device__ __forceinline__ void pk_criteria_combine(double beta, const do
     crit6[3] = D + beta * G + Z; crit6[4] = Z; crit6[5] = G;
 }
 
-// ---- row shards, M-step: every rank stores its statistics (S, n and the number of its families
-// that moved) into its slot of every rank's staging area; after the cross-rank barrier every rank
-// adds the slots in RANK ORDER (integers: exact, and the same on every rank)
-static __device__ void pk_stats_publish(const nemk_persist_args &a, int changed_local) {
-    const int nstat = a.K * a.D + a.K;
-    const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int p = 0; p < a.world; p++) {
-        int32_t *dst = pk_peer<int32_t>(a, p, a.off_stat) + (size_t)a.rank * a.stat_len;
-        for (int q = gtid; q < nstat; q += nthreads) dst[q] = a.stat[q];
-        if (gtid == 0) dst[nstat] = changed_local;
-    }
-    __threadfence_system();
-}
+// ---- row shards, M-step: every rank's statistics (S, n, and the number of its families that
+// moved) live in its exchange block; after the cross-rank barrier every rank reads all of them
+// through peer memory and adds them in RANK ORDER (integers: exact, the same on every rank).  A
+// rank changes its statistics again only after the next cross-rank barrier.
 static __device__ int pk_stats_sum(const nemk_persist_args &a) {
     const int nstat = a.K * a.D + a.K;
     const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int32_t *stage = pk_peer<int32_t>(a, a.rank, a.off_stat);
     for (int q = gtid; q < nstat; q += nthreads) {
         int v = 0;
-        for (int r = 0; r < a.world; r++) v += stage[(size_t)r * a.stat_len + q];
+        for (int r = 0; r < a.world; r++) v += __ldcv(pk_peer<int32_t>(a, r, a.off_stat) + q);
         a.stat_glob[q] = v;
     }
-    int changed = 0;
-    for (int r = 0; r < a.world; r++) changed += ((const volatile int32_t *)stage)[(size_t)r * a.stat_len + nstat];
+    __shared__ int s_changed;
+    if (threadIdx.x == 0) {
+        int changed = 0;
+        for (int r = 0; r < a.world; r++) changed += __ldcv(pk_peer<int32_t>(a, r, a.off_stat) + nstat);
+        s_changed = changed;
+    }
+    __syncthreads();
+    const int changed = s_changed;
+    __syncthreads();
     return changed;
 }
 
@@ -1284,7 +1290,8 @@ k_em_persist(const nemk_persist_args a) {
                 // the shared counters clean)
                 for (int q = 0; q < 8; q++) a.wl_cnt[q] = 0;
                 for (int q = 0; q < 16; q++) a.scratch[q] = 0;
-                if (sharded) for (int q = 0; q < a.world; q++) a.out_cnt[q] = 0;
+                if (sharded)
+                    for (int q = 0; q < 2 * NEMK_PK_MAX_WORLD; q++) pk_peer<int32_t>(a, a.rank, a.off_incnt)[q] = 0;
             }
             PK_SYNC();
             if (sharded) {
@@ -1350,11 +1357,16 @@ k_em_persist(const nemk_persist_args a) {
         } else if (state == S_FINALIZE) {
             stats_valid = 1; delta_mode = 2;    // S and n describe lab[cur] (updated, recounted, or tracked)
             if (sharded) {
-                // ---- the ranks' statistics meet: publish, cross-rank barrier, rank-ordered sum
-                pk_stats_publish(a, chg_local);
+                // ---- the ranks' statistics meet: cross-rank barrier, then a rank-ordered sum of every
+                // rank's block (this rank's a.stat IS its block's statistics area)
+                if (gtid == 0) a.stat[K * D + K] = chg_local;
                 pk_xbarrier(a, xepoch, xerr); barriers += 2;
                 if (xerr) { exit_code = NEMK_PK_EXIT_PEER_TIMEOUT; break; }
                 const int chg_glob = pk_stats_sum(a);
+                // the request counters of the last sweep's meetings: every peer read them before it
+                // came to the barrier above
+                if (gtid == 0)
+                    for (int q = 0; q < 2 * NEMK_PK_MAX_WORLD; q++) pk_peer<int32_t>(a, a.rank, a.off_incnt)[q] = 0;
                 PK_SYNC();
                 if (decide_pending) {        // the convergence test of the iteration whose sweep just ended
                     decide_pending = 0;

@@ -38,7 +38,8 @@ class ShardPlan:
 
 
 def plan(n_glob: int, world: int, rank: int) -> ShardPlan:
-    """Contiguous id ranges of ceil(N/world) families (the last ranks may hold fewer, even none).
+    """Contiguous id ranges of ceil(N/world) families, rounded up to 16 when world > 1 and a shard has 1024 families or more (the last
+    ranks may hold fewer, even none).
 
     Family ids follow chromosome order in PPanGGOLiN (node insertion order, ppanggolin.py:481-517),
     so contiguous ranges keep neighbours together and the cut is a few edges per boundary: this is
@@ -46,6 +47,8 @@ def plan(n_glob: int, world: int, rank: int) -> ShardPlan:
     if world < 1 or not 0 <= rank < world:
         raise ValueError(f"bad rank {rank} of {world}")
     shard_len = (n_glob + world - 1) // world
+    if world > 1 and shard_len >= 1024:
+        shard_len = (shard_len + 15) // 16 * 16      # shards start on 16-family boundaries
     row0 = min(rank * shard_len, n_glob)
     n_loc = max(0, min(shard_len, n_glob - rank * shard_len))
     return ShardPlan(n_glob, world, rank, shard_len, row0, n_loc)
@@ -54,7 +57,7 @@ def plan(n_glob: int, world: int, rank: int) -> ShardPlan:
 def cut_edges(row_ptr: np.ndarray, col: np.ndarray, world: int) -> int:
     """Directed CSR entries whose endpoints live on different ranks (halo size diagnostic)."""
     n = row_ptr.shape[0] - 1
-    shard_len = (n + world - 1) // world
+    shard_len = plan(n, world, 0).shard_len
     src = np.repeat(np.arange(n), np.diff(row_ptr))
     return int(np.count_nonzero(src // shard_len != col // shard_len))
 
