@@ -565,8 +565,11 @@ def main_ours(args):
     gen_s = time.time() - t0
     nnz = 0 if col is None else int(col.shape[0])
     theta0 = synth.default_theta(K, d)
-    opts = dict(k=K, algo="ncem", update="seq", beta=beta, conv="clas", conv_thr=1e-8,
-                it_max=100, prop="pk", disp="sk_", sweep_impl="auto")
+    opts = dict(k=K, algo=args.algo, update=args.update, beta=beta, conv="clas", conv_thr=1e-8,
+                it_max=100, prop="pk", disp=args.disp, sweep_impl="auto")
+    off_default = (args.algo, args.update, args.disp) != ("ncem", "seq", "sk_")
+    if off_default:
+        args.no_extras = True
 
     stream = torch.cuda.current_stream()
     comm = None
@@ -810,11 +813,12 @@ def main_ours(args):
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 popcount + f64 log-domain posteriors",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.workload) if n_glob == n else
-                       workload_name(args.workload).replace("%d families" % n, "%d families (%d per GPU, weak scaling)" % (n_glob, n)),
+            "config": {"workload": (workload_name(args.workload) if n_glob == n else
+                                    workload_name(args.workload).replace("%d families" % n, "%d families (%d per GPU, weak scaling)" % (n_glob, n))
+                                    ).replace("ncem seq bern pk sk_", "%s %s bern pk %s" % (args.algo, args.update, args.disp)),
                        "families": n_glob,
                        "families_per_gpu": n, "genomes": d, "K": K,
-                       "beta": beta, "algo": "ncem", "update": "seq", "nnz": nnz,
+                       "beta": beta, "algo": args.algo, "update": args.update, "dispersion": args.disp, "nnz": nnz,
                        "sweep_dag_depth": depth,
                        "em_iterations_per_fit": f.iters, "converged": f.converged,
                        "fixup_rounds_per_fit": f.fixup_rounds,
@@ -834,7 +838,9 @@ def main_ours(args):
                     "labels_equal_resident_fit": e2e_same,
                     "host_numa_binding": numa,
                     "what": "per rank: nemb_load_shard(host pinned X shard + global CSR: H2D, device-side graph validation) + nemb_fit + nemb_get_labels_rows(own families); *_per_step = summed over the ranks"},
-            "roofline": {"bound": "hbm", "kernel": "k_density_tma (E-step Bernoulli log-likelihood, popcount path)",
+            "roofline": {"bound": "hbm", "kernel": "k_density_tma (E-step Bernoulli log-likelihood, popcount path)"
+                         if args.disp in ("sk_", "s__") else
+                         "k_density_general (E-step Bernoulli log-likelihood, per-genome dispersions)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
@@ -909,6 +915,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip value_no_shortcuts / moving_centres / other_workloads / strong_scaling")
+    ap.add_argument("--algo", default="ncem", choices=["ncem", "nem"],
+                    help="off-default line: nem = fuzzy posteriors (k_sweep_nem_*, k_mstep_nem_*)")
+    ap.add_argument("--update", default="seq", choices=["seq", "para"])
+    ap.add_argument("--disp", default="sk_", choices=["s__", "sk_", "s_d", "skd"],
+                    help="off-default line: skd / s_d = per-genome dispersions (k_density_general; PPanGGOLiN -fd)")
     ap.add_argument("--runs", type=int, default=0, help="c5: number of independent fits (default 1024)")
     ap.add_argument("--workers", type=int, default=8, help="c5: worker streams per GPU")
     args = ap.parse_args()
