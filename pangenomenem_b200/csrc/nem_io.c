@@ -24,6 +24,7 @@
 #include <ctype.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <limits.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -165,6 +166,13 @@ int nemio_read_str(const char *base, FILE *err, char *type, int *n, int *d, char
         fprintf(err, "Structure file (%s) not enough fields\n", path);
         return NEMB_E_FILE;
     }
+    /* N and D are int in the engine's ABI (nem_exe.h:23-35): a header beyond that is an error,
+     * not a silent truncation */
+    for (int q = 0; q < nf; q++)
+        if (v[q] < 0 || v[q] > INT_MAX || (ty == 'I' && q == 1 && v[0] * v[1] > INT_MAX)) {
+            fprintf(err, "Structure file (%s): sizes out of range\n", path);
+            return NEMB_E_FILE;
+        }
     if (ty == 'I') {
         if (nf < 3) { fprintf(err, "Structure file (%s) not enough fields\n", path); return NEMB_E_FILE; }
         *type = 'I'; *n = (int)(v[0] * v[1]); *d = (int)v[2];
@@ -271,17 +279,18 @@ int nemio_read_dat(const char *path, FILE *err, int n, int d, int wpr, uint32_t 
         if (n_threads < 1) n_threads = 1;
         if (n_threads > 64) n_threads = 64;
         if (n < 4096) n_threads = 1;
-        pthread_t th[64]; dat_job jobs[64];
+        pthread_t th[64]; dat_job jobs[64]; int started[64];
         int rows = last_missing ? n - 1 : n;
         for (int t = 0; t < n_threads; t++) {
             jobs[t] = (dat_job){c.base, d, wpr, (int)((long long)rows * t / n_threads),
                                 (int)((long long)rows * (t + 1) / n_threads), out, 0};
-            if (n_threads > 1) pthread_create(&th[t], NULL, dat_worker, &jobs[t]);
-            else dat_worker(&jobs[t]);
+            /* a thread that cannot be created is run inline, like nei_read_lines does */
+            started[t] = n_threads > 1 && pthread_create(&th[t], NULL, dat_worker, &jobs[t]) == 0;
+            if (!started[t]) dat_worker(&jobs[t]);
         }
         int bad = 0;
         for (int t = 0; t < n_threads; t++) {
-            if (n_threads > 1) pthread_join(th[t], NULL);
+            if (started[t]) pthread_join(th[t], NULL);
             bad |= jobs[t].bad;
         }
         done = !bad && !last_missing;

@@ -669,6 +669,126 @@ k_density_general(int K, const uint32_t *__restrict__ x, int n, int D, int wpr,
 }
 
 // =============================================================================================
+// E-step density, general path, tiled (the default for skd / s_d / arbitrary .m when the delta
+// table fits shared memory).  DensBernoulli (nem_mod.c:619-690) summed as
+//   logf_ik = -(base_k + sum_{d: x_id = 1} delta_kd)
+// with LANES OVER FAMILIES and the genomes walked in ascending order: the delta row of a genome is
+// the same for every lane, so it comes out of shared memory as a broadcast (no divergent gathers --
+// the warp-per-family kernel above spends its time in 32-way divergent L1 accesses), and the sum
+// becomes K predicated fp64 adds per (family, genome).  A lane carries DG_R families so that one
+// broadcast feeds DG_R * K adds: the kernel is bound by the fp64 pipe, not by the load/store unit.
+// Shared memory: delta re-laid as [genome][KT] (zero beyond D).  fp64, fixed order (ascending d).
+// =============================================================================================
+template <int KT> struct DgR { static constexpr int R = KT <= 4 ? 4 : (KT <= 8 ? 2 : 1); };
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+k_density_general_tiled(int K, const uint32_t *__restrict__ x, int n, int D, int wpr,
+                        const nemk_coef *__restrict__ coef, const uint32_t *__restrict__ f0,
+                        const uint32_t *__restrict__ f1, const double *__restrict__ delta,
+                        const double *__restrict__ base_g, double *__restrict__ logpf) {
+    constexpr int R = DgR<KT>::R;
+    extern __shared__ __align__(16) double dg_sd[];          // [wreal * 32][KT]
+    __shared__ int s_forb, s_nonfin;
+    if (coef->empty_class | coef->halt) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int wreal = (D + 31) >> 5;
+    if (threadIdx.x == 0) { s_forb = 0; s_nonfin = 0; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < wreal * 32 * KT; idx += blockDim.x) {
+        int d = idx / KT, k = idx - d * KT;
+        const double dv = (d < D && k < K) ? delta[(size_t)k * D + d] : 0.0;
+        dg_sd[idx] = 0.5 * dv;                               // halved: see the fma below
+        if (!(fabs(dv) <= DBL_MAX)) s_nonfin = 1;
+    }
+    {   // does any class forbid a cell (eps = 0)?  almost never: the test is skipped then
+        unsigned any = 0;
+        for (int idx = threadIdx.x; idx < K * wpr; idx += blockDim.x) any |= f0[idx] | f1[idx];
+        if (any) s_forb = 1;
+    }
+    __syncthreads();
+    const bool forb = s_forb != 0, nonfin = s_nonfin != 0;
+    const long long ntiles = ((long long)n + 32 * R - 1) / (32 * R);
+    for (long long t = (long long)blockIdx.x * nw + warp; t < ntiles; t += (long long)gridDim.x * nw) {
+        const uint32_t *xr[R];
+        long long row[R];
+        double acc[R][KT];
+        unsigned nul[R], v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            row[r] = t * (32 * R) + r * 32 + lane;
+            xr[r] = x + (size_t)(row[r] < n ? row[r] : n - 1) * wpr;
+            nul[r] = 0u;
+            v[r] = xr[r][0];
+#pragma unroll
+            for (int k = 0; k < KT; k++) acc[r][k] = 0.0;
+        }
+        for (int w = 0; w < wreal; w++) {
+            const uint32_t live = (w == wreal - 1 && (D & 31)) ? ((1u << (D & 31)) - 1u) : FULL;
+            unsigned cur[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                cur[r] = v[r] & live;
+                if (w + 1 < wreal) v[r] = xr[r][w + 1];      // next word: in flight during the adds
+            }
+            if (forb) {
+                for (int k = 0; k < K; k++) {
+                    const uint32_t m0 = f0[k * wpr + w], m1 = f1[k * wpr + w];
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        if ((cur[r] & m1) | (~cur[r] & live & m0)) nul[r] |= 1u << k;
+                }
+            }
+            const double2 *sp = reinterpret_cast<const double2 *>(dg_sd + (size_t)w * 32 * KT);
+            if (nonfin) {       // a delta of +-inf (eps = 1 in a .m file): literal conditional adds
+#pragma unroll 1
+                for (int b = 0; b < 32; b++)
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        if ((cur[r] >> b) & 1u) {
+#pragma unroll
+                            for (int k = 0; k < KT; k++) acc[r][k] += 2.0 * dg_sd[((size_t)w * 32 + b) * KT + k];
+                        }
+                continue;
+            }
+#pragma unroll
+            for (int b = 0; b < 32; b += 2) {
+                double dd[2 * KT];                           // HALF the deltas of genomes b and b + 1
+#pragma unroll
+                for (int q = 0; q < KT; q++) {
+                    double2 t2 = sp[(b >> 1) * KT + q];
+                    dd[2 * q] = t2.x; dd[2 * q + 1] = t2.y;
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    // bit -> the double 2.0 or 0.0 (high word 0x40000000 or 0): the conditional add
+                    // becomes ONE fma(2 or 0, delta / 2, acc) on the fp64 pipe -- same value as
+                    // acc + delta, no select instructions (a select costs two per add)
+                    const unsigned h0 = (b <= 30 ? cur[r] << (30 - b) : cur[r] >> (b - 30)) & 0x40000000u;
+                    const unsigned h1 = (b + 1 <= 30 ? cur[r] << (29 - b) : cur[r] >> (b - 29)) & 0x40000000u;
+                    const double m0 = __hiloint2double((int)h0, 0), m1 = __hiloint2double((int)h1, 0);
+#pragma unroll
+                    for (int k = 0; k < KT; k++) {
+                        acc[r][k] = fma(m0, dd[k], acc[r][k]);
+                        acc[r][k] = fma(m1, dd[KT + k], acc[r][k]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (row[r] < n) {
+#pragma unroll
+                for (int k = 0; k < KT; k++)
+                    if (k < K)
+                        logpf[(size_t)row[r] * K + k] =
+                            ((nul[r] >> k) & 1u) ? neg_inf() : coef->lp[k] - (base_g[k] + acc[r][k]);
+            }
+        }
+    }
+}
+
+// =============================================================================================
 // E-step site update.  ComputeLocalProba (nem_alg.c:2546-2616) in the log domain,
 // SumNeighsOfClass (nem_alg.c:2850-2884), ComputeMAP first-max (nem_alg.c:603-615).
 // =============================================================================================
@@ -2693,12 +2813,62 @@ extern "C" void nemk_logpf_from_cache(nemk_stream s, int k, int n, const nemk_co
     note_launch();
 }
 
+// launches the tiled general density when its delta table fits shared memory; false = not launched
+template <int KT>
+static bool density_general_tiled_k(nemk_stream s, int k, const uint32_t *x, int n, int d, int wpr,
+                                    const nemk_coef *coef, const uint32_t *mask_f0,
+                                    const uint32_t *mask_f1, const double *delta,
+                                    const double *base_g, double *logpf) {
+    static int smem_max = -1, warp_only = -1;
+    if (warp_only < 0) { const char *e = getenv("NEM_B200_DENSITY_WARP"); warp_only = e && *e; }
+    if (warp_only) return false;
+    if (smem_max < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        smem_max = v;
+    }
+    const size_t smem = (size_t)((d + 31) / 32) * 32 * KT * sizeof(double);
+    if (smem + 1024 > (size_t)smem_max) return false;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        if (cudaFuncSetAttribute(k_density_general_tiled<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+        attr_set = smem;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_density_general_tiled<KT>, 256, smem)
+            != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
+    if (per_sm > 2) per_sm = 2;
+    constexpr int R = DgR<KT>::R;
+    long long ntiles = ((long long)n + 32 * R - 1) / (32 * R);
+    long long grid = (ntiles + 7) / 8;
+    if (grid > (long long)num_sms() * per_sm) grid = (long long)num_sms() * per_sm;
+    k_density_general_tiled<KT><<<(int)grid, 256, smem, S(s)>>>(k, x, n, d, wpr, coef, mask_f0, mask_f1,
+                                                               delta, base_g, logpf);
+    return true;
+}
+static bool density_general_tiled(nemk_stream s, int k, const uint32_t *x, int n, int d, int wpr,
+                                  const nemk_coef *coef, const uint32_t *mask_f0,
+                                  const uint32_t *mask_f1, const double *delta,
+                                  const double *base_g, double *logpf) {
+    bool ok = false;
+    DISPATCH_K(k, (ok = density_general_tiled_k<KT>(s, k, x, n, d, wpr, coef, mask_f0, mask_f1, delta,
+                                                    base_g, logpf)));
+    return ok;
+}
+
 extern "C" void nemk_density_general(nemk_stream s, int k, const uint32_t *x, int n, int d, int wpr,
                                      const nemk_coef *coef, const uint32_t *mask_f0,
                                      const uint32_t *mask_f1, const double *delta, double *logpf) {
     if (n <= 0) return;
     // delta[K*D] is followed by base_g[K] (written by k_theta_tables)
     const double *base_g = delta + (size_t)k * d;
+    if (density_general_tiled(s, k, x, n, d, wpr, coef, mask_f0, mask_f1, delta, base_g, logpf)) {
+        note_launch();
+        return;
+    }
+    // delta does not fit shared memory (or NEM_B200_DENSITY_WARP is set): warp-per-family walk
     int grid = cdiv((long long)n * 32, 256);
     int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
