@@ -792,7 +792,10 @@ def main_ours(args):
         ms_dc = sum(x.stage_ms["density_cached"] for x in fits) / max(n_dc, 1)
         n_md = sum(x.stage_launches["mstep_delta"] for x in fits)
         ms_md = sum(x.stage_ms["mstep_delta"] for x in fits) / max(n_md, 1)
-        traffic, traffic_src = measured_traffic("k_density_tma") if args.workload == "c4" and not args.rows else (None, None)
+        if args.disp in ("sk_", "s__"):
+            traffic, traffic_src = measured_traffic("k_density_tma") if args.workload == "c4" and not args.rows else (None, None)
+        else:
+            traffic, traffic_src = measured_traffic("k_density_general_tiled") if args.workload == "c3" and not args.rows else (None, None)
         den_bytes = n * wb + n * tk                      # SURVEY 8d "E-step-only bytes (density)"
         achieved = den_bytes / (ms_den * 1e-3) / 1e9 if ms_den > 0 else 0.0
         ms_bytes = n * wb + n * tk                       # M-step: X once + t once
@@ -840,12 +843,15 @@ def main_ours(args):
                     "what": "per rank: nemb_load_shard(host pinned X shard + global CSR: H2D, device-side graph validation) + nemb_fit + nemb_get_labels_rows(own families); *_per_step = summed over the ranks"},
             "roofline": {"bound": "hbm", "kernel": "k_density_tma (E-step Bernoulli log-likelihood, popcount path)"
                          if args.disp in ("sk_", "s__") else
-                         "k_density_general (E-step Bernoulli log-likelihood, per-genome dispersions)",
+                         "k_density_general_tiled (E-step Bernoulli log-likelihood, per-genome dispersions; bound by the "
+                         "fp64 pipe -- N*D*K fused multiply-adds per pass -- not by HBM: see fp64_tflops)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "bytes_per_launch": den_bytes, "avg_launch_ms": ms_den,
                          "launches_timed": n_den,
+                         "fp64_tflops": (2.0 * n * d * K / (ms_den * 1e-3) / 1e12 if ms_den > 0 else 0.0)
+                         if args.disp not in ("sk_", "s__") else None,
                          "note": ("achieved = algorithmic bytes of one X pass (N*Wb + N*K*4) / mean CUDA-event "
                                   "time of the launches that READ X; the iterations whose class centres did not "
                                   "move skip the pass and rebuild logpf from cached Hamming counts "

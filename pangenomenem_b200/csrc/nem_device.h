@@ -279,7 +279,7 @@ void nemk_sub_active(nemk_stream s, int n, int wpr, const uint32_t *x, const uin
                      int32_t *flag, int32_t *new_id, int32_t *block_tmp, int32_t *n_eff);
 /* x_new[new_id[i]] = the d_eff selected columns (cols[], ascending) of row i, re-packed; index */
 void nemk_sub_gather(nemk_stream s, int n, int wpr, int d_eff, int wpr_new, const uint32_t *x,
-                     const int32_t *cols, const int32_t *flag, const int32_t *new_id,
+                     const uint32_t *mask, const int32_t *flag, const int32_t *new_id,
                      uint32_t *x_new, int32_t *index);
 /* w_tmp[e] = popc(E_e & mask) (E = edge_bits, or x_i & x_j when NULL); cnt[n_cnt] kept entries per
  * NEW row; new_row_ptr[n_cnt+1] = their exclusive scan; *nnz_new, *maxdeg */

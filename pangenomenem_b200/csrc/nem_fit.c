@@ -598,7 +598,9 @@ static int ensure_t(nemb_handle *h, int k, int both)
 static int ensure_nem_scratch(nemb_handle *h, int k)
 {
     size_t kd = (size_t)k * h->d;
-    h->rows_per_chunk = 4096;
+    /* chunks of 1024 families (4096 beyond 512k: the partial sums are K*D doubles per chunk): with
+     * 512 genomes per CTA the grid needs that many chunks to fill the SMs */
+    h->rows_per_chunk = h->n <= (1 << 19) ? 1024 : 4096;
     h->nchunks = (h->n + h->rows_per_chunk - 1) / h->rows_per_chunk;
     if (h->nchunks < 1) h->nchunks = 1;
     size_t off = 0;

@@ -1999,51 +1999,77 @@ k_mstep_delta(int K, int D, int wpr, const uint32_t *__restrict__ x, const uint8
     mstep_delta_items<KT>(K, D, wpr, x, lab, lab_m, list, *count, S, nk);
 }
 
-// nem (fuzzy): partial sums over a chunk of families, thread = genome, fp64, fixed order.
+// nem (fuzzy): partial sums S_kd = sum_i t_ik x_id over a chunk of families, fp64, fixed order
+// (families ascending inside the chunk, chunks summed in order by k_mstep_nem_reduce).
+// Lanes over genomes: a CTA of 128 threads owns 512 genomes (16 words of the packed row); warp w
+// takes words 4w..4w+3 and lane b their bit b, so ONE broadcast 16-byte shared-memory load of the
+// row's words and K broadcast loads of the posteriors feed 4*K fused multiply-adds per thread.
+// The conditional add is fma(2 or 0, t/2, acc): the bit is rotated to position 30 of the high word
+// of a double (2.0 or 0.0), t is staged halved, so the value equals acc + t without a select.
 template <int KT>
 __global__ void __launch_bounds__(128)
 k_mstep_nem_partial(int K, int n, int D, int wpr, const uint32_t *__restrict__ x,
                     const float *__restrict__ t, int rows_per_chunk, double *__restrict__ partial_s,
                     double *__restrict__ partial_n) {
-    const int TILE = 128;  // families staged per pass
-    __shared__ float st[TILE * KT];
-    __shared__ uint32_t sx[TILE * 4];
+    constexpr int TILE = 128;   // families staged per pass
+    __shared__ __align__(16) double st[TILE * KT];       // t / 2
+    __shared__ __align__(16) uint32_t sx[TILE * 16];
     __shared__ double shn[4 * KT];
-    int chunk = blockIdx.x, db = blockIdx.y;
-    int r0 = chunk * rows_per_chunk, r1 = min(n, r0 + rows_per_chunk);
-    int d = db * 128 + threadIdx.x;
-    int w0 = db * 4;  // 128 genomes = 4 words
-    double acc[KT], accn[KT];
+    const int chunk = blockIdx.x, db = blockIdx.y;
+    const int r0 = chunk * rows_per_chunk, r1 = min(n, r0 + rows_per_chunk);
+    const int w0 = db * 16;     // 512 genomes = 16 words
+    const int wsel = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rot = (30 - lane) & 31;
+    double acc[4][KT], accn[KT];
 #pragma unroll
-    for (int k = 0; k < KT; k++) { acc[k] = 0.0; accn[k] = 0.0; }
+    for (int k = 0; k < KT; k++) {
+        accn[k] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[q][k] = 0.0;
+    }
     for (int base = r0; base < r1; base += TILE) {
-        int cnt = min(TILE, r1 - base);
+        const int cnt = min(TILE, r1 - base);
         __syncthreads();
-        for (int q = threadIdx.x; q < cnt * K; q += 128) st[(q / K) * KT + (q % K)] = t[(size_t)base * K + q];
-        for (int q = threadIdx.x; q < cnt * 4; q += 128) {
-            int r = q >> 2, w = w0 + (q & 3);
+        for (int q = threadIdx.x; q < cnt * KT; q += 128) {
+            int r = q / KT, k = q - r * KT;
+            st[q] = k < K ? 0.5 * (double)t[(size_t)(base + r) * K + k] : 0.0;
+        }
+        for (int q = threadIdx.x; q < cnt * 16; q += 128) {
+            int r = q >> 4, w = w0 + (q & 15);
             sx[q] = (w < wpr) ? x[(size_t)(base + r) * wpr + w] : 0u;
         }
         __syncthreads();
-        int wsel = threadIdx.x >> 5, b = threadIdx.x & 31;
+        const uint4 *sx4 = reinterpret_cast<const uint4 *>(sx) + wsel;
+#pragma unroll 4
         for (int r = 0; r < cnt; r++) {
-            unsigned bit = (sx[r * 4 + wsel] >> b) & 1u;
+            const uint4 xv = sx4[r * 4];
+            double td[KT];
 #pragma unroll
-            for (int k = 0; k < KT; k++)
-                if (bit && k < K) acc[k] += (double)st[r * KT + k];
+            for (int k = 0; k < KT; k++) td[k] = st[r * KT + k];
+            const uint32_t wv[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double m = __hiloint2double((int)(__funnelshift_l(wv[q], wv[q], rot) & 0x40000000u), 0);
+#pragma unroll
+                for (int k = 0; k < KT; k++) acc[q][k] = fma(m, td[k], acc[q][k]);
+            }
         }
         if (db == 0) {  // n_k partial: thread handles family base+threadIdx.x
             if (threadIdx.x < cnt) {
 #pragma unroll
                 for (int k = 0; k < KT; k++)
-                    if (k < K) accn[k] += (double)st[threadIdx.x * KT + k];
+                    if (k < K) accn[k] += 2.0 * st[threadIdx.x * KT + k];
             }
         }
     }
-    if (d < D) {
 #pragma unroll
-        for (int k = 0; k < KT; k++)
-            if (k < K) partial_s[((size_t)chunk * K + k) * D + d] = acc[k];
+    for (int q = 0; q < 4; q++) {
+        const int d = (w0 + wsel * 4 + q) * 32 + lane;
+        if (d < D) {
+#pragma unroll
+            for (int k = 0; k < KT; k++)
+                if (k < K) partial_s[((size_t)chunk * K + k) * D + d] = acc[q][k];
+        }
     }
     if (db == 0) {
         int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -3103,7 +3129,7 @@ extern "C" void nemk_mstep_nem(nemk_stream s, int k, int n, int d, int wpr, cons
                                const float *t, int rows_per_chunk, double *partial_s,
                                double *partial_n, double *s_dbl, double *nk_dbl) {
     int nchunks = cdiv(n, rows_per_chunk);
-    dim3 grid(nchunks, cdiv(d, 128));
+    dim3 grid(nchunks, cdiv(d, 512));
     DISPATCH_K(k, (k_mstep_nem_partial<KT><<<grid, 128, 0, S(s)>>>(k, n, d, wpr, x, t, rows_per_chunk,
                                                                   partial_s, partial_n)));
     note_launch();

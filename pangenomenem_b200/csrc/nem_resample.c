@@ -43,34 +43,32 @@ int nemb_subsample(nemb_handle *src, nemb_handle *h, const uint32_t *genome_mask
     const int n = src->n, D = src->d, wpr = src->wpr, nnz = src->spatial ? src->nnz : 0;
     const int wm = (D + 31) / 32;
 
-    /* host: padded mask + ascending list of the selected genomes */
+    /* host: padded mask (the ascending list of the selected genomes is implicit in it) */
     uint32_t *mask = calloc((size_t)wpr, sizeof(uint32_t));
-    int32_t *cols = malloc(sizeof(int32_t) * (size_t)D);
-    if (!mask || !cols) { free(mask); free(cols); return fail(h, NEMB_E_MEMORY, "host alloc"); }
+    if (!mask) return fail(h, NEMB_E_MEMORY, "host alloc");
     int d_eff = 0;
     for (int w = 0; w < wm; w++) {
         uint32_t m = genome_mask[w];
         if (w == wm - 1 && (D & 31)) m &= (1u << (D & 31)) - 1u;
         mask[w] = m;
-        for (int b = 0; b < 32; b++)
-            if ((m >> b) & 1u) cols[d_eff++] = w * 32 + b;
+        d_eff += __builtin_popcount(m);
     }
-    if (d_eff == 0) { free(mask); free(cols); return fail(h, NEMB_E_ARG, "nemb_subsample: empty genome mask"); }
+    if (d_eff == 0) { free(mask); return fail(h, NEMB_E_ARG, "nemb_subsample: empty genome mask"); }
     const int wpr_new = round_up4((d_eff + 31) / 32);
 
     /* scratch (sized by the SOURCE so that a worker handle never reallocates between samples) */
     const int nb = (n + 1023) / 1024 + 2;
     size_t off = 0;
-    size_t o_mask = carve(&off, sizeof(uint32_t) * wpr), o_cols = carve(&off, sizeof(int32_t) * D);
+    size_t o_mask = carve(&off, sizeof(uint32_t) * wpr);
     size_t o_flag = carve(&off, sizeof(int32_t) * n), o_id = carve(&off, sizeof(int32_t) * ((size_t)n + 1));
     size_t o_cnt = carve(&off, sizeof(int32_t) * ((size_t)n + 1)), o_blk = carve(&off, sizeof(int32_t) * nb);
     size_t o_tot = carve(&off, sizeof(int32_t) * 8), o_w = carve(&off, sizeof(float) * (size_t)(nnz ? nnz : 1));
     int rc;
-#define BAIL(code) do { free(mask); free(cols); return (code); } while (0)
+#define BAIL(code) do { free(mask); return (code); } while (0)
     if ((rc = nemb_i_reserve(h, &h->b_sub, off)) != NEMB_OK) BAIL(rc);
     char *base = h->b_sub.p;
     uint32_t *d_mask = (uint32_t *)(base + o_mask);
-    int32_t *d_cols = (int32_t *)(base + o_cols), *d_flag = (int32_t *)(base + o_flag);
+    int32_t *d_flag = (int32_t *)(base + o_flag);
     int32_t *d_id = (int32_t *)(base + o_id), *d_cnt = (int32_t *)(base + o_cnt);
     int32_t *d_blk = (int32_t *)(base + o_blk), *d_tot = (int32_t *)(base + o_tot);
     float *d_w = (float *)(base + o_w);
@@ -84,12 +82,10 @@ int nemb_subsample(nemb_handle *src, nemb_handle *h, const uint32_t *genome_mask
         if ((rc = nemb_i_reserve(h, &h->b_heavy, sizeof(int32_t) * (hl_blocks + (size_t)n + 1))) != NEMB_OK) BAIL(rc);
         if ((rc = nemb_i_reserve(h, &h->b_flags, 64)) != NEMB_OK) BAIL(rc);
     }
+    /* (pageable source: the runtime stages it before the call returns, so it can be freed at once) */
     cudaError_t ce = cudaMemcpyAsync(d_mask, mask, sizeof(uint32_t) * wpr, cudaMemcpyHostToDevice, h->stream);
-    if (ce == cudaSuccess)
-        ce = cudaMemcpyAsync(d_cols, cols, sizeof(int32_t) * d_eff, cudaMemcpyHostToDevice, h->stream);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(d_tot, 0, sizeof(int32_t) * 8, h->stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);   /* pageable staging can be freed */
-    free(mask); free(cols);
+    free(mask);
 #undef BAIL
     if (ce != cudaSuccess) return fail(h, NEMB_E_CUDA, "nemb_subsample upload: %s", cudaGetErrorString(ce));
 
@@ -97,15 +93,22 @@ int nemb_subsample(nemb_handle *src, nemb_handle *h, const uint32_t *genome_mask
     h->x_owned = 1;
     h->d_index = h->b_index.p;
     nemk_sub_active(h->stream, n, wpr, src->d_x, d_mask, d_flag, d_id, d_blk, &d_tot[0]);
-    nemk_sub_gather(h->stream, n, wpr, d_eff, wpr_new, src->d_x, d_cols, d_flag, d_id, h->d_x, h->d_index);
+    nemk_sub_gather(h->stream, n, wpr, d_eff, wpr_new, src->d_x, d_mask, d_flag, d_id, h->d_x, h->d_index);
     if (src->spatial) {
         nemk_sub_edges(h->stream, n, wpr, src->d_x, d_mask, edge_presence_dev, src->d_row_ptr, src->d_col,
                        d_flag, d_id, d_w, d_cnt, h->b_row_ptr.p, d_blk, &d_tot[1], &d_tot[2], n);
         nemk_sub_fill(h->stream, n, src->d_row_ptr, src->d_col, d_w, d_flag, d_id, h->b_row_ptr.p,
                       h->b_col.p, h->b_wgt.p);
     }
+    if (src->spatial) {
+        /* hub list of the new graph, over the OLD row count (the rows beyond n_eff have no entry):
+         * its size comes back with the totals in one synchronisation */
+        size_t hl_blocks = ((size_t)n + 1023) / 1024 + 1;
+        nemk_heavy_list(h->stream, 0, n, h->b_row_ptr.p, h->b_heavy.p, (int32_t *)h->b_heavy.p + hl_blocks,
+                        &d_tot[3]);
+    }
     CKK();
-    int32_t tot[3] = {0, 0, 0};
+    int32_t tot[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     const int n_eff = tot[0];
@@ -125,12 +128,7 @@ int nemb_subsample(nemb_handle *src, nemb_handle *h, const uint32_t *genome_mask
         h->d_rrow_ptr = h->d_row_ptr; h->d_rcol = h->d_col;
         size_t hl_blocks = ((size_t)n + 1023) / 1024 + 1;
         h->d_heavy = (int32_t *)h->b_heavy.p + hl_blocks;
-        nemk_heavy_list(h->stream, 0, n_eff, h->d_row_ptr, h->b_heavy.p, h->d_heavy, (int32_t *)h->b_flags.p);
-        CKK();
-        int32_t nh = 0;
-        CK(cudaMemcpyAsync(&nh, h->b_flags.p, sizeof nh, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        h->n_heavy = nh;
+        h->n_heavy = tot[3];
     }
     h->loaded = 1;
     if (n_eff_out) *n_eff_out = n_eff;
@@ -187,10 +185,33 @@ typedef struct {
     int32_t *iters_out;
     int next;                 /* atomic run counter */
     int pk_grid_limit;        /* CTAs a worker's persistent fit kernel may use */
+    int fit_slots, build_slots;   /* fits / subsample builds in flight at once (0 = no limit) */
+    int fits_now, builds_now;
+    pthread_mutex_t gate_mu;
+    pthread_cond_t gate_cv;
     pthread_mutex_t mu;
     nemb_batch_stats st;
     char err[256];
 } batch_ctx;
+
+/* counting gates: how many fits (persistent cooperative kernels that spin at device-wide barriers)
+ * and how many builders (bandwidth-bound grids of thousands of CTAs) share the GPU at a time */
+static void gate_enter(batch_ctx *c, int *now, int slots)
+{
+    if (slots <= 0) return;
+    pthread_mutex_lock(&c->gate_mu);
+    while (*now >= slots) pthread_cond_wait(&c->gate_cv, &c->gate_mu);
+    (*now)++;
+    pthread_mutex_unlock(&c->gate_mu);
+}
+static void gate_leave(batch_ctx *c, int *now, int slots)
+{
+    if (slots <= 0) return;
+    pthread_mutex_lock(&c->gate_mu);
+    (*now)--;
+    pthread_cond_broadcast(&c->gate_cv);
+    pthread_mutex_unlock(&c->gate_mu);
+}
 
 static void *batch_worker(void *arg)
 {
@@ -209,7 +230,9 @@ static void *batch_worker(void *arg)
         int r = __atomic_fetch_add(&c->next, 1, __ATOMIC_RELAXED);
         if (r >= c->n_runs) break;
         int n_eff = 0, d_eff = 0;
+        gate_enter(c, &c->builds_now, c->build_slots);
         rc = nemb_subsample(c->src, h, c->masks + (size_t)r * c->wm, c->edge_bits, &n_eff, &d_eff);
+        gate_leave(c, &c->builds_now, c->build_slots);
         if (rc != NEMB_OK) break;
         if (d_eff > cap_d) {
             free(theta);
@@ -223,7 +246,9 @@ static void *batch_worker(void *arg)
         if (c->betas) o.beta = c->betas[r];
         o.profile = 0; o.dolog = 0;
         nemb_result res;
+        gate_enter(c, &c->fits_now, c->fit_slots);
         int frc = nemb_fit(h, &o, prop, center, disp, &res);
+        gate_leave(c, &c->fits_now, c->fit_slots);
         int all_u = 0;
         if (frc == NEMB_W_EMPTYCLASS) { all_u = 1; loc.n_failed++; }   /* no .uf => all undefined */
         else if (frc != NEMB_OK) { rc = frc; break; }
@@ -276,10 +301,21 @@ int nemb_resample_batch(nemb_handle *src, int n_runs, const uint32_t *genome_mas
     c.src = src; c.n_runs = n_runs; c.wm = (src->d + 31) / 32; c.masks = genome_masks; c.betas = betas;
     c.opt = opt; c.edge_bits = edge_presence_dev; c.relaxed = relaxed; c.iters_out = iters_out; c.failed_rc = NEMB_OK;
     {
-        const char *e = getenv("NEM_B200_BATCH_GRID");      /* CTAs per worker fit (0 = all) */
+        /* fits in flight, builders in flight, CTAs per fit: a fit is latency-bound (device-wide
+         * barriers) and gains from running beside others on a share of the SMs; every resident fit
+         * CTA pins half an SM's registers while it spins, so the fits together get at most about
+         * half of the CTA slots and the builders of the other workers the rest */
+        const char *e = getenv("NEM_B200_BATCH_FITS");
         int total = nemk_persist_max_grid(opt->k);
-        c.pk_grid_limit = e && *e ? atoi(e) : (n_workers > 1 && total > 0 ? (total / n_workers < 16 ? 16 : total / n_workers) : 0);
+        c.fit_slots = e && *e ? atoi(e) : (n_workers > 1 ? 4 : 0);
+        e = getenv("NEM_B200_BATCH_BUILDS");
+        c.build_slots = e && *e ? atoi(e) : 0;
+        int conc = c.fit_slots > 0 && c.fit_slots < n_workers ? c.fit_slots : n_workers;
+        e = getenv("NEM_B200_BATCH_GRID");      /* CTAs per worker fit (0 = all) */
+        c.pk_grid_limit = e && *e ? atoi(e) : (conc > 1 && total > 0 ? (total / (2 * conc) < 16 ? 16 : total / (2 * conc)) : 0);
     }
+    pthread_mutex_init(&c.gate_mu, NULL);
+    pthread_cond_init(&c.gate_cv, NULL);
     pthread_mutex_init(&c.mu, NULL);
     size_t vbytes = sizeof(int32_t) * 4 * (size_t)src->n;
     CK(cudaMalloc((void **)&c.d_votes, vbytes));
@@ -290,6 +326,8 @@ int nemb_resample_batch(nemb_handle *src, int n_runs, const uint32_t *genome_mas
         if (pthread_create(&th[started], NULL, batch_worker, &c) == 0) started++;
     for (int w = 0; w < started; w++) pthread_join(th[w], NULL);
     pthread_mutex_destroy(&c.mu);
+    pthread_mutex_destroy(&c.gate_mu);
+    pthread_cond_destroy(&c.gate_cv);
     int rc = c.failed_rc;
     if (n_runs > 0 && started == 0) rc = fail(h, NEMB_E_BUG, "could not start a worker thread");
     else if (rc != NEMB_OK) fail(h, rc, "resample worker: %s", c.err);
