@@ -309,6 +309,8 @@ def main_c5(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()                   # settle the communicator first (see main_ours)
+        torch.cuda.synchronize()
     n, d, beta, graph = WORKLOADS["c5"]
     if args.rows:
         n = args.rows
@@ -515,6 +517,11 @@ def main_ours(args):
     import torch.distributed as dist
     from pangenomenem_b200 import capi, sharded, synth, synth_gpu
 
+    def trace(msg):      # NEM_BENCH_TRACE=1: where a multi-rank run is (stderr, with the device drained)
+        if os.environ.get("NEM_BENCH_TRACE"):
+            torch.cuda.synchronize()
+            print("[bench rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -530,6 +537,11 @@ def main_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        # settle the communicator (connections, peer mappings) before anything else touches the GPUs:
+        # at 8 ranks the first collective racing the data generation below died with an illegal
+        # memory access inside NCCL on this pool (three runs of three; never with these two lines)
+        dist.barrier()
+        torch.cuda.synchronize()
     mode = args.mode if world > 1 else "single"
 
     n, d, beta, graph = WORKLOADS[args.workload]
@@ -541,7 +553,10 @@ def main_ours(args):
 
     # ---- synthetic pangenome: X drawn + packed on the device, graph on the host
     t0 = time.time()
+    trace("process group up")
     xdev, _ = synth_gpu.make_packed_on_device(n, d, seed=42 + rank, device=dev)
+    torch.cuda.synchronize()
+    trace("X drawn")
     wpr = xdev.shape[1]
     xhost = torch.empty(xdev.shape, dtype=torch.int32, pin_memory=True)
     xhost.copy_(xdev)
@@ -561,6 +576,9 @@ def main_ours(args):
             row_ptr, col, wgt = synth_gpu.make_graph(n, xh, seed=42 + rank, kind=graph)
     else:
         row_ptr = col = wgt = None
+    trace("graph built")
+    if os.environ.get("NEM_BENCH_TRACE") == "graph":
+        return
     row_ptr, col, wgt = pinned(row_ptr), pinned(col), pinned(wgt)
     gen_s = time.time() - t0
     nnz = 0 if col is None else int(col.shape[0])
@@ -581,7 +599,9 @@ def main_ours(args):
         eng = capi.Engine(local)
         plan = sharded.plan(n, 1, 0)
     eng.set_stream(stream.cuda_stream)
+    trace("engine + communicator up")
     eng.load_shard_device(xdev.data_ptr(), n_glob, plan.row0, n, d, wpr, row_ptr, col, wgt)
+    trace("shard loaded")
     x_bytes = n * wpr * 4
     flush = None
     if x_bytes < 256 << 20:              # X fits the 126 MB L2: flush between timed steps
@@ -597,6 +617,7 @@ def main_ours(args):
 
     for _ in range(args.warmup):
         one_fit(False)
+        trace("warm-up fit done")
     lab_warm = eng.labels()              # the timed fits below must reproduce these labels
     barrier()
     sampler = ClockSampler(local)

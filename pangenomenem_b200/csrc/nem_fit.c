@@ -1371,7 +1371,7 @@ static int ensure_persist(nemb_handle *h)
     size_t o_wl0 = carve(&off, sizeof(int32_t) * cap), o_wl1 = carve(&off, sizeof(int32_t) * cap);
     size_t o_evf = carve(&off, (size_t)h->n + 64);
     size_t o_hub = carve(&off, sizeof(int32_t) * 4);
-    size_t o_scr = carve(&off, sizeof(int32_t) * 16);
+    size_t o_scr = carve(&off, sizeof(int32_t) * 64);      /* [16..23]: heartbeat of the row-sharded kernel */
     size_t o_cnt = carve(&off, sizeof(nemk_counters) * 2);
     size_t o_bar = carve(&off, sizeof(unsigned) * 4);
     size_t o_crit = carve(&off, sizeof(double) * 4 * 2048);
@@ -1401,8 +1401,26 @@ static int ensure_persist(nemb_handle *h)
 static int wait_persist(nemb_handle *h, unsigned long long seq)
 {
     volatile nemk_persist_out *s = h->pk_out;
+    const double t_wait = h->world > 1 ? now_s() : 0.0;
+    int reported = 0;
     for (unsigned spins = 1; s->seq != seq; spins++) {
         if ((spins & 0xfff) == 0) {
+            if (h->world > 1 && !reported && now_s() - t_wait > 3.0) {
+                /* a row-sharded kernel that has not come back after 3 s: say where it is (the
+                 * heartbeat words of its scratch block, read on a side stream while it runs) */
+                int32_t hb[24];
+                cudaStream_t side = NULL;
+                reported = 1;
+                if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess) {
+                    if (cudaMemcpyAsync(hb, h->d_pk_scratch, sizeof hb, cudaMemcpyDeviceToHost, side) == cudaSuccess &&
+                        cudaStreamSynchronize(side) == cudaSuccess)
+                        fprintf(stderr, "[nem_b200 rank %d] persistent kernel still running after 3 s: round %d, items %d, "
+                                "source %d, cascade epoch %d, barrier entered %d / passed %d, timeout word %d\n", h->rank,
+                                hb[16], hb[17], hb[18], hb[19], hb[20], hb[21], hb[13]);
+                    cudaStreamDestroy(side);
+                }
+                cudaGetLastError();
+            }
             cudaError_t e = cudaStreamQuery(h->stream);
             if (e != cudaSuccess && e != cudaErrorNotReady)
                 return fail(h, NEMB_E_CUDA, "device error inside the persistent EM kernel: %s", cudaGetErrorString(e));
@@ -1537,8 +1555,10 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
         h->pk_xepoch = out.xepoch;
         if (out.exit_code == NEMK_PK_EXIT_PEER_TIMEOUT || out.xerror)
             return fail(h, NEMB_E_CUDA, "row-sharded fit: rank %d waited for a peer that never arrived (epoch %u, "
-                        "iteration %d, %d sweeps and %d barriers into launch %d, entry %d)", h->rank, out.xepoch,
-                        out.iters, out.sweeps, out.barriers, res->pk_launches, a.entry);
+                        "iteration %d, %d sweeps and %d barriers into launch %d, entry %d; missing rank %d whose "
+                        "epoch flag here read %d)", h->rank, out.xepoch,
+                        out.iters, out.sweeps, out.barriers, res->pk_launches, a.entry,
+                        (out.xerror >> 4) & 15, (out.xerror >> 8) & 0xfffff);
         if (out.exit_code == NEMK_PK_EXIT_DONE) { done = 1; break; }
         a.entry = out.resume_entry; a.iter0 = out.iters; a.cur = out.cur; a.stale_par = out.stale_par;
         a.stats_valid = out.stats_valid; a.last_changed = out.last_changed;

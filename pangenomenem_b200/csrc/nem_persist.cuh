@@ -79,6 +79,7 @@ static __device__ void pk_xbarrier(const nemk_persist_args &a, unsigned &epoch, 
     pk_grid_sync(a.bar, gridDim.x);
     epoch++;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *(volatile int *)&a.scratch[20] = (int)epoch;       // heartbeat: barrier entered
         // (every thread that stored into a peer fenced at system scope itself, before the local
         // barrier above: nothing of this rank is still in flight.  The flag goes out as a
         // system-scope reduction -- a plain store may sit in a write buffer while this thread polls)
@@ -89,14 +90,18 @@ static __device__ void pk_xbarrier(const nemk_persist_args &a, unsigned &epoch, 
         for (int q = 0; q < a.world; q++) {
             if (q == a.rank) continue;
             while ((int)(mine[q] - epoch) < 0) {
-                if (clock64() - t0 > 8000000000ll) { *(volatile int *)&a.scratch[13] = 1; break; }
+                if (clock64() - t0 > 8000000000ll) {     // who was missing and what its flag said (diagnostics)
+                    *(volatile int *)&a.scratch[13] = 1 | (q << 4) | (int)((mine[q] & 0xfffffu) << 8);
+                    break;
+                }
             }
         }
         // what the peers stored lives in THIS rank's memory: dropping the SM's L1 (gpu-scope fence of
         // the barrier below) is enough to read it
+        *(volatile int *)&a.scratch[21] = (int)epoch;       // heartbeat: barrier passed
     }
     pk_grid_sync(a.bar, gridDim.x);
-    if (*(volatile int *)&a.scratch[13]) xerr = 1;
+    if (*(volatile int *)&a.scratch[13]) xerr = *(volatile int *)&a.scratch[13];
 }
 // label of own family i := km in the label buffer `buf` of every OTHER rank
 static __device__ __forceinline__ void pk_push_label(const nemk_persist_args &a, int buf, int i, int km) {
@@ -609,6 +614,10 @@ static __device__ bool pk_sweep(const nemk_persist_args &a, const nemk_lpsrc &lp
                     count = inbox_total;
                 if (gtid == 0) { wl_cnt[(round + 2) & 3] = 0; ovf[(round + 2) & 3] = 0; }
                 const int items = all ? n : count;
+                if (sharded && gtid == 0) {                 // heartbeat (read by the host if the fit hangs)
+                    *(volatile int *)&a.scratch[16] = round; *(volatile int *)&a.scratch[17] = items;
+                    *(volatile int *)&a.scratch[18] = all ? 2 : src_mode; *(volatile int *)&a.scratch[19] = (int)xepoch;
+                }
                 if (items == 0) break;
                 rounds++;
                 const int32_t *inbox = pk_peer<int32_t>(a, a.rank, a.off_inbox) + (size_t)(par ^ 1) * a.world * a.xcap;
