@@ -827,9 +827,12 @@ def main_ours(args):
         cpu = cpu_baseline(args.workload, 1) if (world == 1 and not args.no_cpu) else None
         multi = {"single": "single GPU",
                  "sharded": ("ONE pangenome of %d families row-sharded over %d GPUs (%d per GPU): X sharded, "
-                             "graph/theta/labels replicated; per iteration one all-gather of the M-step "
-                             "statistics and label all-gathers inside the exact sequential sweep (NCCL)"
-                             % (n_glob, world, n)),
+                             "graph/theta/labels replicated; " % (n_glob, world, n)) +
+                            ("moved labels, re-evaluation requests and the M-step statistics travel through NVLink "
+                             "peer memory inside the persistent kernel (cross-rank epoch barriers, no collective call)"
+                             if (f.pk and f.pk.get("launches")) else
+                             "per iteration one all-gather of the M-step statistics and label all-gathers inside "
+                             "the exact sequential sweep (NCCL; the peer-memory kernel serves up to 4 ranks)"),
                  "replicas": "independent replicas, one per GPU, no communication"}[mode]
         line = {
             "metric": "NEM family-iterations/s", "value": value, "unit": "family-iterations/s",

@@ -691,6 +691,14 @@ static int ensure_pop(nemb_handle *h)
 }
 
 /* ------------------------------------------------------------------ environment knobs */
+/* Verified on real NVLink boxes at 2 and 4 ranks (tests/nccl_check.py, bench strong_scaling:
+ * identical to the single-GPU fit).  At 8 ranks the C4-sized fit hung in its first beta sweep
+ * (profiles/r2_8gpu_hang.txt: two ranks never reached cross-rank barrier 6, each stuck at a LOCAL
+ * barrier of a fix-up round, i.e. the CTAs of a rank disagreed on a round's item count); until
+ * that is understood, 8 ranks take the NCCL protocol of the launch-per-stage loop. */
+#ifndef PK_SHARD_MAX_WORLD_DEFAULT
+#define PK_SHARD_MAX_WORLD_DEFAULT 4
+#endif
 static int env_flag(const char *name) { const char *e = getenv(name); return e && *e; }
 static void read_env_knobs(nemb_handle *h)
 {
@@ -709,6 +717,11 @@ static void read_env_knobs(nemb_handle *h)
     if (h->no_shortcuts) { h->no_margins = 1; h->full_mstep = 1; h->no_popcache = 1; }
     e = getenv("NEM_B200_MEDIUM_LIST");
     h->medium_list = e && *e ? atoi(e) : 32768;
+    /* largest world size the peer-memory kernel serves (beyond it: the NCCL protocol of the
+     * launch-per-stage loop) */
+    e = getenv("NEM_B200_PERSIST_SHARD_MAX");
+    h->pk_shard_max_world = e && *e ? atoi(e) : PK_SHARD_MAX_WORLD_DEFAULT;
+    if (h->pk_shard_max_world > NEMK_PK_MAX_WORLD) h->pk_shard_max_world = NEMK_PK_MAX_WORLD;
     e = getenv("NEM_B200_PK_GRID");
     h->pk_grid_env = e && *e ? atoi(e) : 0;
     e = getenv("NEM_B200_PK_XLIMIT");           /* bytes of X the in-kernel X / X^T passes accept */
@@ -1259,7 +1272,7 @@ static int persist_eligible(nemb_handle *h, const nemb_options *o, int uniform0,
         /* row shards: the ranks' kernels wait on each other through peer memory, so every rank must
          * own a GPU (NCCL communicator = one process per GPU), the shards must start on 16-family
          * boundaries (vector label accesses), and the sweep must be the sequential one */
-        if (h->no_persist_shard || h->world > NEMK_PK_MAX_WORLD || !nemb_i_comm_is_nccl(h->comm)) return 0;
+        if (h->no_persist_shard || h->world > h->pk_shard_max_world || !nemb_i_comm_is_nccl(h->comm)) return 0;
         if (h->shard_len % 16 || !h->spatial || o->update != NEMB_UPDATE_SEQ) return 0;
     }
     if (o->algo != NEMB_ALGO_NCEM || o->param_fixed || o->conv == NEMB_CONV_CRIT) return 0;

@@ -73,7 +73,7 @@ def test_density_popcount_path(engine, oracle, d):
         assert rel_close(got, pb.logpf(*theta), RTOL)
 
 
-@pytest.mark.parametrize("k,d", [(3, 70), (2, 33), (5, 500), (3, 1000), (9, 40)])
+@pytest.mark.parametrize("k,d", [(3, 70), (2, 33), (5, 500), (3, 1000), (9, 40), (3, 5000), (4, 2500), (8, 3000)])
 def test_density_general_path(engine, oracle, k, d):
     n = 500
     pg = make_case(n, d, seed=d + k, graph="none")
