@@ -169,7 +169,7 @@ void nemb_destroy(nemb_handle *h)
     if (h->h_empty) cudaFreeHost(h->h_empty);
     if (h->ring) cudaFreeHost(h->ring);
     if (h->pk_out) cudaFreeHost(h->pk_out);
-    for (int p = 0; p < NEMK_PK_MAX_WORLD; p++) if (h->xpeer[p] && p != h->rank) cudaIpcCloseMemHandle(h->xpeer[p]);
+    for (int p = 0; p < NEMK_PK_MAX_WORLD; p++) if (h->xpeer[p] && p != h->rank && !h->xpeer_local) cudaIpcCloseMemHandle(h->xpeer[p]);
     if (h->b_xblk.p) cudaFree(h->b_xblk.p);
     if (h->h_lab_stage) cudaFreeHost(h->h_lab_stage);
     if (h->h_theta_stage) cudaFreeHost(h->h_theta_stage);
@@ -719,6 +719,7 @@ static void read_env_knobs(nemb_handle *h)
     h->medium_list = e && *e ? atoi(e) : 32768;
     /* largest world size the peer-memory kernel serves (beyond it: the NCCL protocol of the
      * launch-per-stage loop) */
+    h->persist_local = env_flag("NEM_B200_PERSIST_LOCAL");
     e = getenv("NEM_B200_PERSIST_SHARD_MAX");
     h->pk_shard_max_world = e && *e ? atoi(e) : PK_SHARD_MAX_WORLD_DEFAULT;
     if (h->pk_shard_max_world > NEMK_PK_MAX_WORLD) h->pk_shard_max_world = NEMK_PK_MAX_WORLD;
@@ -1272,7 +1273,11 @@ static int persist_eligible(nemb_handle *h, const nemb_options *o, int uniform0,
         /* row shards: the ranks' kernels wait on each other through peer memory, so every rank must
          * own a GPU (NCCL communicator = one process per GPU), the shards must start on 16-family
          * boundaries (vector label accesses), and the sweep must be the sequential one */
-        if (h->no_persist_shard || h->world > h->pk_shard_max_world || !nemb_i_comm_is_nccl(h->comm)) return 0;
+        /* (NEM_B200_PERSIST_LOCAL=1, debugging only: the in-process test communicator too -- all its
+         * ranks share ONE device, so every rank's cooperative grid gets 1/world of the CTA slots and
+         * the kernels can wait on each other only if all of them are resident at once) */
+        if (h->no_persist_shard || h->world > h->pk_shard_max_world) return 0;
+        if (!nemb_i_comm_is_nccl(h->comm) && !h->persist_local) return 0;
         if (h->shard_len % 16 || !h->spatial || o->update != NEMB_UPDATE_SEQ) return 0;
     }
     if (o->algo != NEMB_ALGO_NCEM || o->param_fixed || o->conv == NEMB_CONV_CRIT) return 0;
@@ -1308,19 +1313,22 @@ static int ensure_xblk(nemb_handle *h, int k)
     o[9] = (long long)carve(&off, sizeof(double) * (size_t)W * 8);                 /* crit */
     /* drop the mappings of a previous layout */
     for (int p = 0; p < NEMK_PK_MAX_WORLD; p++) {
-        if (h->xpeer[p] && p != h->rank) cudaIpcCloseMemHandle(h->xpeer[p]);
+        if (h->xpeer[p] && p != h->rank && !h->xpeer_local) cudaIpcCloseMemHandle(h->xpeer[p]);
         h->xpeer[p] = NULL;
     }
     h->xblk_ok = 0;
+    h->xpeer_local = !nemb_i_comm_is_nccl(h->comm);
     CK(cudaStreamSynchronize(h->stream));
     if (h->b_xblk.p) { cudaFree(h->b_xblk.p); h->b_xblk.p = NULL; h->b_xblk.cap = 0; }
     CK(cudaMalloc(&h->b_xblk.p, off));
     h->b_xblk.cap = off; h->xblk_bytes = off;
     CK(cudaMemsetAsync(h->b_xblk.p, 0, off, h->stream));
     /* handles (and a go/no-go flag) travel through the communicator's all-gather */
-    struct { cudaIpcMemHandle_t hd; int ok; int pad[15]; } mine, all[NEMK_PK_MAX_WORLD];
+    struct { cudaIpcMemHandle_t hd; int ok; int pad; void *raw; int pad2[12]; } mine, all[NEMK_PK_MAX_WORLD];
+    const int local = !nemb_i_comm_is_nccl(h->comm);     /* one process, one device: plain pointers */
     memset(&mine, 0, sizeof mine);
-    mine.ok = cudaIpcGetMemHandle(&mine.hd, h->b_xblk.p) == cudaSuccess;
+    mine.raw = h->b_xblk.p;
+    mine.ok = local ? 1 : cudaIpcGetMemHandle(&mine.hd, h->b_xblk.p) == cudaSuccess;
     if (!mine.ok) cudaGetLastError();
     dbuf tmp = {NULL, 0};
     int rc = reserve(h, &tmp, sizeof mine * (size_t)(W + 1));
@@ -1335,6 +1343,7 @@ static int ensure_xblk(nemb_handle *h, int k)
     for (int p = 0; p < W && ok; p++) {
         if (p == h->rank) { h->xpeer[p] = h->b_xblk.p; continue; }
         void *ptr = NULL;
+        if (local) { h->xpeer[p] = all[p].raw; continue; }
         if (cudaIpcOpenMemHandle(&ptr, all[p].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
             cudaGetLastError();
             ok = 0;
@@ -1366,7 +1375,7 @@ static int ensure_xblk(nemb_handle *h, int k)
     h->pk_xepoch = 0;
     if (!ok)
         for (int p = 0; p < W; p++) {
-            if (h->xpeer[p] && p != h->rank) cudaIpcCloseMemHandle(h->xpeer[p]);
+            if (h->xpeer[p] && p != h->rank && !h->xpeer_local) cudaIpcCloseMemHandle(h->xpeer[p]);
             h->xpeer[p] = NULL;
         }
     return NEMB_OK;
@@ -1529,9 +1538,16 @@ static int em_persist(nemb_handle *h, const nemb_options *o, int uniform0, nemb_
     if (want < 16) want = 16;
     if (h->pk_grid_limit > 0 && want > h->pk_grid_limit) want = h->pk_grid_limit;
     if (h->pk_grid_env > 0) want = h->pk_grid_env;
+    if (h->world > 1 && h->xpeer_local && want > grid / h->world) want = grid / h->world;   /* ranks share the device */
     if (grid > want) grid = want;
     if (grid > 2048) grid = 2048;      /* d_pk_crit rows */
     if (grid < 1) grid = 1;
+    if (h->world > 1 && h->xpeer_local) {
+        /* one-device debugging mode: the ranks' kernels can only meet if they are resident together,
+         * so the host threads line up first (a collective on the test communicator + a drained stream) */
+        if ((rc = gather(h, &h->d_status->cnt, h->d_cnt_all, sizeof(nemk_counters))) != NEMB_OK) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+    }
     int done = 0, guard = 0;
     memset(h->pk_phase_ns, 0, sizeof h->pk_phase_ns);
     nemk_persist_out out;

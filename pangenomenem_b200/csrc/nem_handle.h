@@ -114,6 +114,7 @@ struct nemb_handle {
     int pk_cnt_par, pk_ready_n, pk_ready_heavy;
     long long pk_trace[12][8];            /* per-iteration trace of the LAST launch of the last fit */
     unsigned long long pk_phase_ns[12];   /* of the last fit (nemk_persist_out.phase_ns, summed over its launches) */
+    int persist_local, xpeer_local; /* debugging: peer-memory kernel between the ranks of the in-process test communicator */
     int pk_shard_max_world; /* row shards: largest world size served by the peer-memory kernel */
     int pk_grid_limit;     /* > 0: CTAs a fit of this handle may use (concurrent fits share the GPU) */
     /* environment knobs (tests / A-B runs), read ONCE per fit by read_env_knobs() instead of a

@@ -236,3 +236,15 @@ def test_uf_writer_rounds_like_printf(tmp_path, capi):
     got = open(tmp_path / "o.uf").read().split("\n")
     exp = ["".join(" %5.3f " % float(x) for x in r) for r in v]
     assert got[:len(exp)] == exp
+
+
+def test_str_sizes_beyond_int_are_an_error_not_a_truncation(tmp_path, capi):
+    """N and D are `int` in the engine's ABI like in the reference (nem_exe.h:23-35); ReadStrFile
+    (nem_exe.c:739-898) would store a truncated count.  Here a header beyond INT_MAX is E_FILE."""
+    base = str(tmp_path / "big")
+    for head in ["S 4294967301 5\n", "N 10 99999999999\n", "I 70000 70000 3\n", "S -4 5\n"]:
+        open(base + ".str", "w").write(head)
+        open(base + ".dat", "w").write("0 1 0 1 0\n")
+        with pytest.raises(capi.NemError) as ei:
+            capi.read_files(base, k=0)
+        assert ei.value.code == 3, head
