@@ -397,6 +397,8 @@ typedef struct {
 
 /* grid the cooperative launch may use for this K (CTAs), 0 = unsupported device */
 int  nemk_persist_max_grid(int k);
+/* value-preserving touch of every 4 KB of a peer's exchange block (fresh CUDA IPC mapping) */
+void nemk_touch_peer(nemk_stream s, void *p, size_t bytes);
 /* enqueue the kernel with `grid` CTAs (<= nemk_persist_max_grid) */
 void nemk_persist_launch(nemk_stream s, const nemk_persist_args *a, int grid);
 

@@ -1357,7 +1357,10 @@ static int ensure_xblk(nemb_handle *h, int k)
         if (p == h->rank) continue;
         unsigned probe = 0;
         if (cudaMemcpyAsync(&probe, h->xpeer[p] + h->xoff[4], sizeof probe, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-            cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; continue; }
+        /* ... and every page of it from the device side (atomicOr with 0: the peer's data stand) */
+        nemk_touch_peer(h->stream, h->xpeer[p], off);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     }
     /* second round: every rank must have mapped every block */
     mine.ok = ok;

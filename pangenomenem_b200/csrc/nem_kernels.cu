@@ -3237,6 +3237,21 @@ static int persist_max_grid_t() {
     }
     return per_sm * num_sms();
 }
+// row shards: one value-preserving system-scope read-modify-write per 4 KB of a peer's exchange
+// block, so that every page of a freshly opened CUDA IPC mapping has been reached from this device
+// BEFORE the persistent kernel depends on it (a first access inside the kernel keeps the peers
+// waiting at a cross-rank barrier)
+__global__ void k_touch_peer(unsigned *p, size_t bytes) {
+    const size_t stride = 4096 / sizeof(unsigned), n = bytes / 4096;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x)
+        atomicOr_system(p + q * stride, 0u);
+}
+extern "C" void nemk_touch_peer(nemk_stream s, void *p, size_t bytes) {
+    if (!p || bytes < 4096) return;
+    k_touch_peer<<<64, 256, 0, S(s)>>>((unsigned *)p, bytes);
+    note_launch();
+}
+
 extern "C" int nemk_persist_max_grid(int k) {
     static int cache[5] = {-1, -1, -1, -1, -1};
     int slot = k <= 2 ? 0 : k == 3 ? 1 : k == 4 ? 2 : k <= 8 ? 3 : 4;
