@@ -1358,9 +1358,12 @@ static int ensure_xblk(nemb_handle *h, int k)
         unsigned probe = 0;
         if (cudaMemcpyAsync(&probe, h->xpeer[p] + h->xoff[4], sizeof probe, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
             cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; continue; }
-        /* ... and every page of it from the device side (atomicOr with 0: the peer's data stand) */
-        nemk_touch_peer(h->stream, h->xpeer[p], off);
-        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        /* (NEM_B200_TOUCH_PEERS=1: every page of it from the device side as well -- atomicOr with 0,
+         * the peer's data stand.  Tried against the 8-rank hang: no effect, so off by default) */
+        if (getenv("NEM_B200_TOUCH_PEERS")) {
+            nemk_touch_peer(h->stream, h->xpeer[p], off);
+            if (cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        }
     }
     /* second round: every rank must have mapped every block */
     mine.ok = ok;
