@@ -3147,8 +3147,8 @@ extern "C" void nemk_mstep_finalize_tables(nemk_stream s, int k, int n, int d, i
                                            uint32_t *mask_f1, double *delta, int force_mu_changed) {
     cudaMemsetAsync(&coef->uniform_ok, 1, sizeof(int32_t), S(s));
     cudaMemsetAsync(&coef->mu_changed, force_mu_changed ? 1 : 0, sizeof(int32_t), S(s));
-    // the work is K*D elements: what costs is the chain of barriers.  Up to 8192 genomes one CTA of
-    // 1024 threads per class (block barriers only); beyond, a cluster of 8 CTAs per class (DSMEM sums)
+    // the work is K*D elements: what costs is the chain of barriers.  Always a cluster of 8 CTAs of
+    // 512 threads per class (DSMEM sums); NEM_B200_FT_CLUSTER=1|2 selects one or two CTAs of 1024
     static int force_cl = -1;
     if (force_cl < 0) { const char *e = getenv("NEM_B200_FT_CLUSTER"); force_cl = e ? atoi(e) : 0; }
     int cl = force_cl ? force_cl : 8;   // measured on C4 (D = 5000): 8-CTA clusters beat one CTA per class
